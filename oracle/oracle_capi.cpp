@@ -1,0 +1,542 @@
+// ORACLE (test infrastructure only -- never linked into the product path).
+//
+// Flat C API over the oracle classes so tests/ (ctypes), __graft_entry__.smoke()
+// and bench.py's cpu_baseline leg can drive it.  Nothing under smpl_b200/ may
+// load this library.
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "bfs3d.h"
+#include "collision_space.h"
+#include "distance_map.h"
+#include "kdl_model.h"
+#include "robot_desc.h"
+
+using namespace oracle;
+
+static thread_local std::string g_err;
+
+struct oracle_scene
+{
+    RobotDesc desc;
+    std::string group;
+    std::vector<std::string> planning_joints;
+    std::unique_ptr<EuclidDistanceMap> df;
+    std::unique_ptr<OccupancyGrid> grid;
+    std::unique_ptr<CollisionSpace> cc;
+    std::unique_ptr<KDLRobotModel> kdl;
+    std::unique_ptr<BfsHeuristic> heur;
+    double xyz_offset[3];
+    int dof;
+    oracle_scene() : dof(0) { xyz_offset[0] = xyz_offset[1] = xyz_offset[2] = 0.0; }
+};
+
+static std::vector<std::string> split_csv(const char* s)
+{
+    std::vector<std::string> out;
+    std::stringstream ss(s ? s : "");
+    std::string item;
+    while (std::getline(ss, item, ',')) {
+        if (!item.empty()) out.push_back(item);
+    }
+    return out;
+}
+
+extern "C" {
+
+const char* oracle_last_error(void) { return g_err.c_str(); }
+
+oracle_scene* oracle_scene_create(
+    const char* robot_path, const char* group, const char* planning_joints_csv,
+    const double* origin, const double* size, double res, double max_dist)
+{
+    std::unique_ptr<oracle_scene> s(new oracle_scene);
+    if (!LoadRobotDesc(robot_path, s->desc, &g_err)) {
+        return nullptr;
+    }
+    s->group = group;
+    s->planning_joints = split_csv(planning_joints_csv);
+    s->dof = (int)s->planning_joints.size();
+    s->df.reset(new EuclidDistanceMap(origin[0], origin[1], origin[2], size[0], size[1], size[2], res, max_dist));
+    s->grid.reset(new OccupancyGrid(s->df.get()));
+    s->cc.reset(new CollisionSpace);
+    if (!s->cc->init(s->grid.get(), s->desc, s->group, s->planning_joints, &g_err)) {
+        return nullptr;
+    }
+    return s.release();
+}
+
+void oracle_scene_destroy(oracle_scene* s) { delete s; }
+
+int oracle_scene_dof(oracle_scene* s) { return s->dof; }
+
+int oracle_scene_set_joint(oracle_scene* s, const char* name, double value)
+{
+    return s->cc->setJointPosition(name, value) ? 0 : -1;
+}
+
+/// call_planner.cpp:441-1527 -> CollisionSpace::setAllowedCollisionMatrix
+int oracle_scene_use_desc_acm(oracle_scene* s)
+{
+    AllowedCollisionMatrix acm;
+    for (const AcmEntryDesc& e : s->desc.acm) {
+        acm.setEntry(e.a, e.b, e.allowed);
+    }
+    s->cc->setAllowedCollisionMatrix(acm);
+    return 0;
+}
+
+int oracle_scene_acm_set(oracle_scene* s, const char* a, const char* b, int allowed)
+{
+    AllowedCollisionMatrix acm = s->cc->acm();
+    acm.setEntry(a, b, allowed != 0);
+    s->cc->setAllowedCollisionMatrix(acm);
+    return 0;
+}
+
+int oracle_scene_set_padding(oracle_scene* s, double padding)
+{
+    s->cc->setPadding(padding);
+    return 0;
+}
+
+/// occupied cells given as effective grid coordinates (x,y,z triples)
+int oracle_scene_add_cells(oracle_scene* s, const int32_t* xyz, int n)
+{
+    std::vector<std::array<int, 3>> cells(n);
+    for (int i = 0; i < n; ++i) {
+        cells[i] = {{ xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2] }};
+    }
+    s->df->addCellsToMap(cells);
+    return 0;
+}
+
+int oracle_scene_add_points(oracle_scene* s, const double* xyz, int n)
+{
+    std::vector<Vec3> pts(n);
+    for (int i = 0; i < n; ++i) {
+        pts[i] = Vec3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    }
+    s->df->addPointsToMap(pts);
+    return 0;
+}
+
+int oracle_scene_remove_points(oracle_scene* s, const double* xyz, int n)
+{
+    std::vector<Vec3> pts(n);
+    for (int i = 0; i < n; ++i) {
+        pts[i] = Vec3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    }
+    s->df->removePointsFromMap(pts);
+    return 0;
+}
+
+int oracle_scene_attach_spheres(oracle_scene* s, const char* id, const char* link, const double* centers, int n, double radius)
+{
+    std::vector<Vec3> c(n);
+    for (int i = 0; i < n; ++i) {
+        c[i] = Vec3(centers[3 * i], centers[3 * i + 1], centers[3 * i + 2]);
+    }
+    return s->cc->attachSpheres(id, c, radius, link) ? 0 : -1;
+}
+
+int oracle_scene_detach(oracle_scene* s, const char* id)
+{
+    return s->cc->detachBody(id) ? 0 : -1;
+}
+
+/// the first collision check inserts the voxels of out-of-group links into the
+/// distance field (self_collision_model.cpp:616-837); afterwards the field is
+/// static for a fixed set of non-planning joint values
+int oracle_scene_prime(oracle_scene* s, const double* q)
+{
+    std::vector<double> st(q, q + s->dof);
+    (void)s->cc->isStateValid(st);
+    return 0;
+}
+
+void oracle_scene_grid_info(oracle_scene* s, int32_t* dims, double* origin, double* res, int32_t* dmax_sq)
+{
+    dims[0] = s->df->numCellsX();
+    dims[1] = s->df->numCellsY();
+    dims[2] = s->df->numCellsZ();
+    origin[0] = s->df->originX();
+    origin[1] = s->df->originY();
+    origin[2] = s->df->originZ();
+    *res = s->df->resolution();
+    *dmax_sq = s->df->dmaxSqrd();
+}
+
+/// integer squared cell distances, unpadded, x-major / z-fastest
+int oracle_scene_df_d2(oracle_scene* s, int32_t* out)
+{
+    const int nx = s->df->numCellsX(), ny = s->df->numCellsY(), nz = s->df->numCellsZ();
+    size_t k = 0;
+    for (int x = 0; x < nx; ++x) {
+    for (int y = 0; y < ny; ++y) {
+    for (int z = 0; z < nz; ++z) {
+        out[k++] = s->df->getSquaredCellDistance(x, y, z);
+    }
+    }
+    }
+    return 0;
+}
+
+int oracle_world_to_grid(oracle_scene* s, const double* xyz, int n, int32_t* out)
+{
+    for (int i = 0; i < n; ++i) {
+        int x, y, z;
+        s->df->worldToGrid(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], x, y, z);
+        out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = z;
+    }
+    return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// validity
+///////////////////////////////////////////////////////////////////////////////
+
+int oracle_is_states_valid(oracle_scene* s, const double* q, int n, uint8_t* verdict)
+{
+    std::vector<double> st(s->dof);
+    for (int i = 0; i < n; ++i) {
+        st.assign(q + (size_t)i * s->dof, q + (size_t)(i + 1) * s->dof);
+        verdict[i] = s->cc->isStateValid(st) ? 1 : 0;
+    }
+    return 0;
+}
+
+int oracle_report_states(oracle_scene* s, const double* q, int n, uint8_t* verdict,
+                         int32_t* required_lookups, double* cell_margin, double* pair_margin)
+{
+    std::vector<double> st(s->dof);
+    for (int i = 0; i < n; ++i) {
+        st.assign(q + (size_t)i * s->dof, q + (size_t)(i + 1) * s->dof);
+        StateReport r = s->cc->reportState(st);
+        verdict[i] = r.valid ? 1 : 0;
+        if (required_lookups) required_lookups[i] = r.required_lookups;
+        if (cell_margin) cell_margin[i] = r.min_cell_boundary_margin;
+        if (pair_margin) pair_margin[i] = r.min_sphere_pair_margin;
+    }
+    return 0;
+}
+
+int oracle_is_edges_valid(oracle_scene* s, const double* q0, const double* q1, int n, uint8_t* verdict, int32_t* counts)
+{
+    std::vector<double> a(s->dof), b(s->dof);
+    for (int i = 0; i < n; ++i) {
+        a.assign(q0 + (size_t)i * s->dof, q0 + (size_t)(i + 1) * s->dof);
+        b.assign(q1 + (size_t)i * s->dof, q1 + (size_t)(i + 1) * s->dof);
+        int c = 0;
+        verdict[i] = s->cc->isStateToStateValid(a, b, &c) ? 1 : 0;
+        if (counts) counts[i] = c;
+    }
+    return 0;
+}
+
+int oracle_report_edges(oracle_scene* s, const double* q0, const double* q1, int n, uint8_t* verdict,
+                        int32_t* counts, int32_t* required_lookups)
+{
+    std::vector<double> a(s->dof), b(s->dof);
+    for (int i = 0; i < n; ++i) {
+        a.assign(q0 + (size_t)i * s->dof, q0 + (size_t)(i + 1) * s->dof);
+        b.assign(q1 + (size_t)i * s->dof, q1 + (size_t)(i + 1) * s->dof);
+        int c = 0, L = 0;
+        verdict[i] = s->cc->isStateToStateValidExhaustive(a, b, &c, &L) ? 1 : 0;
+        if (counts) counts[i] = c;
+        if (required_lookups) required_lookups[i] = L;
+    }
+    return 0;
+}
+
+/// waypoints of one edge: out holds max_wp*dof doubles; returns the count
+int oracle_edge_waypoints(oracle_scene* s, const double* q0, const double* q1, double* out, int max_wp)
+{
+    std::vector<double> a(q0, q0 + s->dof), b(q1, q1 + s->dof);
+    std::vector<std::vector<double>> wps;
+    s->cc->edgeWaypoints(a, b, wps);
+    int n = (int)wps.size();
+    for (int i = 0; i < n && i < max_wp; ++i) {
+        std::copy(wps[i].begin(), wps[i].end(), out + (size_t)i * s->dof);
+    }
+    return n;
+}
+
+int oracle_num_nodes(oracle_scene* s)
+{
+    std::vector<Vec3> c;
+    std::vector<double> st(s->dof, 0.0);
+    // sphereCenters size is state independent
+    const auto& cc = *s->cc;
+    int n = 0;
+    for (int ssidx : s->cc->state().groupSpheresStateIndices(cc.groupIndex())) {
+        n += (int)cc.model().spheres_models[ssidx].spheres.nodes.size();
+    }
+    for (int b : cc.groupAttachedBodies()) {
+        n += (int)cc.attachedBodies()[b].spheres.nodes.size();
+    }
+    return n;
+}
+
+int oracle_sphere_centers(oracle_scene* s, const double* q, int n, double* out)
+{
+    std::vector<double> st(s->dof);
+    std::vector<Vec3> c;
+    size_t k = 0;
+    for (int i = 0; i < n; ++i) {
+        st.assign(q + (size_t)i * s->dof, q + (size_t)(i + 1) * s->dof);
+        s->cc->sphereCenters(st, c);
+        for (const Vec3& v : c) {
+            out[k++] = v.x; out[k++] = v.y; out[k++] = v.z;
+        }
+    }
+    return 0;
+}
+
+/// model tables in group order, for comparison with the product's builder.
+/// per node: cx cy cz radius left right tree_index link_index (8 doubles)
+int oracle_node_table(oracle_scene* s, double* out)
+{
+    const auto& cc = *s->cc;
+    size_t k = 0;
+    int tree = 0;
+    for (int ssidx : s->cc->state().groupSpheresStateIndices(cc.groupIndex())) {
+        const auto& sm = cc.model().spheres_models[ssidx];
+        for (const SphereModel& n : sm.spheres.nodes) {
+            out[k++] = n.center.x; out[k++] = n.center.y; out[k++] = n.center.z; out[k++] = n.radius;
+            out[k++] = n.left; out[k++] = n.right; out[k++] = tree; out[k++] = sm.link_index;
+        }
+        ++tree;
+    }
+    for (int b : cc.groupAttachedBodies()) {
+        const auto& ab = cc.attachedBodies()[b];
+        for (const SphereModel& n : ab.spheres.nodes) {
+            out[k++] = n.center.x; out[k++] = n.center.y; out[k++] = n.center.z; out[k++] = n.radius;
+            out[k++] = n.left; out[k++] = n.right; out[k++] = tree; out[k++] = ab.link_index;
+        }
+        ++tree;
+    }
+    return (int)(k / 8);
+}
+
+/// per planning variable: ||MR_center|| + MR_radius of its joint (the weight
+/// getMaxSphereMotion multiplies |dq| by), joint type
+int oracle_motion_weights(oracle_scene* s, double* weights, int32_t* types)
+{
+    const auto& cc = *s->cc;
+    for (int i = 0; i < s->dof; ++i) {
+        int vidx = cc.planningVariables()[i];
+        int jidx = cc.model().jvar_joint_indices[vidx];
+        weights[i] = norm(cc.motionModel().mr_centers[jidx]) + cc.motionModel().mr_radii[jidx];
+        types[i] = (int)cc.model().joint_types[jidx];
+    }
+    return 0;
+}
+
+/// number of checked robot tree pairs (after priming), pairs as group-tree indices
+int oracle_checked_pairs(oracle_scene* s, int32_t* out, int max_pairs)
+{
+    const auto& cc = *s->cc;
+    const auto& gss = s->cc->state().groupSpheresStateIndices(cc.groupIndex());
+    auto tree_of = [&](int ssidx) {
+        return (int)(std::find(gss.begin(), gss.end(), ssidx) - gss.begin());
+    };
+    int n = 0;
+    for (const auto& p : cc.checkedSpheresStates()) {
+        if (n < max_pairs) {
+            out[2 * n] = tree_of(p.first);
+            out[2 * n + 1] = tree_of(p.second);
+        }
+        ++n;
+    }
+    for (const auto& p : cc.checkedAttachedAttached()) {
+        if (n < max_pairs) {
+            out[2 * n] = (int)gss.size() + p.first;
+            out[2 * n + 1] = (int)gss.size() + p.second;
+        }
+        ++n;
+    }
+    for (const auto& p : cc.checkedAttachedRobot()) {
+        if (n < max_pairs) {
+            out[2 * n] = (int)gss.size() + p.first;
+            out[2 * n + 1] = tree_of(p.second);
+        }
+        ++n;
+    }
+    return n;
+}
+
+void oracle_scene_stats(oracle_scene* s, int64_t* df_lookups, int64_t* pair_tests, int64_t* link_updates)
+{
+    *df_lookups = s->cc->stats.df_lookups;
+    *pair_tests = s->cc->stats.sphere_pair_tests;
+    *link_updates = s->cc->state().link_transform_updates;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// KDL-like planning model + BFS heuristic
+///////////////////////////////////////////////////////////////////////////////
+
+int oracle_scene_init_kdl(oracle_scene* s, const char* chain_root, const char* chain_tip,
+                          const char* planning_link, const double* T_kin_to_planning_3x4,
+                          const double* xyz_offset)
+{
+    s->kdl.reset(new KDLRobotModel);
+    if (!s->kdl->init(s->desc, s->planning_joints, chain_root, chain_tip, &g_err)) {
+        s->kdl.reset();
+        return -1;
+    }
+    if (!s->kdl->setPlanningLink(planning_link)) {
+        g_err = "planning link not in chain";
+        return -1;
+    }
+    KdlFrame f;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) f.M[3 * r + c] = T_kin_to_planning_3x4[4 * r + c];
+        f.p[r] = T_kin_to_planning_3x4[4 * r + 3];
+    }
+    s->kdl->setKinematicsToPlanningTransform(f);
+    for (int i = 0; i < 3; ++i) s->xyz_offset[i] = xyz_offset ? xyz_offset[i] : 0.0;
+    return 0;
+}
+
+int oracle_check_joint_limits(oracle_scene* s, const double* q, int n, uint8_t* out)
+{
+    std::vector<double> st(s->dof);
+    for (int i = 0; i < n; ++i) {
+        st.assign(q + (size_t)i * s->dof, q + (size_t)(i + 1) * s->dof);
+        out[i] = s->kdl->checkJointLimits(st) ? 1 : 0;
+    }
+    return 0;
+}
+
+void oracle_joint_limits(oracle_scene* s, double* mins, double* maxs, uint8_t* continuous)
+{
+    for (int i = 0; i < s->dof; ++i) {
+        mins[i] = s->kdl->min_limits[i];
+        maxs[i] = s->kdl->max_limits[i];
+        continuous[i] = s->kdl->continuous[i] ? 1 : 0;
+    }
+}
+
+/// computePlanningFrameFK: planning link FK then target offset; pose6 per state
+int oracle_planning_frame_fk(oracle_scene* s, const double* q, int n, double* pose6)
+{
+    std::vector<double> st(s->dof), pose;
+    for (int i = 0; i < n; ++i) {
+        st.assign(q + (size_t)i * s->dof, q + (size_t)(i + 1) * s->dof);
+        s->kdl->computePlanningLinkFK(st, pose);
+        pose = GetTargetOffsetPose(pose, s->xyz_offset);
+        std::copy(pose.begin(), pose.end(), pose6 + (size_t)i * 6);
+    }
+    return 0;
+}
+
+int oracle_heur_init(oracle_scene* s, double inflation_radius, int cost_per_cell)
+{
+    s->heur.reset(new BfsHeuristic(s->df.get(), inflation_radius, cost_per_cell));
+    return s->heur->wall_count;
+}
+
+int oracle_heur_set_goal(oracle_scene* s, double x, double y, double z)
+{
+    return s->heur->updateGoal(x, y, z) ? 0 : 1;
+}
+
+int oracle_heur_grid(oracle_scene* s, int32_t* out)
+{
+    const auto& g = s->heur->bfs()->grid();
+    std::copy(g.begin(), g.end(), out);
+    return (int)g.size();
+}
+
+int oracle_goal_heuristics(oracle_scene* s, const double* q, int n, int32_t* h)
+{
+    std::vector<double> st(s->dof), pose;
+    for (int i = 0; i < n; ++i) {
+        st.assign(q + (size_t)i * s->dof, q + (size_t)(i + 1) * s->dof);
+        s->kdl->computePlanningLinkFK(st, pose);
+        pose = GetTargetOffsetPose(pose, s->xyz_offset);
+        h[i] = s->heur->getGoalHeuristicAt(pose[0], pose[1], pose[2]);
+    }
+    return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// stand-alone BFS_3D
+///////////////////////////////////////////////////////////////////////////////
+
+BFS_3D* oracle_bfs_create(int nx, int ny, int nz) { return new BFS_3D(nx, ny, nz); }
+void oracle_bfs_destroy(BFS_3D* b) { delete b; }
+
+/// walls: one byte per cell, x-fastest unpadded (index = (z*ny + y)*nx + x)
+int oracle_bfs_set_walls(BFS_3D* b, const uint8_t* walls)
+{
+    const int nx = b->dimX() - 2, ny = b->dimY() - 2, nz = b->dimZ() - 2;
+    for (int z = 0; z < nz; ++z) {
+    for (int y = 0; y < ny; ++y) {
+    for (int x = 0; x < nx; ++x) {
+        if (walls[((size_t)z * ny + y) * nx + x]) {
+            b->setWall(x, y, z);
+        }
+    }
+    }
+    }
+    return 0;
+}
+
+int oracle_bfs_run(BFS_3D* b, int x, int y, int z) { return b->run(x, y, z); }
+int oracle_bfs_run_multi(BFS_3D* b, const int32_t* xyz, int count) { return b->run(xyz, count); }
+
+int oracle_bfs_grid(BFS_3D* b, int32_t* out)
+{
+    std::copy(b->grid().begin(), b->grid().end(), out);
+    return (int)b->grid().size();
+}
+
+int oracle_bfs_get_distance(BFS_3D* b, int x, int y, int z)
+{
+    if (!b->inBounds(x, y, z)) {
+        return -2; // undefined in the reference
+    }
+    return b->getDistance(x, y, z);
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// timing helpers for bench.py's cpu_baseline (time only the checks, as
+// benchmark_cc.cpp:243-249)
+///////////////////////////////////////////////////////////////////////////////
+
+double oracle_time_states_valid(oracle_scene* s, const double* q, int n, uint8_t* verdict)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    oracle_is_states_valid(s, q, n, verdict);
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+double oracle_time_edges_valid(oracle_scene* s, const double* q0, const double* q1, int n, uint8_t* verdict, int32_t* counts)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    oracle_is_edges_valid(s, q0, q1, n, verdict, counts);
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+double oracle_time_bfs_run(BFS_3D* b, int x, int y, int z)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    b->run(x, y, z);
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+} // extern "C"

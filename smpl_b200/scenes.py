@@ -1,0 +1,205 @@
+"""Synthetic scenes and query sets of the shapes BASELINE.json names.
+
+Pure input generators (numpy): occupied-cell lists, random joint states,
+motion-primitive edges, BFS wall grids.  Both the CUDA path and the CPU oracle
+consume exactly these arrays, so no RNG has to agree across languages.
+"""
+import math
+import os
+
+import numpy as np
+
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+PR2_RIGHT_ARM_JOINTS = [
+    "r_shoulder_pan_joint", "r_shoulder_lift_joint", "r_upper_arm_roll_joint", "r_elbow_flex_joint",
+    "r_forearm_roll_joint", "r_wrist_flex_joint", "r_wrist_roll_joint",
+]
+PR2_LEFT_ARM_JOINTS = ["l" + j[1:] for j in PR2_RIGHT_ARM_JOINTS]
+UBR1_ARM_JOINTS = [
+    "shoulder_pan_joint", "shoulder_lift_joint", "upperarm_roll_joint", "elbow_flex_joint",
+    "forearm_roll_joint", "wrist_flex_joint", "wrist_roll_joint",
+]
+
+
+def grid_dims(size, res):
+    """Cell counts as DistanceMap's constructor computes them (distance_map.hpp:136-138)."""
+    inv = 1.0 / res
+    return tuple(int(s * inv + 0.5) for s in size)
+
+
+def box_cells(origin, res, dims, center, size):
+    """Effective grid cells whose centres (origin + i*res) lie inside an axis-aligned box."""
+    lo = [int(math.ceil((center[a] - 0.5 * size[a] - origin[a]) / res - 1e-9)) for a in range(3)]
+    hi = [int(math.floor((center[a] + 0.5 * size[a] - origin[a]) / res + 1e-9)) for a in range(3)]
+    lo = [max(0, v) for v in lo]
+    hi = [min(dims[a] - 1, hi[a]) for a in range(3)]
+    if any(hi[a] < lo[a] for a in range(3)):
+        return np.zeros((0, 3), np.int32)
+    xs, ys, zs = np.meshgrid(np.arange(lo[0], hi[0] + 1), np.arange(lo[1], hi[1] + 1),
+                             np.arange(lo[2], hi[2] + 1), indexing="ij")
+    return np.stack([xs.ravel(), ys.ravel(), zs.ravel()], axis=1).astype(np.int32)
+
+
+class Scene:
+    """Grid parameters + occupied cells + robot setup of one benchmark configuration."""
+
+    def __init__(self, robot, group, planning_joints, origin, size, res, max_dist):
+        self.robot_path = os.path.join(DATA, robot + ".robot")
+        self.group = group
+        self.planning_joints = list(planning_joints)
+        self.origin = tuple(float(v) for v in origin)
+        self.size = tuple(float(v) for v in size)
+        self.res = float(res)
+        self.max_dist = float(max_dist)
+        self.dims = grid_dims(size, res)
+        self.cells = np.zeros((0, 3), np.int32)
+        self.fixed_joints = {}
+        self.use_desc_acm = False
+        self.padding = 0.0
+        # planning model (KDL chain) parameters
+        self.chain_root = None
+        self.chain_tip = None
+        self.planning_link = None
+        self.T_kin_to_planning = np.eye(4)[:3].copy()
+        self.xyz_offset = (0.0, 0.0, 0.0)
+        self.inflation_radius = 0.02   # planning_link_sphere_radius, call_planner.cpp:1715
+        self.cost_per_cell = 250       # planning_params.h:68 default... set by callers
+        self.attached = None           # (id, link, centers[n,3], radius)
+
+    def add_box(self, center, size):
+        c = box_cells(self.origin, self.res, self.dims, center, size)
+        self.cells = np.concatenate([self.cells, c], axis=0)
+
+    @property
+    def dof(self):
+        return len(self.planning_joints)
+
+
+def _pr2_common(scene):
+    scene.fixed_joints = {"torso_lift_joint": 0.16825}           # pr2_goal.yaml:3
+    scene.use_desc_acm = True                                     # call_planner.cpp:1630-1632
+    scene.chain_root = "torso_lift_link"                          # goal_pr2.launch kinematics_frame
+    scene.chain_tip = "r_gripper_palm_link"
+    scene.planning_link = "r_gripper_palm_link"
+    T = np.eye(4)[:3].copy()
+    T[:, 3] = (-0.05, 0.0, 0.959)                                 # pr2_goal.yaml:13-19
+    scene.T_kin_to_planning = T
+    scene.cost_per_cell = 100
+
+
+def pr2_tabletop_scene():
+    """Config 1: smpl_test PR2 right arm in the tabletop env (call_planner.cpp:1587-1594, tabletop.env)."""
+    s = Scene("pr2", "right_arm", PR2_RIGHT_ARM_JOINTS, (-0.75, -1.5, 0.0), (3.0, 3.0, 3.0), 0.02, 1.8)
+    _pr2_common(s)
+    # tabletop.env declares 1 object: id x y z dx dy dz
+    s.add_box((0.55, 0.0, 0.6), (0.4, 1.5, 0.02))
+    return s
+
+
+def pr2_clutter_scene(seed=7, n_boxes=40):
+    """Config 2: 2x2x2 m scene at 2 cm, 40 random boxes."""
+    s = Scene("pr2", "right_arm", PR2_RIGHT_ARM_JOINTS, (-0.5, -1.0, 0.0), (2.0, 2.0, 2.0), 0.02, 0.4)
+    _pr2_common(s)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    shoulder = np.array([-0.05, -0.188, 0.959])
+    placed = 0
+    while placed < n_boxes:
+        size = rng.uniform(0.04, 0.4, 3)
+        center = np.array(s.origin) + rng.uniform(0.0, 1.0, 3) * np.array(s.size)
+        # reject boxes overlapping the shoulder / torso column
+        d = np.maximum(np.abs(center - shoulder) - 0.5 * size, 0.0)
+        if np.linalg.norm(d) < 0.30:
+            continue
+        if abs(center[0] + 0.1) < 0.35 + 0.5 * size[0] and abs(center[1]) < 0.45 + 0.5 * size[1]:
+            continue  # robot body column
+        s.add_box(center, size)
+        placed += 1
+    return s
+
+
+def random_states(n, lo, hi, continuous, seed):
+    """Uniform joint states in [lo, hi] (continuous joints: [-pi, pi]); benchmark_cc.cpp:280-302 recipe."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lo = np.where(np.asarray(continuous, bool), -math.pi, np.asarray(lo, np.float64))
+    hi = np.where(np.asarray(continuous, bool), math.pi, np.asarray(hi, np.float64))
+    u = rng.random((n, len(lo)))
+    return np.ascontiguousarray(lo + u * (hi - lo))
+
+
+def pr2_mprim_deltas():
+    """8 long (7 deg) + 14 short (4 deg) primitives with converses (pr2.mprim, SURVEY 8a defect 2)."""
+    d = []
+    for j in range(4):
+        for sgn in (1.0, -1.0):
+            v = np.zeros(7)
+            v[j] = sgn * math.radians(7.0)
+            d.append(v)
+    for j in range(7):
+        for sgn in (1.0, -1.0):
+            v = np.zeros(7)
+            v[j] = sgn * math.radians(4.0)
+            d.append(v)
+    return np.array(d)
+
+
+def mprim_edges(q, deltas=None):
+    """Edge i goes from q[i] to q[i] + delta[i mod K]."""
+    if deltas is None:
+        deltas = pr2_mprim_deltas()
+    k = np.arange(len(q)) % len(deltas)
+    return np.ascontiguousarray(q), np.ascontiguousarray(q + deltas[k])
+
+
+def bfs_clutter_walls(n=400, seed=11, n_boxes=3000):
+    """Config 3: n^3 occupancy (uint8 [z,y,x]): random boxes + shelf planes with door gaps."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    w = np.zeros((n, n, n), np.uint8)
+    scale = n / 400.0
+    nb = max(1, int(n_boxes * scale ** 3)) if n < 400 else n_boxes
+    for _ in range(nb):
+        e = rng.integers(2, max(3, int(40 * scale)) + 1, 3)
+        c = rng.integers(0, n, 3)
+        lo = np.maximum(c - e // 2, 0)
+        hi = np.minimum(lo + e, n)
+        w[lo[2]:hi[2], lo[1]:hi[1], lo[0]:hi[0]] = 1
+    # six full planes ("shelves") with door gaps
+    for k in range(6):
+        axis = k % 3
+        pos = int(n * (0.15 + 0.14 * k))
+        sl = [slice(None)] * 3
+        sl[2 - axis] = slice(pos, pos + 2)
+        w[tuple(sl)] = 1
+        # door gap
+        g = max(2, int(12 * scale))
+        a = rng.integers(0, n - g, 2)
+        gap = [slice(None)] * 3
+        gap[2 - axis] = slice(pos, pos + 2)
+        others = [i for i in range(3) if i != 2 - axis]
+        gap[others[0]] = slice(int(a[0]), int(a[0]) + g)
+        gap[others[1]] = slice(int(a[1]), int(a[1]) + g)
+        w[tuple(gap)] = 0
+    return w
+
+
+def first_free_cell(walls, start):
+    """First free cell at or after `start` (x,y,z) scanning x fastest."""
+    n_z, n_y, n_x = walls.shape
+    flat = walls.reshape(-1)
+    i0 = (start[2] * n_y + start[1]) * n_x + start[0]
+    free = np.flatnonzero(flat[i0:] == 0)
+    i = i0 + int(free[0])
+    return (i % n_x, (i // n_x) % n_y, i // (n_x * n_y))
+
+
+def attached_box_spheres(size, offset=(0.0, 0.0, 0.0), radius=0.025):
+    """Sphere centres for an attached box: one r=0.025 sphere per voxel at pitch 0.025/sqrt(2)
+    (attached_bodies_collision_model.cpp:281-309)."""
+    pitch = radius / math.sqrt(2.0)
+    axes = []
+    for a in range(3):
+        n = max(1, int(math.ceil(size[a] / pitch)))
+        start = offset[a] - 0.5 * (n - 1) * pitch
+        axes.append(start + pitch * np.arange(n))
+    xs, ys, zs = np.meshgrid(*axes, indexing="ij")
+    return np.stack([xs.ravel(), ys.ravel(), zs.ravel()], axis=1)

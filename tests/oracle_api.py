@@ -1,0 +1,358 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so, oracle/_ref/libref_bfs3d.so).
+
+TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs import this module; nothing under
+smpl_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_LIB = None
+_REF = None
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_uint8_p = C.POINTER(C.c_uint8)
+
+
+def build_oracle():
+    """Compile oracle/liboracle.so (and oracle/_ref when /root/reference exists)."""
+    subprocess.run(["make", "-C", ORACLE_DIR, "-j8"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", ORACLE_DIR, "ref"], check=True, stdout=subprocess.DEVNULL)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int32_p)
+
+
+def _bp(a):
+    return a.ctypes.data_as(c_uint8_p)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        L = C.CDLL(path)
+        L.oracle_last_error.restype = C.c_char_p
+        L.oracle_scene_create.restype = C.c_void_p
+        L.oracle_scene_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, c_double_p, c_double_p,
+                                          C.c_double, C.c_double]
+        L.oracle_bfs_create.restype = C.c_void_p
+        L.oracle_bfs_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        for name in ("oracle_time_states_valid", "oracle_time_edges_valid", "oracle_time_bfs_run"):
+            getattr(L, name).restype = C.c_double
+        L.oracle_time_bfs_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def ref_lib():
+    """The reference's own BFS_3D (compiled from /root/reference), or None."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_bfs3d.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.ref_bfs_create.restype = C.c_void_p
+        R.ref_bfs_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        R.ref_bfs_time_run.restype = C.c_double
+        R.ref_bfs_time_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _REF = R
+    return _REF
+
+
+class OracleScene:
+    def __init__(self, robot_path, group, planning_joints, origin, size, res, max_dist):
+        L = lib()
+        self.L = L
+        o = np.asarray(origin, dtype=np.float64)
+        s = np.asarray(size, dtype=np.float64)
+        self.h = L.oracle_scene_create(robot_path.encode(), group.encode(), ",".join(planning_joints).encode(),
+                                       _dp(o), _dp(s), float(res), float(max_dist))
+        if not self.h:
+            raise RuntimeError("oracle_scene_create: " + L.oracle_last_error().decode())
+        self.h = C.c_void_p(self.h)
+        self.dof = len(planning_joints)
+
+    def close(self):
+        if self.h:
+            self.L.oracle_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scene ----
+    def set_joint(self, name, value):
+        return self.L.oracle_scene_set_joint(self.h, name.encode(), C.c_double(value))
+
+    def use_desc_acm(self):
+        self.L.oracle_scene_use_desc_acm(self.h)
+
+    def acm_set(self, a, b, allowed):
+        self.L.oracle_scene_acm_set(self.h, a.encode(), b.encode(), int(allowed))
+
+    def set_padding(self, p):
+        self.L.oracle_scene_set_padding(self.h, C.c_double(p))
+
+    def add_cells(self, cells):
+        cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 3)
+        self.L.oracle_scene_add_cells(self.h, _ip(cells), len(cells))
+
+    def add_points(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        self.L.oracle_scene_add_points(self.h, _dp(pts), len(pts))
+
+    def remove_points(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        self.L.oracle_scene_remove_points(self.h, _dp(pts), len(pts))
+
+    def attach_spheres(self, body_id, link, centers, radius):
+        c = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3)
+        r = self.L.oracle_scene_attach_spheres(self.h, body_id.encode(), link.encode(), _dp(c), len(c),
+                                               C.c_double(radius))
+        if r != 0:
+            raise RuntimeError("attach failed")
+
+    def prime(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        self.L.oracle_scene_prime(self.h, _dp(q))
+
+    def grid_info(self):
+        dims = np.zeros(3, np.int32)
+        origin = np.zeros(3, np.float64)
+        res = C.c_double()
+        dmax = C.c_int32()
+        self.L.oracle_scene_grid_info(self.h, _ip(dims), _dp(origin), C.byref(res), C.byref(dmax))
+        return dims, origin, res.value, dmax.value
+
+    def df_d2(self):
+        dims, _, _, _ = self.grid_info()
+        out = np.zeros(int(dims[0]) * int(dims[1]) * int(dims[2]), np.int32)
+        self.L.oracle_scene_df_d2(self.h, _ip(out))
+        return out.reshape(tuple(int(d) for d in dims))
+
+    def world_to_grid(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros((len(xyz), 3), np.int32)
+        self.L.oracle_world_to_grid(self.h, _dp(xyz), len(xyz), _ip(out))
+        return out
+
+    # ---- validity ----
+    def _q(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.dof)
+        return q
+
+    def is_states_valid(self, q):
+        q = self._q(q)
+        v = np.zeros(len(q), np.uint8)
+        self.L.oracle_is_states_valid(self.h, _dp(q), len(q), _bp(v))
+        return v
+
+    def time_states_valid(self, q):
+        q = self._q(q)
+        v = np.zeros(len(q), np.uint8)
+        t = self.L.oracle_time_states_valid(self.h, _dp(q), len(q), _bp(v))
+        return t, v
+
+    def report_states(self, q):
+        q = self._q(q)
+        n = len(q)
+        v = np.zeros(n, np.uint8)
+        L = np.zeros(n, np.int32)
+        cm = np.zeros(n, np.float64)
+        pm = np.zeros(n, np.float64)
+        self.L.oracle_report_states(self.h, _dp(q), n, _bp(v), _ip(L), _dp(cm), _dp(pm))
+        return v, L, cm, pm
+
+    def is_edges_valid(self, q0, q1):
+        q0 = self._q(q0)
+        q1 = self._q(q1)
+        v = np.zeros(len(q0), np.uint8)
+        c = np.zeros(len(q0), np.int32)
+        self.L.oracle_is_edges_valid(self.h, _dp(q0), _dp(q1), len(q0), _bp(v), _ip(c))
+        return v, c
+
+    def time_edges_valid(self, q0, q1):
+        q0 = self._q(q0)
+        q1 = self._q(q1)
+        v = np.zeros(len(q0), np.uint8)
+        c = np.zeros(len(q0), np.int32)
+        t = self.L.oracle_time_edges_valid(self.h, _dp(q0), _dp(q1), len(q0), _bp(v), _ip(c))
+        return t, v, c
+
+    def report_edges(self, q0, q1):
+        q0 = self._q(q0)
+        q1 = self._q(q1)
+        v = np.zeros(len(q0), np.uint8)
+        c = np.zeros(len(q0), np.int32)
+        L = np.zeros(len(q0), np.int32)
+        self.L.oracle_report_edges(self.h, _dp(q0), _dp(q1), len(q0), _bp(v), _ip(c), _ip(L))
+        return v, c, L
+
+    def edge_waypoints(self, q0, q1, max_wp=256):
+        q0 = np.ascontiguousarray(q0, dtype=np.float64)
+        q1 = np.ascontiguousarray(q1, dtype=np.float64)
+        out = np.zeros((max_wp, self.dof), np.float64)
+        n = self.L.oracle_edge_waypoints(self.h, _dp(q0), _dp(q1), _dp(out), max_wp)
+        return out[:n].copy()
+
+    def num_nodes(self):
+        return self.L.oracle_num_nodes(self.h)
+
+    def sphere_centers(self, q):
+        q = self._q(q)
+        nn = self.num_nodes()
+        out = np.zeros((len(q), nn, 3), np.float64)
+        self.L.oracle_sphere_centers(self.h, _dp(q), len(q), _dp(out))
+        return out
+
+    def node_table(self):
+        nn = self.num_nodes()
+        out = np.zeros((nn, 8), np.float64)
+        n = self.L.oracle_node_table(self.h, _dp(out))
+        assert n == nn
+        return out
+
+    def motion_weights(self):
+        w = np.zeros(self.dof, np.float64)
+        t = np.zeros(self.dof, np.int32)
+        self.L.oracle_motion_weights(self.h, _dp(w), _ip(t))
+        return w, t
+
+    def checked_pairs(self):
+        out = np.zeros((4096, 2), np.int32)
+        n = self.L.oracle_checked_pairs(self.h, _ip(out), 4096)
+        return out[:n].copy()
+
+    def stats(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.L.oracle_scene_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return dict(df_lookups=a.value, pair_tests=b.value, link_updates=c.value)
+
+    # ---- planning model / heuristic ----
+    def init_kdl(self, chain_root, chain_tip, planning_link, T_kin_to_planning=None, xyz_offset=None):
+        T = np.eye(4)[:3] if T_kin_to_planning is None else np.asarray(T_kin_to_planning, np.float64).reshape(3, 4)
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        off = np.zeros(3) if xyz_offset is None else np.asarray(xyz_offset, np.float64)
+        off = np.ascontiguousarray(off, dtype=np.float64)
+        r = self.L.oracle_scene_init_kdl(self.h, chain_root.encode(), chain_tip.encode(), planning_link.encode(),
+                                         _dp(T), _dp(off))
+        if r != 0:
+            raise RuntimeError("init_kdl: " + self.L.oracle_last_error().decode())
+
+    def check_joint_limits(self, q):
+        q = self._q(q)
+        out = np.zeros(len(q), np.uint8)
+        self.L.oracle_check_joint_limits(self.h, _dp(q), len(q), _bp(out))
+        return out
+
+    def joint_limits(self):
+        lo = np.zeros(self.dof)
+        hi = np.zeros(self.dof)
+        c = np.zeros(self.dof, np.uint8)
+        self.L.oracle_joint_limits(self.h, _dp(lo), _dp(hi), _bp(c))
+        return lo, hi, c
+
+    def planning_frame_fk(self, q):
+        q = self._q(q)
+        out = np.zeros((len(q), 6), np.float64)
+        self.L.oracle_planning_frame_fk(self.h, _dp(q), len(q), _dp(out))
+        return out
+
+    def heur_init(self, inflation_radius, cost_per_cell):
+        return self.L.oracle_heur_init(self.h, C.c_double(inflation_radius), int(cost_per_cell))
+
+    def heur_set_goal(self, x, y, z):
+        return self.L.oracle_heur_set_goal(self.h, C.c_double(x), C.c_double(y), C.c_double(z))
+
+    def heur_grid(self):
+        dims, _, _, _ = self.grid_info()
+        n = int(dims[0] + 2) * int(dims[1] + 2) * int(dims[2] + 2)
+        out = np.zeros(n, np.int32)
+        self.L.oracle_heur_grid(self.h, _ip(out))
+        return out.reshape(int(dims[2] + 2), int(dims[1] + 2), int(dims[0] + 2))
+
+    def goal_heuristics(self, q):
+        q = self._q(q)
+        h = np.zeros(len(q), np.int32)
+        self.L.oracle_goal_heuristics(self.h, _dp(q), len(q), _ip(h))
+        return h
+
+
+class _BfsBase:
+    prefix = None
+
+    def __init__(self, L, nx, ny, nz):
+        self.L = L
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.h = C.c_void_p(getattr(L, self.prefix + "_create")(self.nx, self.ny, self.nz))
+
+    def close(self):
+        if self.h:
+            getattr(self.L, self.prefix + "_destroy")(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_walls(self, walls_zyx):
+        """walls_zyx: uint8 array [nz, ny, nx] (x fastest), nonzero = wall."""
+        w = np.ascontiguousarray(walls_zyx, dtype=np.uint8)
+        assert w.shape == (self.nz, self.ny, self.nx)
+        getattr(self.L, self.prefix + "_set_walls")(self.h, _bp(w))
+
+    def run(self, x, y, z):
+        return getattr(self.L, self.prefix + "_run")(self.h, int(x), int(y), int(z))
+
+    def run_multi(self, seeds):
+        s = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 3)
+        return getattr(self.L, self.prefix + "_run_multi")(self.h, _ip(s), len(s))
+
+    def grid(self):
+        out = np.zeros((self.nz + 2) * (self.ny + 2) * (self.nx + 2), np.int32)
+        getattr(self.L, self.prefix + "_grid")(self.h, _ip(out))
+        return out.reshape(self.nz + 2, self.ny + 2, self.nx + 2)
+
+
+class OracleBfs(_BfsBase):
+    prefix = "oracle_bfs"
+
+    def __init__(self, nx, ny, nz):
+        super().__init__(lib(), nx, ny, nz)
+
+    def time_run(self, x, y, z):
+        return self.L.oracle_time_bfs_run(self.h, int(x), int(y), int(z))
+
+
+class RefBfs(_BfsBase):
+    """The reference's own BFS_3D class (oracle/_ref)."""
+    prefix = "ref_bfs"
+
+    def __init__(self, nx, ny, nz):
+        R = ref_lib()
+        if R is None:
+            raise RuntimeError("oracle/_ref/libref_bfs3d.so not built")
+        super().__init__(R, nx, ny, nz)
+
+    def time_run(self, x, y, z):
+        return self.L.ref_bfs_time_run(self.h, int(x), int(y), int(z))
