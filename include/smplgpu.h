@@ -1,0 +1,231 @@
+/*
+ * smplgpu.h -- C ABI of the B200-native validity + heuristic hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * Every entry point names the reference interface (file:line under the
+ * dyouakim/smpl tree) it replaces.  The reference itself has no FFI -- its
+ * boundary is three pure-virtual C++ plugin classes (smpl/collision_checker.h:48,
+ * smpl/heuristic/robot_heuristic.h:53, smpl/robot_model.h:50-110); the adapter
+ * classes in smpl_b200/host/ implement those virtuals by calling this ABI and
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - return 0 on success, a negative SMPLGPU_ERR_* code on failure;
+ *     smplgpu_last_error() gives the message.  There is NO CPU fallback: with
+ *     no CUDA device smplgpu_create() fails.
+ *   - a context is single-threaded and non-reentrant, like the reference's
+ *     CollisionSpace (collision_space.cpp:741-774); use one context per
+ *     planner thread / per GPU.
+ *   - "host" pointers are ordinary process memory; entry points ending in
+ *     _dev take device pointers valid on the context's device and enqueue on
+ *     the context's stream without synchronising.
+ *   - joint states are row-major double[n][dof] in planning-variable order
+ *     (RobotState = std::vector<double>, smpl/types.h:67).
+ */
+#ifndef SMPLGPU_H
+#define SMPLGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMPLGPU_OK               0
+#define SMPLGPU_ERR_INVALID     -1  /* bad argument */
+#define SMPLGPU_ERR_CUDA        -2  /* CUDA runtime error */
+#define SMPLGPU_ERR_STATE       -3  /* robot / distance field / BFS grid not set */
+#define SMPLGPU_ERR_NO_DEVICE   -4  /* no usable CUDA device */
+#define SMPLGPU_ERR_LIMIT       -5  /* table exceeds a compiled-in limit */
+
+/* BFS_3D cell values (smpl/bfs3d/bfs3d.h:50-51) */
+#define SMPLGPU_BFS_WALL          0x7FFFFFFF
+#define SMPLGPU_BFS_UNDISCOVERED  (-1)
+/* returned by smplgpu_bfs_distances for out-of-bounds cells (undefined
+ * behaviour in the reference, bfs3d.cpp:373-378 indexes node -1) */
+#define SMPLGPU_BFS_OUT_OF_BOUNDS (-2)
+/* RobotHeuristic::Infinity (smpl/heuristic/robot_heuristic.h:62) */
+#define SMPLGPU_HEURISTIC_INFINITY 32767
+
+/* joint transform selector: which function the reference would pick
+ * (robot_collision_model.cpp:331-359, 382-407; transform_functions.h:95-258) */
+enum {
+    SMPLGPU_JOINT_FIXED = 0,
+    SMPLGPU_JOINT_REVOLUTE_X = 1,
+    SMPLGPU_JOINT_REVOLUTE_Y = 2,
+    SMPLGPU_JOINT_REVOLUTE_Z = 3,
+    SMPLGPU_JOINT_REVOLUTE_AXIS = 4,   /* origin * AngleAxis(q, axis) */
+    SMPLGPU_JOINT_PRISMATIC = 5        /* origin * Translate(0, 0, q) */
+};
+
+/* planning variable kind, for interpolation / motion bound
+ * (robot_motion_collision_model.h:224-249, .cpp:371-407) */
+enum {
+    SMPLGPU_VAR_REVOLUTE = 0,
+    SMPLGPU_VAR_CONTINUOUS = 1,
+    SMPLGPU_VAR_PRISMATIC = 2
+};
+
+/* KDL-style chain segment joint kind (orocos_kdl Joint::None/RotAxis/TransAxis) */
+enum {
+    SMPLGPU_SEG_NONE = 0,
+    SMPLGPU_SEG_ROT = 1,
+    SMPLGPU_SEG_TRANS = 2
+};
+
+/*
+ * Flat robot tables.  They restate, as arrays, what the reference keeps in
+ * RobotCollisionModel / RobotCollisionState / RobotMotionCollisionModel /
+ * SelfCollisionModelImpl for ONE collision group and ONE set of planning
+ * variables.  All 3x4 transforms are row-major double[12] (rotation | translation).
+ *
+ * Links: only the links whose pose depends on a planning variable AND that
+ * carry (or lead to) a sphere tree of the group, in topological order (parents
+ * first).  A link whose parent is not in the table has link_parent = -1 and
+ * link_base = the (constant) world pose of its parent link.
+ *   T_link = T_parent * joint_fn(origin, axis, value)       robot_collision_state.h:385-431
+ * value = q[link_var] when link_var >= 0, else link_const.
+ *
+ * Nodes: every node of every sphere tree of the group (robot links first, then
+ * attached bodies), CollisionSphereModelTree order (base_collision_models.cpp:337-444).
+ *   pos = T_link * center                                   robot_collision_state.h:560-581
+ * A group link that no planning variable moves is listed as a link with
+ * link_parent = -1, SMPLGPU_JOINT_FIXED, identity origin and link_base = its pose
+ * (base * identity is exact in IEEE arithmetic).
+ */
+typedef struct smplgpu_robot_desc {
+    int32_t dof;
+
+    int32_t n_links;
+    const int32_t* link_parent;      /* [n_links] */
+    const int32_t* link_joint;       /* [n_links] SMPLGPU_JOINT_* */
+    const double*  link_origin;      /* [n_links][12] */
+    const double*  link_axis;        /* [n_links][3] */
+    const int32_t* link_var;         /* [n_links] planning variable index or -1 */
+    const double*  link_const;       /* [n_links] */
+    const double*  link_base;        /* [n_links][12], used when link_parent < 0 */
+
+    int32_t n_nodes;
+    const int32_t* node_link;        /* [n_nodes] index into the link table */
+    const double*  node_center;      /* [n_nodes][3] */
+    const double*  node_radius;      /* [n_nodes] */
+    const int32_t* node_left;        /* [n_nodes] node index or -1 */
+    const int32_t* node_right;       /* [n_nodes] */
+
+    int32_t n_trees;
+    const int32_t* tree_root;        /* [n_trees] node index; checked against the distance field */
+
+    /* sphere-tree pairs checked for self collision
+     * (SelfCollisionModelImpl::m_checked_*_spheres_states, self_collision_model.cpp:1233-1345) */
+    int32_t n_pairs;
+    const int32_t* pair_a;           /* [n_pairs] tree index */
+    const int32_t* pair_b;           /* [n_pairs] */
+
+    /* leaf pairs whose *sphere names* have an ALWAYS entry in the ACM
+     * (self_collision_model.cpp:1133-1149); normally empty */
+    int32_t n_allowed_leaf_pairs;
+    const int32_t* allowed_leaf_a;   /* node index */
+    const int32_t* allowed_leaf_b;
+
+    /* per planning variable */
+    const int32_t* var_type;         /* [dof] SMPLGPU_VAR_* */
+    const double*  var_motion_weight;/* [dof] ||MR_center|| + MR_radius of the variable's joint */
+    const double*  var_min;          /* [dof] KDLRobotModel min_limits_ (kdl_robot_model.cpp:276-318) */
+    const double*  var_max;          /* [dof] */
+
+    /* planning-link forward kinematics chain (KDLRobotModel, kdl_robot_model.cpp:400-423):
+     * pose = T_kin_to_planning * prod_{i < n_segments} ( joint_pose_i(q) * seg_f_tip_i ) */
+    int32_t n_segments;              /* number of segments multiplied (= the planning link's segment index) */
+    const int32_t* seg_kind;         /* [n_segments] SMPLGPU_SEG_* */
+    const double*  seg_axis;         /* [n_segments][3] */
+    const double*  seg_origin;       /* [n_segments][3] */
+    const double*  seg_f_tip;        /* [n_segments][12] */
+    const int32_t* seg_var;          /* [n_segments] planning variable or -1 */
+    const double*  T_kin_to_planning;/* [12] */
+    double xyz_offset[3];            /* GoalConstraint::xyz_offset (manip_lattice.cpp:2297-2312) */
+} smplgpu_robot_desc;
+
+typedef struct smplgpu_ctx smplgpu_ctx;
+
+/* ---- context -------------------------------------------------------------- */
+smplgpu_ctx* smplgpu_create(int device);              /* NULL when no device; see smplgpu_last_error(NULL) */
+void         smplgpu_destroy(smplgpu_ctx* ctx);
+const char*  smplgpu_last_error(const smplgpu_ctx* ctx);
+int          smplgpu_device(const smplgpu_ctx* ctx);
+/* run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the context's own stream */
+int          smplgpu_set_stream(smplgpu_ctx* ctx, void* cuda_stream);
+int          smplgpu_synchronize(smplgpu_ctx* ctx);
+/* number of kernels this context has launched since creation */
+int64_t      smplgpu_launch_count(const smplgpu_ctx* ctx);
+
+/* ---- scene state ---------------------------------------------------------- */
+/* replaces CollisionSpace::init + RobotCollisionModel/State tables (collision_space.cpp:689-739) */
+int smplgpu_set_robot(smplgpu_ctx* ctx, const smplgpu_robot_desc* desc);
+
+/* replaces the read side of OccupancyGrid / DistanceMap (occupancy_grid.h:233-237,
+ * distance_map.hpp:281-300, 520-536).  d2 = integer squared cell distance to the
+ * nearest obstacle or border cell, capped at dmax_sq, unpadded nx*ny*nz,
+ * x-major / z-fastest like Grid3 (detail/grid.hpp:361-366).  padding is
+ * SelfCollisionModel's sphere padding (self_collision_model.cpp:394-397). */
+int smplgpu_set_distance_field(smplgpu_ctx* ctx, const uint16_t* d2, int nx, int ny, int nz,
+                               const double origin[3], double res, int dmax_sq, double padding);
+int smplgpu_set_distance_field_dev(smplgpu_ctx* ctx, const uint16_t* d2_dev, int nx, int ny, int nz,
+                                   const double origin[3], double res, int dmax_sq, double padding);
+/* build the field on the device from occupied cells (x,y,z triples, effective grid
+ * coordinates): exact Euclidean transform incl. border-as-obstacle, capped.
+ * "next" row f1 (distance_map.hpp:305-328, 728-762) */
+int smplgpu_build_distance_field(smplgpu_ctx* ctx, const int32_t* cells_xyz, int n_cells,
+                                 int nx, int ny, int nz, const double origin[3], double res,
+                                 double max_dist, double padding);
+int smplgpu_download_distance_field(smplgpu_ctx* ctx, uint16_t* d2_out);
+/* device pointer + byte size of the resident field, for a torch.distributed broadcast */
+int smplgpu_distance_field_dev_ptr(smplgpu_ctx* ctx, void** ptr, int64_t* bytes);
+
+/* ---- validity (CollisionChecker) ------------------------------------------ */
+/* CollisionSpace::isStateValid batched (collision_space.cpp:532-536 -> 479-488);
+ * verdict[i] = 1 valid / 0 invalid */
+int smplgpu_is_states_valid(smplgpu_ctx* ctx, const double* q, int n, uint8_t* verdict);
+int smplgpu_is_states_valid_dev(smplgpu_ctx* ctx, const double* q_dev, int n, uint8_t* verdict_dev);
+/* CollisionSpace::isStateToStateValid batched (collision_space.cpp:538-581);
+ * waypoint_counts may be NULL */
+int smplgpu_is_edges_valid(smplgpu_ctx* ctx, const double* q0, const double* q1, int n,
+                           uint8_t* verdict, int32_t* waypoint_counts);
+int smplgpu_is_edges_valid_dev(smplgpu_ctx* ctx, const double* q0_dev, const double* q1_dev, int n,
+                               uint8_t* verdict_dev, int32_t* waypoint_counts_dev);
+/* kernel (1) alone: sphere centres of every tree node, double out[n][n_nodes][3]
+ * (RobotCollisionState::updateSphereStates, robot_collision_state.h:546-581) */
+int smplgpu_fk_sphere_centers(smplgpu_ctx* ctx, const double* q, int n, double* out);
+/* KDLRobotModel::checkJointLimits batched (kdl_robot_model.cpp:210-235, 326-337) */
+int smplgpu_check_joint_limits(smplgpu_ctx* ctx, const double* q, int n, uint8_t* ok);
+/* counters of the last validity call: DF lookups performed, sphere pairs tested, waypoints checked */
+int smplgpu_last_validity_stats(smplgpu_ctx* ctx, int64_t* df_lookups, int64_t* pair_tests, int64_t* waypoints);
+
+/* ---- BFS heuristic (BFS_3D + BfsHeuristic) -------------------------------- */
+/* BfsHeuristic::syncGridAndBfs (bfs_heuristic.cpp:331-353): wall iff getDistance(cell) <= radius.
+ * Returns the wall count (>= 0) or a negative error. */
+int smplgpu_bfs_set_walls_from_df(smplgpu_ctx* ctx, double inflation_radius);
+/* BFS_3D(nx,ny,nz) + setWall (bfs3d.cpp:40-111, 132-141); walls: 1 byte per cell, x fastest */
+int smplgpu_bfs_set_walls(smplgpu_ctx* ctx, int nx, int ny, int nz, const uint8_t* walls);
+int smplgpu_bfs_set_walls_dev(smplgpu_ctx* ctx, int nx, int ny, int nz, const uint8_t* walls_dev);
+/* BFS_3D::run (bfs3d.cpp:156-201; multi-seed bfs3d.h:157-211).  Synchronous on the
+ * stream; returns the number of seeds that were in bounds, or a negative error. */
+int smplgpu_bfs_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz, int n_seeds);
+/* BFS_3D::getDistance for a list of cells (bfs3d.cpp:373-378) */
+int smplgpu_bfs_distances(smplgpu_ctx* ctx, const int32_t* cells_xyz, int n, int32_t* out);
+/* the whole padded grid, int32[(nz+2)][(ny+2)][(nx+2)], x fastest (bfs3d.h:213-220) */
+int smplgpu_bfs_download(smplgpu_ctx* ctx, int32_t* padded_grid);
+int smplgpu_bfs_dims(smplgpu_ctx* ctx, int32_t dims[3]);
+/* number of level-synchronous sweeps the last run needed */
+int smplgpu_bfs_last_levels(smplgpu_ctx* ctx);
+/* BfsHeuristic::GetGoalHeuristic batched (bfs_heuristic.cpp:148-163, 355-366):
+ * planning-link FK + target offset + worldToGrid + cost_per_cell * distance */
+int smplgpu_goal_heuristics(smplgpu_ctx* ctx, const double* q, int n, int cost_per_cell, int32_t* h);
+int smplgpu_goal_heuristics_dev(smplgpu_ctx* ctx, const double* q_dev, int n, int cost_per_cell, int32_t* h_dev);
+/* ForwardKinematicsInterface::computePlanningLinkFK + getTargetOffsetPose: double pose6[n][6] */
+int smplgpu_planning_frame_fk(smplgpu_ctx* ctx, const double* q, int n, double* pose6);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SMPLGPU_H */

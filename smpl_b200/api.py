@@ -1,0 +1,422 @@
+"""ctypes plumbing over the C ABI (include/smplgpu.h, include/smplhost.h).
+
+The compute path is libsmplgpu.so (hand-written sm_100a kernels).  There is no
+CPU fallback: a missing library or a missing GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBDIR = os.path.join(HERE, "lib")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_uint8_p = C.POINTER(C.c_uint8)
+c_uint16_p = C.POINTER(C.c_uint16)
+
+_gpu = None
+_host = None
+
+
+class SmplGpuError(RuntimeError):
+    pass
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int32_p)
+
+
+def _bp(a):
+    return a.ctypes.data_as(c_uint8_p)
+
+
+def gpu_lib():
+    """libsmplgpu.so; raises when it has not been built (no fallback)."""
+    global _gpu
+    if _gpu is None:
+        path = os.path.join(LIBDIR, "libsmplgpu.so")
+        if not os.path.exists(path):
+            raise SmplGpuError("CUDA extension %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        L.smplgpu_create.restype = C.c_void_p
+        L.smplgpu_create.argtypes = [C.c_int]
+        L.smplgpu_last_error.restype = C.c_char_p
+        L.smplgpu_last_error.argtypes = [C.c_void_p]
+        L.smplgpu_launch_count.restype = C.c_int64
+        L.smplgpu_launch_count.argtypes = [C.c_void_p]
+        L.smplgpu_destroy.argtypes = [C.c_void_p]
+        L.smplgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.smplgpu_synchronize.argtypes = [C.c_void_p]
+        vp, dp, ip, bp, i, d = C.c_void_p, c_double_p, c_int32_p, c_uint8_p, C.c_int, C.c_double
+        L.smplgpu_set_distance_field.argtypes = [vp, c_uint16_p, i, i, i, dp, d, i, d]
+        L.smplgpu_set_distance_field_dev.argtypes = [vp, vp, i, i, i, dp, d, i, d]
+        L.smplgpu_build_distance_field.argtypes = [vp, ip, i, i, i, i, dp, d, d, d]
+        L.smplgpu_download_distance_field.argtypes = [vp, c_uint16_p]
+        L.smplgpu_distance_field_dev_ptr.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.smplgpu_is_states_valid.argtypes = [vp, dp, i, bp]
+        L.smplgpu_is_states_valid_dev.argtypes = [vp, vp, i, vp]
+        L.smplgpu_is_edges_valid.argtypes = [vp, dp, dp, i, bp, ip]
+        L.smplgpu_is_edges_valid_dev.argtypes = [vp, vp, vp, i, vp, vp]
+        L.smplgpu_fk_sphere_centers.argtypes = [vp, dp, i, dp]
+        L.smplgpu_check_joint_limits.argtypes = [vp, dp, i, bp]
+        L.smplgpu_last_validity_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.smplgpu_bfs_set_walls_from_df.argtypes = [vp, d]
+        L.smplgpu_bfs_set_walls.argtypes = [vp, i, i, i, bp]
+        L.smplgpu_bfs_set_walls_dev.argtypes = [vp, i, i, i, vp]
+        L.smplgpu_bfs_run.argtypes = [vp, ip, i]
+        L.smplgpu_bfs_distances.argtypes = [vp, ip, i, ip]
+        L.smplgpu_bfs_download.argtypes = [vp, ip]
+        L.smplgpu_bfs_dims.argtypes = [vp, ip]
+        L.smplgpu_bfs_last_levels.argtypes = [vp]
+        L.smplgpu_goal_heuristics.argtypes = [vp, dp, i, i, ip]
+        L.smplgpu_goal_heuristics_dev.argtypes = [vp, vp, i, i, vp]
+        L.smplgpu_planning_frame_fk.argtypes = [vp, dp, i, dp]
+        _gpu = L
+    return _gpu
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        gpu_lib()
+        path = os.path.join(LIBDIR, "libsmplhost.so")
+        if not os.path.exists(path):
+            raise SmplGpuError("host library %s is missing: run __graft_entry__.build()" % path)
+        H = C.CDLL(path)
+        H.smplhost_last_error.restype = C.c_char_p
+        H.smplhost_tables_load.restype = C.c_void_p
+        H.smplhost_tables_load.argtypes = [C.c_char_p]
+        vp = C.c_void_p
+        H.smplhost_tables_destroy.argtypes = [vp]
+        H.smplhost_tables_configure.argtypes = [vp, C.c_char_p, C.c_char_p]
+        H.smplhost_tables_set_joint.argtypes = [vp, C.c_char_p, C.c_double]
+        H.smplhost_tables_use_file_acm.argtypes = [vp]
+        H.smplhost_tables_set_acm_entry.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
+        H.smplhost_tables_attach_spheres.argtypes = [vp, C.c_char_p, C.c_char_p, c_double_p, C.c_int, C.c_double]
+        H.smplhost_tables_detach.argtypes = [vp, C.c_char_p]
+        H.smplhost_tables_set_planning_chain.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, c_double_p, c_double_p]
+        H.smplhost_tables_dof.argtypes = [vp]
+        H.smplhost_tables_limits.argtypes = [vp, c_double_p, c_double_p, c_uint8_p]
+        H.smplhost_tables_apply.argtypes = [vp, vp]
+        H.smplhost_tables_outside_voxels.argtypes = [vp, C.POINTER(c_double_p)]
+        H.smplhost_tables_node_table.argtypes = [vp, c_double_p, C.c_int]
+        H.smplhost_tables_motion_weights.argtypes = [vp, c_double_p, c_int32_p]
+        H.smplhost_tables_pairs.argtypes = [vp, c_int32_p, C.c_int]
+        _host = H
+    return _host
+
+
+class RobotTables:
+    """Host-side model builder (smpl_b200/host/robot_tables.cpp)."""
+
+    def __init__(self, robot_path):
+        self.H = host_lib()
+        h = self.H.smplhost_tables_load(robot_path.encode())
+        if not h:
+            raise SmplGpuError("smplhost_tables_load: " + self.H.smplhost_last_error().decode())
+        self.h = C.c_void_p(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.H.smplhost_tables_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, r, what):
+        if r != 0:
+            raise SmplGpuError("%s: %s" % (what, self.H.smplhost_last_error().decode()))
+
+    def configure(self, group, planning_joints):
+        self._ck(self.H.smplhost_tables_configure(self.h, group.encode(), ",".join(planning_joints).encode()), "configure")
+
+    def set_joint(self, name, value):
+        self._ck(self.H.smplhost_tables_set_joint(self.h, name.encode(), float(value)), "set_joint")
+
+    def use_file_acm(self):
+        self.H.smplhost_tables_use_file_acm(self.h)
+
+    def set_acm_entry(self, a, b, allowed):
+        self.H.smplhost_tables_set_acm_entry(self.h, a.encode(), b.encode(), int(allowed))
+
+    def attach_spheres(self, body_id, link, centers, radius):
+        c = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3)
+        self._ck(self.H.smplhost_tables_attach_spheres(self.h, body_id.encode(), link.encode(), _dp(c), len(c),
+                                                       float(radius)), "attach_spheres")
+
+    def detach(self, body_id):
+        return self.H.smplhost_tables_detach(self.h, body_id.encode()) == 0
+
+    def set_planning_chain(self, root, tip, planning_link, T_kin_to_planning=None, xyz_offset=None):
+        T = np.eye(4)[:3] if T_kin_to_planning is None else np.asarray(T_kin_to_planning, np.float64).reshape(3, 4)
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        off = np.ascontiguousarray(np.zeros(3) if xyz_offset is None else np.asarray(xyz_offset, np.float64))
+        self._ck(self.H.smplhost_tables_set_planning_chain(self.h, root.encode(), tip.encode(), planning_link.encode(),
+                                                           _dp(T), _dp(off)), "set_planning_chain")
+
+    @property
+    def dof(self):
+        return self.H.smplhost_tables_dof(self.h)
+
+    def limits(self):
+        n = self.dof
+        lo, hi, c = np.zeros(n), np.zeros(n), np.zeros(n, np.uint8)
+        self.H.smplhost_tables_limits(self.h, _dp(lo), _dp(hi), _bp(c))
+        return lo, hi, c
+
+    def apply(self, ctx):
+        self._ck(self.H.smplhost_tables_apply(self.h, ctx.h), "apply")
+
+    def outside_voxels(self):
+        p = c_double_p()
+        n = self.H.smplhost_tables_outside_voxels(self.h, C.byref(p))
+        if n <= 0:
+            return np.zeros((0, 3))
+        return np.ctypeslib.as_array(p, shape=(n, 3)).copy()
+
+    def node_table(self):
+        out = np.zeros((4096, 8))
+        n = self.H.smplhost_tables_node_table(self.h, _dp(out), 4096)
+        return out[:n].copy()
+
+    def motion_weights(self):
+        n = self.dof
+        w, t = np.zeros(n), np.zeros(n, np.int32)
+        self.H.smplhost_tables_motion_weights(self.h, _dp(w), _ip(t))
+        return w, t
+
+    def pairs(self):
+        out = np.zeros((4096, 2), np.int32)
+        n = self.H.smplhost_tables_pairs(self.h, _ip(out), 4096)
+        return out[:n].copy()
+
+
+class GpuContext:
+    """One smplgpu context (one GPU, one stream)."""
+
+    def __init__(self, device=0):
+        self.L = gpu_lib()
+        h = self.L.smplgpu_create(int(device))
+        if not h:
+            raise SmplGpuError("smplgpu_create: " + self.L.smplgpu_last_error(None).decode())
+        self.h = C.c_void_p(h)
+        self.dof = None
+        self.n_nodes = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.smplgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, r, what):
+        if r < 0:
+            raise SmplGpuError("%s: %s" % (what, self.L.smplgpu_last_error(self.h).decode()))
+        return r
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.L.smplgpu_set_stream(self.h, C.c_void_p(cuda_stream)), "set_stream")
+
+    def synchronize(self):
+        self._ck(self.L.smplgpu_synchronize(self.h), "synchronize")
+
+    def launch_count(self):
+        return int(self.L.smplgpu_launch_count(self.h))
+
+    # ---- scene ----
+    def set_robot(self, tables):
+        tables.apply(self)
+        self.dof = tables.dof
+        self.n_nodes = len(tables.node_table())
+
+    def set_distance_field(self, d2, origin, res, dmax_sq, padding=0.0):
+        d2 = np.ascontiguousarray(d2, dtype=np.uint16)
+        nx, ny, nz = d2.shape
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        self._ck(self.L.smplgpu_set_distance_field(self.h, d2.ctypes.data_as(c_uint16_p), nx, ny, nz, _dp(o),
+                                                   float(res), int(dmax_sq), float(padding)), "set_distance_field")
+        self.df_dims = (nx, ny, nz)
+
+    def set_distance_field_dev(self, ptr, dims, origin, res, dmax_sq, padding=0.0):
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        self._ck(self.L.smplgpu_set_distance_field_dev(self.h, C.c_void_p(ptr), int(dims[0]), int(dims[1]), int(dims[2]),
+                                                       _dp(o), float(res), int(dmax_sq), float(padding)),
+                 "set_distance_field_dev")
+        self.df_dims = tuple(int(d) for d in dims)
+
+    def build_distance_field(self, cells, dims, origin, res, max_dist, padding=0.0):
+        cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 3)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        self._ck(self.L.smplgpu_build_distance_field(self.h, _ip(cells), len(cells), int(dims[0]), int(dims[1]),
+                                                     int(dims[2]), _dp(o), float(res), float(max_dist), float(padding)),
+                 "build_distance_field")
+        self.df_dims = tuple(int(d) for d in dims)
+
+    def download_distance_field(self):
+        out = np.zeros(self.df_dims, np.uint16)
+        self._ck(self.L.smplgpu_download_distance_field(self.h, out.ctypes.data_as(c_uint16_p)), "download_distance_field")
+        return out
+
+    def distance_field_dev_ptr(self):
+        p = C.c_void_p()
+        n = C.c_int64()
+        self._ck(self.L.smplgpu_distance_field_dev_ptr(self.h, C.byref(p), C.byref(n)), "distance_field_dev_ptr")
+        return p.value, n.value
+
+    # ---- validity ----
+    def _q(self, q):
+        return np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.dof)
+
+    def is_states_valid(self, q):
+        q = self._q(q)
+        v = np.zeros(len(q), np.uint8)
+        self._ck(self.L.smplgpu_is_states_valid(self.h, _dp(q), len(q), _bp(v)), "is_states_valid")
+        return v
+
+    def is_states_valid_dev(self, q_ptr, n, verdict_ptr):
+        self._ck(self.L.smplgpu_is_states_valid_dev(self.h, C.c_void_p(q_ptr), int(n), C.c_void_p(verdict_ptr)),
+                 "is_states_valid_dev")
+
+    def is_edges_valid(self, q0, q1, want_counts=True):
+        q0, q1 = self._q(q0), self._q(q1)
+        v = np.zeros(len(q0), np.uint8)
+        c = np.zeros(len(q0), np.int32) if want_counts else None
+        self._ck(self.L.smplgpu_is_edges_valid(self.h, _dp(q0), _dp(q1), len(q0), _bp(v),
+                                               _ip(c) if want_counts else None), "is_edges_valid")
+        return (v, c) if want_counts else v
+
+    def is_edges_valid_dev(self, q0_ptr, q1_ptr, n, verdict_ptr, counts_ptr=None):
+        self._ck(self.L.smplgpu_is_edges_valid_dev(self.h, C.c_void_p(q0_ptr), C.c_void_p(q1_ptr), int(n),
+                                                   C.c_void_p(verdict_ptr), C.c_void_p(counts_ptr) if counts_ptr else None),
+                 "is_edges_valid_dev")
+
+    def fk_sphere_centers(self, q):
+        q = self._q(q)
+        out = np.zeros((len(q), self.n_nodes, 3))
+        self._ck(self.L.smplgpu_fk_sphere_centers(self.h, _dp(q), len(q), _dp(out)), "fk_sphere_centers")
+        return out
+
+    def check_joint_limits(self, q):
+        q = self._q(q)
+        ok = np.zeros(len(q), np.uint8)
+        self._ck(self.L.smplgpu_check_joint_limits(self.h, _dp(q), len(q), _bp(ok)), "check_joint_limits")
+        return ok
+
+    def last_validity_stats(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self.L.smplgpu_last_validity_stats(self.h, C.byref(a), C.byref(b), C.byref(c)), "last_validity_stats")
+        return dict(df_lookups=a.value, pair_tests=b.value, waypoints=c.value)
+
+    # ---- BFS / heuristic ----
+    def bfs_set_walls_from_df(self, inflation_radius):
+        return self._ck(self.L.smplgpu_bfs_set_walls_from_df(self.h, float(inflation_radius)), "bfs_set_walls_from_df")
+
+    def bfs_set_walls(self, walls_zyx):
+        w = np.ascontiguousarray(walls_zyx, dtype=np.uint8)
+        nz, ny, nx = w.shape
+        self._ck(self.L.smplgpu_bfs_set_walls(self.h, nx, ny, nz, _bp(w)), "bfs_set_walls")
+
+    def bfs_set_walls_dev(self, ptr, nx, ny, nz):
+        self._ck(self.L.smplgpu_bfs_set_walls_dev(self.h, int(nx), int(ny), int(nz), C.c_void_p(ptr)), "bfs_set_walls_dev")
+
+    def bfs_run(self, seeds):
+        s = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 3)
+        return self._ck(self.L.smplgpu_bfs_run(self.h, _ip(s), len(s)), "bfs_run")
+
+    def bfs_dims(self):
+        d = np.zeros(3, np.int32)
+        self._ck(self.L.smplgpu_bfs_dims(self.h, _ip(d)), "bfs_dims")
+        return tuple(int(v) for v in d)
+
+    def bfs_download(self):
+        nx, ny, nz = self.bfs_dims()
+        out = np.zeros((nz + 2, ny + 2, nx + 2), np.int32)
+        self._ck(self.L.smplgpu_bfs_download(self.h, _ip(out)), "bfs_download")
+        return out
+
+    def bfs_distances(self, cells):
+        c = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 3)
+        out = np.zeros(len(c), np.int32)
+        self._ck(self.L.smplgpu_bfs_distances(self.h, _ip(c), len(c), _ip(out)), "bfs_distances")
+        return out
+
+    def bfs_last_levels(self):
+        return self.L.smplgpu_bfs_last_levels(self.h)
+
+    def goal_heuristics(self, q, cost_per_cell):
+        q = self._q(q)
+        h = np.zeros(len(q), np.int32)
+        self._ck(self.L.smplgpu_goal_heuristics(self.h, _dp(q), len(q), int(cost_per_cell), _ip(h)), "goal_heuristics")
+        return h
+
+    def goal_heuristics_dev(self, q_ptr, n, cost_per_cell, h_ptr):
+        self._ck(self.L.smplgpu_goal_heuristics_dev(self.h, C.c_void_p(q_ptr), int(n), int(cost_per_cell),
+                                                    C.c_void_p(h_ptr)), "goal_heuristics_dev")
+
+    def planning_frame_fk(self, q):
+        q = self._q(q)
+        out = np.zeros((len(q), 6))
+        self._ck(self.L.smplgpu_planning_frame_fk(self.h, _dp(q), len(q), _dp(out)), "planning_frame_fk")
+        return out
+
+
+def world_to_grid(points, origin, res):
+    """DistanceMap::worldToGrid (distance_map.hpp:520-527) in IEEE double, C truncation."""
+    p = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    inv = 1.0 / res
+    o = np.asarray(origin, dtype=np.float64) - res
+    t = inv * (p - o) + 0.5
+    return np.trunc(t).astype(np.int64).astype(np.int32) - 1
+
+
+def build_tables(scene):
+    """RobotTables configured for a smpl_b200.scenes.Scene."""
+    t = RobotTables(scene.robot_path)
+    t.configure(scene.group, scene.planning_joints)
+    for k, v in scene.fixed_joints.items():
+        t.set_joint(k, v)
+    if scene.use_desc_acm:
+        t.use_file_acm()
+    if scene.attached is not None:
+        body_id, link, centers, radius = scene.attached
+        t.attach_spheres(body_id, link, centers, radius)
+    if scene.chain_root is not None:
+        t.set_planning_chain(scene.chain_root, scene.chain_tip, scene.planning_link, scene.T_kin_to_planning,
+                             scene.xyz_offset)
+    return t
+
+
+def scene_cells(scene, tables):
+    """Occupied cells of a scene: world obstacles + voxels of out-of-group robot links."""
+    vox = tables.outside_voxels()
+    cells = scene.cells
+    if len(vox):
+        g = world_to_grid(vox, scene.origin, scene.res)
+        ok = np.all((g >= 0) & (g < np.asarray(scene.dims)), axis=1)
+        cells = np.concatenate([cells, g[ok]], axis=0)
+    return np.ascontiguousarray(cells, dtype=np.int32)
+
+
+def setup_context(scene, device=0, ctx=None):
+    """Create a context with robot tables and a device-built distance field for `scene`."""
+    ctx = ctx or GpuContext(device)
+    tables = build_tables(scene)
+    ctx.set_robot(tables)
+    ctx.build_distance_field(scene_cells(scene, tables), scene.dims, scene.origin, scene.res, scene.max_dist,
+                             scene.padding)
+    return ctx, tables

@@ -1,0 +1,957 @@
+// C ABI implementation (include/smplgpu.h) over the sm_100a kernels.
+// Host side is plain CUDA runtime: device buffers, pinned staging, one stream.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smplgpu.h"
+#include "bfs.cuh"
+#include "edt.cuh"
+#include "heuristic.cuh"
+#include "model.cuh"
+#include "validity.cuh"
+
+using namespace smplgpu;
+
+static thread_local std::string g_create_error;
+
+struct smplgpu_ctx
+{
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    int64_t launches = 0;
+
+    // robot
+    bool has_robot = false;
+    DevModel* h_model = nullptr; // host copy
+    DevModel* d_model = nullptr;
+    std::vector<double> node_radius;
+
+    // distance field
+    bool has_df = false;
+    uint16_t* d_df = nullptr;
+    size_t df_cells = 0;
+    GridParams grid{};
+    double res = 0.0, padding = 0.0;
+    double origin[3] = { 0, 0, 0 };
+    int dmax_sq = 0;
+
+    // BFS
+    bool has_bfs = false;
+    BfsGrid bfs{};
+    size_t bfs_words = 0, bfs_cells = 0;
+    int bfs_levels = 0;
+    int* d_seed_count = nullptr;
+
+    // scratch / staging
+    double* d_q0 = nullptr; double* d_q1 = nullptr; size_t q_cap = 0;   // doubles
+    uint8_t* d_verdict = nullptr; int* d_counts = nullptr; size_t v_cap = 0;
+    void* d_misc = nullptr; size_t misc_cap = 0;
+    void* pinned[2] = { nullptr, nullptr }; size_t pinned_cap = 0;
+    void* pinned_out[2] = { nullptr, nullptr }; size_t pinned_out_cap = 0;
+    cudaEvent_t ev[2] = { nullptr, nullptr };
+    unsigned long long* d_stats = nullptr;
+    unsigned long long h_stats[4] = { 0, 0, 0, 0 };
+};
+
+static int fail(smplgpu_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) {
+        ctx->error = buf;
+    } else {
+        g_create_error = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            return fail(ctx, SMPLGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+        }                                                                                          \
+    } while (0)
+
+static int grow(smplgpu_ctx* ctx, void** p, size_t* cap, size_t need)
+{
+    if (need <= *cap) {
+        return 0;
+    }
+    if (*p) {
+        CU(cudaFree(*p));
+        *p = nullptr;
+        *cap = 0;
+    }
+    size_t n = std::max(need, (size_t)1 << 16);
+    CU(cudaMalloc(p, n));
+    *cap = n;
+    return 0;
+}
+
+static int grow_pinned(smplgpu_ctx* ctx, void** p, size_t* cap, size_t need)
+{
+    if (need <= *cap) {
+        return 0;
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (p[i]) {
+            CU(cudaFreeHost(p[i]));
+            p[i] = nullptr;
+        }
+    }
+    *cap = 0;
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMallocHost(&p[i], need));
+    }
+    *cap = need;
+    return 0;
+}
+
+static int ensure_state_buffers(smplgpu_ctx* ctx, size_t n, int dof, bool edges)
+{
+    size_t need_q = n * (size_t)dof * sizeof(double);
+    if (need_q > ctx->q_cap) {
+        if (ctx->d_q0) { CU(cudaFree(ctx->d_q0)); ctx->d_q0 = nullptr; }
+        if (ctx->d_q1) { CU(cudaFree(ctx->d_q1)); ctx->d_q1 = nullptr; }
+        ctx->q_cap = 0;
+        CU(cudaMalloc(&ctx->d_q0, need_q));
+        CU(cudaMalloc(&ctx->d_q1, need_q));
+        ctx->q_cap = need_q;
+    }
+    if (n > ctx->v_cap) {
+        if (ctx->d_verdict) { CU(cudaFree(ctx->d_verdict)); ctx->d_verdict = nullptr; }
+        if (ctx->d_counts) { CU(cudaFree(ctx->d_counts)); ctx->d_counts = nullptr; }
+        ctx->v_cap = 0;
+        CU(cudaMalloc(&ctx->d_verdict, n));
+        CU(cudaMalloc(&ctx->d_counts, n * sizeof(int)));
+        ctx->v_cap = n;
+    }
+    (void)edges;
+    return 0;
+}
+
+extern "C" {
+
+smplgpu_ctx* smplgpu_create(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        fail(nullptr, SMPLGPU_ERR_NO_DEVICE, "no CUDA device: %s (there is no CPU fallback)",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return nullptr;
+    }
+    if (device < 0 || device >= count) {
+        fail(nullptr, SMPLGPU_ERR_INVALID, "device %d out of range (count %d)", device, count);
+        return nullptr;
+    }
+    smplgpu_ctx* ctx = new smplgpu_ctx;
+    ctx->device = device;
+    auto bail = [&](const char* what, cudaError_t err) {
+        fail(nullptr, SMPLGPU_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+        delete ctx;
+        return (smplgpu_ctx*)nullptr;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    ctx->stream = ctx->own_stream;
+    if ((e = cudaMalloc(&ctx->d_model, sizeof(DevModel))) != cudaSuccess) return bail("cudaMalloc(model)", e);
+    if ((e = cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(stats)", e);
+    if ((e = cudaMalloc(&ctx->d_seed_count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc(seed)", e);
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
+    ctx->h_model = new DevModel;
+    memset(ctx->h_model, 0, sizeof(DevModel));
+    return ctx;
+}
+
+static void free_bfs(smplgpu_ctx* ctx)
+{
+    BfsGrid& g = ctx->bfs;
+    cudaFree(g.wall); cudaFree(g.blocked); cudaFree(g.front[0]); cudaFree(g.front[1]);
+    cudaFree(g.row_stamp[0]); cudaFree(g.row_stamp[1]); cudaFree(g.cand_stamp[0]); cudaFree(g.cand_stamp[1]);
+    cudaFree(g.dist); cudaFree(g.ctrl);
+    memset(&g, 0, sizeof(g));
+    ctx->has_bfs = false;
+}
+
+void smplgpu_destroy(smplgpu_ctx* ctx)
+{
+    if (!ctx) {
+        return;
+    }
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_bfs(ctx);
+    cudaFree(ctx->d_model); cudaFree(ctx->d_stats); cudaFree(ctx->d_seed_count); cudaFree(ctx->d_df);
+    cudaFree(ctx->d_q0); cudaFree(ctx->d_q1); cudaFree(ctx->d_verdict); cudaFree(ctx->d_counts); cudaFree(ctx->d_misc);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+        if (ctx->pinned_out[i]) cudaFreeHost(ctx->pinned_out[i]);
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx->h_model;
+    delete ctx;
+}
+
+const char* smplgpu_last_error(const smplgpu_ctx* ctx)
+{
+    return ctx ? ctx->error.c_str() : g_create_error.c_str();
+}
+
+int smplgpu_device(const smplgpu_ctx* ctx) { return ctx ? ctx->device : -1; }
+
+int smplgpu_set_stream(smplgpu_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return 0;
+}
+
+int smplgpu_synchronize(smplgpu_ctx* ctx)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int64_t smplgpu_launch_count(const smplgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+///////////////////////////////////////////////////////////////////////////////
+// robot
+///////////////////////////////////////////////////////////////////////////////
+
+// ok  <=>  (res*sqrt(d2))^2 >= (r+pad)^2, evaluated exactly like
+// collision_operations.h:74-76 over distance_map.hpp:142-146, 298-299
+static int sphere_threshold(double res, int dmax_sq, double radius, double padding)
+{
+    const double eff = radius + padding;
+    const double eff2 = eff * eff;
+    for (int k = 0; k <= dmax_sq; ++k) {
+        const double d = res * std::sqrt((double)k);
+        if (d * d >= eff2) {
+            return k;
+        }
+    }
+    return dmax_sq + 1;
+}
+
+static int upload_model(smplgpu_ctx* ctx)
+{
+    DevModel& m = *ctx->h_model;
+    if (ctx->has_df) {
+        for (int i = 0; i < m.n_nodes; ++i) {
+            m.node_thresh[i] = sphere_threshold(ctx->res, ctx->dmax_sq, m.node_radius[i], ctx->padding);
+        }
+    }
+    CU(cudaMemcpyAsync(ctx->d_model, &m, sizeof(DevModel), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int tree_depth(const DevModel& m, int node)
+{
+    if (m.node_left[node] < 0) {
+        return 1;
+    }
+    return 1 + std::max(tree_depth(m, m.node_left[node]), tree_depth(m, m.node_right[node]));
+}
+
+int smplgpu_set_robot(smplgpu_ctx* ctx, const smplgpu_robot_desc* d)
+{
+    if (!ctx || !d) return SMPLGPU_ERR_INVALID;
+    if (d->dof <= 0 || d->dof > MAX_DOF) return fail(ctx, SMPLGPU_ERR_LIMIT, "dof %d outside [1,%d]", d->dof, MAX_DOF);
+    if (d->n_links < 0 || d->n_links > MAX_LINKS) return fail(ctx, SMPLGPU_ERR_LIMIT, "n_links %d > %d", d->n_links, MAX_LINKS);
+    if (d->n_nodes < 0 || d->n_nodes > MAX_NODES) return fail(ctx, SMPLGPU_ERR_LIMIT, "n_nodes %d > %d", d->n_nodes, MAX_NODES);
+    if (d->n_trees < 0 || d->n_trees > MAX_TREES) return fail(ctx, SMPLGPU_ERR_LIMIT, "n_trees %d > %d", d->n_trees, MAX_TREES);
+    if (d->n_pairs < 0 || d->n_pairs > MAX_PAIRS) return fail(ctx, SMPLGPU_ERR_LIMIT, "n_pairs %d > %d", d->n_pairs, MAX_PAIRS);
+    if (d->n_allowed_leaf_pairs < 0 || d->n_allowed_leaf_pairs > MAX_ALLOWED) return fail(ctx, SMPLGPU_ERR_LIMIT, "allowed leaf pairs %d > %d", d->n_allowed_leaf_pairs, MAX_ALLOWED);
+    if (d->n_segments < 0 || d->n_segments > MAX_SEGMENTS) return fail(ctx, SMPLGPU_ERR_LIMIT, "n_segments %d > %d", d->n_segments, MAX_SEGMENTS);
+
+    DevModel& m = *ctx->h_model;
+    memset(&m, 0, sizeof(m));
+    m.dof = d->dof;
+    m.n_links = d->n_links;
+    m.n_nodes = d->n_nodes;
+    m.n_trees = d->n_trees;
+    m.n_pairs = d->n_pairs;
+    m.n_allowed = d->n_allowed_leaf_pairs;
+    m.n_segments = d->n_segments;
+
+    for (int l = 0; l < m.n_links; ++l) {
+        const int p = d->link_parent[l];
+        if (p >= l) return fail(ctx, SMPLGPU_ERR_INVALID, "link %d: parent %d is not earlier in the table", l, p);
+        const int fn = d->link_joint[l];
+        if (fn < 0 || fn > SMPLGPU_JOINT_PRISMATIC) return fail(ctx, SMPLGPU_ERR_INVALID, "link %d: joint fn %d", l, fn);
+        const int v = d->link_var[l];
+        if (v >= m.dof) return fail(ctx, SMPLGPU_ERR_INVALID, "link %d: variable %d >= dof", l, v);
+        m.link_parent[l] = p < 0 ? -1 : p;
+        m.link_joint[l] = fn;
+        m.link_var[l] = v < 0 ? -1 : v;
+        m.link_const[l] = d->link_const[l];
+        memcpy(m.link_origin[l], d->link_origin + 12 * l, 12 * sizeof(double));
+        memcpy(m.link_axis[l], d->link_axis + 3 * l, 3 * sizeof(double));
+        memcpy(m.link_base[l], d->link_base + 12 * l, 12 * sizeof(double));
+        m.link_slot[l] = -1;
+    }
+    for (int i = 0; i < m.n_nodes; ++i) {
+        const int l = d->node_link[i];
+        if (l < 0 || l >= m.n_links) return fail(ctx, SMPLGPU_ERR_INVALID, "node %d: link %d", i, l);
+        const int a = d->node_left[i], b = d->node_right[i];
+        if ((a < 0) != (b < 0) || a >= m.n_nodes || b >= m.n_nodes) return fail(ctx, SMPLGPU_ERR_INVALID, "node %d: children %d %d", i, a, b);
+        if (a >= 0 && (d->node_link[a] != l || d->node_link[b] != l)) return fail(ctx, SMPLGPU_ERR_INVALID, "node %d: child on another link", i);
+        m.node_link[i] = l;
+        m.node_left[i] = a < 0 ? -1 : a;
+        m.node_right[i] = b < 0 ? -1 : b;
+        m.node_radius[i] = d->node_radius[i];
+        memcpy(m.node_center[i], d->node_center + 3 * i, 3 * sizeof(double));
+        m.node_thresh[i] = 0x7FFFFFFF; // until a distance field is set
+    }
+    int max_depth = 0;
+    for (int t = 0; t < m.n_trees; ++t) {
+        const int r = d->tree_root[t];
+        if (r < 0 || r >= m.n_nodes) return fail(ctx, SMPLGPU_ERR_INVALID, "tree %d: root %d", t, r);
+        m.tree_root[t] = r;
+        max_depth = std::max(max_depth, tree_depth(m, r));
+    }
+    if (2 * max_depth + 2 > MAX_TREE_DEPTH) return fail(ctx, SMPLGPU_ERR_LIMIT, "sphere tree depth %d too deep", max_depth);
+    for (int p = 0; p < m.n_pairs; ++p) {
+        if (d->pair_a[p] < 0 || d->pair_a[p] >= m.n_trees || d->pair_b[p] < 0 || d->pair_b[p] >= m.n_trees)
+            return fail(ctx, SMPLGPU_ERR_INVALID, "pair %d out of range", p);
+        m.pair_a[p] = d->pair_a[p];
+        m.pair_b[p] = d->pair_b[p];
+    }
+    for (int k = 0; k < m.n_allowed; ++k) {
+        m.allowed_a[k] = d->allowed_leaf_a[k];
+        m.allowed_b[k] = d->allowed_leaf_b[k];
+    }
+    for (int v = 0; v < m.dof; ++v) {
+        m.var_type[v] = d->var_type[v];
+        m.var_weight[v] = d->var_motion_weight[v];
+        m.var_min[v] = d->var_min ? d->var_min[v] : -INFINITY;
+        m.var_max[v] = d->var_max ? d->var_max[v] : INFINITY;
+        // angles::normalize_angle(min)  (smpl/angles.h:45-62)
+        double a = m.var_min[v];
+        if (std::fabs(a) > 2.0 * M_PI) a = std::fmod(a, 2.0 * M_PI);
+        if (a < -M_PI) a += 2.0 * M_PI;
+        if (a > M_PI) a -= 2.0 * M_PI;
+        m.var_min_norm[v] = a;
+    }
+    for (int s = 0; s < m.n_segments; ++s) {
+        m.seg_kind[s] = d->seg_kind[s];
+        m.seg_var[s] = d->seg_var[s] < 0 ? -1 : d->seg_var[s];
+        if (m.seg_var[s] >= m.dof) return fail(ctx, SMPLGPU_ERR_INVALID, "segment %d: variable out of range", s);
+        memcpy(m.seg_axis[s], d->seg_axis + 3 * s, 3 * sizeof(double));
+        memcpy(m.seg_origin[s], d->seg_origin + 3 * s, 3 * sizeof(double));
+        memcpy(m.seg_f_tip[s], d->seg_f_tip + 12 * s, 12 * sizeof(double));
+    }
+    if (d->T_kin_to_planning) {
+        memcpy(m.T_kin_to_planning, d->T_kin_to_planning, 12 * sizeof(double));
+    } else {
+        const double I[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+        memcpy(m.T_kin_to_planning, I, sizeof(I));
+    }
+    memcpy(m.xyz_offset, d->xyz_offset, 3 * sizeof(double));
+
+    // trees grouped by the link they ride on (checked inline while T_link is in registers)
+    {
+        std::vector<int> order(m.n_trees);
+        for (int t = 0; t < m.n_trees; ++t) order[t] = t;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return m.node_link[m.tree_root[a]] < m.node_link[m.tree_root[b]];
+        });
+        int k = 0;
+        for (int l = 0; l < m.n_links; ++l) {
+            m.link_tree_begin[l] = k;
+            while (k < m.n_trees && m.node_link[m.tree_root[order[k]]] == l) {
+                m.tree_by_link[k] = order[k];
+                ++k;
+            }
+            m.link_tree_end[l] = k;
+        }
+    }
+    // shared-memory slots: links read again later (tree pairs, or a child that
+    // is not the next link in the table)
+    {
+        std::vector<bool> keep(m.n_links, false);
+        for (int p = 0; p < m.n_pairs; ++p) {
+            keep[m.node_link[m.tree_root[m.pair_a[p]]]] = true;
+            keep[m.node_link[m.tree_root[m.pair_b[p]]]] = true;
+        }
+        for (int l = 0; l < m.n_links; ++l) {
+            const int p = m.link_parent[l];
+            if (p >= 0 && p != l - 1) {
+                keep[p] = true;
+            }
+        }
+        int slots = 0;
+        for (int l = 0; l < m.n_links; ++l) {
+            if (keep[l]) {
+                m.link_slot[l] = slots++;
+            }
+        }
+        m.n_slots = slots;
+        const size_t smem = (size_t)slots * 12 * sizeof(double) * VALIDITY_THREADS;
+        if (smem > 227 * 1024) return fail(ctx, SMPLGPU_ERR_LIMIT, "%d link slots need %zu B of shared memory", slots, smem);
+        CU(cudaFuncSetAttribute(states_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
+        CU(cudaFuncSetAttribute(edges_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
+        CU(cudaFuncSetAttribute(fk_centers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
+    }
+    ctx->has_robot = true;
+    return upload_model(ctx);
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// distance field
+///////////////////////////////////////////////////////////////////////////////
+
+static int set_df_common(smplgpu_ctx* ctx, int nx, int ny, int nz, const double origin[3], double res, int dmax_sq, double padding)
+{
+    if (nx <= 0 || ny <= 0 || nz <= 0 || !(res > 0.0) || dmax_sq < 0 || dmax_sq > 65534)
+        return fail(ctx, SMPLGPU_ERR_INVALID, "bad distance field parameters");
+    const size_t cells = (size_t)nx * ny * nz;
+    if (cells != ctx->df_cells) {
+        if (ctx->d_df) { CU(cudaFree(ctx->d_df)); ctx->d_df = nullptr; }
+        CU(cudaMalloc(&ctx->d_df, cells * sizeof(uint16_t)));
+        ctx->df_cells = cells;
+    }
+    ctx->grid.nx = nx; ctx->grid.ny = ny; ctx->grid.nz = nz;
+    ctx->grid.inv_res = 1.0 / res;                 // m_inv_res(1.0 / resolution), distance_map.hpp:124
+    ctx->grid.ox = origin[0] - res;                // (m_origin_x - m_res), :524
+    ctx->grid.oy = origin[1] - res;
+    ctx->grid.oz = origin[2] - res;
+    ctx->res = res;
+    ctx->padding = padding;
+    ctx->dmax_sq = dmax_sq;
+    memcpy(ctx->origin, origin, 3 * sizeof(double));
+    return 0;
+}
+
+int smplgpu_set_distance_field(smplgpu_ctx* ctx, const uint16_t* d2, int nx, int ny, int nz,
+                               const double origin[3], double res, int dmax_sq, double padding)
+{
+    if (!ctx || !d2 || !origin) return SMPLGPU_ERR_INVALID;
+    int r = set_df_common(ctx, nx, ny, nz, origin, res, dmax_sq, padding);
+    if (r) return r;
+    CU(cudaMemcpyAsync(ctx->d_df, d2, ctx->df_cells * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->has_df = true;
+    return ctx->has_robot ? upload_model(ctx) : 0;
+}
+
+int smplgpu_set_distance_field_dev(smplgpu_ctx* ctx, const uint16_t* d2_dev, int nx, int ny, int nz,
+                                   const double origin[3], double res, int dmax_sq, double padding)
+{
+    if (!ctx || !d2_dev || !origin) return SMPLGPU_ERR_INVALID;
+    int r = set_df_common(ctx, nx, ny, nz, origin, res, dmax_sq, padding);
+    if (r) return r;
+    if (d2_dev != ctx->d_df) {
+        CU(cudaMemcpyAsync(ctx->d_df, d2_dev, ctx->df_cells * sizeof(uint16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->has_df = true;
+    return ctx->has_robot ? upload_model(ctx) : 0;
+}
+
+int smplgpu_build_distance_field(smplgpu_ctx* ctx, const int32_t* cells_xyz, int n_cells,
+                                 int nx, int ny, int nz, const double origin[3], double res,
+                                 double max_dist, double padding)
+{
+    if (!ctx || !origin || n_cells < 0 || (n_cells > 0 && !cells_xyz)) return SMPLGPU_ERR_INVALID;
+    // m_dmax_int((int)std::ceil(m_max_dist * m_inv_res)), distance_map.hpp:125-126
+    const double inv_res = 1.0 / res;
+    const int dmax = (int)std::ceil(max_dist * inv_res);
+    const int dmax_sq = dmax * dmax;
+    int r = set_df_common(ctx, nx, ny, nz, origin, res, dmax_sq, padding);
+    if (r) return r;
+    const size_t cells = ctx->df_cells;
+    // scratch: occupancy bytes + two u16 planes + the cell list
+    const size_t need = cells + 2 * cells * sizeof(uint16_t) + (size_t)n_cells * 3 * sizeof(int) + 64;
+    r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, need);
+    if (r) return r;
+    uint8_t* occ = (uint8_t*)ctx->d_misc;
+    uint16_t* g1 = (uint16_t*)(occ + ((cells + 15) / 16) * 16);
+    uint16_t* g2 = g1 + cells;
+    int* d_cells = (int*)(g2 + cells + (cells & 1));
+    CU(cudaMemsetAsync(occ, 0, cells, ctx->stream));
+    if (n_cells > 0) {
+        CU(cudaMemcpyAsync(d_cells, cells_xyz, (size_t)n_cells * 3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        edt_scatter_kernel<<<(n_cells + 255) / 256, 256, 0, ctx->stream>>>(d_cells, n_cells, nx, ny, nz, occ);
+        ++ctx->launches;
+    }
+    edt_pass_z_kernel<<<(nx * ny + 127) / 128, 128, 0, ctx->stream>>>(occ, nx, ny, nz, dmax, g1);
+    const unsigned blocks = (unsigned)((cells + 255) / 256);
+    edt_pass_axis_kernel<<<blocks, 256, 0, ctx->stream>>>(g1, nx, ny, nz, 1, dmax, dmax_sq, true, g2);
+    edt_pass_axis_kernel<<<blocks, 256, 0, ctx->stream>>>(g2, nx, ny, nz, 0, dmax, dmax_sq, false, ctx->d_df);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->has_df = true;
+    return ctx->has_robot ? upload_model(ctx) : 0;
+}
+
+int smplgpu_download_distance_field(smplgpu_ctx* ctx, uint16_t* out)
+{
+    if (!ctx || !out) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "no distance field");
+    CU(cudaMemcpyAsync(out, ctx->d_df, ctx->df_cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int smplgpu_distance_field_dev_ptr(smplgpu_ctx* ctx, void** ptr, int64_t* bytes)
+{
+    if (!ctx || !ptr || !bytes) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "no distance field");
+    *ptr = ctx->d_df;
+    *bytes = (int64_t)(ctx->df_cells * sizeof(uint16_t));
+    return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// validity
+///////////////////////////////////////////////////////////////////////////////
+
+static int need_scene(smplgpu_ctx* ctx)
+{
+    if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set (smplgpu_set_robot)");
+    if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "distance field not set");
+    return 0;
+}
+
+static size_t validity_smem(const smplgpu_ctx* ctx)
+{
+    return (size_t)ctx->h_model->n_slots * 12 * sizeof(double) * VALIDITY_THREADS;
+}
+
+int smplgpu_is_states_valid_dev(smplgpu_ctx* ctx, const double* q_dev, int n, uint8_t* verdict_dev)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (n == 0) return 0;
+    if (!q_dev || !verdict_dev) return fail(ctx, SMPLGPU_ERR_INVALID, "null device pointer");
+    CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    const int blocks = (n + VALIDITY_THREADS - 1) / VALIDITY_THREADS;
+    states_valid_kernel<<<blocks, VALIDITY_THREADS, validity_smem(ctx), ctx->stream>>>(
+        ctx->d_model, ctx->d_df, ctx->grid, q_dev, n, verdict_dev, ctx->d_stats);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int smplgpu_is_edges_valid_dev(smplgpu_ctx* ctx, const double* q0_dev, const double* q1_dev, int n,
+                               uint8_t* verdict_dev, int32_t* counts_dev)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (n == 0) return 0;
+    if (!q0_dev || !q1_dev || !verdict_dev) return fail(ctx, SMPLGPU_ERR_INVALID, "null device pointer");
+    CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    const int blocks = (n + VALIDITY_THREADS - 1) / VALIDITY_THREADS;
+    edges_valid_kernel<<<blocks, VALIDITY_THREADS, validity_smem(ctx), ctx->stream>>>(
+        ctx->d_model, ctx->d_df, ctx->grid, q0_dev, q1_dev, n, verdict_dev, counts_dev, ctx->d_stats);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Host-pointer entry points: chunked, double-buffered through pinned memory so
+// the host->pinned copy of chunk k+1 overlaps the H2D/kernel/D2H of chunk k.
+static int run_host_batched(smplgpu_ctx* ctx, const double* q0, const double* q1, int n,
+                            uint8_t* verdict, int32_t* counts)
+{
+    const int dof = ctx->h_model->dof;
+    const bool edges = q1 != nullptr;
+    const int chunk = 1 << 18;
+    const int cn = std::min(n, chunk);
+    int r = ensure_state_buffers(ctx, (size_t)cn * 2, dof, edges); // two chunks in flight
+    if (r) return r;
+    const size_t row = (size_t)dof * sizeof(double);
+    const size_t in_bytes = (size_t)cn * row * (edges ? 2 : 1);
+    const size_t out_bytes = (size_t)cn * (1 + (counts ? sizeof(int) : 0));
+    r = grow_pinned(ctx, ctx->pinned, &ctx->pinned_cap, in_bytes);
+    if (r) return r;
+    r = grow_pinned(ctx, ctx->pinned_out, &ctx->pinned_out_cap, out_bytes + 16);
+    if (r) return r;
+    CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+
+    const int nchunks = (n + chunk - 1) / chunk;
+    auto drain = [&](int c) -> int {
+        const int b = c & 1;
+        const int off = c * chunk;
+        const int m = std::min(chunk, n - off);
+        CU(cudaEventSynchronize(ctx->ev[b]));
+        memcpy(verdict + off, ctx->pinned_out[b], (size_t)m);
+        if (counts) {
+            memcpy(counts + off, (uint8_t*)ctx->pinned_out[b] + (((size_t)m + 15) / 16) * 16, (size_t)m * sizeof(int));
+        }
+        return 0;
+    };
+    for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1;
+        const int off = c * chunk;
+        const int m = std::min(chunk, n - off);
+        if (c >= 2) {
+            r = drain(c - 2);
+            if (r) return r;
+        }
+        double* dq0 = ctx->d_q0 + (size_t)b * cn * dof;
+        double* dq1 = ctx->d_q1 + (size_t)b * cn * dof;
+        uint8_t* dv = ctx->d_verdict + (size_t)b * cn;
+        int* dc = ctx->d_counts + (size_t)b * cn;
+        uint8_t* pin = (uint8_t*)ctx->pinned[b];
+        memcpy(pin, q0 + (size_t)off * dof, (size_t)m * row);
+        CU(cudaMemcpyAsync(dq0, pin, (size_t)m * row, cudaMemcpyHostToDevice, ctx->stream));
+        if (edges) {
+            memcpy(pin + (size_t)cn * row, q1 + (size_t)off * dof, (size_t)m * row);
+            CU(cudaMemcpyAsync(dq1, pin + (size_t)cn * row, (size_t)m * row, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        const int blocks = (m + VALIDITY_THREADS - 1) / VALIDITY_THREADS;
+        if (edges) {
+            edges_valid_kernel<<<blocks, VALIDITY_THREADS, validity_smem(ctx), ctx->stream>>>(
+                ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, m, dv, counts ? dc : nullptr, ctx->d_stats);
+        } else {
+            states_valid_kernel<<<blocks, VALIDITY_THREADS, validity_smem(ctx), ctx->stream>>>(
+                ctx->d_model, ctx->d_df, ctx->grid, dq0, m, dv, ctx->d_stats);
+        }
+        ++ctx->launches;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(ctx->pinned_out[b], dv, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (counts) {
+            CU(cudaMemcpyAsync((uint8_t*)ctx->pinned_out[b] + (((size_t)m + 15) / 16) * 16, dc, (size_t)m * sizeof(int),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CU(cudaEventRecord(ctx->ev[b], ctx->stream));
+    }
+    for (int c = std::max(0, nchunks - 2); c < nchunks; ++c) {
+        r = drain(c);
+        if (r) return r;
+    }
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int smplgpu_is_states_valid(smplgpu_ctx* ctx, const double* q, int n, uint8_t* verdict)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (n == 0) return 0;
+    if (!q || !verdict) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    return run_host_batched(ctx, q, nullptr, n, verdict, nullptr);
+}
+
+int smplgpu_is_edges_valid(smplgpu_ctx* ctx, const double* q0, const double* q1, int n,
+                           uint8_t* verdict, int32_t* waypoint_counts)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (n == 0) return 0;
+    if (!q0 || !q1 || !verdict) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    return run_host_batched(ctx, q0, q1, n, verdict, waypoint_counts);
+}
+
+int smplgpu_last_validity_stats(smplgpu_ctx* ctx, int64_t* df_lookups, int64_t* pair_tests, int64_t* waypoints)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (df_lookups) *df_lookups = (int64_t)ctx->h_stats[0];
+    if (pair_tests) *pair_tests = (int64_t)ctx->h_stats[1];
+    if (waypoints) *waypoints = (int64_t)ctx->h_stats[2];
+    return 0;
+}
+
+int smplgpu_fk_sphere_centers(smplgpu_ctx* ctx, const double* q, int n, double* out)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set");
+    if (n == 0) return 0;
+    if (!q || !out) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    const int dof = ctx->h_model->dof, nn = ctx->h_model->n_nodes;
+    const size_t qb = (size_t)n * dof * sizeof(double), ob = (size_t)n * nn * 3 * sizeof(double);
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, qb + ob + 64);
+    if (r) return r;
+    double* dq = (double*)ctx->d_misc;
+    double* dout = dq + (size_t)n * dof;
+    CU(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, ctx->stream));
+    fk_centers_kernel<<<(n + VALIDITY_THREADS - 1) / VALIDITY_THREADS, VALIDITY_THREADS, validity_smem(ctx), ctx->stream>>>(
+        ctx->d_model, dq, n, dout);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int smplgpu_check_joint_limits(smplgpu_ctx* ctx, const double* q, int n, uint8_t* ok)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set");
+    if (n == 0) return 0;
+    if (!q || !ok) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    const int dof = ctx->h_model->dof;
+    const size_t qb = (size_t)n * dof * sizeof(double);
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, qb + n + 64);
+    if (r) return r;
+    double* dq = (double*)ctx->d_misc;
+    uint8_t* dok = (uint8_t*)(dq + (size_t)n * dof);
+    CU(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, ctx->stream));
+    joint_limits_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_model, dq, n, dok);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// BFS
+///////////////////////////////////////////////////////////////////////////////
+
+static int alloc_bfs(smplgpu_ctx* ctx, int nx, int ny, int nz)
+{
+    if (nx <= 0 || ny <= 0 || nz <= 0) return fail(ctx, SMPLGPU_ERR_INVALID, "bad BFS dimensions");
+    if ((long long)(nx + 2) * (ny + 2) * (nz + 2) > 0x7FFFFFFFLL) return fail(ctx, SMPLGPU_ERR_LIMIT, "BFS grid too large for int nodes");
+    if (ctx->has_bfs && ctx->bfs.nx == nx && ctx->bfs.ny == ny && ctx->bfs.nz == nz) {
+        return 0;
+    }
+    free_bfs(ctx);
+    BfsGrid& g = ctx->bfs;
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.DX = nx + 2; g.DY = ny + 2; g.DZ = nz + 2;
+    g.W = ((g.DX + 31) / 32 + 3) / 4 * 4;
+    g.rows = g.DY * g.DZ;
+    ctx->bfs_words = (size_t)g.rows * g.W;
+    ctx->bfs_cells = (size_t)g.rows * g.DX;
+    const size_t wb = ctx->bfs_words * sizeof(uint32_t);
+    CU(cudaMalloc(&g.wall, wb));
+    CU(cudaMalloc(&g.blocked, wb));
+    CU(cudaMalloc(&g.front[0], wb));
+    CU(cudaMalloc(&g.front[1], wb));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&g.row_stamp[i], (size_t)g.rows * sizeof(uint32_t)));
+        CU(cudaMalloc(&g.cand_stamp[i], (size_t)g.rows * sizeof(uint32_t)));
+    }
+    // +32 ints of slack: the reset kernel writes whole 32-cell words' worth only up to DX, no overrun
+    CU(cudaMalloc(&g.dist, ctx->bfs_cells * sizeof(int)));
+    CU(cudaMalloc(&g.ctrl, 8 * sizeof(int)));
+    ctx->has_bfs = true;
+    return 0;
+}
+
+int smplgpu_bfs_set_walls_dev(smplgpu_ctx* ctx, int nx, int ny, int nz, const uint8_t* walls_dev)
+{
+    if (!ctx || !walls_dev) return SMPLGPU_ERR_INVALID;
+    int r = alloc_bfs(ctx, nx, ny, nz);
+    if (r) return r;
+    const int total = (int)ctx->bfs_words;
+    bfs_walls_from_bytes_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->bfs, walls_dev);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int smplgpu_bfs_set_walls(smplgpu_ctx* ctx, int nx, int ny, int nz, const uint8_t* walls)
+{
+    if (!ctx || !walls) return SMPLGPU_ERR_INVALID;
+    const size_t n = (size_t)nx * ny * nz;
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, n);
+    if (r) return r;
+    CU(cudaMemcpyAsync(ctx->d_misc, walls, n, cudaMemcpyHostToDevice, ctx->stream));
+    r = smplgpu_bfs_set_walls_dev(ctx, nx, ny, nz, (const uint8_t*)ctx->d_misc);
+    if (r) return r;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int smplgpu_bfs_set_walls_from_df(smplgpu_ctx* ctx, double inflation_radius)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "distance field not set");
+    int r = alloc_bfs(ctx, ctx->grid.nx, ctx->grid.ny, ctx->grid.nz);
+    if (r) return r;
+    // largest d2 with res*sqrt(d2) <= radius  (grid()->getDistance(x,y,z) <= radius, bfs_heuristic.cpp:343)
+    int kmax = -1;
+    for (int k = 0; k <= ctx->dmax_sq; ++k) {
+        if (ctx->res * std::sqrt((double)k) <= inflation_radius) {
+            kmax = k;
+        } else {
+            break;
+        }
+    }
+    unsigned int* d_count = (unsigned int*)ctx->d_seed_count;
+    CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), ctx->stream));
+    const int total = (int)ctx->bfs_words;
+    bfs_walls_from_df_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->bfs, ctx->d_df, kmax, d_count);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    unsigned int count = 0;
+    CU(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return (int)count;
+}
+
+int smplgpu_bfs_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz, int n_seeds)
+{
+    if (!ctx || n_seeds < 0 || (n_seeds > 0 && !seeds_xyz)) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_bfs) return fail(ctx, SMPLGPU_ERR_STATE, "BFS walls not set");
+    BfsGrid& g = ctx->bfs;
+    const int total = (int)ctx->bfs_words;
+    bfs_reset_kernel<<<(std::max(total, g.rows) + 255) / 256, 256, 0, ctx->stream>>>(g);
+    ++ctx->launches;
+    int in_bounds = 0;
+    if (n_seeds > 0) {
+        int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, (size_t)n_seeds * 3 * sizeof(int));
+        if (r) return r;
+        CU(cudaMemcpyAsync(ctx->d_misc, seeds_xyz, (size_t)n_seeds * 3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_seed_count, 0, sizeof(int), ctx->stream));
+        bfs_seed_kernel<<<(n_seeds + 127) / 128, 128, 0, ctx->stream>>>(g, (const int*)ctx->d_misc, n_seeds, ctx->d_seed_count);
+        ++ctx->launches;
+        CU(cudaMemcpyAsync(&in_bounds, ctx->d_seed_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->bfs_levels = 0;
+    if (in_bounds > 0) {
+        // persistent cooperative kernel: as many co-resident 1024-thread blocks as fit
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_levels_kernel, 1024, 0));
+        if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS kernel does not fit an SM");
+        int blocks = ctx->sm_count * per_sm;
+        const int want = (g.rows + 32 * 32 - 1) / (32 * 32);
+        blocks = std::max(1, std::min(blocks, want));
+        int max_levels = g.nx + g.ny + g.nz; // upper bound is the free-cell count; cap generously below
+        long long cap = (long long)g.nx * g.ny * g.nz;
+        max_levels = (int)std::min<long long>(cap, 0x7FFFFFF0LL);
+        void* args[] = { (void*)&g, (void*)&max_levels };
+        CU(cudaLaunchCooperativeKernel((void*)bfs_levels_kernel, dim3(blocks), dim3(1024), args, 0, ctx->stream));
+        ++ctx->launches;
+        CU(cudaMemcpyAsync(&ctx->bfs_levels, g.ctrl, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return in_bounds;
+}
+
+int smplgpu_bfs_distances(smplgpu_ctx* ctx, const int32_t* cells_xyz, int n, int32_t* out)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_bfs) return fail(ctx, SMPLGPU_ERR_STATE, "BFS walls not set");
+    if (n == 0) return 0;
+    if (!cells_xyz || !out) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, (size_t)n * 4 * sizeof(int));
+    if (r) return r;
+    int* dc = (int*)ctx->d_misc;
+    int* dout = dc + (size_t)n * 3;
+    CU(cudaMemcpyAsync(dc, cells_xyz, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    bfs_gather_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->bfs, dc, n, dout);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int smplgpu_bfs_download(smplgpu_ctx* ctx, int32_t* padded_grid)
+{
+    if (!ctx || !padded_grid) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_bfs) return fail(ctx, SMPLGPU_ERR_STATE, "BFS walls not set");
+    CU(cudaMemcpyAsync(padded_grid, ctx->bfs.dist, ctx->bfs_cells * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int smplgpu_bfs_dims(smplgpu_ctx* ctx, int32_t dims[3])
+{
+    if (!ctx || !dims) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_bfs) return fail(ctx, SMPLGPU_ERR_STATE, "BFS walls not set");
+    dims[0] = ctx->bfs.nx; dims[1] = ctx->bfs.ny; dims[2] = ctx->bfs.nz;
+    return 0;
+}
+
+int smplgpu_bfs_last_levels(smplgpu_ctx* ctx) { return ctx ? ctx->bfs_levels : SMPLGPU_ERR_INVALID; }
+
+///////////////////////////////////////////////////////////////////////////////
+// heuristic
+///////////////////////////////////////////////////////////////////////////////
+
+int smplgpu_goal_heuristics_dev(smplgpu_ctx* ctx, const double* q_dev, int n, int cost_per_cell, int32_t* h_dev)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set");
+    if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "distance field (grid geometry) not set");
+    if (!ctx->has_bfs) return fail(ctx, SMPLGPU_ERR_STATE, "BFS walls not set");
+    if (n == 0) return 0;
+    if (!q_dev || !h_dev) return fail(ctx, SMPLGPU_ERR_INVALID, "null device pointer");
+    goal_heuristic_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(
+        ctx->d_model, ctx->grid, ctx->bfs.dist, ctx->bfs.DX, ctx->bfs.DY, ctx->bfs.DZ, q_dev, n, cost_per_cell, h_dev);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int smplgpu_goal_heuristics(smplgpu_ctx* ctx, const double* q, int n, int cost_per_cell, int32_t* h)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set");
+    if (n == 0) return 0;
+    if (!q || !h) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    const int dof = ctx->h_model->dof;
+    const size_t qb = (size_t)n * dof * sizeof(double);
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, qb + (size_t)n * sizeof(int) + 64);
+    if (r) return r;
+    double* dq = (double*)ctx->d_misc;
+    int* dh = (int*)(dq + (size_t)n * dof);
+    CU(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, ctx->stream));
+    r = smplgpu_goal_heuristics_dev(ctx, dq, n, cost_per_cell, dh);
+    if (r) return r;
+    CU(cudaMemcpyAsync(h, dh, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int smplgpu_planning_frame_fk(smplgpu_ctx* ctx, const double* q, int n, double* pose6)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set");
+    if (n == 0) return 0;
+    if (!q || !pose6) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    const int dof = ctx->h_model->dof;
+    const size_t qb = (size_t)n * dof * sizeof(double), ob = (size_t)n * 6 * sizeof(double);
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, qb + ob + 64);
+    if (r) return r;
+    double* dq = (double*)ctx->d_misc;
+    double* dout = dq + (size_t)n * dof;
+    CU(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, ctx->stream));
+    planning_fk_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_model, dq, n, dout);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pose6, dout, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,472 @@
+// Kernels (1)+(2)+(3): batched forward kinematics -> sphere tree vs distance
+// field -> self-collision sphere pairs, fused; one thread per state (or edge),
+// IEEE double throughout, compiled with --fmad=false so every product and sum
+// rounds exactly like the reference's x86-64 build (no FMA contraction).
+//
+// Reference semantics restated (file:line under dyouakim/smpl):
+//   joint transforms      sbpl_collision_checking/src/transform_functions.h:95-258
+//   link transform        include/sbpl_collision_checking/robot_collision_state.h:385-431
+//   sphere position       robot_collision_state.h:560-581
+//   sphere vs field       src/collision_operations.h:68-77, 105-165
+//   field lookup          smpl/include/smpl/distance_map/detail/distance_map.hpp:281-300, 520-536
+//   sphere pairs + ACM    src/self_collision_model.cpp:1093-1218
+//   edge interpolation    src/collision_space.cpp:538-581,
+//                         include/.../robot_motion_collision_model.h:173-181, 224-249, 297-321, 352-366
+//                         src/robot_motion_collision_model.cpp:371-407; smpl/angles.h:45-99
+#pragma once
+
+#include "model.cuh"
+
+namespace smplgpu {
+
+constexpr int VALIDITY_THREADS = 128;
+
+struct Xf { double m[12]; }; // row-major 3x4
+
+__device__ __forceinline__ double dot3(double a0, double b0, double a1, double b1, double a2, double b2)
+{
+    return (a0 * b0 + a1 * b1) + a2 * b2;
+}
+
+// Eigen Affine3d * Affine3d: linear = L1*L2, translation = L1*t2 + t1
+__device__ __forceinline__ void xf_mul(const Xf& a, const Xf& b, Xf& r)
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            r.m[4 * i + j] = dot3(a.m[4 * i], b.m[j], a.m[4 * i + 1], b.m[4 + j], a.m[4 * i + 2], b.m[8 + j]);
+        }
+        r.m[4 * i + 3] = dot3(a.m[4 * i], b.m[3], a.m[4 * i + 1], b.m[7], a.m[4 * i + 2], b.m[11]) + a.m[4 * i + 3];
+    }
+}
+
+__device__ __forceinline__ void xf_point(const Xf& a, double x, double y, double z, double& px, double& py, double& pz)
+{
+    px = dot3(a.m[0], x, a.m[1], y, a.m[2], z) + a.m[3];
+    py = dot3(a.m[4], x, a.m[5], y, a.m[6], z) + a.m[7];
+    pz = dot3(a.m[8], x, a.m[9], y, a.m[10], z) + a.m[11];
+}
+
+// smpl/angles.h:45-62
+__device__ __forceinline__ double normalize_angle(double angle)
+{
+    const double PI = 3.14159265358979323846;
+    if (fabs(angle) > 2.0 * PI) {
+        angle = fmod(angle, 2.0 * PI);
+    }
+    if (angle < -PI) {
+        angle += 2.0 * PI;
+    }
+    if (angle > PI) {
+        angle -= 2.0 * PI;
+    }
+    return angle;
+}
+
+// Eigen::AngleAxisd(angle, axis).toRotationMatrix() as a 3x4 with zero translation
+__device__ __forceinline__ void angle_axis(double angle, double ax, double ay, double az, Xf& r)
+{
+    double s, c;
+    sincos(angle, &s, &c);
+    const double sx = s * ax, sy = s * ay, sz = s * az;
+    const double k = 1.0 - c;
+    const double cx = k * ax, cy = k * ay, cz = k * az;
+    double tmp;
+    tmp = cx * ay;
+    r.m[1] = tmp - sz;
+    r.m[4] = tmp + sz;
+    tmp = cx * az;
+    r.m[2] = tmp + sy;
+    r.m[8] = tmp - sy;
+    tmp = cy * az;
+    r.m[6] = tmp - sx;
+    r.m[9] = tmp + sx;
+    r.m[0] = cx * ax + c;
+    r.m[5] = cy * ay + c;
+    r.m[10] = cz * az + c;
+    r.m[3] = 0.0;
+    r.m[7] = 0.0;
+    r.m[11] = 0.0;
+}
+
+// transform_functions.h:95-258
+__device__ __forceinline__ void joint_transform(const DevModel* __restrict__ M, int l, double val, Xf& t)
+{
+    const double* o = M->link_origin[l];
+    const int fn = M->link_joint[l];
+    if (fn == 0) { // fixed
+#pragma unroll
+        for (int i = 0; i < 12; ++i) t.m[i] = o[i];
+    } else if (fn <= 3) {
+        double sth, cth;
+        sincos(val, &sth, &cth);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double o0 = o[4 * r], o1 = o[4 * r + 1], o2 = o[4 * r + 2];
+            double t0, t1, t2;
+            if (fn == 1) {          // X
+                t0 = o0;
+                t1 = cth * o1 + sth * o2;
+                t2 = cth * o2 - sth * o1;
+            } else if (fn == 2) {   // Y
+                t0 = cth * o0 - sth * o2;
+                t1 = o1;
+                t2 = sth * o0 + cth * o2;
+            } else {                // Z
+                t0 = o0 * cth + o1 * sth;
+                t1 = o1 * cth - o0 * sth;
+                t2 = o2;
+            }
+            t.m[4 * r] = t0;
+            t.m[4 * r + 1] = t1;
+            t.m[4 * r + 2] = t2;
+            t.m[4 * r + 3] = o[4 * r + 3];
+        }
+    } else if (fn == 4) { // origin * AngleAxis(q, axis)
+        Xf a, oo;
+        angle_axis(val, M->link_axis[l][0], M->link_axis[l][1], M->link_axis[l][2], a);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) oo.m[i] = o[i];
+        xf_mul(oo, a, t);
+    } else { // prismatic: origin * Translate(0, 0, q)
+        Xf a, oo;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { oo.m[i] = o[i]; a.m[i] = 0.0; }
+        a.m[0] = 1.0; a.m[5] = 1.0; a.m[10] = 1.0; a.m[11] = val;
+        xf_mul(oo, a, t);
+    }
+}
+
+// DistanceMap::worldToGrid + isCellValid + cell d2 (0 when outside)
+__device__ __forceinline__ int df_lookup(const uint16_t* __restrict__ df, const GridParams& G, double x, double y, double z)
+{
+    const int gx = __double2int_rz(G.inv_res * (x - G.ox) + 0.5) - 1;
+    const int gy = __double2int_rz(G.inv_res * (y - G.oy) + 0.5) - 1;
+    const int gz = __double2int_rz(G.inv_res * (z - G.oz) + 0.5) - 1;
+    if ((unsigned)gx >= (unsigned)G.nx || (unsigned)gy >= (unsigned)G.ny || (unsigned)gz >= (unsigned)G.nz) {
+        return 0;
+    }
+    return (int)__ldg(&df[((size_t)gx * G.ny + gy) * G.nz + gz]);
+}
+
+struct Counters { unsigned int lookups, pairs, waypoints; };
+
+// per-thread slot storage in shared memory: element e of slot s of thread t
+// lives at smem[(s * 12 + e) * blockDim + t]  (conflict-free for a warp)
+__device__ __forceinline__ void slot_store(double* smem, int slot, const Xf& t)
+{
+    double* p = smem + (size_t)slot * 12 * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) p[e * blockDim.x] = t.m[e];
+}
+
+__device__ __forceinline__ void slot_load(const double* smem, int slot, Xf& t)
+{
+    const double* p = smem + (size_t)slot * 12 * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) t.m[e] = p[e * blockDim.x];
+}
+
+__device__ __forceinline__ void node_pos(const DevModel* __restrict__ M, const double* smem, int node,
+                                         double& x, double& y, double& z)
+{
+    Xf t;
+    slot_load(smem, M->link_slot[M->node_link[node]], t);
+    xf_point(t, M->node_center[node][0], M->node_center[node][1], M->node_center[node][2], x, y, z);
+}
+
+// One state: FK, sphere trees vs field (inline, while T_link is in registers),
+// then tree pairs.  Returns true when the state is valid.
+//   qa/qb/alpha: state value of planning variable v is
+//       qb == nullptr ? qa[v] : qa[v] + alpha * diff(v)     (MotionInterpolation::interpolate)
+__device__ bool check_state(const DevModel* __restrict__ M, const uint16_t* __restrict__ df, const GridParams& G,
+                            const double* __restrict__ qa, const double* __restrict__ qb, double alpha,
+                            double* smem, Counters& cnt)
+{
+    Xf T;  // transform of the previously processed link
+    int stack[MAX_TREE_DEPTH];
+
+    const int nl = M->n_links;
+    for (int l = 0; l < nl; ++l) {
+        // joint value
+        double val;
+        const int v = M->link_var[l];
+        if (v >= 0) {
+            const double a = qa[v];
+            if (qb != nullptr) {
+                const double b = qb[v];
+                const double diff = (M->var_type[v] == 1) ? normalize_angle(b - a) : (b - a);
+                val = a + alpha * diff;
+            } else {
+                val = a;
+            }
+        } else {
+            val = M->link_const[l];
+        }
+
+        Xf J, P;
+        joint_transform(M, l, val, J);
+        const int p = M->link_parent[l];
+        if (p < 0) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) P.m[i] = M->link_base[l][i];
+        } else if (p == l - 1) {
+            P = T;
+        } else {
+            slot_load(smem, M->link_slot[p], P);
+        }
+        xf_mul(P, J, T);
+        const int slot = M->link_slot[l];
+        if (slot >= 0) {
+            slot_store(smem, slot, T);
+        }
+
+        // sphere trees rooted on this link vs the distance field
+        for (int ti = M->link_tree_begin[l]; ti < M->link_tree_end[l]; ++ti) {
+            int sp = 0;
+            stack[sp++] = M->tree_root[M->tree_by_link[ti]];
+            while (sp > 0) {
+                const int node = stack[--sp];
+                double x, y, z;
+                xf_point(T, M->node_center[node][0], M->node_center[node][1], M->node_center[node][2], x, y, z);
+                ++cnt.lookups;
+                const int d2 = df_lookup(df, G, x, y, z);
+                if (d2 >= M->node_thresh[node]) {
+                    continue;
+                }
+                const int left = M->node_left[node];
+                if (left < 0) {
+                    return false; // failing leaf
+                }
+                stack[sp++] = left;
+                stack[sp++] = M->node_right[node];
+            }
+        }
+    }
+
+    // sphere-tree pairs
+    const int np = M->n_pairs;
+    for (int pi = 0; pi < np; ++pi) {
+        int sp = 0;
+        stack[sp++] = (M->tree_root[M->pair_a[pi]] << 16) | M->tree_root[M->pair_b[pi]];
+        while (sp > 0) {
+            const int packed = stack[--sp];
+            const int n1 = packed >> 16, n2 = packed & 0xFFFF;
+            double x1, y1, z1, x2, y2, z2;
+            node_pos(M, smem, n1, x1, y1, z1);
+            node_pos(M, smem, n2, x2, y2, z2);
+            ++cnt.pairs;
+            const double dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+            const double cd2 = (dx * dx + dy * dy) + dz * dz;
+            const double r1 = M->node_radius[n1], r2 = M->node_radius[n2];
+            const double rr = r1 + r2;
+            if (cd2 > rr * rr) {
+                continue;
+            }
+            const int l1 = M->node_left[n1], l2 = M->node_left[n2];
+            if (l1 < 0 && l2 < 0) {
+                bool allowed = false;
+                for (int k = 0; k < M->n_allowed; ++k) {
+                    const int a = M->allowed_a[k], b = M->allowed_b[k];
+                    allowed |= (a == n1 && b == n2) || (a == n2 && b == n1);
+                }
+                if (!allowed) {
+                    return false;
+                }
+                continue;
+            }
+            bool split1;
+            if (l1 < 0) {
+                split1 = false;
+            } else if (l2 < 0) {
+                split1 = true;
+            } else {
+                split1 = r1 > r2;
+            }
+            if (split1) {
+                stack[sp++] = (l1 << 16) | n2;
+                stack[sp++] = (M->node_right[n1] << 16) | n2;
+            } else {
+                stack[sp++] = (n1 << 16) | l2;
+                stack[sp++] = (n1 << 16) | M->node_right[n2];
+            }
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ void flush_counters(const Counters& c, unsigned long long* stats)
+{
+    if (stats == nullptr) {
+        return;
+    }
+    unsigned int a = c.lookups, b = c.pairs, w = c.waypoints;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        w += __shfl_xor_sync(0xffffffffu, w, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats[0], (unsigned long long)a);
+        atomicAdd(&stats[1], (unsigned long long)b);
+        atomicAdd(&stats[2], (unsigned long long)w);
+    }
+}
+
+// CollisionSpace::isStateValid, batched
+__global__ void __launch_bounds__(VALIDITY_THREADS)
+states_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ df, GridParams G,
+                    const double* __restrict__ q, int n, uint8_t* __restrict__ verdict,
+                    unsigned long long* stats)
+{
+    extern __shared__ double smem[];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters cnt = { 0u, 0u, 0u };
+    if (i < n) {
+        cnt.waypoints = 1;
+        const bool ok = check_state(M, df, G, q + (size_t)i * M->dof, nullptr, 0.0, smem, cnt);
+        verdict[i] = ok ? 1 : 0;
+    }
+    flush_counters(cnt, stats);
+}
+
+// CollisionSpace::isStateToStateValid, batched: waypoint generation on the device
+__global__ void __launch_bounds__(VALIDITY_THREADS)
+edges_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ df, GridParams G,
+                   const double* __restrict__ q0, const double* __restrict__ q1, int n,
+                   uint8_t* __restrict__ verdict, int* __restrict__ counts, unsigned long long* stats)
+{
+    extern __shared__ double smem[];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters cnt = { 0u, 0u, 0u };
+    if (i < n) {
+        const int dof = M->dof;
+        const double* a = q0 + (size_t)i * dof;
+        const double* b = q1 + (size_t)i * dof;
+        // RobotMotionCollisionModel::getMaxSphereMotion(start, finish, variables)
+        double motion = 0.0;
+        for (int v = 0; v < dof; ++v) {
+            const int ty = M->var_type[v];
+            double dist;
+            if (ty == 1) {          // continuous
+                dist = fabs(normalize_angle(b[v] - a[v]));
+                motion += M->var_weight[v] * dist;
+            } else if (ty == 0) {   // revolute
+                dist = fabs(b[v] - a[v]);
+                motion += M->var_weight[v] * dist;
+            } else {                // prismatic
+                dist = fabs(b[v] - a[v]);
+                motion += dist;
+            }
+        }
+        // fillMotionInterpolation + setWaypointCount
+        int count = 0;
+        if (motion != 0.0) {
+            count = max(2, (int)ceil(motion / 0.05) + 1);
+        }
+        if (counts != nullptr) {
+            counts[i] = count;
+        }
+        bool ok = true;
+        if (count > 0) {
+            const double inv = 1.0 / (double)(count - 1);
+            const int inc_cc = 5;
+            if (count > inc_cc) {
+                for (int s = 0; s < inc_cc && ok; ++s) {
+                    for (int j = s; j < count && ok; j += inc_cc) {
+                        ++cnt.waypoints;
+                        ok = check_state(M, df, G, a, b, (double)j * inv, smem, cnt);
+                    }
+                }
+            } else {
+                for (int j = 0; j < count && ok; ++j) {
+                    ++cnt.waypoints;
+                    ok = check_state(M, df, G, a, b, (double)j * inv, smem, cnt);
+                }
+            }
+        }
+        verdict[i] = ok ? 1 : 0;
+    }
+    flush_counters(cnt, stats);
+}
+
+// Kernel (1) alone: sphere centres of every tree node, out[n][n_nodes][3]
+__global__ void __launch_bounds__(VALIDITY_THREADS)
+fk_centers_kernel(const DevModel* __restrict__ M, const double* __restrict__ q, int n, double* __restrict__ out)
+{
+    extern __shared__ double smem[];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const double* qa = q + (size_t)i * M->dof;
+    Xf T;
+    for (int l = 0; l < M->n_links; ++l) {
+        const int v = M->link_var[l];
+        const double val = v >= 0 ? qa[v] : M->link_const[l];
+        Xf J, P;
+        joint_transform(M, l, val, J);
+        const int p = M->link_parent[l];
+        if (p < 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) P.m[k] = M->link_base[l][k];
+        } else if (p == l - 1) {
+            P = T;
+        } else {
+            slot_load(smem, M->link_slot[p], P);
+        }
+        xf_mul(P, J, T);
+        if (M->link_slot[l] >= 0) {
+            slot_store(smem, M->link_slot[l], T);
+        }
+        // every node on this link
+        for (int node = 0; node < M->n_nodes; ++node) {
+            if (M->node_link[node] == l) {
+                double x, y, z;
+                xf_point(T, M->node_center[node][0], M->node_center[node][1], M->node_center[node][2], x, y, z);
+                double* o = out + ((size_t)i * M->n_nodes + node) * 3;
+                o[0] = x; o[1] = y; o[2] = z;
+            }
+        }
+    }
+}
+
+// KDLRobotModel::checkJointLimits (kdl_robot_model.cpp:173-189, 210-235, 326-337)
+__global__ void joint_limits_kernel(const DevModel* __restrict__ M, const double* __restrict__ q, int n,
+                                    uint8_t* __restrict__ ok)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const double PI = 3.14159265358979323846;
+    const int dof = M->dof;
+    bool good = true;
+    for (int v = 0; v < dof; ++v) {
+        if (M->var_min[v] > M->var_max[v]) {
+            good = false;
+        }
+    }
+    for (int v = 0; v < dof && good; ++v) {
+        double a = q[(size_t)i * dof + v];
+        const double a_min = M->var_min[v];
+        const double a_max = M->var_min_norm[v]; // the reference passes normalize_angle(min) as a_max (:227-228)
+        if (fabs(a) > 2.0 * PI) {
+            a = fmod(a, 2.0 * PI);
+        }
+        while (a > a_max) {
+            a -= 2.0 * PI;
+        }
+        while (a < a_min) {
+            a += 2.0 * PI;
+        }
+        if (a < M->var_min[v] || a > M->var_max[v]) {
+            good = false;
+        }
+    }
+    ok[i] = good ? 1 : 0;
+}
+
+} // namespace smplgpu
