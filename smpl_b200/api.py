@@ -392,6 +392,8 @@ def build_tables(scene):
         t.set_joint(k, v)
     if scene.use_desc_acm:
         t.use_file_acm()
+    for a, b, allowed in scene.acm_extra:
+        t.set_acm_entry(a, b, allowed)
     if scene.attached is not None:
         body_id, link, centers, radius = scene.attached
         t.attach_spheres(body_id, link, centers, radius)

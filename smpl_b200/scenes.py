@@ -66,6 +66,7 @@ class Scene:
         self.inflation_radius = 0.02   # planning_link_sphere_radius, call_planner.cpp:1715
         self.cost_per_cell = 250       # planning_params.h:68 default... set by callers
         self.attached = None           # (id, link, centers[n,3], radius)
+        self.acm_extra = []            # (a, b, allowed) entries applied on top of the ACM
 
     def add_box(self, center, size):
         c = box_cells(self.origin, self.res, self.dims, center, size)
@@ -115,6 +116,55 @@ def pr2_clutter_scene(seed=7, n_boxes=40):
             continue  # robot body column
         s.add_box(center, size)
         placed += 1
+    return s
+
+
+def ubr1_tabletop_scene(attach=True):
+    """Config 4 shape: UBR1 arm (7-DOF) with an attached 0.05 x 0.05 x 0.20 m box, tabletop_ubr1.env."""
+    s = Scene("ubr1", "arm", UBR1_ARM_JOINTS, (-0.75, -1.25, -0.05), (2.0, 2.0, 2.0), 0.02, 0.4)
+    s.fixed_joints = {"torso_lift_joint": 0.0}
+    s.chain_root = "torso_lift_link"           # ubr1_goal.yaml kinematics_frame
+    s.chain_tip = "gripper_link"               # (the demo's chain tip is a finger link behind a prismatic
+    s.planning_link = "gripper_link"           #  joint that is not a planning joint; we stop at gripper_link)
+    T = np.eye(4)[:3].copy()
+    T[:, 3] = (-0.086875, 0.0, 0.37743)        # base_link -> torso_lift_link at torso_lift_joint = 0
+    s.T_kin_to_planning = T
+    s.cost_per_cell = 100
+    s.add_box((0.8, 0.0, 0.55), (0.3, 1.5, 0.02))   # tabletop_ubr1.env
+    # OUR fixture (the reference would take these from the robot's SRDF): sphere models of links
+    # separated only by a sphere-less link overlap by construction
+    for a, b in (("shoulder_pan_link", "upperarm_roll_link"), ("upperarm_roll_link", "forearm_roll_link"),
+                 ("forearm_roll_link", "wrist_roll_link"), ("wrist_roll_link", "left_gripper_finger_link"),
+                 ("wrist_roll_link", "right_gripper_finger_link"),
+                 ("left_gripper_finger_link", "right_gripper_finger_link")):
+        s.acm_extra.append((a, b, True))
+    if attach:
+        centers = attached_box_spheres((0.05, 0.05, 0.20), offset=(0.26, 0.0, 0.0))
+        s.attached = ("object", "wrist_roll_link", centers, 0.025)
+        for link in ("wrist_roll_link", "gripper_link", "left_gripper_finger_link", "right_gripper_finger_link"):
+            s.acm_extra.append(("object", link, True))   # gripper <-> grasped object ALWAYS (SURVEY.md 8d config 4)
+    return s
+
+
+def pr2_dual_arm_scene(seed=17):
+    """Config 5 shape: PR2 torso + both arms (15-DOF), 3 x 3 x 2 m dense shelf scene at 1 cm."""
+    joints = ["torso_lift_joint"] + PR2_RIGHT_ARM_JOINTS + PR2_LEFT_ARM_JOINTS
+    s = Scene("pr2", "torso", joints, (-1.0, -1.5, 0.0), (3.0, 3.0, 2.0), 0.01, 0.2)
+    s.use_desc_acm = True
+    s.cost_per_cell = 100
+    rng = np.random.Generator(np.random.PCG64(seed))
+    # shelf unit in front of the robot: 5 shelves x 4 bays of 2-cell-thick planes
+    x0, x1, y0, y1 = 0.75, 1.25, -1.0, 1.0
+    for k in range(5):
+        s.add_box((0.5 * (x0 + x1), 0.0, 0.3 + 0.35 * k), (x1 - x0, y1 - y0, 0.02))
+    for b in range(5):
+        y = y0 + b * (y1 - y0) / 4.0
+        s.add_box((0.5 * (x0 + x1), y, 1.0), (x1 - x0, 0.02, 1.7))
+    s.add_box((x1, 0.0, 1.0), (0.02, y1 - y0, 1.7))
+    for _ in range(60):
+        size = rng.uniform(0.04, 0.2, 3)
+        c = np.array([rng.uniform(x0 + 0.1, x1 - 0.1), rng.uniform(y0 + 0.1, y1 - 0.1), rng.uniform(0.35, 1.7)])
+        s.add_box(c, size)
     return s
 
 

@@ -1,0 +1,85 @@
+#!/usr/bin/env python3
+"""Generate the committed golden fixtures under tests/golden/.
+
+Runs in the authoring container only:
+  * bfs_reference_24.npz      -- inputs + outputs of the REFERENCE's own BFS_3D (compiled from
+                                 /root/reference by `make -C oracle ref`), three seeds on a 24^3 grid;
+  * pr2_right_arm_validity.csv -- `benchmark_cc export` format (benchmark_cc.cpp:1390-1409): q0..q6 verdict
+                                 at 12 significant digits; verdicts from the oracle (parity unpinned:
+                                 the reference ships no such file);
+  * pr2_right_arm_edges.csv    -- q0[7] q1[7] verdict waypoint_count, same convention;
+  * ubr1_attached_validity.csv -- UBR1 arm + attached box (config 4 shape).
+The CSVs freeze the oracle's behaviour so that a later change to oracle/ cannot silently move the
+target the CUDA path is compared with.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from helpers import make_oracle  # noqa: E402
+from oracle_api import RefBfs  # noqa: E402
+from smpl_b200 import scenes  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def round12(a):
+    return np.array([[float("%.12g" % v) for v in row] for row in a])
+
+
+def gen_bfs():
+    rng = np.random.default_rng(24)
+    walls = (rng.random((24, 24, 24)) < 0.3).astype(np.uint8)
+    walls[10:12, :, :] = 1
+    walls[10:12, 5:8, 5:8] = 0
+    seeds = np.array([scenes.first_free_cell(walls, (12, 12, 12)), (0, 0, 0), (23, 23, 5)], np.int32)
+    out = {"walls": walls, "seeds": seeds}
+    for k, s in enumerate(seeds):
+        b = RefBfs(24, 24, 24)
+        b.set_walls(walls)
+        b.run(*s)
+        out["dist_%d" % k] = b.grid()
+        b.close()
+    np.savez_compressed(os.path.join(OUT, "bfs_reference_24.npz"), **out)
+
+
+def gen_pr2():
+    scene = scenes.pr2_clutter_scene()
+    o = make_oracle(scene)
+    lo, hi, cont = o.joint_limits()
+    q = round12(scenes.random_states(768, lo, hi, cont, seed=99))
+    v = o.is_states_valid(q)
+    with open(os.path.join(OUT, "pr2_right_arm_validity.csv"), "w") as f:
+        for row, vv in zip(q, v):
+            f.write(" ".join("%.12g" % x for x in row) + " %d\n" % vv)
+    q0 = q[:512]
+    q1 = round12(scenes.mprim_edges(q0)[1])
+    ev, ec = o.is_edges_valid(q0, q1)
+    with open(os.path.join(OUT, "pr2_right_arm_edges.csv"), "w") as f:
+        for a, b, vv, cc in zip(q0, q1, ev, ec):
+            f.write(" ".join("%.12g" % x for x in np.concatenate([a, b])) + " %d %d\n" % (vv, cc))
+    print("pr2: %.1f%% valid states, %.1f%% valid edges" % (100 * v.mean(), 100 * ev.mean()))
+
+
+def gen_ubr1():
+    scene = scenes.ubr1_tabletop_scene()
+    o = make_oracle(scene)
+    lo, hi, cont = o.joint_limits()
+    q = round12(scenes.random_states(512, lo, hi, cont, seed=98))
+    v = o.is_states_valid(q)
+    with open(os.path.join(OUT, "ubr1_attached_validity.csv"), "w") as f:
+        for row, vv in zip(q, v):
+            f.write(" ".join("%.12g" % x for x in row) + " %d\n" % vv)
+    print("ubr1: %.1f%% valid states" % (100 * v.mean()))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_bfs()
+    gen_pr2()
+    gen_ubr1()
