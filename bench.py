@@ -220,7 +220,10 @@ def main():
     # ---- scene: rank 0 builds the distance field on its GPU, then ONE broadcast over NCCL ----
     scene = scenes.pr2_clutter_scene()
     ctx = api.GpuContext(local_rank)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    # time on ONE explicit stream shared by torch (events) and the library (kernels, copies)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     tables = api.build_tables(scene)
     ctx.set_robot(tables)
     nx, ny, nz = scene.dims

@@ -12,15 +12,13 @@
 //   wall     walls incl. the border shell (persistent across runs)
 //   blocked  wall | discovered
 //   front[2] cells discovered at the previous / current level (ping-pong)
-// plus two per-row "level stamps": row_stamp (last level at which the row
-// received frontier bits) and cand_stamp (last level at which the row or one of
-// its eight (y,z) neighbours did), so a sweep touches only the 3x3 row
-// neighbourhood of the wavefront.  Each level a warp scans 32 cand_stamps at a
-// time (one coalesced 128-byte load), __ballot_sync/__ffs compacts the
-// candidate rows, and the whole warp then expands one row: lanes = words, the
-// nine neighbour rows are OR-ed, x-dilation is done with shifts and shuffles,
-// and distances are written with one coalesced store per non-empty word.  One
-// persistent cooperative kernel runs all levels with grid-wide barriers; frontier bitmaps stay L2 resident.
+// plus a per-row candidate word (level, mask of the nine (y,z) neighbour rows
+// that received cells at that level), so a sweep touches only the 3x3 row
+// neighbourhood of the wavefront.  Each level a warp scans 32 candidate words,
+// __ballot_sync/__ffs compacts the candidate rows, and each half-warp expands
+// one row: lanes = words, the active neighbour rows are OR-ed, x-dilation is
+// done with shifts and shuffles, and distances are written with coalesced
+// stores per non-empty word.  One persistent cooperative kernel runs all levels with grid-wide barriers; frontier bitmaps stay L2 resident.
 #pragma once
 
 #include <cooperative_groups.h>
@@ -38,16 +36,15 @@ struct BfsGrid
     int rows;              // DY * DZ
     uint32_t* wall;
     uint32_t* blocked;
-    uint32_t* front[2];
-    // stamps are ping-ponged by level parity: level L writes [L&1] and reads [(L-1)&1],
-    // so a row that is re-stamped during level L still reads as "active at L-1"
-    uint32_t* row_stamp[2];   // [rows] last level (of that parity) at which the row received frontier bits
-    uint32_t* cand_stamp[2];  // [rows] last level at which the row or one of its 8 neighbours did
+    uint32_t* front0;
+    uint32_t* front1;
+    // candidate words, ping-ponged by level parity: level L writes [L&1] and reads [(L-1)&1]
+    uint32_t* cand0;          // [rows] (level << 9) | mask of neighbour rows that got cells at `level`
+    uint32_t* cand1;
     int* dist;             // [DZ*DY*DX]
     int* ctrl;             // [0] = levels run, [1..3] = rotating new-cell flags
 };
 
-constexpr uint32_t STAMP_NEVER = 0xFFFFFFFFu;
 
 // wall bitmap from one byte per cell (x fastest, unpadded); border shell = wall
 __global__ void bfs_walls_from_bytes_kernel(BfsGrid g, const uint8_t* __restrict__ walls)
@@ -114,10 +111,8 @@ __global__ void bfs_reset_kernel(BfsGrid g)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < g.rows) {
-        g.row_stamp[0][idx] = STAMP_NEVER;
-        g.row_stamp[1][idx] = STAMP_NEVER;
-        g.cand_stamp[0][idx] = STAMP_NEVER;
-        g.cand_stamp[1][idx] = STAMP_NEVER;
+        g.cand0[idx] = 0;
+        g.cand1[idx] = 0;
     }
     if (idx < 4) {
         g.ctrl[idx] = 0;
@@ -127,8 +122,8 @@ __global__ void bfs_reset_kernel(BfsGrid g)
     }
     const uint32_t wbits = g.wall[idx];
     g.blocked[idx] = wbits;
-    g.front[0][idx] = 0;
-    g.front[1][idx] = 0;
+    g.front0[idx] = 0;
+    g.front1[idx] = 0;
     const int row = idx / g.W, w = idx - row * g.W;
     int* d = g.dist + (size_t)row * g.DX + w * 32;
     const int xmax = min(32, g.DX - w * 32);
@@ -156,15 +151,16 @@ __global__ void bfs_seed_kernel(BfsGrid g, const int* __restrict__ seeds, int n_
     const uint32_t bit = 1u << (px & 31);
     atomicAnd(&g.wall[word], ~bit);
     atomicOr(&g.blocked[word], bit);
-    atomicOr(&g.front[0][word], bit);
+    atomicOr(&g.front0[word], bit);
     g.dist[(size_t)row * g.DX + px] = 0;
-    g.row_stamp[0][row] = 0;
+    // level 0 published to the nine neighbour rows: the seed row is neighbour k of (pz - dz, py - dy)
     for (int k = 0; k < 9; ++k) {
-        g.cand_stamp[0][(pz + k / 3 - 1) * g.DY + (py + k % 3 - 1)] = 0;
+        atomicOr(&g.cand0[(pz - (k / 3 - 1)) * g.DY + (py - (k % 3 - 1))], 1u << k);
     }
 }
 
-// OR of the frontier words `w` of the (up to nine) active neighbour rows of (y,z)
+// OR of the frontier words `w` of the active neighbour rows of (y,z); bit k of
+// `active9` <=> neighbour row (z + k/3 - 1, y + k%3 - 1) has frontier bits
 __device__ __forceinline__ uint32_t gather9(const uint32_t* __restrict__ fr, const BfsGrid& g,
                                             int y, int z, int w, uint32_t active9)
 {
@@ -179,114 +175,132 @@ __device__ __forceinline__ uint32_t gather9(const uint32_t* __restrict__ fr, con
     return m;
 }
 
-// Process one candidate row (whole warp).  Returns true when the row received new cells.
-__device__ __forceinline__ bool bfs_expand_row(const BfsGrid& g, const uint32_t* __restrict__ fcur,
-                                               uint32_t* __restrict__ fnext, int row, uint32_t level, int lane)
-{
-    const int z = row / g.DY, y = row - z * g.DY;
-    const uint32_t prev = level - 1;
-    // which of the nine neighbour rows carry frontier bits of the previous level
-    uint32_t rs = STAMP_NEVER;
-    if (lane < 9) {
-        rs = __ldcg(&g.row_stamp[prev & 1][(z + lane / 3 - 1) * g.DY + (y + lane % 3 - 1)]);
-    }
-    const uint32_t active9 = __ballot_sync(0xffffffffu, rs == prev) & 0x1FFu;
-    if (active9 == 0) {
-        return false;
-    }
-    bool row_new = false;
-    const int chunks = (g.W + 31) / 32;
-    for (int c = 0; c < chunks; ++c) {
-        const int w = c * 32 + lane;
-        uint32_t m = 0;
-        if (w < g.W) {
-            m = gather9(fcur, g, y, z, w, active9);
-        }
-        uint32_t left = __shfl_up_sync(0xffffffffu, m, 1);
-        uint32_t right = __shfl_down_sync(0xffffffffu, m, 1);
-        if (lane == 0) {
-            left = (w > 0) ? gather9(fcur, g, y, z, w - 1, active9) : 0;
-        }
-        if (lane == 31) {
-            right = (w + 1 < g.W) ? gather9(fcur, g, y, z, w + 1, active9) : 0;
-        }
-        uint32_t fresh = 0;
-        if (w < g.W) {
-            const uint32_t dil = m | (m << 1) | (m >> 1) | (left >> 31) | (right << 31);
-            const size_t idx = (size_t)row * g.W + w;
-            const uint32_t blk = __ldcg(&g.blocked[idx]);
-            fresh = dil & ~blk;
-            if (fresh) {
-                g.blocked[idx] = blk | fresh;
-            }
-            // a stamped row must have every word current; unstamped rows are never read
-            fnext[idx] = fresh;
-        }
-        // distances: one coalesced 128-byte store per non-empty word
-        uint32_t nz = __ballot_sync(0xffffffffu, fresh != 0);
-        row_new |= nz != 0;
-        while (nz) {
-            const int j = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const uint32_t wj = __shfl_sync(0xffffffffu, fresh, j);
-            if ((wj >> lane) & 1u) {
-                g.dist[(size_t)row * g.DX + (size_t)(c * 32 + j) * 32 + lane] = (int)level;
-            }
-        }
-    }
-    if (row_new && lane < 9) {
-        // mark this row and its eight neighbours as candidates for the next level
-        g.cand_stamp[level & 1][(z + lane / 3 - 1) * g.DY + (y + lane % 3 - 1)] = level;
-        if (lane == 0) {
-            g.row_stamp[level & 1][row] = level;
-        }
-    }
-    return row_new;
-}
+constexpr int BFS_THREADS = 512;
 
-// All levels in one cooperative launch.  ctrl[1..3] are rotating "new cells at
-// level L" flags: flag[L%3] is set during level L, read after the barrier, and
-// flag[(L+1)%3] is cleared during level L (its last readers ran before the
-// previous barrier), so one grid barrier per level suffices.
-__global__ void __launch_bounds__(1024)
-bfs_levels_kernel(BfsGrid g, int max_levels)
+// All levels in one cooperative launch.
+//
+// cand[p][row] = (level << 9) | mask9: bit k of mask9 says that neighbour row k of
+// `row` received frontier cells at `level` (parity p = level & 1).  A row that gets
+// new cells at level L publishes itself to its nine (y,z) neighbours with
+// atomicMax (moves the word to level L, clearing older mask bits) + atomicOr.
+// Level L+1 scans cand[L & 1]: rows are interleaved over warps (row = warp + j *
+// nwarps) so the wavefront's rows spread evenly, each lane loads one word,
+// __ballot_sync/__ffs compacts the candidates, and the warp then expands two
+// candidate rows at a time, one per half-warp (lanes = 32-bit words of the row).
+//
+// ctrl[1..3] are rotating "new cells at level L" flags: flag[L%3] is set during
+// level L and read after the barrier; flag[(L+1)%3] is cleared during level L (its
+// last readers ran before the previous barrier): one grid barrier per level.
+__global__ void __launch_bounds__(BFS_THREADS, 3)
+bfs_levels_kernel(const __grid_constant__ BfsGrid g, int max_levels)
 {
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31;
+    const int half = lane >> 4, sl = lane & 15;
     const int warps_per_block = blockDim.x >> 5;
     const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * warps_per_block;
+    const int chunks = (g.W + 15) / 16;
 
     uint32_t level = 1;
     for (; level <= (uint32_t)max_levels; ++level) {
-        const uint32_t* __restrict__ fcur = g.front[(level - 1) & 1];
-        uint32_t* __restrict__ fnext = g.front[level & 1];
+        const bool odd = level & 1;
+        const uint32_t* __restrict__ fcur = odd ? g.front0 : g.front1;
+        uint32_t* __restrict__ fnext = odd ? g.front1 : g.front0;
         const uint32_t prev = level - 1;
+        const uint32_t* __restrict__ cand_in = odd ? g.cand0 : g.cand1;
+        uint32_t* __restrict__ cand_out = odd ? g.cand1 : g.cand0;
         int* newflag = &g.ctrl[1 + level % 3];
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             g.ctrl[1 + (level + 1) % 3] = 0;
         }
         bool any_new = false;
-        // scan: lane <-> row, 32 rows per warp step; ballot-compact the candidates
-        for (int base = gwarp * 32; base < g.rows; base += nwarps * 32) {
-            const int r = base + lane;
-            uint32_t st = STAMP_NEVER;
-            if (r < g.rows) {
-                st = __ldcg(&g.cand_stamp[prev & 1][r]);
+        for (int base = gwarp; base < g.rows; base += nwarps * 32) {
+            const int myrow = base + lane * nwarps;
+            uint32_t word = 0;
+            if (myrow < g.rows) {
+                word = __ldcg(&cand_in[myrow]);
             }
-            uint32_t cand = __ballot_sync(0xffffffffu, st == prev);
-            while (cand) {
-                const int j = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const int row = base + j;
-                const int z = row / g.DY, y = row - z * g.DY;
-                if (z == 0 || z == g.DZ - 1 || y == 0 || y == g.DY - 1) {
-                    continue; // border shell rows are all wall
+            uint32_t cmask = __ballot_sync(0xffffffffu, (word >> 9) == prev && (word & 0x1FFu) != 0);
+            while (cmask) {
+                // two candidates per pass, one per half-warp
+                const int j0 = __ffs(cmask) - 1;
+                cmask &= cmask - 1;
+                int j1 = -1;
+                if (cmask) {
+                    j1 = __ffs(cmask) - 1;
+                    cmask &= cmask - 1;
                 }
-                any_new |= bfs_expand_row(g, fcur, fnext, row, level, lane);
+                const int j = half ? j1 : j0;
+                const uint32_t w9 = __shfl_sync(0xffffffffu, word, j < 0 ? 0 : j);
+                int row = j < 0 ? -1 : base + j * nwarps;
+                int z = 0, y = 0;
+                if (row >= 0) {
+                    z = row / g.DY;
+                    y = row - z * g.DY;
+                    if (z == 0 || z == g.DZ - 1 || y == 0 || y == g.DY - 1) {
+                        row = -1; // border shell rows are all wall
+                    }
+                }
+                const uint32_t active9 = row >= 0 ? (w9 & 0x1FFu) : 0u;
+                bool row_new = false;
+                for (int c = 0; c < chunks; ++c) {
+                    const int w = c * 16 + sl;
+                    const bool on = row >= 0 && w < g.W;
+                    uint32_t m = 0, blk = 0xFFFFFFFFu;
+                    size_t idx = 0;
+                    if (on) {
+                        idx = (size_t)row * g.W + w;
+                        blk = __ldcg(&g.blocked[idx]);
+                        m = gather9(fcur, g, y, z, w, active9);
+                    }
+                    uint32_t left = __shfl_up_sync(0xffffffffu, m, 1, 16);
+                    uint32_t right = __shfl_down_sync(0xffffffffu, m, 1, 16);
+                    if (sl == 0) {
+                        left = (on && w > 0) ? gather9(fcur, g, y, z, w - 1, active9) : 0;
+                    }
+                    if (sl == 15) {
+                        right = (on && w + 1 < g.W) ? gather9(fcur, g, y, z, w + 1, active9) : 0;
+                    }
+                    uint32_t fresh = 0;
+                    if (on) {
+                        const uint32_t dil = m | (m << 1) | (m >> 1) | (left >> 31) | (right << 31);
+                        fresh = dil & ~blk;
+                        if (fresh) {
+                            g.blocked[idx] = blk | fresh;
+                        }
+                        fnext[idx] = fresh; // a published row has every word current
+                    }
+                    // distances: per non-empty word, two coalesced 64-byte stores per half-warp
+                    uint32_t nz = (__ballot_sync(0xffffffffu, fresh != 0) >> (half * 16)) & 0xFFFFu;
+                    row_new |= nz != 0;
+                    const uint32_t hmask = half ? 0xFFFF0000u : 0x0000FFFFu; // the halves loop independently
+                    while (nz) {
+                        const int k = __ffs(nz) - 1;
+                        nz &= nz - 1;
+                        const uint32_t wk = __shfl_sync(hmask, fresh, half * 16 + k);
+                        int* d = g.dist + (size_t)row * g.DX + (size_t)(c * 16 + k) * 32;
+                        if ((wk >> sl) & 1u) {
+                            d[sl] = (int)level;
+                        }
+                        if ((wk >> (sl + 16)) & 1u) {
+                            d[sl + 16] = (int)level;
+                        }
+                    }
+                }
+                if (row_new) {
+                    if (sl < 9) {
+                        // this row is neighbour k = sl of row (z - dz, y - dy)
+                        const int dz = sl / 3 - 1, dy = sl % 3 - 1;
+                        uint32_t* cw = &cand_out[(z - dz) * g.DY + (y - dy)];
+                        atomicMax(cw, level << 9);
+                        atomicOr(cw, 1u << sl);
+                    }
+                    any_new = true;
+                }
             }
         }
-        if (any_new && lane == 0) {
+        if (__any_sync(0xffffffffu, any_new) && lane == 0) {
             *newflag = 1;
         }
         grid.sync();

@@ -34,7 +34,7 @@ struct smplgpu_ctx
     bool has_robot = false;
     DevModel* h_model = nullptr; // host copy
     DevModel* d_model = nullptr;
-    std::vector<double> node_radius;
+    int validity_threads = VALIDITY_THREADS;
 
     // distance field
     bool has_df = false;
@@ -187,8 +187,8 @@ smplgpu_ctx* smplgpu_create(int device)
 static void free_bfs(smplgpu_ctx* ctx)
 {
     BfsGrid& g = ctx->bfs;
-    cudaFree(g.wall); cudaFree(g.blocked); cudaFree(g.front[0]); cudaFree(g.front[1]);
-    cudaFree(g.row_stamp[0]); cudaFree(g.row_stamp[1]); cudaFree(g.cand_stamp[0]); cudaFree(g.cand_stamp[1]);
+    cudaFree(g.wall); cudaFree(g.blocked); cudaFree(g.front0); cudaFree(g.front1);
+    cudaFree(g.cand0); cudaFree(g.cand1);
     cudaFree(g.dist); cudaFree(g.ctrl);
     memset(&g, 0, sizeof(g));
     ctx->has_bfs = false;
@@ -411,8 +411,16 @@ int smplgpu_set_robot(smplgpu_ctx* ctx, const smplgpu_robot_desc* d)
             }
         }
         m.n_slots = slots;
-        const size_t smem = (size_t)slots * 12 * sizeof(double) * VALIDITY_THREADS;
-        if (smem > 227 * 1024) return fail(ctx, SMPLGPU_ERR_LIMIT, "%d link slots need %zu B of shared memory", slots, smem);
+        // threads per block: as many warps (<= 4) as the per-thread slot storage lets one block hold
+        const size_t per_thread = (size_t)slots * 12 * sizeof(double) + 2 * sizeof(int) + 1;
+        const size_t smem_max = 227 * 1024;
+        int threads = VALIDITY_THREADS;
+        while (threads > 32 && per_thread * threads > smem_max) {
+            threads -= 32;
+        }
+        if (per_thread * threads > smem_max) return fail(ctx, SMPLGPU_ERR_LIMIT, "%d link slots need %zu B of shared memory per warp", slots, per_thread * 32);
+        ctx->validity_threads = threads;
+        const size_t smem = per_thread * threads + 16;
         CU(cudaFuncSetAttribute(states_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
         CU(cudaFuncSetAttribute(edges_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
         CU(cudaFuncSetAttribute(fk_centers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
@@ -541,7 +549,9 @@ static int need_scene(smplgpu_ctx* ctx)
 
 static size_t validity_smem(const smplgpu_ctx* ctx)
 {
-    return (size_t)ctx->h_model->n_slots * 12 * sizeof(double) * VALIDITY_THREADS;
+    // slot storage + the edge kernel's offsets / verdict scratch
+    return (size_t)ctx->h_model->n_slots * 12 * sizeof(double) * ctx->validity_threads
+           + (2 * (size_t)ctx->validity_threads + 2) * sizeof(int);
 }
 
 int smplgpu_is_states_valid_dev(smplgpu_ctx* ctx, const double* q_dev, int n, uint8_t* verdict_dev)
@@ -552,8 +562,9 @@ int smplgpu_is_states_valid_dev(smplgpu_ctx* ctx, const double* q_dev, int n, ui
     if (n == 0) return 0;
     if (!q_dev || !verdict_dev) return fail(ctx, SMPLGPU_ERR_INVALID, "null device pointer");
     CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    const int blocks = (n + VALIDITY_THREADS - 1) / VALIDITY_THREADS;
-    states_valid_kernel<<<blocks, VALIDITY_THREADS, validity_smem(ctx), ctx->stream>>>(
+    const int vt = ctx->validity_threads;
+    const int blocks = (n + vt - 1) / vt;
+    states_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
         ctx->d_model, ctx->d_df, ctx->grid, q_dev, n, verdict_dev, ctx->d_stats);
     ++ctx->launches;
     CU(cudaGetLastError());
@@ -569,8 +580,9 @@ int smplgpu_is_edges_valid_dev(smplgpu_ctx* ctx, const double* q0_dev, const dou
     if (n == 0) return 0;
     if (!q0_dev || !q1_dev || !verdict_dev) return fail(ctx, SMPLGPU_ERR_INVALID, "null device pointer");
     CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    const int blocks = (n + VALIDITY_THREADS - 1) / VALIDITY_THREADS;
-    edges_valid_kernel<<<blocks, VALIDITY_THREADS, validity_smem(ctx), ctx->stream>>>(
+    const int vt = ctx->validity_threads;
+    const int blocks = (n + vt - 1) / vt;
+    edges_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
         ctx->d_model, ctx->d_df, ctx->grid, q0_dev, q1_dev, n, verdict_dev, counts_dev, ctx->d_stats);
     ++ctx->launches;
     CU(cudaGetLastError());
@@ -628,12 +640,13 @@ static int run_host_batched(smplgpu_ctx* ctx, const double* q0, const double* q1
             memcpy(pin + (size_t)cn * row, q1 + (size_t)off * dof, (size_t)m * row);
             CU(cudaMemcpyAsync(dq1, pin + (size_t)cn * row, (size_t)m * row, cudaMemcpyHostToDevice, ctx->stream));
         }
-        const int blocks = (m + VALIDITY_THREADS - 1) / VALIDITY_THREADS;
+        const int vt = ctx->validity_threads;
+        const int blocks = (m + vt - 1) / vt;
         if (edges) {
-            edges_valid_kernel<<<blocks, VALIDITY_THREADS, validity_smem(ctx), ctx->stream>>>(
+            edges_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
                 ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, m, dv, counts ? dc : nullptr, ctx->d_stats);
         } else {
-            states_valid_kernel<<<blocks, VALIDITY_THREADS, validity_smem(ctx), ctx->stream>>>(
+            states_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
                 ctx->d_model, ctx->d_df, ctx->grid, dq0, m, dv, ctx->d_stats);
         }
         ++ctx->launches;
@@ -699,7 +712,8 @@ int smplgpu_fk_sphere_centers(smplgpu_ctx* ctx, const double* q, int n, double* 
     double* dq = (double*)ctx->d_misc;
     double* dout = dq + (size_t)n * dof;
     CU(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, ctx->stream));
-    fk_centers_kernel<<<(n + VALIDITY_THREADS - 1) / VALIDITY_THREADS, VALIDITY_THREADS, validity_smem(ctx), ctx->stream>>>(
+    const int vt = ctx->validity_threads;
+    fk_centers_kernel<<<(n + vt - 1) / vt, vt, validity_smem(ctx), ctx->stream>>>(
         ctx->d_model, dq, n, dout);
     ++ctx->launches;
     CU(cudaGetLastError());
@@ -751,12 +765,10 @@ static int alloc_bfs(smplgpu_ctx* ctx, int nx, int ny, int nz)
     const size_t wb = ctx->bfs_words * sizeof(uint32_t);
     CU(cudaMalloc(&g.wall, wb));
     CU(cudaMalloc(&g.blocked, wb));
-    CU(cudaMalloc(&g.front[0], wb));
-    CU(cudaMalloc(&g.front[1], wb));
-    for (int i = 0; i < 2; ++i) {
-        CU(cudaMalloc(&g.row_stamp[i], (size_t)g.rows * sizeof(uint32_t)));
-        CU(cudaMalloc(&g.cand_stamp[i], (size_t)g.rows * sizeof(uint32_t)));
-    }
+    CU(cudaMalloc(&g.front0, wb));
+    CU(cudaMalloc(&g.front1, wb));
+    CU(cudaMalloc(&g.cand0, (size_t)g.rows * sizeof(uint32_t)));
+    CU(cudaMalloc(&g.cand1, (size_t)g.rows * sizeof(uint32_t)));
     // +32 ints of slack: the reset kernel writes whole 32-cell words' worth only up to DX, no overrun
     CU(cudaMalloc(&g.dist, ctx->bfs_cells * sizeof(int)));
     CU(cudaMalloc(&g.ctrl, 8 * sizeof(int)));
@@ -837,18 +849,19 @@ int smplgpu_bfs_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz, int n_seeds)
     }
     ctx->bfs_levels = 0;
     if (in_bounds > 0) {
-        // persistent cooperative kernel: as many co-resident 1024-thread blocks as fit
+        // persistent cooperative kernel: every co-resident block the device can hold
         int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_levels_kernel, 1024, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_levels_kernel, BFS_THREADS, 0));
         if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS kernel does not fit an SM");
         int blocks = ctx->sm_count * per_sm;
-        const int want = (g.rows + 32 * 32 - 1) / (32 * 32);
+        const int warps_per_block = BFS_THREADS / 32;
+        const int want = (g.rows + warps_per_block - 1) / warps_per_block; // at most one row per warp per scan slot
         blocks = std::max(1, std::min(blocks, want));
         int max_levels = g.nx + g.ny + g.nz; // upper bound is the free-cell count; cap generously below
         long long cap = (long long)g.nx * g.ny * g.nz;
-        max_levels = (int)std::min<long long>(cap, 0x7FFFFFF0LL);
+        max_levels = (int)std::min<long long>(cap, (1LL << 22)); // level << 9 must fit the candidate word
         void* args[] = { (void*)&g, (void*)&max_levels };
-        CU(cudaLaunchCooperativeKernel((void*)bfs_levels_kernel, dim3(blocks), dim3(1024), args, 0, ctx->stream));
+        CU(cudaLaunchCooperativeKernel((void*)bfs_levels_kernel, dim3(blocks), dim3(BFS_THREADS), args, 0, ctx->stream));
         ++ctx->launches;
         CU(cudaMemcpyAsync(&ctx->bfs_levels, g.ctrl, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }

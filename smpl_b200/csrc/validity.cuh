@@ -332,17 +332,33 @@ states_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__
     flush_counters(cnt, stats);
 }
 
-// CollisionSpace::isStateToStateValid, batched: waypoint generation on the device
+// CollisionSpace::isStateToStateValid, batched.  Waypoints are generated on the
+// device and spread over the block: each thread computes the waypoint count of
+// its own edge, a block-wide exclusive scan turns the counts into offsets, and
+// the block's threads then walk the flattened (edge, waypoint) list, so lanes
+// stay busy whatever the mix of short and long edges.  Consecutive lanes hold
+// consecutive waypoints of one edge (similar poses => similar control flow).
+// The verdict is the AND over all waypoints (order only affects early-out in
+// the reference); a waypoint is skipped once its edge is known to be invalid.
+//
+// Dynamic shared memory: slot storage (n_slots*12*blockDim doubles) followed by
+// (blockDim + 1) ints of offsets and blockDim ints of per-edge verdicts.
 __global__ void __launch_bounds__(VALIDITY_THREADS)
 edges_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ df, GridParams G,
                    const double* __restrict__ q0, const double* __restrict__ q1, int n,
                    uint8_t* __restrict__ verdict, int* __restrict__ counts, unsigned long long* stats)
 {
     extern __shared__ double smem[];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int* s_off = reinterpret_cast<int*>(smem + (size_t)M->n_slots * 12 * blockDim.x);
+    int* s_ok = s_off + blockDim.x + 1;
+    const int tid = threadIdx.x;
+    const int first = blockIdx.x * blockDim.x;
+    const int i = first + tid;
+    const int dof = M->dof;
     Counters cnt = { 0u, 0u, 0u };
+
+    int count = 0;
     if (i < n) {
-        const int dof = M->dof;
         const double* a = q0 + (size_t)i * dof;
         const double* b = q1 + (size_t)i * dof;
         // RobotMotionCollisionModel::getMaxSphereMotion(start, finish, variables)
@@ -362,32 +378,60 @@ edges_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ 
             }
         }
         // fillMotionInterpolation + setWaypointCount
-        int count = 0;
         if (motion != 0.0) {
             count = max(2, (int)ceil(motion / 0.05) + 1);
         }
         if (counts != nullptr) {
             counts[i] = count;
         }
-        bool ok = true;
-        if (count > 0) {
-            const double inv = 1.0 / (double)(count - 1);
-            const int inc_cc = 5;
-            if (count > inc_cc) {
-                for (int s = 0; s < inc_cc && ok; ++s) {
-                    for (int j = s; j < count && ok; j += inc_cc) {
-                        ++cnt.waypoints;
-                        ok = check_state(M, df, G, a, b, (double)j * inv, smem, cnt);
-                    }
-                }
+    }
+    // block-wide inclusive scan of the counts (Hillis-Steele over <= 128 entries)
+    s_off[tid + 1] = count;
+    s_ok[tid] = 1;
+    if (tid == 0) {
+        s_off[0] = 0;
+    }
+    __syncthreads();
+    for (int d = 1; d < (int)blockDim.x; d <<= 1) {
+        int add = 0;
+        if (tid + 1 > d) {
+            add = s_off[tid + 1 - d];
+        }
+        __syncthreads();
+        s_off[tid + 1] += add;
+        __syncthreads();
+    }
+    const int total = s_off[blockDim.x];
+
+    for (int item = tid; item < total; item += blockDim.x) {
+        // edge of this item: largest e with s_off[e] <= item
+        int lo = 0, hi = blockDim.x;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= item) {
+                lo = mid;
             } else {
-                for (int j = 0; j < count && ok; ++j) {
-                    ++cnt.waypoints;
-                    ok = check_state(M, df, G, a, b, (double)j * inv, smem, cnt);
-                }
+                hi = mid;
             }
         }
-        verdict[i] = ok ? 1 : 0;
+        const int e = lo;
+        if (s_ok[e] == 0) {
+            continue; // edge already invalid
+        }
+        const int w = item - s_off[e];
+        const int cnt_e = s_off[e + 1] - s_off[e];
+        const double inv = 1.0 / (double)(cnt_e - 1);     // m_waypoint_count_inv
+        const double alpha = (double)w * inv;             // interpolate(n): alpha = n * inv
+        const double* a = q0 + (size_t)(first + e) * dof;
+        const double* b = q1 + (size_t)(first + e) * dof;
+        ++cnt.waypoints;
+        if (!check_state(M, df, G, a, b, alpha, smem, cnt)) {
+            s_ok[e] = 0;
+        }
+    }
+    __syncthreads();
+    if (i < n) {
+        verdict[i] = s_ok[tid] ? 1 : 0;
     }
     flush_counters(cnt, stats);
 }
