@@ -224,6 +224,28 @@ int smplgpu_goal_heuristics_dev(smplgpu_ctx* ctx, const double* q_dev, int n, in
 /* ForwardKinematicsInterface::computePlanningLinkFK + getTargetOffsetPose: double pose6[n][6] */
 int smplgpu_planning_frame_fk(smplgpu_ctx* ctx, const double* q, int n, double* pose6);
 
+/* ---- many queries at once (batched GetSuccs) ---- */
+/* A bank of n_slots BfsHeuristic instances over the current distance field: one BFS_3D per
+ * planning query (each query has its own goal => its own BFS, bfs_heuristic.cpp:83-101).
+ * The slots are stacked along z in ONE padded grid, so a single wavefront launch runs every
+ * slot's search at once.  Returns the wall count of one slot. */
+int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radius);
+/* BFS_3D::run for every slot: seeds_xyz[n_slots][3]; a slot whose seed is out of bounds is left undiscovered */
+int smplgpu_bfs_bank_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz);
+/* BFS_3D::getDistance(cell) of slot[i] */
+int smplgpu_bfs_bank_distances(smplgpu_ctx* ctx, const int32_t* slot, const int32_t* cells_xyz, int n, int32_t* out);
+/* One ManipLattice::GetSuccs worth of device work for MANY expansions at once
+ * (manip_lattice.cpp:219-313, 1511-1580; manip_lattice_action_space.cpp:385-396; arastar.cpp:613-618):
+ * for edge i from q0[i] to q1[i] of the query that owns bank slot[i]:
+ *   verdict[i]         CollisionSpace::isStateToStateValid(q0, q1)
+ *   h[i]               BfsHeuristic::GetGoalHeuristic of q1 (cost_per_cell * BFS distance at the target-offset pose cell)
+ *   goal_dist_cells[i] BFS_3D distance at the planning link cell of q1 (WALL when out of bounds), i.e.
+ *                      getMetricGoalDistance / resolution (bfs_heuristic.cpp:127-138)
+ *   offset_xyz[i][3]   computePlanningFrameFK(q1) position, for ManipLattice::isGoal */
+int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, const int32_t* slot, int n,
+                         int cost_per_cell, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells,
+                         double* offset_xyz);
+
 #ifdef __cplusplus
 }
 #endif

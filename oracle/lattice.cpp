@@ -1,0 +1,362 @@
+// ORACLE (test infrastructure only -- never linked into the product path).
+#include "lattice.h"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+namespace oracle {
+
+static const int INFINITECOST = 1000000000; // SBPL's INFINITECOST
+
+ManipLatticePlanner::ManipLatticePlanner(
+    CollisionSpace* cc, KDLRobotModel* robot, BfsHeuristic* heur,
+    const double xyz_offset[3], int /*cost_per_cell*/, const PlanParams& params)
+:
+    m_cc(cc), m_robot(robot), m_heur(heur), m_params(params),
+    m_goal_state_id(-1), m_start_state_id(-1), m_eps(1.0), m_iteration(1), m_call_number(0)
+{
+    for (int i = 0; i < 3; ++i) m_xyz_offset[i] = xyz_offset[i];
+    // addMotionPrim(..., add_converse = true): each primitive is followed by its negation
+    for (const MotionPrim& p : params.mprims) {
+        m_prim_deltas.push_back(p.delta);
+        m_prim_short.push_back(p.short_dist);
+        std::vector<double> neg(p.delta);
+        for (double& v : neg) v *= -1.0;
+        m_prim_deltas.push_back(neg);
+        m_prim_short.push_back(p.short_dist);
+    }
+    // ManipLattice::init (manip_lattice.cpp:105-146)
+    const size_t n = robot->min_limits.size();
+    m_min_limits = robot->min_limits;
+    m_max_limits = robot->max_limits;
+    m_continuous.resize(n);
+    m_bounded.resize(n);
+    m_coord_vals.resize(n);
+    m_coord_deltas.resize(n);
+    for (size_t v = 0; v < n; ++v) {
+        m_continuous[v] = robot->continuous[v];
+        m_bounded[v] = !robot->continuous[v]; // KDLRobotModel::hasPosLimit
+        const double res = params.resolutions[v];
+        if (m_continuous[v]) {
+            m_coord_vals[v] = (int)std::round((2.0 * M_PI) / res);
+            m_coord_deltas[v] = (2.0 * M_PI) / (double)m_coord_vals[v];
+        } else if (m_bounded[v]) {
+            const double span = std::fabs(m_max_limits[v] - m_min_limits[v]);
+            m_coord_vals[v] = std::max(1, (int)std::round(span / res));
+            m_coord_deltas[v] = span / (double)m_coord_vals[v];
+        } else {
+            m_coord_vals[v] = std::numeric_limits<int>::max();
+            m_coord_deltas[v] = res;
+        }
+    }
+}
+
+/// manip_lattice.cpp:1263-1289
+void ManipLatticePlanner::stateToCoord(const std::vector<double>& state, std::vector<int>& coord) const
+{
+    coord.resize(state.size());
+    for (size_t i = 0; i < state.size(); ++i) {
+        if (m_continuous[i]) {
+            double pos_angle = normalize_angle(state[i]);
+            if (pos_angle < 0.0) {
+                pos_angle += 2.0 * M_PI; // angles::normalize_angle_positive
+            }
+            coord[i] = (int)((pos_angle + m_coord_deltas[i] * 0.5) / m_coord_deltas[i]);
+            if (coord[i] == m_coord_vals[i]) {
+                coord[i] = 0;
+            }
+        } else if (!m_bounded[i]) {
+            if (state[i] >= 0.0) {
+                coord[i] = (int)(state[i] / m_coord_deltas[i] + 0.5);
+            } else {
+                coord[i] = (int)(state[i] / m_coord_deltas[i] - 0.5);
+            }
+        } else {
+            coord[i] = (int)(((state[i] - m_min_limits[i]) / m_coord_deltas[i]) + 0.5);
+        }
+    }
+}
+
+int ManipLatticePlanner::getOrCreateState(const std::vector<int>& coord, const std::vector<double>& state)
+{
+    auto it = m_coord_to_id.find(coord);
+    if (it != m_coord_to_id.end()) {
+        return it->second;
+    }
+    const int id = (int)m_states.size();
+    m_states.push_back(LatticeState{ coord, state });
+    m_coord_to_id[coord] = id;
+    return id;
+}
+
+/// manip_lattice.cpp:1673-1687 (XYZ_GOAL)
+bool ManipLatticePlanner::isGoal(const std::vector<double>& state) const
+{
+    std::vector<double> pose;
+    m_robot->computePlanningLinkFK(state, pose);
+    pose = GetTargetOffsetPose(pose, m_xyz_offset);
+    return std::fabs(pose[0] - m_goal[0]) <= m_params.xyz_tolerance[0] &&
+           std::fabs(pose[1] - m_goal[1]) <= m_params.xyz_tolerance[1] &&
+           std::fabs(pose[2] - m_goal[2]) <= m_params.xyz_tolerance[2];
+}
+
+/// BfsHeuristic::GetGoalHeuristic over ManipLattice::projectToPose (bfs_heuristic.cpp:148-163,
+/// manip_lattice.cpp:1174-1206): the goal state projects to the goal pose itself
+int ManipLatticePlanner::goalHeuristic(int state_id) const
+{
+    if (state_id == m_goal_state_id) {
+        return m_heur->getGoalHeuristicAt(m_goal[0], m_goal[1], m_goal[2]);
+    }
+    std::vector<double> pose;
+    m_robot->computePlanningLinkFK(m_states[state_id].state, pose);
+    pose = GetTargetOffsetPose(pose, m_xyz_offset);
+    return m_heur->getGoalHeuristicAt(pose[0], pose[1], pose[2]);
+}
+
+/// ManipLattice::GetSuccs + ManipLatticeActionSpace::apply + ManipLattice::checkAction
+void ManipLatticePlanner::getSuccs(int state_id, std::vector<int>& succs, std::vector<int>& costs)
+{
+    if (state_id == m_goal_state_id) {
+        return; // goal state is absorbing
+    }
+    const std::vector<double> parent = m_states[state_id].state;
+
+    std::vector<double> pose;
+    m_robot->computePlanningLinkFK(parent, pose);
+    const double goal_dist = m_heur->getMetricGoalDistance(pose[0], pose[1], pose[2]);
+    const bool near_goal = goal_dist <= m_params.short_dist_thresh;
+
+    std::vector<double> succ(parent.size());
+    std::vector<int> coord;
+    for (size_t p = 0; p < m_prim_deltas.size(); ++p) {
+        // mprimActive (manip_lattice_action_space.cpp:662-691)
+        bool active;
+        if (!m_prim_short[p]) {
+            active = !(m_params.use_short_dist && near_goal);
+        } else {
+            active = m_params.use_short_dist && near_goal;
+        }
+        if (!active) {
+            continue;
+        }
+        for (size_t j = 0; j < parent.size(); ++j) {
+            succ[j] = m_prim_deltas[p][j] + parent[j];
+        }
+        // checkAction: joint limits of every waypoint, then the edge parent -> waypoint
+        if (!m_robot->checkJointLimits(succ)) {
+            continue;
+        }
+        if (!m_cc->isStateToStateValid(parent, succ)) {
+            continue;
+        }
+        stateToCoord(succ, coord);
+        const int succ_id = getOrCreateState(coord, succ);
+        const bool is_goal = isGoal(succ);
+        succs.push_back(is_goal ? m_goal_state_id : succ_id);
+        costs.push_back((int)(1000 * 1.0)); // DefaultCostMultiplier * actionWeight
+    }
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// ARA*
+///////////////////////////////////////////////////////////////////////////////
+
+ManipLatticePlanner::SearchState& ManipLatticePlanner::searchState(int id)
+{
+    if ((int)m_search.size() <= id) {
+        SearchState blank;
+        blank.state_id = -1;
+        blank.call_number = 0;
+        blank.heap_index = 0;
+        blank.g = blank.h = blank.f = blank.eg = 0;
+        blank.iteration_closed = 0;
+        blank.bp = -1;
+        blank.incons = false;
+        const size_t old = m_search.size();
+        m_search.resize(id + 1, blank);
+        for (size_t k = old; k < m_search.size(); ++k) {
+            m_search[k].state_id = (int)k;
+        }
+    }
+    return m_search[id];
+}
+
+/// arastar.cpp:613-627
+void ManipLatticePlanner::reinit(SearchState& s)
+{
+    if (s.call_number != m_call_number) {
+        s.g = INFINITECOST;
+        s.h = goalHeuristic(s.state_id);
+        s.f = INFINITECOST;
+        s.eg = INFINITECOST;
+        s.iteration_closed = 0;
+        s.call_number = m_call_number;
+        s.bp = -1;
+        s.incons = false;
+    }
+}
+
+/// arastar.cpp:579-582
+int ManipLatticePlanner::computeKey(const SearchState& s) const
+{
+    return s.g + (unsigned int)(m_eps * s.h);
+}
+
+void ManipLatticePlanner::percolateUp(size_t pivot)
+{
+    const int tmp = m_open[pivot];
+    while (pivot != 1) {
+        const size_t p = pivot >> 1;
+        if (heapLess(m_open[p], tmp)) {
+            break;
+        }
+        m_open[pivot] = m_open[p];
+        m_search[m_open[pivot]].heap_index = (int)pivot;
+        pivot = p;
+    }
+    m_open[pivot] = tmp;
+    m_search[tmp].heap_index = (int)pivot;
+}
+
+void ManipLatticePlanner::percolateDown(size_t pivot)
+{
+    if (pivot >= m_open.size()) {
+        return;
+    }
+    size_t left = pivot << 1, right = left + 1;
+    const int tmp = m_open[pivot];
+    while (left < m_open.size()) {
+        size_t s = right;
+        if (right >= m_open.size() || heapLess(m_open[left], m_open[right])) {
+            s = left;
+        }
+        if (heapLess(m_open[s], tmp)) {
+            m_open[pivot] = m_open[s];
+            m_search[m_open[pivot]].heap_index = (int)pivot;
+            pivot = s;
+        } else {
+            break;
+        }
+        left = pivot << 1;
+        right = left + 1;
+    }
+    m_open[pivot] = tmp;
+    m_search[tmp].heap_index = (int)pivot;
+}
+
+void ManipLatticePlanner::heapPush(int id)
+{
+    m_search[id].heap_index = (int)m_open.size();
+    m_open.push_back(id);
+    percolateUp(m_open.size() - 1);
+}
+
+void ManipLatticePlanner::heapPop()
+{
+    m_search[m_open[1]].heap_index = 0;
+    m_open[1] = m_open.back();
+    m_open.pop_back();
+    percolateDown(1);
+}
+
+void ManipLatticePlanner::heapDecrease(int id)
+{
+    percolateUp((size_t)m_search[id].heap_index);
+}
+
+PlanResult ManipLatticePlanner::plan(const std::vector<double>& start, const double goal_xyz[3])
+{
+    PlanResult res;
+    m_states.clear();
+    m_coord_to_id.clear();
+    m_search.clear();
+    m_open.assign(1, -1);
+    for (int i = 0; i < 3; ++i) m_goal[i] = goal_xyz[i];
+
+    // reserveHashEntry for the goal state (manip_lattice.cpp:122): id 0
+    m_goal_state_id = 0;
+    m_states.push_back(LatticeState());
+
+    // setGoal -> BfsHeuristic::updateGoal
+    m_heur->updateGoal(goal_xyz[0], goal_xyz[1], goal_xyz[2]);
+
+    // setStart (manip_lattice.cpp:1944-1980)
+    if (!m_robot->checkJointLimits(start) || !m_cc->isStateValid(start)) {
+        return res;
+    }
+    std::vector<int> coord;
+    stateToCoord(start, coord);
+    m_start_state_id = getOrCreateState(coord, start);
+
+    // replan (arastar.cpp:107-215), first solution at the initial epsilon
+    ++m_call_number;
+    m_iteration = 1;
+    m_eps = m_params.epsilon;
+    // vector growth may move elements: fetch by index after both exist
+    searchState(std::max(m_start_state_id, m_goal_state_id));
+    reinit(m_search[m_start_state_id]);
+    reinit(m_search[m_goal_state_id]);
+    m_search[m_start_state_id].g = 0;
+    m_search[m_start_state_id].f = computeKey(m_search[m_start_state_id]);
+    heapPush(m_start_state_id);
+
+    std::vector<int> succs, costs;
+    bool found = false;
+    while (m_open.size() > 1) {
+        const int min_id = m_open[1];
+        if (m_search[min_id].f >= m_search[m_goal_state_id].f || min_id == m_goal_state_id) {
+            found = true;
+            break;
+        }
+        if (res.expansions >= m_params.max_expansions) {
+            break;
+        }
+        heapPop();
+        m_search[min_id].iteration_closed = m_iteration;
+        m_search[min_id].eg = m_search[min_id].g;
+
+        // expand (arastar.cpp:531-568)
+        succs.clear();
+        costs.clear();
+        getSuccs(min_id, succs, costs);
+        for (size_t k = 0; k < succs.size(); ++k) {
+            searchState(succs[k]);
+            SearchState& ss = m_search[succs[k]];
+            reinit(ss);
+            const int new_cost = m_search[min_id].eg + costs[k];
+            if (new_cost < ss.g) {
+                ss.g = new_cost;
+                ss.bp = min_id;
+                if (ss.iteration_closed != m_iteration) {
+                    ss.f = computeKey(ss);
+                    if (ss.heap_index != 0) {
+                        heapDecrease(ss.state_id);
+                    } else {
+                        heapPush(ss.state_id);
+                    }
+                } else if (!ss.incons) {
+                    ss.incons = true; // (the reference forgets to set the flag; harmless for one iteration)
+                }
+            }
+        }
+        ++res.expansions;
+    }
+    res.num_states = (int)m_states.size();
+    if (!found || m_search[m_goal_state_id].g >= INFINITECOST) {
+        return res;
+    }
+    // extractPath (arastar.cpp:629-640)
+    for (int s = m_goal_state_id; s >= 0; s = m_search[s].bp) {
+        res.path_ids.push_back(s);
+    }
+    std::reverse(res.path_ids.begin(), res.path_ids.end());
+    res.cost = m_search[m_goal_state_id].g;
+    res.success = true;
+    for (int id : res.path_ids) {
+        res.path_states.push_back(m_states[id].state);
+    }
+    return res;
+}
+
+} // namespace oracle

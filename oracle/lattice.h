@@ -1,0 +1,122 @@
+// ORACLE (test infrastructure only -- never linked into the product path).
+//
+// Minimal CPU restatement of the CALLER of the hot path, used to check
+// query-level parity (identical paths, costs, expansion counts) and to time
+// "plan queries/s" on the host:
+//   ManipLattice      smpl/src/graph/manip_lattice.cpp:72-150 (init), 219-313 (GetSuccs),
+//                     1245-1289 (coord <-> state), 1511-1580 (checkAction), 1582-1696 (isGoal),
+//                     1944-1980 (setStart)
+//   ManipLatticeActionSpace  smpl/src/graph/manip_lattice_action_space.cpp:201-228 (addMotionPrim),
+//                     376-449 (apply), 507-573 (getAction), 662-691 (mprimActive)
+//   ARAStar           smpl/src/search/arastar.cpp:107-215 (replan), 486-527 (improvePath),
+//                     531-568 (expand), 579-582 (computeKey), 613-640 (reinitSearchState, extractPath)
+//   intrusive_heap    smpl/include/smpl/detail/intrusive_heap.hpp (push/pop/decrease, percolate_up/down)
+//
+// Decisions (fork defect 2): motion primitives use the documented plain format
+// (delta per joint, weight 1, no base rotation hack, converse added after each primitive); the IK "snap"
+// primitives need third-party IK and are outside the parity set; the goal is an XYZ_GOAL (position within
+// xyz_tolerance of the target offset pose, manip_lattice.cpp:1673-1687); the search stops at the first
+// solution of the initial epsilon (improve = false) or after max_expansions, so results do not depend on
+// wall-clock time.  parity unpinned (the reference records no expected plans).
+#ifndef ORACLE_LATTICE_H
+#define ORACLE_LATTICE_H
+
+#include <map>
+#include <vector>
+
+#include "collision_space.h"
+#include "kdl_model.h"
+
+namespace oracle {
+
+struct MotionPrim
+{
+    std::vector<double> delta;
+    bool short_dist;
+};
+
+struct PlanParams
+{
+    std::vector<double> resolutions;   // per planning variable (radians / metres)
+    std::vector<MotionPrim> mprims;    // in file order; converses are added by the lattice
+    bool use_short_dist;
+    double short_dist_thresh;
+    double epsilon;
+    int max_expansions;
+    double xyz_tolerance[3];
+};
+
+struct PlanResult
+{
+    bool success;
+    int expansions;
+    int cost;
+    std::vector<int> path_ids;
+    std::vector<std::vector<double>> path_states;
+    int num_states;
+    PlanResult() : success(false), expansions(0), cost(0), num_states(0) { }
+};
+
+class ManipLatticePlanner
+{
+public:
+    ManipLatticePlanner(CollisionSpace* cc, KDLRobotModel* robot, BfsHeuristic* heur,
+                        const double xyz_offset[3], int cost_per_cell, const PlanParams& params);
+
+    /// PlannerInterface::planToPose reduced to: setGoal (BFS from the goal cell), setStart, ARA* replan
+    PlanResult plan(const std::vector<double>& start, const double goal_xyz[3]);
+
+private:
+    struct LatticeState { std::vector<int> coord; std::vector<double> state; };
+    struct SearchState
+    {
+        int state_id;
+        int g, h, f, eg;
+        int iteration_closed, call_number;
+        int bp;
+        bool incons;
+        int heap_index;
+    };
+
+    CollisionSpace* m_cc;
+    KDLRobotModel* m_robot;
+    BfsHeuristic* m_heur;
+    double m_xyz_offset[3];
+    PlanParams m_params;
+    std::vector<std::vector<double>> m_prim_deltas;
+    std::vector<bool> m_prim_short;
+
+    std::vector<double> m_min_limits, m_max_limits, m_coord_deltas;
+    std::vector<bool> m_continuous, m_bounded;
+    std::vector<int> m_coord_vals;
+
+    std::vector<LatticeState> m_states;
+    std::map<std::vector<int>, int> m_coord_to_id;
+    int m_goal_state_id, m_start_state_id;
+    double m_goal[3];
+
+    std::vector<SearchState> m_search;
+    std::vector<int> m_open; // 1-based binary heap of state ids
+    double m_eps;
+    int m_iteration, m_call_number;
+
+    void stateToCoord(const std::vector<double>& state, std::vector<int>& coord) const;
+    int getOrCreateState(const std::vector<int>& coord, const std::vector<double>& state);
+    bool isGoal(const std::vector<double>& state) const;
+    void getSuccs(int state_id, std::vector<int>& succs, std::vector<int>& costs);
+    int goalHeuristic(int state_id) const;
+
+    SearchState& searchState(int id);
+    void reinit(SearchState& s);
+    int computeKey(const SearchState& s) const;
+    bool heapLess(int a, int b) const { return m_search[a].f < m_search[b].f; }
+    void heapPush(int id);
+    void heapPop();
+    void heapDecrease(int id);
+    void percolateUp(size_t pivot);
+    void percolateDown(size_t pivot);
+};
+
+} // namespace oracle
+
+#endif

@@ -18,6 +18,7 @@
 #include "collision_space.h"
 #include "distance_map.h"
 #include "kdl_model.h"
+#include "lattice.h"
 #include "robot_desc.h"
 
 using namespace oracle;
@@ -468,6 +469,46 @@ int oracle_goal_heuristics(oracle_scene* s, const double* q, int n, int32_t* h)
         h[i] = s->heur->getGoalHeuristicAt(pose[0], pose[1], pose[2]);
     }
     return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// planning query: ManipLattice + ARA* over the oracle's checker / heuristic
+///////////////////////////////////////////////////////////////////////////////
+
+/// mprims: n_prims rows of dof deltas (radians); short_flags[n_prims].
+/// out_summary: success, expansions, cost, path_len, num_states.  Returns seconds spent in plan().
+double oracle_plan(oracle_scene* s, const double* start, const double* goal_xyz,
+                   const double* resolutions, const double* mprims, const uint8_t* short_flags, int n_prims,
+                   int use_short_dist, double short_dist_thresh, double epsilon, int max_expansions,
+                   const double* xyz_tolerance, int32_t* out_summary, int32_t* path_ids, int max_path)
+{
+    PlanParams pp;
+    pp.resolutions.assign(resolutions, resolutions + s->dof);
+    for (int p = 0; p < n_prims; ++p) {
+        MotionPrim mp;
+        mp.delta.assign(mprims + (size_t)p * s->dof, mprims + (size_t)(p + 1) * s->dof);
+        mp.short_dist = short_flags[p] != 0;
+        pp.mprims.push_back(mp);
+    }
+    pp.use_short_dist = use_short_dist != 0;
+    pp.short_dist_thresh = short_dist_thresh;
+    pp.epsilon = epsilon;
+    pp.max_expansions = max_expansions;
+    for (int i = 0; i < 3; ++i) pp.xyz_tolerance[i] = xyz_tolerance[i];
+    ManipLatticePlanner planner(s->cc.get(), s->kdl.get(), s->heur.get(), s->xyz_offset, 0, pp);
+    std::vector<double> st(start, start + s->dof);
+    auto t0 = std::chrono::steady_clock::now();
+    PlanResult r = planner.plan(st, goal_xyz);
+    auto t1 = std::chrono::steady_clock::now();
+    out_summary[0] = r.success ? 1 : 0;
+    out_summary[1] = r.expansions;
+    out_summary[2] = r.cost;
+    out_summary[3] = (int)r.path_ids.size();
+    out_summary[4] = r.num_states;
+    for (size_t i = 0; i < r.path_ids.size() && (int)i < max_path; ++i) {
+        path_ids[i] = r.path_ids[i];
+    }
+    return std::chrono::duration<double>(t1 - t0).count();
 }
 
 ///////////////////////////////////////////////////////////////////////////////

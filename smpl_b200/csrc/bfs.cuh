@@ -72,27 +72,31 @@ __global__ void bfs_walls_from_bytes_kernel(BfsGrid g, const uint8_t* __restrict
 }
 
 // BfsHeuristic::syncGridAndBfs: wall iff d2(cell) <= d2_wall_max  (<=> res*sqrt(d2) <= radius)
+// slot_dz: padded z extent of one slot when several BFS_3D instances are stacked along z
+// (== g.DZ for a single grid); every slot gets its own border shell.
 __global__ void bfs_walls_from_df_kernel(BfsGrid g, const uint16_t* __restrict__ df, int d2_wall_max,
-                                         unsigned int* __restrict__ wall_count)
+                                         int slot_dz, unsigned int* __restrict__ wall_count)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int cnt = 0;
     if (idx < g.rows * g.W) {
         const int row = idx / g.W, w = idx - row * g.W;
-        const int z = row / g.DY, y = row - z * g.DY;
+        const int zt = row / g.DY, y = row - zt * g.DY;
+        const int z = zt % slot_dz;           // z within the slot
+        const int nz = slot_dz - 2;
         uint32_t bits = 0;
         for (int b = 0; b < 32; ++b) {
             const int x = w * 32 + b;
             bool wall;
             if (x >= g.DX) {
                 wall = true;
-            } else if (x == 0 || x == g.DX - 1 || y == 0 || y == g.DY - 1 || z == 0 || z == g.DZ - 1) {
+            } else if (x == 0 || x == g.DX - 1 || y == 0 || y == g.DY - 1 || z == 0 || z == slot_dz - 1) {
                 wall = true;
             } else {
                 // distance field is x-major / z-fastest
-                const int d2 = df[((size_t)(x - 1) * g.ny + (y - 1)) * g.nz + (z - 1)];
+                const int d2 = df[((size_t)(x - 1) * g.ny + (y - 1)) * nz + (z - 1)];
                 wall = d2 <= d2_wall_max;
-                cnt += wall ? 1u : 0u;
+                cnt += (wall && zt < slot_dz) ? 1u : 0u;   // count the first slot only
             }
             bits |= (wall ? 1u : 0u) << b;
         }

@@ -53,8 +53,10 @@ __device__ __forceinline__ void rot2(const double* v, double angle, double* M)
     M[6] = -m_st_1 + m_vt_0_2;  M[7] = m_st_0 + m_vt_1_2;   M[8] = ct + m_vt_2 * v[2];
 }
 
-// computePlanningLinkFK + getTargetOffsetPose: pose6 = x y z roll pitch yaw
-__device__ void planning_frame_fk(const DevModel* __restrict__ M, const double* __restrict__ q, double* pose)
+// computePlanningLinkFK + getTargetOffsetPose: pose6 = x y z roll pitch yaw of the target-offset
+// frame; link_xyz (optional) = position of the planning link itself (before the offset)
+__device__ void planning_frame_fk(const DevModel* __restrict__ M, const double* __restrict__ q, double* pose,
+                                  double* link_xyz = nullptr)
 {
     KFrame f1;
 #pragma unroll
@@ -95,6 +97,9 @@ __device__ void planning_frame_fk(const DevModel* __restrict__ M, const double* 
     KFrame Tk, f;
     kframe_from12(M->T_kin_to_planning, Tk);
     kframe_mul(Tk, f1, f);
+    if (link_xyz != nullptr) {
+        link_xyz[0] = f.p[0]; link_xyz[1] = f.p[1]; link_xyz[2] = f.p[2];
+    }
 
     // KDL Rotation::GetRPY
     double roll, pitch, yaw;
@@ -165,6 +170,58 @@ __global__ void goal_heuristic_kernel(const DevModel* __restrict__ M, GridParams
         out = (d == 0x7FFFFFFF) ? 32767 : cost_per_cell * d;
     }
     h[i] = out;
+}
+
+// BFS cell value at a world point in bank slot `slot` (slots stacked along z, each with its own
+// padded shell); returns 0x7FFFFFFF (WALL) when the point is outside the grid
+__device__ __forceinline__ int bank_lookup(const int* __restrict__ bfs, int dimx, int dimy, int slot_dimz, int slot,
+                                           const GridParams& G, double x, double y, double z, bool& in_bounds)
+{
+    const int gx = __double2int_rz(G.inv_res * (x - G.ox) + 0.5) - 1;
+    const int gy = __double2int_rz(G.inv_res * (y - G.oy) + 0.5) - 1;
+    const int gz = __double2int_rz(G.inv_res * (z - G.oz) + 0.5) - 1;
+    in_bounds = !(gx < 0 || gy < 0 || gz < 0 || gx >= dimx - 2 || gy >= dimy - 2 || gz >= slot_dimz - 2);
+    if (!in_bounds) {
+        return 0x7FFFFFFF;
+    }
+    return bfs[((size_t)(slot * slot_dimz + gz + 1) * dimy + (gy + 1)) * dimx + (gx + 1)];
+}
+
+// per successor: heuristic, metric goal distance (in cells) and target-offset position
+__global__ void expand_info_kernel(const DevModel* __restrict__ M, GridParams G, const int* __restrict__ bfs,
+                                   int dimx, int dimy, int slot_dimz, const double* __restrict__ q,
+                                   const int* __restrict__ slot, int n, int cost_per_cell,
+                                   int* __restrict__ h, int* __restrict__ gdist, double* __restrict__ off_xyz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    double pose[6], link[3];
+    planning_frame_fk(M, q + (size_t)i * M->dof, pose, link);
+    const int s = slot[i];
+    bool inb;
+    const int d_off = bank_lookup(bfs, dimx, dimy, slot_dimz, s, G, pose[0], pose[1], pose[2], inb);
+    h[i] = (!inb || d_off == 0x7FFFFFFF) ? 32767 : cost_per_cell * d_off;
+    gdist[i] = bank_lookup(bfs, dimx, dimy, slot_dimz, s, G, link[0], link[1], link[2], inb);
+    off_xyz[3 * i] = pose[0];
+    off_xyz[3 * i + 1] = pose[1];
+    off_xyz[3 * i + 2] = pose[2];
+}
+
+__global__ void bank_gather_kernel(const int* __restrict__ bfs, int nx, int ny, int nz, const int* __restrict__ slot,
+                                   const int* __restrict__ cells, int n, int* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const int x = cells[3 * i], y = cells[3 * i + 1], z = cells[3 * i + 2];
+    if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) {
+        out[i] = -2;
+        return;
+    }
+    out[i] = bfs[((size_t)(slot[i] * (nz + 2) + z + 1) * (ny + 2) + (y + 1)) * (nx + 2) + (x + 1)];
 }
 
 } // namespace smplgpu

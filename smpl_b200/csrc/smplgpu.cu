@@ -52,6 +52,12 @@ struct smplgpu_ctx
     int bfs_levels = 0;
     int* d_seed_count = nullptr;
 
+    // bank of stacked BFS grids (one per concurrent planning query)
+    bool has_bank = false;
+    BfsGrid bank{};
+    size_t bank_words = 0, bank_cells = 0;
+    int bank_slots = 0, bank_slot_dz = 0, bank_kmax = -1;
+
     // scratch / staging
     double* d_q0 = nullptr; double* d_q1 = nullptr; size_t q_cap = 0;   // doubles
     uint8_t* d_verdict = nullptr; int* d_counts = nullptr; size_t v_cap = 0;
@@ -184,13 +190,17 @@ smplgpu_ctx* smplgpu_create(int device)
     return ctx;
 }
 
-static void free_bfs(smplgpu_ctx* ctx)
+static void free_grid(BfsGrid& g)
 {
-    BfsGrid& g = ctx->bfs;
     cudaFree(g.wall); cudaFree(g.blocked); cudaFree(g.front0); cudaFree(g.front1);
     cudaFree(g.cand0); cudaFree(g.cand1);
     cudaFree(g.dist); cudaFree(g.ctrl);
     memset(&g, 0, sizeof(g));
+}
+
+static void free_bfs(smplgpu_ctx* ctx)
+{
+    free_grid(ctx->bfs);
     ctx->has_bfs = false;
 }
 
@@ -202,6 +212,7 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_bfs(ctx);
+    free_grid(ctx->bank);
     cudaFree(ctx->d_model); cudaFree(ctx->d_stats); cudaFree(ctx->d_seed_count); cudaFree(ctx->d_df);
     cudaFree(ctx->d_q0); cudaFree(ctx->d_q1); cudaFree(ctx->d_verdict); cudaFree(ctx->d_counts); cudaFree(ctx->d_misc);
     for (int i = 0; i < 2; ++i) {
@@ -747,32 +758,84 @@ int smplgpu_check_joint_limits(smplgpu_ctx* ctx, const double* q, int n, uint8_t
 // BFS
 ///////////////////////////////////////////////////////////////////////////////
 
-static int alloc_bfs(smplgpu_ctx* ctx, int nx, int ny, int nz)
+static int alloc_grid(smplgpu_ctx* ctx, BfsGrid& g, int nx, int ny, int nz, size_t* words, size_t* cells)
 {
     if (nx <= 0 || ny <= 0 || nz <= 0) return fail(ctx, SMPLGPU_ERR_INVALID, "bad BFS dimensions");
     if ((long long)(nx + 2) * (ny + 2) * (nz + 2) > 0x7FFFFFFFLL) return fail(ctx, SMPLGPU_ERR_LIMIT, "BFS grid too large for int nodes");
-    if (ctx->has_bfs && ctx->bfs.nx == nx && ctx->bfs.ny == ny && ctx->bfs.nz == nz) {
-        return 0;
-    }
-    free_bfs(ctx);
-    BfsGrid& g = ctx->bfs;
+    free_grid(g);
     g.nx = nx; g.ny = ny; g.nz = nz;
     g.DX = nx + 2; g.DY = ny + 2; g.DZ = nz + 2;
     g.W = ((g.DX + 31) / 32 + 3) / 4 * 4;
     g.rows = g.DY * g.DZ;
-    ctx->bfs_words = (size_t)g.rows * g.W;
-    ctx->bfs_cells = (size_t)g.rows * g.DX;
-    const size_t wb = ctx->bfs_words * sizeof(uint32_t);
+    *words = (size_t)g.rows * g.W;
+    *cells = (size_t)g.rows * g.DX;
+    const size_t wb = *words * sizeof(uint32_t);
     CU(cudaMalloc(&g.wall, wb));
     CU(cudaMalloc(&g.blocked, wb));
     CU(cudaMalloc(&g.front0, wb));
     CU(cudaMalloc(&g.front1, wb));
     CU(cudaMalloc(&g.cand0, (size_t)g.rows * sizeof(uint32_t)));
     CU(cudaMalloc(&g.cand1, (size_t)g.rows * sizeof(uint32_t)));
-    // +32 ints of slack: the reset kernel writes whole 32-cell words' worth only up to DX, no overrun
-    CU(cudaMalloc(&g.dist, ctx->bfs_cells * sizeof(int)));
+    CU(cudaMalloc(&g.dist, *cells * sizeof(int)));
     CU(cudaMalloc(&g.ctrl, 8 * sizeof(int)));
+    return 0;
+}
+
+static int alloc_bfs(smplgpu_ctx* ctx, int nx, int ny, int nz)
+{
+    if (ctx->has_bfs && ctx->bfs.nx == nx && ctx->bfs.ny == ny && ctx->bfs.nz == nz) {
+        return 0;
+    }
+    ctx->has_bfs = false;
+    int r = alloc_grid(ctx, ctx->bfs, nx, ny, nz, &ctx->bfs_words, &ctx->bfs_cells);
+    if (r) return r;
     ctx->has_bfs = true;
+    return 0;
+}
+
+// largest d2 with res*sqrt(d2) <= radius  (grid()->getDistance(x,y,z) <= radius, bfs_heuristic.cpp:343)
+static int wall_threshold(const smplgpu_ctx* ctx, double inflation_radius)
+{
+    int kmax = -1;
+    for (int k = 0; k <= ctx->dmax_sq; ++k) {
+        if (ctx->res * std::sqrt((double)k) <= inflation_radius) {
+            kmax = k;
+        } else {
+            break;
+        }
+    }
+    return kmax;
+}
+
+// reset + seed + all levels on one grid; seeds already on the device (padded-grid-free coordinates)
+static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_seeds, int n_seeds, int* levels_out)
+{
+    const int total = (int)words;
+    bfs_reset_kernel<<<(std::max(total, g.rows) + 255) / 256, 256, 0, ctx->stream>>>(g);
+    ++ctx->launches;
+    if (n_seeds <= 0) {
+        CU(cudaGetLastError());
+        return 0;
+    }
+    CU(cudaMemsetAsync(ctx->d_seed_count, 0, sizeof(int), ctx->stream));
+    bfs_seed_kernel<<<(n_seeds + 127) / 128, 128, 0, ctx->stream>>>(g, d_seeds, n_seeds, ctx->d_seed_count);
+    ++ctx->launches;
+    // persistent cooperative kernel: every co-resident block the device can hold
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_levels_kernel, BFS_THREADS, 0));
+    if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS kernel does not fit an SM");
+    int blocks = ctx->sm_count * per_sm;
+    const int warps_per_block = BFS_THREADS / 32;
+    const int want = (g.rows + warps_per_block - 1) / warps_per_block; // at most one row per warp per scan slot
+    blocks = std::max(1, std::min(blocks, want));
+    long long cap = (long long)g.nx * g.ny * g.nz;
+    int max_levels = (int)std::min<long long>(cap, (1LL << 22)); // level << 9 must fit the candidate word
+    void* args[] = { (void*)&g, (void*)&max_levels };
+    CU(cudaLaunchCooperativeKernel((void*)bfs_levels_kernel, dim3(blocks), dim3(BFS_THREADS), args, 0, ctx->stream));
+    ++ctx->launches;
+    if (levels_out) {
+        CU(cudaMemcpyAsync(levels_out, g.ctrl, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     return 0;
 }
 
@@ -807,19 +870,11 @@ int smplgpu_bfs_set_walls_from_df(smplgpu_ctx* ctx, double inflation_radius)
     if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "distance field not set");
     int r = alloc_bfs(ctx, ctx->grid.nx, ctx->grid.ny, ctx->grid.nz);
     if (r) return r;
-    // largest d2 with res*sqrt(d2) <= radius  (grid()->getDistance(x,y,z) <= radius, bfs_heuristic.cpp:343)
-    int kmax = -1;
-    for (int k = 0; k <= ctx->dmax_sq; ++k) {
-        if (ctx->res * std::sqrt((double)k) <= inflation_radius) {
-            kmax = k;
-        } else {
-            break;
-        }
-    }
+    const int kmax = wall_threshold(ctx, inflation_radius);
     unsigned int* d_count = (unsigned int*)ctx->d_seed_count;
     CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), ctx->stream));
     const int total = (int)ctx->bfs_words;
-    bfs_walls_from_df_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->bfs, ctx->d_df, kmax, d_count);
+    bfs_walls_from_df_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->bfs, ctx->d_df, kmax, ctx->bfs.DZ, d_count);
     ++ctx->launches;
     CU(cudaGetLastError());
     unsigned int count = 0;
@@ -833,40 +888,25 @@ int smplgpu_bfs_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz, int n_seeds)
     if (!ctx || n_seeds < 0 || (n_seeds > 0 && !seeds_xyz)) return SMPLGPU_ERR_INVALID;
     if (!ctx->has_bfs) return fail(ctx, SMPLGPU_ERR_STATE, "BFS walls not set");
     BfsGrid& g = ctx->bfs;
-    const int total = (int)ctx->bfs_words;
-    bfs_reset_kernel<<<(std::max(total, g.rows) + 255) / 256, 256, 0, ctx->stream>>>(g);
-    ++ctx->launches;
-    int in_bounds = 0;
-    if (n_seeds > 0) {
-        int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, (size_t)n_seeds * 3 * sizeof(int));
+    // in-bounds seeds only (BFS_3D::run returns 0 for an out-of-bounds origin, bfs3d.cpp:169-171)
+    std::vector<int> inb;
+    for (int i = 0; i < n_seeds; ++i) {
+        const int x = seeds_xyz[3 * i], y = seeds_xyz[3 * i + 1], z = seeds_xyz[3 * i + 2];
+        if (x >= 0 && y >= 0 && z >= 0 && x < g.nx && y < g.ny && z < g.nz) {
+            inb.push_back(x); inb.push_back(y); inb.push_back(z);
+        }
+    }
+    const int n_in = (int)inb.size() / 3;
+    if (n_in > 0) {
+        int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, inb.size() * sizeof(int));
         if (r) return r;
-        CU(cudaMemcpyAsync(ctx->d_misc, seeds_xyz, (size_t)n_seeds * 3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemsetAsync(ctx->d_seed_count, 0, sizeof(int), ctx->stream));
-        bfs_seed_kernel<<<(n_seeds + 127) / 128, 128, 0, ctx->stream>>>(g, (const int*)ctx->d_misc, n_seeds, ctx->d_seed_count);
-        ++ctx->launches;
-        CU(cudaMemcpyAsync(&in_bounds, ctx->d_seed_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_misc, inb.data(), inb.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
     ctx->bfs_levels = 0;
-    if (in_bounds > 0) {
-        // persistent cooperative kernel: every co-resident block the device can hold
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_levels_kernel, BFS_THREADS, 0));
-        if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS kernel does not fit an SM");
-        int blocks = ctx->sm_count * per_sm;
-        const int warps_per_block = BFS_THREADS / 32;
-        const int want = (g.rows + warps_per_block - 1) / warps_per_block; // at most one row per warp per scan slot
-        blocks = std::max(1, std::min(blocks, want));
-        int max_levels = g.nx + g.ny + g.nz; // upper bound is the free-cell count; cap generously below
-        long long cap = (long long)g.nx * g.ny * g.nz;
-        max_levels = (int)std::min<long long>(cap, (1LL << 22)); // level << 9 must fit the candidate word
-        void* args[] = { (void*)&g, (void*)&max_levels };
-        CU(cudaLaunchCooperativeKernel((void*)bfs_levels_kernel, dim3(blocks), dim3(BFS_THREADS), args, 0, ctx->stream));
-        ++ctx->launches;
-        CU(cudaMemcpyAsync(&ctx->bfs_levels, g.ctrl, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    }
+    int r = run_grid(ctx, g, ctx->bfs_words, (const int*)ctx->d_misc, n_in, &ctx->bfs_levels);
+    if (r) return r;
     CU(cudaStreamSynchronize(ctx->stream));
-    return in_bounds;
+    return n_in;
 }
 
 int smplgpu_bfs_distances(smplgpu_ctx* ctx, const int32_t* cells_xyz, int n, int32_t* out)
@@ -964,6 +1004,147 @@ int smplgpu_planning_frame_fk(smplgpu_ctx* ctx, const double* q, int n, double* 
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(pose6, dout, ob, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// many queries at once: BFS bank + fused expansion batch
+///////////////////////////////////////////////////////////////////////////////
+
+int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radius)
+{
+    if (!ctx || n_slots <= 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "distance field not set");
+    const int nx = ctx->grid.nx, ny = ctx->grid.ny, nz = ctx->grid.nz;
+    const long long total_nz = (long long)n_slots * (nz + 2) - 2;
+    if ((long long)(nx + 2) * (ny + 2) * (total_nz + 2) > 0x7FFFFFFFLL)
+        return fail(ctx, SMPLGPU_ERR_LIMIT, "%d slots of %dx%dx%d exceed int node indices", n_slots, nx, ny, nz);
+    ctx->has_bank = false;
+    int r = alloc_grid(ctx, ctx->bank, nx, ny, (int)total_nz, &ctx->bank_words, &ctx->bank_cells);
+    if (r) return r;
+    ctx->bank_slots = n_slots;
+    ctx->bank_slot_dz = nz + 2;
+    const int kmax = wall_threshold(ctx, inflation_radius);
+    ctx->bank_kmax = kmax;
+    unsigned int* d_count = (unsigned int*)ctx->d_seed_count;
+    CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), ctx->stream));
+    const int total = (int)ctx->bank_words;
+    bfs_walls_from_df_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->bank, ctx->d_df, kmax, ctx->bank_slot_dz, d_count);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    unsigned int count = 0;
+    CU(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->has_bank = true;
+    return (int)count;
+}
+
+int smplgpu_bfs_bank_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz)
+{
+    if (!ctx || !seeds_xyz) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_bank) return fail(ctx, SMPLGPU_ERR_STATE, "BFS bank not created");
+    const int nx = ctx->grid.nx, ny = ctx->grid.ny, nz = ctx->grid.nz;
+    std::vector<int> inb;
+    for (int s = 0; s < ctx->bank_slots; ++s) {
+        const int x = seeds_xyz[3 * s], y = seeds_xyz[3 * s + 1], z = seeds_xyz[3 * s + 2];
+        if (x >= 0 && y >= 0 && z >= 0 && x < nx && y < ny && z < nz) {
+            inb.push_back(x); inb.push_back(y); inb.push_back(s * ctx->bank_slot_dz + z);
+        }
+    }
+    const int n_in = (int)inb.size() / 3;
+    if (n_in > 0) {
+        int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, inb.size() * sizeof(int));
+        if (r) return r;
+        CU(cudaMemcpyAsync(ctx->d_misc, inb.data(), inb.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // every run starts from the scene's walls: a fresh BfsHeuristic per query (seeding a wall cell
+    // un-walls it for the lifetime of a BFS_3D object, bfs3d.cpp:181-187 -- not across queries here)
+    unsigned int* d_count = (unsigned int*)ctx->d_seed_count;
+    CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), ctx->stream));
+    bfs_walls_from_df_kernel<<<((int)ctx->bank_words + 255) / 256, 256, 0, ctx->stream>>>(
+        ctx->bank, ctx->d_df, ctx->bank_kmax, ctx->bank_slot_dz, d_count);
+    ++ctx->launches;
+    int r = run_grid(ctx, ctx->bank, ctx->bank_words, (const int*)ctx->d_misc, n_in, nullptr);
+    if (r) return r;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return n_in;
+}
+
+int smplgpu_bfs_bank_distances(smplgpu_ctx* ctx, const int32_t* slot, const int32_t* cells_xyz, int n, int32_t* out)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_bank) return fail(ctx, SMPLGPU_ERR_STATE, "BFS bank not created");
+    if (n == 0) return 0;
+    if (!slot || !cells_xyz || !out) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    for (int i = 0; i < n; ++i) {
+        if (slot[i] < 0 || slot[i] >= ctx->bank_slots) return fail(ctx, SMPLGPU_ERR_INVALID, "slot %d out of range", slot[i]);
+    }
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, (size_t)n * 5 * sizeof(int));
+    if (r) return r;
+    int* dc = (int*)ctx->d_misc;
+    int* ds = dc + (size_t)n * 3;
+    int* dout = ds + n;
+    CU(cudaMemcpyAsync(dc, cells_xyz, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ds, slot, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    bank_gather_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->bank.dist, ctx->grid.nx, ctx->grid.ny, ctx->grid.nz, ds, dc, n, dout);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, const int32_t* slot, int n,
+                         int cost_per_cell, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells, double* offset_xyz)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (!ctx->has_bank) return fail(ctx, SMPLGPU_ERR_STATE, "BFS bank not created");
+    if (n == 0) return 0;
+    if (!q0 || !q1 || !slot || !verdict || !h || !goal_dist_cells || !offset_xyz) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    const int dof = ctx->h_model->dof;
+    const size_t row = (size_t)dof * sizeof(double);
+    // one pinned staging block in, one out
+    const size_t in_bytes = 2 * n * row + (size_t)n * sizeof(int);
+    const size_t out_bytes = (size_t)n * (1 + 2 * sizeof(int) + 3 * sizeof(double)) + 64;
+    r = grow_pinned(ctx, ctx->pinned, &ctx->pinned_cap, std::max(in_bytes, (size_t)1 << 16));
+    if (r) return r;
+    r = grow_pinned(ctx, ctx->pinned_out, &ctx->pinned_out_cap, std::max(out_bytes, (size_t)1 << 16));
+    if (r) return r;
+    r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, in_bytes + out_bytes + 256);
+    if (r) return r;
+    uint8_t* pin = (uint8_t*)ctx->pinned[0];
+    memcpy(pin, q0, n * row);
+    memcpy(pin + n * row, q1, n * row);
+    memcpy(pin + 2 * n * row, slot, (size_t)n * sizeof(int));
+    uint8_t* dbase = (uint8_t*)ctx->d_misc;
+    CU(cudaMemcpyAsync(dbase, pin, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    double* dq0 = (double*)dbase;
+    double* dq1 = (double*)(dbase + n * row);
+    int* dslot = (int*)(dbase + 2 * n * row);
+    uint8_t* obase = dbase + ((in_bytes + 63) / 64) * 64;
+    double* doff = (double*)obase;
+    int* dh = (int*)(obase + (size_t)n * 3 * sizeof(double));
+    int* dg = dh + n;
+    uint8_t* dv = (uint8_t*)(dg + n);
+    CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    const int vt = ctx->validity_threads;
+    edges_valid_kernel<<<(n + vt - 1) / vt, vt, validity_smem(ctx), ctx->stream>>>(
+        ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, n, dv, nullptr, ctx->d_stats);
+    expand_info_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(
+        ctx->d_model, ctx->grid, ctx->bank.dist, ctx->bank.DX, ctx->bank.DY, ctx->bank_slot_dz, dq1, dslot, n,
+        cost_per_cell, dh, dg, doff);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    uint8_t* pout = (uint8_t*)ctx->pinned_out[0];
+    const size_t o_bytes = (size_t)n * (3 * sizeof(double) + 2 * sizeof(int) + 1);
+    CU(cudaMemcpyAsync(pout, obase, o_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(offset_xyz, pout, (size_t)n * 3 * sizeof(double));
+    memcpy(h, pout + (size_t)n * 3 * sizeof(double), (size_t)n * sizeof(int));
+    memcpy(goal_dist_cells, pout + (size_t)n * (3 * sizeof(double) + sizeof(int)), (size_t)n * sizeof(int));
+    memcpy(verdict, pout + (size_t)n * (3 * sizeof(double) + 2 * sizeof(int)), (size_t)n);
     return 0;
 }
 

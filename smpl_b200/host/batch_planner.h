@@ -1,0 +1,121 @@
+// Host side of the caller of the hot path, B200-first: MANY independent ARA* searches on the
+// manipulation lattice advance in lock step, and every round submits the successors of all of
+// them to the device in ONE smplgpu_expand_batch call (edge validity + heuristic + goal test
+// inputs), so the per-launch batch is (active queries x ~8-22 edges) instead of one edge.
+//
+// It mirrors, per query, the reference's
+//   ManipLattice::GetSuccs / checkAction / isGoal / stateToCoord   smpl/src/graph/manip_lattice.cpp:219-313, 1263-1289, 1511-1580, 1673-1687
+//   ManipLatticeActionSpace::apply / mprimActive                   smpl/src/graph/manip_lattice_action_space.cpp:376-449, 662-691
+//   ARAStar::replan / improvePath / expand / computeKey            smpl/src/search/arastar.cpp:107-215, 486-568, 579-582
+//   intrusive_heap                                                 smpl/include/smpl/detail/intrusive_heap.hpp
+// so that each query returns the same path, cost and expansion count as the reference-shaped
+// sequential planner (first solution at the initial epsilon; see SURVEY.md section 8 defect 2 for
+// the motion-primitive format and goal type decisions).  The OPEN lists, hash tables and the
+// lattice stay on the host, as BASELINE.json's north_star prescribes.
+#ifndef SMPLHOST_BATCH_PLANNER_H
+#define SMPLHOST_BATCH_PLANNER_H
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/smplgpu.h"
+
+namespace smplhost {
+
+struct PlannerConfig
+{
+    int dof = 0;
+    std::vector<double> resolutions;
+    std::vector<double> mprims;         // n_prims x dof deltas, file order (converses are added here)
+    std::vector<uint8_t> short_flags;   // n_prims
+    bool use_short_dist = true;
+    double short_dist_thresh = 0.4;
+    double epsilon = 100.0;
+    int max_expansions = 200000;
+    double xyz_tolerance[3] = { 0.015, 0.015, 0.015 };
+    int cost_per_cell = 100;
+    double inflation_radius = 0.02;
+    // joint limits as KDLRobotModel reports them (min/max/continuous per planning variable)
+    std::vector<double> var_min, var_max;
+    std::vector<int> var_continuous;
+    // grid geometry for host-side worldToGrid of the goal
+    double origin[3] = { 0, 0, 0 };
+    double res = 0.02;
+    int dims[3] = { 0, 0, 0 };
+};
+
+struct QueryResult
+{
+    bool success = false;
+    int expansions = 0;
+    int cost = 0;
+    int num_states = 0;
+    std::vector<int> path_ids;
+};
+
+struct BatchStats
+{
+    int rounds = 0;
+    long long edges_submitted = 0;
+    long long device_calls = 0;
+    double device_seconds = 0.0;   // time inside smplgpu_* calls
+    double host_seconds = 0.0;     // everything else
+};
+
+class BatchPlanner
+{
+public:
+    BatchPlanner(smplgpu_ctx* ctx, const PlannerConfig& cfg, int max_concurrent);
+
+    /// starts: nq x dof, goals: nq x 3 (target-offset position in the planning frame)
+    bool plan(const double* starts, const double* goals, int nq, std::vector<QueryResult>& out, std::string* err);
+
+    const BatchStats& stats() const { return m_stats; }
+
+private:
+    struct LState { std::vector<int> coord; std::vector<double> q; int h; int gdist; };
+    struct SState { int g, h, f, eg, iteration_closed, bp, heap_index; bool touched; };
+    struct Query
+    {
+        int index;
+        int slot;
+        double goal[3];
+        int goal_h;
+        std::vector<LState> states;
+        std::map<std::vector<int>, int> coord_to_id;
+        std::vector<SState> search;
+        std::vector<int> open; // 1-based heap of state ids
+        int expanding;         // state popped this round
+        bool done;
+        QueryResult result;
+    };
+
+    smplgpu_ctx* m_ctx;
+    PlannerConfig m_cfg;
+    int m_max_concurrent;
+    std::vector<std::vector<double>> m_prim_deltas;
+    std::vector<bool> m_prim_short;
+    std::vector<double> m_coord_deltas;
+    std::vector<int> m_coord_vals;
+    BatchStats m_stats;
+
+    void stateToCoord(const double* q, std::vector<int>& coord) const;
+    bool checkJointLimits(const double* q) const;
+    void worldToGrid(const double* p, int* cell) const;
+    int computeKey(const SState& s) const;
+    SState& sstate(Query& Q, int id);
+    void touch(Query& Q, int id);
+    void heapPush(Query& Q, int id);
+    void heapPop(Query& Q);
+    void percolateUp(Query& Q, size_t pivot);
+    void percolateDown(Query& Q, size_t pivot);
+    void finish(Query& Q, bool found);
+    bool runWave(const double* starts, const double* goals, const std::vector<int>& ids,
+                 std::vector<QueryResult>& out, std::string* err);
+};
+
+} // namespace smplhost
+
+#endif

@@ -193,6 +193,32 @@ def pr2_mprim_deltas():
     return np.array(d)
 
 
+class PlanParams:
+    """Planner parameters of the smpl_test demo (pr2_right_arm.yaml, pr2.mprim, call_planner.cpp:93-96, 1715-1729)."""
+
+    def __init__(self, dof=7):
+        deg = math.pi / 180.0
+        self.resolutions = [0.017453292519943295] * dof
+        prims, flags = [], []
+        for j in range(min(4, dof)):          # pr2.mprim rows 1-4: 7 degrees on the first four joints (long)
+            v = [0.0] * dof
+            v[j] = 7.0 * deg
+            prims.append(v)
+            flags.append(0)
+        for j in range(dof):                  # rows 5-11: 4 degrees on every joint (short)
+            v = [0.0] * dof
+            v[j] = 4.0 * deg
+            prims.append(v)
+            flags.append(1)
+        self.mprims = np.array(prims)
+        self.short_flags = np.array(flags, np.uint8)
+        self.use_short_dist = True
+        self.short_dist_thresh = 0.4
+        self.epsilon = 100.0
+        self.max_expansions = 200000
+        self.xyz_tolerance = [0.015, 0.015, 0.015]
+
+
 def mprim_edges(q, deltas=None):
     """Edge i goes from q[i] to q[i] + delta[i mod K]."""
     if deltas is None:

@@ -51,7 +51,7 @@ def lib():
                                           C.c_double, C.c_double]
         L.oracle_bfs_create.restype = C.c_void_p
         L.oracle_bfs_create.argtypes = [C.c_int, C.c_int, C.c_int]
-        for name in ("oracle_time_states_valid", "oracle_time_edges_valid", "oracle_time_bfs_run"):
+        for name in ("oracle_time_states_valid", "oracle_time_edges_valid", "oracle_time_bfs_run", "oracle_plan"):
             getattr(L, name).restype = C.c_double
         L.oracle_time_bfs_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         _LIB = L
@@ -294,6 +294,25 @@ class OracleScene:
         h = np.zeros(len(q), np.int32)
         self.L.oracle_goal_heuristics(self.h, _dp(q), len(q), _ip(h))
         return h
+
+
+    def plan(self, start, goal_xyz, params, max_path=4096):
+        """params: smpl_b200.scenes.PlanParams.  Returns dict(success, expansions, cost, path_ids, num_states, seconds)."""
+        start = np.ascontiguousarray(start, dtype=np.float64)
+        goal = np.ascontiguousarray(goal_xyz, dtype=np.float64)
+        res = np.ascontiguousarray(params.resolutions, dtype=np.float64)
+        prims = np.ascontiguousarray(params.mprims, dtype=np.float64)
+        flags = np.ascontiguousarray(params.short_flags, dtype=np.uint8)
+        tol = np.ascontiguousarray(params.xyz_tolerance, dtype=np.float64)
+        summary = np.zeros(8, np.int32)
+        path = np.zeros(max_path, np.int32)
+        secs = self.L.oracle_plan(self.h, _dp(start), _dp(goal), _dp(res), _dp(prims), _bp(flags), len(prims),
+                                  int(params.use_short_dist), C.c_double(params.short_dist_thresh),
+                                  C.c_double(params.epsilon), int(params.max_expansions), _dp(tol),
+                                  _ip(summary), _ip(path), max_path)
+        n = int(summary[3])
+        return dict(success=bool(summary[0]), expansions=int(summary[1]), cost=int(summary[2]),
+                    path_ids=path[:min(n, max_path)].copy(), num_states=int(summary[4]), seconds=float(secs))
 
 
 class _BfsBase:
