@@ -49,6 +49,65 @@ int smplhost_tables_node_table(smplhost_tables* h, double* out /*[n][8]*/, int m
 int smplhost_tables_motion_weights(smplhost_tables* h, double* weights, int32_t* types);
 int smplhost_tables_pairs(smplhost_tables* h, int32_t* out /*[n][2]*/, int max_pairs);
 
+/* ---- batched planner: many ARA* searches on the manipulation lattice in lock step, one device call per
+ * round (smpl_b200/host/batch_planner.h; mirrors ManipLattice::GetSuccs + ARAStar::improvePath,
+ * manip_lattice.cpp:219-313, arastar.cpp:486-568).  The OPEN lists and the lattice stay on the host. ---- */
+typedef struct smplhost_plan_params
+{
+    int dof;
+    const double* resolutions;      /* [dof] lattice discretisation (pr2_right_arm.yaml:1-8) */
+    const double* mprims;           /* [n_prims][dof] deltas in radians, file order; converses are added */
+    const uint8_t* short_flags;     /* [n_prims] 1 = short-distance primitive */
+    int n_prims;
+    int use_short_dist;
+    double short_dist_thresh;       /* metres (pr2_right_arm.yaml:16) */
+    double epsilon;                 /* ARA* initial epsilon (call_planner.cpp:1729) */
+    int max_expansions;
+    double xyz_tolerance[3];        /* XYZ_GOAL tolerance (call_planner.cpp:93-96) */
+    int cost_per_cell;
+    double inflation_radius;        /* planning_link_sphere_radius (call_planner.cpp:1715) */
+    const double* var_min;          /* [dof] KDLRobotModel limits */
+    const double* var_max;
+    const uint8_t* var_continuous;
+    double origin[3];               /* grid geometry (OccupancyGrid), for the goal cell */
+    double res;
+    int dims[3];
+} smplhost_plan_params;
+
+/* Plans nq queries (starts[nq][dof], goals[nq][3]) with at most max_concurrent searches in flight.
+ * summary[nq][5] = success, expansions, cost, path length, lattice states created;
+ * path_ids[nq][max_path] = state ids of the path (goal state id = 0, start = 1), truncated to max_path;
+ * stats[6] = rounds, edges submitted, device calls, seconds inside smplgpu_* calls, host seconds, total seconds.
+ * Returns 0, or a negative smplgpu error code (smplhost_last_error() has the text). */
+int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* params, const double* starts,
+                        const double* goals, int nq, int max_concurrent, int32_t* summary, int32_t* path_ids,
+                        int max_path, double* stats);
+
+/* ---- drop-in adapters (smpl_b200/host/gpu_adapters.h): the reference's CollisionChecker / RobotModel /
+ * RobotHeuristic virtuals implemented over the C ABI.  These shims drive the C++ objects one virtual call at
+ * a time, the way the reference's planner does (n = 1 per call); a C++ caller uses the classes directly. ---- */
+typedef struct smplhost_adapters smplhost_adapters;
+smplhost_adapters* smplhost_adapters_create(smplgpu_ctx* ctx, smplhost_tables* tables, const char* planning_link,
+                                            const double origin[3], double res, const int32_t dims[3],
+                                            double inflation_radius, int cost_per_cell);
+void smplhost_adapters_destroy(smplhost_adapters* a);
+/* CollisionChecker::isStateValid / isStateToStateValid (collision_checker.h:62-88): 1 valid, 0 invalid */
+int smplhost_cc_is_state_valid(smplhost_adapters* a, const double* q);
+int smplhost_cc_is_state_to_state_valid(smplhost_adapters* a, const double* q0, const double* q1);
+/* CollisionChecker::interpolatePath: waypoints out[count][dof]; returns count, -1 on failure or overflow */
+int smplhost_cc_interpolate_path(smplhost_adapters* a, const double* q0, const double* q1, double* out, int max_waypoints);
+/* GpuCollisionSpace::isStatesValid / isEdgesValid (the batched entry points behind the same object) */
+int smplhost_cc_is_states_valid(smplhost_adapters* a, const double* q, int n, uint8_t* valid);
+int smplhost_cc_is_edges_valid(smplhost_adapters* a, const double* q0, const double* q1, int n, uint8_t* valid);
+/* RobotModel::checkJointLimits, ForwardKinematicsInterface::computePlanningLinkFK (robot_model.h:50-110) */
+int smplhost_rm_check_joint_limits(smplhost_adapters* a, const double* q);
+int smplhost_rm_compute_planning_link_fk(smplhost_adapters* a, const double* q, double* pose6);
+/* RobotHeuristic::updateGoal / GetGoalHeuristic / getMetricGoalDistance (robot_heuristic.h:53-100); the state
+ * is registered as a lattice state first and the heuristic is asked for by state id, as ARA* does */
+int smplhost_heur_update_goal(smplhost_adapters* a, const double xyz[3]);
+int smplhost_heur_goal_heuristic(smplhost_adapters* a, const double* q);
+double smplhost_heur_metric_goal_distance(smplhost_adapters* a, double x, double y, double z);
+
 #ifdef __cplusplus
 }
 #endif

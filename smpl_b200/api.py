@@ -36,6 +36,16 @@ def _bp(a):
     return a.ctypes.data_as(c_uint8_p)
 
 
+class PlanParamsC(C.Structure):
+    """smplhost_plan_params (include/smplhost.h)."""
+    _fields_ = [("dof", C.c_int), ("resolutions", c_double_p), ("mprims", c_double_p), ("short_flags", c_uint8_p),
+                ("n_prims", C.c_int), ("use_short_dist", C.c_int), ("short_dist_thresh", C.c_double),
+                ("epsilon", C.c_double), ("max_expansions", C.c_int), ("xyz_tolerance", C.c_double * 3),
+                ("cost_per_cell", C.c_int), ("inflation_radius", C.c_double), ("var_min", c_double_p),
+                ("var_max", c_double_p), ("var_continuous", c_uint8_p), ("origin", C.c_double * 3),
+                ("res", C.c_double), ("dims", C.c_int * 3)]
+
+
 def gpu_lib():
     """libsmplgpu.so; raises when it has not been built (no fallback)."""
     global _gpu
@@ -77,6 +87,10 @@ def gpu_lib():
         L.smplgpu_goal_heuristics.argtypes = [vp, dp, i, i, ip]
         L.smplgpu_goal_heuristics_dev.argtypes = [vp, vp, i, i, vp]
         L.smplgpu_planning_frame_fk.argtypes = [vp, dp, i, dp]
+        L.smplgpu_bfs_bank_create.argtypes = [vp, i, d]
+        L.smplgpu_bfs_bank_run.argtypes = [vp, ip]
+        L.smplgpu_bfs_bank_distances.argtypes = [vp, ip, ip, i, ip]
+        L.smplgpu_expand_batch.argtypes = [vp, dp, dp, ip, i, i, bp, ip, ip, dp]
         _gpu = L
     return _gpu
 
@@ -108,6 +122,22 @@ def host_lib():
         H.smplhost_tables_node_table.argtypes = [vp, c_double_p, C.c_int]
         H.smplhost_tables_motion_weights.argtypes = [vp, c_double_p, c_int32_p]
         H.smplhost_tables_pairs.argtypes = [vp, c_int32_p, C.c_int]
+        H.smplhost_plan_batch.argtypes = [vp, C.POINTER(PlanParamsC), c_double_p, c_double_p, C.c_int, C.c_int,
+                                          c_int32_p, c_int32_p, C.c_int, c_double_p]
+        H.smplhost_adapters_create.restype = C.c_void_p
+        H.smplhost_adapters_create.argtypes = [vp, vp, C.c_char_p, c_double_p, C.c_double, c_int32_p, C.c_double, C.c_int]
+        H.smplhost_adapters_destroy.argtypes = [vp]
+        H.smplhost_cc_is_state_valid.argtypes = [vp, c_double_p]
+        H.smplhost_cc_is_state_to_state_valid.argtypes = [vp, c_double_p, c_double_p]
+        H.smplhost_cc_interpolate_path.argtypes = [vp, c_double_p, c_double_p, c_double_p, C.c_int]
+        H.smplhost_cc_is_states_valid.argtypes = [vp, c_double_p, C.c_int, c_uint8_p]
+        H.smplhost_cc_is_edges_valid.argtypes = [vp, c_double_p, c_double_p, C.c_int, c_uint8_p]
+        H.smplhost_rm_check_joint_limits.argtypes = [vp, c_double_p]
+        H.smplhost_rm_compute_planning_link_fk.argtypes = [vp, c_double_p, c_double_p]
+        H.smplhost_heur_update_goal.argtypes = [vp, c_double_p]
+        H.smplhost_heur_goal_heuristic.argtypes = [vp, c_double_p]
+        H.smplhost_heur_metric_goal_distance.restype = C.c_double
+        H.smplhost_heur_metric_goal_distance.argtypes = [vp, C.c_double, C.c_double, C.c_double]
         _host = H
     return _host
 
@@ -373,6 +403,140 @@ class GpuContext:
         out = np.zeros((len(q), 6))
         self._ck(self.L.smplgpu_planning_frame_fk(self.h, _dp(q), len(q), _dp(out)), "planning_frame_fk")
         return out
+
+
+    # ---- many queries at once ----
+    def bfs_bank_create(self, n_slots, inflation_radius):
+        return self._ck(self.L.smplgpu_bfs_bank_create(self.h, int(n_slots), float(inflation_radius)), "bfs_bank_create")
+
+    def bfs_bank_run(self, seeds):
+        s = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 3)
+        return self._ck(self.L.smplgpu_bfs_bank_run(self.h, _ip(s)), "bfs_bank_run")
+
+    def bfs_bank_distances(self, slot, cells):
+        c = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 3)
+        sl = np.ascontiguousarray(slot, dtype=np.int32)
+        out = np.zeros(len(c), np.int32)
+        self._ck(self.L.smplgpu_bfs_bank_distances(self.h, _ip(sl), _ip(c), len(c), _ip(out)), "bfs_bank_distances")
+        return out
+
+    def expand_batch(self, q0, q1, slot, cost_per_cell):
+        q0, q1 = self._q(q0), self._q(q1)
+        n = len(q0)
+        sl = np.ascontiguousarray(slot, dtype=np.int32)
+        v, h, g, off = np.zeros(n, np.uint8), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros((n, 3))
+        self._ck(self.L.smplgpu_expand_batch(self.h, _dp(q0), _dp(q1), _ip(sl), n, int(cost_per_cell), _bp(v), _ip(h),
+                                             _ip(g), _dp(off)), "expand_batch")
+        return v, h, g, off
+
+
+class Adapters:
+    """The C++ drop-in adapters (GpuCollisionSpace / GpuRobotModel / GpuBfsHeuristic) driven one virtual call
+    at a time, as the reference's planner drives its plugins."""
+
+    def __init__(self, ctx, scene, tables):
+        self.H = host_lib()
+        self.dof = tables.dof
+        o = np.ascontiguousarray(scene.origin, dtype=np.float64)
+        d = np.ascontiguousarray(scene.dims, dtype=np.int32)
+        h = self.H.smplhost_adapters_create(ctx.h, tables.h, (scene.planning_link or "").encode(), _dp(o),
+                                            float(scene.res), _ip(d), float(scene.inflation_radius),
+                                            int(scene.cost_per_cell))
+        if not h:
+            raise SmplGpuError("adapters: " + self.H.smplhost_last_error().decode())
+        self.h = C.c_void_p(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.H.smplhost_adapters_destroy(self.h)
+            self.h = None
+
+    def _v(self, q):
+        return np.ascontiguousarray(q, dtype=np.float64)
+
+    def is_state_valid(self, q):
+        return self.H.smplhost_cc_is_state_valid(self.h, _dp(self._v(q)))
+
+    def is_state_to_state_valid(self, q0, q1):
+        return self.H.smplhost_cc_is_state_to_state_valid(self.h, _dp(self._v(q0)), _dp(self._v(q1)))
+
+    def interpolate_path(self, q0, q1, max_waypoints=512):
+        out = np.zeros((max_waypoints, self.dof))
+        n = self.H.smplhost_cc_interpolate_path(self.h, _dp(self._v(q0)), _dp(self._v(q1)), _dp(out), max_waypoints)
+        return None if n < 0 else out[:n].copy()
+
+    def is_states_valid(self, q):
+        q = self._v(q).reshape(-1, self.dof)
+        v = np.zeros(len(q), np.uint8)
+        if self.H.smplhost_cc_is_states_valid(self.h, _dp(q), len(q), _bp(v)) != 0:
+            raise SmplGpuError("isStatesValid failed")
+        return v
+
+    def is_edges_valid(self, q0, q1):
+        q0, q1 = self._v(q0).reshape(-1, self.dof), self._v(q1).reshape(-1, self.dof)
+        v = np.zeros(len(q0), np.uint8)
+        if self.H.smplhost_cc_is_edges_valid(self.h, _dp(q0), _dp(q1), len(q0), _bp(v)) != 0:
+            raise SmplGpuError("isEdgesValid failed")
+        return v
+
+    def check_joint_limits(self, q):
+        return self.H.smplhost_rm_check_joint_limits(self.h, _dp(self._v(q)))
+
+    def compute_planning_link_fk(self, q):
+        out = np.zeros(6)
+        if self.H.smplhost_rm_compute_planning_link_fk(self.h, _dp(self._v(q)), _dp(out)) != 0:
+            return None
+        return out
+
+    def update_goal(self, xyz):
+        return self.H.smplhost_heur_update_goal(self.h, _dp(self._v(xyz)))
+
+    def goal_heuristic(self, q):
+        return self.H.smplhost_heur_goal_heuristic(self.h, _dp(self._v(q)))
+
+    def metric_goal_distance(self, x, y, z):
+        return self.H.smplhost_heur_metric_goal_distance(self.h, float(x), float(y), float(z))
+
+
+def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max_path=512):
+    """smplhost_plan_batch: many ARA* queries in lock step, one device call per round.
+    params: smpl_b200.scenes.PlanParams.  Returns (list of dict per query, stats dict)."""
+    H = host_lib()
+    dof = tables.dof
+    starts = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, dof)
+    goals = np.ascontiguousarray(goals, dtype=np.float64).reshape(-1, 3)
+    nq = len(starts)
+    lo, hi, cont = tables.limits()
+    res = np.ascontiguousarray(params.resolutions, dtype=np.float64)
+    prims = np.ascontiguousarray(params.mprims, dtype=np.float64)
+    flags = np.ascontiguousarray(params.short_flags, dtype=np.uint8)
+    P = PlanParamsC()
+    P.dof = dof
+    P.resolutions, P.mprims, P.short_flags, P.n_prims = _dp(res), _dp(prims), _bp(flags), len(prims)
+    P.use_short_dist, P.short_dist_thresh = int(params.use_short_dist), float(params.short_dist_thresh)
+    P.epsilon, P.max_expansions = float(params.epsilon), int(params.max_expansions)
+    P.cost_per_cell, P.inflation_radius = int(scene.cost_per_cell), float(scene.inflation_radius)
+    P.var_min, P.var_max, P.var_continuous = _dp(lo), _dp(hi), _bp(cont)
+    P.res = float(scene.res)
+    for a in range(3):
+        P.xyz_tolerance[a] = float(params.xyz_tolerance[a])
+        P.origin[a] = float(scene.origin[a])
+        P.dims[a] = int(scene.dims[a])
+    summary = np.zeros((nq, 5), np.int32)
+    paths = np.full((nq, max_path), -1, np.int32)
+    stats = np.zeros(6)
+    r = H.smplhost_plan_batch(ctx.h, C.byref(P), _dp(starts), _dp(goals), nq, int(max_concurrent), _ip(summary),
+                              _ip(paths), int(max_path), _dp(stats))
+    if r != 0:
+        raise SmplGpuError("plan_batch: " + H.smplhost_last_error().decode())
+    out = []
+    for i in range(nq):
+        n = int(summary[i, 3])
+        out.append(dict(success=bool(summary[i, 0]), expansions=int(summary[i, 1]), cost=int(summary[i, 2]),
+                        path_ids=paths[i, :min(n, max_path)].copy(), num_states=int(summary[i, 4])))
+    st = dict(rounds=int(stats[0]), edges_submitted=int(stats[1]), device_calls=int(stats[2]),
+              device_seconds=float(stats[3]), host_seconds=float(stats[4]), total_seconds=float(stats[5]))
+    return out, st
 
 
 def world_to_grid(points, origin, res):

@@ -1,6 +1,7 @@
 // Flat C entry points over the host-side C++ (model builder + adapters) so the
 // Python plumbing (tests, bench.py) can drive it with ctypes.  Declared in
 // include/smplhost.h.
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <sstream>
@@ -9,6 +10,8 @@
 
 #include "../../include/smplgpu.h"
 #include "../../include/smplhost.h"
+#include "batch_planner.h"
+#include "gpu_adapters.h"
 #include "robot_tables.h"
 
 using smplhost::RobotTables;
@@ -192,6 +195,218 @@ int smplhost_tables_pairs(smplhost_tables* h, int32_t* out, int max_pairs)
         out[2 * p + 1] = d->pair_b[p];
     }
     return d->n_pairs;
+}
+
+int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* p, const double* starts,
+                        const double* goals, int nq, int max_concurrent, int32_t* summary, int32_t* path_ids,
+                        int max_path, double* stats)
+{
+    if (!ctx || !p || nq < 0 || (nq > 0 && (!starts || !goals || !summary))) {
+        g_err = "smplhost_plan_batch: null argument";
+        return SMPLGPU_ERR_INVALID;
+    }
+    if (p->dof <= 0 || p->n_prims < 0 || !p->resolutions || !p->var_min || !p->var_max || !p->var_continuous ||
+        (p->n_prims > 0 && (!p->mprims || !p->short_flags))) {
+        g_err = "smplhost_plan_batch: incomplete parameters";
+        return SMPLGPU_ERR_INVALID;
+    }
+    smplhost::PlannerConfig cfg;
+    cfg.dof = p->dof;
+    cfg.resolutions.assign(p->resolutions, p->resolutions + p->dof);
+    cfg.mprims.assign(p->mprims, p->mprims + (size_t)p->n_prims * p->dof);
+    cfg.short_flags.assign(p->short_flags, p->short_flags + p->n_prims);
+    cfg.use_short_dist = p->use_short_dist != 0;
+    cfg.short_dist_thresh = p->short_dist_thresh;
+    cfg.epsilon = p->epsilon;
+    cfg.max_expansions = p->max_expansions;
+    cfg.cost_per_cell = p->cost_per_cell;
+    cfg.inflation_radius = p->inflation_radius;
+    cfg.var_min.assign(p->var_min, p->var_min + p->dof);
+    cfg.var_max.assign(p->var_max, p->var_max + p->dof);
+    cfg.var_continuous.assign(p->var_continuous, p->var_continuous + p->dof);
+    cfg.res = p->res;
+    for (int a = 0; a < 3; ++a) {
+        cfg.xyz_tolerance[a] = p->xyz_tolerance[a];
+        cfg.origin[a] = p->origin[a];
+        cfg.dims[a] = p->dims[a];
+    }
+    smplhost::BatchPlanner planner(ctx, cfg, max_concurrent);
+    std::vector<smplhost::QueryResult> out;
+    std::string err;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!planner.plan(starts, goals, nq, out, &err)) {
+        g_err = err;
+        return SMPLGPU_ERR_CUDA;
+    }
+    const double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (int i = 0; i < nq; ++i) {
+        const smplhost::QueryResult& r = out[i];
+        summary[5 * i] = r.success ? 1 : 0;
+        summary[5 * i + 1] = r.expansions;
+        summary[5 * i + 2] = r.cost;
+        summary[5 * i + 3] = (int)r.path_ids.size();
+        summary[5 * i + 4] = r.num_states;
+        if (path_ids) {
+            for (int k = 0; k < max_path; ++k) {
+                path_ids[(size_t)i * max_path + k] = k < (int)r.path_ids.size() ? r.path_ids[k] : -1;
+            }
+        }
+    }
+    if (stats) {
+        const smplhost::BatchStats& s = planner.stats();
+        stats[0] = s.rounds;
+        stats[1] = (double)s.edges_submitted;
+        stats[2] = (double)s.device_calls;
+        stats[3] = s.device_seconds;
+        stats[4] = s.host_seconds;
+        stats[5] = total;
+    }
+    return 0;
+}
+
+struct smplhost_adapters
+{
+    std::unique_ptr<smplhost::GpuCollisionSpace> cc;
+    std::unique_ptr<smplhost::GpuRobotModel> rm;
+    std::unique_ptr<smplhost::GpuBfsHeuristic> heur;
+    std::vector<sbpl::motion::RobotState> states; // the "lattice": state id -> joint state; id 0 = goal state
+    int dof = 0;
+};
+
+smplhost_adapters* smplhost_adapters_create(smplgpu_ctx* ctx, smplhost_tables* tables, const char* planning_link,
+                                            const double origin[3], double res, const int32_t dims[3],
+                                            double inflation_radius, int cost_per_cell)
+{
+    if (!ctx || !tables || !planning_link || !origin || !dims) {
+        g_err = "smplhost_adapters_create: null argument";
+        return nullptr;
+    }
+    std::unique_ptr<smplhost_adapters> a(new smplhost_adapters);
+    const smplgpu_robot_desc* d = tables->t.desc();
+    a->dof = d->dof;
+    a->cc.reset(new smplhost::GpuCollisionSpace(ctx, d->dof));
+    std::vector<int> types(d->var_type, d->var_type + d->dof);
+    std::vector<double> weights(d->var_motion_weight, d->var_motion_weight + d->dof);
+    a->cc->setVariableInfo(tables->t.varContinuous(), weights, types);
+    a->rm.reset(new smplhost::GpuRobotModel(ctx, &tables->t, planning_link));
+    const int idims[3] = { dims[0], dims[1], dims[2] };
+    a->heur.reset(new smplhost::GpuBfsHeuristic(ctx, origin, res, idims));
+    a->heur->setInflationRadius(inflation_radius);
+    a->heur->setCostPerCell(cost_per_cell);
+    a->states.push_back(sbpl::motion::RobotState()); // goal state placeholder
+    smplhost_adapters* raw = a.get();
+    auto lookup = [raw](int id, sbpl::motion::RobotState& q) {
+        if (id <= 0 || id >= (int)raw->states.size()) return false;
+        q = raw->states[id];
+        return true;
+    };
+    if (!a->heur->init(lookup, 0)) {
+        g_err = smplgpu_last_error(ctx);
+        return nullptr;
+    }
+    return a.release();
+}
+
+void smplhost_adapters_destroy(smplhost_adapters* a) { delete a; }
+
+static sbpl::motion::RobotState to_state(const smplhost_adapters* a, const double* q)
+{
+    return sbpl::motion::RobotState(q, q + a->dof);
+}
+
+int smplhost_cc_is_state_valid(smplhost_adapters* a, const double* q)
+{
+    if (!a || !q) return -1;
+    sbpl::motion::CollisionChecker* cc = a->cc.get(); // through the interface, as the planner holds it
+    return cc->isStateValid(to_state(a, q)) ? 1 : 0;
+}
+
+int smplhost_cc_is_state_to_state_valid(smplhost_adapters* a, const double* q0, const double* q1)
+{
+    if (!a || !q0 || !q1) return -1;
+    sbpl::motion::CollisionChecker* cc = a->cc.get();
+    return cc->isStateToStateValid(to_state(a, q0), to_state(a, q1)) ? 1 : 0;
+}
+
+int smplhost_cc_interpolate_path(smplhost_adapters* a, const double* q0, const double* q1, double* out, int max_waypoints)
+{
+    if (!a || !q0 || !q1 || !out) return -1;
+    std::vector<sbpl::motion::RobotState> path;
+    if (!a->cc->interpolatePath(to_state(a, q0), to_state(a, q1), path) || (int)path.size() > max_waypoints) {
+        return -1;
+    }
+    for (size_t i = 0; i < path.size(); ++i) {
+        std::copy(path[i].begin(), path[i].end(), out + i * a->dof);
+    }
+    return (int)path.size();
+}
+
+int smplhost_cc_is_states_valid(smplhost_adapters* a, const double* q, int n, uint8_t* valid)
+{
+    if (!a || n < 0 || (n > 0 && (!q || !valid))) return -1;
+    std::vector<sbpl::motion::RobotState> states(n);
+    for (int i = 0; i < n; ++i) states[i].assign(q + (size_t)i * a->dof, q + (size_t)(i + 1) * a->dof);
+    std::vector<uint8_t> v;
+    if (!a->cc->isStatesValid(states, v)) return -1;
+    std::copy(v.begin(), v.end(), valid);
+    return 0;
+}
+
+int smplhost_cc_is_edges_valid(smplhost_adapters* a, const double* q0, const double* q1, int n, uint8_t* valid)
+{
+    if (!a || n < 0 || (n > 0 && (!q0 || !q1 || !valid))) return -1;
+    std::vector<sbpl::motion::RobotState> s0(n), s1(n);
+    for (int i = 0; i < n; ++i) {
+        s0[i].assign(q0 + (size_t)i * a->dof, q0 + (size_t)(i + 1) * a->dof);
+        s1[i].assign(q1 + (size_t)i * a->dof, q1 + (size_t)(i + 1) * a->dof);
+    }
+    std::vector<uint8_t> v;
+    if (!a->cc->isEdgesValid(s0, s1, v)) return -1;
+    std::copy(v.begin(), v.end(), valid);
+    return 0;
+}
+
+int smplhost_rm_check_joint_limits(smplhost_adapters* a, const double* q)
+{
+    if (!a || !q) return -1;
+    sbpl::motion::RobotModel* rm = a->rm.get();
+    return rm->checkJointLimits(to_state(a, q)) ? 1 : 0;
+}
+
+int smplhost_rm_compute_planning_link_fk(smplhost_adapters* a, const double* q, double* pose6)
+{
+    if (!a || !q || !pose6) return -1;
+    sbpl::motion::Extension* ext = a->rm.get(); // looked up the way the planner does (extension.h:40-60)
+    sbpl::motion::ForwardKinematicsInterface* fk = ext->getExtension<sbpl::motion::ForwardKinematicsInterface>();
+    std::vector<double> pose;
+    if (!fk || !fk->computePlanningLinkFK(to_state(a, q), pose)) return -1;
+    std::copy(pose.begin(), pose.end(), pose6);
+    return 0;
+}
+
+int smplhost_heur_update_goal(smplhost_adapters* a, const double xyz[3])
+{
+    if (!a || !xyz) return -1;
+    sbpl::motion::GoalConstraint goal;
+    goal.type = sbpl::motion::XYZ_GOAL;
+    goal.tgt_off_pose = { xyz[0], xyz[1], xyz[2], 0.0, 0.0, 0.0 };
+    sbpl::motion::RobotHeuristic* h = a->heur.get();
+    h->updateGoal(goal);
+    return 0;
+}
+
+int smplhost_heur_goal_heuristic(smplhost_adapters* a, const double* q)
+{
+    if (!a || !q) return -1;
+    a->states.push_back(to_state(a, q));
+    sbpl::motion::RobotHeuristic* h = a->heur.get();
+    return h->GetGoalHeuristic((int)a->states.size() - 1);
+}
+
+double smplhost_heur_metric_goal_distance(smplhost_adapters* a, double x, double y, double z)
+{
+    if (!a) return -1.0;
+    return a->heur->getMetricGoalDistance(x, y, z);
 }
 
 } // extern "C"

@@ -279,3 +279,16 @@ def attached_box_spheres(size, offset=(0.0, 0.0, 0.0), radius=0.025):
         axes.append(start + pitch * np.arange(n))
     xs, ys, zs = np.meshgrid(*axes, indexing="ij")
     return np.stack([xs.ravel(), ys.ravel(), zs.ravel()], axis=1)
+
+
+PR2_DEMO_START = (-0.5, 0.3, 0.0, -1.0, 0.0, -0.5, 0.0)   # OUR fixture: a collision-free right-arm pose
+
+
+def tabletop_queries(n, seed=13, dof=7):
+    """Config 4 recipe on the PR2 tabletop scene: start fixed, goal positions uniform over a
+    0.6 x 1.0 x 0.5 m box above the table."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lo = np.array([0.35, -0.6, 0.70])
+    goals = lo + rng.random((n, 3)) * np.array([0.45, 0.9, 0.5])
+    starts = np.tile(np.array(PR2_DEMO_START[:dof], np.float64), (n, 1))
+    return np.ascontiguousarray(starts), np.ascontiguousarray(goals)

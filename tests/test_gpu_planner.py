@@ -1,0 +1,112 @@
+"""Query-level parity: the lock-step batch planner over the CUDA path must
+return, for every query, the same path (lattice state ids), cost and expansion count as the sequential
+reference-shaped planner of the oracle (ManipLattice + ARA*, first solution at the initial epsilon)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from helpers import make_oracle
+from smpl_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def tabletop():
+    scene = scenes.pr2_tabletop_scene()
+    o = make_oracle(scene)
+    ctx, tables = api.setup_context(scene)
+    yield scene, o, ctx, tables
+    ctx.close()
+
+
+def test_bfs_bank_equals_single_runs(tabletop):
+    scene, o, ctx, tables = tabletop
+    walls = ctx.bfs_set_walls_from_df(scene.inflation_radius)
+    assert ctx.bfs_bank_create(5, scene.inflation_radius) == walls
+    _, goals = scenes.tabletop_queries(4, seed=31)
+    seeds = api.world_to_grid(goals, scene.origin, scene.res)
+    seeds = np.concatenate([seeds, [[-1, 0, 0]]]).astype(np.int32)   # slot 4: out-of-bounds seed => no search
+    assert ctx.bfs_bank_run(seeds) == 4
+    rng = np.random.default_rng(5)
+    cells = rng.integers(0, np.asarray(scene.dims), (4000, 3)).astype(np.int32)
+    for s in range(4):
+        ctx.bfs_set_walls_from_df(scene.inflation_radius)   # fresh walls: a seed on a wall un-walls it (bfs3d.cpp:181-187)
+        ctx.bfs_run([seeds[s]])
+        single = ctx.bfs_distances(cells)
+        bank = ctx.bfs_bank_distances(np.full(len(cells), s, np.int32), cells)
+        assert np.array_equal(single, bank)
+        assert (single > 0).any()
+    d = ctx.bfs_bank_distances(np.full(len(cells), 4, np.int32), cells)
+    assert np.all((d == -1) | (d == 0x7FFFFFFF))
+
+
+def test_expand_batch_matches_oracle(tabletop):
+    scene, o, ctx, tables = tabletop
+    lo, hi, cont = tables.limits()
+    n = 3000
+    q = scenes.random_states(n, lo, hi, cont, seed=41)
+    q0, q1 = scenes.mprim_edges(q)
+    ctx.bfs_bank_create(2, scene.inflation_radius)
+    goals = np.array([[0.5, -0.3, 0.8], [0.6, 0.2, 1.0]])
+    seeds = api.world_to_grid(goals, scene.origin, scene.res)
+    ctx.bfs_bank_run(seeds)
+    slot = (np.arange(n) % 2).astype(np.int32)
+    v, h, g, off = ctx.expand_batch(q0, q1, slot, scene.cost_per_cell)
+    ev, _ = o.is_edges_valid(q0, q1)
+    assert np.array_equal(v, ev)
+    pose = o.planning_frame_fk(q1)
+    assert np.abs(off - pose[:, :3]).max() < 1e-13
+    for s in range(2):
+        o.heur_init(scene.inflation_radius, scene.cost_per_cell)
+        o.heur_set_goal(*goals[s])
+        sel = slot == s
+        assert np.array_equal(h[sel], o.goal_heuristics(q1[sel]))
+
+
+def _run_oracle(o, scene, params, starts, goals):
+    out = []
+    for s, g in zip(starts, goals):
+        o.heur_init(scene.inflation_radius, scene.cost_per_cell)   # a fresh BfsHeuristic per query
+        out.append(o.plan(s, g, params))
+    return out
+
+
+def test_batch_planner_matches_sequential_oracle(tabletop):
+    scene, o, ctx, tables = tabletop
+    params = scenes.PlanParams(scene.dof)
+    params.max_expansions = 4000
+    starts, goals = scenes.tabletop_queries(24, seed=13)
+    goals[5] = (0.4, -0.2, 0.36)        # the demo's goal (pr2_goal.yaml:38-44): under the table top, hard
+    goals[7] = (5.0, 0.0, 1.0)          # outside the grid: heuristic is Infinity everywhere
+    starts[9, 1] = 3.0                  # start violates joint limits: setStart fails
+    ref = _run_oracle(o, scene, params, starts, goals)
+    got, stats = api.plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=10)
+    n_ok = 0
+    for i, (a, b) in enumerate(zip(ref, got)):
+        assert a["success"] == b["success"], i
+        assert a["expansions"] == b["expansions"], (i, a["expansions"], b["expansions"])
+        assert a["cost"] == b["cost"], i
+        assert a["num_states"] == b["num_states"], i
+        assert np.array_equal(a["path_ids"], b["path_ids"]), i
+        n_ok += a["success"]
+    assert n_ok >= 12 and not ref[9]["success"]
+    assert stats["rounds"] > 0 and stats["edges_submitted"] > 0
+    print("planner parity: %d queries, %d solved, %d rounds, %d edges, device %.3fs host %.3fs" % (
+        len(ref), n_ok, stats["rounds"], stats["edges_submitted"], stats["device_seconds"], stats["host_seconds"]))
+
+
+def test_batch_planner_reproduces_golden_plans(tabletop):
+    scene, o, ctx, tables = tabletop
+    gold = json.load(open(os.path.join(GOLD, "pr2_tabletop_plans.json")))
+    params = scenes.PlanParams(scene.dof)
+    params.max_expansions = gold["max_expansions"]
+    starts, goals = np.array(gold["starts"]), np.array(gold["goals"])
+    got, _ = api.plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64)
+    for g, r in zip(got, gold["results"]):
+        assert [int(g["success"]), g["expansions"], g["cost"], g["num_states"]] == r[:4]
+        assert list(map(int, g["path_ids"])) == r[4]

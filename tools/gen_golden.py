@@ -32,6 +32,24 @@ def round12(a):
     return np.array([[float("%.12g" % v) for v in row] for row in a])
 
 
+def gen_plans():
+    """pr2_tabletop_plans.json -- ARA* results of the oracle's ManipLattice driver on the config-1 scene."""
+    import json
+    scene = scenes.pr2_tabletop_scene()
+    o = make_oracle(scene)
+    params = scenes.PlanParams(scene.dof)
+    params.max_expansions = 3000
+    starts, goals = scenes.tabletop_queries(12, seed=113)
+    starts, goals = round12(starts), round12(goals)
+    results = []
+    for s, g in zip(starts, goals):
+        o.heur_init(scene.inflation_radius, scene.cost_per_cell)
+        p = o.plan(s, g, params)
+        results.append([int(p["success"]), p["expansions"], p["cost"], p["num_states"], [int(v) for v in p["path_ids"]]])
+    json.dump({"max_expansions": params.max_expansions, "starts": starts.tolist(), "goals": goals.tolist(),
+               "results": results}, open(os.path.join(OUT, "pr2_tabletop_plans.json"), "w"))
+
+
 def gen_bfs():
     rng = np.random.default_rng(24)
     walls = (rng.random((24, 24, 24)) < 0.3).astype(np.uint8)
@@ -80,6 +98,6 @@ def gen_ubr1():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    gen_bfs()
-    gen_pr2()
-    gen_ubr1()
+    which = sys.argv[1:] or ["bfs", "pr2", "ubr1", "plans"]
+    for name in which:
+        {"bfs": gen_bfs, "pr2": gen_pr2, "ubr1": gen_ubr1, "plans": gen_plans}[name]()
