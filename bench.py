@@ -291,6 +291,9 @@ def main():
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     total_ms_max = float(t_ms.item())
     gpu_stats = ctx.last_validity_stats()
+    gpu_stats["f64_resolved_edges_last_launch"] = ctx.last_f64_resolved()
+    cert_in_use, e_pos, eps_cells = ctx.certified_bounds()
+    gpu_stats["certified_f32"] = {"in_use": cert_in_use, "e_pos_m": e_pos, "eps_cells": eps_cells}
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
     hq = torch.from_numpy(q).pin_memory()
@@ -393,8 +396,8 @@ def main():
                 "frac": dom["achieved"] / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "launch_ms": dom["ms"],
                 "Lbar_state": Lbar_state, "Lbar_edge": Lbar_edge,
-                "note": "FP64-issue bound (FK + sincos), not memory bound: the HBM fraction is reported as the contract asks; "
-                        "see DESIGN.md and profiles/ for the fp64 pipe utilisation",
+                "note": "issue/latency bound (FK arithmetic + dependent L2 lookups), not HBM bound: the HBM fraction is reported "
+                        "as the contract asks; see DESIGN.md and profiles/ for pipe utilisation and stall reasons",
                 "other_kernel": other}
     if bfs is not None:
         roofline["bfs"] = {"bound": "hbm", "achieved": bfs["achieved_gbs"], "peak": peak, "unit": "GB/s",
@@ -404,7 +407,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f32 certified, f64 resolves the undecidable items (verdicts = all-f64)", "data": "synthetic",
         "config": {"workload": "config[1] validity sweep: PR2 right arm (7-DOF) states + mprim edges vs 2 m^3 clutter scene @ 2 cm",
                    "states_per_step_per_gpu": n, "edges_per_step_per_gpu": n, "validated_states_per_step_per_gpu": units_per_step,
                    "l2_policy": "inputs (%.0f MB/step) exceed the 126 MB L2; the 2 MB distance field is L2-resident by design" % ((3 * n * dof * 8) / 1e6),

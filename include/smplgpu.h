@@ -47,6 +47,12 @@ extern "C" {
 /* RobotHeuristic::Infinity (smpl/heuristic/robot_heuristic.h:62) */
 #define SMPLGPU_HEURISTIC_INFINITY 32767
 
+/* How the validity kernels compute (smplgpu_set_precision_mode).  Verdicts are identical in both modes:
+ * CERTIFIED_F32 decides in single precision only what is provably unaffected by the single-precision
+ * error and resolves the rest with the double-precision kernels; EXACT_F64 uses those alone. */
+#define SMPLGPU_PRECISION_CERTIFIED_F32 0   /* default */
+#define SMPLGPU_PRECISION_EXACT_F64     1
+
 /* joint transform selector: which function the reference would pick
  * (robot_collision_model.cpp:331-359, 382-407; transform_functions.h:95-258) */
 enum {
@@ -223,6 +229,16 @@ int smplgpu_goal_heuristics(smplgpu_ctx* ctx, const double* q, int n, int cost_p
 int smplgpu_goal_heuristics_dev(smplgpu_ctx* ctx, const double* q_dev, int n, int cost_per_cell, int32_t* h_dev);
 /* ForwardKinematicsInterface::computePlanningLinkFK + getTargetOffsetPose: double pose6[n][6] */
 int smplgpu_planning_frame_fk(smplgpu_ctx* ctx, const double* q, int n, double* pose6);
+
+/* ---- precision control / certification (no counterpart in the reference) ---- */
+int smplgpu_set_precision_mode(smplgpu_ctx* ctx, int mode);
+/* bound on |sphere centre (float) - sphere centre (double)| in metres and on the grid-coordinate error in cells;
+ * returns 1 when the single-precision model is in use for this scene, 0 when the scene falls back to double */
+int smplgpu_certified_bounds(smplgpu_ctx* ctx, double* e_pos, double* eps_cells);
+/* items (states / edges) of the last validity call that the double-precision kernels had to resolve */
+int smplgpu_last_f64_resolved(smplgpu_ctx* ctx, int64_t* items);
+/* sphere centres as the single-precision path computes them, float out[n][n_nodes][3] (error-bound test) */
+int smplgpu_fk_sphere_centers_f32(smplgpu_ctx* ctx, const double* q, int n, float* out);
 
 /* ---- many queries at once (batched GetSuccs) ---- */
 /* A bank of n_slots BfsHeuristic instances over the current distance field: one BFS_3D per

@@ -283,6 +283,7 @@ PlanResult ManipLatticePlanner::plan(const std::vector<double>& start, const dou
 
     // setStart (manip_lattice.cpp:1944-1980)
     if (!m_robot->checkJointLimits(start) || !m_cc->isStateValid(start)) {
+        res.num_states = (int)m_states.size();
         return res;
     }
     std::vector<int> coord;

@@ -87,6 +87,10 @@ def gpu_lib():
         L.smplgpu_goal_heuristics.argtypes = [vp, dp, i, i, ip]
         L.smplgpu_goal_heuristics_dev.argtypes = [vp, vp, i, i, vp]
         L.smplgpu_planning_frame_fk.argtypes = [vp, dp, i, dp]
+        L.smplgpu_set_precision_mode.argtypes = [vp, i]
+        L.smplgpu_certified_bounds.argtypes = [vp, dp, dp]
+        L.smplgpu_last_f64_resolved.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.smplgpu_fk_sphere_centers_f32.argtypes = [vp, dp, i, C.POINTER(C.c_float)]
         L.smplgpu_bfs_bank_create.argtypes = [vp, i, d]
         L.smplgpu_bfs_bank_run.argtypes = [vp, ip]
         L.smplgpu_bfs_bank_distances.argtypes = [vp, ip, ip, i, ip]
@@ -346,6 +350,29 @@ class GpuContext:
         ok = np.zeros(len(q), np.uint8)
         self._ck(self.L.smplgpu_check_joint_limits(self.h, _dp(q), len(q), _bp(ok)), "check_joint_limits")
         return ok
+
+    CERTIFIED_F32, EXACT_F64 = 0, 1
+
+    def set_precision_mode(self, mode):
+        self._ck(self.L.smplgpu_set_precision_mode(self.h, int(mode)), "set_precision_mode")
+
+    def certified_bounds(self):
+        """(in_use, e_pos metres, eps cells) of the certified single-precision model."""
+        a, b = C.c_double(), C.c_double()
+        r = self._ck(self.L.smplgpu_certified_bounds(self.h, C.byref(a), C.byref(b)), "certified_bounds")
+        return bool(r), a.value, b.value
+
+    def last_f64_resolved(self):
+        n = C.c_int64()
+        self._ck(self.L.smplgpu_last_f64_resolved(self.h, C.byref(n)), "last_f64_resolved")
+        return n.value
+
+    def fk_sphere_centers_f32(self, q):
+        q = self._q(q)
+        out = np.zeros((len(q), self.n_nodes, 3), np.float32)
+        self._ck(self.L.smplgpu_fk_sphere_centers_f32(self.h, _dp(q), len(q), out.ctypes.data_as(C.POINTER(C.c_float))),
+                 "fk_sphere_centers_f32")
+        return out
 
     def last_validity_stats(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

@@ -16,6 +16,7 @@
 #include "heuristic.cuh"
 #include "model.cuh"
 #include "validity.cuh"
+#include "validity32.cuh"
 
 using namespace smplgpu;
 
@@ -35,6 +36,18 @@ struct smplgpu_ctx
     DevModel* h_model = nullptr; // host copy
     DevModel* d_model = nullptr;
     int validity_threads = VALIDITY_THREADS;
+
+    // certified single-precision model (validity32.cuh)
+    int precision_mode = SMPLGPU_PRECISION_CERTIFIED_F32;
+    bool has_model32 = false;
+    std::vector<float> h_blob;
+    float* d_blob = nullptr; size_t blob_cap = 0;   // bytes
+    int blob_words = 0;
+    int v32_threads = V32_THREADS;
+    double e_pos = 0.0, eps_cells = 0.0;
+    Grid32 grid32{};
+    int* d_unc_list = nullptr; size_t unc_cap = 0;  // ints
+    int* d_unc_count = nullptr;
 
     // distance field
     bool has_df = false;
@@ -64,7 +77,9 @@ struct smplgpu_ctx
     void* d_misc = nullptr; size_t misc_cap = 0;
     void* pinned[2] = { nullptr, nullptr }; size_t pinned_cap = 0;
     void* pinned_out[2] = { nullptr, nullptr }; size_t pinned_out_cap = 0;
-    cudaEvent_t ev[2] = { nullptr, nullptr };
+    cudaEvent_t ev[2] = { nullptr, nullptr };      // chunk b: kernels + result copies done
+    cudaEvent_t ev_in[2] = { nullptr, nullptr };   // chunk b: inputs on the device
+    cudaStream_t copy_stream = nullptr;
     unsigned long long* d_stats = nullptr;
     unsigned long long h_stats[4] = { 0, 0, 0, 0 };
 };
@@ -182,8 +197,11 @@ smplgpu_ctx* smplgpu_create(int device)
     if ((e = cudaMalloc(&ctx->d_model, sizeof(DevModel))) != cudaSuccess) return bail("cudaMalloc(model)", e);
     if ((e = cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(stats)", e);
     if ((e = cudaMalloc(&ctx->d_seed_count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc(seed)", e);
+    if ((e = cudaMalloc(&ctx->d_unc_count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc(unc)", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (int i = 0; i < 2; ++i) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
     ctx->h_model = new DevModel;
     memset(ctx->h_model, 0, sizeof(DevModel));
@@ -214,12 +232,15 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
     free_bfs(ctx);
     free_grid(ctx->bank);
     cudaFree(ctx->d_model); cudaFree(ctx->d_stats); cudaFree(ctx->d_seed_count); cudaFree(ctx->d_df);
+    cudaFree(ctx->d_blob); cudaFree(ctx->d_unc_list); cudaFree(ctx->d_unc_count);
     cudaFree(ctx->d_q0); cudaFree(ctx->d_q1); cudaFree(ctx->d_verdict); cudaFree(ctx->d_counts); cudaFree(ctx->d_misc);
     for (int i = 0; i < 2; ++i) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
         if (ctx->pinned_out[i]) cudaFreeHost(ctx->pinned_out[i]);
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
     }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx->h_model;
     delete ctx;
@@ -267,6 +288,250 @@ static int sphere_threshold(double res, int dmax_sq, double radius, double paddi
     return dmax_sq + 1;
 }
 
+///////////////////////////////////////////////////////////////////////////////
+// certified single-precision model
+///////////////////////////////////////////////////////////////////////////////
+
+static double norm3(const double* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+// origin * joint_fn(value) in double, for joints whose value is a constant of the scene
+static void const_joint_transform(int fn, const double* o, const double* axis, double val, double* t)
+{
+    double R[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+    const double s = std::sin(val), c = std::cos(val);
+    if (fn == 1) { R[5] = c; R[6] = -s; R[9] = s; R[10] = c; }
+    else if (fn == 2) { R[0] = c; R[2] = s; R[8] = -s; R[10] = c; }
+    else if (fn == 3) { R[0] = c; R[1] = -s; R[4] = s; R[5] = c; }
+    else if (fn == 4) {
+        const double k = 1.0 - c, x = axis[0], y = axis[1], z = axis[2];
+        R[0] = k * x * x + c;     R[1] = k * x * y - s * z; R[2] = k * x * z + s * y;
+        R[4] = k * x * y + s * z; R[5] = k * y * y + c;     R[6] = k * y * z - s * x;
+        R[8] = k * x * z - s * y; R[9] = k * y * z + s * x; R[10] = k * z * z + c;
+    } else if (fn == 5) { R[11] = val; }
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 4; ++j) {
+            t[4 * i + j] = o[4 * i] * R[j] + o[4 * i + 1] * R[4 + j] + o[4 * i + 2] * R[8 + j] + (j == 3 ? o[4 * i + 3] : 0.0);
+        }
+    }
+}
+
+// Builds the shared-memory blob of validity32.cuh and the error bounds that certify it.
+//
+// Error model (u = 2^-24, all norms Euclidean; R = rotation part, t = translation part of a link transform):
+//   joint transform J(q):  ||dR_J||_F <= 3.5u (constant), 40u (axis-aligned revolute: sincosf <= 2 ulp, hi/lo
+//                          angle split, 2 roundings per entry), 80u (general axis); ||dt_J|| <= u ||t_J|| (+ 4u |q|max
+//                          for a prismatic joint, whose low part of q is dropped)
+//   product T = P J:       ||dR_T||_F <= ||dR_P||_F + ||dR_J||_F + 12u                  (||R|| = 1)
+//                          ||dt_T||   <= ||dt_P|| + ||dR_P||_F ||t_J|| + ||dt_J|| + 7u tn,   tn >= ||t_T||
+//   centre  x = T c:       ||dx||     <= ||dt_T|| + ||dR_T||_F ||c|| + 7u (tn + ||c||) + u ||c||
+// E_pos = 1.5 * max over nodes.  Grid coordinate g = inv_res (x - o) + 1/2 evaluated in float:
+//   |dg| <= inv_res E_pos + u (inv_res max|o| + 4 (max_dim + 4)) + 1e-7.
+static int build_model32(smplgpu_ctx* ctx)
+{
+    const DevModel& m = *ctx->h_model;
+    ctx->has_model32 = false;
+    if (!ctx->has_robot || !ctx->has_df) {
+        return 0;
+    }
+    if (m.n_nodes >= 65536) {
+        return 0; // node ids are packed in 16 bits in the pair descent: fall back to the double path
+    }
+    const double u = std::ldexp(1.0, -24);
+    const int nl = m.n_links, nn = m.n_nodes;
+
+    // ---- pre-order renumbering, trees grouped by link ----
+    std::vector<int> new_of(nn, -1), orig_of, skip, link_nbeg(nl), link_nend(nl);
+    orig_of.reserve(nn);
+    for (int l = 0; l < nl; ++l) {
+        link_nbeg[l] = (int)orig_of.size();
+        for (int ti = m.link_tree_begin[l]; ti < m.link_tree_end[l]; ++ti) {
+            // iterative pre-order (left child first)
+            std::vector<int> st(1, m.tree_root[m.tree_by_link[ti]]);
+            while (!st.empty()) {
+                const int node = st.back();
+                st.pop_back();
+                new_of[node] = (int)orig_of.size();
+                orig_of.push_back(node);
+                if (m.node_left[node] >= 0) {
+                    st.push_back(m.node_right[node]);
+                    st.push_back(m.node_left[node]);
+                }
+            }
+        }
+        link_nend[l] = (int)orig_of.size();
+    }
+    const int n32 = (int)orig_of.size();   // nodes reachable from a tree root
+    skip.assign(n32, 0);
+    {
+        // subtree sizes: skip[i] = i + size(i)
+        std::vector<int> size(nn, 0);
+        for (int i = n32 - 1; i >= 0; --i) {
+            const int node = orig_of[i];
+            size[node] = 1;
+            if (m.node_left[node] >= 0) {
+                size[node] += size[m.node_left[node]] + size[m.node_right[node]];
+            }
+            skip[i] = i + size[node];
+        }
+    }
+    // ranks of the double radii (the pair descent splits the larger sphere)
+    std::vector<double> radii;
+    for (int i = 0; i < n32; ++i) radii.push_back(m.node_radius[orig_of[i]]);
+    std::sort(radii.begin(), radii.end());
+    radii.erase(std::unique(radii.begin(), radii.end()), radii.end());
+
+    // ---- error bounds ----
+    std::vector<double> EF(nl), Et(nl), tn(nl);
+    double q_lin_max = 0.0;
+    for (int v = 0; v < m.dof; ++v) {
+        if (m.var_type[v] == 2) {
+            double lim = std::max(std::fabs(m.var_min[v]), std::fabs(m.var_max[v]));
+            if (!std::isfinite(lim)) lim = 4.0;
+            q_lin_max = std::max(q_lin_max, lim + 1.0);
+        }
+    }
+    double e_max = 0.0;
+    for (int l = 0; l < nl; ++l) {
+        const int fn = m.link_joint[l];
+        const bool moving = m.link_var[l] >= 0;
+        const double* o = m.link_origin[l];
+        const double to[3] = { o[3], o[7], o[11] };
+        double EF_J, Et_J, tJ;
+        if (!moving || fn == 0) {
+            EF_J = 3.5 * u;
+            tJ = norm3(to) + ((fn == 5) ? std::fabs(m.link_const[l]) : 0.0);
+            Et_J = u * tJ;
+        } else if (fn <= 3) {
+            EF_J = 40.0 * u; tJ = norm3(to); Et_J = u * tJ;
+        } else if (fn == 4) {
+            EF_J = 80.0 * u; tJ = norm3(to); Et_J = u * tJ;
+        } else {
+            EF_J = 3.5 * u; tJ = norm3(to) + q_lin_max; Et_J = u * tJ + 4.0 * u * q_lin_max;
+        }
+        double EF_P, Et_P, tn_P;
+        const int p = m.link_parent[l];
+        if (p < 0) {
+            const double* b = m.link_base[l];
+            const double tb[3] = { b[3], b[7], b[11] };
+            EF_P = 3.5 * u; tn_P = norm3(tb); Et_P = u * tn_P;
+        } else {
+            EF_P = EF[p]; Et_P = Et[p]; tn_P = tn[p];
+        }
+        EF[l] = EF_P + EF_J + 12.0 * u;
+        tn[l] = tn_P + tJ;
+        Et[l] = Et_P + EF_P * tJ + Et_J + 7.0 * u * tn[l];
+        for (int i = link_nbeg[l]; i < link_nend[l]; ++i) {
+            const double cn = norm3(m.node_center[orig_of[i]]);
+            e_max = std::max(e_max, Et[l] + EF[l] * cn + 7.0 * u * (tn[l] + cn) + u * cn);
+        }
+    }
+    const double e_pos = 1.5 * e_max;
+    const double inv_res = ctx->grid.inv_res;
+    const int max_dim = std::max(ctx->grid.nx, std::max(ctx->grid.ny, ctx->grid.nz));
+    const double o_max = std::max(std::fabs(ctx->grid.ox), std::max(std::fabs(ctx->grid.oy), std::fabs(ctx->grid.oz)));
+    const double eps_cells = inv_res * e_pos + u * (inv_res * o_max + 4.0 * (max_dim + 4)) + 1e-7;
+    ctx->e_pos = e_pos;
+    ctx->eps_cells = eps_cells;
+    if (!(eps_cells < 0.125)) {
+        return 0; // bound too loose for this resolution: the double path handles everything
+    }
+
+    // ---- blob ----
+    auto align4 = [](int w) { return (w + 3) / 4 * 4; };
+    Model32Header h;
+    memset(&h, 0, sizeof(h));
+    int w = (int)(sizeof(Model32Header) / 4);
+    h.n_links = nl; h.n_nodes = n32; h.n_pairs = m.n_pairs; h.n_allowed = m.n_allowed; h.n_slots = m.n_slots; h.dof = m.dof;
+    h.off_link_i = w; w += 4 * nl;
+    h.off_link_n = w; w = align4(w + 2 * nl);
+    h.off_origin = w; w += 12 * nl;
+    h.off_axis = w; w += 4 * nl;
+    h.off_base = w; w += 12 * nl;
+    h.off_node_c = w; w += 4 * n32;
+    h.off_node_i = w; w += 4 * n32;
+    h.off_node_orig = w; w = align4(w + n32);
+    h.off_pair = w; w = align4(w + 2 * m.n_pairs);
+    h.off_allowed = w; w = align4(w + 2 * m.n_allowed);
+    h.words = w;
+    h.e_pos = (float)e_pos;
+    h.eps_cells = (float)(eps_cells * 1.0000002);
+    h.pair_k = (float)(2.5 * e_pos);
+    h.q_lin_max = (float)q_lin_max;
+    std::vector<float>& B = ctx->h_blob;
+    B.assign(w, 0.0f);
+    memcpy(B.data(), &h, sizeof(h));
+    int* BI = reinterpret_cast<int*>(B.data());
+    for (int l = 0; l < nl; ++l) {
+        int fn = m.link_joint[l];
+        double J[12];
+        if (m.link_var[l] < 0 && fn != 0) {
+            const_joint_transform(fn, m.link_origin[l], m.link_axis[l], m.link_const[l], J);
+            fn = 0;
+        } else {
+            memcpy(J, m.link_origin[l], sizeof(J));
+        }
+        BI[h.off_link_i + 4 * l] = m.link_parent[l];
+        BI[h.off_link_i + 4 * l + 1] = fn;
+        BI[h.off_link_i + 4 * l + 2] = m.link_var[l];
+        BI[h.off_link_i + 4 * l + 3] = m.link_slot[l];
+        BI[h.off_link_n + 2 * l] = link_nbeg[l];
+        BI[h.off_link_n + 2 * l + 1] = link_nend[l];
+        for (int k = 0; k < 12; ++k) {
+            B[h.off_origin + 12 * l + k] = (float)J[k];
+            B[h.off_base + 12 * l + k] = (float)m.link_base[l][k];
+        }
+        for (int k = 0; k < 3; ++k) B[h.off_axis + 4 * l + k] = (float)m.link_axis[l][k];
+    }
+    for (int i = 0; i < n32; ++i) {
+        const int node = orig_of[i];
+        for (int k = 0; k < 3; ++k) B[h.off_node_c + 4 * i + k] = (float)m.node_center[node][k];
+        B[h.off_node_c + 4 * i + 3] = (float)m.node_radius[node];
+        BI[h.off_node_i + 4 * i] = skip[i];
+        BI[h.off_node_i + 4 * i + 1] = m.node_thresh[node];
+        BI[h.off_node_i + 4 * i + 2] = m.link_slot[m.node_link[node]];
+        BI[h.off_node_i + 4 * i + 3] = (int)(std::lower_bound(radii.begin(), radii.end(), m.node_radius[node]) - radii.begin());
+        BI[h.off_node_orig + i] = node;
+    }
+    for (int p = 0; p < m.n_pairs; ++p) {
+        BI[h.off_pair + 2 * p] = new_of[m.tree_root[m.pair_a[p]]];
+        BI[h.off_pair + 2 * p + 1] = new_of[m.tree_root[m.pair_b[p]]];
+    }
+    for (int k = 0; k < m.n_allowed; ++k) {
+        BI[h.off_allowed + 2 * k] = new_of[m.allowed_a[k]];
+        BI[h.off_allowed + 2 * k + 1] = new_of[m.allowed_b[k]];
+    }
+
+    // ---- launch geometry + upload ----
+    const size_t per_thread = (size_t)m.n_slots * 12 * sizeof(float) + 3 * sizeof(int);
+    const size_t fixed = (size_t)w * 4 + 64;
+    const size_t smem_max = 227 * 1024;
+    int threads = V32_THREADS;
+    while (threads > 32 && fixed + per_thread * threads > smem_max) threads -= 32;
+    if (fixed + per_thread * threads > smem_max) {
+        return 0;
+    }
+    ctx->v32_threads = threads;
+    const int smem = (int)std::max(fixed + per_thread * threads, (size_t)1024);
+    CU(cudaFuncSetAttribute(states_valid32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(edges_valid32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(fk_centers32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int r = grow(ctx, (void**)&ctx->d_blob, &ctx->blob_cap, (size_t)w * 4);
+    if (r) return r;
+    CU(cudaMemcpyAsync(ctx->d_blob, B.data(), (size_t)w * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->blob_words = w;
+    ctx->grid32.nx = ctx->grid.nx; ctx->grid32.ny = ctx->grid.ny; ctx->grid32.nz = ctx->grid.nz;
+    ctx->grid32.inv_res = (float)ctx->grid.inv_res;
+    ctx->grid32.ox = (float)ctx->grid.ox; ctx->grid32.oy = (float)ctx->grid.oy; ctx->grid32.oz = (float)ctx->grid.oz;
+    ctx->has_model32 = true;
+    return 0;
+}
+
+static size_t v32_smem(const smplgpu_ctx* ctx)
+{
+    return (size_t)ctx->blob_words * 4 + (size_t)ctx->h_model->n_slots * 12 * sizeof(float) * ctx->v32_threads
+           + (3 * (size_t)ctx->v32_threads + 2) * sizeof(int);
+}
+
 static int upload_model(smplgpu_ctx* ctx)
 {
     DevModel& m = *ctx->h_model;
@@ -276,6 +541,8 @@ static int upload_model(smplgpu_ctx* ctx)
         }
     }
     CU(cudaMemcpyAsync(ctx->d_model, &m, sizeof(DevModel), cudaMemcpyHostToDevice, ctx->stream));
+    int r = build_model32(ctx);
+    if (r) return r;
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -423,7 +690,7 @@ int smplgpu_set_robot(smplgpu_ctx* ctx, const smplgpu_robot_desc* d)
         }
         m.n_slots = slots;
         // threads per block: as many warps (<= 4) as the per-thread slot storage lets one block hold
-        const size_t per_thread = (size_t)slots * 12 * sizeof(double) + 2 * sizeof(int) + 1;
+        const size_t per_thread = (size_t)slots * 12 * sizeof(double) + 3 * sizeof(int) + 1;
         const size_t smem_max = 227 * 1024;
         int threads = VALIDITY_THREADS;
         while (threads > 32 && per_thread * threads > smem_max) {
@@ -562,7 +829,76 @@ static size_t validity_smem(const smplgpu_ctx* ctx)
 {
     // slot storage + the edge kernel's offsets / verdict scratch
     return (size_t)ctx->h_model->n_slots * 12 * sizeof(double) * ctx->validity_threads
-           + (2 * (size_t)ctx->validity_threads + 2) * sizeof(int);
+           + (3 * (size_t)ctx->validity_threads + 2) * sizeof(int);
+}
+
+static int ensure_unc(smplgpu_ctx* ctx, size_t n)
+{
+    if (n <= ctx->unc_cap) {
+        return 0;
+    }
+    if (ctx->d_unc_list) { CU(cudaFree(ctx->d_unc_list)); ctx->d_unc_list = nullptr; ctx->unc_cap = 0; }
+    const size_t cap = std::max(n, (size_t)1 << 16);
+    CU(cudaMalloc(&ctx->d_unc_list, cap * sizeof(int)));
+    ctx->unc_cap = cap;
+    return 0;
+}
+
+static bool use_f32(const smplgpu_ctx* ctx)
+{
+    return ctx->precision_mode == SMPLGPU_PRECISION_CERTIFIED_F32 && ctx->has_model32;
+}
+
+// CollisionSpace::isStateValid for n resident states: the certified single-precision pass, then the
+// double-precision kernel on the states it could not decide (or the double kernel alone in EXACT mode)
+static int launch_states(smplgpu_ctx* ctx, const double* dq, int n, uint8_t* dv)
+{
+    const int vt = ctx->validity_threads;
+    if (!use_f32(ctx)) {
+        states_valid_kernel<<<(n + vt - 1) / vt, vt, validity_smem(ctx), ctx->stream>>>(
+            ctx->d_model, ctx->d_df, ctx->grid, dq, n, dv, ctx->d_stats, nullptr, nullptr);
+        ++ctx->launches;
+        CU(cudaGetLastError());
+        return 0;
+    }
+    int r = ensure_unc(ctx, (size_t)n);
+    if (r) return r;
+    CU(cudaMemsetAsync(ctx->d_unc_count, 0, sizeof(int), ctx->stream));
+    const int t32 = ctx->v32_threads;
+    states_valid32_kernel<<<(n + t32 - 1) / t32, t32, v32_smem(ctx), ctx->stream>>>(
+        ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq, n, dv, ctx->d_unc_list,
+        ctx->d_unc_count, ctx->d_stats);
+    const int blocks = std::max(1, std::min((n + vt - 1) / vt, 2 * ctx->sm_count));
+    states_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
+        ctx->d_model, ctx->d_df, ctx->grid, dq, n, dv, nullptr, ctx->d_unc_list, ctx->d_unc_count);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int launch_edges(smplgpu_ctx* ctx, const double* dq0, const double* dq1, int n, uint8_t* dv, int* dc)
+{
+    const int vt = ctx->validity_threads;
+    if (!use_f32(ctx)) {
+        edges_valid_kernel<<<(n + vt - 1) / vt, vt, validity_smem(ctx), ctx->stream>>>(
+            ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, n, dv, dc, ctx->d_stats, nullptr, nullptr);
+        ++ctx->launches;
+        CU(cudaGetLastError());
+        return 0;
+    }
+    int r = ensure_unc(ctx, (size_t)n);
+    if (r) return r;
+    CU(cudaMemsetAsync(ctx->d_unc_count, 0, sizeof(int), ctx->stream));
+    const int t32 = ctx->v32_threads;
+    edges_valid32_kernel<<<(n + t32 - 1) / t32, t32, v32_smem(ctx), ctx->stream>>>(
+        ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq0, dq1, n, dv, dc, ctx->d_unc_list,
+        ctx->d_unc_count, ctx->d_stats);
+    const int blocks = std::max(1, std::min((n + vt - 1) / vt, 2 * ctx->sm_count));
+    edges_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
+        ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, n, dv, nullptr, nullptr, ctx->d_unc_list, ctx->d_unc_count);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
 }
 
 int smplgpu_is_states_valid_dev(smplgpu_ctx* ctx, const double* q_dev, int n, uint8_t* verdict_dev)
@@ -573,13 +909,7 @@ int smplgpu_is_states_valid_dev(smplgpu_ctx* ctx, const double* q_dev, int n, ui
     if (n == 0) return 0;
     if (!q_dev || !verdict_dev) return fail(ctx, SMPLGPU_ERR_INVALID, "null device pointer");
     CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    const int vt = ctx->validity_threads;
-    const int blocks = (n + vt - 1) / vt;
-    states_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
-        ctx->d_model, ctx->d_df, ctx->grid, q_dev, n, verdict_dev, ctx->d_stats);
-    ++ctx->launches;
-    CU(cudaGetLastError());
-    return 0;
+    return launch_states(ctx, q_dev, n, verdict_dev);
 }
 
 int smplgpu_is_edges_valid_dev(smplgpu_ctx* ctx, const double* q0_dev, const double* q1_dev, int n,
@@ -591,37 +921,53 @@ int smplgpu_is_edges_valid_dev(smplgpu_ctx* ctx, const double* q0_dev, const dou
     if (n == 0) return 0;
     if (!q0_dev || !q1_dev || !verdict_dev) return fail(ctx, SMPLGPU_ERR_INVALID, "null device pointer");
     CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    const int vt = ctx->validity_threads;
-    const int blocks = (n + vt - 1) / vt;
-    edges_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
-        ctx->d_model, ctx->d_df, ctx->grid, q0_dev, q1_dev, n, verdict_dev, counts_dev, ctx->d_stats);
-    ++ctx->launches;
-    CU(cudaGetLastError());
-    return 0;
+    return launch_edges(ctx, q0_dev, q1_dev, n, verdict_dev, counts_dev);
 }
 
-// Host-pointer entry points: chunked, double-buffered through pinned memory so
-// the host->pinned copy of chunk k+1 overlaps the H2D/kernel/D2H of chunk k.
+// true when `p` is page-locked host memory the device can DMA from / to directly
+static bool is_pinned_host(const void* p)
+{
+    if (p == nullptr) {
+        return false;
+    }
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Host-pointer entry points.  The batch is cut into chunks; the host->device copy of chunk k+1 runs on a
+// second stream while the kernels of chunk k run, and verdicts stream back behind the kernels.  Page-locked
+// caller buffers are used as DMA source / target directly; pageable ones go through pinned staging.
 static int run_host_batched(smplgpu_ctx* ctx, const double* q0, const double* q1, int n,
                             uint8_t* verdict, int32_t* counts)
 {
     const int dof = ctx->h_model->dof;
     const bool edges = q1 != nullptr;
-    const int chunk = 1 << 18;
+    const int chunk = 1 << 17;
     const int cn = std::min(n, chunk);
     int r = ensure_state_buffers(ctx, (size_t)cn * 2, dof, edges); // two chunks in flight
     if (r) return r;
     const size_t row = (size_t)dof * sizeof(double);
-    const size_t in_bytes = (size_t)cn * row * (edges ? 2 : 1);
-    const size_t out_bytes = (size_t)cn * (1 + (counts ? sizeof(int) : 0));
-    r = grow_pinned(ctx, ctx->pinned, &ctx->pinned_cap, in_bytes);
-    if (r) return r;
-    r = grow_pinned(ctx, ctx->pinned_out, &ctx->pinned_out_cap, out_bytes + 16);
-    if (r) return r;
+    const bool in_direct = is_pinned_host(q0) && (!edges || is_pinned_host(q1));
+    const bool out_direct = is_pinned_host(verdict) && (!counts || is_pinned_host(counts));
+    if (!in_direct) {
+        r = grow_pinned(ctx, ctx->pinned, &ctx->pinned_cap, (size_t)cn * row * (edges ? 2 : 1));
+        if (r) return r;
+    }
+    if (!out_direct) {
+        r = grow_pinned(ctx, ctx->pinned_out, &ctx->pinned_out_cap, (size_t)cn * (1 + (counts ? sizeof(int) : 0)) + 16);
+        if (r) return r;
+    }
     CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    // the copy stream starts after whatever the caller queued on the compute stream
+    CU(cudaEventRecord(ctx->ev_in[0], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_in[0], 0));
 
     const int nchunks = (n + chunk - 1) / chunk;
-    auto drain = [&](int c) -> int {
+    auto drain = [&](int c) -> int {   // staged output of chunk c -> caller buffers
         const int b = c & 1;
         const int off = c * chunk;
         const int m = std::min(chunk, n - off);
@@ -636,42 +982,57 @@ static int run_host_batched(smplgpu_ctx* ctx, const double* q0, const double* q1
         const int b = c & 1;
         const int off = c * chunk;
         const int m = std::min(chunk, n - off);
-        if (c >= 2) {
-            r = drain(c - 2);
-            if (r) return r;
-        }
         double* dq0 = ctx->d_q0 + (size_t)b * cn * dof;
         double* dq1 = ctx->d_q1 + (size_t)b * cn * dof;
         uint8_t* dv = ctx->d_verdict + (size_t)b * cn;
         int* dc = ctx->d_counts + (size_t)b * cn;
-        uint8_t* pin = (uint8_t*)ctx->pinned[b];
-        memcpy(pin, q0 + (size_t)off * dof, (size_t)m * row);
-        CU(cudaMemcpyAsync(dq0, pin, (size_t)m * row, cudaMemcpyHostToDevice, ctx->stream));
-        if (edges) {
-            memcpy(pin + (size_t)cn * row, q1 + (size_t)off * dof, (size_t)m * row);
-            CU(cudaMemcpyAsync(dq1, pin + (size_t)cn * row, (size_t)m * row, cudaMemcpyHostToDevice, ctx->stream));
+        if (c >= 2) {
+            if (!out_direct) {
+                r = drain(c - 2);      // also proves the kernels of chunk c-2 are done with buffer b
+                if (r) return r;
+            } else if (!in_direct) {
+                CU(cudaEventSynchronize(ctx->ev[b]));
+            }
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[b], 0));   // device buffer b is free again
         }
-        const int vt = ctx->validity_threads;
-        const int blocks = (m + vt - 1) / vt;
+        const double* s0 = q0 + (size_t)off * dof;
+        const double* s1 = edges ? q1 + (size_t)off * dof : nullptr;
+        if (!in_direct) {
+            uint8_t* pin = (uint8_t*)ctx->pinned[b];
+            memcpy(pin, s0, (size_t)m * row);
+            s0 = (const double*)pin;
+            if (edges) {
+                memcpy(pin + (size_t)cn * row, s1, (size_t)m * row);
+                s1 = (const double*)(pin + (size_t)cn * row);
+            }
+        }
+        CU(cudaMemcpyAsync(dq0, s0, (size_t)m * row, cudaMemcpyHostToDevice, ctx->copy_stream));
         if (edges) {
-            edges_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
-                ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, m, dv, counts ? dc : nullptr, ctx->d_stats);
+            CU(cudaMemcpyAsync(dq1, s1, (size_t)m * row, cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+        CU(cudaEventRecord(ctx->ev_in[b], ctx->copy_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        r = edges ? launch_edges(ctx, dq0, dq1, m, dv, counts ? dc : nullptr) : launch_states(ctx, dq0, m, dv);
+        if (r) return r;
+        if (out_direct) {
+            CU(cudaMemcpyAsync(verdict + off, dv, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+            if (counts) {
+                CU(cudaMemcpyAsync(counts + off, dc, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            }
         } else {
-            states_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
-                ctx->d_model, ctx->d_df, ctx->grid, dq0, m, dv, ctx->d_stats);
-        }
-        ++ctx->launches;
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(ctx->pinned_out[b], dv, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
-        if (counts) {
-            CU(cudaMemcpyAsync((uint8_t*)ctx->pinned_out[b] + (((size_t)m + 15) / 16) * 16, dc, (size_t)m * sizeof(int),
-                               cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->pinned_out[b], dv, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+            if (counts) {
+                CU(cudaMemcpyAsync((uint8_t*)ctx->pinned_out[b] + (((size_t)m + 15) / 16) * 16, dc, (size_t)m * sizeof(int),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+            }
         }
         CU(cudaEventRecord(ctx->ev[b], ctx->stream));
     }
-    for (int c = std::max(0, nchunks - 2); c < nchunks; ++c) {
-        r = drain(c);
-        if (r) return r;
+    if (!out_direct) {
+        for (int c = std::max(0, nchunks - 2); c < nchunks; ++c) {
+            r = drain(c);
+            if (r) return r;
+        }
     }
     CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -697,6 +1058,55 @@ int smplgpu_is_edges_valid(smplgpu_ctx* ctx, const double* q0, const double* q1,
     if (n == 0) return 0;
     if (!q0 || !q1 || !verdict) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
     return run_host_batched(ctx, q0, q1, n, verdict, waypoint_counts);
+}
+
+int smplgpu_set_precision_mode(smplgpu_ctx* ctx, int mode)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    if (mode != SMPLGPU_PRECISION_CERTIFIED_F32 && mode != SMPLGPU_PRECISION_EXACT_F64)
+        return fail(ctx, SMPLGPU_ERR_INVALID, "unknown precision mode %d", mode);
+    ctx->precision_mode = mode;
+    return 0;
+}
+
+int smplgpu_certified_bounds(smplgpu_ctx* ctx, double* e_pos, double* eps_cells)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    if (e_pos) *e_pos = ctx->e_pos;
+    if (eps_cells) *eps_cells = ctx->eps_cells;
+    return ctx->has_model32 ? 1 : 0;
+}
+
+int smplgpu_last_f64_resolved(smplgpu_ctx* ctx, int64_t* items)
+{
+    if (!ctx || !items) return SMPLGPU_ERR_INVALID;
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *items = (int64_t)ctx->h_stats[3];
+    return 0;
+}
+
+int smplgpu_fk_sphere_centers_f32(smplgpu_ctx* ctx, const double* q, int n, float* out)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_model32) return fail(ctx, SMPLGPU_ERR_STATE, "single-precision model not built (robot + distance field needed)");
+    if (n == 0) return 0;
+    if (!q || !out) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    const int dof = ctx->h_model->dof, nn = ctx->h_model->n_nodes;
+    const size_t qb = (size_t)n * dof * sizeof(double), ob = (size_t)n * nn * 3 * sizeof(float);
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, qb + ob + 64);
+    if (r) return r;
+    double* dq = (double*)ctx->d_misc;
+    float* dout = (float*)(dq + (size_t)n * dof);
+    CU(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(dout, 0, ob, ctx->stream));
+    const int t32 = ctx->v32_threads;
+    fk_centers32_kernel<<<(n + t32 - 1) / t32, t32, v32_smem(ctx), ctx->stream>>>(ctx->d_blob, ctx->blob_words, dq, n, dout);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 int smplgpu_last_validity_stats(smplgpu_ctx* ctx, int64_t* df_lookups, int64_t* pair_tests, int64_t* waypoints)
@@ -1129,13 +1539,12 @@ int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, c
     int* dg = dh + n;
     uint8_t* dv = (uint8_t*)(dg + n);
     CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    const int vt = ctx->validity_threads;
-    edges_valid_kernel<<<(n + vt - 1) / vt, vt, validity_smem(ctx), ctx->stream>>>(
-        ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, n, dv, nullptr, ctx->d_stats);
+    r = launch_edges(ctx, dq0, dq1, n, dv, nullptr);
+    if (r) return r;
     expand_info_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(
         ctx->d_model, ctx->grid, ctx->bank.dist, ctx->bank.DX, ctx->bank.DY, ctx->bank_slot_dz, dq1, dslot, n,
         cost_per_cell, dh, dg, doff);
-    ctx->launches += 2;
+    ++ctx->launches;
     CU(cudaGetLastError());
     uint8_t* pout = (uint8_t*)ctx->pinned_out[0];
     const size_t o_bytes = (size_t)n * (3 * sizeof(double) + 2 * sizeof(int) + 1);

@@ -315,17 +315,19 @@ __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long 
     }
 }
 
-// CollisionSpace::isStateValid, batched
+// CollisionSpace::isStateValid, batched.  With `list` the kernel resolves only the states the
+// single-precision pass (validity32.cuh) could not decide: item k is state list[k], k < *list_n.
 __global__ void __launch_bounds__(VALIDITY_THREADS)
 states_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ df, GridParams G,
                     const double* __restrict__ q, int n, uint8_t* __restrict__ verdict,
-                    unsigned long long* stats)
+                    unsigned long long* stats, const int* __restrict__ list, const int* __restrict__ list_n)
 {
     extern __shared__ double smem[];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = list != nullptr ? min(*list_n, n) : n;
     Counters cnt = { 0u, 0u, 0u };
-    if (i < n) {
-        cnt.waypoints = 1;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        const int i = list != nullptr ? list[k] : k;
+        ++cnt.waypoints;
         const bool ok = check_state(M, df, G, q + (size_t)i * M->dof, nullptr, 0.0, smem, cnt);
         verdict[i] = ok ? 1 : 0;
     }
@@ -342,96 +344,104 @@ states_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__
 // the reference); a waypoint is skipped once its edge is known to be invalid.
 //
 // Dynamic shared memory: slot storage (n_slots*12*blockDim doubles) followed by
-// (blockDim + 1) ints of offsets and blockDim ints of per-edge verdicts.
+// (blockDim + 1) ints of offsets, blockDim ints of per-edge verdicts and blockDim edge ids.
 __global__ void __launch_bounds__(VALIDITY_THREADS)
 edges_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ df, GridParams G,
                    const double* __restrict__ q0, const double* __restrict__ q1, int n,
-                   uint8_t* __restrict__ verdict, int* __restrict__ counts, unsigned long long* stats)
+                   uint8_t* __restrict__ verdict, int* __restrict__ counts, unsigned long long* stats,
+                   const int* __restrict__ list, const int* __restrict__ list_n)
 {
     extern __shared__ double smem[];
     int* s_off = reinterpret_cast<int*>(smem + (size_t)M->n_slots * 12 * blockDim.x);
     int* s_ok = s_off + blockDim.x + 1;
+    int* s_eid = s_ok + blockDim.x;
     const int tid = threadIdx.x;
-    const int first = blockIdx.x * blockDim.x;
-    const int i = first + tid;
     const int dof = M->dof;
+    const int total_edges = list != nullptr ? min(*list_n, n) : n;
     Counters cnt = { 0u, 0u, 0u };
 
-    int count = 0;
-    if (i < n) {
-        const double* a = q0 + (size_t)i * dof;
-        const double* b = q1 + (size_t)i * dof;
-        // RobotMotionCollisionModel::getMaxSphereMotion(start, finish, variables)
-        double motion = 0.0;
-        for (int v = 0; v < dof; ++v) {
-            const int ty = M->var_type[v];
-            double dist;
-            if (ty == 1) {          // continuous
-                dist = fabs(normalize_angle(b[v] - a[v]));
-                motion += M->var_weight[v] * dist;
-            } else if (ty == 0) {   // revolute
-                dist = fabs(b[v] - a[v]);
-                motion += M->var_weight[v] * dist;
-            } else {                // prismatic
-                dist = fabs(b[v] - a[v]);
-                motion += dist;
+    // with `list` (edges the single-precision pass could not decide) a block walks several chunks
+    for (int first = blockIdx.x * blockDim.x; first < total_edges; first += gridDim.x * blockDim.x) {
+        const int k = first + tid;
+        const int i = k < total_edges ? (list != nullptr ? list[k] : k) : -1;
+        int count = 0;
+        if (i >= 0) {
+            const double* a = q0 + (size_t)i * dof;
+            const double* b = q1 + (size_t)i * dof;
+            // RobotMotionCollisionModel::getMaxSphereMotion(start, finish, variables)
+            double motion = 0.0;
+            for (int v = 0; v < dof; ++v) {
+                const int ty = M->var_type[v];
+                double dist;
+                if (ty == 1) {          // continuous
+                    dist = fabs(normalize_angle(b[v] - a[v]));
+                    motion += M->var_weight[v] * dist;
+                } else if (ty == 0) {   // revolute
+                    dist = fabs(b[v] - a[v]);
+                    motion += M->var_weight[v] * dist;
+                } else {                // prismatic
+                    dist = fabs(b[v] - a[v]);
+                    motion += dist;
+                }
+            }
+            // fillMotionInterpolation + setWaypointCount
+            if (motion != 0.0) {
+                count = max(2, (int)ceil(motion / 0.05) + 1);
+            }
+            if (counts != nullptr) {
+                counts[i] = count;
             }
         }
-        // fillMotionInterpolation + setWaypointCount
-        if (motion != 0.0) {
-            count = max(2, (int)ceil(motion / 0.05) + 1);
-        }
-        if (counts != nullptr) {
-            counts[i] = count;
-        }
-    }
-    // block-wide inclusive scan of the counts (Hillis-Steele over <= 128 entries)
-    s_off[tid + 1] = count;
-    s_ok[tid] = 1;
-    if (tid == 0) {
-        s_off[0] = 0;
-    }
-    __syncthreads();
-    for (int d = 1; d < (int)blockDim.x; d <<= 1) {
-        int add = 0;
-        if (tid + 1 > d) {
-            add = s_off[tid + 1 - d];
+        // block-wide inclusive scan of the counts (Hillis-Steele over <= 128 entries)
+        s_off[tid + 1] = count;
+        s_ok[tid] = 1;
+        s_eid[tid] = i;
+        if (tid == 0) {
+            s_off[0] = 0;
         }
         __syncthreads();
-        s_off[tid + 1] += add;
-        __syncthreads();
-    }
-    const int total = s_off[blockDim.x];
+        for (int d = 1; d < (int)blockDim.x; d <<= 1) {
+            int add = 0;
+            if (tid + 1 > d) {
+                add = s_off[tid + 1 - d];
+            }
+            __syncthreads();
+            s_off[tid + 1] += add;
+            __syncthreads();
+        }
+        const int total = s_off[blockDim.x];
 
-    for (int item = tid; item < total; item += blockDim.x) {
-        // edge of this item: largest e with s_off[e] <= item
-        int lo = 0, hi = blockDim.x;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_off[mid] <= item) {
-                lo = mid;
-            } else {
-                hi = mid;
+        for (int item = tid; item < total; item += blockDim.x) {
+            // edge of this item: largest e with s_off[e] <= item
+            int lo = 0, hi = blockDim.x;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= item) {
+                    lo = mid;
+                } else {
+                    hi = mid;
+                }
+            }
+            const int e = lo;
+            if (s_ok[e] == 0) {
+                continue; // edge already invalid
+            }
+            const int w = item - s_off[e];
+            const int cnt_e = s_off[e + 1] - s_off[e];
+            const double inv = 1.0 / (double)(cnt_e - 1);     // m_waypoint_count_inv
+            const double alpha = (double)w * inv;             // interpolate(n): alpha = n * inv
+            const double* a = q0 + (size_t)s_eid[e] * dof;
+            const double* b = q1 + (size_t)s_eid[e] * dof;
+            ++cnt.waypoints;
+            if (!check_state(M, df, G, a, b, alpha, smem, cnt)) {
+                s_ok[e] = 0;
             }
         }
-        const int e = lo;
-        if (s_ok[e] == 0) {
-            continue; // edge already invalid
+        __syncthreads();
+        if (i >= 0) {
+            verdict[i] = s_ok[tid] ? 1 : 0;
         }
-        const int w = item - s_off[e];
-        const int cnt_e = s_off[e + 1] - s_off[e];
-        const double inv = 1.0 / (double)(cnt_e - 1);     // m_waypoint_count_inv
-        const double alpha = (double)w * inv;             // interpolate(n): alpha = n * inv
-        const double* a = q0 + (size_t)(first + e) * dof;
-        const double* b = q1 + (size_t)(first + e) * dof;
-        ++cnt.waypoints;
-        if (!check_state(M, df, G, a, b, alpha, smem, cnt)) {
-            s_ok[e] = 0;
-        }
-    }
-    __syncthreads();
-    if (i < n) {
-        verdict[i] = s_ok[tid] ? 1 : 0;
+        __syncthreads();
     }
     flush_counters(cnt, stats);
 }
