@@ -195,6 +195,10 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1 << 19, help="states (and edges) timed on the CPU oracle")
     ap.add_argument("--ref-sample", type=int, default=1 << 17)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--plan-queries", type=int, default=512, help="planning queries per GPU (0 = skip)")
+    ap.add_argument("--plan-concurrent", type=int, default=512)
+    ap.add_argument("--plan-max-expansions", type=int, default=2000)
+    ap.add_argument("--plan-cpu-queries", type=int, default=12)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "smpl_b200" else args.warmup
 
@@ -351,6 +355,36 @@ def main():
                "mvoxel_s": nb ** 3 / (bfs_ms * 1e-3) / 1e6,
                "algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (bfs_ms * 1e-3) / 1e9}
 
+    # ---- plan queries/s (config[0]/[3] shape): PR2 right arm on the tabletop scene, queries sharded over ranks ----
+    plan = None
+    if args.plan_queries > 0:
+        pscene = scenes.pr2_tabletop_scene()
+        pctx, ptables = api.setup_context(pscene, device=local_rank)
+        pparams = scenes.PlanParams(pscene.dof)
+        pparams.max_expansions = args.plan_max_expansions
+        nq_total = args.plan_queries * world
+        starts_all, goals_all = scenes.tabletop_queries(nq_total, seed=13)
+        mine = np.arange(rank, nq_total, world)          # round-robin sharding, no collective
+        n_thr = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
+        api.plan_batch(pctx, pscene, ptables, pparams, starts_all[mine][:8], goals_all[mine][:8], max_concurrent=8)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        pres, pstats = api.plan_batch(pctx, pscene, ptables, pparams, starts_all[mine], goals_all[mine],
+                                      max_concurrent=args.plan_concurrent, n_threads=n_thr)
+        dt = time.perf_counter() - t0
+        t_plan = torch.tensor([dt], device=dev, dtype=torch.float64)
+        n_exp = torch.tensor([float(sum(r["expansions"] for r in pres)), float(sum(r["success"] for r in pres))],
+                             device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_plan, op=dist.ReduceOp.MAX)
+            dist.all_reduce(n_exp, op=dist.ReduceOp.SUM)
+        plan = {"scene": "PR2 right arm, tabletop env, 150^3 field @ 2 cm, ARA* eps 100, first solution, <= %d expansions" % args.plan_max_expansions,
+                "queries": nq_total, "solved": int(n_exp[1].item()), "expansions": int(n_exp[0].item()),
+                "seconds": float(t_plan.item()), "queries_per_s": nq_total / float(t_plan.item()),
+                "expansions_per_s": float(n_exp[0].item()) / float(t_plan.item()), "concurrent_per_gpu": args.plan_concurrent,
+                "rank0": pstats}
+        pctx.close()
+
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -377,6 +411,20 @@ def main():
         cpu = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "%d states + %d edges of the same workload, oracle (CPU port of sbpl_collision_checking), 1 thread; "
                          "states %.0f/s, edge waypoints %.0f/s" % (m, m, m / t_s, int(c.sum()) / t_e)}
+        if plan is not None and args.plan_cpu_queries > 0:
+            po = make_oracle(pscene, np.zeros(pscene.dof))
+            po.init_kdl(pscene.chain_root, pscene.chain_tip, pscene.planning_link, pscene.T_kin_to_planning, pscene.xyz_offset)
+            k = min(args.plan_cpu_queries, len(starts_all))
+            secs, cexp = 0.0, 0
+            for s_, g_ in zip(starts_all[:k], goals_all[:k]):
+                po.heur_init(pscene.inflation_radius, pscene.cost_per_cell)
+                t0 = time.perf_counter()
+                pr = po.plan(s_, g_, pparams)
+                secs += time.perf_counter() - t0      # includes the per-query BFS, as the GPU figure does
+                cexp += pr["expansions"]
+            plan["cpu_queries_per_s"] = k / secs
+            plan["cpu_expansions_per_s"] = cexp / secs
+            plan["cpu_sample"] = "first %d queries, oracle ManipLattice + ARA*, 1 thread" % k
         if bfs is not None:
             mv, kind, dt = cpu_bfs_rate(args.bfs_n)
             bfs["cpu_mvoxel_s"] = mv
@@ -418,6 +466,8 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "bfs": bfs,
+        "plan": plan,
+        "host_cores": os.cpu_count(),
         "gpu_stats_last_launch": gpu_stats,
     }
     print(json.dumps(line))

@@ -248,6 +248,9 @@ int smplgpu_fk_sphere_centers_f32(smplgpu_ctx* ctx, const double* q, int n, floa
 int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radius);
 /* BFS_3D::run for every slot: seeds_xyz[n_slots][3]; a slot whose seed is out of bounds is left undiscovered */
 int smplgpu_bfs_bank_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz);
+/* The same for n listed slots only (slots[n], seeds_xyz[n][3]); the other slots keep their distances, so a
+ * finished query's slot can be handed to the next query while the rest keep searching */
+int smplgpu_bfs_bank_run_slots(smplgpu_ctx* ctx, const int32_t* slots, const int32_t* seeds_xyz, int n);
 /* BFS_3D::getDistance(cell) of slot[i] */
 int smplgpu_bfs_bank_distances(smplgpu_ctx* ctx, const int32_t* slot, const int32_t* cells_xyz, int n, int32_t* out);
 /* One ManipLattice::GetSuccs worth of device work for MANY expansions at once

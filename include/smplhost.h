@@ -72,12 +72,14 @@ typedef struct smplhost_plan_params
     double origin[3];               /* grid geometry (OccupancyGrid), for the goal cell */
     double res;
     int dims[3];
+    int n_threads;                  /* host threads for the per-query work (>= 1); results do not depend on it */
 } smplhost_plan_params;
 
 /* Plans nq queries (starts[nq][dof], goals[nq][3]) with at most max_concurrent searches in flight.
  * summary[nq][5] = success, expansions, cost, path length, lattice states created;
  * path_ids[nq][max_path] = state ids of the path (goal state id = 0, start = 1), truncated to max_path;
- * stats[6] = rounds, edges submitted, device calls, seconds inside smplgpu_* calls, host seconds, total seconds.
+ * stats[7] = rounds, edges submitted, device calls, seconds inside smplgpu_* calls, host seconds, total seconds,
+ * BFS bank runs.
  * Returns 0, or a negative smplgpu error code (smplhost_last_error() has the text). */
 int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* params, const double* starts,
                         const double* goals, int nq, int max_concurrent, int32_t* summary, int32_t* path_ids,

@@ -43,7 +43,7 @@ class PlanParamsC(C.Structure):
                 ("epsilon", C.c_double), ("max_expansions", C.c_int), ("xyz_tolerance", C.c_double * 3),
                 ("cost_per_cell", C.c_int), ("inflation_radius", C.c_double), ("var_min", c_double_p),
                 ("var_max", c_double_p), ("var_continuous", c_uint8_p), ("origin", C.c_double * 3),
-                ("res", C.c_double), ("dims", C.c_int * 3)]
+                ("res", C.c_double), ("dims", C.c_int * 3), ("n_threads", C.c_int)]
 
 
 def gpu_lib():
@@ -93,6 +93,7 @@ def gpu_lib():
         L.smplgpu_fk_sphere_centers_f32.argtypes = [vp, dp, i, C.POINTER(C.c_float)]
         L.smplgpu_bfs_bank_create.argtypes = [vp, i, d]
         L.smplgpu_bfs_bank_run.argtypes = [vp, ip]
+        L.smplgpu_bfs_bank_run_slots.argtypes = [vp, ip, ip, i]
         L.smplgpu_bfs_bank_distances.argtypes = [vp, ip, ip, i, ip]
         L.smplgpu_expand_batch.argtypes = [vp, dp, dp, ip, i, i, bp, ip, ip, dp]
         _gpu = L
@@ -525,7 +526,7 @@ class Adapters:
         return self.H.smplhost_heur_metric_goal_distance(self.h, float(x), float(y), float(z))
 
 
-def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max_path=512):
+def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max_path=512, n_threads=1):
     """smplhost_plan_batch: many ARA* queries in lock step, one device call per round.
     params: smpl_b200.scenes.PlanParams.  Returns (list of dict per query, stats dict)."""
     H = host_lib()
@@ -545,13 +546,14 @@ def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max
     P.cost_per_cell, P.inflation_radius = int(scene.cost_per_cell), float(scene.inflation_radius)
     P.var_min, P.var_max, P.var_continuous = _dp(lo), _dp(hi), _bp(cont)
     P.res = float(scene.res)
+    P.n_threads = int(n_threads)
     for a in range(3):
         P.xyz_tolerance[a] = float(params.xyz_tolerance[a])
         P.origin[a] = float(scene.origin[a])
         P.dims[a] = int(scene.dims[a])
     summary = np.zeros((nq, 5), np.int32)
     paths = np.full((nq, max_path), -1, np.int32)
-    stats = np.zeros(6)
+    stats = np.zeros(8)
     r = H.smplhost_plan_batch(ctx.h, C.byref(P), _dp(starts), _dp(goals), nq, int(max_concurrent), _ip(summary),
                               _ip(paths), int(max_path), _dp(stats))
     if r != 0:
@@ -562,7 +564,8 @@ def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max
         out.append(dict(success=bool(summary[i, 0]), expansions=int(summary[i, 1]), cost=int(summary[i, 2]),
                         path_ids=paths[i, :min(n, max_path)].copy(), num_states=int(summary[i, 4])))
     st = dict(rounds=int(stats[0]), edges_submitted=int(stats[1]), device_calls=int(stats[2]),
-              device_seconds=float(stats[3]), host_seconds=float(stats[4]), total_seconds=float(stats[5]))
+              device_seconds=float(stats[3]), host_seconds=float(stats[4]), total_seconds=float(stats[5]),
+              bfs_runs=int(stats[6]), n_threads=int(n_threads))
     return out, st
 
 

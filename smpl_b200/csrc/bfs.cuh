@@ -39,10 +39,10 @@ struct BfsGrid
     uint32_t* front0;
     uint32_t* front1;
     // candidate words, ping-ponged by level parity: level L writes [L&1] and reads [(L-1)&1]
-    uint32_t* cand0;          // [rows] (level << 9) | mask of neighbour rows that got cells at `level`
+    uint32_t* cand0;          // [rows] neighbour-row mask (bits 0-8) | published words mod 16 (bits 9-24)
     uint32_t* cand1;
     int* dist;             // [DZ*DY*DX]
-    int* ctrl;             // [0] = levels run, [1..3] = rotating new-cell flags
+    int* ctrl;             // [0] = levels run, [4..5] = 64-bit grid barrier word (arrivals | blocks with new cells << 32)
 };
 
 
@@ -74,12 +74,18 @@ __global__ void bfs_walls_from_bytes_kernel(BfsGrid g, const uint8_t* __restrict
 // BfsHeuristic::syncGridAndBfs: wall iff d2(cell) <= d2_wall_max  (<=> res*sqrt(d2) <= radius)
 // slot_dz: padded z extent of one slot when several BFS_3D instances are stacked along z
 // (== g.DZ for a single grid); every slot gets its own border shell.
+// slot_mask (optional): only slots with a non-zero entry are rewritten.
 __global__ void bfs_walls_from_df_kernel(BfsGrid g, const uint16_t* __restrict__ df, int d2_wall_max,
-                                         int slot_dz, unsigned int* __restrict__ wall_count)
+                                         int slot_dz, unsigned int* __restrict__ wall_count,
+                                         const uint8_t* __restrict__ slot_mask)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int cnt = 0;
-    if (idx < g.rows * g.W) {
+    bool on = idx < g.rows * g.W;
+    if (on && slot_mask != nullptr) {
+        on = slot_mask[(idx / g.W / g.DY) / slot_dz] != 0;
+    }
+    if (on) {
         const int row = idx / g.W, w = idx - row * g.W;
         const int zt = row / g.DY, y = row - zt * g.DY;
         const int z = zt % slot_dz;           // z within the slot
@@ -110,29 +116,51 @@ __global__ void bfs_walls_from_df_kernel(BfsGrid g, const uint16_t* __restrict__
     }
 }
 
-// BFS_3D::run reset: non-walls -> UNDISCOVERED, blocked = wall, stamps cleared
-__global__ void bfs_reset_kernel(BfsGrid g)
+// BFS_3D::run reset: non-walls -> UNDISCOVERED, blocked = wall, stamps cleared.
+// slot_mask (optional): only the masked slots of a stacked bank are reset (candidate stamps always are).
+// One warp per bitmap word: lane b writes the distance of bit b, so a word's 32 distances go out as one
+// coalesced 128-byte store.
+__global__ void bfs_reset_kernel(BfsGrid g, const uint8_t* __restrict__ slot_mask, int slot_dz)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < g.rows) {
-        g.cand0[idx] = 0;
-        g.cand1[idx] = 0;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < g.rows) {
+        g.cand0[tid] = 0;
+        g.cand1[tid] = 0;
     }
-    if (idx < 4) {
-        g.ctrl[idx] = 0;
+    if (tid < 8) {
+        g.ctrl[tid] = 0;
     }
-    if (idx >= g.rows * g.W) {
-        return;
-    }
-    const uint32_t wbits = g.wall[idx];
-    g.blocked[idx] = wbits;
-    g.front0[idx] = 0;
-    g.front1[idx] = 0;
-    const int row = idx / g.W, w = idx - row * g.W;
-    int* d = g.dist + (size_t)row * g.DX + w * 32;
-    const int xmax = min(32, g.DX - w * 32);
-    for (int b = 0; b < xmax; ++b) {
-        d[b] = ((wbits >> b) & 1u) ? 0x7FFFFFFF : -1;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = g.rows * g.W;
+    for (int base = (tid >> 5) * 32; base < total; base += nwarps * 32) {
+        // lane l owns word base + l for the bitmap stores
+        const int idx = base + lane;
+        uint32_t wbits = 0;
+        bool on = idx < total;
+        if (on && slot_mask != nullptr) {
+            on = slot_mask[(idx / g.W / g.DY) / slot_dz] != 0;
+        }
+        if (on) {
+            wbits = g.wall[idx];
+            g.blocked[idx] = wbits;
+            g.front0[idx] = 0;
+            g.front1[idx] = 0;
+        }
+        // distances: the warp walks its 32 words together
+        const uint32_t live = __ballot_sync(0xffffffffu, on);
+        for (int k = 0; k < 32; ++k) {
+            if (!((live >> k) & 1u)) {
+                continue;
+            }
+            const uint32_t wk = __shfl_sync(0xffffffffu, wbits, k);
+            const int id = base + k;
+            const int row = id / g.W, w = id - row * g.W;
+            const int x = w * 32 + lane;
+            if (x < g.DX) {
+                g.dist[(size_t)row * g.DX + x] = ((wk >> lane) & 1u) ? 0x7FFFFFFF : -1;
+            }
+        }
     }
 }
 
@@ -159,7 +187,7 @@ __global__ void bfs_seed_kernel(BfsGrid g, const int* __restrict__ seeds, int n_
     g.dist[(size_t)row * g.DX + px] = 0;
     // level 0 published to the nine neighbour rows: the seed row is neighbour k of (pz - dz, py - dy)
     for (int k = 0; k < 9; ++k) {
-        atomicOr(&g.cand0[(pz - (k / 3 - 1)) * g.DY + (py - (k % 3 - 1))], 1u << k);
+        atomicOr(&g.cand0[(pz - (k / 3 - 1)) * g.DY + (py - (k % 3 - 1))], (1u << k) | (1u << (9 + ((px >> 5) & 15))));
     }
 }
 
@@ -179,138 +207,218 @@ __device__ __forceinline__ uint32_t gather9(const uint32_t* __restrict__ fr, con
     return m;
 }
 
-constexpr int BFS_THREADS = 512;
+constexpr int BFS_THREADS = 1024;      // one block per SM
+constexpr int BFS_ROWS_PER_THREAD = 2; // candidate words a thread fetches per batch (issued together)
+constexpr int BFS_ITEM_CAP = 5120;     // (row, word) work items a block holds at a time
 
-// All levels in one cooperative launch.
+// Grid-wide barrier for a cooperative (co-resident) launch with one block per SM.  One 64-bit counter
+// carries the arrivals (low word) and the number of blocks that discovered cells at this level (high
+// word), so leaving the barrier also answers "did anything happen" without another round trip.
+__device__ __forceinline__ unsigned long long grid_barrier(unsigned long long* counter, unsigned int target, bool block_new)
+{
+    __shared__ unsigned long long s_seen;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ull | ((unsigned long long)(block_new ? 1u : 0u) << 32));
+        unsigned long long v;
+        do {
+            v = *((volatile unsigned long long*)counter);
+        } while ((unsigned int)v < target);
+        __threadfence();
+        s_seen = v;
+    }
+    __syncthreads();
+    return s_seen;
+}
+
+// All levels in one cooperative launch, one block per SM.
 //
-// cand[p][row] = (level << 9) | mask9: bit k of mask9 says that neighbour row k of
-// `row` received frontier cells at `level` (parity p = level & 1).  A row that gets
-// new cells at level L publishes itself to its nine (y,z) neighbours with
-// atomicMax (moves the word to level L, clearing older mask bits) + atomicOr.
-// Level L+1 scans cand[L & 1]: rows are interleaved over warps (row = warp + j *
-// nwarps) so the wavefront's rows spread evenly, each lane loads one word,
-// __ballot_sync/__ffs compacts the candidates, and the warp then expands two
-// candidate rows at a time, one per half-warp (lanes = 32-bit words of the row).
+// cand[p][row] (p = parity of the level that wrote it): bits 0-8 = which of the nine (y,z) neighbour rows of
+// `row` received frontier cells, bits 9-24 = in which 32-bit words (word index mod 16).  A (row, word) that
+// gets new cells at level L publishes itself to its nine neighbour rows with one atomicOr each; the row's
+// scanner at level L+1 reads the word and clears it for level L+3.
 //
-// ctrl[1..3] are rotating "new cells at level L" flags: flag[L%3] is set during
-// level L and read after the barrier; flag[(L+1)%3] is cleared during level L (its
-// last readers ran before the previous barrier): one grid barrier per level.
-__global__ void __launch_bounds__(BFS_THREADS, 3)
+// Level L+1: rows are dealt to the blocks in groups of eight (one 32-byte sector of candidate words; every
+// block sees a thin slice of the whole grid, which balances the wavefront across SMs).  A block fetches its
+// candidate words, turns each candidate row into (row, word) items for the words that can change (published
+// words dilated by one), compacts them into a shared-memory list (warp scan + one shared atomic per warp) and
+// then expands the list ONE LANE PER ITEM: OR of the active neighbour rows' frontier words, x-dilation by
+// shifts with the edge bits of the neighbouring words, `& ~blocked`, distance stores for the new bits, and
+// the nine publishes.  A wavefront face perpendicular to x touches one word per row, so this costs one lane
+// per row instead of a half-warp.
+//
+// Frontier words are only current for the words a row published; a stale word holds cells discovered two
+// levels earlier, whose neighbours are all discovered already, so whatever it contributes is removed by
+// `& ~blocked`.
+__global__ void __launch_bounds__(BFS_THREADS, 1)
 bfs_levels_kernel(const __grid_constant__ BfsGrid g, int max_levels)
 {
-    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t s_item[BFS_ITEM_CAP];   // row
+    __shared__ uint32_t s_info[BFS_ITEM_CAP];   // word | nbrmask << 8 | has_left << 17 | has_right << 18
+    __shared__ int s_warp_sum[BFS_THREADS / 32];
+    __shared__ int s_total;
     const int lane = threadIdx.x & 31;
-    const int half = lane >> 4, sl = lane & 15;
-    const int warps_per_block = blockDim.x >> 5;
-    const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    const int nwarps = gridDim.x * warps_per_block;
-    const int chunks = (g.W + 15) / 16;
+    const int warp = threadIdx.x >> 5;
+    const int groups = (g.rows + 7) / 8;                         // groups of 8 consecutive rows
+    const int slots = (groups + (int)gridDim.x - 1) / (int)gridDim.x * 8;   // row slots of this block
+    const uint32_t wmask_all = g.W >= 16 ? 0xFFFFu : ((1u << g.W) - 1u);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(&g.ctrl[4]);
+    unsigned int news_before = 0;
 
     uint32_t level = 1;
     for (; level <= (uint32_t)max_levels; ++level) {
         const bool odd = level & 1;
         const uint32_t* __restrict__ fcur = odd ? g.front0 : g.front1;
         uint32_t* __restrict__ fnext = odd ? g.front1 : g.front0;
-        const uint32_t prev = level - 1;
-        const uint32_t* __restrict__ cand_in = odd ? g.cand0 : g.cand1;
+        uint32_t* __restrict__ cand_in = odd ? g.cand0 : g.cand1;
         uint32_t* __restrict__ cand_out = odd ? g.cand1 : g.cand0;
-        int* newflag = &g.ctrl[1 + level % 3];
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            g.ctrl[1 + (level + 1) % 3] = 0;
-        }
         bool any_new = false;
-        for (int base = gwarp; base < g.rows; base += nwarps * 32) {
-            const int myrow = base + lane * nwarps;
-            uint32_t word = 0;
-            if (myrow < g.rows) {
-                word = __ldcg(&cand_in[myrow]);
-            }
-            uint32_t cmask = __ballot_sync(0xffffffffu, (word >> 9) == prev && (word & 0x1FFu) != 0);
-            while (cmask) {
-                // two candidates per pass, one per half-warp
-                const int j0 = __ffs(cmask) - 1;
-                cmask &= cmask - 1;
-                int j1 = -1;
-                if (cmask) {
-                    j1 = __ffs(cmask) - 1;
-                    cmask &= cmask - 1;
-                }
-                const int j = half ? j1 : j0;
-                const uint32_t w9 = __shfl_sync(0xffffffffu, word, j < 0 ? 0 : j);
-                int row = j < 0 ? -1 : base + j * nwarps;
-                int z = 0, y = 0;
-                if (row >= 0) {
-                    z = row / g.DY;
-                    y = row - z * g.DY;
-                    if (z == 0 || z == g.DZ - 1 || y == 0 || y == g.DY - 1) {
-                        row = -1; // border shell rows are all wall
-                    }
-                }
-                const uint32_t active9 = row >= 0 ? (w9 & 0x1FFu) : 0u;
-                bool row_new = false;
-                for (int c = 0; c < chunks; ++c) {
-                    const int w = c * 16 + sl;
-                    const bool on = row >= 0 && w < g.W;
-                    uint32_t m = 0, blk = 0xFFFFFFFFu;
-                    size_t idx = 0;
-                    if (on) {
-                        idx = (size_t)row * g.W + w;
-                        blk = __ldcg(&g.blocked[idx]);
-                        m = gather9(fcur, g, y, z, w, active9);
-                    }
-                    uint32_t left = __shfl_up_sync(0xffffffffu, m, 1, 16);
-                    uint32_t right = __shfl_down_sync(0xffffffffu, m, 1, 16);
-                    if (sl == 0) {
-                        left = (on && w > 0) ? gather9(fcur, g, y, z, w - 1, active9) : 0;
-                    }
-                    if (sl == 15) {
-                        right = (on && w + 1 < g.W) ? gather9(fcur, g, y, z, w + 1, active9) : 0;
-                    }
-                    uint32_t fresh = 0;
-                    if (on) {
-                        const uint32_t dil = m | (m << 1) | (m >> 1) | (left >> 31) | (right << 31);
-                        fresh = dil & ~blk;
-                        if (fresh) {
-                            g.blocked[idx] = blk | fresh;
-                        }
-                        fnext[idx] = fresh; // a published row has every word current
-                    }
-                    // distances: per non-empty word, two coalesced 64-byte stores per half-warp
-                    uint32_t nz = (__ballot_sync(0xffffffffu, fresh != 0) >> (half * 16)) & 0xFFFFu;
-                    row_new |= nz != 0;
-                    const uint32_t hmask = half ? 0xFFFF0000u : 0x0000FFFFu; // the halves loop independently
-                    while (nz) {
-                        const int k = __ffs(nz) - 1;
-                        nz &= nz - 1;
-                        const uint32_t wk = __shfl_sync(hmask, fresh, half * 16 + k);
-                        int* d = g.dist + (size_t)row * g.DX + (size_t)(c * 16 + k) * 32;
-                        if ((wk >> sl) & 1u) {
-                            d[sl] = (int)level;
-                        }
-                        if ((wk >> (sl + 16)) & 1u) {
-                            d[sl + 16] = (int)level;
-                        }
-                    }
-                }
-                if (row_new) {
-                    if (sl < 9) {
-                        // this row is neighbour k = sl of row (z - dz, y - dy)
-                        const int dz = sl / 3 - 1, dy = sl % 3 - 1;
-                        uint32_t* cw = &cand_out[(z - dz) * g.DY + (y - dy)];
-                        atomicMax(cw, level << 9);
-                        atomicOr(cw, 1u << sl);
-                    }
-                    any_new = true;
+
+        for (int t0 = 0; t0 < slots; t0 += BFS_THREADS * BFS_ROWS_PER_THREAD) {
+            // ---- fetch this thread's candidate words (independent loads, one latency) ----
+            int rows[BFS_ROWS_PER_THREAD];
+            uint32_t words[BFS_ROWS_PER_THREAD];
+#pragma unroll
+            for (int u = 0; u < BFS_ROWS_PER_THREAD; ++u) {
+                const int t = t0 + u * BFS_THREADS + threadIdx.x;
+                const int gi = blockIdx.x + (t >> 3) * gridDim.x;
+                rows[u] = gi * 8 + (t & 7);
+                words[u] = 0;
+                if (t < slots && gi < groups && rows[u] < g.rows) {
+                    words[u] = __ldcg(&cand_in[rows[u]]);
                 }
             }
+            // ---- items per candidate row: published words dilated by one ----
+            uint32_t dmask[BFS_ROWS_PER_THREAD];
+            int mine = 0;
+#pragma unroll
+            for (int u = 0; u < BFS_ROWS_PER_THREAD; ++u) {
+                dmask[u] = 0;
+                if (words[u] != 0) {
+                    cand_in[rows[u]] = 0;   // consumed; this array is written again two levels from now
+                    const int z = rows[u] / g.DY, y = rows[u] - z * g.DY;
+                    if (!(z == 0 || z == g.DZ - 1 || y == 0 || y == g.DY - 1)) {   // border shell rows are all wall
+                        const uint32_t wm = (words[u] >> 9) & 0xFFFFu;
+                        // word index is kept mod 16: with more than 16 words per row bit 15 neighbours bit 0
+                        uint32_t d = wm | (wm << 1) | (wm >> 1);
+                        if (g.W > 16) {
+                            d |= (wm >> 15) | (wm << 15);
+                        }
+                        dmask[u] = d & wmask_all;
+                    }
+                }
+                // with W > 16 every word congruent to a set bit becomes an item
+                int n = __popc(dmask[u]);
+                if (g.W > 16) {
+                    n = 0;
+                    for (int w = 0; w < g.W; ++w) n += (dmask[u] >> (w & 15)) & 1u;
+                }
+                mine += n;
+            }
+            // ---- block-wide exclusive scan of `mine` ----
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) {
+                s_warp_sum[warp] = incl;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int v = s_warp_sum[lane];
+                int inc2 = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int x = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if (lane >= o) inc2 += x;
+                }
+                s_warp_sum[lane] = inc2 - v;
+                if (lane == 31) {
+                    s_total = inc2;
+                }
+            }
+            __syncthreads();
+            const int my_off = s_warp_sum[warp] + incl - mine;
+            const int total = s_total;
+
+            // ---- rounds of at most BFS_ITEM_CAP items ----
+            for (int r0 = 0; r0 < total; r0 += BFS_ITEM_CAP) {
+                int pos = my_off;
+#pragma unroll
+                for (int u = 0; u < BFS_ROWS_PER_THREAD; ++u) {
+                    if (dmask[u] == 0) {
+                        continue;
+                    }
+                    const uint32_t wm = (words[u] >> 9) & 0xFFFFu;
+                    const uint32_t nb = words[u] & 0x1FFu;
+                    for (int w = 0; w < g.W; ++w) {
+                        if (!((dmask[u] >> (w & 15)) & 1u)) {
+                            continue;
+                        }
+                        if (pos >= r0 && pos < r0 + BFS_ITEM_CAP) {
+                            const uint32_t hl = (w > 0 && ((wm >> ((w - 1) & 15)) & 1u)) ? 1u : 0u;
+                            const uint32_t hr = (w + 1 < g.W && ((wm >> ((w + 1) & 15)) & 1u)) ? 1u : 0u;
+                            const uint32_t hs = (wm >> (w & 15)) & 1u;
+                            s_item[pos - r0] = (uint32_t)rows[u];
+                            s_info[pos - r0] = (uint32_t)w | (nb << 8) | (hl << 17) | (hr << 18) | (hs << 19);
+                        }
+                        ++pos;
+                    }
+                }
+                __syncthreads();
+                const int n_items = min(BFS_ITEM_CAP, total - r0);
+                for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+                    const int row = (int)s_item[i];
+                    const uint32_t info = s_info[i];
+                    const int w = info & 0xFFu;
+                    const uint32_t nb = (info >> 8) & 0x1FFu;
+                    const bool hl = (info >> 17) & 1u, hr = (info >> 18) & 1u, hs = (info >> 19) & 1u;
+                    const int z = row / g.DY, y = row - z * g.DY;
+                    const size_t idx = (size_t)row * g.W + w;
+                    const uint32_t blk = __ldcg(&g.blocked[idx]);
+                    uint32_t m = 0, ml = 0, mr = 0;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        if (nb & (1u << k)) {
+                            const uint32_t* fr = fcur + (size_t)((z + k / 3 - 1) * g.DY + (y + k % 3 - 1)) * g.W + w;
+                            if (hs) m |= __ldcg(fr);
+                            if (hl) ml |= __ldcg(fr - 1);
+                            if (hr) mr |= __ldcg(fr + 1);
+                        }
+                    }
+                    const uint32_t dil = m | (m << 1) | (m >> 1) | (ml >> 31) | (mr << 31);
+                    uint32_t fresh = dil & ~blk;
+                    fnext[idx] = fresh;
+                    if (fresh) {
+                        g.blocked[idx] = blk | fresh;
+                        any_new = true;
+                        const uint32_t pub = 1u << (9 + (w & 15));
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) {
+                            // this row is neighbour k of row (z - dz, y - dy)
+                            atomicOr(&cand_out[(z - (k / 3 - 1)) * g.DY + (y - (k % 3 - 1))], pub | (1u << k));
+                        }
+                        int* d = g.dist + (size_t)row * g.DX + (size_t)w * 32;
+                        while (fresh) {
+                            const int b = __ffs(fresh) - 1;
+                            fresh &= fresh - 1;
+                            d[b] = (int)level;
+                        }
+                    }
+                }
+                __syncthreads();   // the list is rebuilt by the next round / batch
+            }
         }
-        if (__any_sync(0xffffffffu, any_new) && lane == 0) {
-            *newflag = 1;
+        const bool block_new = __syncthreads_or(any_new ? 1 : 0) != 0;
+        const unsigned long long seen = grid_barrier(bar, level * gridDim.x, block_new);
+        const unsigned int news = (unsigned int)(seen >> 32);
+        if (news == news_before) {
+            break;   // no block discovered anything at this level
         }
-        grid.sync();
-        if (!__ldcg(newflag)) {
-            break;
-        }
+        news_before = news;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         g.ctrl[0] = (int)level;

@@ -1218,10 +1218,15 @@ static int wall_threshold(const smplgpu_ctx* ctx, double inflation_radius)
 }
 
 // reset + seed + all levels on one grid; seeds already on the device (padded-grid-free coordinates)
-static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_seeds, int n_seeds, int* levels_out)
+static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_seeds, int n_seeds, int* levels_out,
+                    const uint8_t* d_slot_mask = nullptr, int slot_dz = 1)
 {
     const int total = (int)words;
-    bfs_reset_kernel<<<(std::max(total, g.rows) + 255) / 256, 256, 0, ctx->stream>>>(g);
+    {
+        // one warp per 32 bitmap words; at least one thread per row for the candidate stamps
+        const long long threads = std::max<long long>(g.rows, std::min<long long>((long long)total, 148LL * 2048 * 4));
+        bfs_reset_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(g, d_slot_mask, slot_dz);
+    }
     ++ctx->launches;
     if (n_seeds <= 0) {
         CU(cudaGetLastError());
@@ -1230,16 +1235,15 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
     CU(cudaMemsetAsync(ctx->d_seed_count, 0, sizeof(int), ctx->stream));
     bfs_seed_kernel<<<(n_seeds + 127) / 128, 128, 0, ctx->stream>>>(g, d_seeds, n_seeds, ctx->d_seed_count);
     ++ctx->launches;
-    // persistent cooperative kernel: every co-resident block the device can hold
+    // persistent cooperative kernel, one block per SM (the grid barrier costs one arrival per block)
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_levels_kernel, BFS_THREADS, 0));
     if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS kernel does not fit an SM");
-    int blocks = ctx->sm_count * per_sm;
-    const int warps_per_block = BFS_THREADS / 32;
-    const int want = (g.rows + warps_per_block - 1) / warps_per_block; // at most one row per warp per scan slot
-    blocks = std::max(1, std::min(blocks, want));
+    const int groups = (g.rows + 7) / 8;
+    const int blocks = std::max(1, std::min(ctx->sm_count, groups));
     long long cap = (long long)g.nx * g.ny * g.nz;
     int max_levels = (int)std::min<long long>(cap, (1LL << 22)); // level << 9 must fit the candidate word
+    max_levels = (int)std::min<long long>(max_levels, 0x7FFFFFFFLL / blocks - 1);   // barrier target level * blocks
     void* args[] = { (void*)&g, (void*)&max_levels };
     CU(cudaLaunchCooperativeKernel((void*)bfs_levels_kernel, dim3(blocks), dim3(BFS_THREADS), args, 0, ctx->stream));
     ++ctx->launches;
@@ -1284,7 +1288,7 @@ int smplgpu_bfs_set_walls_from_df(smplgpu_ctx* ctx, double inflation_radius)
     unsigned int* d_count = (unsigned int*)ctx->d_seed_count;
     CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), ctx->stream));
     const int total = (int)ctx->bfs_words;
-    bfs_walls_from_df_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->bfs, ctx->d_df, kmax, ctx->bfs.DZ, d_count);
+    bfs_walls_from_df_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->bfs, ctx->d_df, kmax, ctx->bfs.DZ, d_count, nullptr);
     ++ctx->launches;
     CU(cudaGetLastError());
     unsigned int count = 0;
@@ -1439,7 +1443,7 @@ int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radi
     unsigned int* d_count = (unsigned int*)ctx->d_seed_count;
     CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), ctx->stream));
     const int total = (int)ctx->bank_words;
-    bfs_walls_from_df_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->bank, ctx->d_df, kmax, ctx->bank_slot_dz, d_count);
+    bfs_walls_from_df_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->bank, ctx->d_df, kmax, ctx->bank_slot_dz, d_count, nullptr);
     ++ctx->launches;
     CU(cudaGetLastError());
     unsigned int count = 0;
@@ -1449,35 +1453,53 @@ int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radi
     return (int)count;
 }
 
-int smplgpu_bfs_bank_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz)
+int smplgpu_bfs_bank_run_slots(smplgpu_ctx* ctx, const int32_t* slots, const int32_t* seeds_xyz, int n)
 {
-    if (!ctx || !seeds_xyz) return SMPLGPU_ERR_INVALID;
+    if (!ctx || n < 0 || (n > 0 && (!slots || !seeds_xyz))) return SMPLGPU_ERR_INVALID;
     if (!ctx->has_bank) return fail(ctx, SMPLGPU_ERR_STATE, "BFS bank not created");
+    if (n == 0) return 0;
     const int nx = ctx->grid.nx, ny = ctx->grid.ny, nz = ctx->grid.nz;
     std::vector<int> inb;
-    for (int s = 0; s < ctx->bank_slots; ++s) {
-        const int x = seeds_xyz[3 * s], y = seeds_xyz[3 * s + 1], z = seeds_xyz[3 * s + 2];
+    std::vector<uint8_t> mask(ctx->bank_slots, 0);
+    for (int i = 0; i < n; ++i) {
+        const int s = slots[i];
+        if (s < 0 || s >= ctx->bank_slots) return fail(ctx, SMPLGPU_ERR_INVALID, "slot %d out of range", s);
+        if (mask[s]) return fail(ctx, SMPLGPU_ERR_INVALID, "slot %d listed twice", s);
+        mask[s] = 1;
+        const int x = seeds_xyz[3 * i], y = seeds_xyz[3 * i + 1], z = seeds_xyz[3 * i + 2];
         if (x >= 0 && y >= 0 && z >= 0 && x < nx && y < ny && z < nz) {
             inb.push_back(x); inb.push_back(y); inb.push_back(s * ctx->bank_slot_dz + z);
         }
     }
     const int n_in = (int)inb.size() / 3;
+    const size_t seed_bytes = (inb.size() * sizeof(int) + 15) / 16 * 16;
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, seed_bytes + mask.size() + 64);
+    if (r) return r;
+    uint8_t* d_mask = (uint8_t*)ctx->d_misc + seed_bytes;
     if (n_in > 0) {
-        int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, inb.size() * sizeof(int));
-        if (r) return r;
         CU(cudaMemcpyAsync(ctx->d_misc, inb.data(), inb.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
+    CU(cudaMemcpyAsync(d_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, ctx->stream));
     // every run starts from the scene's walls: a fresh BfsHeuristic per query (seeding a wall cell
     // un-walls it for the lifetime of a BFS_3D object, bfs3d.cpp:181-187 -- not across queries here)
     unsigned int* d_count = (unsigned int*)ctx->d_seed_count;
     CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), ctx->stream));
     bfs_walls_from_df_kernel<<<((int)ctx->bank_words + 255) / 256, 256, 0, ctx->stream>>>(
-        ctx->bank, ctx->d_df, ctx->bank_kmax, ctx->bank_slot_dz, d_count);
+        ctx->bank, ctx->d_df, ctx->bank_kmax, ctx->bank_slot_dz, d_count, d_mask);
     ++ctx->launches;
-    int r = run_grid(ctx, ctx->bank, ctx->bank_words, (const int*)ctx->d_misc, n_in, nullptr);
+    r = run_grid(ctx, ctx->bank, ctx->bank_words, (const int*)ctx->d_misc, n_in, nullptr, d_mask, ctx->bank_slot_dz);
     if (r) return r;
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // the host vectors above are read by the async copies
     return n_in;
+}
+
+int smplgpu_bfs_bank_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz)
+{
+    if (!ctx || !seeds_xyz) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_bank) return fail(ctx, SMPLGPU_ERR_STATE, "BFS bank not created");
+    std::vector<int32_t> slots(ctx->bank_slots);
+    for (int s = 0; s < ctx->bank_slots; ++s) slots[s] = s;
+    return smplgpu_bfs_bank_run_slots(ctx, slots.data(), seeds_xyz, ctx->bank_slots);
 }
 
 int smplgpu_bfs_bank_distances(smplgpu_ctx* ctx, const int32_t* slot, const int32_t* cells_xyz, int n, int32_t* out)

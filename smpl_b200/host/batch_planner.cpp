@@ -39,6 +39,64 @@ double normalizeAngle(double angle)
 }
 } // namespace
 
+int BatchPlanner::Lattice::find(const int* c) const
+{
+    if (table.empty()) {
+        return -1;
+    }
+    const size_t mask = table.size() - 1;
+    for (size_t i = (size_t)hash(c, dof) & mask;; i = (i + 1) & mask) {
+        const int id = table[i];
+        if (id < 0) {
+            return -1;
+        }
+        if (std::equal(c, c + dof, &coords[(size_t)id * dof])) {
+            return id;
+        }
+    }
+}
+
+void BatchPlanner::Lattice::grow()
+{
+    const size_t n = table.empty() ? 256 : table.size() * 2;
+    table.assign(n, -1);
+    const size_t mask = n - 1;
+    for (int id = 1; id < size(); ++id) {   // id 0 (the goal state) has no coordinate
+        size_t i = (size_t)hash(&coords[(size_t)id * dof], dof) & mask;
+        while (table[i] >= 0) {
+            i = (i + 1) & mask;
+        }
+        table[i] = id;
+    }
+}
+
+int BatchPlanner::Lattice::add(const int* c, const double* q, int hv, int gd, bool index)
+{
+    const int id = size();
+    if (c != nullptr) {
+        coords.insert(coords.end(), c, c + dof);
+        qs.insert(qs.end(), q, q + dof);
+    } else {
+        coords.insert(coords.end(), dof, 0);
+        qs.insert(qs.end(), dof, 0.0);
+    }
+    h.push_back(hv);
+    gdist.push_back(gd);
+    if (index) {
+        if ((size_t)(id + 1) * 2 > table.size()) {
+            grow();   // re-enters every state including this one
+        } else {
+            const size_t mask = table.size() - 1;
+            size_t i = (size_t)hash(c, dof) & mask;
+            while (table[i] >= 0) {
+                i = (i + 1) & mask;
+            }
+            table[i] = id;
+        }
+    }
+    return id;
+}
+
 BatchPlanner::BatchPlanner(smplgpu_ctx* ctx, const PlannerConfig& cfg, int max_concurrent) :
     m_ctx(ctx), m_cfg(cfg), m_max_concurrent(std::max(1, max_concurrent))
 {
@@ -151,7 +209,7 @@ void BatchPlanner::touch(Query& Q, int id)
     SState& s = sstate(Q, id);
     if (!s.touched) {
         s.g = INFINITECOST;
-        s.h = (id == 0) ? Q.goal_h : Q.states[id].h;
+        s.h = (id == 0) ? Q.goal_h : Q.lat.h[id];
         s.f = INFINITECOST;
         s.eg = INFINITECOST;
         s.iteration_closed = 0;
@@ -220,7 +278,7 @@ void BatchPlanner::heapPop(Query& Q)
 void BatchPlanner::finish(Query& Q, bool found)
 {
     Q.done = true;
-    Q.result.num_states = (int)Q.states.size();
+    Q.result.num_states = Q.lat.size();
     if (!found || Q.search.empty() || Q.search[0].g >= INFINITECOST) {
         return;
     }
@@ -232,232 +290,342 @@ void BatchPlanner::finish(Query& Q, bool found)
     Q.result.success = true;
 }
 
+///////////////////////////////////////////////////////////////////////////////
+// fork-join pool
+///////////////////////////////////////////////////////////////////////////////
+
+BatchPlanner::Pool::Pool(int n) : m_n(std::max(1, n))
+{
+    for (int t = 1; t < m_n; ++t) {
+        m_threads.emplace_back(&Pool::worker, this, t);
+    }
+}
+
+BatchPlanner::Pool::~Pool()
+{
+    m_stop.store(true);
+    m_generation.fetch_add(1);
+    for (std::thread& t : m_threads) {
+        t.join();
+    }
+}
+
+void BatchPlanner::Pool::worker(int tid)
+{
+    int seen = 0;
+    for (;;) {
+        int spins = 0;
+        while (m_generation.load(std::memory_order_acquire) == seen) {
+            if (++spins > 256) {
+                std::this_thread::yield();
+            }
+        }
+        seen = m_generation.load(std::memory_order_acquire);
+        if (m_stop.load()) {
+            return;
+        }
+        (*m_job)(tid);
+        m_done.fetch_add(1, std::memory_order_release);
+    }
+}
+
+void BatchPlanner::Pool::run(const std::function<void(int)>& f)
+{
+    if (m_n == 1) {
+        f(0);
+        return;
+    }
+    m_job = &f;
+    m_done.store(0, std::memory_order_relaxed);
+    m_generation.fetch_add(1, std::memory_order_release);
+    f(0);
+    int spins = 0;
+    while (m_done.load(std::memory_order_acquire) != m_n - 1) {
+        if (++spins > 256) {
+            std::this_thread::yield();
+        }
+    }
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// per-query steps
+///////////////////////////////////////////////////////////////////////////////
+
+void BatchPlanner::initQuery(Query& Q, int index, int slot, const double* goal)
+{
+    Q = Query();
+    Q.index = index;
+    Q.slot = slot;
+    Q.done = false;
+    Q.expanding = -1;
+    Q.n_succ = 0;
+    Q.edge_begin = 0;
+    for (int a = 0; a < 3; ++a) Q.goal[a] = goal[a];
+    int cell[3];
+    worldToGrid(Q.goal, cell);
+    const bool inb = cell[0] >= 0 && cell[1] >= 0 && cell[2] >= 0 &&
+                     cell[0] < m_cfg.dims[0] && cell[1] < m_cfg.dims[1] && cell[2] < m_cfg.dims[2];
+    // the seed cell holds distance 0 even if it was a wall (bfs3d.cpp:181-187)
+    Q.goal_h = inb ? 0 : SMPLGPU_HEURISTIC_INFINITY;
+    Q.open.assign(1, -1);
+    Q.lat.dof = m_cfg.dof;
+    Q.lat.add(nullptr, nullptr, 0, 0, false); // id 0 = the goal state (manip_lattice.cpp:122)
+}
+
+// ARAStar::improvePath loop head (arastar.cpp:486-527) + ManipLatticeActionSpace::apply + the joint-limit
+// part of ManipLattice::checkAction
+void BatchPlanner::expandOne(Query& Q)
+{
+    const int dof = m_cfg.dof;
+    Q.expanding = -1;
+    Q.n_succ = 0;
+    Q.succ_q1.clear();
+    if (Q.open.size() <= 1) {
+        finish(Q, false);
+        return;
+    }
+    const int min_id = Q.open[1];
+    if (Q.search[min_id].f >= Q.search[0].f || min_id == 0) {
+        finish(Q, true);
+        return;
+    }
+    if (Q.result.expansions >= m_cfg.max_expansions) {
+        finish(Q, false);
+        return;
+    }
+    heapPop(Q);
+    Q.search[min_id].iteration_closed = 1;
+    Q.search[min_id].eg = Q.search[min_id].g;
+    Q.expanding = min_id;
+    ++Q.result.expansions;
+
+    const double* Pq = Q.lat.q(min_id);
+    const double goal_dist = (double)Q.lat.gdist[min_id] * m_cfg.res;
+    const bool near_goal = goal_dist <= m_cfg.short_dist_thresh;
+    for (size_t p = 0; p < m_prim_deltas.size(); ++p) {
+        const bool active_prim = m_prim_short[p] ? (m_cfg.use_short_dist && near_goal)
+                                                 : !(m_cfg.use_short_dist && near_goal);
+        if (!active_prim) {
+            continue;
+        }
+        const size_t base = Q.succ_q1.size();
+        Q.succ_q1.resize(base + dof);
+        for (int j = 0; j < dof; ++j) {
+            Q.succ_q1[base + j] = m_prim_deltas[p][j] + Pq[j];
+        }
+        if (!checkJointLimits(&Q.succ_q1[base])) { // checkAction: joint limits first
+            Q.succ_q1.resize(base);
+            continue;
+        }
+        ++Q.n_succ;
+    }
+}
+
+// GetSuccs bookkeeping + ARAStar::expand relaxations (arastar.cpp:531-568) for this query's edges, in
+// submission (= primitive) order
+void BatchPlanner::absorbOne(Query& Q, const uint8_t* verdict, const int32_t* h, const int32_t* gd, const double* off)
+{
+    const int dof = m_cfg.dof;
+    std::vector<int> coord;
+    for (int e = 0; e < Q.n_succ; ++e) {
+        if (!verdict[e]) {
+            continue;
+        }
+        const double* qs = &Q.succ_q1[(size_t)e * dof];
+        stateToCoord(qs, coord);
+        int succ_id = Q.lat.find(coord.data());
+        if (succ_id < 0) {
+            succ_id = Q.lat.add(coord.data(), qs, h[e], gd[e], true);
+        }
+        // ManipLattice::isGoal, XYZ_GOAL (manip_lattice.cpp:1673-1687)
+        const bool is_goal = std::fabs(off[3 * e] - Q.goal[0]) <= m_cfg.xyz_tolerance[0] &&
+                             std::fabs(off[3 * e + 1] - Q.goal[1]) <= m_cfg.xyz_tolerance[1] &&
+                             std::fabs(off[3 * e + 2] - Q.goal[2]) <= m_cfg.xyz_tolerance[2];
+        const int target = is_goal ? 0 : succ_id;
+        sstate(Q, target);
+        touch(Q, target);
+        SState& ss = Q.search[target];
+        const int new_cost = Q.search[Q.expanding].eg + (int)(1000 * 1.0);
+        if (new_cost < ss.g) {
+            ss.g = new_cost;
+            ss.bp = Q.expanding;
+            if (ss.iteration_closed != 1) {
+                ss.f = computeKey(ss);
+                if (ss.heap_index != 0) {
+                    percolateUp(Q, (size_t)ss.heap_index);
+                } else {
+                    heapPush(Q, target);
+                }
+            }
+        }
+    }
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// the lock-step driver
+///////////////////////////////////////////////////////////////////////////////
+
 bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::vector<QueryResult>& out, std::string* err)
 {
     out.assign(nq, QueryResult());
     m_stats = BatchStats();
-    Timer t;
-    const int slots = std::min(m_max_concurrent, std::max(1, nq));
-    int r = smplgpu_bfs_bank_create(m_ctx, slots, m_cfg.inflation_radius);
-    m_stats.device_seconds += t.lap();
-    ++m_stats.device_calls;
-    if (r < 0) {
-        if (err) *err = smplgpu_last_error(m_ctx);
-        return false;
+    if (nq == 0) {
+        return true;
     }
-    for (int first = 0; first < nq; first += slots) {
-        std::vector<int> ids;
-        for (int i = first; i < std::min(nq, first + slots); ++i) ids.push_back(i);
-        if (!runWave(starts, goals, ids, out, err)) {
-            return false;
-        }
-    }
-    return true;
-}
-
-bool BatchPlanner::runWave(const double* starts, const double* goals, const std::vector<int>& ids,
-                           std::vector<QueryResult>& out, std::string* err)
-{
     const int dof = m_cfg.dof;
-    const int nw = (int)ids.size();
     Timer t;
     auto fail_dev = [&]() {
         if (err) *err = smplgpu_last_error(m_ctx);
         return false;
     };
-
-    // ---- setGoal: one BFS per query, all in one bank run (BfsHeuristic::updateGoal) ----
-    std::vector<Query> W(nw);
-    const int bank_slots = std::min(m_max_concurrent, std::max(1, (int)out.size()));
-    std::vector<int32_t> seeds((size_t)bank_slots * 3, -1);
-    for (int k = 0; k < nw; ++k) {
-        Query& Q = W[k];
-        Q.index = ids[k];
-        Q.slot = k;
-        Q.done = false;
-        Q.expanding = -1;
-        for (int a = 0; a < 3; ++a) Q.goal[a] = goals[(size_t)ids[k] * 3 + a];
-        int cell[3];
-        worldToGrid(Q.goal, cell);
-        const bool inb = cell[0] >= 0 && cell[1] >= 0 && cell[2] >= 0 &&
-                         cell[0] < m_cfg.dims[0] && cell[1] < m_cfg.dims[1] && cell[2] < m_cfg.dims[2];
-        for (int a = 0; a < 3; ++a) seeds[(size_t)k * 3 + a] = cell[a];
-        // the seed cell holds distance 0 even if it was a wall (bfs3d.cpp:181-187)
-        Q.goal_h = inb ? 0 : SMPLGPU_HEURISTIC_INFINITY;
-        Q.open.assign(1, -1);
-        Q.states.push_back(LState()); // id 0 = the goal state (manip_lattice.cpp:122)
-    }
-    m_stats.host_seconds += t.lap();
-    if (smplgpu_bfs_bank_run(m_ctx, seeds.data()) < 0) return fail_dev();
+    const int n_slots = std::min(m_max_concurrent, nq);
+    if (smplgpu_bfs_bank_create(m_ctx, n_slots, m_cfg.inflation_radius) < 0) return fail_dev();
     ++m_stats.device_calls;
-
-    // ---- setStart: limits + validity, then heuristic / metric distance of the start ----
-    std::vector<double> q0((size_t)nw * dof), q1;
-    std::vector<int32_t> slot(nw);
-    for (int k = 0; k < nw; ++k) {
-        std::copy(starts + (size_t)ids[k] * dof, starts + (size_t)(ids[k] + 1) * dof, q0.begin() + (size_t)k * dof);
-        slot[k] = k;
-    }
-    std::vector<uint8_t> verdict(nw);
-    std::vector<int32_t> h(nw), gd(nw);
-    std::vector<double> off((size_t)nw * 3);
-    if (smplgpu_is_states_valid(m_ctx, q0.data(), nw, verdict.data()) < 0) return fail_dev();
-    std::vector<uint8_t> dummy(nw);
-    if (smplgpu_expand_batch(m_ctx, q0.data(), q0.data(), slot.data(), nw, m_cfg.cost_per_cell,
-                             dummy.data(), h.data(), gd.data(), off.data()) < 0) return fail_dev();
-    m_stats.device_calls += 2;
     m_stats.device_seconds += t.lap();
 
-    int active = 0;
-    std::vector<int> coord;
-    for (int k = 0; k < nw; ++k) {
-        Query& Q = W[k];
-        const double* qs = &q0[(size_t)k * dof];
-        if (!checkJointLimits(qs) || !verdict[k]) {
-            finish(Q, false);
-            continue;
-        }
-        stateToCoord(qs, coord);
-        LState ls;
-        ls.coord = coord;
-        ls.q.assign(qs, qs + dof);
-        ls.h = h[k];
-        ls.gdist = gd[k];
-        Q.states.push_back(ls);
-        Q.coord_to_id[coord] = 1;
-        sstate(Q, 1);
-        touch(Q, 1);
-        touch(Q, 0);
-        Q.search[1].g = 0;
-        Q.search[1].f = computeKey(Q.search[1]);
-        heapPush(Q, 1);
-        ++active;
-    }
+    Pool pool(m_cfg.n_threads);
+    std::vector<Query> S(n_slots);          // slot -> query occupying it
+    std::vector<char> occupied(n_slots, 0);
+    std::vector<int> active;                // occupied slots with a search in progress
+    int next_query = 0, finished = 0;
+    // refill in groups so that one bank run (one wavefront launch sequence) serves several new queries
+    const int refill_min = std::max(1, n_slots / 4);
 
-    // ---- lock-step rounds ----
-    struct EdgeRef { int k; };
-    std::vector<EdgeRef> owner;
-    while (active > 0) {
-        q0.clear();
-        q1.clear();
-        slot.clear();
-        owner.clear();
-        for (int k = 0; k < nw; ++k) {
-            Query& Q = W[k];
-            if (Q.done) {
-                continue;
-            }
-            Q.expanding = -1;
-            if (Q.open.size() <= 1) {
-                finish(Q, false);
-                --active;
-                continue;
-            }
-            const int min_id = Q.open[1];
-            if (Q.search[min_id].f >= Q.search[0].f || min_id == 0) {
-                finish(Q, true);
-                --active;
-                continue;
-            }
-            if (Q.result.expansions >= m_cfg.max_expansions) {
-                finish(Q, false);
-                --active;
-                continue;
-            }
-            heapPop(Q);
-            Q.search[min_id].iteration_closed = 1;
-            Q.search[min_id].eg = Q.search[min_id].g;
-            Q.expanding = min_id;
-            ++Q.result.expansions;
+    std::vector<double> q0, q1, off;
+    std::vector<int32_t> slot, h, gd;
+    std::vector<uint8_t> verdict;
 
-            // ManipLatticeActionSpace::apply: which primitives are active at this state
-            const LState& P = Q.states[min_id];
-            const double goal_dist = (double)P.gdist * m_cfg.res;
-            const bool near_goal = goal_dist <= m_cfg.short_dist_thresh;
-            for (size_t p = 0; p < m_prim_deltas.size(); ++p) {
-                const bool active_prim = m_prim_short[p] ? (m_cfg.use_short_dist && near_goal)
-                                                         : !(m_cfg.use_short_dist && near_goal);
-                if (!active_prim) {
+    while (finished < nq) {
+        // ---- hand free slots to waiting queries: setGoal (one BFS per query) + setStart ----
+        int n_free = 0;
+        for (int s = 0; s < n_slots; ++s) n_free += occupied[s] ? 0 : 1;
+        if (next_query < nq && (n_free >= refill_min || active.empty())) {
+            std::vector<int32_t> new_slots, seeds;
+            for (int s = 0; s < n_slots && next_query < nq; ++s) {
+                if (occupied[s]) {
                     continue;
                 }
-                const size_t base = q1.size();
-                q1.resize(base + dof);
-                for (int j = 0; j < dof; ++j) {
-                    q1[base + j] = m_prim_deltas[p][j] + P.q[j];
-                }
-                if (!checkJointLimits(&q1[base])) { // checkAction: joint limits first
-                    q1.resize(base);
+                initQuery(S[s], next_query, s, goals + (size_t)next_query * 3);
+                ++next_query;
+                occupied[s] = 1;
+                new_slots.push_back(s);
+                int cell[3];
+                worldToGrid(S[s].goal, cell);
+                seeds.insert(seeds.end(), cell, cell + 3);
+            }
+            const int nn = (int)new_slots.size();
+            m_stats.host_seconds += t.lap();
+            if (smplgpu_bfs_bank_run_slots(m_ctx, new_slots.data(), seeds.data(), nn) < 0) return fail_dev();
+            ++m_stats.bfs_runs;
+            // setStart: limits + validity, then heuristic / metric distance of the start state
+            q0.resize((size_t)nn * dof);
+            for (int k = 0; k < nn; ++k) {
+                const int qi = S[new_slots[k]].index;
+                std::copy(starts + (size_t)qi * dof, starts + (size_t)(qi + 1) * dof, q0.begin() + (size_t)k * dof);
+            }
+            verdict.resize(nn);
+            h.resize(nn);
+            gd.resize(nn);
+            off.resize((size_t)nn * 3);
+            std::vector<uint8_t> dummy(nn);
+            if (smplgpu_is_states_valid(m_ctx, q0.data(), nn, verdict.data()) < 0) return fail_dev();
+            if (smplgpu_expand_batch(m_ctx, q0.data(), q0.data(), new_slots.data(), nn, m_cfg.cost_per_cell,
+                                     dummy.data(), h.data(), gd.data(), off.data()) < 0) return fail_dev();
+            m_stats.device_calls += 3;
+            m_stats.device_seconds += t.lap();
+            std::vector<int> coord;
+            for (int k = 0; k < nn; ++k) {
+                Query& Q = S[new_slots[k]];
+                const double* qs = &q0[(size_t)k * dof];
+                if (!checkJointLimits(qs) || !verdict[k]) {
+                    finish(Q, false);
                     continue;
                 }
-                q0.insert(q0.end(), P.q.begin(), P.q.end());
-                slot.push_back(Q.slot);
-                owner.push_back(EdgeRef{ k });
+                stateToCoord(qs, coord);
+                Q.lat.add(coord.data(), qs, h[k], gd[k], true);
+                sstate(Q, 1);
+                touch(Q, 1);
+                touch(Q, 0);
+                Q.search[1].g = 0;
+                Q.search[1].f = computeKey(Q.search[1]);
+                heapPush(Q, 1);
+            }
+            active.clear();
+            for (int s = 0; s < n_slots; ++s) {
+                if (occupied[s]) active.push_back(s);
             }
         }
-        const int ne = (int)owner.size();
-        m_stats.host_seconds += t.lap();
-        if (ne == 0) {
-            continue; // queries that expanded a state without any in-limits successor carry on next round
-        }
-        verdict.resize(ne);
-        h.resize(ne);
-        gd.resize(ne);
-        off.resize((size_t)ne * 3);
-        if (smplgpu_expand_batch(m_ctx, q0.data(), q1.data(), slot.data(), ne, m_cfg.cost_per_cell,
-                                 verdict.data(), h.data(), gd.data(), off.data()) < 0) return fail_dev();
-        ++m_stats.device_calls;
-        ++m_stats.rounds;
-        m_stats.edges_submitted += ne;
-        m_stats.device_seconds += t.lap();
 
-        // ---- GetSuccs bookkeeping + ARAStar::expand relaxations, per query in submission order ----
-        for (int e = 0; e < ne; ++e) {
-            if (!verdict[e]) {
-                continue;
+        // ---- one lock-step round: every active query pops one state and generates its successors ----
+        const int na = (int)active.size();
+        pool.run([&](int tid) {
+            for (int k = tid; k < na; k += pool.size()) {
+                Query& Q = S[active[k]];
+                if (!Q.done) {
+                    expandOne(Q);
+                }
             }
-            Query& Q = W[owner[e].k];
-            const double* qs = &q1[(size_t)e * dof];
-            stateToCoord(qs, coord);
-            int succ_id;
-            auto it = Q.coord_to_id.find(coord);
-            if (it != Q.coord_to_id.end()) {
-                succ_id = it->second;
-            } else {
-                succ_id = (int)Q.states.size();
-                LState ls;
-                ls.coord = coord;
-                ls.q.assign(qs, qs + dof);
-                ls.h = h[e];
-                ls.gdist = gd[e];
-                Q.states.push_back(ls);
-                Q.coord_to_id[coord] = succ_id;
-            }
-            // ManipLattice::isGoal, XYZ_GOAL (manip_lattice.cpp:1673-1687)
-            const bool is_goal = std::fabs(off[3 * e] - Q.goal[0]) <= m_cfg.xyz_tolerance[0] &&
-                                 std::fabs(off[3 * e + 1] - Q.goal[1]) <= m_cfg.xyz_tolerance[1] &&
-                                 std::fabs(off[3 * e + 2] - Q.goal[2]) <= m_cfg.xyz_tolerance[2];
-            const int target = is_goal ? 0 : succ_id;
-            sstate(Q, target);
-            touch(Q, target);
-            SState& ss = Q.search[target];
-            const int new_cost = Q.search[Q.expanding].eg + (int)(1000 * 1.0);
-            if (new_cost < ss.g) {
-                ss.g = new_cost;
-                ss.bp = Q.expanding;
-                if (ss.iteration_closed != 1) {
-                    ss.f = computeKey(ss);
-                    if (ss.heap_index != 0) {
-                        percolateUp(Q, (size_t)ss.heap_index);
-                    } else {
-                        heapPush(Q, target);
+        });
+        int ne = 0;
+        for (int k = 0; k < na; ++k) {
+            Query& Q = S[active[k]];
+            Q.edge_begin = ne;
+            ne += Q.done ? 0 : Q.n_succ;
+        }
+        if (ne > 0) {
+            q0.resize((size_t)ne * dof);
+            q1.resize((size_t)ne * dof);
+            slot.resize(ne);
+            pool.run([&](int tid) {
+                for (int k = tid; k < na; k += pool.size()) {
+                    const Query& Q = S[active[k]];
+                    if (Q.done || Q.n_succ == 0) {
+                        continue;
                     }
+                    const double* pq = Q.lat.q(Q.expanding);
+                    for (int e = 0; e < Q.n_succ; ++e) {
+                        std::copy(pq, pq + dof, q0.begin() + (size_t)(Q.edge_begin + e) * dof);
+                        slot[Q.edge_begin + e] = Q.slot;
+                    }
+                    std::copy(Q.succ_q1.begin(), Q.succ_q1.end(), q1.begin() + (size_t)Q.edge_begin * dof);
                 }
+            });
+            verdict.resize(ne);
+            h.resize(ne);
+            gd.resize(ne);
+            off.resize((size_t)ne * 3);
+            m_stats.host_seconds += t.lap();
+            if (smplgpu_expand_batch(m_ctx, q0.data(), q1.data(), slot.data(), ne, m_cfg.cost_per_cell,
+                                     verdict.data(), h.data(), gd.data(), off.data()) < 0) return fail_dev();
+            ++m_stats.device_calls;
+            ++m_stats.rounds;
+            m_stats.edges_submitted += ne;
+            m_stats.device_seconds += t.lap();
+            pool.run([&](int tid) {
+                for (int k = tid; k < na; k += pool.size()) {
+                    Query& Q = S[active[k]];
+                    if (Q.done || Q.n_succ == 0) {
+                        continue;
+                    }
+                    absorbOne(Q, verdict.data() + Q.edge_begin, h.data() + Q.edge_begin, gd.data() + Q.edge_begin,
+                              off.data() + (size_t)Q.edge_begin * 3);
+                }
+            });
+        }
+        // ---- retire finished queries, freeing their slots ----
+        size_t keep = 0;
+        for (int k = 0; k < na; ++k) {
+            const int s = active[k];
+            if (S[s].done) {
+                out[S[s].index] = S[s].result;
+                occupied[s] = 0;
+                ++finished;
+            } else {
+                active[keep++] = s;
             }
         }
+        active.resize(keep);
         m_stats.host_seconds += t.lap();
-    }
-    for (int k = 0; k < nw; ++k) {
-        out[W[k].index] = W[k].result;
     }
     return true;
 }

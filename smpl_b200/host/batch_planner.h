@@ -15,9 +15,11 @@
 #ifndef SMPLHOST_BATCH_PLANNER_H
 #define SMPLHOST_BATCH_PLANNER_H
 
+#include <atomic>
 #include <cstdint>
-#include <map>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/smplgpu.h"
@@ -44,6 +46,9 @@ struct PlannerConfig
     double origin[3] = { 0, 0, 0 };
     double res = 0.02;
     int dims[3] = { 0, 0, 0 };
+    // host threads for the per-query work (successor generation, hashing, OPEN list updates); queries are
+    // independent, so the result does not depend on this
+    int n_threads = 1;
 };
 
 struct QueryResult
@@ -58,6 +63,7 @@ struct QueryResult
 struct BatchStats
 {
     int rounds = 0;
+    int bfs_runs = 0;              // bank runs (each covers every slot that was refilled at that point)
     long long edges_submitted = 0;
     long long device_calls = 0;
     double device_seconds = 0.0;   // time inside smplgpu_* calls
@@ -75,7 +81,29 @@ public:
     const BatchStats& stats() const { return m_stats; }
 
 private:
-    struct LState { std::vector<int> coord; std::vector<double> q; int h; int gdist; };
+    // Lattice states of one query, flat (no per-state allocation): state id -> coord[dof], q[dof], h, gdist,
+    // and an open-addressing hash table coord -> id (the role of ManipLattice's m_state_to_id, manip_lattice.h)
+    struct Lattice
+    {
+        int dof = 0;
+        std::vector<int> coords;
+        std::vector<double> qs;
+        std::vector<int> h, gdist;
+        std::vector<int> table;      // size is a power of two, -1 = empty
+        int size() const { return (int)h.size(); }
+        const double* q(int id) const { return &qs[(size_t)id * dof]; }
+        static uint64_t hash(const int* c, int dof)
+        {
+            uint64_t x = 0x9E3779B97F4A7C15ull;
+            for (int i = 0; i < dof; ++i) {
+                x ^= (uint64_t)(uint32_t)c[i] + 0x9E3779B97F4A7C15ull + (x << 6) + (x >> 2);
+            }
+            return x;
+        }
+        int find(const int* c) const;
+        int add(const int* c, const double* q, int hv, int gd, bool index);   // index = enter it in the table
+        void grow();
+    };
     struct SState { int g, h, f, eg, iteration_closed, bp, heap_index; bool touched; };
     struct Query
     {
@@ -83,13 +111,34 @@ private:
         int slot;
         double goal[3];
         int goal_h;
-        std::vector<LState> states;
-        std::map<std::vector<int>, int> coord_to_id;
+        Lattice lat;
         std::vector<SState> search;
         std::vector<int> open; // 1-based heap of state ids
         int expanding;         // state popped this round
         bool done;
         QueryResult result;
+        // this round's successors (filled by expandOne, consumed by absorbOne)
+        std::vector<double> succ_q1;
+        int n_succ;
+        int edge_begin;
+    };
+
+    // minimal fork-join pool: run(f) calls f(tid) on every thread (the caller is tid 0)
+    class Pool
+    {
+    public:
+        explicit Pool(int n);
+        ~Pool();
+        void run(const std::function<void(int)>& f);
+        int size() const { return m_n; }
+    private:
+        int m_n;
+        std::vector<std::thread> m_threads;
+        std::atomic<int> m_generation{ 0 };
+        std::atomic<int> m_done{ 0 };
+        std::atomic<bool> m_stop{ false };
+        const std::function<void(int)>* m_job = nullptr;
+        void worker(int tid);
     };
 
     smplgpu_ctx* m_ctx;
@@ -112,8 +161,9 @@ private:
     void percolateUp(Query& Q, size_t pivot);
     void percolateDown(Query& Q, size_t pivot);
     void finish(Query& Q, bool found);
-    bool runWave(const double* starts, const double* goals, const std::vector<int>& ids,
-                 std::vector<QueryResult>& out, std::string* err);
+    void initQuery(Query& Q, int index, int slot, const double* goal);
+    void expandOne(Query& Q);   // pop the next state and generate its in-limit successors (no device work)
+    void absorbOne(Query& Q, const uint8_t* verdict, const int32_t* h, const int32_t* gd, const double* off);
 };
 
 } // namespace smplhost

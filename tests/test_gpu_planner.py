@@ -45,6 +45,26 @@ def test_bfs_bank_equals_single_runs(tabletop):
     assert np.all((d == -1) | (d == 0x7FFFFFFF))
 
 
+def test_bank_slot_refill_leaves_other_slots_untouched(tabletop):
+    scene, o, ctx, tables = tabletop
+    ctx.bfs_bank_create(3, scene.inflation_radius)
+    _, goals = scenes.tabletop_queries(4, seed=33)
+    seeds = api.world_to_grid(goals, scene.origin, scene.res).astype(np.int32)
+    ctx.bfs_bank_run(seeds[:3])
+    rng = np.random.default_rng(6)
+    cells = rng.integers(0, np.asarray(scene.dims), (3000, 3)).astype(np.int32)
+    before = [ctx.bfs_bank_distances(np.full(len(cells), s, np.int32), cells) for s in range(3)]
+    # slot 1 goes to a new query; slots 0 and 2 keep searching with their own distances
+    sl = np.array([1], np.int32)
+    assert ctx._ck(ctx.L.smplgpu_bfs_bank_run_slots(ctx.h, api._ip(sl), api._ip(np.ascontiguousarray(seeds[3:4])), 1), "run_slots") == 1
+    after = [ctx.bfs_bank_distances(np.full(len(cells), s, np.int32), cells) for s in range(3)]
+    assert np.array_equal(before[0], after[0]) and np.array_equal(before[2], after[2])
+    ctx.bfs_set_walls_from_df(scene.inflation_radius)
+    ctx.bfs_run([seeds[3]])
+    assert np.array_equal(after[1], ctx.bfs_distances(cells))
+    assert not np.array_equal(before[1], after[1])
+
+
 def test_expand_batch_matches_oracle(tabletop):
     scene, o, ctx, tables = tabletop
     lo, hi, cont = tables.limits()
@@ -85,7 +105,7 @@ def test_batch_planner_matches_sequential_oracle(tabletop):
     goals[7] = (5.0, 0.0, 1.0)          # outside the grid: heuristic is Infinity everywhere
     starts[9, 1] = 3.0                  # start violates joint limits: setStart fails
     ref = _run_oracle(o, scene, params, starts, goals)
-    got, stats = api.plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=10)
+    got, stats = api.plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=10, n_threads=3)
     n_ok = 0
     for i, (a, b) in enumerate(zip(ref, got)):
         assert a["success"] == b["success"], i
