@@ -150,6 +150,27 @@ def cpu_bfs_rate(n):
     return n ** 3 / dt / 1e6, kind, dt
 
 
+def setup_shared_scene(scene, local_rank, rank, world, dev):
+    """Context for `scene` on this rank's GPU: rank 0 builds the distance field on its GPU, every other rank
+    receives it in ONE broadcast (NCCL over NVLink) -- the only collective of the data path."""
+    import torch
+    from smpl_b200 import api, sharding
+    ctx = api.GpuContext(local_rank)
+    tables = api.build_tables(scene)
+    ctx.set_robot(tables)
+    if rank == 0:
+        ctx.build_distance_field(api.scene_cells(scene, tables), scene.dims, scene.origin, scene.res, scene.max_dist,
+                                 scene.padding)
+    if world > 1:
+        d2 = ctx.download_distance_field() if rank == 0 else None
+        df_t = sharding.broadcast_distance_field(d2, scene.dims, src=0, device=dev)
+        torch.cuda.synchronize()
+        if rank != 0:
+            dmax = int(np.ceil(scene.max_dist * (1.0 / scene.res)))
+            ctx.set_distance_field_dev(df_t.data_ptr(), scene.dims, scene.origin, scene.res, dmax * dmax, scene.padding)
+    return ctx, tables
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port) on all host threads."""
     if rank != 0:
@@ -212,39 +233,25 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from smpl_b200 import api, scenes
+    from smpl_b200 import api, scenes, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("SMPL_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- scene: rank 0 builds the distance field on its GPU, then ONE broadcast over NCCL ----
     scene = scenes.pr2_clutter_scene()
-    ctx = api.GpuContext(local_rank)
+    ctx, tables = setup_shared_scene(scene, local_rank, rank, world, dev)
     # time on ONE explicit stream shared by torch (events) and the library (kernels, copies)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    tables = api.build_tables(scene)
-    ctx.set_robot(tables)
-    nx, ny, nz = scene.dims
-    inv = 1.0 / scene.res
-    dmax = int(np.ceil(scene.max_dist * inv))
-    if rank == 0:
-        ctx.build_distance_field(api.scene_cells(scene, tables), scene.dims, scene.origin, scene.res, scene.max_dist)
-    if world > 1:
-        df_t = torch.empty(nx * ny * nz, dtype=torch.int16, device=dev)
-        if rank == 0:
-            ptr, nbytes = ctx.distance_field_dev_ptr()
-            src = torch.from_numpy(ctx.download_distance_field().view(np.int16).reshape(-1)).to(dev)
-            df_t.copy_(src)
-        dist.broadcast(df_t, src=0)
-        torch.cuda.synchronize()
-        if rank != 0:
-            ctx.set_distance_field_dev(df_t.data_ptr(), scene.dims, scene.origin, scene.res, dmax * dmax)
     lo, hi, cont = tables.limits()
 
     n = args.states
@@ -359,13 +366,13 @@ def main():
     plan = None
     if args.plan_queries > 0:
         pscene = scenes.pr2_tabletop_scene()
-        pctx, ptables = api.setup_context(pscene, device=local_rank)
+        pctx, ptables = setup_shared_scene(pscene, local_rank, rank, world, dev)
         pparams = scenes.PlanParams(pscene.dof)
         pparams.max_expansions = args.plan_max_expansions
         nq_total = args.plan_queries * world
         starts_all, goals_all = scenes.tabletop_queries(nq_total, seed=13)
-        mine = np.arange(rank, nq_total, world)          # round-robin sharding, no collective
-        n_thr = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
+        mine = sharding.round_robin_shard(nq_total, rank, world)   # no collective
+        n_thr = max(1, min(14, (os.cpu_count() or 1) // max(1, world) - 2))
         api.plan_batch(pctx, pscene, ptables, pparams, starts_all[mine][:8], goals_all[mine][:8], max_concurrent=8)  # warm-up
         barrier()
         t0 = time.perf_counter()

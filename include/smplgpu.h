@@ -265,6 +265,14 @@ int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, c
                          int cost_per_cell, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells,
                          double* offset_xyz);
 
+/* The same in two halves, so the host can prepare / absorb one batch while the device works on another:
+ * submit copies the inputs and queues the work on the context's stream and returns at once; wait blocks until
+ * that batch is done and copies the results out (returns n).  buffer = 0 or 1: two batches may be in flight. */
+int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double* q1, const int32_t* slot, int n,
+                                int cost_per_cell, int buffer);
+int smplgpu_expand_batch_wait(smplgpu_ctx* ctx, int buffer, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells,
+                              double* offset_xyz);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,12 @@ struct smplgpu_ctx
     void* pinned[2] = { nullptr, nullptr }; size_t pinned_cap = 0;
     void* pinned_out[2] = { nullptr, nullptr }; size_t pinned_out_cap = 0;
     cudaEvent_t ev[2] = { nullptr, nullptr };      // chunk b: kernels + result copies done
+    // two expansion batches may be in flight (smplgpu_expand_batch_submit / _wait)
+    void* exp_in[2] = { nullptr, nullptr }; size_t exp_in_cap[2] = { 0, 0 };     // pinned
+    void* exp_out[2] = { nullptr, nullptr }; size_t exp_out_cap[2] = { 0, 0 };   // pinned
+    void* d_exp[2] = { nullptr, nullptr }; size_t d_exp_cap[2] = { 0, 0 };
+    cudaEvent_t ev_exp[2] = { nullptr, nullptr };
+    int exp_n[2] = { -1, -1 };
     cudaEvent_t ev_in[2] = { nullptr, nullptr };   // chunk b: inputs on the device
     cudaStream_t copy_stream = nullptr;
     unsigned long long* d_stats = nullptr;
@@ -202,6 +208,7 @@ smplgpu_ctx* smplgpu_create(int device)
     for (int i = 0; i < 2; ++i) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
         if ((e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_exp[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
     ctx->h_model = new DevModel;
     memset(ctx->h_model, 0, sizeof(DevModel));
@@ -239,6 +246,10 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
         if (ctx->pinned_out[i]) cudaFreeHost(ctx->pinned_out[i]);
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_exp[i]) cudaEventDestroy(ctx->ev_exp[i]);
+        if (ctx->exp_in[i]) cudaFreeHost(ctx->exp_in[i]);
+        if (ctx->exp_out[i]) cudaFreeHost(ctx->exp_out[i]);
+        cudaFree(ctx->d_exp[i]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -893,7 +904,8 @@ static int launch_edges(smplgpu_ctx* ctx, const double* dq0, const double* dq1, 
     edges_valid32_kernel<<<(n + t32 - 1) / t32, t32, v32_smem(ctx), ctx->stream>>>(
         ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq0, dq1, n, dv, dc, ctx->d_unc_list,
         ctx->d_unc_count, ctx->d_stats);
-    const int blocks = std::max(1, std::min((n + vt - 1) / vt, 2 * ctx->sm_count));
+    const int per_block = std::max(1, vt / 4);
+    const int blocks = std::max(1, std::min((n + per_block - 1) / per_block, 2 * ctx->sm_count));
     edges_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
         ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, n, dv, nullptr, nullptr, ctx->d_unc_list, ctx->d_unc_count);
     ctx->launches += 2;
@@ -1526,36 +1538,52 @@ int smplgpu_bfs_bank_distances(smplgpu_ctx* ctx, const int32_t* slot, const int3
     return 0;
 }
 
-int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, const int32_t* slot, int n,
-                         int cost_per_cell, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells, double* offset_xyz)
+static int grow_pinned1(smplgpu_ctx* ctx, void** p, size_t* cap, size_t need)
 {
-    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (need <= *cap) {
+        return 0;
+    }
+    if (*p) {
+        CU(cudaFreeHost(*p));
+        *p = nullptr;
+        *cap = 0;
+    }
+    const size_t n = std::max(need + need / 2, (size_t)1 << 16);
+    CU(cudaMallocHost(p, n));
+    *cap = n;
+    return 0;
+}
+
+int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double* q1, const int32_t* slot, int n,
+                                int cost_per_cell, int buffer)
+{
+    if (!ctx || n < 0 || buffer < 0 || buffer > 1) return SMPLGPU_ERR_INVALID;
     int r = need_scene(ctx);
     if (r) return r;
     if (!ctx->has_bank) return fail(ctx, SMPLGPU_ERR_STATE, "BFS bank not created");
+    if (ctx->exp_n[buffer] >= 0) return fail(ctx, SMPLGPU_ERR_STATE, "expansion buffer %d is still in flight", buffer);
+    if (n > 0 && (!q0 || !q1 || !slot)) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    ctx->exp_n[buffer] = n;
     if (n == 0) return 0;
-    if (!q0 || !q1 || !slot || !verdict || !h || !goal_dist_cells || !offset_xyz) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    const int b = buffer;
     const int dof = ctx->h_model->dof;
     const size_t row = (size_t)dof * sizeof(double);
-    // one pinned staging block in, one out
     const size_t in_bytes = 2 * n * row + (size_t)n * sizeof(int);
-    const size_t out_bytes = (size_t)n * (1 + 2 * sizeof(int) + 3 * sizeof(double)) + 64;
-    r = grow_pinned(ctx, ctx->pinned, &ctx->pinned_cap, std::max(in_bytes, (size_t)1 << 16));
-    if (r) return r;
-    r = grow_pinned(ctx, ctx->pinned_out, &ctx->pinned_out_cap, std::max(out_bytes, (size_t)1 << 16));
-    if (r) return r;
-    r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, in_bytes + out_bytes + 256);
-    if (r) return r;
-    uint8_t* pin = (uint8_t*)ctx->pinned[0];
+    const size_t in_pad = (in_bytes + 63) / 64 * 64;
+    const size_t out_bytes = (size_t)n * (3 * sizeof(double) + 2 * sizeof(int) + 1);
+    if ((r = grow_pinned1(ctx, &ctx->exp_in[b], &ctx->exp_in_cap[b], in_bytes))) return r;
+    if ((r = grow_pinned1(ctx, &ctx->exp_out[b], &ctx->exp_out_cap[b], out_bytes))) return r;
+    if ((r = grow(ctx, &ctx->d_exp[b], &ctx->d_exp_cap[b], in_pad + out_bytes + 256))) return r;
+    uint8_t* pin = (uint8_t*)ctx->exp_in[b];
     memcpy(pin, q0, n * row);
     memcpy(pin + n * row, q1, n * row);
     memcpy(pin + 2 * n * row, slot, (size_t)n * sizeof(int));
-    uint8_t* dbase = (uint8_t*)ctx->d_misc;
+    uint8_t* dbase = (uint8_t*)ctx->d_exp[b];
     CU(cudaMemcpyAsync(dbase, pin, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     double* dq0 = (double*)dbase;
     double* dq1 = (double*)(dbase + n * row);
     int* dslot = (int*)(dbase + 2 * n * row);
-    uint8_t* obase = dbase + ((in_bytes + 63) / 64) * 64;
+    uint8_t* obase = dbase + in_pad;
     double* doff = (double*)obase;
     int* dh = (int*)(obase + (size_t)n * 3 * sizeof(double));
     int* dg = dh + n;
@@ -1568,15 +1596,39 @@ int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, c
         cost_per_cell, dh, dg, doff);
     ++ctx->launches;
     CU(cudaGetLastError());
-    uint8_t* pout = (uint8_t*)ctx->pinned_out[0];
-    const size_t o_bytes = (size_t)n * (3 * sizeof(double) + 2 * sizeof(int) + 1);
-    CU(cudaMemcpyAsync(pout, obase, o_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(ctx->exp_out[b], obase, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_exp[b], ctx->stream));
+    return 0;
+}
+
+int smplgpu_expand_batch_wait(smplgpu_ctx* ctx, int buffer, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells,
+                              double* offset_xyz)
+{
+    if (!ctx || buffer < 0 || buffer > 1) return SMPLGPU_ERR_INVALID;
+    const int n = ctx->exp_n[buffer];
+    if (n < 0) return fail(ctx, SMPLGPU_ERR_STATE, "expansion buffer %d has nothing in flight", buffer);
+    ctx->exp_n[buffer] = -1;
+    if (n == 0) return 0;
+    if (!verdict || !h || !goal_dist_cells || !offset_xyz) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    CU(cudaEventSynchronize(ctx->ev_exp[buffer]));
+    const uint8_t* pout = (const uint8_t*)ctx->exp_out[buffer];
     memcpy(offset_xyz, pout, (size_t)n * 3 * sizeof(double));
     memcpy(h, pout + (size_t)n * 3 * sizeof(double), (size_t)n * sizeof(int));
     memcpy(goal_dist_cells, pout + (size_t)n * (3 * sizeof(double) + sizeof(int)), (size_t)n * sizeof(int));
     memcpy(verdict, pout + (size_t)n * (3 * sizeof(double) + 2 * sizeof(int)), (size_t)n);
-    return 0;
+    return n;
+}
+
+int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, const int32_t* slot, int n,
+                         int cost_per_cell, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells, double* offset_xyz)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (n == 0) return 0;
+    if (!q0 || !q1 || !slot || !verdict || !h || !goal_dist_cells || !offset_xyz) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    int r = smplgpu_expand_batch_submit(ctx, q0, q1, slot, n, cost_per_cell, 0);
+    if (r < 0) return r;
+    r = smplgpu_expand_batch_wait(ctx, 0, verdict, h, goal_dist_cells, offset_xyz);
+    return r < 0 ? r : 0;
 }
 
 } // extern "C"

@@ -360,10 +360,13 @@ edges_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ 
     const int total_edges = list != nullptr ? min(*list_n, n) : n;
     Counters cnt = { 0u, 0u, 0u };
 
-    // with `list` (edges the single-precision pass could not decide) a block walks several chunks
-    for (int first = blockIdx.x * blockDim.x; first < total_edges; first += gridDim.x * blockDim.x) {
+    // with `list` (the few edges the single-precision pass could not decide) a block takes only a quarter
+    // as many edges as it has threads, so a thread ends up with about one waypoint and the pass stays short;
+    // a block may then walk several chunks
+    const int per_block = list != nullptr ? max(1, (int)blockDim.x / 4) : (int)blockDim.x;
+    for (int first = blockIdx.x * per_block; first < total_edges; first += gridDim.x * per_block) {
         const int k = first + tid;
-        const int i = k < total_edges ? (list != nullptr ? list[k] : k) : -1;
+        const int i = (tid < per_block && k < total_edges) ? (list != nullptr ? list[k] : k) : -1;
         int count = 0;
         if (i >= 0) {
             const double* a = q0 + (size_t)i * dof;

@@ -303,21 +303,35 @@ BatchPlanner::Pool::Pool(int n) : m_n(std::max(1, n))
 
 BatchPlanner::Pool::~Pool()
 {
-    m_stop.store(true);
-    m_generation.fetch_add(1);
+    {
+        std::lock_guard<std::mutex> lk(m_mutex);
+        m_stop.store(true);
+        m_generation.fetch_add(1);
+    }
+    m_cv.notify_all();
     for (std::thread& t : m_threads) {
         t.join();
     }
 }
 
+// workers spin briefly for the next job (jobs arrive every few tens of microseconds while the planner is
+// busy) and block on the condition variable when nothing comes, so idle workers do not eat the cores the
+// other ranks' planners need
 void BatchPlanner::Pool::worker(int tid)
 {
     int seen = 0;
     for (;;) {
         int spins = 0;
         while (m_generation.load(std::memory_order_acquire) == seen) {
-            if (++spins > 256) {
-                std::this_thread::yield();
+            if (++spins < 4000) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            } else {
+                std::unique_lock<std::mutex> lk(m_mutex);
+                m_sleepers.fetch_add(1);
+                m_cv.wait(lk, [&] { return m_generation.load(std::memory_order_acquire) != seen; });
+                m_sleepers.fetch_sub(1);
             }
         }
         seen = m_generation.load(std::memory_order_acquire);
@@ -337,7 +351,13 @@ void BatchPlanner::Pool::run(const std::function<void(int)>& f)
     }
     m_job = &f;
     m_done.store(0, std::memory_order_relaxed);
-    m_generation.fetch_add(1, std::memory_order_release);
+    {
+        std::lock_guard<std::mutex> lk(m_mutex);   // a worker between its predicate check and its wait cannot miss this
+        m_generation.fetch_add(1, std::memory_order_release);
+    }
+    if (m_sleepers.load() > 0) {
+        m_cv.notify_all();
+    }
     f(0);
     int spins = 0;
     while (m_done.load(std::memory_order_acquire) != m_n - 1) {
@@ -486,20 +506,126 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
     Pool pool(m_cfg.n_threads);
     std::vector<Query> S(n_slots);          // slot -> query occupying it
     std::vector<char> occupied(n_slots, 0);
-    std::vector<int> active;                // occupied slots with a search in progress
     int next_query = 0, finished = 0;
     // refill in groups so that one bank run (one wavefront launch sequence) serves several new queries
     const int refill_min = std::max(1, n_slots / 4);
 
-    std::vector<double> q0, q1, off;
-    std::vector<int32_t> slot, h, gd;
-    std::vector<uint8_t> verdict;
+    // The active queries work in two groups (slot parity).  While the device expands one group's batch the
+    // host absorbs the other group's results and prepares its next batch, so host and device overlap.
+    struct Group
+    {
+        std::vector<int> active;            // occupied slots of this group with a search in progress
+        std::vector<double> q0, q1, off;
+        std::vector<int32_t> slot, h, gd;
+        std::vector<uint8_t> verdict;
+        bool in_flight = false;
+        int ne = 0;
+    };
+    Group G[2];
+    std::vector<double> sq;                 // setStart scratch
+    std::vector<int32_t> sh, sgd;
+    std::vector<uint8_t> sv;
+    std::vector<double> soff;
+
+    // wait for a group's batch, relax its queries, retire the finished ones
+    auto absorb = [&](int gi) -> bool {
+        Group& g = G[gi];
+        if (g.in_flight) {
+            m_stats.host_seconds += t.lap();
+            if (smplgpu_expand_batch_wait(m_ctx, gi, g.verdict.data(), g.h.data(), g.gd.data(), g.off.data()) < 0) return false;
+            m_stats.device_seconds += t.lap();
+            g.in_flight = false;
+            const int na = (int)g.active.size();
+            pool.run([&](int tid) {
+                for (int k = tid; k < na; k += pool.size()) {
+                    Query& Q = S[g.active[k]];
+                    if (Q.done || Q.n_succ == 0) {
+                        continue;
+                    }
+                    absorbOne(Q, g.verdict.data() + Q.edge_begin, g.h.data() + Q.edge_begin, g.gd.data() + Q.edge_begin,
+                              g.off.data() + (size_t)Q.edge_begin * 3);
+                }
+            });
+        }
+        size_t keep = 0;
+        for (size_t k = 0; k < g.active.size(); ++k) {
+            const int s = g.active[k];
+            if (S[s].done) {
+                out[S[s].index] = S[s].result;
+                occupied[s] = 0;
+                ++finished;
+            } else {
+                g.active[keep++] = s;
+            }
+        }
+        g.active.resize(keep);
+        return true;
+    };
+
+    // every active query of the group pops one state and generates its successors; one device batch
+    auto expand = [&](int gi) -> bool {
+        Group& g = G[gi];
+        const int na = (int)g.active.size();
+        if (na == 0) {
+            return true;
+        }
+        pool.run([&](int tid) {
+            for (int k = tid; k < na; k += pool.size()) {
+                Query& Q = S[g.active[k]];
+                if (!Q.done) {
+                    expandOne(Q);
+                }
+            }
+        });
+        int ne = 0;
+        for (int k = 0; k < na; ++k) {
+            Query& Q = S[g.active[k]];
+            Q.edge_begin = ne;
+            ne += Q.done ? 0 : Q.n_succ;
+        }
+        g.ne = ne;
+        if (ne == 0) {
+            return true;   // finished / successor-less queries are retired by the next absorb
+        }
+        g.q0.resize((size_t)ne * dof);
+        g.q1.resize((size_t)ne * dof);
+        g.slot.resize(ne);
+        pool.run([&](int tid) {
+            for (int k = tid; k < na; k += pool.size()) {
+                const Query& Q = S[g.active[k]];
+                if (Q.done || Q.n_succ == 0) {
+                    continue;
+                }
+                const double* pq = Q.lat.q(Q.expanding);
+                for (int e = 0; e < Q.n_succ; ++e) {
+                    std::copy(pq, pq + dof, g.q0.begin() + (size_t)(Q.edge_begin + e) * dof);
+                    g.slot[Q.edge_begin + e] = Q.slot;
+                }
+                std::copy(Q.succ_q1.begin(), Q.succ_q1.end(), g.q1.begin() + (size_t)Q.edge_begin * dof);
+            }
+        });
+        g.verdict.resize(ne);
+        g.h.resize(ne);
+        g.gd.resize(ne);
+        g.off.resize((size_t)ne * 3);
+        if (smplgpu_expand_batch_submit(m_ctx, g.q0.data(), g.q1.data(), g.slot.data(), ne, m_cfg.cost_per_cell, gi) < 0) return false;
+        g.in_flight = true;
+        ++m_stats.device_calls;
+        ++m_stats.rounds;
+        m_stats.edges_submitted += ne;
+        return true;
+    };
 
     while (finished < nq) {
         // ---- hand free slots to waiting queries: setGoal (one BFS per query) + setStart ----
         int n_free = 0;
         for (int s = 0; s < n_slots; ++s) n_free += occupied[s] ? 0 : 1;
-        if (next_query < nq && (n_free >= refill_min || active.empty())) {
+        const bool idle = G[0].active.empty() && G[1].active.empty();
+        if (next_query < nq && (n_free >= refill_min || idle)) {
+            // the refill uses the synchronous entry points: nothing may be in flight
+            for (int gi = 0; gi < 2; ++gi) {
+                if (!absorb(gi)) return fail_dev();
+            }
             std::vector<int32_t> new_slots, seeds;
             for (int s = 0; s < n_slots && next_query < nq; ++s) {
                 if (occupied[s]) {
@@ -518,31 +644,32 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
             if (smplgpu_bfs_bank_run_slots(m_ctx, new_slots.data(), seeds.data(), nn) < 0) return fail_dev();
             ++m_stats.bfs_runs;
             // setStart: limits + validity, then heuristic / metric distance of the start state
-            q0.resize((size_t)nn * dof);
+            sq.resize((size_t)nn * dof);
             for (int k = 0; k < nn; ++k) {
                 const int qi = S[new_slots[k]].index;
-                std::copy(starts + (size_t)qi * dof, starts + (size_t)(qi + 1) * dof, q0.begin() + (size_t)k * dof);
+                std::copy(starts + (size_t)qi * dof, starts + (size_t)(qi + 1) * dof, sq.begin() + (size_t)k * dof);
             }
-            verdict.resize(nn);
-            h.resize(nn);
-            gd.resize(nn);
-            off.resize((size_t)nn * 3);
+            sv.resize(nn);
+            sh.resize(nn);
+            sgd.resize(nn);
+            soff.resize((size_t)nn * 3);
             std::vector<uint8_t> dummy(nn);
-            if (smplgpu_is_states_valid(m_ctx, q0.data(), nn, verdict.data()) < 0) return fail_dev();
-            if (smplgpu_expand_batch(m_ctx, q0.data(), q0.data(), new_slots.data(), nn, m_cfg.cost_per_cell,
-                                     dummy.data(), h.data(), gd.data(), off.data()) < 0) return fail_dev();
+            if (smplgpu_is_states_valid(m_ctx, sq.data(), nn, sv.data()) < 0) return fail_dev();
+            if (smplgpu_expand_batch(m_ctx, sq.data(), sq.data(), new_slots.data(), nn, m_cfg.cost_per_cell,
+                                     dummy.data(), sh.data(), sgd.data(), soff.data()) < 0) return fail_dev();
             m_stats.device_calls += 3;
             m_stats.device_seconds += t.lap();
             std::vector<int> coord;
             for (int k = 0; k < nn; ++k) {
                 Query& Q = S[new_slots[k]];
-                const double* qs = &q0[(size_t)k * dof];
-                if (!checkJointLimits(qs) || !verdict[k]) {
-                    finish(Q, false);
+                const double* qs = &sq[(size_t)k * dof];
+                G[new_slots[k] & 1].active.push_back(new_slots[k]);
+                if (!checkJointLimits(qs) || !sv[k]) {
+                    finish(Q, false);   // retired by the group's next absorb
                     continue;
                 }
                 stateToCoord(qs, coord);
-                Q.lat.add(coord.data(), qs, h[k], gd[k], true);
+                Q.lat.add(coord.data(), qs, sh[k], sgd[k], true);
                 sstate(Q, 1);
                 touch(Q, 1);
                 touch(Q, 0);
@@ -550,82 +677,21 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
                 Q.search[1].f = computeKey(Q.search[1]);
                 heapPush(Q, 1);
             }
-            active.clear();
-            for (int s = 0; s < n_slots; ++s) {
-                if (occupied[s]) active.push_back(s);
-            }
         }
 
-        // ---- one lock-step round: every active query pops one state and generates its successors ----
-        const int na = (int)active.size();
-        pool.run([&](int tid) {
-            for (int k = tid; k < na; k += pool.size()) {
-                Query& Q = S[active[k]];
-                if (!Q.done) {
-                    expandOne(Q);
-                }
-            }
-        });
-        int ne = 0;
-        for (int k = 0; k < na; ++k) {
-            Query& Q = S[active[k]];
-            Q.edge_begin = ne;
-            ne += Q.done ? 0 : Q.n_succ;
+        // ---- one pipelined round: each group absorbs its previous batch and submits the next ----
+        for (int gi = 0; gi < 2; ++gi) {
+            if (!absorb(gi)) return fail_dev();
+            if (!expand(gi)) return fail_dev();
         }
-        if (ne > 0) {
-            q0.resize((size_t)ne * dof);
-            q1.resize((size_t)ne * dof);
-            slot.resize(ne);
-            pool.run([&](int tid) {
-                for (int k = tid; k < na; k += pool.size()) {
-                    const Query& Q = S[active[k]];
-                    if (Q.done || Q.n_succ == 0) {
-                        continue;
-                    }
-                    const double* pq = Q.lat.q(Q.expanding);
-                    for (int e = 0; e < Q.n_succ; ++e) {
-                        std::copy(pq, pq + dof, q0.begin() + (size_t)(Q.edge_begin + e) * dof);
-                        slot[Q.edge_begin + e] = Q.slot;
-                    }
-                    std::copy(Q.succ_q1.begin(), Q.succ_q1.end(), q1.begin() + (size_t)Q.edge_begin * dof);
-                }
-            });
-            verdict.resize(ne);
-            h.resize(ne);
-            gd.resize(ne);
-            off.resize((size_t)ne * 3);
-            m_stats.host_seconds += t.lap();
-            if (smplgpu_expand_batch(m_ctx, q0.data(), q1.data(), slot.data(), ne, m_cfg.cost_per_cell,
-                                     verdict.data(), h.data(), gd.data(), off.data()) < 0) return fail_dev();
-            ++m_stats.device_calls;
-            ++m_stats.rounds;
-            m_stats.edges_submitted += ne;
-            m_stats.device_seconds += t.lap();
-            pool.run([&](int tid) {
-                for (int k = tid; k < na; k += pool.size()) {
-                    Query& Q = S[active[k]];
-                    if (Q.done || Q.n_succ == 0) {
-                        continue;
-                    }
-                    absorbOne(Q, verdict.data() + Q.edge_begin, h.data() + Q.edge_begin, gd.data() + Q.edge_begin,
-                              off.data() + (size_t)Q.edge_begin * 3);
-                }
-            });
-        }
-        // ---- retire finished queries, freeing their slots ----
-        size_t keep = 0;
-        for (int k = 0; k < na; ++k) {
-            const int s = active[k];
-            if (S[s].done) {
-                out[S[s].index] = S[s].result;
-                occupied[s] = 0;
-                ++finished;
-            } else {
-                active[keep++] = s;
-            }
-        }
-        active.resize(keep);
         m_stats.host_seconds += t.lap();
+    }
+    // nothing can be in flight here: a group's queries finish in absorb or expand, and a batch is only
+    // submitted for queries that are not done; drain defensively anyway
+    for (int gi = 0; gi < 2; ++gi) {
+        if (G[gi].in_flight) {
+            if (smplgpu_expand_batch_wait(m_ctx, gi, G[gi].verdict.data(), G[gi].h.data(), G[gi].gd.data(), G[gi].off.data()) < 0) return fail_dev();
+        }
     }
     return true;
 }

@@ -16,6 +16,8 @@
 #define SMPLHOST_BATCH_PLANNER_H
 
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <cstdint>
 #include <functional>
 #include <string>
@@ -137,6 +139,9 @@ private:
         std::atomic<int> m_generation{ 0 };
         std::atomic<int> m_done{ 0 };
         std::atomic<bool> m_stop{ false };
+        std::atomic<int> m_sleepers{ 0 };
+        std::mutex m_mutex;
+        std::condition_variable m_cv;
         const std::function<void(int)>* m_job = nullptr;
         void worker(int tid);
     };
