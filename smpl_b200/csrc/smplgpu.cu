@@ -44,6 +44,7 @@ struct smplgpu_ctx
     float* d_blob = nullptr; size_t blob_cap = 0;   // bytes
     int blob_words = 0;
     int v32_threads = V32_THREADS;
+    int v32_slots = 0, v32_ptrees = 0;
     double e_pos = 0.0, eps_cells = 0.0;
     Grid32 grid32{};
     int* d_unc_list = nullptr; size_t unc_cap = 0;  // ints
@@ -385,11 +386,6 @@ static int build_model32(smplgpu_ctx* ctx)
             skip[i] = i + size[node];
         }
     }
-    // ranks of the double radii (the pair descent splits the larger sphere)
-    std::vector<double> radii;
-    for (int i = 0; i < n32; ++i) radii.push_back(m.node_radius[orig_of[i]]);
-    std::sort(radii.begin(), radii.end());
-    radii.erase(std::unique(radii.begin(), radii.end()), radii.end());
 
     // ---- error bounds ----
     std::vector<double> EF(nl), Et(nl), tn(nl);
@@ -447,12 +443,51 @@ static int build_model32(smplgpu_ctx* ctx)
         return 0; // bound too loose for this resolution: the double path handles everything
     }
 
+    // ---- per-thread shared-memory state: transforms of branching parents, root centres of pair trees ----
+    std::vector<int> slot32(nl, -1), ptree_of_tree(m.n_trees, -1);
+    int n_slots32 = 0, n_ptrees = 0;
+    for (int l = 0; l < nl; ++l) {
+        const int p = m.link_parent[l];
+        if (p >= 0 && p != l - 1 && slot32[p] < 0) {
+            slot32[p] = 0;   // marked; numbered below in link order
+        }
+    }
+    for (int l = 0; l < nl; ++l) {
+        if (slot32[l] == 0) slot32[l] = n_slots32++;
+    }
+    // Pair tests: with few checked pairs (one arm) the root spheres almost never overlap, so the kernel keeps
+    // only the root centres and sends an overlap to the double kernel; with many pairs (two arms + torso: root
+    // overlaps in every sixth state) it keeps the transforms of all paired links and descends itself.
+    const bool roots_only = m.n_pairs <= 24;
+    if (roots_only) {
+        for (int p = 0; p < m.n_pairs; ++p) {
+            if (ptree_of_tree[m.pair_a[p]] < 0) ptree_of_tree[m.pair_a[p]] = n_ptrees++;
+            if (ptree_of_tree[m.pair_b[p]] < 0) ptree_of_tree[m.pair_b[p]] = n_ptrees++;
+        }
+    } else {
+        n_slots32 = 0;
+        for (int l = 0; l < nl; ++l) {
+            slot32[l] = m.link_slot[l];     // the double kernels' slot set: branching parents + paired links
+            n_slots32 = std::max(n_slots32, slot32[l] + 1);
+        }
+    }
+    // ranks of the double radii (the full pair descent splits the larger sphere)
+    std::vector<double> radii;
+    for (int i = 0; i < n32; ++i) radii.push_back(m.node_radius[orig_of[i]]);
+    std::sort(radii.begin(), radii.end());
+    radii.erase(std::unique(radii.begin(), radii.end()), radii.end());
+    std::vector<int> ptree_of_root(nn, -1);
+    for (int t = 0; t < m.n_trees; ++t) {
+        if (ptree_of_tree[t] >= 0) ptree_of_root[m.tree_root[t]] = ptree_of_tree[t];
+    }
+
     // ---- blob ----
     auto align4 = [](int w) { return (w + 3) / 4 * 4; };
     Model32Header h;
     memset(&h, 0, sizeof(h));
     int w = (int)(sizeof(Model32Header) / 4);
-    h.n_links = nl; h.n_nodes = n32; h.n_pairs = m.n_pairs; h.n_allowed = m.n_allowed; h.n_slots = m.n_slots; h.dof = m.dof;
+    h.n_links = nl; h.n_nodes = n32; h.n_pairs = m.n_pairs; h.n_allowed = m.n_allowed; h.n_slots = n_slots32; h.dof = m.dof;
+    h.n_ptrees = n_ptrees;
     h.off_link_i = w; w += 4 * nl;
     h.off_link_n = w; w = align4(w + 2 * nl);
     h.off_origin = w; w += 12 * nl;
@@ -461,7 +496,7 @@ static int build_model32(smplgpu_ctx* ctx)
     h.off_node_c = w; w += 4 * n32;
     h.off_node_i = w; w += 4 * n32;
     h.off_node_orig = w; w = align4(w + n32);
-    h.off_pair = w; w = align4(w + 2 * m.n_pairs);
+    h.off_pair = w; w = align4(w + 4 * m.n_pairs);
     h.off_allowed = w; w = align4(w + 2 * m.n_allowed);
     h.words = w;
     h.e_pos = (float)e_pos;
@@ -484,7 +519,7 @@ static int build_model32(smplgpu_ctx* ctx)
         BI[h.off_link_i + 4 * l] = m.link_parent[l];
         BI[h.off_link_i + 4 * l + 1] = fn;
         BI[h.off_link_i + 4 * l + 2] = m.link_var[l];
-        BI[h.off_link_i + 4 * l + 3] = m.link_slot[l];
+        BI[h.off_link_i + 4 * l + 3] = slot32[l];
         BI[h.off_link_n + 2 * l] = link_nbeg[l];
         BI[h.off_link_n + 2 * l + 1] = link_nend[l];
         for (int k = 0; k < 12; ++k) {
@@ -499,13 +534,15 @@ static int build_model32(smplgpu_ctx* ctx)
         B[h.off_node_c + 4 * i + 3] = (float)m.node_radius[node];
         BI[h.off_node_i + 4 * i] = skip[i];
         BI[h.off_node_i + 4 * i + 1] = m.node_thresh[node];
-        BI[h.off_node_i + 4 * i + 2] = m.link_slot[m.node_link[node]];
+        BI[h.off_node_i + 4 * i + 2] = roots_only ? ptree_of_root[node] : m.link_slot[m.node_link[node]];
         BI[h.off_node_i + 4 * i + 3] = (int)(std::lower_bound(radii.begin(), radii.end(), m.node_radius[node]) - radii.begin());
         BI[h.off_node_orig + i] = node;
     }
     for (int p = 0; p < m.n_pairs; ++p) {
-        BI[h.off_pair + 2 * p] = new_of[m.tree_root[m.pair_a[p]]];
-        BI[h.off_pair + 2 * p + 1] = new_of[m.tree_root[m.pair_b[p]]];
+        BI[h.off_pair + 4 * p] = ptree_of_tree[m.pair_a[p]];
+        BI[h.off_pair + 4 * p + 1] = ptree_of_tree[m.pair_b[p]];
+        BI[h.off_pair + 4 * p + 2] = new_of[m.tree_root[m.pair_a[p]]];
+        BI[h.off_pair + 4 * p + 3] = new_of[m.tree_root[m.pair_b[p]]];
     }
     for (int k = 0; k < m.n_allowed; ++k) {
         BI[h.off_allowed + 2 * k] = new_of[m.allowed_a[k]];
@@ -513,8 +550,10 @@ static int build_model32(smplgpu_ctx* ctx)
     }
 
     // ---- launch geometry + upload ----
-    const size_t per_thread = (size_t)m.n_slots * 12 * sizeof(float) + 3 * sizeof(int);
+    const size_t per_thread = ((size_t)n_slots32 * 12 + (size_t)n_ptrees * 3) * sizeof(float) + 3 * sizeof(int);
     const size_t fixed = (size_t)w * 4 + 64;
+    ctx->v32_slots = n_slots32;
+    ctx->v32_ptrees = n_ptrees;
     const size_t smem_max = 227 * 1024;
     int threads = V32_THREADS;
     while (threads > 32 && fixed + per_thread * threads > smem_max) threads -= 32;
@@ -539,7 +578,8 @@ static int build_model32(smplgpu_ctx* ctx)
 
 static size_t v32_smem(const smplgpu_ctx* ctx)
 {
-    return (size_t)ctx->blob_words * 4 + (size_t)ctx->h_model->n_slots * 12 * sizeof(float) * ctx->v32_threads
+    return (size_t)ctx->blob_words * 4
+           + ((size_t)ctx->v32_slots * 12 + (size_t)ctx->v32_ptrees * 3) * sizeof(float) * ctx->v32_threads
            + (3 * (size_t)ctx->v32_threads + 2) * sizeof(int);
 }
 

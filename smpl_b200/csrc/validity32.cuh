@@ -23,8 +23,10 @@
 // Work decomposition: one thread per state (edges: the block's waypoints are
 // spread over its threads as in validity.cuh); the robot tables live in shared
 // memory (a compact float copy, pre-order sphere trees with skip links so the
-// descent needs no stack); link transforms that are needed again live in
-// per-thread shared-memory slots.
+// descent needs no stack); per thread, shared memory keeps the transforms of
+// branching parents and the root-sphere centres of the trees that take part in
+// pair tests (12 bytes per tree instead of a 48-byte transform per link, which
+// doubles the resident warps).
 //
 // Reference semantics restated: see validity.cuh.
 #pragma once
@@ -42,22 +44,24 @@ constexpr float V32_MAX_ANGLE = 64.0f;   // beyond this the hi/lo split no longe
 struct Model32Header
 {
     int words;            // total size of the blob
-    int n_links, n_nodes, n_pairs, n_allowed, n_slots, dof;
+    int n_links, n_nodes, n_pairs, n_allowed, n_slots, dof;   // n_slots: transforms kept for branching parents
     int off_link_i;       // int4 per link: parent, fn, var, slot
     int off_link_n;       // int2 per link: first node, end node (pre-order ids of the trees riding on the link)
     int off_origin;       // float[12] per link (joint origin; constant joints pre-multiplied)
     int off_axis;         // float4 per link
     int off_base;         // float[12] per link (used when parent < 0)
     int off_node_c;       // float4 per node: centre xyz, radius
-    int off_node_i;       // int4 per node: skip, threshold, slot of its link, rank of the (double) radius
+    int off_node_i;       // int4 per node: skip, threshold, z, rank of the (double) radius; z = pair-tree index of a
+                          // paired tree's root (else -1) in roots-only mode, slot of the node's link in full mode
     int off_node_orig;    // int per node: index in the caller's node table
-    int off_pair;         // int2 per pair: root nodes (pre-order ids)
+    int off_pair;         // int4 per pair: pair-tree index a, b; root node a, b (pre-order ids)
     int off_allowed;      // int2 per allowed leaf pair (pre-order ids)
     float e_pos;          // bound on |centre_f32 - centre_f64| (metres)
     float eps_cells;      // bound on the grid-coordinate error (cells)
     float pair_k;         // 2.5 * e_pos
     float q_lin_max;      // largest |q| of a prismatic variable the bound covers
-    int pad[3];
+    int n_ptrees;         // roots-only pair mode: trees in pair tests (one saved root centre each); 0 = full descent mode
+    int pad[2];
 };
 static_assert(sizeof(Model32Header) % 16 == 0, "header must keep 16-byte alignment of the arrays");
 
@@ -161,7 +165,7 @@ struct S32
     const float* base;
     const float4* node_c;
     const int4* node_i;
-    const int2* pair;
+    const int4* pair;
     const int2* allowed;
     const int* node_orig;
 };
@@ -178,7 +182,7 @@ __device__ __forceinline__ S32 view32(const float* blob)
     s.base = blob + h->off_base;
     s.node_c = reinterpret_cast<const float4*>(blob + h->off_node_c);
     s.node_i = reinterpret_cast<const int4*>(blob + h->off_node_i);
-    s.pair = reinterpret_cast<const int2*>(blob + h->off_pair);
+    s.pair = reinterpret_cast<const int4*>(blob + h->off_pair);
     s.allowed = reinterpret_cast<const int2*>(blob + h->off_allowed);
     s.node_orig = reinterpret_cast<const int*>(blob + h->off_node_orig);
     return s;
@@ -290,9 +294,14 @@ __device__ int check_state32(const S32& S, const int* __restrict__ var_type, con
         int node = nr.x;
         while (node < nr.y) {
             const float4 c = S.node_c[node];
-            const int4 ni = S.node_i[node];   // skip, thresh, slot, radius rank
+            const int4 ni = S.node_i[node];   // skip, thresh, pair-tree index, -
             float x, y, z;
             xf32_point(T, c.x, c.y, c.z, x, y, z);
+            if (H->n_ptrees > 0 && ni.z >= 0) {
+                // root of a tree that takes part in pair tests: keep its centre
+                float* o = slots + ((size_t)H->n_slots * 12 + (size_t)ni.z * 3) * blockDim.x + threadIdx.x;
+                o[0] = x; o[blockDim.x] = y; o[2 * blockDim.x] = z;
+            }
             ++cnt.lookups;
             const int r = lookup32(df, G, eps, x, y, z, ni.y);
             if (r == 1) {
@@ -308,13 +317,51 @@ __device__ int check_state32(const S32& S, const int* __restrict__ var_type, con
         }
     }
 
-    // sphere-tree pairs
-    int stack[MAX_TREE_DEPTH];
     const int np = H->n_pairs;
+    if (H->n_ptrees > 0) {
+        // Sphere-tree pairs: only the root spheres are tested here, from the root centres saved above.  Roots that
+        // are certainly apart prune the pair, which is what happens in all but a handful of states; a pair of
+        // overlapping single-sphere trees is a certain collision; anything else (overlapping roots that need the
+        // descent, or an undecidable distance) goes to the double-precision kernel, which keeps the link
+        // transforms the descent needs.
+        const float* rp = slots + (size_t)H->n_slots * 12 * blockDim.x + threadIdx.x;
+        for (int pi = 0; pi < np; ++pi) {
+            const int4 pr = S.pair[pi];   // pair-tree index a, b; root node a, b
+            const float* pa = rp + (size_t)pr.x * 3 * blockDim.x;
+            const float* pb = rp + (size_t)pr.y * 3 * blockDim.x;
+            const float dx = pb[0] - pa[0], dy = pb[blockDim.x] - pa[blockDim.x], dz = pb[2 * blockDim.x] - pa[2 * blockDim.x];
+            ++cnt.pairs;
+            const float cd2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            const float rr = S.node_c[pr.z].w + S.node_c[pr.w].w;
+            const float rr2 = rr * rr;
+            const float tol = fmaf(H->pair_k, sqrtf(cd2) + rr, 2e-6f * (cd2 + rr2));
+            const float d = cd2 - rr2;
+            if (d > tol) {
+                continue;
+            }
+            const int4 i1 = S.node_i[pr.z], i2 = S.node_i[pr.w];
+            if (d < -tol && i1.x == pr.z + 1 && i2.x == pr.w + 1) {
+                bool allowed = false;
+                for (int k = 0; k < H->n_allowed; ++k) {
+                    const int2 al = S.allowed[k];
+                    allowed |= (al.x == pr.z && al.y == pr.w) || (al.x == pr.w && al.y == pr.z);
+                }
+                if (!allowed) {
+                    return 0;
+                }
+                continue;
+            }
+            amb = true;
+        }
+        return amb ? 2 : 1;
+    }
+    // Sphere-tree pairs, full descent (robots whose pair roots overlap often, e.g. two arms + torso): the
+    // transforms of all links with paired trees are in the slots.
+    int stack[MAX_TREE_DEPTH];
     for (int pi = 0; pi < np; ++pi) {
         int sp = 0;
-        const int2 roots = S.pair[pi];
-        stack[sp++] = (roots.x << 16) | roots.y;
+        const int4 proots = S.pair[pi];
+        stack[sp++] = (proots.z << 16) | proots.w;
         while (sp > 0) {
             const int packed = stack[--sp];
             const int n1 = packed >> 16, n2 = packed & 0xFFFF;
@@ -399,7 +446,8 @@ __device__ __forceinline__ void append_uncertain(bool push, int item, int* __res
     }
 }
 
-// dynamic shared memory: blob | slots (n_slots * 12 * blockDim floats) | edges: (blockDim + 1) offsets, blockDim ok, blockDim unc
+// dynamic shared memory: blob | slots (n_slots * 12 * blockDim floats) | root centres (n_ptrees * 3 * blockDim floats)
+//                        | edges: (blockDim + 1) offsets, blockDim ok, blockDim unc
 __global__ void __launch_bounds__(V32_THREADS)
 states_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const DevModel* __restrict__ M,
                       const uint16_t* __restrict__ df, Grid32 G, const double* __restrict__ q, int n,
@@ -469,7 +517,7 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
     __syncthreads();   // blob copied
     const S32 S = view32(blob);
     float* slots = blob + blob_words;
-    int* s_off = reinterpret_cast<int*>(slots + (size_t)S.h->n_slots * 12 * blockDim.x);
+    int* s_off = reinterpret_cast<int*>(slots + ((size_t)S.h->n_slots * 12 + (size_t)S.h->n_ptrees * 3) * blockDim.x);
     int* s_ok = s_off + blockDim.x + 1;
     int* s_unc = s_ok + blockDim.x;
     s_off[tid + 1] = count;
