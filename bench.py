@@ -309,7 +309,8 @@ def main():
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
     hq = torch.from_numpy(q).pin_memory()
     hq0 = torch.from_numpy(q0).pin_memory()
-    hq1 = torch.from_numpy(q1).pin_memory()
+    deltas = np.ascontiguousarray(scenes.pr2_mprim_deltas())
+    hpid = torch.from_numpy((np.arange(n) % len(deltas)).astype(np.int32)).pin_memory()   # edge i = state i + primitive i mod 22
     hv = torch.empty(n, dtype=torch.uint8).pin_memory()
     hev = torch.empty(n, dtype=torch.uint8).pin_memory()
     L = ctx.L
@@ -317,8 +318,10 @@ def main():
 
     def step_e2e():
         r = L.smplgpu_is_states_valid(ctx.h, C.cast(hq.data_ptr(), api.c_double_p), n, C.cast(hv.data_ptr(), api.c_uint8_p))
-        r |= L.smplgpu_is_edges_valid(ctx.h, C.cast(hq0.data_ptr(), api.c_double_p), C.cast(hq1.data_ptr(), api.c_double_p),
-                                      n, C.cast(hev.data_ptr(), api.c_uint8_p), None)
+        # edges as GetSuccs produces them: (parent state, motion primitive id) against the primitive table
+        r |= L.smplgpu_is_mprim_edges_valid(ctx.h, C.cast(hq0.data_ptr(), api.c_double_p), C.cast(hpid.data_ptr(), api.c_int32_p),
+                                            n, deltas.ctypes.data_as(api.c_double_p), len(deltas),
+                                            C.cast(hev.data_ptr(), api.c_uint8_p), None)
         if r != 0:
             raise RuntimeError(L.smplgpu_last_error(ctx.h).decode())
 
@@ -335,7 +338,6 @@ def main():
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * units_per_step * e2e_steps / (float(e2e_ms.item()) * 1e-3)
     assert torch.equal(hv.to(dev), d_v) and torch.equal(hev.to(dev), d_ev), "host-buffer path disagrees with resident path"
 
@@ -361,6 +363,8 @@ def main():
         bfs = {"grid": "%d^3" % nb, "levels": ctx.bfs_last_levels(), "ms": bfs_ms,
                "mvoxel_s": nb ** 3 / (bfs_ms * 1e-3) / 1e6,
                "algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (bfs_ms * 1e-3) / 1e9}
+
+    clocks = sampler.stop() if rank == 0 else None   # sampled across the validity, end-to-end and BFS regions
 
     # ---- plan queries/s (config[0]/[3] shape): PR2 right arm on the tabletop scene, queries sharded over ranks ----
     plan = None
@@ -477,7 +481,8 @@ def main():
                    "l2_policy": "inputs (%.0f MB/step) exceed the 126 MB L2; the 2 MB distance field is L2-resident by design" % ((3 * n * dof * 8) / 1e6),
                    "valid_fraction_states": float(d_v.float().mean().item()), "valid_fraction_edges": float(d_ev.float().mean().item())},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * n * dof * 8, "d2h_bytes_per_step": 2 * n},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * dof * 8 + 4 * n, "d2h_bytes_per_step": 2 * n,
+                "calls": "smplgpu_is_states_valid(q) + smplgpu_is_mprim_edges_valid(q, primitive ids, table): host buffers in, verdicts out"},
         "gpu_launches": int(gpu_launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -230,6 +230,14 @@ int smplgpu_goal_heuristics_dev(smplgpu_ctx* ctx, const double* q_dev, int n, in
 /* ForwardKinematicsInterface::computePlanningLinkFK + getTargetOffsetPose: double pose6[n][6] */
 int smplgpu_planning_frame_fk(smplgpu_ctx* ctx, const double* q, int n, double* pose6);
 
+/* The same for edges given the way ManipLattice::GetSuccs produces them -- a parent state and a motion primitive
+ * (ManipLatticeActionSpace::applyMotionPrimitive, manip_lattice_action_space.cpp:575-610): edge i goes from q0[i]
+ * to q0[i] + deltas[prim_id[i]] (deltas[n_prims][dof]; an id outside [0, n_prims) means a zero-length edge).  The
+ * successor is formed on the device with the same single IEEE addition per joint the host would do, so only the
+ * parents and one int per edge cross the bus. */
+int smplgpu_is_mprim_edges_valid(smplgpu_ctx* ctx, const double* q0, const int32_t* prim_id, int n,
+                                 const double* deltas, int n_prims, uint8_t* verdict, int32_t* waypoint_counts);
+
 /* ---- precision control / certification (no counterpart in the reference) ---- */
 int smplgpu_set_precision_mode(smplgpu_ctx* ctx, int mode);
 /* bound on |sphere centre (float) - sphere centre (double)| in metres and on the grid-coordinate error in cells;

@@ -87,6 +87,7 @@ def gpu_lib():
         L.smplgpu_goal_heuristics.argtypes = [vp, dp, i, i, ip]
         L.smplgpu_goal_heuristics_dev.argtypes = [vp, vp, i, i, vp]
         L.smplgpu_planning_frame_fk.argtypes = [vp, dp, i, dp]
+        L.smplgpu_is_mprim_edges_valid.argtypes = [vp, dp, ip, i, dp, i, bp, ip]
         L.smplgpu_set_precision_mode.argtypes = [vp, i]
         L.smplgpu_certified_bounds.argtypes = [vp, dp, dp]
         L.smplgpu_last_f64_resolved.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -333,6 +334,17 @@ class GpuContext:
         c = np.zeros(len(q0), np.int32) if want_counts else None
         self._ck(self.L.smplgpu_is_edges_valid(self.h, _dp(q0), _dp(q1), len(q0), _bp(v),
                                                _ip(c) if want_counts else None), "is_edges_valid")
+        return (v, c) if want_counts else v
+
+    def is_mprim_edges_valid(self, q0, prim_id, deltas, want_counts=True):
+        """Edges q0[i] -> q0[i] + deltas[prim_id[i]] (the form GetSuccs produces them in)."""
+        q0 = self._q(q0)
+        pid = np.ascontiguousarray(prim_id, dtype=np.int32)
+        d = np.ascontiguousarray(deltas, dtype=np.float64).reshape(-1, self.dof)
+        v = np.zeros(len(q0), np.uint8)
+        c = np.zeros(len(q0), np.int32) if want_counts else None
+        self._ck(self.L.smplgpu_is_mprim_edges_valid(self.h, _dp(q0), _ip(pid), len(q0), _dp(d), len(d), _bp(v),
+                                                     _ip(c) if want_counts else None), "is_mprim_edges_valid")
         return (v, c) if want_counts else v
 
     def is_edges_valid_dev(self, q0_ptr, q1_ptr, n, verdict_ptr, counts_ptr=None):

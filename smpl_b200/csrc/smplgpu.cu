@@ -47,6 +47,8 @@ struct smplgpu_ctx
     int v32_slots = 0, v32_ptrees = 0;
     double e_pos = 0.0, eps_cells = 0.0;
     Grid32 grid32{};
+    int* d_prim = nullptr; size_t prim_cap = 0;     // bytes; primitive ids of two chunks in flight
+    double* d_deltas = nullptr; size_t deltas_cap = 0;
     int* d_unc_list = nullptr; size_t unc_cap = 0;  // ints
     int* d_unc_count = nullptr;
 
@@ -241,6 +243,7 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
     free_grid(ctx->bank);
     cudaFree(ctx->d_model); cudaFree(ctx->d_stats); cudaFree(ctx->d_seed_count); cudaFree(ctx->d_df);
     cudaFree(ctx->d_blob); cudaFree(ctx->d_unc_list); cudaFree(ctx->d_unc_count);
+    cudaFree(ctx->d_prim); cudaFree(ctx->d_deltas);
     cudaFree(ctx->d_q0); cudaFree(ctx->d_q1); cudaFree(ctx->d_verdict); cudaFree(ctx->d_counts); cudaFree(ctx->d_misc);
     for (int i = 0; i < 2; ++i) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
@@ -993,17 +996,25 @@ static bool is_pinned_host(const void* p)
 // Host-pointer entry points.  The batch is cut into chunks; the host->device copy of chunk k+1 runs on a
 // second stream while the kernels of chunk k run, and verdicts stream back behind the kernels.  Page-locked
 // caller buffers are used as DMA source / target directly; pageable ones go through pinned staging.
+// With `prim_id` the edges are (parent, motion primitive) pairs: only the parents and one int per edge cross
+// the bus, the successors are formed on the device from the primitive table `d_deltas`.
 static int run_host_batched(smplgpu_ctx* ctx, const double* q0, const double* q1, int n,
-                            uint8_t* verdict, int32_t* counts)
+                            uint8_t* verdict, int32_t* counts, const int32_t* prim_id = nullptr,
+                            const double* d_deltas = nullptr, int n_prims = 0)
 {
     const int dof = ctx->h_model->dof;
-    const bool edges = q1 != nullptr;
+    const bool by_prim = prim_id != nullptr;
+    const bool edges = q1 != nullptr || by_prim;
     const int chunk = 1 << 17;
     const int cn = std::min(n, chunk);
     int r = ensure_state_buffers(ctx, (size_t)cn * 2, dof, edges); // two chunks in flight
     if (r) return r;
     const size_t row = (size_t)dof * sizeof(double);
-    const bool in_direct = is_pinned_host(q0) && (!edges || is_pinned_host(q1));
+    const bool in_direct = is_pinned_host(q0) && (!edges || is_pinned_host(by_prim ? (const void*)prim_id : (const void*)q1));
+    if (by_prim) {
+        r = grow(ctx, (void**)&ctx->d_prim, &ctx->prim_cap, (size_t)cn * 2 * sizeof(int));
+        if (r) return r;
+    }
     const bool out_direct = is_pinned_host(verdict) && (!counts || is_pinned_host(counts));
     if (!in_direct) {
         r = grow_pinned(ctx, ctx->pinned, &ctx->pinned_cap, (size_t)cn * row * (edges ? 2 : 1));
@@ -1048,22 +1059,30 @@ static int run_host_batched(smplgpu_ctx* ctx, const double* q0, const double* q1
             CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[b], 0));   // device buffer b is free again
         }
         const double* s0 = q0 + (size_t)off * dof;
-        const double* s1 = edges ? q1 + (size_t)off * dof : nullptr;
+        // second input of an edge batch: the successor states, or one primitive id per edge
+        const void* s1 = by_prim ? (const void*)(prim_id + off) : (edges ? (const void*)(q1 + (size_t)off * dof) : nullptr);
+        const size_t s1_bytes = by_prim ? (size_t)m * sizeof(int) : (size_t)m * row;
+        int* dprim = by_prim ? ctx->d_prim + (size_t)b * cn : nullptr;
         if (!in_direct) {
             uint8_t* pin = (uint8_t*)ctx->pinned[b];
             memcpy(pin, s0, (size_t)m * row);
             s0 = (const double*)pin;
             if (edges) {
-                memcpy(pin + (size_t)cn * row, s1, (size_t)m * row);
-                s1 = (const double*)(pin + (size_t)cn * row);
+                memcpy(pin + (size_t)cn * row, s1, s1_bytes);
+                s1 = pin + (size_t)cn * row;
             }
         }
         CU(cudaMemcpyAsync(dq0, s0, (size_t)m * row, cudaMemcpyHostToDevice, ctx->copy_stream));
         if (edges) {
-            CU(cudaMemcpyAsync(dq1, s1, (size_t)m * row, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(cudaMemcpyAsync(by_prim ? (void*)dprim : (void*)dq1, s1, s1_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         }
         CU(cudaEventRecord(ctx->ev_in[b], ctx->copy_stream));
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        if (by_prim) {
+            const size_t total = (size_t)m * dof;
+            apply_mprims_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(dq0, dprim, d_deltas, n_prims, dof, m, dq1);
+            ++ctx->launches;
+        }
         r = edges ? launch_edges(ctx, dq0, dq1, m, dv, counts ? dc : nullptr) : launch_states(ctx, dq0, m, dv);
         if (r) return r;
         if (out_direct) {
@@ -1110,6 +1129,24 @@ int smplgpu_is_edges_valid(smplgpu_ctx* ctx, const double* q0, const double* q1,
     if (n == 0) return 0;
     if (!q0 || !q1 || !verdict) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
     return run_host_batched(ctx, q0, q1, n, verdict, waypoint_counts);
+}
+
+int smplgpu_is_mprim_edges_valid(smplgpu_ctx* ctx, const double* q0, const int32_t* prim_id, int n,
+                                 const double* deltas, int n_prims, uint8_t* verdict, int32_t* waypoint_counts)
+{
+    if (!ctx || n < 0 || n_prims < 0) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (n == 0) return 0;
+    if (!q0 || !prim_id || !verdict || (n_prims > 0 && !deltas)) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    const size_t bytes = (size_t)std::max(1, n_prims) * ctx->h_model->dof * sizeof(double);
+    r = grow(ctx, (void**)&ctx->d_deltas, &ctx->deltas_cap, bytes);
+    if (r) return r;
+    if (n_prims > 0) {
+        CU(cudaMemcpyAsync(ctx->d_deltas, deltas, (size_t)n_prims * ctx->h_model->dof * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));   // `deltas` may be pageable: do not leave the copy reading it
+    }
+    return run_host_batched(ctx, q0, nullptr, n, verdict, waypoint_counts, prim_id, ctx->d_deltas, n_prims);
 }
 
 int smplgpu_set_precision_mode(smplgpu_ctx* ctx, int mode)

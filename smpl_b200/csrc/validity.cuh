@@ -449,6 +449,22 @@ edges_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ 
     flush_counters(cnt, stats);
 }
 
+// ManipLatticeActionSpace::applyMotionPrimitive (manip_lattice_action_space.cpp:575-610) for a batch:
+// successor = parent + delta of the edge's motion primitive (one IEEE addition per joint)
+__global__ void apply_mprims_kernel(const double* __restrict__ q0, const int* __restrict__ prim,
+                                    const double* __restrict__ deltas, int n_prims, int dof, int n,
+                                    double* __restrict__ q1)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * dof) {
+        return;
+    }
+    const int e = (int)(i / dof), v = (int)(i - (size_t)e * dof);
+    const int p = prim[e];
+    const double a = q0[i];
+    q1[i] = (p >= 0 && p < n_prims) ? deltas[(size_t)p * dof + v] + a : a;
+}
+
 // Kernel (1) alone: sphere centres of every tree node, out[n][n_nodes][3]
 __global__ void __launch_bounds__(VALIDITY_THREADS)
 fk_centers_kernel(const DevModel* __restrict__ M, const double* __restrict__ q, int n, double* __restrict__ out)

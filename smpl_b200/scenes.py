@@ -292,3 +292,16 @@ def tabletop_queries(n, seed=13, dof=7):
     goals = lo + rng.random((n, 3)) * np.array([0.45, 0.9, 0.5])
     starts = np.tile(np.array(PR2_DEMO_START[:dof], np.float64), (n, 1))
     return np.ascontiguousarray(starts), np.ascontiguousarray(goals)
+
+
+UBR1_DEMO_START = (0.0, 0.3, 0.0, -1.2, 0.0, 0.9, 0.0)    # OUR fixture: arm over the table, object in hand
+
+
+def ubr1_tabletop_queries(n, seed=13):
+    """Config 4: UBR1 arm + attached object, start fixed, goals uniform over a 0.6 x 1.0 x 0.5 m box above the
+    table."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lo = np.array([0.45, -0.5, 0.65])
+    goals = lo + rng.random((n, 3)) * np.array([0.6, 1.0, 0.5])
+    starts = np.tile(np.array(UBR1_DEMO_START, np.float64), (n, 1))
+    return np.ascontiguousarray(starts), np.ascontiguousarray(goals)

@@ -120,6 +120,30 @@ def test_batch_planner_matches_sequential_oracle(tabletop):
         len(ref), n_ok, stats["rounds"], stats["edges_submitted"], stats["device_seconds"], stats["host_seconds"]))
 
 
+def test_ubr1_with_attached_object_queries_match_oracle():
+    """Config 4 shape: UBR1 arm, attached box, extra ACM entries; queries dealt round-robin as on 2 GPUs."""
+    from smpl_b200 import sharding
+    scene = scenes.ubr1_tabletop_scene()
+    o = make_oracle(scene)
+    ctx, tables = api.setup_context(scene)
+    params = scenes.PlanParams(scene.dof)
+    params.max_expansions = 1500
+    starts, goals = scenes.ubr1_tabletop_queries(20, seed=13)
+    ref = _run_oracle(o, scene, params, starts, goals)
+    solved = 0
+    for rank in range(2):
+        mine = sharding.round_robin_shard(len(starts), rank, 2)
+        got, _ = api.plan_batch(ctx, scene, tables, params, starts[mine], goals[mine], max_concurrent=6, n_threads=2)
+        for i, b in zip(mine, got):
+            a = ref[i]
+            assert (a["success"], a["expansions"], a["cost"], a["num_states"]) == \
+                   (b["success"], b["expansions"], b["cost"], b["num_states"]), i
+            assert np.array_equal(a["path_ids"], b["path_ids"]), i
+            solved += a["success"]
+    assert solved >= 10
+    ctx.close()
+
+
 def test_batch_planner_reproduces_golden_plans(tabletop):
     scene, o, ctx, tables = tabletop
     gold = json.load(open(os.path.join(GOLD, "pr2_tabletop_plans.json")))

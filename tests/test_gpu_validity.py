@@ -101,6 +101,24 @@ def test_edges_parity(pr2):
     assert np.array_equal(gc, cc) and np.array_equal(gv, cv)
 
 
+def test_edges_given_as_parent_plus_motion_primitive(pr2):
+    """smplgpu_is_mprim_edges_valid forms q1 = q0 + delta[prim] on the device: same verdicts and counts as
+    shipping q1, and as the oracle."""
+    scene, o, ctx, tables = pr2
+    lo, hi, cont = tables.limits()
+    q = scenes.random_states(300000, lo, hi, cont, seed=29)     # several chunks of the host pipeline
+    deltas = scenes.pr2_mprim_deltas()
+    pid = (np.arange(len(q)) % len(deltas)).astype(np.int32)
+    pid[::1000] = -1                                            # out-of-table id: zero-length edge
+    q1 = q + np.where(pid[:, None] >= 0, deltas[np.maximum(pid, 0)], 0.0)
+    v_a, c_a = ctx.is_mprim_edges_valid(q, pid, deltas)
+    v_b, c_b = ctx.is_edges_valid(q, q1)
+    assert np.array_equal(v_a, v_b) and np.array_equal(c_a, c_b)
+    assert (c_a[::1000] == 0).all() and (v_a[::1000] == 1).all()
+    v_o, c_o = o.is_edges_valid(q[:4000], q1[:4000])
+    assert np.array_equal(v_a[:4000], v_o) and np.array_equal(c_a[:4000], c_o)
+
+
 def test_edge_cases(pr2):
     scene, o, ctx, tables = pr2
     lo, hi, cont = tables.limits()
