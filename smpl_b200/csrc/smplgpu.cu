@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -553,7 +554,7 @@ static int build_model32(smplgpu_ctx* ctx)
     }
 
     // ---- launch geometry + upload ----
-    const size_t per_thread = ((size_t)n_slots32 * 12 + (size_t)n_ptrees * 3) * sizeof(float) + 3 * sizeof(int);
+    const size_t per_thread = ((size_t)n_slots32 * 12 + (size_t)n_ptrees * 3) * sizeof(float) + 4 * sizeof(int);
     const size_t fixed = (size_t)w * 4 + 64;
     ctx->v32_slots = n_slots32;
     ctx->v32_ptrees = n_ptrees;
@@ -583,7 +584,7 @@ static size_t v32_smem(const smplgpu_ctx* ctx)
 {
     return (size_t)ctx->blob_words * 4
            + ((size_t)ctx->v32_slots * 12 + (size_t)ctx->v32_ptrees * 3) * sizeof(float) * ctx->v32_threads
-           + (3 * (size_t)ctx->v32_threads + 2) * sizeof(int);
+           + (4 * (size_t)ctx->v32_threads + 2) * sizeof(int);
 }
 
 static int upload_model(smplgpu_ctx* ctx)
@@ -1005,7 +1006,11 @@ static int run_host_batched(smplgpu_ctx* ctx, const double* q0, const double* q1
     const int dof = ctx->h_model->dof;
     const bool by_prim = prim_id != nullptr;
     const bool edges = q1 != nullptr || by_prim;
-    const int chunk = 1 << 17;
+    static const int chunk = [] {
+        const char* e = getenv("SMPLGPU_HOST_CHUNK");   // items per pipeline stage (tuning knob)
+        const int v = e ? atoi(e) : 0;
+        return v >= 1024 ? v : (1 << 16);
+    }();
     const int cn = std::min(n, chunk);
     int r = ensure_state_buffers(ctx, (size_t)cn * 2, dof, edges); // two chunks in flight
     if (r) return r;

@@ -447,7 +447,7 @@ __device__ __forceinline__ void append_uncertain(bool push, int item, int* __res
 }
 
 // dynamic shared memory: blob | slots (n_slots * 12 * blockDim floats) | root centres (n_ptrees * 3 * blockDim floats)
-//                        | edges: (blockDim + 1) offsets, blockDim ok, blockDim unc
+//                        | edges: (blockDim + 1) offsets, blockDim ok, blockDim unc, blockDim counts
 __global__ void __launch_bounds__(V32_THREADS)
 states_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const DevModel* __restrict__ M,
                       const uint16_t* __restrict__ df, Grid32 G, const double* __restrict__ q, int n,
@@ -520,9 +520,21 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
     int* s_off = reinterpret_cast<int*>(slots + ((size_t)S.h->n_slots * 12 + (size_t)S.h->n_ptrees * 3) * blockDim.x);
     int* s_ok = s_off + blockDim.x + 1;
     int* s_unc = s_ok + blockDim.x;
-    s_off[tid + 1] = count;
-    s_ok[tid] = 1;
-    s_unc[tid] = 0;
+    // Round A: every thread checks the first waypoint of its own edge (alpha = 0 is exactly q0), the one the
+    // reference checks first too (collision_space.cpp:561-577), so an edge that starts in collision costs one
+    // state check, not `count`.
+    int ok = 1, unc = 0;
+    if (count > 0) {
+        ++cnt.waypoints;
+        const int r = check_state32(S, M->var_type, df, G, q0 + (size_t)i * dof, q1 + (size_t)i * dof, 0.0, slots, cnt);
+        ok = r != 0;
+        unc = r == 2;
+    }
+    // Round B: the remaining waypoints of the surviving edges, flattened over the block
+    const int rest = ok ? max(count - 1, 0) : 0;
+    s_off[tid + 1] = rest;
+    s_ok[tid] = ok;
+    s_unc[tid] = unc;
     if (tid == 0) {
         s_off[0] = 0;
     }
@@ -537,6 +549,9 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
         __syncthreads();
     }
     const int total = s_off[blockDim.x];
+    int* s_cnt = s_unc + blockDim.x;     // waypoint count per edge of the block
+    s_cnt[tid] = count;
+    __syncthreads();
 
     for (int item = tid; item < total; item += blockDim.x) {
         int lo = 0, hi = blockDim.x;
@@ -552,9 +567,8 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
         if (s_ok[e] == 0) {
             continue;
         }
-        const int w = item - s_off[e];
-        const int cnt_e = s_off[e + 1] - s_off[e];
-        const double inv = 1.0 / (double)(cnt_e - 1);
+        const int w = item - s_off[e] + 1;               // waypoint 0 was round A
+        const double inv = 1.0 / (double)(s_cnt[e] - 1); // m_waypoint_count_inv
         const double alpha = (double)w * inv;
         ++cnt.waypoints;
         const int r = check_state32(S, M->var_type, df, G, q0 + (size_t)(first + e) * dof, q1 + (size_t)(first + e) * dof,
