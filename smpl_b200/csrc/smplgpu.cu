@@ -1009,7 +1009,7 @@ static int run_host_batched(smplgpu_ctx* ctx, const double* q0, const double* q1
     static const int chunk = [] {
         const char* e = getenv("SMPLGPU_HOST_CHUNK");   // items per pipeline stage (tuning knob)
         const int v = e ? atoi(e) : 0;
-        return v >= 1024 ? v : (1 << 16);
+        return v >= 1024 ? v : (1 << 18);
     }();
     const int cn = std::min(n, chunk);
     int r = ensure_state_buffers(ctx, (size_t)cn * 2, dof, edges); // two chunks in flight
