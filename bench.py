@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--plan-concurrent", type=int, default=512)
     ap.add_argument("--plan-max-expansions", type=int, default=2000)
     ap.add_argument("--plan-cpu-queries", type=int, default=12)
+    ap.add_argument("--plan-threads", type=int, default=8, help="planner threads (= contexts) per GPU, capped by the host cores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "smpl_b200" else args.warmup
 
@@ -376,12 +377,17 @@ def main():
         nq_total = args.plan_queries * world
         starts_all, goals_all = scenes.tabletop_queries(nq_total, seed=13)
         mine = sharding.round_robin_shard(nq_total, rank, world)   # no collective
-        n_thr = max(1, min(8, (os.cpu_count() or 1) // max(1, world) // 2))   # spinning fork-join workers: leave cores for CUDA
-        api.plan_batch(pctx, pscene, ptables, pparams, starts_all[mine][:8], goals_all[mine][:8], max_concurrent=8)  # warm-up
+        # one planner thread per context (the reference's threading model), all on this rank's GPU
+        n_thr = max(1, min(args.plan_threads, (os.cpu_count() or 1) // max(1, world) - 2))
+        pctxs = [pctx] + [api.clone_context(pctx, pscene, ptables, device=local_rank) for _ in range(n_thr - 1)]
+        per_ctx = max(1, (args.plan_concurrent + n_thr - 1) // n_thr)
+        api.plan_batch(pctxs, pscene, ptables, pparams, starts_all[mine][:4 * n_thr], goals_all[mine][:4 * n_thr],
+                       max_concurrent=4)  # warm-up
         barrier()
         t0 = time.perf_counter()
-        pres, pstats = api.plan_batch(pctx, pscene, ptables, pparams, starts_all[mine], goals_all[mine],
-                                      max_concurrent=args.plan_concurrent, n_threads=n_thr)
+        pres, pstats = api.plan_batch(pctxs, pscene, ptables, pparams, starts_all[mine], goals_all[mine],
+                                      max_concurrent=per_ctx)
+        pstats["planner_threads"] = n_thr
         dt = time.perf_counter() - t0
         t_plan = torch.tensor([dt], device=dev, dtype=torch.float64)
         n_exp = torch.tensor([float(sum(r["expansions"] for r in pres)), float(sum(r["success"] for r in pres))],
@@ -394,7 +400,8 @@ def main():
                 "seconds": float(t_plan.item()), "queries_per_s": nq_total / float(t_plan.item()),
                 "expansions_per_s": float(n_exp[0].item()) / float(t_plan.item()), "concurrent_per_gpu": args.plan_concurrent,
                 "rank0": pstats}
-        pctx.close()
+        for c in pctxs:
+            c.close()
 
     if world > 1:
         dist.barrier()

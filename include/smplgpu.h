@@ -158,6 +158,9 @@ smplgpu_ctx* smplgpu_create(int device);              /* NULL when no device; se
 void         smplgpu_destroy(smplgpu_ctx* ctx);
 const char*  smplgpu_last_error(const smplgpu_ctx* ctx);
 int          smplgpu_device(const smplgpu_ctx* ctx);
+/* make the context's device current for the calling host thread (a new thread starts on device 0); call once
+ * from every thread that will use the context.  One context per planner thread, as in the reference. */
+int          smplgpu_bind_thread(smplgpu_ctx* ctx);
 /* run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the context's own stream */
 int          smplgpu_set_stream(smplgpu_ctx* ctx, void* cuda_stream);
 int          smplgpu_synchronize(smplgpu_ctx* ctx);

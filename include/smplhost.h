@@ -85,6 +85,15 @@ int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* params, co
                         const double* goals, int nq, int max_concurrent, int32_t* summary, int32_t* path_ids,
                         int max_path, double* stats);
 
+/* The same with one planner thread per context (the reference's threading model: one CollisionSpace per planner
+ * thread): queries are dealt round-robin to n_ctx contexts on the same GPU, each driven by its own host thread
+ * with its own stream, BFS bank and lock-step pipeline, so the host-side lattice / OPEN-list work runs in
+ * parallel without a barrier per round.  Every context must hold the same robot and distance field.
+ * stats: sums over the contexts, except the seconds entries (maximum). */
+int smplhost_plan_batch_multi(smplgpu_ctx* const* ctxs, int n_ctx, const smplhost_plan_params* params,
+                              const double* starts, const double* goals, int nq, int max_concurrent_per_ctx,
+                              int32_t* summary, int32_t* path_ids, int max_path, double* stats);
+
 /* ---- drop-in adapters (smpl_b200/host/gpu_adapters.h): the reference's CollisionChecker / RobotModel /
  * RobotHeuristic virtuals implemented over the C ABI.  These shims drive the C++ objects one virtual call at
  * a time, the way the reference's planner does (n = 1 per call); a C++ caller uses the classes directly. ---- */

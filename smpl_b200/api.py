@@ -62,6 +62,7 @@ def gpu_lib():
         L.smplgpu_launch_count.argtypes = [C.c_void_p]
         L.smplgpu_destroy.argtypes = [C.c_void_p]
         L.smplgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.smplgpu_bind_thread.argtypes = [C.c_void_p]
         L.smplgpu_synchronize.argtypes = [C.c_void_p]
         vp, dp, ip, bp, i, d = C.c_void_p, c_double_p, c_int32_p, c_uint8_p, C.c_int, C.c_double
         L.smplgpu_set_distance_field.argtypes = [vp, c_uint16_p, i, i, i, dp, d, i, d]
@@ -130,6 +131,8 @@ def host_lib():
         H.smplhost_tables_pairs.argtypes = [vp, c_int32_p, C.c_int]
         H.smplhost_plan_batch.argtypes = [vp, C.POINTER(PlanParamsC), c_double_p, c_double_p, C.c_int, C.c_int,
                                           c_int32_p, c_int32_p, C.c_int, c_double_p]
+        H.smplhost_plan_batch_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(PlanParamsC), c_double_p, c_double_p,
+                                                C.c_int, C.c_int, c_int32_p, c_int32_p, C.c_int, c_double_p]
         H.smplhost_adapters_create.restype = C.c_void_p
         H.smplhost_adapters_create.argtypes = [vp, vp, C.c_char_p, c_double_p, C.c_double, c_int32_p, C.c_double, C.c_int]
         H.smplhost_adapters_destroy.argtypes = [vp]
@@ -538,9 +541,22 @@ class Adapters:
         return self.H.smplhost_heur_metric_goal_distance(self.h, float(x), float(y), float(z))
 
 
+def clone_context(ctx, scene, tables, device=0):
+    """Another context on the same GPU with the same robot tables and a device-to-device copy of the distance field
+    (one context per planner thread)."""
+    c = GpuContext(device)
+    c.set_robot(tables)
+    ptr, _ = ctx.distance_field_dev_ptr()
+    dmax = int(np.ceil(scene.max_dist * (1.0 / scene.res)))
+    c.set_distance_field_dev(ptr, scene.dims, scene.origin, scene.res, dmax * dmax, scene.padding)
+    return c
+
+
 def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max_path=512, n_threads=1):
     """smplhost_plan_batch: many ARA* queries in lock step, one device call per round.
-    params: smpl_b200.scenes.PlanParams.  Returns (list of dict per query, stats dict)."""
+    params: smpl_b200.scenes.PlanParams.  Returns (list of dict per query, stats dict).
+    `ctx` may be a list of contexts (same GPU, same scene): one planner thread per context
+    (smplhost_plan_batch_multi), max_concurrent is then per context."""
     H = host_lib()
     dof = tables.dof
     starts = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, dof)
@@ -566,8 +582,13 @@ def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max
     summary = np.zeros((nq, 5), np.int32)
     paths = np.full((nq, max_path), -1, np.int32)
     stats = np.zeros(8)
-    r = H.smplhost_plan_batch(ctx.h, C.byref(P), _dp(starts), _dp(goals), nq, int(max_concurrent), _ip(summary),
-                              _ip(paths), int(max_path), _dp(stats))
+    if isinstance(ctx, (list, tuple)):
+        arr = (C.c_void_p * len(ctx))(*[c.h for c in ctx])
+        r = H.smplhost_plan_batch_multi(arr, len(ctx), C.byref(P), _dp(starts), _dp(goals), nq, int(max_concurrent),
+                                        _ip(summary), _ip(paths), int(max_path), _dp(stats))
+    else:
+        r = H.smplhost_plan_batch(ctx.h, C.byref(P), _dp(starts), _dp(goals), nq, int(max_concurrent), _ip(summary),
+                                  _ip(paths), int(max_path), _dp(stats))
     if r != 0:
         raise SmplGpuError("plan_batch: " + H.smplhost_last_error().decode())
     out = []

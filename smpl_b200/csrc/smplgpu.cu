@@ -269,6 +269,13 @@ const char* smplgpu_last_error(const smplgpu_ctx* ctx)
 
 int smplgpu_device(const smplgpu_ctx* ctx) { return ctx ? ctx->device : -1; }
 
+int smplgpu_bind_thread(smplgpu_ctx* ctx)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    return 0;
+}
+
 int smplgpu_set_stream(smplgpu_ctx* ctx, void* cuda_stream)
 {
     if (!ctx) return SMPLGPU_ERR_INVALID;

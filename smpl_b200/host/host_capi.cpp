@@ -6,6 +6,7 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/smplgpu.h"
@@ -262,6 +263,78 @@ int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* p, const d
         stats[4] = s.host_seconds;
         stats[5] = total;
         stats[6] = s.bfs_runs;
+    }
+    return 0;
+}
+
+int smplhost_plan_batch_multi(smplgpu_ctx* const* ctxs, int n_ctx, const smplhost_plan_params* p,
+                              const double* starts, const double* goals, int nq, int max_concurrent_per_ctx,
+                              int32_t* summary, int32_t* path_ids, int max_path, double* stats)
+{
+    if (!ctxs || n_ctx <= 0 || !p || nq < 0) {
+        g_err = "smplhost_plan_batch_multi: bad argument";
+        return SMPLGPU_ERR_INVALID;
+    }
+    if (n_ctx == 1) {
+        return smplhost_plan_batch(ctxs[0], p, starts, goals, nq, max_concurrent_per_ctx, summary, path_ids, max_path, stats);
+    }
+    const int dof = p->dof;
+    std::vector<int> rc(n_ctx, 0);
+    std::vector<std::string> errs(n_ctx);
+    std::vector<std::vector<double>> st(n_ctx, std::vector<double>(8, 0.0));
+    std::vector<std::thread> threads;
+    for (int t = 0; t < n_ctx; ++t) {
+        threads.emplace_back([&, t]() {
+            // this thread's share: queries t, t + n_ctx, ...
+            std::vector<int> mine;
+            for (int i = t; i < nq; i += n_ctx) mine.push_back(i);
+            const int m = (int)mine.size();
+            if (m == 0) {
+                return;
+            }
+            if (smplgpu_bind_thread(ctxs[t]) != 0) {
+                rc[t] = SMPLGPU_ERR_CUDA;
+                errs[t] = smplgpu_last_error(ctxs[t]);
+                return;
+            }
+            std::vector<double> s((size_t)m * dof), g((size_t)m * 3);
+            for (int k = 0; k < m; ++k) {
+                std::copy(starts + (size_t)mine[k] * dof, starts + (size_t)(mine[k] + 1) * dof, s.begin() + (size_t)k * dof);
+                std::copy(goals + (size_t)mine[k] * 3, goals + (size_t)(mine[k] + 1) * 3, g.begin() + (size_t)k * 3);
+            }
+            std::vector<int32_t> sum((size_t)m * 5), paths(path_ids ? (size_t)m * max_path : 0);
+            smplhost_plan_params pt = *p;
+            pt.n_threads = 1;
+            rc[t] = smplhost_plan_batch(ctxs[t], &pt, s.data(), g.data(), m, max_concurrent_per_ctx, sum.data(),
+                                        path_ids ? paths.data() : nullptr, max_path, st[t].data());
+            if (rc[t] != 0) {
+                errs[t] = g_err;   // thread-local: copy it out
+                return;
+            }
+            for (int k = 0; k < m; ++k) {
+                std::copy(sum.begin() + (size_t)k * 5, sum.begin() + (size_t)(k + 1) * 5, summary + (size_t)mine[k] * 5);
+                if (path_ids) {
+                    std::copy(paths.begin() + (size_t)k * max_path, paths.begin() + (size_t)(k + 1) * max_path,
+                              path_ids + (size_t)mine[k] * max_path);
+                }
+            }
+        });
+    }
+    for (std::thread& th : threads) {
+        th.join();
+    }
+    for (int t = 0; t < n_ctx; ++t) {
+        if (rc[t] != 0) {
+            g_err = errs[t];
+            return rc[t];
+        }
+    }
+    if (stats) {
+        for (int k = 0; k < 7; ++k) stats[k] = 0.0;
+        for (int t = 0; t < n_ctx; ++t) {
+            for (int k : { 0, 1, 2, 6 }) stats[k] += st[t][k];
+            for (int k : { 3, 4, 5 }) stats[k] = std::max(stats[k], st[t][k]);
+        }
     }
     return 0;
 }

@@ -120,6 +120,23 @@ def test_batch_planner_matches_sequential_oracle(tabletop):
         len(ref), n_ok, stats["rounds"], stats["edges_submitted"], stats["device_seconds"], stats["host_seconds"]))
 
 
+def test_one_planner_thread_per_context_gives_the_same_plans(tabletop):
+    scene, o, ctx, tables = tabletop
+    params = scenes.PlanParams(scene.dof)
+    params.max_expansions = 800
+    starts, goals = scenes.tabletop_queries(30, seed=17)
+    single, _ = api.plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=8)
+    ctxs = [ctx] + [api.clone_context(ctx, scene, tables) for _ in range(2)]
+    multi, stats = api.plan_batch(ctxs, scene, tables, params, starts, goals, max_concurrent=4)
+    for a, b in zip(single, multi):
+        assert (a["success"], a["expansions"], a["cost"], a["num_states"]) == \
+               (b["success"], b["expansions"], b["cost"], b["num_states"])
+        assert np.array_equal(a["path_ids"], b["path_ids"])
+    assert stats["edges_submitted"] > 0
+    for c in ctxs[1:]:
+        c.close()
+
+
 def test_ubr1_with_attached_object_queries_match_oracle():
     """Config 4 shape: UBR1 arm, attached box, extra ACM entries; queries dealt round-robin as on 2 GPUs."""
     from smpl_b200 import sharding
