@@ -50,6 +50,11 @@ extern "C" {
 /* How the validity kernels compute (smplgpu_set_precision_mode).  Verdicts are identical in both modes:
  * CERTIFIED_F32 decides in single precision only what is provably unaffected by the single-precision
  * error and resolves the rest with the double-precision kernels; EXACT_F64 uses those alone. */
+/* Which wavefront kernel runs BFS_3D (smplgpu_bfs_set_mode); distances are identical. */
+#define SMPLGPU_BFS_TILES  0   /* 8 levels per grid barrier on shared-memory tiles (bfs_tiles.cuh): latency-bound grids */
+#define SMPLGPU_BFS_LEVELS 1   /* one level per grid barrier, sparse (row, word) items (bfs.cuh): throughput-bound grids */
+#define SMPLGPU_BFS_AUTO   2   /* default: tiles for one grid of up to 8 M padded cells, levels otherwise */
+
 #define SMPLGPU_PRECISION_CERTIFIED_F32 0   /* default */
 #define SMPLGPU_PRECISION_EXACT_F64     1
 
@@ -240,6 +245,8 @@ int smplgpu_planning_frame_fk(smplgpu_ctx* ctx, const double* q, int n, double* 
  * parents and one int per edge cross the bus. */
 int smplgpu_is_mprim_edges_valid(smplgpu_ctx* ctx, const double* q0, const int32_t* prim_id, int n,
                                  const double* deltas, int n_prims, uint8_t* verdict, int32_t* waypoint_counts);
+
+int smplgpu_bfs_set_mode(smplgpu_ctx* ctx, int mode);
 
 /* ---- precision control / certification (no counterpart in the reference) ---- */
 int smplgpu_set_precision_mode(smplgpu_ctx* ctx, int mode);

@@ -90,6 +90,7 @@ def gpu_lib():
         L.smplgpu_planning_frame_fk.argtypes = [vp, dp, i, dp]
         L.smplgpu_is_mprim_edges_valid.argtypes = [vp, dp, ip, i, dp, i, bp, ip]
         L.smplgpu_set_precision_mode.argtypes = [vp, i]
+        L.smplgpu_bfs_set_mode.argtypes = [vp, i]
         L.smplgpu_certified_bounds.argtypes = [vp, dp, dp]
         L.smplgpu_last_f64_resolved.argtypes = [vp, C.POINTER(C.c_int64)]
         L.smplgpu_fk_sphere_centers_f32.argtypes = [vp, dp, i, C.POINTER(C.c_float)]
@@ -396,6 +397,11 @@ class GpuContext:
         return dict(df_lookups=a.value, pair_tests=b.value, waypoints=c.value)
 
     # ---- BFS / heuristic ----
+    BFS_TILES, BFS_LEVELS, BFS_AUTO = 0, 1, 2
+
+    def bfs_set_mode(self, mode):
+        self._ck(self.L.smplgpu_bfs_set_mode(self.h, int(mode)), "bfs_set_mode")
+
     def bfs_set_walls_from_df(self, inflation_radius):
         return self._ck(self.L.smplgpu_bfs_set_walls_from_df(self.h, float(inflation_radius)), "bfs_set_walls_from_df")
 

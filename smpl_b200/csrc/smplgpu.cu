@@ -13,6 +13,7 @@
 
 #include "../../include/smplgpu.h"
 #include "bfs.cuh"
+#include "bfs_tiles.cuh"
 #include "edt.cuh"
 #include "heuristic.cuh"
 #include "model.cuh"
@@ -67,6 +68,8 @@ struct smplgpu_ctx
     BfsGrid bfs{};
     size_t bfs_words = 0, bfs_cells = 0;
     int bfs_levels = 0;
+    BfsTiles bfs_tiles{}, bank_tiles{};
+    int bfs_mode = SMPLGPU_BFS_AUTO;
     int* d_seed_count = nullptr;
 
     // bank of stacked BFS grids (one per concurrent planning query)
@@ -219,6 +222,28 @@ smplgpu_ctx* smplgpu_create(int device)
     return ctx;
 }
 
+static void free_tiles(BfsTiles& t)
+{
+    cudaFree(t.blocked1); cudaFree(t.ver);
+    memset(&t, 0, sizeof(t));
+}
+
+static int alloc_tiles(smplgpu_ctx* ctx, const BfsGrid& g, BfsTiles& t, size_t words)
+{
+    free_tiles(t);
+    t.ntx = (g.DX + 31) / 32;
+    t.nty = (g.DY + TILE_Y - 1) / TILE_Y;
+    t.ntz = (g.DZ + TILE_Y - 1) / TILE_Y;
+    t.ntiles = t.ntx * t.nty * t.ntz;
+    CU(cudaMalloc(&t.blocked1, words * sizeof(uint32_t)));
+    // ver[ntiles] | flag[3][ntiles] | queue[3][ntiles] | qn[3] (+ pad), all 32-bit
+    CU(cudaMalloc(&t.ver, ((size_t)7 * t.ntiles + 4) * sizeof(uint32_t)));
+    t.flag = t.ver + t.ntiles;
+    t.queue = reinterpret_cast<int*>(t.flag + (size_t)3 * t.ntiles);
+    t.qn = t.queue + (size_t)3 * t.ntiles;
+    return 0;
+}
+
 static void free_grid(BfsGrid& g)
 {
     cudaFree(g.wall); cudaFree(g.blocked); cudaFree(g.front0); cudaFree(g.front1);
@@ -230,6 +255,7 @@ static void free_grid(BfsGrid& g)
 static void free_bfs(smplgpu_ctx* ctx)
 {
     free_grid(ctx->bfs);
+    free_tiles(ctx->bfs_tiles);
     ctx->has_bfs = false;
 }
 
@@ -242,6 +268,7 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     free_bfs(ctx);
     free_grid(ctx->bank);
+    free_tiles(ctx->bank_tiles);
     cudaFree(ctx->d_model); cudaFree(ctx->d_stats); cudaFree(ctx->d_seed_count); cudaFree(ctx->d_df);
     cudaFree(ctx->d_blob); cudaFree(ctx->d_unc_list); cudaFree(ctx->d_unc_count);
     cudaFree(ctx->d_prim); cudaFree(ctx->d_deltas);
@@ -1300,6 +1327,8 @@ static int alloc_bfs(smplgpu_ctx* ctx, int nx, int ny, int nz)
     ctx->has_bfs = false;
     int r = alloc_grid(ctx, ctx->bfs, nx, ny, nz, &ctx->bfs_words, &ctx->bfs_cells);
     if (r) return r;
+    r = alloc_tiles(ctx, ctx->bfs, ctx->bfs_tiles, ctx->bfs_words);
+    if (r) return r;
     ctx->has_bfs = true;
     return 0;
 }
@@ -1323,12 +1352,22 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
                     const uint8_t* d_slot_mask = nullptr, int slot_dz = 1)
 {
     const int total = (int)words;
+    BfsTiles& t = (&g == &ctx->bank) ? ctx->bank_tiles : ctx->bfs_tiles;
+    // AUTO: the tile kernel wins where the per-level latency dominates (one small grid), the level kernel where
+    // throughput does (large grids, stacked banks); see bfs_tiles.cuh
+    const bool small_single = (&g != &ctx->bank) && (long long)g.DX * g.DY * g.DZ <= 8LL * 1000 * 1000;
+    const bool tiles = ctx->bfs_mode == SMPLGPU_BFS_TILES || (ctx->bfs_mode == SMPLGPU_BFS_AUTO && small_single);
     {
         // one warp per 32 bitmap words; at least one thread per row for the candidate stamps
         const long long threads = std::max<long long>(g.rows, std::min<long long>((long long)total, 148LL * 2048 * 4));
         bfs_reset_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(g, d_slot_mask, slot_dz);
     }
     ++ctx->launches;
+    if (tiles) {
+        bfs_tiles_reset_kernel<<<std::min((total + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(g, t, d_slot_mask, slot_dz);
+        ++ctx->launches;
+        CU(cudaMemsetAsync(t.ver, 0, ((size_t)7 * t.ntiles + 4) * sizeof(uint32_t), ctx->stream));
+    }
     if (n_seeds <= 0) {
         CU(cudaGetLastError());
         return 0;
@@ -1336,21 +1375,43 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
     CU(cudaMemsetAsync(ctx->d_seed_count, 0, sizeof(int), ctx->stream));
     bfs_seed_kernel<<<(n_seeds + 127) / 128, 128, 0, ctx->stream>>>(g, d_seeds, n_seeds, ctx->d_seed_count);
     ++ctx->launches;
-    // persistent cooperative kernel, one block per SM (the grid barrier costs one arrival per block)
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_levels_kernel, BFS_THREADS, 0));
-    if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS kernel does not fit an SM");
-    const int groups = (g.rows + 7) / 8;
-    const int blocks = std::max(1, std::min(ctx->sm_count, groups));
     long long cap = (long long)g.nx * g.ny * g.nz;
-    int max_levels = (int)std::min<long long>(cap, (1LL << 22)); // level << 9 must fit the candidate word
-    max_levels = (int)std::min<long long>(max_levels, 0x7FFFFFFFLL / blocks - 1);   // barrier target level * blocks
-    void* args[] = { (void*)&g, (void*)&max_levels };
-    CU(cudaLaunchCooperativeKernel((void*)bfs_levels_kernel, dim3(blocks), dim3(BFS_THREADS), args, 0, ctx->stream));
-    ++ctx->launches;
+    if (tiles) {
+        bfs_tiles_seed_kernel<<<(n_seeds + 127) / 128, 128, 0, ctx->stream>>>(g, t, d_seeds, n_seeds);
+        ++ctx->launches;
+        // persistent cooperative kernel: TILE_K levels per grid barrier, one 1024-thread block per SM
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_tiles_kernel, TILE_THREADS, 0));
+        if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS tile kernel does not fit an SM");
+        const int blocks = std::max(1, std::min(ctx->sm_count * per_sm, t.ntiles));
+        int max_steps = (int)std::min<long long>(cap / TILE_K + 2, 0x7FFFFFFFLL / blocks - 1);
+        void* args[] = { (void*)&g, (void*)&t, (void*)&max_steps };
+        CU(cudaLaunchCooperativeKernel((void*)bfs_tiles_kernel, dim3(blocks), dim3(TILE_THREADS), args, 0, ctx->stream));
+        ++ctx->launches;
+    } else {
+        // persistent cooperative kernel, one block per SM (the grid barrier costs one arrival per block)
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_levels_kernel, BFS_THREADS, 0));
+        if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS kernel does not fit an SM");
+        const int groups = (g.rows + 7) / 8;
+        const int blocks = std::max(1, std::min(ctx->sm_count, groups));
+        int max_levels = (int)std::min<long long>(cap, (1LL << 22));
+        max_levels = (int)std::min<long long>(max_levels, 0x7FFFFFFFLL / blocks - 1);   // barrier target level * blocks
+        void* args[] = { (void*)&g, (void*)&max_levels };
+        CU(cudaLaunchCooperativeKernel((void*)bfs_levels_kernel, dim3(blocks), dim3(BFS_THREADS), args, 0, ctx->stream));
+        ++ctx->launches;
+    }
     if (levels_out) {
         CU(cudaMemcpyAsync(levels_out, g.ctrl, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
+    return 0;
+}
+
+int smplgpu_bfs_set_mode(smplgpu_ctx* ctx, int mode)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    if (mode != SMPLGPU_BFS_TILES && mode != SMPLGPU_BFS_LEVELS && mode != SMPLGPU_BFS_AUTO) return fail(ctx, SMPLGPU_ERR_INVALID, "unknown BFS mode %d", mode);
+    ctx->bfs_mode = mode;
     return 0;
 }
 
@@ -1421,6 +1482,13 @@ int smplgpu_bfs_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz, int n_seeds)
     int r = run_grid(ctx, g, ctx->bfs_words, (const int*)ctx->d_misc, n_in, &ctx->bfs_levels);
     if (r) return r;
     CU(cudaStreamSynchronize(ctx->stream));
+#ifdef SMPLGPU_BFS_STATS
+    {
+        int c[8];
+        cudaMemcpy(c, g.ctrl, sizeof(c), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[bfs stats] queued tile-steps %d, with frontier %d, sub-levels run %d\n", c[3], c[6], c[7]);
+    }
+#endif
     return n_in;
 }
 
@@ -1536,6 +1604,8 @@ int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radi
         return fail(ctx, SMPLGPU_ERR_LIMIT, "%d slots of %dx%dx%d exceed int node indices", n_slots, nx, ny, nz);
     ctx->has_bank = false;
     int r = alloc_grid(ctx, ctx->bank, nx, ny, (int)total_nz, &ctx->bank_words, &ctx->bank_cells);
+    if (r) return r;
+    r = alloc_tiles(ctx, ctx->bank, ctx->bank_tiles, ctx->bank_words);
     if (r) return r;
     ctx->bank_slots = n_slots;
     ctx->bank_slot_dz = nz + 2;

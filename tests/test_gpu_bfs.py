@@ -148,3 +148,37 @@ def test_full_size_400_cubed_properties(ctx):
     assert np.array_equal(got, want)
     print("400^3: %d levels, %.1f%% walls, %.1f%% discovered" % (
         ctx.bfs_last_levels(), 100.0 * (walls != 0).mean(), 100.0 * disc.mean()))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_both_kernels_on_odd_shapes_and_quirks(ctx, mode):
+    """Non-multiple-of-16 dims, a seed on a wall, a seed next to the border, multi-seed: both kernels."""
+    ctx.bfs_set_mode(mode)
+    rng = np.random.default_rng(77)
+    for dims in ((37, 21, 50), (5, 70, 9), (33, 33, 33)):
+        nx, ny, nz = dims
+        walls = (rng.random((nz, ny, nx)) < 0.35).astype(np.uint8)
+        seeds = [(0, 0, 0), (nx - 1, ny - 1, nz - 1), (nx // 2, ny // 2, nz // 2)]
+        walls[nz // 2, ny // 2, nx // 2] = 1                      # seeding a wall cell un-walls it
+        ctx.bfs_set_walls(walls)
+        ctx.bfs_run(seeds)
+        # (the reference's multi-seed iterator drops the last triple, bfs3d.h:157-211: feed it a sentinel)
+        assert np.array_equal(ctx.bfs_download(), oracle_grid(walls, seeds + [(0, 0, 0)], multi=True)), (dims, mode)
+    ctx.bfs_set_mode(ctx.BFS_AUTO)
+
+
+def test_level_kernel_and_tile_kernel_agree(ctx):
+    """Both wavefront kernels (one level per grid barrier / eight levels per barrier on shared-memory tiles)
+    produce the reference's distances."""
+    walls = scenes.bfs_clutter_walls(96, seed=21)
+    seed = scenes.first_free_cell(walls, (48, 48, 48))
+    ob = OracleBfs(96, 96, 96)
+    ob.set_walls(walls)
+    ob.run(*seed)
+    want = ob.grid()
+    for mode in (ctx.BFS_LEVELS, ctx.BFS_TILES):
+        ctx.bfs_set_mode(mode)
+        ctx.bfs_set_walls(walls)
+        ctx.bfs_run([seed])
+        assert np.array_equal(ctx.bfs_download(), want), mode
+    ctx.bfs_set_mode(ctx.BFS_AUTO)
