@@ -48,7 +48,7 @@ struct BfsTiles
     uint32_t* ver;               // [ntiles] (super-step of the last flip + 1) << 1 | copy holding the tile's interior
     uint32_t* flag;              // [3][ntiles] tile is queued for super-step n (index n % 3)
     int* queue;                  // [3][ntiles] tiles to run in super-step n (index n % 3)
-    int* qn;                     // [3] queue lengths
+    int* qn;                     // [3] queue lengths, [3] pull cursors
 };
 
 // which blocked copy held `tile`'s interior at the START of super-step n (a tile that flips during n stamps n)
@@ -117,12 +117,18 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
     __shared__ uint8_t sAny[2][TILE_THREADS];        // row has frontier bits (per buffer)
     __shared__ uint8_t sZ[2][TILE_E];                // z-row (= warp) has frontier bits (per buffer)
     __shared__ unsigned int s_act;                   // which of the 27 neighbour directions get activated
+    __shared__ int s_next;                           // next queue position of this block
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int ry = tid & (TILE_E - 1), rz = tid >> 5;   // TILE_E == 32: a warp is one z-row of the extended tile
     const bool rim = ry == 0 || ry == TILE_E - 1 || rz == 0 || rz == TILE_E - 1;
     const bool interior_row = ry >= TILE_K && ry < TILE_K + TILE_Y && rz >= TILE_K && rz < TILE_K + TILE_Y;
+    // rows away from the interior (0 inside); a halo row j rows out can reach the interior by level TILE_K only
+    // through levels <= TILE_K - j, so level s needs just the rows with j <= TILE_K - s
+    const int jy = ry < TILE_K ? TILE_K - ry : (ry >= TILE_K + TILE_Y ? ry - (TILE_K + TILE_Y - 1) : 0);
+    const int jz = rz < TILE_K ? TILE_K - rz : (rz >= TILE_K + TILE_Y ? rz - (TILE_K + TILE_Y - 1) : 0);
+    const int row_out = max(jy, jz);
     const int xwords = (g.DX + 31) / 32;                // words that hold cells
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(&g.ctrl[4]);
     int max_level = 0;
@@ -145,12 +151,21 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
         if (blockIdx.x == 0 && tid == 0) {
             t.qn[qi_free] = 0;   // its readers ran before the last barrier, its writers start after the next one
         }
+        if (blockIdx.x == 0 && tid == 0) {
+            t.qn[3 + qi_free] = 0;   // pull cursor of that queue
+        }
         {
-            for (int a = blockIdx.x; a < q_len; a += gridDim.x) {
+            // the first tile by block id, the following ones pulled from a shared cursor as blocks become free
+            // (tiles differ a lot in cost: a face across x keeps all 1024 rows busy, most others a few)
+            for (int a = blockIdx.x; a < q_len;) {
                 const int tile = __ldcg(&t.queue[(size_t)qi * t.ntiles + a]);
                 if (tid == 0) {
                     t.flag[(size_t)qi * t.ntiles + tile] = 0;   // consumed
+                    s_next = (int)gridDim.x + atomicAdd(&t.qn[3 + qi], 1);   // next queue position, fetched while this tile runs
                 }
+#ifdef SMPLGPU_BFS_STATS
+                const long long c0 = clock64();
+#endif
                 const int tx = tile % t.ntx, ty = (tile / t.ntx) % t.nty, tz = tile / (t.ntx * t.nty);
                 const int gy = ty * TILE_Y - TILE_K + ry, gz = tz * TILE_Y - TILE_K + rz;
                 const bool row_in = gy >= 0 && gy < g.DY && gz >= 0 && gz < g.DZ;
@@ -183,7 +198,8 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                     s_act = 0;
                 }
                 if (!__syncthreads_or(any ? 1 : 0)) {
-                    continue;   // (block-uniform) the barrier above also protects the shared buffers
+                    a = s_next;   // (block-uniform) the barrier above also protects the shared buffers
+                    continue;
                 }
 #ifdef SMPLGPU_BFS_STATS
                 if (tid == 0) atomicAdd(&g.ctrl[6], 1);
@@ -202,6 +218,10 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                     blk[w] = bb;
                 }
 
+#ifdef SMPLGPU_BFS_STATS
+                __syncthreads();
+                const long long c1 = clock64();
+#endif
                 // ---- TILE_K levels in shared memory ----
                 bool changed = false;      // this thread's interior word gained cells
                 uint32_t last = 0;         // interior frontier word after the last level run
@@ -210,9 +230,9 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                     uint32_t fresh[3] = { 0, 0, 0 };
                     bool got = false;
                     // a warp is one z-row of the tile: nothing to do unless this or an adjacent z-row has frontier
-                    const bool zact = rz > 0 && rz < TILE_E - 1 && (sZ[cur][rz - 1] | sZ[cur][rz] | sZ[cur][rz + 1]);
+                    const bool zact = jz <= TILE_K - s && (sZ[cur][rz - 1] | sZ[cur][rz] | sZ[cur][rz + 1]);
                     const bool zstale = sZ[cur ^ 1][rz] != 0;   // the buffer written now held cells two levels ago
-                    if (zact && !rim) {
+                    if (zact && row_out <= TILE_K - s) {
                         // any frontier in the 3 x 3 rows around this one?
                         const uint8_t* A = sAny[cur];
                         const int near = A[tid - 33] | A[tid - 32] | A[tid - 31] | A[tid - 1] | A[tid] | A[tid + 1] |
@@ -261,18 +281,27 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
 #ifdef SMPLGPU_BFS_STATS
                     if (tid == 0) atomicAdd(&g.ctrl[7], 1);
 #endif
-                    // distances of the interior word, one warp per z-row: lanes = rows on the way in, bits on the way out
+                    // distances of the interior word: a row with a few new cells (a wavefront face across x) stores
+                    // them itself; dense rows (faces along x) go out warp-wide, lanes = bits, one 128-byte store per row
                     if (zgot && rz >= TILE_K && rz < TILE_K + TILE_Y) {
-                        const uint32_t rows_new = __ballot_sync(0xffffffffu, interior_row && fresh[1] != 0);
-                        uint32_t todo = rows_new;
+                        const bool mine = interior_row && fresh[1] != 0;
+                        const bool dense = mine && __popc(fresh[1]) > 4;
+                        if (mine && !dense) {
+                            int* d = g.dist + ((size_t)gz * g.DY + gy) * g.DX + (size_t)tx * 32;
+                            uint32_t f = fresh[1];
+                            while (f) {
+                                d[__ffs(f) - 1] = level0 + s;
+                                f &= f - 1;
+                            }
+                        }
+                        uint32_t todo = __ballot_sync(0xffffffffu, dense);
                         while (todo) {
                             const int r = __ffs(todo) - 1;
                             todo &= todo - 1;
                             const uint32_t wk = __shfl_sync(0xffffffffu, fresh[1], r);
                             const int y2 = ty * TILE_Y - TILE_K + r;
-                            const int x = tx * 32 + lane;
-                            if (((wk >> lane) & 1u) && x < g.DX) {
-                                g.dist[((size_t)gz * g.DY + y2) * g.DX + x] = level0 + s;
+                            if ((wk >> lane) & 1u) {
+                                g.dist[((size_t)gz * g.DY + y2) * g.DX + (size_t)tx * 32 + lane] = level0 + s;
                             }
                         }
                     }
@@ -282,6 +311,9 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                     }
                 }
 
+#ifdef SMPLGPU_BFS_STATS
+                const long long c2 = clock64();
+#endif
                 // ---- write back the interior: blocked into the other copy, frontier for the next super-step ----
                 if (__syncthreads_or(changed ? 1 : 0)) {
                     const uint32_t v = tile_copy(t, tile, n);
@@ -320,9 +352,24 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                     }
                 }
                 __syncthreads();   // shared buffers are reused by the next tile
+                a = s_next;
+#ifdef SMPLGPU_BFS_STATS
+                if (tid == 0) {
+                    const long long c3 = clock64();
+                    atomicAdd(reinterpret_cast<unsigned long long*>(t.qn + 8), (unsigned long long)(c1 - c0));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(t.qn + 10), (unsigned long long)(c2 - c1));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(t.qn + 12), (unsigned long long)(c3 - c2));
+                }
+#endif
             }
         }
+#ifdef SMPLGPU_BFS_STATS
+        const long long b0 = clock64();
+#endif
         grid_barrier(bar, (unsigned int)(n + 1) * gridDim.x, false);
+#ifdef SMPLGPU_BFS_STATS
+        if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(t.qn + 14), (unsigned long long)(clock64() - b0));
+#endif
     }
     // levels run = deepest level that discovered a cell, + 1 (as bfs_levels_kernel reports it)
     for (int o = 16; o > 0; o >>= 1) {

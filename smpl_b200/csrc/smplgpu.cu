@@ -237,7 +237,7 @@ static int alloc_tiles(smplgpu_ctx* ctx, const BfsGrid& g, BfsTiles& t, size_t w
     t.ntiles = t.ntx * t.nty * t.ntz;
     CU(cudaMalloc(&t.blocked1, words * sizeof(uint32_t)));
     // ver[ntiles] | flag[3][ntiles] | queue[3][ntiles] | qn[3] (+ pad), all 32-bit
-    CU(cudaMalloc(&t.ver, ((size_t)7 * t.ntiles + 4) * sizeof(uint32_t)));
+    CU(cudaMalloc(&t.ver, ((size_t)7 * t.ntiles + 16) * sizeof(uint32_t)));
     t.flag = t.ver + t.ntiles;
     t.queue = reinterpret_cast<int*>(t.flag + (size_t)3 * t.ntiles);
     t.qn = t.queue + (size_t)3 * t.ntiles;
@@ -1366,7 +1366,7 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
     if (tiles) {
         bfs_tiles_reset_kernel<<<std::min((total + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(g, t, d_slot_mask, slot_dz);
         ++ctx->launches;
-        CU(cudaMemsetAsync(t.ver, 0, ((size_t)7 * t.ntiles + 4) * sizeof(uint32_t), ctx->stream));
+        CU(cudaMemsetAsync(t.ver, 0, ((size_t)7 * t.ntiles + 16) * sizeof(uint32_t), ctx->stream));
     }
     if (n_seeds <= 0) {
         CU(cudaGetLastError());
@@ -1487,6 +1487,12 @@ int smplgpu_bfs_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz, int n_seeds)
         int c[8];
         cudaMemcpy(c, g.ctrl, sizeof(c), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[bfs stats] queued tile-steps %d, with frontier %d, sub-levels run %d\n", c[3], c[6], c[7]);
+        if (ctx->bfs_tiles.qn) {
+            unsigned long long tt[4];
+            cudaMemcpy(tt, ctx->bfs_tiles.qn + 8, sizeof(tt), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[bfs stats] block-cycles: load %.1f M, levels %.1f M, write-back %.1f M, grid barrier %.1f M\n",
+                    tt[0] * 1e-6, tt[1] * 1e-6, tt[2] * 1e-6, tt[3] * 1e-6);
+        }
     }
 #endif
     return n_in;
