@@ -23,13 +23,11 @@
 // by then, so whatever they contribute is removed by `& ~blocked` (same argument as in bfs.cuh).
 // One grid barrier per super-step; the search ends when a queue comes up empty.
 //
-// Measured on B200 (tools/bfs_only.py, tools/bank_bfs_time.py): single grids up to ~200^3 run 1.5-2x faster
-// than with bfs_levels_kernel (150^3: 0.50 vs 0.99 ms), because they are bound by the per-level latency; a
-// 400^3 grid (4.8 vs 4.3 ms) and the stacked planner banks (0.21 vs 0.15 ms per query) are throughput bound
-// and the tile kernel's halo recomputation and row-strided tile loads cost more than the barriers it saves.
-// smplgpu.cu picks the kernel by grid size unless smplgpu_bfs_set_mode forces one.
-//
-// Reference semantics: smpl/src/bfs3d.cpp:156-201 (run), :501-547 (search); see bfs.cuh.
+// Measured on B200 (tools/bfs_only.py, tools/bank_bfs_time.py): single grids run faster than with
+// bfs_levels_kernel (64^3: 0.19 vs 0.35 ms, 150^3: 0.44 vs 0.99 ms, 400^3: 3.7 vs 4.3 ms) because they are
+// bound by the per-level latency; the stacked planner banks (many wavefronts at once: 0.18 vs 0.15 ms per
+// query) are throughput bound and the tile kernel's halo recomputation costs more than the barriers it saves.
+// smplgpu.cu picks the kernel accordingly unless smplgpu_bfs_set_mode forces one.
 #pragma once
 
 #include "bfs.cuh"
@@ -114,7 +112,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1)
 bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsTiles t, int max_supersteps)
 {
     __shared__ uint32_t sF[2][TILE_THREADS * 3];
-    __shared__ uint8_t sAny[2][TILE_THREADS];        // row has frontier bits (per buffer)
+    __shared__ uint8_t sAny[2][TILE_THREADS];        // which words of the row have frontier bits (per buffer)
     __shared__ uint8_t sZ[2][TILE_E];                // z-row (= warp) has frontier bits (per buffer)
     __shared__ unsigned int s_act;                   // which of the 27 neighbour directions get activated
     __shared__ int s_next;                           // next queue position of this block
@@ -173,7 +171,7 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
 
                 // ---- load the frontier of this thread's row (3 words); a tile with no frontier cell in reach
                 //      has nothing to do (flags are raised conservatively) ----
-                bool any = false;
+                unsigned wm = 0;   // which of the row's three words hold frontier cells
 #pragma unroll
                 for (int w = 0; w < 3; ++w) {
                     const int gw = tx - 1 + w;
@@ -183,9 +181,10 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                     }
                     sF[0][tid * 3 + w] = f;
                     sF[1][tid * 3 + w] = 0;
-                    any |= f != 0;
+                    wm |= (f != 0 ? 1u : 0u) << w;
                 }
-                sAny[0][tid] = any ? 1 : 0;
+                const bool any = wm != 0;
+                sAny[0][tid] = (uint8_t)wm;
                 sAny[1][tid] = 0;
                 {
                     const bool zany = __any_sync(0xffffffffu, any);
@@ -235,16 +234,21 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                     if (zact && row_out <= TILE_K - s) {
                         // any frontier in the 3 x 3 rows around this one?
                         const uint8_t* A = sAny[cur];
-                        const int near = A[tid - 33] | A[tid - 32] | A[tid - 31] | A[tid - 1] | A[tid] | A[tid + 1] |
-                                         A[tid + 31] | A[tid + 32] | A[tid + 33];
+                        // words of the 3 x 3 rows around this one that hold frontier cells (a wavefront face across x
+                        // touches one word per row: only that word is gathered)
+                        const unsigned near = A[tid - 33] | A[tid - 32] | A[tid - 31] | A[tid - 1] | A[tid] | A[tid + 1] |
+                                              A[tid + 31] | A[tid + 32] | A[tid + 33];
                         if (near) {
                             const uint32_t* F = sF[cur];
                             uint32_t m[3];
 #pragma unroll
                             for (int w = 0; w < 3; ++w) {
-                                m[w] = F[(tid - 33) * 3 + w] | F[(tid - 32) * 3 + w] | F[(tid - 31) * 3 + w] |
-                                       F[(tid - 1) * 3 + w] | F[tid * 3 + w] | F[(tid + 1) * 3 + w] |
-                                       F[(tid + 31) * 3 + w] | F[(tid + 32) * 3 + w] | F[(tid + 33) * 3 + w];
+                                m[w] = 0;
+                                if ((near >> w) & 1u) {
+                                    m[w] = F[(tid - 33) * 3 + w] | F[(tid - 32) * 3 + w] | F[(tid - 31) * 3 + w] |
+                                           F[(tid - 1) * 3 + w] | F[tid * 3 + w] | F[(tid + 1) * 3 + w] |
+                                           F[(tid + 31) * 3 + w] | F[(tid + 32) * 3 + w] | F[(tid + 33) * 3 + w];
+                                }
                             }
                             const uint32_t d0 = m[0] | (m[0] << 1) | (m[0] >> 1) | (m[1] << 31);
                             const uint32_t d1 = m[1] | (m[1] << 1) | (m[1] >> 1) | (m[0] >> 31) | (m[2] << 31);
@@ -263,7 +267,7 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                         sF[cur ^ 1][tid * 3] = fresh[0];
                         sF[cur ^ 1][tid * 3 + 1] = fresh[1];
                         sF[cur ^ 1][tid * 3 + 2] = fresh[2];
-                        sAny[cur ^ 1][tid] = got ? 1 : 0;
+                        sAny[cur ^ 1][tid] = (uint8_t)((fresh[0] != 0 ? 1u : 0u) | (fresh[1] != 0 ? 2u : 0u) | (fresh[2] != 0 ? 4u : 0u));
                     }
                     const bool zgot = __any_sync(0xffffffffu, got);
                     if (lane == 0 && (zgot || zstale)) {

@@ -1353,10 +1353,10 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
 {
     const int total = (int)words;
     BfsTiles& t = (&g == &ctx->bank) ? ctx->bank_tiles : ctx->bfs_tiles;
-    // AUTO: the tile kernel wins where the per-level latency dominates (one small grid), the level kernel where
-    // throughput does (large grids, stacked banks); see bfs_tiles.cuh
-    const bool small_single = (&g != &ctx->bank) && (long long)g.DX * g.DY * g.DZ <= 8LL * 1000 * 1000;
-    const bool tiles = ctx->bfs_mode == SMPLGPU_BFS_TILES || (ctx->bfs_mode == SMPLGPU_BFS_AUTO && small_single);
+    // AUTO: the tile kernel for a single grid (bound by the per-level latency), the level kernel for the stacked
+    // banks (many wavefronts at once: throughput bound); see bfs_tiles.cuh
+    const bool single = &g != &ctx->bank;
+    const bool tiles = ctx->bfs_mode == SMPLGPU_BFS_TILES || (ctx->bfs_mode == SMPLGPU_BFS_AUTO && single);
     {
         // one warp per 32 bitmap words; at least one thread per row for the candidate stamps
         const long long threads = std::max<long long>(g.rows, std::min<long long>((long long)total, 148LL * 2048 * 4));
