@@ -150,6 +150,23 @@ def cpu_bfs_rate(n):
     return n ** 3 / dt / 1e6, kind, dt
 
 
+class StdoutToStderr:
+    """stdout carries exactly one JSON line: anything a library prints while this is active (NCCL's version
+    banner at the first collective, at file-descriptor level) goes to stderr instead."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def setup_shared_scene(scene, local_rank, rank, world, dev):
     """Context for `scene` on this rank's GPU: rank 0 builds the distance field on its GPU, every other rank
     receives it in ONE broadcast (NCCL over NVLink) -- the only collective of the data path."""
@@ -240,15 +257,14 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("SMPL_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-
     # ---- scene: rank 0 builds the distance field on its GPU, then ONE broadcast over NCCL ----
     scene = scenes.pr2_clutter_scene()
-    ctx, tables = setup_shared_scene(scene, local_rank, rank, world, dev)
+    with StdoutToStderr():
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+        ctx, tables = setup_shared_scene(scene, local_rank, rank, world, dev)
+        if world > 1:
+            dist.barrier()
     # time on ONE explicit stream shared by torch (events) and the library (kernels, copies)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -378,7 +394,9 @@ def main():
         starts_all, goals_all = scenes.tabletop_queries(nq_total, seed=13)
         mine = sharding.round_robin_shard(nq_total, rank, world)   # no collective
         # one planner thread per context (the reference's threading model), all on this rank's GPU
-        n_thr = max(1, min(args.plan_threads, (os.cpu_count() or 1) // max(1, world) - 2))
+        # planner threads spin on their streams: beyond ~40 % of the rank's cores the CUDA / NCCL helper threads starve
+        # and the rounds become erratic (measured: 6 of 16 cores 700 q/s, 8 of 16 cores 200-340 q/s)
+        n_thr = max(1, min(args.plan_threads, int(0.4 * (os.cpu_count() or 1) / max(1, world) + 0.5)))
         pctxs = [pctx] + [api.clone_context(pctx, pscene, ptables, device=local_rank) for _ in range(n_thr - 1)]
         per_ctx = max(1, (args.plan_concurrent + n_thr - 1) // n_thr)
         api.plan_batch(pctxs, pscene, ptables, pparams, starts_all[mine][:4 * n_thr], goals_all[mine][:4 * n_thr],

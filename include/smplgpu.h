@@ -283,6 +283,9 @@ int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, c
                          int cost_per_cell, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells,
                          double* offset_xyz);
 
+/* Size the batch buffers for up to max_n edges once (device allocations synchronise the whole device, which
+ * stalls every other context's stream: do it before the planners start, not while they run). */
+int smplgpu_expand_batch_reserve(smplgpu_ctx* ctx, int max_n);
 /* The same in two halves, so the host can prepare / absorb one batch while the device works on another:
  * submit copies the inputs and queues the work on the context's stream and returns at once; wait blocks until
  * that batch is done and copies the results out (returns n).  buffer = 0 or 1: two batches may be in flight. */

@@ -1719,6 +1719,32 @@ static int grow_pinned1(smplgpu_ctx* ctx, void** p, size_t* cap, size_t need)
     return 0;
 }
 
+static int reserve_expand(smplgpu_ctx* ctx, int b, int n)
+{
+    const int dof = ctx->h_model->dof;
+    const size_t row = (size_t)dof * sizeof(double);
+    const size_t in_bytes = 2 * n * row + (size_t)n * sizeof(int);
+    const size_t in_pad = (in_bytes + 63) / 64 * 64;
+    const size_t out_bytes = (size_t)n * (3 * sizeof(double) + 2 * sizeof(int) + 1);
+    int r;
+    if ((r = grow_pinned1(ctx, &ctx->exp_in[b], &ctx->exp_in_cap[b], in_bytes))) return r;
+    if ((r = grow_pinned1(ctx, &ctx->exp_out[b], &ctx->exp_out_cap[b], out_bytes))) return r;
+    if ((r = grow(ctx, &ctx->d_exp[b], &ctx->d_exp_cap[b], in_pad + out_bytes + 256))) return r;
+    return 0;
+}
+
+int smplgpu_expand_batch_reserve(smplgpu_ctx* ctx, int max_n)
+{
+    if (!ctx || max_n < 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set");
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->exp_n[b] >= 0) return fail(ctx, SMPLGPU_ERR_STATE, "expansion buffer %d is in flight", b);
+        int r = reserve_expand(ctx, b, std::max(max_n, 1));
+        if (r) return r;
+    }
+    return ensure_unc(ctx, (size_t)std::max(max_n, 1));
+}
+
 int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double* q1, const int32_t* slot, int n,
                                 int cost_per_cell, int buffer)
 {
@@ -1736,9 +1762,7 @@ int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double
     const size_t in_bytes = 2 * n * row + (size_t)n * sizeof(int);
     const size_t in_pad = (in_bytes + 63) / 64 * 64;
     const size_t out_bytes = (size_t)n * (3 * sizeof(double) + 2 * sizeof(int) + 1);
-    if ((r = grow_pinned1(ctx, &ctx->exp_in[b], &ctx->exp_in_cap[b], in_bytes))) return r;
-    if ((r = grow_pinned1(ctx, &ctx->exp_out[b], &ctx->exp_out_cap[b], out_bytes))) return r;
-    if ((r = grow(ctx, &ctx->d_exp[b], &ctx->d_exp_cap[b], in_pad + out_bytes + 256))) return r;
+    if ((r = reserve_expand(ctx, b, n))) return r;   // no-op once smplgpu_expand_batch_reserve has sized the buffers
     uint8_t* pin = (uint8_t*)ctx->exp_in[b];
     memcpy(pin, q0, n * row);
     memcpy(pin + n * row, q1, n * row);

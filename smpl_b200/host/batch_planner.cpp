@@ -500,6 +500,9 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
     };
     const int n_slots = std::min(m_max_concurrent, nq);
     if (smplgpu_bfs_bank_create(m_ctx, n_slots, m_cfg.inflation_radius) < 0) return fail_dev();
+    // every device / pinned allocation happens here: allocating while other planner threads run would stall
+    // their streams (allocation synchronises the device)
+    if (smplgpu_expand_batch_reserve(m_ctx, (n_slots + 1) * (int)m_prim_deltas.size()) < 0) return fail_dev();
     ++m_stats.device_calls;
     m_stats.device_seconds += t.lap();
 
