@@ -7,14 +7,13 @@
 
 namespace oracle {
 
-static const int INFINITECOST = 1000000000; // SBPL's INFINITECOST
 
 ManipLatticePlanner::ManipLatticePlanner(
     CollisionSpace* cc, KDLRobotModel* robot, BfsHeuristic* heur,
     const double xyz_offset[3], int /*cost_per_cell*/, const PlanParams& params)
 :
     m_cc(cc), m_robot(robot), m_heur(heur), m_params(params),
-    m_goal_state_id(-1), m_start_state_id(-1), m_eps(1.0), m_iteration(1), m_call_number(0)
+    m_goal_state_id(-1), m_start_state_id(-1)
 {
     for (int i = 0; i < 3; ++i) m_xyz_offset[i] = xyz_offset[i];
     // addMotionPrim(..., add_converse = true): each primitive is followed by its negation
@@ -158,120 +157,11 @@ void ManipLatticePlanner::getSuccs(int state_id, std::vector<int>& succs, std::v
     }
 }
 
-///////////////////////////////////////////////////////////////////////////////
-// ARA*
-///////////////////////////////////////////////////////////////////////////////
-
-ManipLatticePlanner::SearchState& ManipLatticePlanner::searchState(int id)
-{
-    if ((int)m_search.size() <= id) {
-        SearchState blank;
-        blank.state_id = -1;
-        blank.call_number = 0;
-        blank.heap_index = 0;
-        blank.g = blank.h = blank.f = blank.eg = 0;
-        blank.iteration_closed = 0;
-        blank.bp = -1;
-        blank.incons = false;
-        const size_t old = m_search.size();
-        m_search.resize(id + 1, blank);
-        for (size_t k = old; k < m_search.size(); ++k) {
-            m_search[k].state_id = (int)k;
-        }
-    }
-    return m_search[id];
-}
-
-/// arastar.cpp:613-627
-void ManipLatticePlanner::reinit(SearchState& s)
-{
-    if (s.call_number != m_call_number) {
-        s.g = INFINITECOST;
-        s.h = goalHeuristic(s.state_id);
-        s.f = INFINITECOST;
-        s.eg = INFINITECOST;
-        s.iteration_closed = 0;
-        s.call_number = m_call_number;
-        s.bp = -1;
-        s.incons = false;
-    }
-}
-
-/// arastar.cpp:579-582
-int ManipLatticePlanner::computeKey(const SearchState& s) const
-{
-    return s.g + (unsigned int)(m_eps * s.h);
-}
-
-void ManipLatticePlanner::percolateUp(size_t pivot)
-{
-    const int tmp = m_open[pivot];
-    while (pivot != 1) {
-        const size_t p = pivot >> 1;
-        if (heapLess(m_open[p], tmp)) {
-            break;
-        }
-        m_open[pivot] = m_open[p];
-        m_search[m_open[pivot]].heap_index = (int)pivot;
-        pivot = p;
-    }
-    m_open[pivot] = tmp;
-    m_search[tmp].heap_index = (int)pivot;
-}
-
-void ManipLatticePlanner::percolateDown(size_t pivot)
-{
-    if (pivot >= m_open.size()) {
-        return;
-    }
-    size_t left = pivot << 1, right = left + 1;
-    const int tmp = m_open[pivot];
-    while (left < m_open.size()) {
-        size_t s = right;
-        if (right >= m_open.size() || heapLess(m_open[left], m_open[right])) {
-            s = left;
-        }
-        if (heapLess(m_open[s], tmp)) {
-            m_open[pivot] = m_open[s];
-            m_search[m_open[pivot]].heap_index = (int)pivot;
-            pivot = s;
-        } else {
-            break;
-        }
-        left = pivot << 1;
-        right = left + 1;
-    }
-    m_open[pivot] = tmp;
-    m_search[tmp].heap_index = (int)pivot;
-}
-
-void ManipLatticePlanner::heapPush(int id)
-{
-    m_search[id].heap_index = (int)m_open.size();
-    m_open.push_back(id);
-    percolateUp(m_open.size() - 1);
-}
-
-void ManipLatticePlanner::heapPop()
-{
-    m_search[m_open[1]].heap_index = 0;
-    m_open[1] = m_open.back();
-    m_open.pop_back();
-    percolateDown(1);
-}
-
-void ManipLatticePlanner::heapDecrease(int id)
-{
-    percolateUp((size_t)m_search[id].heap_index);
-}
-
 PlanResult ManipLatticePlanner::plan(const std::vector<double>& start, const double goal_xyz[3])
 {
     PlanResult res;
     m_states.clear();
     m_coord_to_id.clear();
-    m_search.clear();
-    m_open.assign(1, -1);
     for (int i = 0; i < 3; ++i) m_goal[i] = goal_xyz[i];
 
     // reserveHashEntry for the goal state (manip_lattice.cpp:122): id 0
@@ -290,69 +180,18 @@ PlanResult ManipLatticePlanner::plan(const std::vector<double>& start, const dou
     stateToCoord(start, coord);
     m_start_state_id = getOrCreateState(coord, start);
 
-    // replan (arastar.cpp:107-215), first solution at the initial epsilon
-    ++m_call_number;
-    m_iteration = 1;
-    m_eps = m_params.epsilon;
-    // vector growth may move elements: fetch by index after both exist
-    searchState(std::max(m_start_state_id, m_goal_state_id));
-    reinit(m_search[m_start_state_id]);
-    reinit(m_search[m_goal_state_id]);
-    m_search[m_start_state_id].g = 0;
-    m_search[m_start_state_id].f = computeKey(m_search[m_start_state_id]);
-    heapPush(m_start_state_id);
-
-    std::vector<int> succs, costs;
-    bool found = false;
-    while (m_open.size() > 1) {
-        const int min_id = m_open[1];
-        if (m_search[min_id].f >= m_search[m_goal_state_id].f || min_id == m_goal_state_id) {
-            found = true;
-            break;
-        }
-        if (res.expansions >= m_params.max_expansions) {
-            break;
-        }
-        heapPop();
-        m_search[min_id].iteration_closed = m_iteration;
-        m_search[min_id].eg = m_search[min_id].g;
-
-        // expand (arastar.cpp:531-568)
-        succs.clear();
-        costs.clear();
-        getSuccs(min_id, succs, costs);
-        for (size_t k = 0; k < succs.size(); ++k) {
-            searchState(succs[k]);
-            SearchState& ss = m_search[succs[k]];
-            reinit(ss);
-            const int new_cost = m_search[min_id].eg + costs[k];
-            if (new_cost < ss.g) {
-                ss.g = new_cost;
-                ss.bp = min_id;
-                if (ss.iteration_closed != m_iteration) {
-                    ss.f = computeKey(ss);
-                    if (ss.heap_index != 0) {
-                        heapDecrease(ss.state_id);
-                    } else {
-                        heapPush(ss.state_id);
-                    }
-                } else if (!ss.incons) {
-                    ss.incons = true; // (the reference forgets to set the flag; harmless for one iteration)
-                }
-            }
-        }
-        ++res.expansions;
-    }
+    // replan (arastar.cpp:107-215), first solution at the initial epsilon: oracle/arastar.h
+    AraStar search(
+        [this](int id, std::vector<int>& succs, std::vector<int>& costs) { getSuccs(id, succs, costs); },
+        [this](int id) { return goalHeuristic(id); });
+    const AraStar::Result r = search.search(m_start_state_id, m_goal_state_id, m_params.epsilon, m_params.max_expansions);
+    res.expansions = r.expansions;
     res.num_states = (int)m_states.size();
-    if (!found || m_search[m_goal_state_id].g >= INFINITECOST) {
-        return res;
+    if (!r.found || r.cost >= AraStar::INFINITE_COST) {
+        return res;   // no path, or the reference's degenerate "[goal] at INFINITECOST" answer (see arastar.h)
     }
-    // extractPath (arastar.cpp:629-640)
-    for (int s = m_goal_state_id; s >= 0; s = m_search[s].bp) {
-        res.path_ids.push_back(s);
-    }
-    std::reverse(res.path_ids.begin(), res.path_ids.end());
-    res.cost = m_search[m_goal_state_id].g;
+    res.path_ids = r.path;
+    res.cost = r.cost;
     res.success = true;
     for (int id : res.path_ids) {
         res.path_states.push_back(m_states[id].state);

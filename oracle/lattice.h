@@ -8,9 +8,7 @@
 //                     1944-1980 (setStart)
 //   ManipLatticeActionSpace  smpl/src/graph/manip_lattice_action_space.cpp:201-228 (addMotionPrim),
 //                     376-449 (apply), 507-573 (getAction), 662-691 (mprimActive)
-//   ARAStar           smpl/src/search/arastar.cpp:107-215 (replan), 486-527 (improvePath),
-//                     531-568 (expand), 579-582 (computeKey), 613-640 (reinitSearchState, extractPath)
-//   intrusive_heap    smpl/include/smpl/detail/intrusive_heap.hpp (push/pop/decrease, percolate_up/down)
+//   ARAStar           oracle/arastar.h (pinned against the reference's own arastar.cpp)
 //
 // Decisions (fork defect 2): motion primitives use the documented plain format
 // (delta per joint, weight 1, no base rotation hack, converse added after each primitive); the IK "snap"
@@ -24,6 +22,7 @@
 #include <map>
 #include <vector>
 
+#include "arastar.h"
 #include "collision_space.h"
 #include "kdl_model.h"
 
@@ -68,16 +67,6 @@ public:
 
 private:
     struct LatticeState { std::vector<int> coord; std::vector<double> state; };
-    struct SearchState
-    {
-        int state_id;
-        int g, h, f, eg;
-        int iteration_closed, call_number;
-        int bp;
-        bool incons;
-        int heap_index;
-    };
-
     CollisionSpace* m_cc;
     KDLRobotModel* m_robot;
     BfsHeuristic* m_heur;
@@ -95,26 +84,12 @@ private:
     int m_goal_state_id, m_start_state_id;
     double m_goal[3];
 
-    std::vector<SearchState> m_search;
-    std::vector<int> m_open; // 1-based binary heap of state ids
-    double m_eps;
-    int m_iteration, m_call_number;
-
     void stateToCoord(const std::vector<double>& state, std::vector<int>& coord) const;
     int getOrCreateState(const std::vector<int>& coord, const std::vector<double>& state);
     bool isGoal(const std::vector<double>& state) const;
     void getSuccs(int state_id, std::vector<int>& succs, std::vector<int>& costs);
     int goalHeuristic(int state_id) const;
 
-    SearchState& searchState(int id);
-    void reinit(SearchState& s);
-    int computeKey(const SearchState& s) const;
-    bool heapLess(int a, int b) const { return m_search[a].f < m_search[b].f; }
-    void heapPush(int id);
-    void heapPop();
-    void heapDecrease(int id);
-    void percolateUp(size_t pivot);
-    void percolateDown(size_t pivot);
 };
 
 } // namespace oracle

@@ -18,6 +18,7 @@
 #include "collision_space.h"
 #include "distance_map.h"
 #include "kdl_model.h"
+#include "arastar.h"
 #include "lattice.h"
 #include "robot_desc.h"
 
@@ -509,6 +510,32 @@ double oracle_plan(oracle_scene* s, const double* start, const double* goal_xyz,
         path_ids[i] = r.path_ids[i];
     }
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+/// oracle/arastar.h on an explicit graph (CSR successor lists), same signature as ref_arastar_search
+/// (oracle/ref_arastar_shim.cpp): out[0] = found, out[1] = cost, out[2] = expansions, out[3] = path length
+int oracle_arastar_search(int n, const int* off, const int* dst, const int* cost, const int* h,
+                          int start, int goal, double eps, int max_expansions,
+                          int* path, int max_path, int* out)
+{
+    (void)n;
+    AraStar search(
+        [&](int s, std::vector<int>& succs, std::vector<int>& costs) {
+            for (int k = off[s]; k < off[s + 1]; ++k) {
+                succs.push_back(dst[k]);
+                costs.push_back(cost[k]);
+            }
+        },
+        [&](int s) { return h[s]; });
+    const AraStar::Result r = search.search(start, goal, eps, max_expansions);
+    out[0] = r.found ? 1 : 0;
+    out[1] = r.cost;
+    out[2] = r.expansions;
+    out[3] = (int)r.path.size();
+    for (int i = 0; i < (int)r.path.size() && i < max_path; ++i) {
+        path[i] = r.path[i];
+    }
+    return 0;
 }
 
 ///////////////////////////////////////////////////////////////////////////////

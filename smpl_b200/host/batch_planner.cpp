@@ -279,7 +279,7 @@ void BatchPlanner::finish(Query& Q, bool found)
 {
     Q.done = true;
     Q.result.num_states = Q.lat.size();
-    if (!found || Q.search.empty() || Q.search[0].g >= INFINITECOST) {
+    if (!found || Q.search.empty() || Q.search[0].g >= (unsigned int)INFINITECOST) {
         return;
     }
     for (int s = 0; s >= 0; s = Q.search[s].bp) {
@@ -466,7 +466,7 @@ void BatchPlanner::absorbOne(Query& Q, const uint8_t* verdict, const int32_t* h,
         touch(Q, target);
         SState& ss = Q.search[target];
         const int new_cost = Q.search[Q.expanding].eg + (int)(1000 * 1.0);
-        if (new_cost < ss.g) {
+        if ((unsigned int)new_cost < ss.g) {   // int vs unsigned, compared as unsigned (arastar.cpp:545-548)
             ss.g = new_cost;
             ss.bp = Q.expanding;
             if (ss.iteration_closed != 1) {

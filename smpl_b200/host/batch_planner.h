@@ -106,7 +106,9 @@ private:
         int add(const int* c, const double* q, int hv, int gd, bool index);   // index = enter it in the table
         void grow();
     };
-    struct SState { int g, h, f, eg, iteration_closed, bp, heap_index; bool touched; };
+    // g, h, f, eg are unsigned as in the reference's ARAStar::SearchState (arastar.h:176-187): a negative heuristic
+    // (unreachable BFS cell: cost_per_cell * -1) sorts last in OPEN
+    struct SState { unsigned int g, h, f, eg; int iteration_closed, bp, heap_index; bool touched; };
     struct Query
     {
         int index;

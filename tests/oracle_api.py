@@ -74,6 +74,40 @@ def ref_lib():
     return _REF
 
 
+_REF_ARA = None
+
+
+def ref_arastar_lib():
+    """The reference's own ARA* (smpl/src/search/arastar.cpp compiled from /root/reference), or None."""
+    global _REF_ARA
+    if _REF_ARA is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_arastar.so")
+        if not os.path.exists(path):
+            return None
+        _REF_ARA = C.CDLL(path)
+    return _REF_ARA
+
+
+def arastar_search(which, off, dst, cost, h, start, goal, eps, max_expansions, max_path=4096):
+    """ARA* (first solution at `eps`, at most `max_expansions` expansions) on an explicit CSR graph.
+    which = "oracle" (oracle/arastar.h) or "reference" (the reference's arastar.cpp).
+    Returns dict(found, cost, expansions, path)."""
+    off = np.ascontiguousarray(off, dtype=np.int32)
+    dst = np.ascontiguousarray(dst, dtype=np.int32)
+    cost = np.ascontiguousarray(cost, dtype=np.int32)
+    h = np.ascontiguousarray(h, dtype=np.int32)
+    path = np.zeros(max_path, np.int32)
+    out = np.zeros(4, np.int32)
+    if which == "reference":
+        fn = ref_arastar_lib().ref_arastar_search
+    else:
+        fn = lib().oracle_arastar_search
+    fn(len(off) - 1, _ip(off), _ip(dst), _ip(cost), _ip(h), int(start), int(goal), C.c_double(eps), int(max_expansions),
+       _ip(path), max_path, _ip(out))
+    n = int(out[3])
+    return dict(found=bool(out[0]), cost=int(out[1]), expansions=int(out[2]), path=path[:min(n, max_path)].copy())
+
+
 class OracleScene:
     def __init__(self, robot_path, group, planning_joints, origin, size, res, max_dist):
         L = lib()

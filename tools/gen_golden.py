@@ -50,6 +50,22 @@ def gen_plans():
                "results": results}, open(os.path.join(OUT, "pr2_tabletop_plans.json"), "w"))
 
 
+def gen_arastar():
+    """arastar_reference.npz -- outputs of the REFERENCE's own ARA* (oracle/_ref/libref_arastar.so) on the graphs
+    of tests/test_oracle_arastar.py."""
+    from oracle_api import arastar_search
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_oracle_arastar as T
+    out = {}
+    for k, (seed, eps, max_exp) in enumerate(T.CASES):
+        off, dst, cost, h, start, goal = T.lattice_graph(seed, weird_h=seed != 3)
+        r = arastar_search("reference", off, dst, cost, h, start, goal, eps, max_exp)
+        out["summary_%d" % k] = np.array([int(r["found"]), r["cost"], r["expansions"]], np.int32)
+        out["path_%d" % k] = r["path"]
+        print("arastar case %d: found=%s cost=%d expansions=%d" % (k, r["found"], r["cost"], r["expansions"]))
+    np.savez_compressed(os.path.join(OUT, "arastar_reference.npz"), **out)
+
+
 def gen_bfs():
     rng = np.random.default_rng(24)
     walls = (rng.random((24, 24, 24)) < 0.3).astype(np.uint8)
@@ -98,6 +114,6 @@ def gen_ubr1():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["bfs", "pr2", "ubr1", "plans"]
+    which = sys.argv[1:] or ["bfs", "pr2", "ubr1", "plans", "arastar"]
     for name in which:
-        {"bfs": gen_bfs, "pr2": gen_pr2, "ubr1": gen_ubr1, "plans": gen_plans}[name]()
+        {"bfs": gen_bfs, "pr2": gen_pr2, "ubr1": gen_ubr1, "plans": gen_plans, "arastar": gen_arastar}[name]()
