@@ -74,6 +74,64 @@ def ref_lib():
     return _REF
 
 
+_REF_DM = None
+
+
+def ref_distmap_lib():
+    """The reference's own EuclidDistanceMap (compiled from /root/reference), or None."""
+    global _REF_DM
+    if _REF_DM is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_distmap.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.ref_distmap_create.restype = C.c_void_p
+        R.ref_distmap_create.argtypes = [C.c_double] * 8
+        R.ref_distmap_distance.restype = C.c_double
+        R.ref_distmap_distance.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        R.ref_distmap_world_to_grid.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, c_int32_p]
+        _REF_DM = R
+    return _REF_DM
+
+
+class RefDistanceMap:
+    """sbpl::EuclidDistanceMap of the reference (with the fork's commented-out interior initialisation restored
+    by the shim, oracle/ref_distmap_shim.cpp)."""
+
+    def __init__(self, origin, size, res, max_dist):
+        self.R = ref_distmap_lib()
+        self.h = C.c_void_p(self.R.ref_distmap_create(*(float(v) for v in (*origin, *size, res, max_dist))))
+        d = np.zeros(3, np.int32)
+        self.R.ref_distmap_dims(self.h, _ip(d))
+        self.dims = tuple(int(v) for v in d)
+
+    def close(self):
+        if self.h:
+            self.R.ref_distmap_destroy(self.h)
+            self.h = None
+
+    def add_points(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        self.R.ref_distmap_add_points(self.h, _dp(pts), len(pts))
+
+    def remove_points(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        self.R.ref_distmap_remove_points(self.h, _dp(pts), len(pts))
+
+    def d2(self):
+        out = np.zeros(self.dims[0] * self.dims[1] * self.dims[2], np.int32)
+        self.R.ref_distmap_d2(self.h, _ip(out))
+        return out.reshape(self.dims)
+
+    def distance(self, x, y, z):
+        return self.R.ref_distmap_distance(self.h, float(x), float(y), float(z))
+
+    def world_to_grid(self, p):
+        g = np.zeros(3, np.int32)
+        self.R.ref_distmap_world_to_grid(self.h, float(p[0]), float(p[1]), float(p[2]), _ip(g))
+        return g
+
+
 _REF_ARA = None
 
 

@@ -66,6 +66,25 @@ def gen_arastar():
     np.savez_compressed(os.path.join(OUT, "arastar_reference.npz"), **out)
 
 
+def gen_distmap():
+    """distmap_reference.npz -- fields of the REFERENCE's own EuclidDistanceMap (oracle/_ref/libref_distmap.so)."""
+    from oracle_api import RefDistanceMap
+    import test_oracle_distance_map as T
+    scene = T.small_scene()
+    o = make_oracle(scene)
+    ref = RefDistanceMap(scene.origin, scene.size, scene.res, scene.max_dist)
+    ref.add_points(T.obstacle_points(o))
+    out = {"d2_after_add": ref.d2().astype(np.uint16)}
+    rng = np.random.default_rng(8)
+    more = np.array(scene.origin) - 0.05 + rng.random((300, 3)) * (np.array(scene.size) + 0.1)
+    more = np.concatenate([more, more[:20]])
+    ref.add_points(more)
+    ref.remove_points(more[:150])
+    out["d2_after_remove"] = ref.d2().astype(np.uint16)
+    np.savez_compressed(os.path.join(OUT, "distmap_reference.npz"), **out)
+    print("distmap: dims", ref.dims, "max d2", int(out["d2_after_add"].max()))
+
+
 def gen_bfs():
     rng = np.random.default_rng(24)
     walls = (rng.random((24, 24, 24)) < 0.3).astype(np.uint8)
@@ -114,6 +133,6 @@ def gen_ubr1():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["bfs", "pr2", "ubr1", "plans", "arastar"]
+    which = sys.argv[1:] or ["bfs", "pr2", "ubr1", "plans", "arastar", "distmap"]
     for name in which:
-        {"bfs": gen_bfs, "pr2": gen_pr2, "ubr1": gen_ubr1, "plans": gen_plans, "arastar": gen_arastar}[name]()
+        {"bfs": gen_bfs, "pr2": gen_pr2, "ubr1": gen_ubr1, "plans": gen_plans, "arastar": gen_arastar, "distmap": gen_distmap}[name]()
