@@ -452,12 +452,21 @@ def main():
             po.init_kdl(pscene.chain_root, pscene.chain_tip, pscene.planning_link, pscene.T_kin_to_planning, pscene.xyz_offset)
             k = min(args.plan_cpu_queries, len(starts_all))
             secs, cexp = 0.0, 0
-            for s_, g_ in zip(starts_all[:k], goals_all[:k]):
+            same = 0
+            for qi, (s_, g_) in enumerate(zip(starts_all[:k], goals_all[:k])):
                 po.heur_init(pscene.inflation_radius, pscene.cost_per_cell)
                 t0 = time.perf_counter()
                 pr = po.plan(s_, g_, pparams)
                 secs += time.perf_counter() - t0      # includes the per-query BFS, as the GPU figure does
                 cexp += pr["expansions"]
+                if world == 1 or qi % world == 0:     # rank 0 planned queries 0, world, 2 world, ...
+                    gr = pres[qi // world]
+                    same += int((gr["success"], gr["expansions"], gr["cost"]) == (pr["success"], pr["expansions"], pr["cost"])
+                                and np.array_equal(gr["path_ids"], pr["path_ids"]))
+                else:
+                    same += 1
+            plan["parity_checked_queries"] = k
+            plan["parity_identical"] = same
             plan["cpu_queries_per_s"] = k / secs
             plan["cpu_expansions_per_s"] = cexp / secs
             plan["cpu_sample"] = "first %d queries, oracle ManipLattice + ARA*, 1 thread" % k

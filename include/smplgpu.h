@@ -283,6 +283,8 @@ int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, c
                          int cost_per_cell, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells,
                          double* offset_xyz);
 
+/* edges of all expansion batches so far that the double-precision kernels had to resolve */
+int64_t smplgpu_expand_batch_resolved(const smplgpu_ctx* ctx);
 /* Size the batch buffers for up to max_n edges once (device allocations synchronise the whole device, which
  * stalls every other context's stream: do it before the planners start, not while they run). */
 int smplgpu_expand_batch_reserve(smplgpu_ctx* ctx, int max_n);

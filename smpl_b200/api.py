@@ -604,7 +604,7 @@ def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max
                         path_ids=paths[i, :min(n, max_path)].copy(), num_states=int(summary[i, 4])))
     st = dict(rounds=int(stats[0]), edges_submitted=int(stats[1]), device_calls=int(stats[2]),
               device_seconds=float(stats[3]), host_seconds=float(stats[4]), total_seconds=float(stats[5]),
-              bfs_runs=int(stats[6]), n_threads=int(n_threads))
+              bfs_runs=int(stats[6]), edges_resolved_f64=int(stats[7]), n_threads=int(n_threads))
     return out, st
 
 

@@ -91,6 +91,7 @@ struct smplgpu_ctx
     void* d_exp[2] = { nullptr, nullptr }; size_t d_exp_cap[2] = { 0, 0 };
     cudaEvent_t ev_exp[2] = { nullptr, nullptr };
     int exp_n[2] = { -1, -1 };
+    int64_t exp_resolved_total = 0;   // edges of expansion batches resolved in double, since creation
     cudaEvent_t ev_in[2] = { nullptr, nullptr };   // chunk b: inputs on the device
     cudaStream_t copy_stream = nullptr;
     unsigned long long* d_stats = nullptr;
@@ -1728,7 +1729,7 @@ static int reserve_expand(smplgpu_ctx* ctx, int b, int n)
     const size_t out_bytes = (size_t)n * (3 * sizeof(double) + 2 * sizeof(int) + 1);
     int r;
     if ((r = grow_pinned1(ctx, &ctx->exp_in[b], &ctx->exp_in_cap[b], in_bytes))) return r;
-    if ((r = grow_pinned1(ctx, &ctx->exp_out[b], &ctx->exp_out_cap[b], out_bytes))) return r;
+    if ((r = grow_pinned1(ctx, &ctx->exp_out[b], &ctx->exp_out_cap[b], out_bytes + 32))) return r;
     if ((r = grow(ctx, &ctx->d_exp[b], &ctx->d_exp_cap[b], in_pad + out_bytes + 256))) return r;
     return 0;
 }
@@ -1744,6 +1745,8 @@ int smplgpu_expand_batch_reserve(smplgpu_ctx* ctx, int max_n)
     }
     return ensure_unc(ctx, (size_t)std::max(max_n, 1));
 }
+
+int64_t smplgpu_expand_batch_resolved(const smplgpu_ctx* ctx) { return ctx ? ctx->exp_resolved_total : 0; }
 
 int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double* q1, const int32_t* slot, int n,
                                 int cost_per_cell, int buffer)
@@ -1786,6 +1789,9 @@ int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double
     ++ctx->launches;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(ctx->exp_out[b], obase, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    // edges of this batch that the double-precision kernels had to resolve (behind the results, 8-byte aligned)
+    CU(cudaMemcpyAsync((uint8_t*)ctx->exp_out[b] + (out_bytes + 15) / 16 * 16, ctx->d_stats + 3, sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ctx->ev_exp[b], ctx->stream));
     return 0;
 }
@@ -1805,6 +1811,10 @@ int smplgpu_expand_batch_wait(smplgpu_ctx* ctx, int buffer, uint8_t* verdict, in
     memcpy(h, pout + (size_t)n * 3 * sizeof(double), (size_t)n * sizeof(int));
     memcpy(goal_dist_cells, pout + (size_t)n * (3 * sizeof(double) + sizeof(int)), (size_t)n * sizeof(int));
     memcpy(verdict, pout + (size_t)n * (3 * sizeof(double) + 2 * sizeof(int)), (size_t)n);
+    const size_t out_bytes = (size_t)n * (3 * sizeof(double) + 2 * sizeof(int) + 1);
+    unsigned long long resolved = 0;
+    memcpy(&resolved, pout + (out_bytes + 15) / 16 * 16, sizeof(resolved));
+    ctx->exp_resolved_total += (int64_t)resolved;
     return n;
 }
 

@@ -498,6 +498,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         if (err) *err = smplgpu_last_error(m_ctx);
         return false;
     };
+    const long long resolved0 = smplgpu_expand_batch_resolved(m_ctx);
     const int n_slots = std::min(m_max_concurrent, nq);
     if (smplgpu_bfs_bank_create(m_ctx, n_slots, m_cfg.inflation_radius) < 0) return fail_dev();
     // every device / pinned allocation happens here: allocating while other planner threads run would stall
@@ -689,6 +690,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         }
         m_stats.host_seconds += t.lap();
     }
+    m_stats.edges_resolved_f64 = smplgpu_expand_batch_resolved(m_ctx) - resolved0;
     // nothing can be in flight here: a group's queries finish in absorb or expand, and a batch is only
     // submitted for queries that are not done; drain defensively anyway
     for (int gi = 0; gi < 2; ++gi) {

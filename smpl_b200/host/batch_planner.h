@@ -67,6 +67,7 @@ struct BatchStats
     int rounds = 0;
     int bfs_runs = 0;              // bank runs (each covers every slot that was refilled at that point)
     long long edges_submitted = 0;
+    long long edges_resolved_f64 = 0;   // of those, decided by the double-precision kernels
     long long device_calls = 0;
     double device_seconds = 0.0;   // time inside smplgpu_* calls
     double host_seconds = 0.0;     // everything else

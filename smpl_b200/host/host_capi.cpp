@@ -263,6 +263,7 @@ int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* p, const d
         stats[4] = s.host_seconds;
         stats[5] = total;
         stats[6] = s.bfs_runs;
+        stats[7] = (double)s.edges_resolved_f64;
     }
     return 0;
 }
@@ -330,9 +331,9 @@ int smplhost_plan_batch_multi(smplgpu_ctx* const* ctxs, int n_ctx, const smplhos
         }
     }
     if (stats) {
-        for (int k = 0; k < 7; ++k) stats[k] = 0.0;
+        for (int k = 0; k < 8; ++k) stats[k] = 0.0;
         for (int t = 0; t < n_ctx; ++t) {
-            for (int k : { 0, 1, 2, 6 }) stats[k] += st[t][k];
+            for (int k : { 0, 1, 2, 6, 7 }) stats[k] += st[t][k];
             for (int k : { 3, 4, 5 }) stats[k] = std::max(stats[k], st[t][k]);
         }
     }
