@@ -399,14 +399,22 @@ def main():
         n_thr = max(1, min(args.plan_threads, int(0.4 * (os.cpu_count() or 1) / max(1, world) + 0.5)))
         pctxs = [pctx] + [api.clone_context(pctx, pscene, ptables, device=local_rank) for _ in range(n_thr - 1)]
         per_ctx = max(1, (args.plan_concurrent + n_thr - 1) // n_thr)
-        api.plan_batch(pctxs, pscene, ptables, pparams, starts_all[mine][:4 * n_thr], goals_all[mine][:4 * n_thr],
-                       max_concurrent=4)  # warm-up
+        # warm-up with the same bank shape: the BFS bank (a scene-level allocation of per_ctx grids per context) is
+        # created here and reused by the timed call
+        wq = min(len(mine), per_ctx * n_thr)
+        wparams = scenes.PlanParams(pscene.dof)
+        wparams.max_expansions = 20
+        api.plan_batch(pctxs, pscene, ptables, wparams, starts_all[mine][:wq], goals_all[mine][:wq], max_concurrent=per_ctx)
         barrier()
+        psampler = ClockSampler(local_rank)
+        if rank == 0:
+            psampler.start()
         t0 = time.perf_counter()
         pres, pstats = api.plan_batch(pctxs, pscene, ptables, pparams, starts_all[mine], goals_all[mine],
                                       max_concurrent=per_ctx)
-        pstats["planner_threads"] = n_thr
         dt = time.perf_counter() - t0
+        pclocks = psampler.stop() if rank == 0 else None
+        pstats["planner_threads"] = n_thr
         t_plan = torch.tensor([dt], device=dev, dtype=torch.float64)
         n_exp = torch.tensor([float(sum(r["expansions"] for r in pres)), float(sum(r["success"] for r in pres))],
                              device=dev, dtype=torch.float64)
@@ -417,7 +425,7 @@ def main():
                 "queries": nq_total, "solved": int(n_exp[1].item()), "expansions": int(n_exp[0].item()),
                 "seconds": float(t_plan.item()), "queries_per_s": nq_total / float(t_plan.item()),
                 "expansions_per_s": float(n_exp[0].item()) / float(t_plan.item()), "concurrent_per_gpu": args.plan_concurrent,
-                "rank0": pstats}
+                "rank0": pstats, "clocks": pclocks}
         for c in pctxs:
             c.close()
 

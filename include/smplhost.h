@@ -78,8 +78,9 @@ typedef struct smplhost_plan_params
 /* Plans nq queries (starts[nq][dof], goals[nq][3]) with at most max_concurrent searches in flight.
  * summary[nq][5] = success, expansions, cost, path length, lattice states created;
  * path_ids[nq][max_path] = state ids of the path (goal state id = 0, start = 1), truncated to max_path;
- * stats[8] = rounds, edges submitted, device calls, seconds inside smplgpu_* calls, host seconds, total seconds,
- * BFS bank runs, edges resolved by the double-precision kernels.
+ * stats[10] = rounds, edges submitted, device calls, seconds inside smplgpu_* calls, host seconds, total seconds,
+ * BFS bank runs, edges resolved by the double-precision kernels, seconds of set-up device calls (bank, BFS,
+ * setStart), longest single wait for a batch.
  * Returns 0, or a negative smplgpu error code (smplhost_last_error() has the text). */
 int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* params, const double* starts,
                         const double* goals, int nq, int max_concurrent, int32_t* summary, int32_t* path_ids,

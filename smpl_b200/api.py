@@ -587,7 +587,7 @@ def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max
         P.dims[a] = int(scene.dims[a])
     summary = np.zeros((nq, 5), np.int32)
     paths = np.full((nq, max_path), -1, np.int32)
-    stats = np.zeros(8)
+    stats = np.zeros(12)
     if isinstance(ctx, (list, tuple)):
         arr = (C.c_void_p * len(ctx))(*[c.h for c in ctx])
         r = H.smplhost_plan_batch_multi(arr, len(ctx), C.byref(P), _dp(starts), _dp(goals), nq, int(max_concurrent),
@@ -604,7 +604,8 @@ def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max
                         path_ids=paths[i, :min(n, max_path)].copy(), num_states=int(summary[i, 4])))
     st = dict(rounds=int(stats[0]), edges_submitted=int(stats[1]), device_calls=int(stats[2]),
               device_seconds=float(stats[3]), host_seconds=float(stats[4]), total_seconds=float(stats[5]),
-              bfs_runs=int(stats[6]), edges_resolved_f64=int(stats[7]), n_threads=int(n_threads))
+              bfs_runs=int(stats[6]), edges_resolved_f64=int(stats[7]), setup_seconds=float(stats[8]),
+              max_wait_seconds=float(stats[9]), n_threads=int(n_threads))
     return out, st
 
 

@@ -1609,11 +1609,17 @@ int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radi
     const long long total_nz = (long long)n_slots * (nz + 2) - 2;
     if ((long long)(nx + 2) * (ny + 2) * (total_nz + 2) > 0x7FFFFFFFLL)
         return fail(ctx, SMPLGPU_ERR_LIMIT, "%d slots of %dx%dx%d exceed int node indices", n_slots, nx, ny, nz);
+    // the bank is a scene-level resource: keep the (multi-gigabyte) allocation when the shape is unchanged --
+    // allocating it takes anything from 0.1 to 0.7 s
+    const bool same_shape = ctx->has_bank && ctx->bank_slots == n_slots && ctx->bank.nx == nx && ctx->bank.ny == ny &&
+                            ctx->bank.nz == (int)total_nz;
     ctx->has_bank = false;
-    int r = alloc_grid(ctx, ctx->bank, nx, ny, (int)total_nz, &ctx->bank_words, &ctx->bank_cells);
-    if (r) return r;
-    r = alloc_tiles(ctx, ctx->bank, ctx->bank_tiles, ctx->bank_words);
-    if (r) return r;
+    if (!same_shape) {
+        int r = alloc_grid(ctx, ctx->bank, nx, ny, (int)total_nz, &ctx->bank_words, &ctx->bank_cells);
+        if (r) return r;
+        r = alloc_tiles(ctx, ctx->bank, ctx->bank_tiles, ctx->bank_words);
+        if (r) return r;
+    }
     ctx->bank_slots = n_slots;
     ctx->bank_slot_dz = nz + 2;
     const int kmax = wall_threshold(ctx, inflation_radius);

@@ -505,7 +505,11 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
     // their streams (allocation synchronises the device)
     if (smplgpu_expand_batch_reserve(m_ctx, (n_slots + 1) * (int)m_prim_deltas.size()) < 0) return fail_dev();
     ++m_stats.device_calls;
-    m_stats.device_seconds += t.lap();
+    {
+        const double dt = t.lap();
+        m_stats.device_seconds += dt;
+        m_stats.setup_seconds += dt;
+    }
 
     Pool pool(m_cfg.n_threads);
     std::vector<Query> S(n_slots);          // slot -> query occupying it
@@ -537,7 +541,11 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         if (g.in_flight) {
             m_stats.host_seconds += t.lap();
             if (smplgpu_expand_batch_wait(m_ctx, gi, g.verdict.data(), g.h.data(), g.gd.data(), g.off.data()) < 0) return false;
-            m_stats.device_seconds += t.lap();
+            {
+                const double dt = t.lap();
+                m_stats.device_seconds += dt;
+                m_stats.max_wait_seconds = std::max(m_stats.max_wait_seconds, dt);
+            }
             g.in_flight = false;
             const int na = (int)g.active.size();
             pool.run([&](int tid) {
@@ -662,7 +670,11 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
             if (smplgpu_expand_batch(m_ctx, sq.data(), sq.data(), new_slots.data(), nn, m_cfg.cost_per_cell,
                                      dummy.data(), sh.data(), sgd.data(), soff.data()) < 0) return fail_dev();
             m_stats.device_calls += 3;
-            m_stats.device_seconds += t.lap();
+            {
+                const double dt = t.lap();
+                m_stats.device_seconds += dt;
+                m_stats.setup_seconds += dt;
+            }
             std::vector<int> coord;
             for (int k = 0; k < nn; ++k) {
                 Query& Q = S[new_slots[k]];

@@ -71,6 +71,8 @@ struct BatchStats
     long long device_calls = 0;
     double device_seconds = 0.0;   // time inside smplgpu_* calls
     double host_seconds = 0.0;     // everything else
+    double setup_seconds = 0.0;    // of device_seconds: bank creation, BFS bank runs, setStart (per refill)
+    double max_wait_seconds = 0.0; // longest single wait for an expansion batch
 };
 
 class BatchPlanner

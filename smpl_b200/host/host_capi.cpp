@@ -264,6 +264,8 @@ int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* p, const d
         stats[5] = total;
         stats[6] = s.bfs_runs;
         stats[7] = (double)s.edges_resolved_f64;
+        stats[8] = s.setup_seconds;
+        stats[9] = s.max_wait_seconds;
     }
     return 0;
 }
@@ -282,7 +284,7 @@ int smplhost_plan_batch_multi(smplgpu_ctx* const* ctxs, int n_ctx, const smplhos
     const int dof = p->dof;
     std::vector<int> rc(n_ctx, 0);
     std::vector<std::string> errs(n_ctx);
-    std::vector<std::vector<double>> st(n_ctx, std::vector<double>(8, 0.0));
+    std::vector<std::vector<double>> st(n_ctx, std::vector<double>(10, 0.0));
     std::vector<std::thread> threads;
     for (int t = 0; t < n_ctx; ++t) {
         threads.emplace_back([&, t]() {
@@ -331,10 +333,10 @@ int smplhost_plan_batch_multi(smplgpu_ctx* const* ctxs, int n_ctx, const smplhos
         }
     }
     if (stats) {
-        for (int k = 0; k < 8; ++k) stats[k] = 0.0;
+        for (int k = 0; k < 10; ++k) stats[k] = 0.0;
         for (int t = 0; t < n_ctx; ++t) {
             for (int k : { 0, 1, 2, 6, 7 }) stats[k] += st[t][k];
-            for (int k : { 3, 4, 5 }) stats[k] = std::max(stats[k], st[t][k]);
+            for (int k : { 3, 4, 5, 8, 9 }) stats[k] = std::max(stats[k], st[t][k]);
         }
     }
     return 0;
