@@ -233,11 +233,11 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1 << 19, help="states (and edges) timed on the CPU oracle")
     ap.add_argument("--ref-sample", type=int, default=1 << 17)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--plan-queries", type=int, default=512, help="planning queries per GPU (0 = skip)")
-    ap.add_argument("--plan-concurrent", type=int, default=512)
+    ap.add_argument("--plan-queries", type=int, default=2048, help="planning queries per GPU (0 = skip)")
+    ap.add_argument("--plan-concurrent", type=int, default=2048, help="queries in flight per GPU (one BFS grid each)")
     ap.add_argument("--plan-max-expansions", type=int, default=2000)
     ap.add_argument("--plan-cpu-queries", type=int, default=12)
-    ap.add_argument("--plan-threads", type=int, default=8, help="planner threads (= contexts) per GPU, capped by the host cores")
+    ap.add_argument("--plan-threads", type=int, default=0, help="planner threads (= contexts) per GPU; 0 = 75 %% of the rank's cores, at most 12")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "smpl_b200" else args.warmup
 
@@ -394,9 +394,9 @@ def main():
         starts_all, goals_all = scenes.tabletop_queries(nq_total, seed=13)
         mine = sharding.round_robin_shard(nq_total, rank, world)   # no collective
         # one planner thread per context (the reference's threading model), all on this rank's GPU
-        # planner threads spin on their streams: beyond ~40 % of the rank's cores the CUDA / NCCL helper threads starve
-        # and the rounds become erratic (measured: 6 of 16 cores 700 q/s, 8 of 16 cores 200-340 q/s)
-        n_thr = max(1, min(args.plan_threads, int(0.4 * (os.cpu_count() or 1) / max(1, world) + 0.5)))
+        # the planner is bound by the host-side lattice / OPEN-list work once enough queries are in flight
+        # (measured on 16 cores, 2048 queries: 8 threads 916 q/s, 12 threads 1229 q/s)
+        n_thr = args.plan_threads if args.plan_threads > 0 else max(1, min(12, int(0.75 * (os.cpu_count() or 1) / max(1, world))))
         pctxs = [pctx] + [api.clone_context(pctx, pscene, ptables, device=local_rank) for _ in range(n_thr - 1)]
         per_ctx = max(1, (args.plan_concurrent + n_thr - 1) // n_thr)
         # warm-up with the same bank shape: the BFS bank (a scene-level allocation of per_ctx grids per context) is
