@@ -397,6 +397,8 @@ def main():
         # the planner is bound by the host-side lattice / OPEN-list work once enough queries are in flight
         # (measured on 16 cores, 2048 queries: 8 threads 916 q/s, 12 threads 1229 q/s)
         n_thr = args.plan_threads if args.plan_threads > 0 else max(1, min(12, int(0.75 * (os.cpu_count() or 1) / max(1, world))))
+        # a context's BFS bank keeps int node indices (<= 611 slots of 150^3): enough contexts for the queries in flight
+        n_thr = max(n_thr, (args.plan_concurrent + 511) // 512)
         pctxs = [pctx] + [api.clone_context(pctx, pscene, ptables, device=local_rank) for _ in range(n_thr - 1)]
         per_ctx = max(1, (args.plan_concurrent + n_thr - 1) // n_thr)
         # warm-up with the same bank shape: the BFS bank (a scene-level allocation of per_ctx grids per context) is

@@ -264,6 +264,10 @@ int smplgpu_fk_sphere_centers_f32(smplgpu_ctx* ctx, const double* q, int n, floa
  * The slots are stacked along z in ONE padded grid, so a single wavefront launch runs every
  * slot's search at once.  Returns the wall count of one slot. */
 int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radius);
+/* Largest n_slots smplgpu_bfs_bank_create accepts for the current distance field: the stacked grid keeps the
+ * reference's `int` node indices (bfs3d.h:213-220), so slots * padded cells must stay below 2^31, and the
+ * bank must fit in the free device memory.  Callers clamp their concurrency to it. */
+int smplgpu_bfs_bank_max_slots(smplgpu_ctx* ctx);
 /* BFS_3D::run for every slot: seeds_xyz[n_slots][3]; a slot whose seed is out of bounds is left undiscovered */
 int smplgpu_bfs_bank_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz);
 /* The same for n listed slots only (slots[n], seeds_xyz[n][3]); the other slots keep their distances, so a

@@ -95,6 +95,7 @@ def gpu_lib():
         L.smplgpu_last_f64_resolved.argtypes = [vp, C.POINTER(C.c_int64)]
         L.smplgpu_fk_sphere_centers_f32.argtypes = [vp, dp, i, C.POINTER(C.c_float)]
         L.smplgpu_bfs_bank_create.argtypes = [vp, i, d]
+        L.smplgpu_bfs_bank_max_slots.argtypes = [vp]
         L.smplgpu_bfs_bank_run.argtypes = [vp, ip]
         L.smplgpu_bfs_bank_run_slots.argtypes = [vp, ip, ip, i]
         L.smplgpu_bfs_bank_distances.argtypes = [vp, ip, ip, i, ip]
@@ -457,6 +458,9 @@ class GpuContext:
     # ---- many queries at once ----
     def bfs_bank_create(self, n_slots, inflation_radius):
         return self._ck(self.L.smplgpu_bfs_bank_create(self.h, int(n_slots), float(inflation_radius)), "bfs_bank_create")
+
+    def bfs_bank_max_slots(self):
+        return self._ck(self.L.smplgpu_bfs_bank_max_slots(self.h), "bfs_bank_max_slots")
 
     def bfs_bank_run(self, seeds):
         s = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 3)

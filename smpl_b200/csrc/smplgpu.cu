@@ -1601,6 +1601,23 @@ int smplgpu_planning_frame_fk(smplgpu_ctx* ctx, const double* q, int n, double* 
 // many queries at once: BFS bank + fused expansion batch
 ///////////////////////////////////////////////////////////////////////////////
 
+int smplgpu_bfs_bank_max_slots(smplgpu_ctx* ctx)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "distance field not set");
+    const long long nx = ctx->grid.nx, ny = ctx->grid.ny, nz = ctx->grid.nz;
+    // (nx+2)(ny+2)(n (nz+2)) <= 2^31 - 1
+    long long by_index = 0x7FFFFFFFLL / ((nx + 2) * (ny + 2)) / (nz + 2);
+    // distances (4 B per padded cell) + four bitmaps + candidate words: ~4.7 B per cell; keep half the free memory
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        size_t have = free_b + (ctx->has_bank ? (size_t)ctx->bank_cells * 5 : 0);
+        long long by_mem = (long long)((double)have * 0.5 / (4.7 * (double)((nx + 2) * (ny + 2) * (nz + 2))));
+        by_index = std::min(by_index, by_mem);
+    }
+    return (int)std::max(1LL, std::min(by_index, 1LL << 20));
+}
+
 int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radius)
 {
     if (!ctx || n_slots <= 0) return SMPLGPU_ERR_INVALID;

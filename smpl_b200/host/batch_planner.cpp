@@ -499,7 +499,10 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         return false;
     };
     const long long resolved0 = smplgpu_expand_batch_resolved(m_ctx);
-    const int n_slots = std::min(m_max_concurrent, nq);
+    // the bank keeps the reference's int node indices and has to fit in device memory: clamp the concurrency to it
+    const int max_slots = smplgpu_bfs_bank_max_slots(m_ctx);
+    if (max_slots < 0) return fail_dev();
+    const int n_slots = std::min(std::min(m_max_concurrent, nq), max_slots);
     if (smplgpu_bfs_bank_create(m_ctx, n_slots, m_cfg.inflation_radius) < 0) return fail_dev();
     // every device / pinned allocation happens here: allocating while other planner threads run would stall
     // their streams (allocation synchronises the device)

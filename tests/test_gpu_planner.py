@@ -45,6 +45,16 @@ def test_bfs_bank_equals_single_runs(tabletop):
     assert np.all((d == -1) | (d == 0x7FFFFFFF))
 
 
+def test_bank_max_slots_bounds_the_stacked_grid(tabletop):
+    """The stacked bank keeps BFS_3D's int node indices (bfs3d.h:213-220): the slot limit the planner clamps to."""
+    scene, o, ctx, tables = tabletop
+    nx, ny, nz = scene.dims
+    m = ctx.bfs_bank_max_slots()
+    assert 1 <= m <= 0x7FFFFFFF // ((nx + 2) * (ny + 2) * (nz + 2))
+    with pytest.raises(api.SmplGpuError):
+        ctx.bfs_bank_create(0x7FFFFFFF // ((nx + 2) * (ny + 2) * (nz + 2)) + 1, scene.inflation_radius)
+
+
 def test_bank_slot_refill_leaves_other_slots_untouched(tabletop):
     scene, o, ctx, tables = tabletop
     ctx.bfs_bank_create(3, scene.inflation_radius)
