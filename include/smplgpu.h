@@ -245,6 +245,12 @@ int smplgpu_planning_frame_fk(smplgpu_ctx* ctx, const double* q, int n, double* 
  * parents and one int per edge cross the bus. */
 int smplgpu_is_mprim_edges_valid(smplgpu_ctx* ctx, const double* q0, const int32_t* prim_id, int n,
                                  const double* deltas, int n_prims, uint8_t* verdict, int32_t* waypoint_counts);
+/* isStateToStateValid for n edges between rows of ONE point table: edge e runs from points[idx_a[e]] to
+ * points[idx_b[e]] (points[n_points][dof]).  Path post-processing asks for many motions between the points of a
+ * path (JointPositionShortcutPathGenerator, post_processing.cpp:99-121; shortcut.hpp:112-283): the points cross
+ * the bus once and an edge costs 8 bytes. */
+int smplgpu_is_indexed_edges_valid(smplgpu_ctx* ctx, const double* points, int n_points, const int32_t* idx_a,
+                                   const int32_t* idx_b, int n, uint8_t* verdict, int32_t* waypoint_counts /*nullable*/);
 
 int smplgpu_bfs_set_mode(smplgpu_ctx* ctx, int mode);
 

@@ -81,10 +81,12 @@ typedef struct smplhost_plan_params
  * stats[10] = rounds, edges submitted, device calls, seconds inside smplgpu_* calls, host seconds, total seconds,
  * BFS bank runs, edges resolved by the double-precision kernels, seconds of set-up device calls (bank, BFS,
  * setStart), longest single wait for a batch.
+ * path_states (nullable) [nq][max_path][dof] = ManipLattice::extractPath (manip_lattice.cpp:2018-2160): the joint
+ * values of every path state, the goal id replaced by the state of the first valid goal-reaching action.
  * Returns 0, or a negative smplgpu error code (smplhost_last_error() has the text). */
 int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* params, const double* starts,
                         const double* goals, int nq, int max_concurrent, int32_t* summary, int32_t* path_ids,
-                        int max_path, double* stats);
+                        int max_path, double* stats, double* path_states);
 
 /* The same with one planner thread per context (the reference's threading model: one CollisionSpace per planner
  * thread): queries are dealt round-robin to n_ctx contexts on the same GPU, each driven by its own host thread
@@ -93,7 +95,7 @@ int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* params, co
  * stats: sums over the contexts, except the seconds entries (maximum). */
 int smplhost_plan_batch_multi(smplgpu_ctx* const* ctxs, int n_ctx, const smplhost_plan_params* params,
                               const double* starts, const double* goals, int nq, int max_concurrent_per_ctx,
-                              int32_t* summary, int32_t* path_ids, int max_path, double* stats);
+                              int32_t* summary, int32_t* path_ids, int max_path, double* stats, double* path_states);
 
 /* ---- drop-in adapters (smpl_b200/host/gpu_adapters.h): the reference's CollisionChecker / RobotModel /
  * RobotHeuristic virtuals implemented over the C ABI.  These shims drive the C++ objects one virtual call at
@@ -119,6 +121,26 @@ int smplhost_rm_compute_planning_link_fk(smplhost_adapters* a, const double* q, 
 int smplhost_heur_update_goal(smplhost_adapters* a, const double xyz[3]);
 int smplhost_heur_goal_heuristic(smplhost_adapters* a, const double* q);
 double smplhost_heur_metric_goal_distance(smplhost_adapters* a, double x, double y, double z);
+
+/* ---- path post-processing over the batched validity path (smpl_b200/host/post_processing.h) ----
+ * Paths are concatenated: path p = points[offsets[p] .. offsets[p+1]) rows of dof joint positions, offsets[0] = 0.
+ * stats[5] (nullable) = motions checked, states checked, device calls, seconds inside smplgpu_* calls, host seconds. */
+/* ShortcutPath(rm, cc, pin, pout, type) (smpl/src/post_processing.cpp:284-365) for n_paths paths at once: every
+ * candidate motion (all point pairs of every path) is checked in ONE smplgpu_is_indexed_edges_valid call, then
+ * shortcut::ShortcutPath (and, for type 1, DivideAndConquerShortcutPath; the cheaper result wins) runs per path.
+ * type 0 = ShortcutType::JOINT_SPACE, 1 = JOINT_POSITION_VELOCITY_SPACE; continuous[dof] = !RobotModel::hasPosLimit.
+ * out_idx (room for offsets[n_paths] ints) / out_offsets[n_paths+1]: the points each shortcut path keeps, as
+ * indices into its input path. */
+int smplhost_shortcut_paths(smplgpu_ctx* ctx, int dof, const uint8_t* continuous, const double* points,
+                            const int32_t* offsets, int n_paths, int type, int32_t* out_idx, int32_t* out_offsets,
+                            double* stats);
+/* InterpolatePath(cc, path) (post_processing.cpp:476-540) for n_paths paths at once: the waypoints of every
+ * segment (CollisionChecker::interpolatePath) are checked in ONE smplgpu_is_states_valid call; a segment whose
+ * waypoints are all valid is replaced by them, otherwise its end point is kept.  Returns the total number of
+ * output points (written to out_points[max_points][dof], out_offsets[n_paths+1]); with out_points == NULL only
+ * counts; SMPLGPU_ERR_LIMIT when max_points is too small. */
+int smplhost_interpolate_paths(smplgpu_ctx* ctx, smplhost_tables* tables, const double* points, const int32_t* offsets,
+                               int n_paths, double* out_points, int max_points, int32_t* out_offsets, double* stats);
 
 #ifdef __cplusplus
 }

@@ -193,10 +193,77 @@ PlanResult ManipLatticePlanner::plan(const std::vector<double>& start, const dou
     res.path_ids = r.path;
     res.cost = r.cost;
     res.success = true;
-    for (int id : res.path_ids) {
-        res.path_states.push_back(m_states[id].state);
-    }
+    extractPath(res.path_ids, res.path_states);
     return res;
+}
+
+/// ManipLattice::extractPath (manip_lattice.cpp:2018-2160): the joint values of every state of an id path.  The
+/// goal id stands for any state satisfying the goal, so its predecessor's actions are applied again and the
+/// cheapest valid one ending in a goal state (strict <, every action costs the same: the first) names the
+/// lattice state whose joint values are reported.
+bool ManipLatticePlanner::extractPath(const std::vector<int>& ids, std::vector<std::vector<double>>& path) const
+{
+    path.clear();
+    if (ids.empty()) {
+        return true;
+    }
+    if (ids.size() == 1) {
+        path.push_back(m_states[ids[0] == m_goal_state_id ? m_start_state_id : ids[0]].state);
+        return true;
+    }
+    if (ids[0] == m_goal_state_id) {
+        return false;
+    }
+    path.push_back(m_states[ids[0]].state);
+    for (size_t i = 1; i < ids.size(); ++i) {
+        const int prev_id = ids[i - 1], curr_id = ids[i];
+        if (prev_id == m_goal_state_id) {
+            return false;
+        }
+        if (curr_id != m_goal_state_id) {
+            path.push_back(m_states[curr_id].state);
+            continue;
+        }
+        const std::vector<double>& parent = m_states[prev_id].state;
+        std::vector<double> pose;
+        m_robot->computePlanningLinkFK(parent, pose);
+        const bool near_goal = m_heur->getMetricGoalDistance(pose[0], pose[1], pose[2]) <= m_params.short_dist_thresh;
+        std::vector<double> succ(parent.size());
+        std::vector<int> coord;
+        int best_cost = std::numeric_limits<int>::max();
+        int best = -1;
+        for (size_t p = 0; p < m_prim_deltas.size(); ++p) {
+            const bool active = m_prim_short[p] ? (m_params.use_short_dist && near_goal)
+                                                : !(m_params.use_short_dist && near_goal);
+            if (!active) {
+                continue;
+            }
+            for (size_t j = 0; j < parent.size(); ++j) {
+                succ[j] = m_prim_deltas[p][j] + parent[j];
+            }
+            if (!isGoal(succ)) {
+                continue;
+            }
+            if (!m_robot->checkJointLimits(succ) || !m_cc->isStateToStateValid(parent, succ)) {
+                continue;   // checkAction
+            }
+            stateToCoord(succ, coord);
+            auto it = m_coord_to_id.find(coord);
+            if (it == m_coord_to_id.end()) {
+                continue;   // the reference asserts the entry exists
+            }
+            const int edge_cost = (int)(1000 * 1.0);
+            if (edge_cost < best_cost) {
+                best_cost = edge_cost;
+                best = it->second;
+            }
+        }
+        if (best < 0) {
+            return false;
+        }
+        path.push_back(m_states[best].state);
+    }
+    return true;
 }
 
 } // namespace oracle

@@ -5,7 +5,7 @@
 // "plan queries/s" on the host:
 //   ManipLattice      smpl/src/graph/manip_lattice.cpp:72-150 (init), 219-313 (GetSuccs),
 //                     1245-1289 (coord <-> state), 1511-1580 (checkAction), 1582-1696 (isGoal),
-//                     1944-1980 (setStart)
+//                     1944-1980 (setStart), 2018-2160 (extractPath)
 //   ManipLatticeActionSpace  smpl/src/graph/manip_lattice_action_space.cpp:201-228 (addMotionPrim),
 //                     376-449 (apply), 507-573 (getAction), 662-691 (mprimActive)
 //   ARAStar           oracle/arastar.h (pinned against the reference's own arastar.cpp)
@@ -89,6 +89,7 @@ private:
     bool isGoal(const std::vector<double>& state) const;
     void getSuccs(int state_id, std::vector<int>& succs, std::vector<int>& costs);
     int goalHeuristic(int state_id) const;
+    bool extractPath(const std::vector<int>& ids, std::vector<std::vector<double>>& path) const;
 
 };
 

@@ -20,6 +20,7 @@
 #include "kdl_model.h"
 #include "arastar.h"
 #include "lattice.h"
+#include "shortcut.h"
 #include "robot_desc.h"
 
 using namespace oracle;
@@ -481,7 +482,8 @@ int oracle_goal_heuristics(oracle_scene* s, const double* q, int n, int32_t* h)
 double oracle_plan(oracle_scene* s, const double* start, const double* goal_xyz,
                    const double* resolutions, const double* mprims, const uint8_t* short_flags, int n_prims,
                    int use_short_dist, double short_dist_thresh, double epsilon, int max_expansions,
-                   const double* xyz_tolerance, int32_t* out_summary, int32_t* path_ids, int max_path)
+                   const double* xyz_tolerance, int32_t* out_summary, int32_t* path_ids, int max_path,
+                   double* path_states /* nullable: [max_path][dof], ManipLattice::extractPath */)
 {
     PlanParams pp;
     pp.resolutions.assign(resolutions, resolutions + s->dof);
@@ -508,6 +510,12 @@ double oracle_plan(oracle_scene* s, const double* start, const double* goal_xyz,
     out_summary[4] = r.num_states;
     for (size_t i = 0; i < r.path_ids.size() && (int)i < max_path; ++i) {
         path_ids[i] = r.path_ids[i];
+    }
+    if (path_states) {
+        for (size_t i = 0; i < r.path_states.size() && (int)i < max_path; ++i) {
+            std::copy(r.path_states[i].begin(), r.path_states[i].end(), path_states + i * (size_t)s->dof);
+        }
+        out_summary[5] = (int)r.path_states.size();
     }
     return std::chrono::duration<double>(t1 - t0).count();
 }
@@ -536,6 +544,94 @@ int oracle_arastar_search(int n, const int* off, const int* dst, const int* cost
         path[i] = r.path[i];
     }
     return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// path post-processing: oracle/shortcut.h
+///////////////////////////////////////////////////////////////////////////////
+
+/// The two shortcut templates on an index path with explicit tables (valid[n][n], pair_cost[n][n]); same
+/// signature as ref_shortcut_path's result (oracle/ref_shortcut_shim.cpp).  algo 0 = greedy, 1 = divide & conquer.
+int oracle_shortcut_table(int n, const double* costs, const uint8_t* valid, const double* pair_cost, int algo,
+                          int granularity, int32_t* out, int max_out)
+{
+    std::vector<double> cvec(costs, costs + (n > 0 ? n - 1 : 0));
+    std::vector<ShortcutGenerator> gens = {
+        [&](int a, int b, double& c) {
+            if (!valid[(size_t)a * n + b]) return false;
+            c = pair_cost[(size_t)a * n + b];
+            return true;
+        } };
+    std::vector<int> result;
+    const bool ok = algo == 0 ? ShortcutPath(n, cvec, gens, result, (size_t)granularity)
+                              : DivideAndConquerShortcutPath(n, cvec, gens, result);
+    if (!ok || (int)result.size() > max_out) {
+        return -1;
+    }
+    std::copy(result.begin(), result.end(), out);
+    return (int)result.size();
+}
+
+/// ShortcutPath(rm, cc, pin, pout, type) (post_processing.cpp:284-365) over the oracle's CollisionSpace, one
+/// isStateToStateValid per generator request like the reference.  continuous[dof] = !RobotModel::hasPosLimit.
+/// Returns the number of output points; out_idx = their indices in the input path; edge_checks (nullable) =
+/// number of isStateToStateValid calls made.
+int oracle_shortcut_path(oracle_scene* s, const double* path, int n, const uint8_t* continuous, int kind,
+                         int32_t* out_idx, int64_t* edge_checks)
+{
+    std::vector<bool> cont(continuous, continuous + s->dof);
+    int64_t checks = 0;
+    auto valid = [&](int a, int b) {
+        ++checks;
+        std::vector<double> q0(path + (size_t)a * s->dof, path + (size_t)(a + 1) * s->dof);
+        std::vector<double> q1(path + (size_t)b * s->dof, path + (size_t)(b + 1) * s->dof);
+        return s->cc->isStateToStateValid(q0, q1, nullptr);
+    };
+    const std::vector<int> idx = ShortcutJointPath(cont, path, n, valid, kind);
+    std::copy(idx.begin(), idx.end(), out_idx);
+    if (edge_checks) *edge_checks = checks;
+    return (int)idx.size();
+}
+
+/// InterpolatePath (post_processing.cpp:476-540): every segment is replaced by the waypoints of
+/// CollisionChecker::interpolatePath when all of them are valid, else its end point is kept.  The reference's
+/// interpolatePath rejects every motion whose end points are WITHIN the limits (collision_space.cpp:592-597,
+/// SURVEY.md section 8a defect 7); that test is left out here and in the product.
+/// out: [max_points][dof]; returns the number of points or -1 when max_points is too small.
+int oracle_interpolate_path(oracle_scene* s, const double* path, int n, double* out, int max_points)
+{
+    const int dof = s->dof;
+    std::vector<std::vector<double>> opath;
+    if (n > 0) {
+        opath.emplace_back(path, path + dof);
+    }
+    for (int i = 0; i + 1 < n; ++i) {
+        std::vector<double> q0(path + (size_t)i * dof, path + (size_t)(i + 1) * dof);
+        std::vector<double> q1(path + (size_t)(i + 1) * dof, path + (size_t)(i + 2) * dof);
+        std::vector<std::vector<double>> ipath;
+        s->cc->edgeWaypoints(q0, q1, ipath);
+        bool collision = false;
+        for (const std::vector<double>& p : ipath) {
+            if (!s->cc->isStateValid(p)) {
+                collision = true;
+                break;
+            }
+        }
+        if (collision) {
+            opath.push_back(q1);
+            continue;
+        }
+        if (!ipath.empty()) {
+            opath.insert(opath.end(), ipath.begin() + 1, ipath.end());
+        }
+    }
+    if ((int)opath.size() > max_points) {
+        return -1;
+    }
+    for (size_t i = 0; i < opath.size(); ++i) {
+        std::copy(opath[i].begin(), opath[i].end(), out + i * (size_t)dof);
+    }
+    return (int)opath.size();
 }
 
 ///////////////////////////////////////////////////////////////////////////////

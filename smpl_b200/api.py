@@ -89,6 +89,7 @@ def gpu_lib():
         L.smplgpu_goal_heuristics_dev.argtypes = [vp, vp, i, i, vp]
         L.smplgpu_planning_frame_fk.argtypes = [vp, dp, i, dp]
         L.smplgpu_is_mprim_edges_valid.argtypes = [vp, dp, ip, i, dp, i, bp, ip]
+        L.smplgpu_is_indexed_edges_valid.argtypes = [vp, dp, i, ip, ip, i, bp, ip]
         L.smplgpu_set_precision_mode.argtypes = [vp, i]
         L.smplgpu_bfs_set_mode.argtypes = [vp, i]
         L.smplgpu_certified_bounds.argtypes = [vp, dp, dp]
@@ -132,9 +133,13 @@ def host_lib():
         H.smplhost_tables_motion_weights.argtypes = [vp, c_double_p, c_int32_p]
         H.smplhost_tables_pairs.argtypes = [vp, c_int32_p, C.c_int]
         H.smplhost_plan_batch.argtypes = [vp, C.POINTER(PlanParamsC), c_double_p, c_double_p, C.c_int, C.c_int,
-                                          c_int32_p, c_int32_p, C.c_int, c_double_p]
+                                          c_int32_p, c_int32_p, C.c_int, c_double_p, c_double_p]
         H.smplhost_plan_batch_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(PlanParamsC), c_double_p, c_double_p,
-                                                C.c_int, C.c_int, c_int32_p, c_int32_p, C.c_int, c_double_p]
+                                                C.c_int, C.c_int, c_int32_p, c_int32_p, C.c_int, c_double_p, c_double_p]
+        H.smplhost_shortcut_paths.argtypes = [vp, C.c_int, c_uint8_p, c_double_p, c_int32_p, C.c_int, C.c_int, c_int32_p,
+                                              c_int32_p, c_double_p]
+        H.smplhost_interpolate_paths.argtypes = [vp, vp, c_double_p, c_int32_p, C.c_int, c_double_p, C.c_int, c_int32_p,
+                                                 c_double_p]
         H.smplhost_adapters_create.restype = C.c_void_p
         H.smplhost_adapters_create.argtypes = [vp, vp, C.c_char_p, c_double_p, C.c_double, c_int32_p, C.c_double, C.c_int]
         H.smplhost_adapters_destroy.argtypes = [vp]
@@ -352,6 +357,17 @@ class GpuContext:
                                                      _ip(c) if want_counts else None), "is_mprim_edges_valid")
         return (v, c) if want_counts else v
 
+    def is_indexed_edges_valid(self, points, idx_a, idx_b, want_counts=True):
+        """Edges points[idx_a[e]] -> points[idx_b[e]] between rows of one point table."""
+        pts = self._q(points)
+        a = np.ascontiguousarray(idx_a, dtype=np.int32)
+        b = np.ascontiguousarray(idx_b, dtype=np.int32)
+        v = np.zeros(len(a), np.uint8)
+        c = np.zeros(len(a), np.int32) if want_counts else None
+        self._ck(self.L.smplgpu_is_indexed_edges_valid(self.h, _dp(pts), len(pts), _ip(a), _ip(b), len(a), _bp(v),
+                                                       _ip(c) if want_counts else None), "is_indexed_edges_valid")
+        return (v, c) if want_counts else v
+
     def is_edges_valid_dev(self, q0_ptr, q1_ptr, n, verdict_ptr, counts_ptr=None):
         self._ck(self.L.smplgpu_is_edges_valid_dev(self.h, C.c_void_p(q0_ptr), C.c_void_p(q1_ptr), int(n),
                                                    C.c_void_p(verdict_ptr), C.c_void_p(counts_ptr) if counts_ptr else None),
@@ -562,7 +578,8 @@ def clone_context(ctx, scene, tables, device=0):
     return c
 
 
-def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max_path=512, n_threads=1):
+def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max_path=512, n_threads=1,
+               want_states=False):
     """smplhost_plan_batch: many ARA* queries in lock step, one device call per round.
     params: smpl_b200.scenes.PlanParams.  Returns (list of dict per query, stats dict).
     `ctx` may be a list of contexts (same GPU, same scene): one planner thread per context
@@ -592,13 +609,15 @@ def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max
     summary = np.zeros((nq, 5), np.int32)
     paths = np.full((nq, max_path), -1, np.int32)
     stats = np.zeros(12)
+    pstates = np.zeros((nq, max_path, dof), np.float64) if want_states else None
+    ps_ptr = _dp(pstates) if want_states else None
     if isinstance(ctx, (list, tuple)):
         arr = (C.c_void_p * len(ctx))(*[c.h for c in ctx])
         r = H.smplhost_plan_batch_multi(arr, len(ctx), C.byref(P), _dp(starts), _dp(goals), nq, int(max_concurrent),
-                                        _ip(summary), _ip(paths), int(max_path), _dp(stats))
+                                        _ip(summary), _ip(paths), int(max_path), _dp(stats), ps_ptr)
     else:
         r = H.smplhost_plan_batch(ctx.h, C.byref(P), _dp(starts), _dp(goals), nq, int(max_concurrent), _ip(summary),
-                                  _ip(paths), int(max_path), _dp(stats))
+                                  _ip(paths), int(max_path), _dp(stats), ps_ptr)
     if r != 0:
         raise SmplGpuError("plan_batch: " + H.smplhost_last_error().decode())
     out = []
@@ -606,11 +625,63 @@ def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max
         n = int(summary[i, 3])
         out.append(dict(success=bool(summary[i, 0]), expansions=int(summary[i, 1]), cost=int(summary[i, 2]),
                         path_ids=paths[i, :min(n, max_path)].copy(), num_states=int(summary[i, 4])))
+        if want_states:   # ManipLattice::extractPath: joint values of the path states
+            out[-1]["path_states"] = pstates[i, :min(n, max_path)].copy()
     st = dict(rounds=int(stats[0]), edges_submitted=int(stats[1]), device_calls=int(stats[2]),
               device_seconds=float(stats[3]), host_seconds=float(stats[4]), total_seconds=float(stats[5]),
               bfs_runs=int(stats[6]), edges_resolved_f64=int(stats[7]), setup_seconds=float(stats[8]),
               max_wait_seconds=float(stats[9]), n_threads=int(n_threads))
     return out, st
+
+
+def _concat_paths(paths, dof):
+    pts = [np.ascontiguousarray(p, dtype=np.float64).reshape(-1, dof) for p in paths]
+    offsets = np.zeros(len(pts) + 1, np.int32)
+    offsets[1:] = np.cumsum([len(p) for p in pts])
+    flat = np.ascontiguousarray(np.concatenate(pts) if pts else np.zeros((0, dof)), dtype=np.float64)
+    return flat, offsets
+
+
+def shortcut_paths(ctx, tables, paths, kind=0):
+    """smplhost_shortcut_paths: ShortcutPath (post_processing.cpp:284-365) for a list of joint-space paths; every
+    candidate motion is checked in one device call.  kind 0 = JOINT_SPACE, 1 = JOINT_POSITION_VELOCITY_SPACE.
+    Returns (list of index arrays -- the points each shortcut path keeps, stats dict)."""
+    H = host_lib()
+    dof = tables.dof
+    flat, offsets = _concat_paths(paths, dof)
+    _, _, cont = tables.limits()
+    cont = np.ascontiguousarray(cont, dtype=np.uint8)
+    out_idx = np.zeros(max(1, int(offsets[-1])), np.int32)
+    out_off = np.zeros(len(offsets), np.int32)
+    stats = np.zeros(5)
+    r = H.smplhost_shortcut_paths(ctx.h, dof, _bp(cont), _dp(flat), _ip(offsets), len(paths), int(kind), _ip(out_idx),
+                                  _ip(out_off), _dp(stats))
+    if r != 0:
+        raise SmplGpuError("shortcut_paths: " + H.smplhost_last_error().decode())
+    st = dict(edges_checked=int(stats[0]), states_checked=int(stats[1]), device_calls=int(stats[2]),
+              device_seconds=float(stats[3]), host_seconds=float(stats[4]))
+    return [out_idx[out_off[i]:out_off[i + 1]].copy() for i in range(len(paths))], st
+
+
+def interpolate_paths(ctx, tables, paths):
+    """smplhost_interpolate_paths: InterpolatePath (post_processing.cpp:476-540) for a list of joint-space paths; the
+    waypoints of every segment are checked in one device call.  Returns (list of point arrays, stats dict)."""
+    H = host_lib()
+    dof = tables.dof
+    flat, offsets = _concat_paths(paths, dof)
+    out_off = np.zeros(len(offsets), np.int32)
+    stats = np.zeros(5)
+    total = H.smplhost_interpolate_paths(ctx.h, tables.h, _dp(flat), _ip(offsets), len(paths), None, 0, _ip(out_off), None)
+    if total < 0:
+        raise SmplGpuError("interpolate_paths: " + H.smplhost_last_error().decode())
+    out = np.zeros((max(1, total), dof), np.float64)
+    r = H.smplhost_interpolate_paths(ctx.h, tables.h, _dp(flat), _ip(offsets), len(paths), _dp(out), max(1, total),
+                                     _ip(out_off), _dp(stats))
+    if r < 0:
+        raise SmplGpuError("interpolate_paths: " + H.smplhost_last_error().decode())
+    st = dict(edges_checked=int(stats[0]), states_checked=int(stats[1]), device_calls=int(stats[2]),
+              device_seconds=float(stats[3]), host_seconds=float(stats[4]))
+    return [out[out_off[i]:out_off[i + 1]].copy() for i in range(len(paths))], st
 
 
 def world_to_grid(points, origin, res):

@@ -1189,6 +1189,56 @@ int smplgpu_is_mprim_edges_valid(smplgpu_ctx* ctx, const double* q0, const int32
     return run_host_batched(ctx, q0, nullptr, n, verdict, waypoint_counts, prim_id, ctx->d_deltas, n_prims);
 }
 
+int smplgpu_is_indexed_edges_valid(smplgpu_ctx* ctx, const double* points, int n_points, const int32_t* idx_a,
+                                   const int32_t* idx_b, int n, uint8_t* verdict, int32_t* waypoint_counts)
+{
+    if (!ctx || n < 0 || n_points < 0) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (n == 0) return 0;
+    if (!points || !idx_a || !idx_b || !verdict) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    for (int e = 0; e < n; ++e) {
+        if (idx_a[e] < 0 || idx_a[e] >= n_points || idx_b[e] < 0 || idx_b[e] >= n_points)
+            return fail(ctx, SMPLGPU_ERR_INVALID, "edge %d: point index out of range", e);
+    }
+    const int dof = ctx->h_model->dof;
+    // resident for the whole call: the point table, the index pairs, every verdict (and waypoint count)
+    const size_t pb = (((size_t)n_points * dof * sizeof(double)) + 255) / 256 * 256;
+    const size_t ib = (((size_t)n * sizeof(int)) + 255) / 256 * 256;
+    const size_t vb = ((size_t)n + 255) / 256 * 256;
+    r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, pb + 2 * ib + vb + (waypoint_counts ? ib : 0));
+    if (r) return r;
+    uint8_t* base = (uint8_t*)ctx->d_misc;
+    double* d_points = (double*)base;
+    int* d_a = (int*)(base + pb);
+    int* d_b = (int*)(base + pb + ib);
+    uint8_t* d_v = base + pb + 2 * ib;
+    int* d_c = waypoint_counts ? (int*)(base + pb + 2 * ib + vb) : nullptr;
+    const int chunk = 1 << 18;
+    const int cn = std::min(n, chunk);
+    r = ensure_state_buffers(ctx, (size_t)cn, dof, true);
+    if (r) return r;
+    CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemcpyAsync(d_points, points, (size_t)n_points * dof * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_a, idx_a, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_b, idx_b, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    for (int off = 0; off < n; off += chunk) {
+        const int m = std::min(chunk, n - off);
+        const size_t total = (size_t)m * dof;
+        gather_edges_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_points, d_a + off, d_b + off, dof, m,
+                                                                                       ctx->d_q0, ctx->d_q1);
+        ++ctx->launches;
+        r = launch_edges(ctx, ctx->d_q0, ctx->d_q1, m, d_v + off, d_c ? d_c + off : nullptr);
+        if (r) return r;
+    }
+    CU(cudaMemcpyAsync(verdict, d_v, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (waypoint_counts) {
+        CU(cudaMemcpyAsync(waypoint_counts, d_c, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int smplgpu_set_precision_mode(smplgpu_ctx* ctx, int mode)
 {
     if (!ctx) return SMPLGPU_ERR_INVALID;

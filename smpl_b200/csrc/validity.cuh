@@ -465,6 +465,21 @@ __global__ void apply_mprims_kernel(const double* __restrict__ q0, const int* __
     q1[i] = (p >= 0 && p < n_prims) ? deltas[(size_t)p * dof + v] + a : a;
 }
 
+// Edges between rows of a point table (path post-processing: every (i, j) pair of a path's points is a candidate
+// shortcut, post_processing.cpp:99-121): q0[e] = points[a[e]], q1[e] = points[b[e]]
+__global__ void gather_edges_kernel(const double* __restrict__ points, const int* __restrict__ a,
+                                    const int* __restrict__ b, int dof, int n,
+                                    double* __restrict__ q0, double* __restrict__ q1)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * dof) {
+        return;
+    }
+    const int e = (int)(i / dof), v = (int)(i - (size_t)e * dof);
+    q0[i] = points[(size_t)a[e] * dof + v];
+    q1[i] = points[(size_t)b[e] * dof + v];
+}
+
 // Kernel (1) alone: sphere centres of every tree node, out[n][n_nodes][3]
 __global__ void __launch_bounds__(VALIDITY_THREADS)
 fk_centers_kernel(const DevModel* __restrict__ M, const double* __restrict__ q, int n, double* __restrict__ out)

@@ -288,6 +288,29 @@ void BatchPlanner::finish(Query& Q, bool found)
     std::reverse(Q.result.path_ids.begin(), Q.result.path_ids.end());
     Q.result.cost = Q.search[0].g;
     Q.result.success = true;
+    // ManipLattice::extractPath (manip_lattice.cpp:2018-2160)
+    const int dof = m_cfg.dof;
+    const std::vector<int>& ids = Q.result.path_ids;
+    Q.result.path_states.assign(ids.size() * (size_t)dof, 0.0);
+    for (size_t i = 0; i < ids.size(); ++i) {
+        int id = ids[i];
+        if (id == 0) {   // the goal state id stands for "any state satisfying the goal"
+            id = -1;
+            if (i > 0) {
+                for (const std::pair<int, int>& gs : Q.goal_succ) {
+                    if (gs.first == ids[i - 1]) {
+                        id = gs.second;
+                        break;
+                    }
+                }
+            }
+            if (id < 0) {
+                Q.result.path_states.resize(i * (size_t)dof);   // cannot happen for a found path; keep what is known
+                break;
+            }
+        }
+        std::copy(Q.lat.q(id), Q.lat.q(id) + dof, Q.result.path_states.begin() + i * (size_t)dof);
+    }
 }
 
 ///////////////////////////////////////////////////////////////////////////////
@@ -461,6 +484,9 @@ void BatchPlanner::absorbOne(Query& Q, const uint8_t* verdict, const int32_t* h,
         const bool is_goal = std::fabs(off[3 * e] - Q.goal[0]) <= m_cfg.xyz_tolerance[0] &&
                              std::fabs(off[3 * e + 1] - Q.goal[1]) <= m_cfg.xyz_tolerance[1] &&
                              std::fabs(off[3 * e + 2] - Q.goal[2]) <= m_cfg.xyz_tolerance[2];
+        if (is_goal && (Q.goal_succ.empty() || Q.goal_succ.back().first != Q.expanding)) {
+            Q.goal_succ.emplace_back(Q.expanding, succ_id);   // first valid goal action of this expansion
+        }
         const int target = is_goal ? 0 : succ_id;
         sstate(Q, target);
         touch(Q, target);

@@ -60,6 +60,9 @@ struct QueryResult
     int cost = 0;
     int num_states = 0;
     std::vector<int> path_ids;
+    // ManipLattice::extractPath (manip_lattice.cpp:2018-2160): the joint-space state of every path id; the goal id
+    // is replaced by the lattice state of the first valid goal-reaching action of its predecessor
+    std::vector<double> path_states;   // path_ids.size() x dof
 };
 
 struct BatchStats
@@ -124,6 +127,9 @@ private:
         int expanding;         // state popped this round
         bool done;
         QueryResult result;
+        // (expanded state, lattice id of its first valid successor that satisfied the goal): what extractPath's
+        // "cheapest valid goal action" search finds, every action costing the same (manip_lattice.cpp:2098-2124)
+        std::vector<std::pair<int, int>> goal_succ;
         // this round's successors (filled by expandOne, consumed by absorbOne)
         std::vector<double> succ_q1;
         int n_succ;

@@ -13,6 +13,7 @@
 #include "../../include/smplhost.h"
 #include "batch_planner.h"
 #include "gpu_adapters.h"
+#include "post_processing.h"
 #include "robot_tables.h"
 
 using smplhost::RobotTables;
@@ -200,7 +201,7 @@ int smplhost_tables_pairs(smplhost_tables* h, int32_t* out, int max_pairs)
 
 int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* p, const double* starts,
                         const double* goals, int nq, int max_concurrent, int32_t* summary, int32_t* path_ids,
-                        int max_path, double* stats)
+                        int max_path, double* stats, double* path_states)
 {
     if (!ctx || !p || nq < 0 || (nq > 0 && (!starts || !goals || !summary))) {
         g_err = "smplhost_plan_batch: null argument";
@@ -253,6 +254,10 @@ int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* p, const d
                 path_ids[(size_t)i * max_path + k] = k < (int)r.path_ids.size() ? r.path_ids[k] : -1;
             }
         }
+        if (path_states) {
+            const size_t m = std::min(r.path_states.size(), (size_t)max_path * p->dof);
+            std::copy(r.path_states.begin(), r.path_states.begin() + m, path_states + (size_t)i * max_path * p->dof);
+        }
     }
     if (stats) {
         const smplhost::BatchStats& s = planner.stats();
@@ -272,14 +277,15 @@ int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* p, const d
 
 int smplhost_plan_batch_multi(smplgpu_ctx* const* ctxs, int n_ctx, const smplhost_plan_params* p,
                               const double* starts, const double* goals, int nq, int max_concurrent_per_ctx,
-                              int32_t* summary, int32_t* path_ids, int max_path, double* stats)
+                              int32_t* summary, int32_t* path_ids, int max_path, double* stats, double* path_states)
 {
     if (!ctxs || n_ctx <= 0 || !p || nq < 0) {
         g_err = "smplhost_plan_batch_multi: bad argument";
         return SMPLGPU_ERR_INVALID;
     }
     if (n_ctx == 1) {
-        return smplhost_plan_batch(ctxs[0], p, starts, goals, nq, max_concurrent_per_ctx, summary, path_ids, max_path, stats);
+        return smplhost_plan_batch(ctxs[0], p, starts, goals, nq, max_concurrent_per_ctx, summary, path_ids, max_path, stats,
+                                   path_states);
     }
     const int dof = p->dof;
     std::vector<int> rc(n_ctx, 0);
@@ -306,10 +312,13 @@ int smplhost_plan_batch_multi(smplgpu_ctx* const* ctxs, int n_ctx, const smplhos
                 std::copy(goals + (size_t)mine[k] * 3, goals + (size_t)(mine[k] + 1) * 3, g.begin() + (size_t)k * 3);
             }
             std::vector<int32_t> sum((size_t)m * 5), paths(path_ids ? (size_t)m * max_path : 0);
+            const size_t ps = (size_t)max_path * dof;
+            std::vector<double> pstates(path_states ? (size_t)m * ps : 0);
             smplhost_plan_params pt = *p;
             pt.n_threads = 1;
             rc[t] = smplhost_plan_batch(ctxs[t], &pt, s.data(), g.data(), m, max_concurrent_per_ctx, sum.data(),
-                                        path_ids ? paths.data() : nullptr, max_path, st[t].data());
+                                        path_ids ? paths.data() : nullptr, max_path, st[t].data(),
+                                        path_states ? pstates.data() : nullptr);
             if (rc[t] != 0) {
                 errs[t] = g_err;   // thread-local: copy it out
                 return;
@@ -319,6 +328,10 @@ int smplhost_plan_batch_multi(smplgpu_ctx* const* ctxs, int n_ctx, const smplhos
                 if (path_ids) {
                     std::copy(paths.begin() + (size_t)k * max_path, paths.begin() + (size_t)(k + 1) * max_path,
                               path_ids + (size_t)mine[k] * max_path);
+                }
+                if (path_states) {
+                    std::copy(pstates.begin() + (size_t)k * ps, pstates.begin() + (size_t)(k + 1) * ps,
+                              path_states + (size_t)mine[k] * ps);
                 }
             }
         });
@@ -485,6 +498,78 @@ double smplhost_heur_metric_goal_distance(smplhost_adapters* a, double x, double
 {
     if (!a) return -1.0;
     return a->heur->getMetricGoalDistance(x, y, z);
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// path post-processing (post_processing.h)
+///////////////////////////////////////////////////////////////////////////////
+
+static void copy_post_stats(const smplhost::PostProcessingStats& st, double* stats)
+{
+    if (stats) {
+        stats[0] = (double)st.edges_checked;
+        stats[1] = (double)st.states_checked;
+        stats[2] = (double)st.device_calls;
+        stats[3] = st.device_seconds;
+        stats[4] = st.host_seconds;
+    }
+}
+
+int smplhost_shortcut_paths(smplgpu_ctx* ctx, int dof, const uint8_t* continuous, const double* points,
+                            const int32_t* offsets, int n_paths, int type, int32_t* out_idx, int32_t* out_offsets,
+                            double* stats)
+{
+    if (!ctx || dof <= 0 || n_paths < 0 || (n_paths > 0 && (!continuous || !points || !offsets || !out_idx || !out_offsets))) {
+        g_err = "smplhost_shortcut_paths: bad argument";
+        return SMPLGPU_ERR_INVALID;
+    }
+    if (type != smplhost::SHORTCUT_JOINT_SPACE && type != smplhost::SHORTCUT_JOINT_POSITION_VELOCITY_SPACE) {
+        g_err = "smplhost_shortcut_paths: only the joint-space shortcut types run here (EUCLID_SPACE needs the IK plugin)";
+        return SMPLGPU_ERR_INVALID;
+    }
+    for (int p = 0; p < n_paths; ++p) {
+        if (offsets[p + 1] < offsets[p] || offsets[0] != 0) {
+            g_err = "smplhost_shortcut_paths: offsets must start at 0 and not decrease";
+            return SMPLGPU_ERR_INVALID;
+        }
+    }
+    std::vector<int32_t> idx, off;
+    smplhost::PostProcessingStats st;
+    std::string err;
+    if (!smplhost::ShortcutPaths(ctx, dof, continuous, points, offsets, n_paths, type, idx, off, &st, &err)) {
+        g_err = err;
+        return SMPLGPU_ERR_CUDA;
+    }
+    std::copy(idx.begin(), idx.end(), out_idx);
+    std::copy(off.begin(), off.end(), out_offsets);
+    copy_post_stats(st, stats);
+    return 0;
+}
+
+int smplhost_interpolate_paths(smplgpu_ctx* ctx, smplhost_tables* tables, const double* points, const int32_t* offsets,
+                               int n_paths, double* out_points, int max_points, int32_t* out_offsets, double* stats)
+{
+    if (!ctx || !tables || n_paths < 0 || (n_paths > 0 && (!points || !offsets || !out_offsets))) {
+        g_err = "smplhost_interpolate_paths: bad argument";
+        return SMPLGPU_ERR_INVALID;
+    }
+    const smplgpu_robot_desc* d = tables->t.desc();
+    std::vector<double> pts;
+    std::vector<int32_t> off;
+    smplhost::PostProcessingStats st;
+    std::string err;
+    if (!smplhost::InterpolatePaths(ctx, d->dof, d->var_type, d->var_motion_weight, points, offsets, n_paths, pts, off, &st, &err)) {
+        g_err = err;
+        return SMPLGPU_ERR_CUDA;
+    }
+    std::copy(off.begin(), off.end(), out_offsets);
+    copy_post_stats(st, stats);
+    const int total = (int)(pts.size() / d->dof);
+    if (total > max_points || !out_points) {
+        return total > 0 && out_points ? SMPLGPU_ERR_LIMIT : total;   // call again with room for out_offsets[n_paths] points
+    }
+    std::copy(pts.begin(), pts.end(), out_points);
+    return total;
 }
 
 } // extern "C"

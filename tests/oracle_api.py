@@ -166,6 +166,42 @@ def arastar_search(which, off, dst, cost, h, start, goal, eps, max_expansions, m
     return dict(found=bool(out[0]), cost=int(out[1]), expansions=int(out[2]), path=path[:min(n, max_path)].copy())
 
 
+_REF_SC = None
+
+
+def ref_shortcut_lib():
+    """The reference's own shortcut templates (smpl/geometry/shortcut.h instantiated by oracle/ref_shortcut_shim.cpp,
+    compiled from /root/reference), or None."""
+    global _REF_SC
+    if _REF_SC is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_shortcut.so")
+        if not os.path.exists(path):
+            return None
+        _REF_SC = C.CDLL(path)
+    return _REF_SC
+
+
+def shortcut_table(which, costs, valid, pair_cost, algo, granularity=1):
+    """shortcut::ShortcutPath (algo 0) / DivideAndConquerShortcutPath (algo 1) on an index path of n points:
+    costs[n-1] of the original segments, valid[n][n] and pair_cost[n][n] = the generator's answer for (i, j).
+    which = "oracle" (oracle/shortcut.h) or "reference".  Returns the output indices, or None on failure."""
+    costs = np.ascontiguousarray(costs, dtype=np.float64)
+    n = len(costs) + 1 if len(valid) else 0
+    valid = np.ascontiguousarray(valid, dtype=np.uint8).reshape(n, n)
+    pair_cost = np.ascontiguousarray(pair_cost, dtype=np.float64).reshape(n, n)
+    out = np.zeros(max(2 * n, 4), np.int32)
+    if which == "reference":
+        VF = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_void_p)
+        CF = C.CFUNCTYPE(C.c_double, C.c_int, C.c_int, C.c_void_p)
+        vf = VF(lambda a, b, u: int(valid[a, b]))
+        cf = CF(lambda a, b, u: float(pair_cost[a, b]))
+        r = ref_shortcut_lib().ref_shortcut_path(n, _dp(costs), vf, cf, None, int(algo), int(granularity), _ip(out), len(out))
+    else:
+        r = lib().oracle_shortcut_table(n, _dp(costs), _bp(valid), _dp(pair_cost), int(algo), int(granularity),
+                                        _ip(out), len(out))
+    return None if r < 0 else out[:r].copy()
+
+
 class OracleScene:
     def __init__(self, robot_path, group, planning_joints, origin, size, res, max_dist):
         L = lib()
@@ -388,6 +424,25 @@ class OracleScene:
         return h
 
 
+    def shortcut_path(self, path, continuous, kind=0):
+        """ShortcutPath(rm, cc, pin, pout, type) (post_processing.cpp:284-365): indices of the shortcut path's
+        points and the number of isStateToStateValid calls made.  kind 0 = JOINT_SPACE, 1 = JOINT_POSITION_VELOCITY_SPACE."""
+        path = self._q(path)
+        cont = np.ascontiguousarray(continuous, dtype=np.uint8)
+        out = np.zeros(max(len(path), 1), np.int32)
+        checks = C.c_int64(0)
+        n = self.L.oracle_shortcut_path(self.h, _dp(path), len(path), _bp(cont), int(kind), _ip(out), C.byref(checks))
+        return out[:n].copy(), int(checks.value)
+
+    def interpolate_path(self, path, max_points=1 << 16):
+        """InterpolatePath (post_processing.cpp:476-540)."""
+        path = self._q(path)
+        out = np.zeros((max_points, path.shape[1]), np.float64)
+        n = self.L.oracle_interpolate_path(self.h, _dp(path), len(path), _dp(out), max_points)
+        if n < 0:
+            raise RuntimeError("interpolate_path: more than %d points" % max_points)
+        return out[:n].copy()
+
     def plan(self, start, goal_xyz, params, max_path=4096):
         """params: smpl_b200.scenes.PlanParams.  Returns dict(success, expansions, cost, path_ids, num_states, seconds)."""
         start = np.ascontiguousarray(start, dtype=np.float64)
@@ -398,12 +453,14 @@ class OracleScene:
         tol = np.ascontiguousarray(params.xyz_tolerance, dtype=np.float64)
         summary = np.zeros(8, np.int32)
         path = np.zeros(max_path, np.int32)
+        pstates = np.zeros((max_path, len(start)), np.float64)
         secs = self.L.oracle_plan(self.h, _dp(start), _dp(goal), _dp(res), _dp(prims), _bp(flags), len(prims),
                                   int(params.use_short_dist), C.c_double(params.short_dist_thresh),
                                   C.c_double(params.epsilon), int(params.max_expansions), _dp(tol),
-                                  _ip(summary), _ip(path), max_path)
+                                  _ip(summary), _ip(path), max_path, _dp(pstates))
         n = int(summary[3])
-        return dict(success=bool(summary[0]), expansions=int(summary[1]), cost=int(summary[2]),
+        assert int(summary[5]) == n, "extractPath failed"
+        return dict(path_states=pstates[:min(n, max_path)].copy(), success=bool(summary[0]), expansions=int(summary[1]), cost=int(summary[2]),
                     path_ids=path[:min(n, max_path)].copy(), num_states=int(summary[4]), seconds=float(secs))
 
 

@@ -66,6 +66,19 @@ def gen_arastar():
     np.savez_compressed(os.path.join(OUT, "arastar_reference.npz"), **out)
 
 
+def gen_shortcut():
+    """shortcut_reference.npz -- outputs of the REFERENCE's own shortcut templates (oracle/_ref/libref_shortcut.so)
+    on the tables of tests/test_oracle_shortcut.py."""
+    from oracle_api import shortcut_table
+    import test_oracle_shortcut as T
+    out = {}
+    for k, (seed, algo, gran) in enumerate(T.CASES):
+        costs, valid, pair = T.table_case(seed)
+        out["out_%d" % k] = shortcut_table("reference", costs, valid, pair, algo, gran)
+    np.savez_compressed(os.path.join(OUT, "shortcut_reference.npz"), **out)
+    print("shortcut: %d cases" % len(T.CASES))
+
+
 def gen_distmap():
     """distmap_reference.npz -- fields of the REFERENCE's own EuclidDistanceMap (oracle/_ref/libref_distmap.so)."""
     from oracle_api import RefDistanceMap
@@ -133,6 +146,7 @@ def gen_ubr1():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["bfs", "pr2", "ubr1", "plans", "arastar", "distmap"]
+    which = sys.argv[1:] or ["bfs", "pr2", "ubr1", "plans", "arastar", "distmap", "shortcut"]
     for name in which:
-        {"bfs": gen_bfs, "pr2": gen_pr2, "ubr1": gen_ubr1, "plans": gen_plans, "arastar": gen_arastar, "distmap": gen_distmap}[name]()
+        {"bfs": gen_bfs, "pr2": gen_pr2, "ubr1": gen_ubr1, "plans": gen_plans, "arastar": gen_arastar, "distmap": gen_distmap,
+         "shortcut": gen_shortcut}[name]()
