@@ -222,6 +222,25 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def wandering_paths(anchors, n_paths, dof, seed):
+    """Joint-space paths for the shortcut leg: random walks of small steps, jittered straight lines and detours
+    between valid states (20 to 60 points), the shapes tests/test_gpu_postprocessing.py checks against the oracle."""
+    rng = np.random.default_rng(seed)
+    paths = []
+    for p in range(n_paths):
+        m = int(rng.integers(20, 61))
+        a, b = anchors[rng.integers(0, len(anchors), 2)]
+        if p % 3 == 0:
+            pts = a + np.cumsum(rng.normal(0.0, 0.06, (m, dof)), axis=0)
+        elif p % 3 == 1:
+            pts = a + np.linspace(0.0, 1.0, m)[:, None] * (b - a) * 0.5 + rng.normal(0.0, 0.02, (m, dof))
+        else:
+            t = np.concatenate([np.linspace(0, 1, m // 2 + 1), np.linspace(1, 0.2, m - m // 2 - 1)])[:, None]
+            pts = a + t * (b - a) * 0.4
+        paths.append(np.ascontiguousarray(pts[:m]))
+    return paths
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -237,6 +256,8 @@ def main():
     ap.add_argument("--plan-concurrent", type=int, default=2048, help="queries in flight per GPU (one BFS grid each)")
     ap.add_argument("--plan-max-expansions", type=int, default=2000)
     ap.add_argument("--plan-cpu-queries", type=int, default=12)
+    ap.add_argument("--post-paths", type=int, default=1024, help="joint-space paths shortcut in one call (0 = skip)")
+    ap.add_argument("--post-cpu-paths", type=int, default=48)
     ap.add_argument("--plan-threads", type=int, default=0, help="planner threads (= contexts) per GPU; 0 = 75 %% of the rank's cores, at most 12")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "smpl_b200" else args.warmup
@@ -381,7 +402,22 @@ def main():
                "mvoxel_s": nb ** 3 / (bfs_ms * 1e-3) / 1e6,
                "algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (bfs_ms * 1e-3) / 1e9}
 
-    clocks = sampler.stop() if rank == 0 else None   # sampled across the validity, end-to-end and BFS regions
+    # ---- path post-processing: shortcut many paths with ONE batch of candidate motions ----
+    post = None
+    post_paths = None
+    if rank == 0 and args.post_paths > 0:
+        post_paths = wandering_paths(q[d_v.cpu().numpy().astype(bool)], args.post_paths, dof, seed=5)
+        api.shortcut_paths(ctx, tables, post_paths[:8], kind=0)
+        t0 = time.perf_counter()
+        short, pst = api.shortcut_paths(ctx, tables, post_paths, kind=0)
+        dt = time.perf_counter() - t0
+        post = {"paths": len(post_paths), "points": int(sum(len(p) for p in post_paths)),
+                "points_after": int(sum(len(g) for g in short)), "candidate_motions": pst["edges_checked"],
+                "seconds": dt, "device_seconds": pst["device_seconds"], "paths_per_s": len(post_paths) / dt,
+                "call": "smplhost_shortcut_paths (ShortcutPath JOINT_SPACE): all point pairs of every path in one "
+                        "smplgpu_is_indexed_edges_valid call", "_short": short}
+
+    clocks = sampler.stop() if rank == 0 else None   # sampled across the validity, end-to-end, BFS and shortcut regions
 
     # ---- plan queries/s (config[0]/[3] shape): PR2 right arm on the tabletop scene, queries sharded over ranks ----
     plan = None
@@ -480,6 +516,17 @@ def main():
             plan["cpu_queries_per_s"] = k / secs
             plan["cpu_expansions_per_s"] = cexp / secs
             plan["cpu_sample"] = "first %d queries, oracle ManipLattice + ARA*, 1 thread" % k
+        if post is not None:
+            k = min(args.post_cpu_paths, len(post_paths))
+            t0 = time.perf_counter()
+            same = 0
+            for p_, g_ in zip(post_paths[:k], post["_short"][:k]):
+                ref_idx, _ = o.shortcut_path(p_, cont, kind=0)
+                same += int(np.array_equal(ref_idx, g_))
+            dt = time.perf_counter() - t0
+            post["cpu_paths_per_s"] = k / dt
+            post["cpu_sample"] = "first %d paths, oracle ShortcutPath (one isStateToStateValid per request), 1 thread" % k
+            post["parity_identical"] = "%d / %d" % (same, k)
         if bfs is not None:
             mv, kind, dt = cpu_bfs_rate(args.bfs_n)
             bfs["cpu_mvoxel_s"] = mv
@@ -532,9 +579,12 @@ def main():
         "cpu_baseline": cpu,
         "bfs": bfs,
         "plan": plan,
+        "post_processing": post,
         "host_cores": os.cpu_count(),
         "gpu_stats_last_launch": gpu_stats,
     }
+    if post is not None:
+        post.pop("_short", None)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
