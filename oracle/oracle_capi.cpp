@@ -21,6 +21,7 @@
 #include "arastar.h"
 #include "lattice.h"
 #include "shortcut.h"
+#include "voxelize.h"
 #include "robot_desc.h"
 
 using namespace oracle;
@@ -544,6 +545,85 @@ int oracle_arastar_search(int n, const int* off, const int* dst, const int* cost
         path[i] = r.path[i];
     }
     return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// scene ingest: oracle/voxelize.h
+///////////////////////////////////////////////////////////////////////////////
+
+static int emit_voxels(const std::vector<Vec3>& voxels, double* out, int max_out)
+{
+    if ((int)voxels.size() > max_out) {
+        return -(int)voxels.size();
+    }
+    for (size_t i = 0; i < voxels.size(); ++i) {
+        out[3 * i] = voxels[i].x;
+        out[3 * i + 1] = voxels[i].y;
+        out[3 * i + 2] = voxels[i].z;
+    }
+    return (int)voxels.size();
+}
+
+static Affine3 to_affine(const double* m /*3x4 row-major*/)
+{
+    Affine3 t;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 4; ++c) t.m[r][c] = m[4 * r + c];
+    }
+    return t;
+}
+
+/// same signatures as oracle/ref_voxelize_shim.cpp
+int oracle_voxelize_mesh(const double* vertices, int nv, const int32_t* triangles, int nt, double res,
+                         const double* voxel_origin, int fill, double* out, int max_out)
+{
+    std::vector<Vec3> v(nv);
+    for (int i = 0; i < nv; ++i) v[i] = Vec3(vertices[3 * i], vertices[3 * i + 1], vertices[3 * i + 2]);
+    std::vector<int> t(triangles, triangles + 3 * (size_t)nt);
+    std::vector<Vec3> voxels;
+    VoxelizeMesh(v, t, res, voxel_origin, fill != 0, voxels);
+    return emit_voxels(voxels, out, max_out);
+}
+
+int oracle_voxelize_box(double length, double width, double height, const double* pose3x4, double res,
+                        const double* voxel_origin, int fill, double* out, int max_out)
+{
+    std::vector<Vec3> voxels;
+    VoxelizeBox(length, width, height, to_affine(pose3x4), res, voxel_origin, fill != 0, voxels);
+    return emit_voxels(voxels, out, max_out);
+}
+
+void oracle_box_mesh(double length, double width, double height, double* vertices, int32_t* indices)
+{
+    std::vector<Vec3> v;
+    std::vector<int> t;
+    CreateIndexedBoxMesh(length, width, height, v, t);
+    for (size_t i = 0; i < v.size(); ++i) {
+        vertices[3 * i] = v[i].x;
+        vertices[3 * i + 1] = v[i].y;
+        vertices[3 * i + 2] = v[i].z;
+    }
+    std::copy(t.begin(), t.end(), indices);
+}
+
+/// WorldCollisionModel::insertObject (world_collision_model.cpp:193-234) for box primitives: VoxelizeBox with the
+/// grid origin as voxel origin, fill = false (voxel_operations.cpp:357-369), then addPointsToField.
+/// boxes[n][3 + 12] = size, pose 3x4.  Returns the number of voxels handed to the field.
+int oracle_scene_insert_boxes(oracle_scene* s, const double* boxes, int n)
+{
+    int32_t dims[3];
+    double origin[3], res;
+    int32_t dmax_sq;
+    oracle_scene_grid_info(s, dims, origin, &res, &dmax_sq);
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        const double* b = boxes + 15 * (size_t)i;
+        std::vector<Vec3> voxels;
+        VoxelizeBox(b[0], b[1], b[2], to_affine(b + 3), res, origin, false, voxels);
+        s->df->addPointsToMap(voxels);
+        total += (int)voxels.size();
+    }
+    return total;
 }
 
 ///////////////////////////////////////////////////////////////////////////////

@@ -202,6 +202,65 @@ def shortcut_table(which, costs, valid, pair_cost, algo, granularity=1):
     return None if r < 0 else out[:r].copy()
 
 
+_REF_VOX = None
+
+
+def ref_voxelize_lib():
+    """The reference's own voxeliser (smpl/src/geometry/voxelize.cpp + mesh_utils.cpp compiled from /root/reference
+    against the arithmetic Eigen stand-in), or None."""
+    global _REF_VOX
+    if _REF_VOX is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_voxelize.so")
+        if not os.path.exists(path):
+            return None
+        _REF_VOX = C.CDLL(path)
+    return _REF_VOX
+
+
+def _vox_lib(which):
+    return (ref_voxelize_lib(), "ref_") if which == "reference" else (lib(), "oracle_")
+
+
+def voxelize_mesh(which, vertices, triangles, res, voxel_origin=None, fill=False):
+    """geometry::VoxelizeMesh: voxel centres [n][3] in ExtractVoxels order.  voxel_origin None = half-res grid."""
+    L, pre = _vox_lib(which)
+    v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+    t = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
+    o = None if voxel_origin is None else np.ascontiguousarray(voxel_origin, dtype=np.float64)
+    cap = 1 << 16
+    while True:
+        out = np.zeros((cap, 3), np.float64)
+        n = getattr(L, pre + "voxelize_mesh")(_dp(v), len(v), _ip(t), len(t), C.c_double(res),
+                                              None if o is None else _dp(o), int(fill), _dp(out), cap)
+        if n >= 0:
+            return out[:n].copy()
+        cap = -n
+
+
+def voxelize_box(which, size, pose3x4, res, voxel_origin=None, fill=False):
+    """geometry::VoxelizeBox(length, width, height, pose, res[, voxel_origin], voxels, fill)."""
+    L, pre = _vox_lib(which)
+    p = np.ascontiguousarray(pose3x4, dtype=np.float64).reshape(3, 4)
+    o = None if voxel_origin is None else np.ascontiguousarray(voxel_origin, dtype=np.float64)
+    cap = 1 << 16
+    while True:
+        out = np.zeros((cap, 3), np.float64)
+        n = getattr(L, pre + "voxelize_box")(C.c_double(size[0]), C.c_double(size[1]), C.c_double(size[2]), _dp(p),
+                                             C.c_double(res), None if o is None else _dp(o), int(fill), _dp(out), cap)
+        if n >= 0:
+            return out[:n].copy()
+        cap = -n
+
+
+def box_mesh(which, size):
+    """geometry::CreateIndexedBoxMesh: (vertices[8][3], triangles[12][3])."""
+    L, pre = _vox_lib(which)
+    v = np.zeros((8, 3), np.float64)
+    t = np.zeros(36, np.int32)
+    getattr(L, pre + "box_mesh")(C.c_double(size[0]), C.c_double(size[1]), C.c_double(size[2]), _dp(v), _ip(t))
+    return v, t.reshape(12, 3)
+
+
 class OracleScene:
     def __init__(self, robot_path, group, planning_joints, origin, size, res, max_dist):
         L = lib()
@@ -423,6 +482,11 @@ class OracleScene:
         self.L.oracle_goal_heuristics(self.h, _dp(q), len(q), _ip(h))
         return h
 
+
+    def insert_boxes(self, boxes):
+        """WorldCollisionModel::insertObject for box primitives: boxes[n][15] = size(3), pose 3x4 row-major."""
+        b = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 15)
+        return self.L.oracle_scene_insert_boxes(self.h, _dp(b), len(b))
 
     def shortcut_path(self, path, continuous, kind=0):
         """ShortcutPath(rm, cc, pin, pout, type) (post_processing.cpp:284-365): indices of the shortcut path's

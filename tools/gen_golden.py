@@ -79,6 +79,21 @@ def gen_shortcut():
     print("shortcut: %d cases" % len(T.CASES))
 
 
+def gen_voxelize():
+    """voxelize_reference.npz -- voxel lists of the REFERENCE's own voxeliser (oracle/_ref/libref_voxelize.so)."""
+    from oracle_api import voxelize_box, voxelize_mesh
+    import test_oracle_voxelize as T
+    out = {}
+    for seed in range(T.N_BOX):
+        size, pose, res, origin, fill = T.box_case(seed)
+        out["box_%d" % seed] = voxelize_box("reference", size, pose, res, origin, fill)
+    for seed in range(T.N_SOUP):
+        v, t, res, origin, fill = T.soup_case(seed)
+        out["soup_%d" % seed] = voxelize_mesh("reference", v, t, res, origin, fill)
+    np.savez_compressed(os.path.join(OUT, "voxelize_reference.npz"), **out)
+    print("voxelize: %d voxels" % sum(len(v) for v in out.values()))
+
+
 def gen_distmap():
     """distmap_reference.npz -- fields of the REFERENCE's own EuclidDistanceMap (oracle/_ref/libref_distmap.so)."""
     from oracle_api import RefDistanceMap
@@ -146,7 +161,7 @@ def gen_ubr1():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["bfs", "pr2", "ubr1", "plans", "arastar", "distmap", "shortcut"]
+    which = sys.argv[1:] or ["bfs", "pr2", "ubr1", "plans", "arastar", "distmap", "shortcut", "voxelize"]
     for name in which:
         {"bfs": gen_bfs, "pr2": gen_pr2, "ubr1": gen_ubr1, "plans": gen_plans, "arastar": gen_arastar, "distmap": gen_distmap,
-         "shortcut": gen_shortcut}[name]()
+         "shortcut": gen_shortcut, "voxelize": gen_voxelize}[name]()
