@@ -191,6 +191,26 @@ int smplgpu_set_distance_field_dev(smplgpu_ctx* ctx, const uint16_t* d2_dev, int
 int smplgpu_build_distance_field(smplgpu_ctx* ctx, const int32_t* cells_xyz, int n_cells,
                                  int nx, int ny, int nz, const double origin[3], double res,
                                  double max_dist, double padding);
+/* ---- scene ingest on the device ---- */
+/* geometry::VoxelizeMesh(vertices, triangles, res[, voxel_origin], voxels, fill = false)
+ * (smpl/src/geometry/voxelize.cpp:962-1054; VoxelizeTriangle, geometry/detail/voxelize.hpp:45-181): the surface
+ * voxels of a triangle mesh, vertices[n_vertices][3], triangles[n_triangles][3].  voxel_origin != NULL: cells centred
+ * on voxel_origin + i res (PivotVoxelGrid, what the world / attached-body models use); NULL: on (i + 1/2) res
+ * (HalfResVoxelGrid, robot link meshes).  voxels[max_voxels][3] receives the voxel centres in the reference's
+ * ExtractVoxels order; returns the number of voxels found (which may exceed max_voxels).  Every collision-model
+ * caller of the reference passes fill = false (voxel_operations.cpp:319-401), so ScanFill is not built. */
+int smplgpu_voxelize_mesh(smplgpu_ctx* ctx, const double* vertices, int n_vertices, const int32_t* triangles,
+                          int n_triangles, double res, const double* voxel_origin /*nullable*/, double* voxels,
+                          int max_voxels);
+/* WorldCollisionModel::insertObject for a whole scene (world_collision_model.cpp:193-234) + the distance field:
+ * the meshes (all objects concatenated, already in the grid frame) are voxelised with the grid origin as voxel
+ * origin, their voxel centres go through OccupancyGrid::addPointsToField (occupancy_grid.cpp:357-382), the extra
+ * cells (e.g. the robot's out-of-group link voxels) are added, and the field is built as by
+ * smplgpu_build_distance_field.  Nothing but the vertices and triangles crosses the bus. */
+int smplgpu_build_distance_field_from_meshes(smplgpu_ctx* ctx, const double* vertices, int n_vertices,
+                                             const int32_t* triangles, int n_triangles, const int32_t* cells_xyz,
+                                             int n_cells, int nx, int ny, int nz, const double origin[3], double res,
+                                             double max_dist, double padding);
 int smplgpu_download_distance_field(smplgpu_ctx* ctx, uint16_t* d2_out);
 /* device pointer + byte size of the resident field, for a torch.distributed broadcast */
 int smplgpu_distance_field_dev_ptr(smplgpu_ctx* ctx, void** ptr, int64_t* bytes);

@@ -142,6 +142,13 @@ int smplhost_shortcut_paths(smplgpu_ctx* ctx, int dof, const uint8_t* continuous
 int smplhost_interpolate_paths(smplgpu_ctx* ctx, smplhost_tables* tables, const double* points, const int32_t* offsets,
                                int n_paths, double* out_points, int max_points, int32_t* out_offsets, double* stats);
 
+/* ---- scene ingest (smpl_b200/host/scene_ingest.h) ----
+ * Box primitives -> triangle meshes in the grid frame: geometry::CreateIndexedBoxMesh + TransformVertices
+ * (smpl/src/geometry/mesh_utils.cpp:39-113, voxelize.cpp:608-615).  boxes[n_boxes][15] = length, width, height and
+ * the pose as a 3x4 row-major rigid transform; vertices[8 n_boxes][3], triangles[12 n_boxes][3] (indices into the
+ * concatenated vertex array).  Feed the result to smplgpu_voxelize_mesh or smplgpu_build_distance_field_from_meshes. */
+int smplhost_box_meshes(const double* boxes, int n_boxes, double* vertices, int32_t* triangles);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,8 @@ def gpu_lib():
         L.smplgpu_fk_sphere_centers_f32.argtypes = [vp, dp, i, C.POINTER(C.c_float)]
         L.smplgpu_bfs_bank_create.argtypes = [vp, i, d]
         L.smplgpu_bfs_bank_max_slots.argtypes = [vp]
+        L.smplgpu_voxelize_mesh.argtypes = [vp, dp, i, ip, i, d, dp, dp, i]
+        L.smplgpu_build_distance_field_from_meshes.argtypes = [vp, dp, i, ip, i, ip, i, i, i, i, dp, d, d, d]
         L.smplgpu_bfs_bank_run.argtypes = [vp, ip]
         L.smplgpu_bfs_bank_run_slots.argtypes = [vp, ip, ip, i]
         L.smplgpu_bfs_bank_distances.argtypes = [vp, ip, ip, i, ip]
@@ -140,6 +142,7 @@ def host_lib():
                                               c_int32_p, c_double_p]
         H.smplhost_interpolate_paths.argtypes = [vp, vp, c_double_p, c_int32_p, C.c_int, c_double_p, C.c_int, c_int32_p,
                                                  c_double_p]
+        H.smplhost_box_meshes.argtypes = [c_double_p, C.c_int, c_double_p, c_int32_p]
         H.smplhost_adapters_create.restype = C.c_void_p
         H.smplhost_adapters_create.argtypes = [vp, vp, C.c_char_p, c_double_p, C.c_double, c_int32_p, C.c_double, C.c_int]
         H.smplhost_adapters_destroy.argtypes = [vp]
@@ -312,6 +315,31 @@ class GpuContext:
                                                      int(dims[2]), _dp(o), float(res), float(max_dist), float(padding)),
                  "build_distance_field")
         self.df_dims = tuple(int(d) for d in dims)
+
+    def build_distance_field_from_meshes(self, vertices, triangles, cells, dims, origin, res, max_dist, padding=0.0):
+        """WorldCollisionModel::insertObject for a whole scene + the field: meshes voxelised on the device."""
+        v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
+        cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 3)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        self._ck(self.L.smplgpu_build_distance_field_from_meshes(
+            self.h, _dp(v), len(v), _ip(t), len(t), _ip(cells), len(cells), int(dims[0]), int(dims[1]), int(dims[2]),
+            _dp(o), float(res), float(max_dist), float(padding)), "build_distance_field_from_meshes")
+        self.df_dims = tuple(int(d) for d in dims)
+
+    def voxelize_mesh(self, vertices, triangles, res, voxel_origin=None):
+        """geometry::VoxelizeMesh (fill = false) on the device: voxel centres [n][3] in ExtractVoxels order."""
+        v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
+        o = None if voxel_origin is None else np.ascontiguousarray(voxel_origin, dtype=np.float64)
+        cap = 1 << 16
+        while True:
+            out = np.zeros((cap, 3), np.float64)
+            n = self._ck(self.L.smplgpu_voxelize_mesh(self.h, _dp(v), len(v), _ip(t), len(t), float(res),
+                                                      None if o is None else _dp(o), _dp(out), cap), "voxelize_mesh")
+            if n <= cap:
+                return out[:n].copy()
+            cap = n
 
     def download_distance_field(self):
         out = np.zeros(self.df_dims, np.uint16)
@@ -723,11 +751,28 @@ def scene_cells(scene, tables):
     return np.ascontiguousarray(cells, dtype=np.int32)
 
 
+def box_meshes(boxes):
+    """smplhost_box_meshes: boxes[n][15] (size, pose 3x4) -> (vertices[8n][3], triangles[12n][3])."""
+    H = host_lib()
+    b = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 15)
+    v = np.zeros((8 * len(b), 3), np.float64)
+    t = np.zeros((12 * len(b), 3), np.int32)
+    if H.smplhost_box_meshes(_dp(b), len(b), _dp(v), _ip(t)) != 0:
+        raise SmplGpuError("box_meshes: " + H.smplhost_last_error().decode())
+    return v, t
+
+
 def setup_context(scene, device=0, ctx=None):
-    """Create a context with robot tables and a device-built distance field for `scene`."""
+    """Create a context with robot tables and a device-built distance field for `scene`.  Box objects of the scene
+    (scene.boxes) go through the device voxeliser, the way WorldCollisionModel::insertObject ingests them."""
     ctx = ctx or GpuContext(device)
     tables = build_tables(scene)
     ctx.set_robot(tables)
-    ctx.build_distance_field(scene_cells(scene, tables), scene.dims, scene.origin, scene.res, scene.max_dist,
-                             scene.padding)
+    cells = scene_cells(scene, tables)
+    if len(getattr(scene, "boxes", [])):
+        v, t = box_meshes(scene.boxes)
+        ctx.build_distance_field_from_meshes(v, t, cells, scene.dims, scene.origin, scene.res, scene.max_dist,
+                                             scene.padding)
+    else:
+        ctx.build_distance_field(cells, scene.dims, scene.origin, scene.res, scene.max_dist, scene.padding)
     return ctx, tables

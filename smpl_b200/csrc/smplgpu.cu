@@ -15,6 +15,7 @@
 #include "bfs.cuh"
 #include "bfs_tiles.cuh"
 #include "edt.cuh"
+#include "voxelize.cuh"
 #include "heuristic.cuh"
 #include "model.cuh"
 #include "validity.cuh"
@@ -82,6 +83,7 @@ struct smplgpu_ctx
     double* d_q0 = nullptr; double* d_q1 = nullptr; size_t q_cap = 0;   // doubles
     uint8_t* d_verdict = nullptr; int* d_counts = nullptr; size_t v_cap = 0;
     void* d_misc = nullptr; size_t misc_cap = 0;
+    void* d_vox = nullptr; size_t vox_cap = 0;      // voxeliser: vertices, triangles, per-triangle constants
     void* pinned[2] = { nullptr, nullptr }; size_t pinned_cap = 0;
     void* pinned_out[2] = { nullptr, nullptr }; size_t pinned_out_cap = 0;
     cudaEvent_t ev[2] = { nullptr, nullptr };      // chunk b: kernels + result copies done
@@ -273,7 +275,7 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
     cudaFree(ctx->d_model); cudaFree(ctx->d_stats); cudaFree(ctx->d_seed_count); cudaFree(ctx->d_df);
     cudaFree(ctx->d_blob); cudaFree(ctx->d_unc_list); cudaFree(ctx->d_unc_count);
     cudaFree(ctx->d_prim); cudaFree(ctx->d_deltas);
-    cudaFree(ctx->d_q0); cudaFree(ctx->d_q1); cudaFree(ctx->d_verdict); cudaFree(ctx->d_counts); cudaFree(ctx->d_misc);
+    cudaFree(ctx->d_q0); cudaFree(ctx->d_q1); cudaFree(ctx->d_verdict); cudaFree(ctx->d_counts); cudaFree(ctx->d_misc); cudaFree(ctx->d_vox);
     for (int i = 0; i < 2; ++i) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
         if (ctx->pinned_out[i]) cudaFreeHost(ctx->pinned_out[i]);
@@ -849,9 +851,149 @@ int smplgpu_set_distance_field_dev(smplgpu_ctx* ctx, const uint16_t* d2_dev, int
     return ctx->has_robot ? upload_model(ctx) : 0;
 }
 
+// Voxelises a triangle mesh on the device (voxelize.cuh).  mode 0: bits = bitmap over the mesh's own voxel grid
+// (gmin, gext); mode 1: occ = occupancy bytes of the distance-field grid (addPointsToField).  The per-triangle
+// work sizes come back to the host once (they size the launch); vertices and triangles are host pointers.
+static int voxelize_on_device(smplgpu_ctx* ctx, const double* vertices, int n_vertices, const int32_t* triangles,
+                              int n_triangles, const VoxDisc& D, int mode, int3 gmin, int3 gext, unsigned int* bits,
+                              uint8_t* occ)
+{
+    for (int i = 0; i < 3 * n_triangles; ++i) {
+        if (triangles[i] < 0 || triangles[i] >= n_vertices)
+            return fail(ctx, SMPLGPU_ERR_INVALID, "triangle %d: vertex index out of range", i / 3);
+    }
+    const size_t vb = (((size_t)n_vertices * 3 * sizeof(double)) + 255) / 256 * 256;
+    const size_t tb = (((size_t)n_triangles * 3 * sizeof(int)) + 255) / 256 * 256;
+    const size_t sb = (((size_t)n_triangles * sizeof(TriSetup)) + 255) / 256 * 256;
+    const size_t ob = (((size_t)(n_triangles + 1) * sizeof(unsigned long long)) + 255) / 256 * 256;
+    int r = grow(ctx, &ctx->d_vox, &ctx->vox_cap, vb + tb + sb + ob);
+    if (r) return r;
+    uint8_t* base = (uint8_t*)ctx->d_vox;
+    double* d_vertices = (double*)base;
+    int* d_tris = (int*)(base + vb);
+    TriSetup* d_setup = (TriSetup*)(base + vb + tb);
+    unsigned long long* d_off = (unsigned long long*)(base + vb + tb + sb);
+    CU(cudaMemcpyAsync(d_vertices, vertices, (size_t)n_vertices * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_tris, triangles, (size_t)n_triangles * 3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    vox_setup_kernel<<<(n_triangles + 127) / 128, 128, 0, ctx->stream>>>(d_vertices, d_tris, n_triangles, D, d_setup, d_off);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    std::vector<unsigned long long> off((size_t)n_triangles + 1);
+    CU(cudaMemcpyAsync(off.data(), d_off, (size_t)n_triangles * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    unsigned long long total = 0;
+    for (int i = 0; i < n_triangles; ++i) {
+        const unsigned long long c = off[i];
+        off[i] = total;
+        total += c;
+    }
+    off[n_triangles] = total;
+    if (total == 0) {
+        return 0;
+    }
+    if (total > (1ull << 40)) return fail(ctx, SMPLGPU_ERR_LIMIT, "mesh covers %llu candidate voxels", total);
+    CU(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned long long want = (total + 255) / 256;
+    const unsigned blocks = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctx->sm_count * 64);
+    vox_cells_kernel<<<blocks, 256, 0, ctx->stream>>>(d_setup, d_off, n_triangles, total, D, mode, gmin, gext, bits, ctx->grid, occ);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));   // `off` is read by the copy above
+    return 0;
+}
+
+int smplgpu_voxelize_mesh(smplgpu_ctx* ctx, const double* vertices, int n_vertices, const int32_t* triangles,
+                          int n_triangles, double res, const double* voxel_origin, double* voxels, int max_voxels)
+{
+    if (!ctx || n_vertices < 0 || n_triangles < 0 || max_voxels < 0 || !(res > 0.0)) return SMPLGPU_ERR_INVALID;
+    if (n_vertices == 0 || n_triangles == 0) return 0;
+    if (!vertices || !triangles || (max_voxels > 0 && !voxels)) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    VoxDisc D;
+    D.half_res = voxel_origin ? 0 : 1;
+    D.res = res;
+    for (int a = 0; a < 3; ++a) D.pivot[a] = voxel_origin ? voxel_origin[a] : 0.0;
+    // the mesh's voxel grid (ComputeAxisAlignedBoundingBox, voxelize.cpp:224-259; VoxelGrid extent, voxel_grid.h:133-141)
+    double mn[3], mx[3];
+    for (int a = 0; a < 3; ++a) mn[a] = mx[a] = vertices[a];
+    for (int i = 0; i < n_vertices; ++i) {
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = std::min(mn[a], vertices[3 * (size_t)i + a]);
+            mx[a] = std::max(mx[a], vertices[3 * (size_t)i + a]);
+        }
+    }
+    int g0[3], g1[3];
+    for (int a = 0; a < 3; ++a) {
+        const double lo = mn[a], hi = mn[a] + (mx[a] - mn[a]);
+        if (D.half_res) {
+            g0[a] = (lo >= 0) ? (int)(lo / res) : ((int)(lo / res) - 1);
+            g1[a] = (hi >= 0) ? (int)(hi / res) : ((int)(hi / res) - 1);
+        } else {
+            g0[a] = (int)std::floor((lo - D.pivot[a]) / res + 0.5);
+            g1[a] = (int)std::floor((hi - D.pivot[a]) / res + 0.5);
+        }
+    }
+    const int3 gmin = make_int3(g0[0], g0[1], g0[2]);
+    const int3 gext = make_int3(g1[0] - g0[0] + 1, g1[1] - g0[1] + 1, g1[2] - g0[2] + 1);
+    const unsigned long long n_cells = (unsigned long long)gext.x * gext.y * gext.z;
+    if (gext.x <= 0 || gext.y <= 0 || gext.z <= 0 || n_cells > (1ull << 36))
+        return fail(ctx, SMPLGPU_ERR_LIMIT, "voxel grid of %d x %d x %d cells", gext.x, gext.y, gext.z);
+    const size_t n_words = (size_t)((n_cells + 31) / 32);
+    const int n_blocks = (int)((n_words + VOX_SCAN_THREADS - 1) / VOX_SCAN_THREADS);
+    const size_t wb = ((n_words * sizeof(unsigned int)) + 255) / 256 * 256;
+    const size_t bb = (((size_t)n_blocks + 1) * sizeof(unsigned int) + 255) / 256 * 256;
+    const size_t outb = (size_t)max_voxels * 3 * sizeof(double);
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, 2 * wb + bb + outb + 256);
+    if (r) return r;
+    uint8_t* base = (uint8_t*)ctx->d_misc;
+    unsigned int* d_bits = (unsigned int*)base;
+    unsigned int* d_prefix = (unsigned int*)(base + wb);
+    unsigned int* d_blocks = (unsigned int*)(base + 2 * wb);       // n_blocks entries + the grand total
+    double* d_out = (double*)(base + 2 * wb + bb);
+    CU(cudaMemsetAsync(d_bits, 0, wb, ctx->stream));
+    r = voxelize_on_device(ctx, vertices, n_vertices, triangles, n_triangles, D, 0, gmin, gext, d_bits, nullptr);
+    if (r) return r;
+    vox_count_kernel<<<n_blocks, VOX_SCAN_THREADS, 0, ctx->stream>>>(d_bits, n_words, d_prefix, d_blocks);
+    vox_scan_blocks_kernel<<<1, VOX_SCAN_THREADS, 0, ctx->stream>>>(d_blocks, n_blocks, d_blocks + n_blocks);
+    vox_extract_kernel<<<n_blocks, VOX_SCAN_THREADS, 0, ctx->stream>>>(d_bits, n_words, d_prefix, d_blocks, D, gmin, gext, d_out,
+                                                                       (unsigned int)max_voxels);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    unsigned int total = 0;
+    CU(cudaMemcpyAsync(&total, d_blocks + n_blocks, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const size_t m = std::min((size_t)total, (size_t)max_voxels);
+    if (m > 0) {
+        CU(cudaMemcpyAsync(voxels, d_out, m * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return (int)total;
+}
+
+static int build_distance_field_impl(smplgpu_ctx* ctx, const double* vertices, int n_vertices, const int32_t* triangles,
+                                     int n_triangles, const int32_t* cells_xyz, int n_cells, int nx, int ny, int nz,
+                                     const double origin[3], double res, double max_dist, double padding);
+
 int smplgpu_build_distance_field(smplgpu_ctx* ctx, const int32_t* cells_xyz, int n_cells,
                                  int nx, int ny, int nz, const double origin[3], double res,
                                  double max_dist, double padding)
+{
+    return build_distance_field_impl(ctx, nullptr, 0, nullptr, 0, cells_xyz, n_cells, nx, ny, nz, origin, res, max_dist, padding);
+}
+
+int smplgpu_build_distance_field_from_meshes(smplgpu_ctx* ctx, const double* vertices, int n_vertices,
+                                             const int32_t* triangles, int n_triangles, const int32_t* cells_xyz,
+                                             int n_cells, int nx, int ny, int nz, const double origin[3], double res,
+                                             double max_dist, double padding)
+{
+    if (n_vertices < 0 || n_triangles < 0 || (n_triangles > 0 && (!vertices || !triangles || n_vertices == 0)))
+        return SMPLGPU_ERR_INVALID;
+    return build_distance_field_impl(ctx, vertices, n_vertices, triangles, n_triangles, cells_xyz, n_cells, nx, ny, nz, origin,
+                                     res, max_dist, padding);
+}
+
+static int build_distance_field_impl(smplgpu_ctx* ctx, const double* vertices, int n_vertices, const int32_t* triangles,
+                                     int n_triangles, const int32_t* cells_xyz, int n_cells, int nx, int ny, int nz,
+                                     const double origin[3], double res, double max_dist, double padding)
 {
     if (!ctx || !origin || n_cells < 0 || (n_cells > 0 && !cells_xyz)) return SMPLGPU_ERR_INVALID;
     // m_dmax_int((int)std::ceil(m_max_dist * m_inv_res)), distance_map.hpp:125-126
@@ -874,6 +1016,16 @@ int smplgpu_build_distance_field(smplgpu_ctx* ctx, const int32_t* cells_xyz, int
         CU(cudaMemcpyAsync(d_cells, cells_xyz, (size_t)n_cells * 3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         edt_scatter_kernel<<<(n_cells + 255) / 256, 256, 0, ctx->stream>>>(d_cells, n_cells, nx, ny, nz, occ);
         ++ctx->launches;
+    }
+    if (n_triangles > 0) {
+        // WorldCollisionModel::insertObject: voxelise with the grid origin as voxel origin, then addPointsToField
+        VoxDisc D;
+        D.half_res = 0;
+        D.res = res;
+        for (int a = 0; a < 3; ++a) D.pivot[a] = origin[a];
+        r = voxelize_on_device(ctx, vertices, n_vertices, triangles, n_triangles, D, 1, make_int3(0, 0, 0), make_int3(0, 0, 0),
+                               nullptr, occ);
+        if (r) return r;
     }
     edt_pass_z_kernel<<<(nx * ny + 127) / 128, 128, 0, ctx->stream>>>(occ, nx, ny, nz, dmax, g1);
     const unsigned blocks = (unsigned)((cells + 255) / 256);

@@ -14,6 +14,7 @@
 #include "batch_planner.h"
 #include "gpu_adapters.h"
 #include "post_processing.h"
+#include "scene_ingest.h"
 #include "robot_tables.h"
 
 using smplhost::RobotTables;
@@ -570,6 +571,27 @@ int smplhost_interpolate_paths(smplgpu_ctx* ctx, smplhost_tables* tables, const 
     }
     std::copy(pts.begin(), pts.end(), out_points);
     return total;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// scene ingest (scene_ingest.h)
+///////////////////////////////////////////////////////////////////////////////
+
+int smplhost_box_meshes(const double* boxes, int n_boxes, double* vertices, int32_t* triangles)
+{
+    if (n_boxes < 0 || (n_boxes > 0 && (!boxes || !vertices || !triangles))) {
+        g_err = "smplhost_box_meshes: bad argument";
+        return SMPLGPU_ERR_INVALID;
+    }
+    std::vector<double> v;
+    std::vector<int32_t> t;
+    for (int i = 0; i < n_boxes; ++i) {
+        const double* b = boxes + 15 * (size_t)i;
+        smplhost::AppendBoxMesh(b[0], b[1], b[2], b + 3, v, t);
+    }
+    std::copy(v.begin(), v.end(), vertices);
+    std::copy(t.begin(), t.end(), triangles);
+    return 0;
 }
 
 } // extern "C"

@@ -67,10 +67,25 @@ class Scene:
         self.cost_per_cell = 250       # planning_params.h:68 default... set by callers
         self.attached = None           # (id, link, centers[n,3], radius)
         self.acm_extra = []            # (a, b, allowed) entries applied on top of the ACM
+        # box collision objects ingested the reference's way (VoxelizeBox, surface voxels): rows of 15 doubles =
+        # length, width, height, pose 3x4 row-major in the grid frame
+        self.boxes = np.zeros((0, 15), np.float64)
 
     def add_box(self, center, size):
         c = box_cells(self.origin, self.res, self.dims, center, size)
         self.cells = np.concatenate([self.cells, c], axis=0)
+
+    def add_box_object(self, center, size, rpy=(0.0, 0.0, 0.0)):
+        """A box collision object (call_planner.cpp GetCollisionCube: id x y z dx dy dz; rpy for rotated shelves)."""
+        cr, sr = math.cos(rpy[0]), math.sin(rpy[0])
+        cp, sp = math.cos(rpy[1]), math.sin(rpy[1])
+        cy, sy = math.cos(rpy[2]), math.sin(rpy[2])
+        R = np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                      [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                      [-sp, cp * sr, cp * cr]]) if any(rpy) else np.eye(3)
+        pose = np.concatenate([R, np.asarray(center, dtype=np.float64).reshape(3, 1)], axis=1)
+        row = np.concatenate([np.asarray(size, dtype=np.float64), pose.ravel()])
+        self.boxes = np.concatenate([self.boxes, row[None, :]], axis=0)
 
     @property
     def dof(self):
@@ -95,6 +110,35 @@ def pr2_tabletop_scene():
     _pr2_common(s)
     # tabletop.env declares 1 object: id x y z dx dy dz
     s.add_box((0.55, 0.0, 0.6), (0.4, 1.5, 0.02))
+    return s
+
+
+def pr2_tabletop_env_scene():
+    """Config 1 with the table ingested the reference's way: the env box goes through VoxelizeBox (surface voxels,
+    voxel origin = grid origin) and addPointsToField instead of our filled cell box."""
+    s = Scene("pr2", "right_arm", PR2_RIGHT_ARM_JOINTS, (-0.75, -1.5, 0.0), (3.0, 3.0, 3.0), 0.02, 1.8)
+    _pr2_common(s)
+    s.add_box_object((0.55, 0.0, 0.6), (0.4, 1.5, 0.02))
+    return s
+
+
+def pr2_shelf_objects_scene(seed=23, n_boxes=30):
+    """The clutter volume (2 m^3 at 2 cm) filled with box OBJECTS at arbitrary orientations: shelf boards, tilted
+    panels and small items, some sticking out of the grid."""
+    s = Scene("pr2", "right_arm", PR2_RIGHT_ARM_JOINTS, (-0.5, -1.0, 0.0), (2.0, 2.0, 2.0), 0.02, 0.4)
+    _pr2_common(s)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    for z in (0.4, 0.8, 1.2):
+        s.add_box_object((0.95, 0.0, z), (0.5, 1.6, 0.02))
+    s.add_box_object((1.45, 0.9, 1.0), (0.3, 0.5, 1.2), rpy=(0.0, 0.0, 0.3))          # half outside the grid
+    placed = 0
+    while placed < n_boxes:
+        size = rng.uniform(0.03, 0.3, 3)
+        center = np.array(s.origin) + rng.uniform(0.0, 1.0, 3) * np.array(s.size)
+        if abs(center[0] + 0.1) < 0.5 + 0.5 * size.max() and abs(center[1]) < 0.6 + 0.5 * size.max():
+            continue  # robot body column
+        s.add_box_object(center, size, rpy=tuple(rng.uniform(-1.0, 1.0, 3)) if placed % 3 else (0.0, 0.0, 0.0))
+        placed += 1
     return s
 
 

@@ -20,6 +20,8 @@ def make_oracle(scene, prime_q=None, with_kdl=True):
         o.attach_spheres(body_id, link, centers, radius)
     if len(scene.cells):
         o.add_cells(scene.cells)
+    if len(getattr(scene, "boxes", [])):
+        o.insert_boxes(scene.boxes)     # WorldCollisionModel::insertObject: VoxelizeBox + addPointsToField
     if with_kdl and scene.chain_root is not None:
         o.init_kdl(scene.chain_root, scene.chain_tip, scene.planning_link, scene.T_kin_to_planning, scene.xyz_offset)
     o.prime(np.zeros(scene.dof) if prime_q is None else prime_q)

@@ -1,0 +1,90 @@
+"""Scene ingest on the device: the voxels the CUDA voxeliser finds for a mesh, and the
+distance field built from a scene's box objects, must equal the reference-shaped CPU code of the oracle
+(oracle/voxelize.cpp, pinned against the reference's own voxelize.cpp) voxel for voxel and cell for cell."""
+import numpy as np
+import pytest
+
+from helpers import make_oracle
+from oracle_api import voxelize_box, voxelize_mesh
+from smpl_b200 import api, scenes
+from test_oracle_voxelize import N_BOX, N_SOUP, box_case, soup_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.GpuContext(0)
+    yield c
+    c.close()
+
+
+def test_box_voxels_equal_oracle(ctx):
+    total = 0
+    for seed in range(N_BOX):
+        size, pose, res, origin, fill = box_case(seed)
+        v, t = api.box_meshes(np.concatenate([size, pose.ravel()])[None, :])
+        got = ctx.voxelize_mesh(v, t, res, origin)
+        ref = voxelize_box("oracle", size, pose, res, origin, False)
+        assert got.shape == ref.shape and np.array_equal(got, ref), seed    # same centres, same (ExtractVoxels) order
+        total += len(got)
+    assert total > 20000
+
+
+def test_triangle_soups_equal_oracle(ctx):
+    total = 0
+    for seed in range(N_SOUP):
+        v, t, res, origin, _ = soup_case(seed)
+        got = ctx.voxelize_mesh(v, t, res, origin)
+        ref = voxelize_mesh("oracle", v, t, res, origin, False)
+        assert got.shape == ref.shape and np.array_equal(got, ref), seed
+        total += len(got)
+    assert total > 5000
+
+
+def test_degenerate_and_empty_meshes(ctx):
+    v = np.array([[0.0, 0, 0], [1, 0, 0], [2, 0, 0], [0.5, 0, 0]])
+    assert len(ctx.voxelize_mesh(v, [[0, 1, 2], [0, 0, 3]], 0.05, (0, 0, 0))) == 0      # colinear / repeated vertex
+    assert len(ctx.voxelize_mesh(v, np.zeros((0, 3), np.int32), 0.05, (0, 0, 0))) == 0
+    with pytest.raises(api.SmplGpuError):
+        ctx.voxelize_mesh(v, [[0, 1, 4]], 0.05, (0, 0, 0))                              # vertex index out of range
+    # a large thin triangle: many candidate cells per triangle
+    big = np.array([[0.0, 0.0, 0.013], [3.0, 0.1, 0.013], [0.2, 2.5, 0.4]])
+    got = ctx.voxelize_mesh(big, [[0, 1, 2]], 0.01, (0.0, 0.0, 0.0))
+    ref = voxelize_mesh("oracle", big, [[0, 1, 2]], 0.01, (0.0, 0.0, 0.0), False)
+    assert len(ref) > 40000 and np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("make_scene", [scenes.pr2_tabletop_env_scene, scenes.pr2_shelf_objects_scene])
+def test_distance_field_from_box_objects_equals_oracle(make_scene):
+    scene = make_scene()
+    o = make_oracle(scene, with_kdl=False)
+    c, tables = api.setup_context(scene)
+    try:
+        ref = o.df_d2()
+        got = c.download_distance_field().astype(np.int32)
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref), "%d cells differ" % int((got != ref).sum())
+        assert (ref == 0).sum() > 1000
+        lo, hi, cont = tables.limits()
+        q = scenes.random_states(20000, lo, hi, cont, seed=4)
+        v = c.is_states_valid(q)
+        assert np.array_equal(v, o.is_states_valid(q))
+        assert 0.05 < v.mean() < 0.95
+    finally:
+        c.close()
+
+
+def test_surface_ingest_differs_from_filled_cells():
+    """The reference ingests SURFACE voxels (fill = false): the inside of a thick box is free space in its field."""
+    s = scenes.Scene("pr2", "right_arm", scenes.PR2_RIGHT_ARM_JOINTS, (-0.5, -1.0, 0.0), (2.0, 2.0, 2.0), 0.02, 0.4)
+    scenes._pr2_common(s)
+    s.add_box_object((0.9, 0.4, 1.0), (0.4, 0.4, 0.4))
+    c, tables = api.setup_context(s)
+    try:
+        d2 = c.download_distance_field()
+        centre = api.world_to_grid([[0.9, 0.4, 1.0]], s.origin, s.res)[0]
+        face = api.world_to_grid([[0.7, 0.4, 1.0]], s.origin, s.res)[0]
+        assert d2[tuple(face)] == 0 and d2[tuple(centre)] >= 64      # 10 cells from every face, minus the shell
+    finally:
+        c.close()
