@@ -103,7 +103,10 @@ def make_oracle(scene, prime_q):
         o.use_desc_acm()
     for a, b, allowed in scene.acm_extra:
         o.acm_set(a, b, allowed)
-    o.add_cells(scene.cells)
+    if len(scene.cells):
+        o.add_cells(scene.cells)
+    if len(getattr(scene, "boxes", [])):
+        o.insert_boxes(scene.boxes)
     o.prime(prime_q)
     return o
 
@@ -258,6 +261,7 @@ def main():
     ap.add_argument("--plan-cpu-queries", type=int, default=12)
     ap.add_argument("--post-paths", type=int, default=1024, help="joint-space paths shortcut in one call (0 = skip)")
     ap.add_argument("--post-cpu-paths", type=int, default=48)
+    ap.add_argument("--no-ingest", dest="ingest", action="store_false", help="skip the scene-ingest leg")
     ap.add_argument("--plan-threads", type=int, default=0, help="planner threads (= contexts) per GPU; 0 = 75 %% of the rank's cores, at most 12")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "smpl_b200" else args.warmup
@@ -417,7 +421,30 @@ def main():
                 "call": "smplhost_shortcut_paths (ShortcutPath JOINT_SPACE): all point pairs of every path in one "
                         "smplgpu_is_indexed_edges_valid call", "_short": short}
 
-    clocks = sampler.stop() if rank == 0 else None   # sampled across the validity, end-to-end, BFS and shortcut regions
+    # ---- scene ingest: box objects -> surface voxels -> distance field, all on the device ----
+    ingest = None
+    if rank == 0 and args.ingest:
+        iscene = scenes.pr2_shelf_objects_scene()
+        ictx = api.GpuContext(local_rank)
+        itables = api.build_tables(iscene)
+        ictx.set_robot(itables)
+        icells = api.scene_cells(iscene, itables)
+        iv, it = api.box_meshes(iscene.boxes)
+        for _ in range(2):
+            ictx.build_distance_field_from_meshes(iv, it, icells, iscene.dims, iscene.origin, iscene.res, iscene.max_dist)
+        t0 = time.perf_counter()
+        reps = 10
+        for _ in range(reps):
+            ictx.build_distance_field_from_meshes(iv, it, icells, iscene.dims, iscene.origin, iscene.res, iscene.max_dist)
+        dt = (time.perf_counter() - t0) / reps
+        d2 = ictx.download_distance_field()
+        ingest = {"scene": "34 box objects (12 triangles each, arbitrary poses) in 2 m^3 @ 2 cm", "triangles": int(len(it)),
+                  "grid_cells": int(d2.size), "occupied_cells": int((d2 == 0).sum()), "ms": dt * 1e3,
+                  "call": "smplgpu_build_distance_field_from_meshes: voxelise + addPointsToField + distance field, host call to field ready",
+                  "_d2": d2, "_scene": iscene}
+        ictx.close()
+
+    clocks = sampler.stop() if rank == 0 else None   # sampled across the validity, end-to-end, BFS, shortcut and ingest regions
 
     # ---- plan queries/s (config[0]/[3] shape): PR2 right arm on the tabletop scene, queries sharded over ranks ----
     plan = None
@@ -527,6 +554,15 @@ def main():
             post["cpu_paths_per_s"] = k / dt
             post["cpu_sample"] = "first %d paths, oracle ShortcutPath (one isStateToStateValid per request), 1 thread" % k
             post["parity_identical"] = "%d / %d" % (same, k)
+        if ingest is not None:
+            t0 = time.perf_counter()
+            io = make_oracle(ingest["_scene"], np.zeros(dof))     # VoxelizeBox per object + addPointsToField + propagation
+            dt = time.perf_counter() - t0
+            ref_d2 = io.df_d2()
+            ingest["cpu_ms"] = dt * 1e3
+            ingest["cpu_sample"] = "oracle: scene construction incl. VoxelizeBox + DistanceMap propagation, 1 thread"
+            ingest["occupied_cells_identical"] = bool(np.array_equal(ref_d2 == 0, ingest["_d2"] == 0))
+            ingest["cells_where_reference_propagation_is_inexact"] = int((ref_d2 != ingest["_d2"]).sum())
         if bfs is not None:
             mv, kind, dt = cpu_bfs_rate(args.bfs_n)
             bfs["cpu_mvoxel_s"] = mv
@@ -580,11 +616,15 @@ def main():
         "bfs": bfs,
         "plan": plan,
         "post_processing": post,
+        "scene_ingest": ingest,
         "host_cores": os.cpu_count(),
         "gpu_stats_last_launch": gpu_stats,
     }
     if post is not None:
         post.pop("_short", None)
+    if ingest is not None:
+        ingest.pop("_d2", None)
+        ingest.pop("_scene", None)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
