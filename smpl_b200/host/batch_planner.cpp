@@ -1,6 +1,8 @@
 #include "batch_planner.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <chrono>
 #include <cmath>
 #include <limits>
@@ -39,38 +41,55 @@ double normalizeAngle(double angle)
 }
 } // namespace
 
-int BatchPlanner::Lattice::find(const int* c) const
+// A table slot holds (low 32 hash bits << 32 | state id): a probe is decided from the slot alone unless the tag
+// matches, so the coordinate array (another cache miss) is only read for a state that is almost surely the one
+int BatchPlanner::Lattice::find(const int* c, uint64_t hv) const
 {
     if (table.empty()) {
         return -1;
     }
     const size_t mask = table.size() - 1;
-    for (size_t i = (size_t)hash(c, dof) & mask;; i = (i + 1) & mask) {
-        const int id = table[i];
-        if (id < 0) {
+    const uint32_t tag = (uint32_t)hv;
+    for (size_t i = (size_t)tag & mask;; i = (i + 1) & mask) {
+        const uint64_t slot = table[i];
+        if (slot == EMPTY) {
             return -1;
         }
-        if (std::equal(c, c + dof, &coords[(size_t)id * dof])) {
-            return id;
+        if ((uint32_t)(slot >> 32) == tag) {
+            const int id = (int)(uint32_t)slot;
+            if (std::equal(c, c + dof, &coords[(size_t)id * dof])) {
+                return id;
+            }
         }
     }
 }
 
-void BatchPlanner::Lattice::grow()
+void BatchPlanner::Lattice::enter(uint32_t tag, int id)
 {
-    const size_t n = table.empty() ? 256 : table.size() * 2;
-    table.assign(n, -1);
-    const size_t mask = n - 1;
-    for (int id = 1; id < size(); ++id) {   // id 0 (the goal state) has no coordinate
-        size_t i = (size_t)hash(&coords[(size_t)id * dof], dof) & mask;
-        while (table[i] >= 0) {
-            i = (i + 1) & mask;
-        }
-        table[i] = id;
+    const size_t mask = table.size() - 1;
+    size_t i = (size_t)tag & mask;
+    while (table[i] != EMPTY) {
+        i = (i + 1) & mask;
     }
+    table[i] = ((uint64_t)tag << 32) | (uint32_t)id;
 }
 
-int BatchPlanner::Lattice::add(const int* c, const double* q, int hv, int gd, bool index)
+void BatchPlanner::Lattice::grow(uint32_t new_tag, int new_id)
+{
+    // the tags carry every hash bit a table of up to 2^32 slots needs: re-enter the old slots without reading
+    // a single coordinate, then the state that triggered the growth
+    std::vector<uint64_t> old;
+    old.swap(table);
+    table.assign(old.empty() ? 256 : old.size() * 2, EMPTY);
+    for (const uint64_t slot : old) {
+        if (slot != EMPTY) {
+            enter((uint32_t)(slot >> 32), (int)(uint32_t)slot);
+        }
+    }
+    enter(new_tag, new_id);
+}
+
+int BatchPlanner::Lattice::add(const int* c, const double* q, int hval, int gd, bool index, uint64_t hv)
 {
     const int id = size();
     if (c != nullptr) {
@@ -80,18 +99,13 @@ int BatchPlanner::Lattice::add(const int* c, const double* q, int hv, int gd, bo
         coords.insert(coords.end(), dof, 0);
         qs.insert(qs.end(), dof, 0.0);
     }
-    h.push_back(hv);
+    h.push_back(hval);
     gdist.push_back(gd);
     if (index) {
         if ((size_t)(id + 1) * 2 > table.size()) {
-            grow();   // re-enters every state including this one
+            grow((uint32_t)hv, id);
         } else {
-            const size_t mask = table.size() - 1;
-            size_t i = (size_t)hash(c, dof) & mask;
-            while (table[i] >= 0) {
-                i = (i + 1) & mask;
-            }
-            table[i] = id;
+            enter((uint32_t)hv, id);
         }
     }
     return id;
@@ -220,18 +234,18 @@ void BatchPlanner::touch(Query& Q, int id)
 
 void BatchPlanner::percolateUp(Query& Q, size_t pivot)
 {
-    const int tmp = Q.open[pivot];
+    const Query::HeapEntry tmp = Q.open[pivot];
     while (pivot != 1) {
         const size_t p = pivot >> 1;
-        if (Q.search[Q.open[p]].f < Q.search[tmp].f) {
+        if (Q.open[p].f < tmp.f) {
             break;
         }
         Q.open[pivot] = Q.open[p];
-        Q.search[Q.open[pivot]].heap_index = (int)pivot;
+        Q.search[Q.open[pivot].id].heap_index = (int)pivot;
         pivot = p;
     }
     Q.open[pivot] = tmp;
-    Q.search[tmp].heap_index = (int)pivot;
+    Q.search[tmp.id].heap_index = (int)pivot;
 }
 
 void BatchPlanner::percolateDown(Query& Q, size_t pivot)
@@ -240,15 +254,15 @@ void BatchPlanner::percolateDown(Query& Q, size_t pivot)
         return;
     }
     size_t left = pivot << 1, right = left + 1;
-    const int tmp = Q.open[pivot];
+    const Query::HeapEntry tmp = Q.open[pivot];
     while (left < Q.open.size()) {
         size_t s = right;
-        if (right >= Q.open.size() || Q.search[Q.open[left]].f < Q.search[Q.open[right]].f) {
+        if (right >= Q.open.size() || Q.open[left].f < Q.open[right].f) {
             s = left;
         }
-        if (Q.search[Q.open[s]].f < Q.search[tmp].f) {
+        if (Q.open[s].f < tmp.f) {
             Q.open[pivot] = Q.open[s];
-            Q.search[Q.open[pivot]].heap_index = (int)pivot;
+            Q.search[Q.open[pivot].id].heap_index = (int)pivot;
             pivot = s;
         } else {
             break;
@@ -257,19 +271,19 @@ void BatchPlanner::percolateDown(Query& Q, size_t pivot)
         right = left + 1;
     }
     Q.open[pivot] = tmp;
-    Q.search[tmp].heap_index = (int)pivot;
+    Q.search[tmp.id].heap_index = (int)pivot;
 }
 
 void BatchPlanner::heapPush(Query& Q, int id)
 {
     Q.search[id].heap_index = (int)Q.open.size();
-    Q.open.push_back(id);
+    Q.open.push_back(Query::HeapEntry{ Q.search[id].f, id });
     percolateUp(Q, Q.open.size() - 1);
 }
 
 void BatchPlanner::heapPop(Query& Q)
 {
-    Q.search[Q.open[1]].heap_index = 0;
+    Q.search[Q.open[1].id].heap_index = 0;
     Q.open[1] = Q.open.back();
     Q.open.pop_back();
     percolateDown(Q, 1);
@@ -396,7 +410,38 @@ void BatchPlanner::Pool::run(const std::function<void(int)>& f)
 
 void BatchPlanner::initQuery(Query& Q, int index, int slot, const double* goal)
 {
-    Q = Query();
+    // keep the slot's allocations from the query it served before (growing a multi-megabyte vector means mmap +
+    // copy + munmap, and every munmap interrupts all planner threads); a fresh slot reserves room up front
+    Query fresh = Query();
+    std::swap(fresh.lat.coords, Q.lat.coords);
+    std::swap(fresh.lat.qs, Q.lat.qs);
+    std::swap(fresh.lat.h, Q.lat.h);
+    std::swap(fresh.lat.gdist, Q.lat.gdist);
+    std::swap(fresh.lat.table, Q.lat.table);
+    std::swap(fresh.search, Q.search);
+    std::swap(fresh.open, Q.open);
+    std::swap(fresh.succ_q1, Q.succ_q1);
+    std::swap(fresh.succ_coord, Q.succ_coord);
+    std::swap(fresh.succ_hslot, Q.succ_hslot);
+    std::swap(fresh.succ_id, Q.succ_id);
+    fresh.lat.coords.clear();
+    fresh.lat.qs.clear();
+    fresh.lat.h.clear();
+    fresh.lat.gdist.clear();
+    fresh.lat.table.clear();
+    fresh.search.clear();
+    fresh.open.clear();
+    Q = std::move(fresh);
+    {
+        const size_t per_expansion = std::max<size_t>(1, m_prim_deltas.size() / 2);
+        const size_t n = std::min<size_t>(2 + (size_t)std::max(0, m_cfg.max_expansions) * per_expansion, (size_t)1 << 15);
+        const size_t dofs = (size_t)m_cfg.dof;
+        Q.lat.coords.reserve(n * dofs);
+        Q.lat.qs.reserve(n * dofs);
+        Q.lat.h.reserve(n);
+        Q.lat.gdist.reserve(n);
+        Q.search.reserve(n);
+    }
     Q.index = index;
     Q.slot = slot;
     Q.done = false;
@@ -410,9 +455,9 @@ void BatchPlanner::initQuery(Query& Q, int index, int slot, const double* goal)
                      cell[0] < m_cfg.dims[0] && cell[1] < m_cfg.dims[1] && cell[2] < m_cfg.dims[2];
     // the seed cell holds distance 0 even if it was a wall (bfs3d.cpp:181-187)
     Q.goal_h = inb ? 0 : SMPLGPU_HEURISTIC_INFINITY;
-    Q.open.assign(1, -1);
+    Q.open.assign(1, Query::HeapEntry{ 0u, -1 });
     Q.lat.dof = m_cfg.dof;
-    Q.lat.add(nullptr, nullptr, 0, 0, false); // id 0 = the goal state (manip_lattice.cpp:122)
+    Q.lat.add(nullptr, nullptr, 0, 0, false, 0); // id 0 = the goal state (manip_lattice.cpp:122)
 }
 
 // ARAStar::improvePath loop head (arastar.cpp:486-527) + ManipLatticeActionSpace::apply + the joint-limit
@@ -427,7 +472,7 @@ void BatchPlanner::expandOne(Query& Q)
         finish(Q, false);
         return;
     }
-    const int min_id = Q.open[1];
+    const int min_id = Q.open[1].id;
     if (Q.search[min_id].f >= Q.search[0].f || min_id == 0) {
         finish(Q, true);
         return;
@@ -466,20 +511,65 @@ void BatchPlanner::expandOne(Query& Q)
 
 // GetSuccs bookkeeping + ARAStar::expand relaxations (arastar.cpp:531-568) for this query's edges, in
 // submission (= primitive) order
+static thread_local double g_abs_prof[4] = { 0, 0, 0, 0 };   // SMPLHOST_PLAN_PROFILE: coord+hash, prefetch pass, lookup, relax
+
 void BatchPlanner::absorbOne(Query& Q, const uint8_t* verdict, const int32_t* h, const int32_t* gd, const double* off)
 {
     const int dof = m_cfg.dof;
+    static const bool profile = getenv("SMPLHOST_PLAN_PROFILE") != nullptr;
+    Timer pt;
     std::vector<int> coord;
+    // The lattice of a query is megabytes of hash table, coordinates and search states, and hundreds of queries
+    // take turns on one thread: every lookup below misses the caches.  Two prefetch-only passes (they decide
+    // nothing) start those loads for all successors of this expansion before the sequential relaxation runs.
+    Q.succ_coord.resize((size_t)Q.n_succ * dof);
+    Q.succ_hslot.resize(Q.n_succ);
+    const size_t mask = Q.lat.table.empty() ? 0 : Q.lat.table.size() - 1;
     for (int e = 0; e < Q.n_succ; ++e) {
         if (!verdict[e]) {
             continue;
         }
-        const double* qs = &Q.succ_q1[(size_t)e * dof];
-        stateToCoord(qs, coord);
-        int succ_id = Q.lat.find(coord.data());
-        if (succ_id < 0) {
-            succ_id = Q.lat.add(coord.data(), qs, h[e], gd[e], true);
+        stateToCoord(&Q.succ_q1[(size_t)e * dof], coord);
+        std::copy(coord.begin(), coord.end(), Q.succ_coord.begin() + (size_t)e * dof);
+        Q.succ_hslot[e] = Lattice::hash(coord.data(), dof);
+        if (!Q.lat.table.empty()) {
+            __builtin_prefetch(&Q.lat.table[(size_t)Q.succ_hslot[e] & mask]);
         }
+    }
+    if (profile) g_abs_prof[0] += pt.lap();
+    for (int e = 0; e < Q.n_succ; ++e) {
+        if (!verdict[e] || Q.lat.table.empty()) {
+            continue;
+        }
+        const uint64_t slot = Q.lat.table[(size_t)Q.succ_hslot[e] & mask];
+        const int id = slot == Lattice::EMPTY ? -1 : (int)(uint32_t)slot;
+        if (id >= 0) {
+            __builtin_prefetch(&Q.lat.coords[(size_t)id * dof]);
+            if ((size_t)id < Q.search.size()) {
+                __builtin_prefetch(&Q.search[id]);
+            }
+        }
+    }
+    if (profile) g_abs_prof[1] += pt.lap();
+    Q.succ_id.resize(Q.n_succ);
+    int* ids = Q.succ_id.data();   // lattice id of successor e
+    for (int e = 0; e < Q.n_succ; ++e) {
+        if (!verdict[e]) {
+            continue;
+        }
+        const int* c = &Q.succ_coord[(size_t)e * dof];
+        int succ_id = Q.lat.find(c, Q.succ_hslot[e]);
+        if (succ_id < 0) {
+            succ_id = Q.lat.add(c, &Q.succ_q1[(size_t)e * dof], h[e], gd[e], true, Q.succ_hslot[e]);
+        }
+        ids[e] = succ_id;
+    }
+    if (profile) g_abs_prof[2] += pt.lap();
+    for (int e = 0; e < Q.n_succ; ++e) {
+        if (!verdict[e]) {
+            continue;
+        }
+        const int succ_id = ids[e];
         // ManipLattice::isGoal, XYZ_GOAL (manip_lattice.cpp:1673-1687)
         const bool is_goal = std::fabs(off[3 * e] - Q.goal[0]) <= m_cfg.xyz_tolerance[0] &&
                              std::fabs(off[3 * e + 1] - Q.goal[1]) <= m_cfg.xyz_tolerance[1] &&
@@ -498,6 +588,7 @@ void BatchPlanner::absorbOne(Query& Q, const uint8_t* verdict, const int32_t* h,
             if (ss.iteration_closed != 1) {
                 ss.f = computeKey(ss);
                 if (ss.heap_index != 0) {
+                    Q.open[ss.heap_index].f = ss.f;
                     percolateUp(Q, (size_t)ss.heap_index);
                 } else {
                     heapPush(Q, target);
@@ -505,6 +596,7 @@ void BatchPlanner::absorbOne(Query& Q, const uint8_t* verdict, const int32_t* h,
             }
         }
     }
+    if (profile) g_abs_prof[3] += pt.lap();
 }
 
 ///////////////////////////////////////////////////////////////////////////////
@@ -559,6 +651,10 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         int ne = 0;
     };
     Group G[2];
+    // SMPLHOST_PLAN_PROFILE=1: where the host time of this planner thread goes (printed to stderr at the end)
+    static const bool profile = getenv("SMPLHOST_PLAN_PROFILE") != nullptr;
+    double prof[6] = { 0, 0, 0, 0, 0, 0 };  // absorb, retire, expand, pack, submit, refill
+    Timer pt;
     std::vector<double> sq;                 // setStart scratch
     std::vector<int32_t> sh, sgd;
     std::vector<uint8_t> sv;
@@ -577,6 +673,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
             }
             g.in_flight = false;
             const int na = (int)g.active.size();
+            pt.lap();
             pool.run([&](int tid) {
                 for (int k = tid; k < na; k += pool.size()) {
                     Query& Q = S[g.active[k]];
@@ -587,7 +684,9 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
                               g.off.data() + (size_t)Q.edge_begin * 3);
                 }
             });
+            prof[0] += pt.lap();
         }
+        pt.lap();
         size_t keep = 0;
         for (size_t k = 0; k < g.active.size(); ++k) {
             const int s = g.active[k];
@@ -600,6 +699,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
             }
         }
         g.active.resize(keep);
+        prof[1] += pt.lap();
         return true;
     };
 
@@ -610,6 +710,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         if (na == 0) {
             return true;
         }
+        pt.lap();
         pool.run([&](int tid) {
             for (int k = tid; k < na; k += pool.size()) {
                 Query& Q = S[g.active[k]];
@@ -618,6 +719,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
                 }
             }
         });
+        prof[2] += pt.lap();
         int ne = 0;
         for (int k = 0; k < na; ++k) {
             Query& Q = S[g.active[k]];
@@ -649,7 +751,9 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         g.h.resize(ne);
         g.gd.resize(ne);
         g.off.resize((size_t)ne * 3);
+        prof[3] += pt.lap();
         if (smplgpu_expand_batch_submit(m_ctx, g.q0.data(), g.q1.data(), g.slot.data(), ne, m_cfg.cost_per_cell, gi) < 0) return false;
+        prof[4] += pt.lap();
         g.in_flight = true;
         ++m_stats.device_calls;
         ++m_stats.rounds;
@@ -714,7 +818,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
                     continue;
                 }
                 stateToCoord(qs, coord);
-                Q.lat.add(coord.data(), qs, sh[k], sgd[k], true);
+                Q.lat.add(coord.data(), qs, sh[k], sgd[k], true, Lattice::hash(coord.data(), dof));
                 sstate(Q, 1);
                 touch(Q, 1);
                 touch(Q, 0);
@@ -730,6 +834,15 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
             if (!expand(gi)) return fail_dev();
         }
         m_stats.host_seconds += t.lap();
+    }
+    if (profile) {
+        fprintf(stderr, "[plan profile] rounds %d edges %lld expansions/ctx: absorb %.3f retire %.3f expand %.3f pack %.3f submit %.3f | "
+                        "device wait %.3f setup %.3f host %.3f s\n", m_stats.rounds, m_stats.edges_submitted, prof[0], prof[1],
+                prof[2], prof[3], prof[4], m_stats.device_seconds - m_stats.setup_seconds, m_stats.setup_seconds,
+                m_stats.host_seconds);
+        fprintf(stderr, "[plan profile]   absorb: coord+hash %.3f prefetch %.3f lookup/insert %.3f relax/heap %.3f s\n",
+                g_abs_prof[0], g_abs_prof[1], g_abs_prof[2], g_abs_prof[3]);
+        for (double& v : g_abs_prof) v = 0.0;
     }
     m_stats.edges_resolved_f64 = smplgpu_expand_batch_resolved(m_ctx) - resolved0;
     // nothing can be in flight here: a group's queries finish in absorb or expand, and a batch is only

@@ -97,7 +97,8 @@ private:
         std::vector<int> coords;
         std::vector<double> qs;
         std::vector<int> h, gdist;
-        std::vector<int> table;      // size is a power of two, -1 = empty
+        std::vector<uint64_t> table; // size is a power of two; slot = low 32 hash bits << 32 | state id, EMPTY = all ones
+        static constexpr uint64_t EMPTY = ~0ull;
         int size() const { return (int)h.size(); }
         const double* q(int id) const { return &qs[(size_t)id * dof]; }
         static uint64_t hash(const int* c, int dof)
@@ -108,9 +109,10 @@ private:
             }
             return x;
         }
-        int find(const int* c) const;
-        int add(const int* c, const double* q, int hv, int gd, bool index);   // index = enter it in the table
-        void grow();
+        int find(const int* c, uint64_t hv) const;
+        int add(const int* c, const double* q, int hval, int gd, bool index, uint64_t hv);   // index = enter it in the table
+        void grow(uint32_t new_tag, int new_id);
+        void enter(uint32_t tag, int id);
     };
     // g, h, f, eg are unsigned as in the reference's ARAStar::SearchState (arastar.h:176-187): a negative heuristic
     // (unreachable BFS cell: cost_per_cell * -1) sorts last in OPEN
@@ -123,7 +125,10 @@ private:
         int goal_h;
         Lattice lat;
         std::vector<SState> search;
-        std::vector<int> open; // 1-based heap of state ids
+        // 1-based binary heap of (f, state id): the key travels with the entry so that sifting reads one
+        // contiguous array instead of one search state per comparison (same comparisons as intrusive_heap.h)
+        struct HeapEntry { unsigned int f; int id; };
+        std::vector<HeapEntry> open;
         int expanding;         // state popped this round
         bool done;
         QueryResult result;
@@ -132,6 +137,9 @@ private:
         std::vector<std::pair<int, int>> goal_succ;
         // this round's successors (filled by expandOne, consumed by absorbOne)
         std::vector<double> succ_q1;
+        std::vector<int> succ_coord;   // absorbOne scratch: lattice coordinates / table slots of the valid successors
+        std::vector<uint64_t> succ_hslot;   // full hash of successor e
+        std::vector<int> succ_id;
         int n_succ;
         int edge_begin;
     };
