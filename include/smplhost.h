@@ -32,6 +32,12 @@ int smplhost_tables_set_acm_entry(smplhost_tables* h, const char* a, const char*
 /* AttachedBodiesCollisionModel::attachBody with a ready spheres model (attached_bodies_collision_model.cpp:70-141) */
 int smplhost_tables_attach_spheres(smplhost_tables* h, const char* id, const char* link,
                                    const double* centers, int n, double radius);
+/* AttachedBodiesCollisionModel::attachBody for a box (attached_bodies_collision_model.cpp:94-160, 264-309): the
+ * sphere model is generated as the reference does -- surface voxels of the shape at 0.025 / sqrt(2) with the voxel
+ * origin at zero (voxelised on the device, smplgpu_voxelize_mesh), one sphere of radius 0.025 per voxel.  pose3x4:
+ * the box in the frame of `link`.  Returns the number of spheres, negative on error. */
+int smplhost_tables_attach_box(smplhost_tables* h, smplgpu_ctx* ctx, const char* id, const char* link,
+                               const double size[3], const double* pose3x4);
 int smplhost_tables_detach(smplhost_tables* h, const char* id);
 /* KDLRobotModel::init + setPlanningLink + setKinematicsToPlanningTransform (kdl_robot_model.cpp:59-171) */
 int smplhost_tables_set_planning_chain(smplhost_tables* h, const char* root, const char* tip,

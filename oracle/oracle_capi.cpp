@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <array>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -150,6 +151,25 @@ int oracle_scene_attach_spheres(oracle_scene* s, const char* id, const char* lin
         c[i] = Vec3(centers[3 * i], centers[3 * i + 1], centers[3 * i + 2]);
     }
     return s->cc->attachSpheres(id, c, radius, link) ? 0 : -1;
+}
+
+/// AttachedBodiesCollisionModel::attachBody for a box shape: generateSpheresModel
+/// (attached_bodies_collision_model.cpp:264-309) -- VoxelizeShape at 0.025 / sqrt(2), voxel origin zero, one
+/// sphere of radius 0.025 per surface voxel.  Returns the number of spheres.
+int oracle_scene_attach_box(oracle_scene* s, const char* id, const char* link, const double* size, const double* pose3x4)
+{
+    const double object_enclosing_sphere_radius = 0.025;
+    const double zero[3] = { 0.0, 0.0, 0.0 };
+    Affine3 pose;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 4; ++c) pose.m[r][c] = pose3x4[4 * r + c];
+    }
+    std::vector<Vec3> voxels;
+    VoxelizeBox(size[0], size[1], size[2], pose, object_enclosing_sphere_radius / std::sqrt(2), zero, false, voxels);
+    if (!s->cc->attachSpheres(id, voxels, object_enclosing_sphere_radius, link)) {
+        return -1;
+    }
+    return (int)voxels.size();
 }
 
 int oracle_scene_detach(oracle_scene* s, const char* id)

@@ -142,6 +142,7 @@ def host_lib():
                                               c_int32_p, c_double_p]
         H.smplhost_interpolate_paths.argtypes = [vp, vp, c_double_p, c_int32_p, C.c_int, c_double_p, C.c_int, c_int32_p,
                                                  c_double_p]
+        H.smplhost_tables_attach_box.argtypes = [vp, vp, C.c_char_p, C.c_char_p, c_double_p, c_double_p]
         H.smplhost_box_meshes.argtypes = [c_double_p, C.c_int, c_double_p, c_int32_p]
         H.smplhost_adapters_create.restype = C.c_void_p
         H.smplhost_adapters_create.argtypes = [vp, vp, C.c_char_p, c_double_p, C.c_double, c_int32_p, C.c_double, C.c_int]
@@ -202,6 +203,15 @@ class RobotTables:
         c = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3)
         self._ck(self.H.smplhost_tables_attach_spheres(self.h, body_id.encode(), link.encode(), _dp(c), len(c),
                                                        float(radius)), "attach_spheres")
+
+    def attach_box(self, ctx, body_id, link, size, pose3x4):
+        """attachBody for a box: sphere model generated from the shape's surface voxels (on the device)."""
+        sz = np.ascontiguousarray(size, dtype=np.float64)
+        p = np.ascontiguousarray(pose3x4, dtype=np.float64).reshape(3, 4)
+        n = self.H.smplhost_tables_attach_box(self.h, ctx.h, body_id.encode(), link.encode(), _dp(sz), _dp(p))
+        if n < 0:
+            raise SmplGpuError("attach_box: " + self.H.smplhost_last_error().decode())
+        return n
 
     def detach(self, body_id):
         return self.H.smplhost_tables_detach(self.h, body_id.encode()) == 0

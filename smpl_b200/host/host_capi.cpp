@@ -2,6 +2,7 @@
 // Python plumbing (tests, bench.py) can drive it with ctypes.  Declared in
 // include/smplhost.h.
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <sstream>
@@ -92,6 +93,37 @@ int smplhost_tables_attach_spheres(smplhost_tables* h, const char* id, const cha
         return -1;
     }
     return 0;
+}
+
+// AttachedBodiesCollisionModel::attachBody for a box shape (attached_bodies_collision_model.cpp:94-160, 264-309):
+// generateSpheresModel voxelises the shape at 0.025 / sqrt(2) with the voxel origin at zero (surface voxels) and
+// puts a sphere of radius 0.025 on every voxel; the voxelisation runs on the device
+int smplhost_tables_attach_box(smplhost_tables* h, smplgpu_ctx* ctx, const char* id, const char* link,
+                               const double size[3], const double* pose3x4)
+{
+    if (!h || !ctx || !id || !link || !size || !pose3x4) return -1;
+    const double object_enclosing_sphere_radius = 0.025;
+    std::vector<double> vertices;
+    std::vector<int32_t> triangles;
+    smplhost::AppendBoxMesh(size[0], size[1], size[2], pose3x4, vertices, triangles);
+    const double zero[3] = { 0.0, 0.0, 0.0 };
+    const double res = object_enclosing_sphere_radius / std::sqrt(2);
+    int n = smplgpu_voxelize_mesh(ctx, vertices.data(), 8, triangles.data(), 12, res, zero, nullptr, 0);
+    if (n < 0) {
+        g_err = smplgpu_last_error(ctx);
+        return n;
+    }
+    std::vector<double> centers((size_t)std::max(n, 1) * 3);
+    n = smplgpu_voxelize_mesh(ctx, vertices.data(), 8, triangles.data(), 12, res, zero, centers.data(), n);
+    if (n < 0) {
+        g_err = smplgpu_last_error(ctx);
+        return n;
+    }
+    if (!h->t.attachSpheres(id, link, centers.data(), n, object_enclosing_sphere_radius)) {
+        g_err = "attach failed (unknown link, duplicate id or empty body)";
+        return -1;
+    }
+    return n;
 }
 
 int smplhost_tables_detach(smplhost_tables* h, const char* id)

@@ -483,6 +483,12 @@ class OracleScene:
         return h
 
 
+    def attach_box(self, body_id, link, size, pose3x4):
+        """attachBody for a box shape: spheres generated from the shape's surface voxels."""
+        sz = np.ascontiguousarray(size, dtype=np.float64)
+        p = np.ascontiguousarray(pose3x4, dtype=np.float64).reshape(3, 4)
+        return self.L.oracle_scene_attach_box(self.h, body_id.encode(), link.encode(), _dp(sz), _dp(p))
+
     def insert_boxes(self, boxes):
         """WorldCollisionModel::insertObject for box primitives: boxes[n][15] = size(3), pose 3x4 row-major."""
         b = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 15)

@@ -102,3 +102,37 @@ def test_surface_ingest_differs_from_filled_cells():
         assert d2[tuple(face)] == 0 and d2[tuple(centre)] >= 64      # 10 cells from every face, minus the shell
     finally:
         c.close()
+
+
+def test_attached_box_sphere_model_generated_from_voxels():
+    """attachBody (attached_bodies_collision_model.cpp:264-309): the body's spheres sit on its surface voxels at
+    0.025 / sqrt(2); generated on the device for the product, by the oracle's voxeliser for the check."""
+    scene = scenes.ubr1_tabletop_scene(attach=False)
+    pose = np.concatenate([np.eye(3), [[0.26], [0.0], [0.0]]], axis=1)      # the box in the wrist_roll_link frame
+    size = (0.05, 0.05, 0.20)
+    o = make_oracle(scene, with_kdl=False)
+    n_ref = o.attach_box("object", "wrist_roll_link", size, pose)
+    grasp = ("wrist_roll_link", "gripper_link", "left_gripper_finger_link", "right_gripper_finger_link")
+    for link in grasp:
+        o.acm_set("object", link, True)
+    c = api.GpuContext(0)
+    try:
+        tables = api.build_tables(scene)
+        n = tables.attach_box(c, "object", "wrist_roll_link", size, pose)
+        assert n == n_ref and n > 50
+        for link in grasp:
+            tables.set_acm_entry("object", link, True)
+        c.set_robot(tables)
+        c.build_distance_field(api.scene_cells(scene, tables), scene.dims, scene.origin, scene.res, scene.max_dist,
+                               scene.padding)
+        lo, hi, cont = tables.limits()
+        q = scenes.random_states(20000, lo, hi, cont, seed=9)
+        v = c.is_states_valid(q)
+        assert np.array_equal(v, o.is_states_valid(q))
+        q0, q1 = scenes.mprim_edges(q[:4000])
+        e, cnt = c.is_edges_valid(q0, q1)
+        e_ref, cnt_ref = o.is_edges_valid(q0, q1)
+        assert np.array_equal(e, e_ref) and np.array_equal(cnt, cnt_ref)
+        assert 0.02 < v.mean() < 0.9
+    finally:
+        c.close()
