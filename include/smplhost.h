@@ -154,6 +154,13 @@ int smplhost_interpolate_paths(smplgpu_ctx* ctx, smplhost_tables* tables, const 
  * the pose as a 3x4 row-major rigid transform; vertices[8 n_boxes][3], triangles[12 n_boxes][3] (indices into the
  * concatenated vertex array).  Feed the result to smplgpu_voxelize_mesh or smplgpu_build_distance_field_from_meshes. */
 int smplhost_box_meshes(const double* boxes, int n_boxes, double* vertices, int32_t* triangles);
+/* The same for any primitive of voxel_operations.cpp:121-170: shapes[n_shapes][16] = kind (0 box, 1 sphere,
+ * 2 cylinder, 3 cone), three dimensions (box l w h; sphere r; cylinder r length; cone r height), pose 3x4.
+ * CreateIndexed{Sphere,Cylinder,Cone}Mesh (mesh_utils.cpp:116-300) with the counts VoxelizeSphere etc. use
+ * (7 x 8 sphere, 16 rim points).  smplhost_shape_mesh_size gives the vertices / triangles one shape adds;
+ * smplhost_shape_meshes returns the total triangle count. */
+int smplhost_shape_mesh_size(int kind, int32_t* n_vertices, int32_t* n_triangles);
+int smplhost_shape_meshes(const double* shapes, int n_shapes, double* vertices, int32_t* triangles);
 
 #ifdef __cplusplus
 }

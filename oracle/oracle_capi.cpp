@@ -626,6 +626,26 @@ void oracle_box_mesh(double length, double width, double height, double* vertice
     std::copy(t.begin(), t.end(), indices);
 }
 
+/// CreateIndexed{Box,Sphere,Cylinder,Cone}Mesh at the origin (kind 0..3; dims = l,w,h / r / r,length / r,height);
+/// same signature as ref_shape_mesh.  Returns the vertex count, *n_indices the index count.
+int oracle_shape_mesh(int kind, const double* dims, double* vertices, int32_t* indices, int* n_indices)
+{
+    std::vector<Vec3> v;
+    std::vector<int> t;
+    if (kind == 0) CreateIndexedBoxMesh(dims[0], dims[1], dims[2], v, t);
+    else if (kind == 1) CreateIndexedSphereMesh(dims[0], 7, 8, v, t);
+    else if (kind == 2) CreateIndexedCylinderMesh(dims[0], dims[1], v, t);
+    else CreateIndexedConeMesh(dims[0], dims[1], v, t);
+    for (size_t i = 0; i < v.size(); ++i) {
+        vertices[3 * i] = v[i].x;
+        vertices[3 * i + 1] = v[i].y;
+        vertices[3 * i + 2] = v[i].z;
+    }
+    std::copy(t.begin(), t.end(), indices);
+    *n_indices = (int)t.size();
+    return (int)v.size();
+}
+
 /// WorldCollisionModel::insertObject (world_collision_model.cpp:193-234) for box primitives: VoxelizeBox with the
 /// grid origin as voxel origin, fill = false (voxel_operations.cpp:357-369), then addPointsToField.
 /// boxes[n][3 + 12] = size, pose 3x4.  Returns the number of voxels handed to the field.

@@ -83,4 +83,23 @@ void ref_box_mesh(double length, double width, double height, double* vertices, 
     for (size_t i = 0; i < t.size(); ++i) indices[i] = t[i];
 }
 
+/// geometry::CreateIndexed{Box,Sphere,Cylinder,Cone}Mesh (kind 0..3) with the parameters VoxelizeSphere etc. pass
+int ref_shape_mesh(int kind, const double* dims, double* vertices, int32_t* indices, int* n_indices)
+{
+    std::vector<Eigen::Vector3d> v;
+    std::vector<int> t;
+    if (kind == 0) sbpl::geometry::CreateIndexedBoxMesh(dims[0], dims[1], dims[2], v, t);
+    else if (kind == 1) sbpl::geometry::CreateIndexedSphereMesh(dims[0], 7, 8, v, t);
+    else if (kind == 2) sbpl::geometry::CreateIndexedCylinderMesh(dims[0], dims[1], v, t);
+    else sbpl::geometry::CreateIndexedConeMesh(dims[0], dims[1], v, t);
+    for (size_t i = 0; i < v.size(); ++i) {
+        vertices[3 * i] = v[i].x();
+        vertices[3 * i + 1] = v[i].y();
+        vertices[3 * i + 2] = v[i].z();
+    }
+    for (size_t i = 0; i < t.size(); ++i) indices[i] = t[i];
+    *n_indices = (int)t.size();
+    return (int)v.size();
+}
+
 } // extern "C"

@@ -30,6 +30,86 @@ void CreateIndexedBoxMesh(double length, double width, double height, std::vecto
     (void)base;
 }
 
+void CreateIndexedSphereMesh(double radius, int longitude_count, int latitude_count, std::vector<Vec3>& vertices, std::vector<int>& indices)
+{
+    vertices.push_back(Vec3(0.0, 0.0, radius));   // north pole
+    const double theta_inc = M_PI / (latitude_count + 1);
+    const double phi_inc = (2.0 * M_PI) / longitude_count;
+    for (int t = 0; t < latitude_count; ++t) {
+        for (int p = 0; p < longitude_count; ++p) {
+            const double theta = (t + 1) * theta_inc, phi = p * phi_inc;
+            vertices.push_back(Vec3(radius * std::sin(theta) * std::cos(phi), radius * std::sin(theta) * std::sin(phi),
+                                    radius * std::cos(theta)));
+        }
+    }
+    vertices.push_back(Vec3(0.0, 0.0, -radius));  // south pole
+    for (int i = 0; i < longitude_count; ++i) {   // fan around the north pole
+        indices.push_back(0);
+        indices.push_back(i + 1);
+        indices.push_back(i == longitude_count - 1 ? 1 : i + 2);
+    }
+    for (int i = 0; i < latitude_count - 1; ++i) {   // quads between neighbouring lines of latitude
+        for (int j = 0; j < longitude_count; ++j) {
+            const int base = i * longitude_count + j + 1;
+            const int below = base + longitude_count;
+            int below_right = below + 1, right = base + 1;
+            if ((below_right - 1) / longitude_count != (below - 1) / longitude_count) below_right -= longitude_count;
+            if ((right - 1) / longitude_count != (base - 1) / longitude_count) right -= longitude_count;
+            const int quad[6] = { base, below, below_right, base, below_right, right };
+            indices.insert(indices.end(), quad, quad + 6);
+        }
+    }
+    const int last = (int)vertices.size() - 1;    // the reference uses the size of the WHOLE vertex array here
+    for (int i = 0; i < longitude_count; ++i) {   // fan around the south pole
+        indices.push_back(last);
+        indices.push_back(i == 0 ? last - longitude_count : last - i);
+        indices.push_back(last - (i + 1));
+    }
+}
+
+void CreateIndexedCylinderMesh(double radius, double length, std::vector<Vec3>& vertices, std::vector<int>& indices)
+{
+    const int rim = 16;
+    for (int cap = 0; cap < 2; ++cap) {
+        for (int i = 0; i < rim; ++i) {
+            const double theta = 2.0 * M_PI * (double)i / double(rim);
+            vertices.push_back(Vec3(radius * std::cos(theta), radius * std::sin(theta), cap == 0 ? 0.5 * length : -0.5 * length));
+        }
+    }
+    vertices.push_back(Vec3(0.0, 0.0, 0.5 * length));
+    vertices.push_back(Vec3(0.0, 0.0, -0.5 * length));
+    for (int i = 0; i < rim; ++i) {
+        const int n = (i + 1) % rim;
+        const int side[6] = { i, n, i + rim, n, n + rim, i + rim };
+        indices.insert(indices.end(), side, side + 6);
+    }
+    for (int i = 0; i < rim; ++i) {
+        const int top[3] = { 2 * rim, (i + 1) % rim, i };
+        indices.insert(indices.end(), top, top + 3);
+    }
+    for (int i = 0; i < rim; ++i) {
+        const int bottom[3] = { 2 * rim + 1, (i + 1) % rim + rim, i + rim };
+        indices.insert(indices.end(), bottom, bottom + 3);
+    }
+}
+
+void CreateIndexedConeMesh(double radius, double height, std::vector<Vec3>& vertices, std::vector<int>& indices)
+{
+    const int rim = 16;
+    for (int i = 0; i < rim; ++i) {
+        const double theta = 2.0 * M_PI * (double)i / (double)rim;
+        vertices.push_back(Vec3(radius * std::cos(theta), radius * std::sin(theta), -0.5 * height));
+    }
+    vertices.push_back(Vec3(0.0, 0.0, 0.5 * height));
+    vertices.push_back(Vec3(0.0, 0.0, -0.5 * height));
+    for (int apex = rim; apex <= rim + 1; ++apex) {   // the mantle, then the bottom fan
+        for (int i = 0; i < rim; ++i) {
+            const int tri[3] = { i, (i + 1) % rim, apex };
+            indices.insert(indices.end(), tri, tri + 3);
+        }
+    }
+}
+
 int VoxelDiscretizer::discretize(int axis, double d) const
 {
     if (half_res) {

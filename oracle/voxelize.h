@@ -2,7 +2,7 @@
 //
 // CPU restatement of the reference's scene ingest: shapes -> triangle mesh ->
 // surface voxels -> OccupancyGrid::addPointsToField.
-//   CreateIndexedBoxMesh      smpl/src/geometry/mesh_utils.cpp:39-113
+//   CreateIndexedBoxMesh / SphereMesh / CylinderMesh / ConeMesh   smpl/src/geometry/mesh_utils.cpp:39-300
 //   VoxelizeBox / VoxelizeMesh (pose, res, voxel_origin)   smpl/src/geometry/voxelize.cpp:673-736, 962-1054
 //   VoxelizeMeshAwesome       voxelize.cpp:134-146
 //   VoxelizeTriangle          smpl/include/smpl/geometry/detail/voxelize.hpp:45-181
@@ -30,6 +30,12 @@ namespace oracle {
 
 /// mesh_utils.cpp:39-113: 8 vertices, 12 triangles (36 indices), appended
 void CreateIndexedBoxMesh(double length, double width, double height, std::vector<Vec3>& vertices, std::vector<int>& indices);
+
+/// mesh_utils.cpp:116-205 (VoxelizeSphere passes 7 lines of longitude, 8 of latitude: voxelize.cpp:741-811),
+/// :208-264 (16 rim points), :268-300 (16 rim points); all appended, indices relative to this shape's first vertex
+void CreateIndexedSphereMesh(double radius, int longitude_count, int latitude_count, std::vector<Vec3>& vertices, std::vector<int>& indices);
+void CreateIndexedCylinderMesh(double radius, double length, std::vector<Vec3>& vertices, std::vector<int>& indices);
+void CreateIndexedConeMesh(double radius, double height, std::vector<Vec3>& vertices, std::vector<int>& indices);
 
 /// One of the reference's two voxel grids: cells centred on pivot + i res (PivotVoxelGrid) or on (i + 1/2) res
 /// (HalfResVoxelGrid)

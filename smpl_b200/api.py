@@ -144,6 +144,8 @@ def host_lib():
                                                  c_double_p]
         H.smplhost_tables_attach_box.argtypes = [vp, vp, C.c_char_p, C.c_char_p, c_double_p, c_double_p]
         H.smplhost_box_meshes.argtypes = [c_double_p, C.c_int, c_double_p, c_int32_p]
+        H.smplhost_shape_mesh_size.argtypes = [C.c_int, c_int32_p, c_int32_p]
+        H.smplhost_shape_meshes.argtypes = [c_double_p, C.c_int, c_double_p, c_int32_p]
         H.smplhost_adapters_create.restype = C.c_void_p
         H.smplhost_adapters_create.argtypes = [vp, vp, C.c_char_p, c_double_p, C.c_double, c_int32_p, C.c_double, C.c_int]
         H.smplhost_adapters_destroy.argtypes = [vp]
@@ -770,6 +772,27 @@ def box_meshes(boxes):
     if H.smplhost_box_meshes(_dp(b), len(b), _dp(v), _ip(t)) != 0:
         raise SmplGpuError("box_meshes: " + H.smplhost_last_error().decode())
     return v, t
+
+
+SHAPE_BOX, SHAPE_SPHERE, SHAPE_CYLINDER, SHAPE_CONE = 0, 1, 2, 3
+
+
+def shape_meshes(shapes):
+    """smplhost_shape_meshes: shapes[n][16] = kind, 3 dimensions, pose 3x4 -> (vertices[.][3], triangles[.][3])."""
+    H = host_lib()
+    sh = np.ascontiguousarray(shapes, dtype=np.float64).reshape(-1, 16)
+    nv = nt = 0
+    for row in sh:
+        a, b = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        if H.smplhost_shape_mesh_size(int(row[0]), _ip(a), _ip(b)) != 0:
+            raise SmplGpuError("shape_meshes: unknown shape kind %d" % int(row[0]))
+        nv += int(a[0])
+        nt += int(b[0])
+    v = np.zeros((max(nv, 1), 3), np.float64)
+    t = np.zeros((max(nt, 1), 3), np.int32)
+    if H.smplhost_shape_meshes(_dp(sh), len(sh), _dp(v), _ip(t)) != nt:
+        raise SmplGpuError("shape_meshes: " + H.smplhost_last_error().decode())
+    return v[:nv], t[:nt]
 
 
 def setup_context(scene, device=0, ctx=None):

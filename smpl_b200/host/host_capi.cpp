@@ -609,6 +609,36 @@ int smplhost_interpolate_paths(smplgpu_ctx* ctx, smplhost_tables* tables, const 
 // scene ingest (scene_ingest.h)
 ///////////////////////////////////////////////////////////////////////////////
 
+int smplhost_shape_mesh_size(int kind, int32_t* n_vertices, int32_t* n_triangles)
+{
+    if (!n_vertices || !n_triangles) return SMPLGPU_ERR_INVALID;
+    int nv = 0, nt = 0;
+    smplhost::ShapeMeshSize(kind, &nv, &nt);
+    *n_vertices = nv;
+    *n_triangles = nt;
+    return nv > 0 ? 0 : SMPLGPU_ERR_INVALID;
+}
+
+int smplhost_shape_meshes(const double* shapes, int n_shapes, double* vertices, int32_t* triangles)
+{
+    if (n_shapes < 0 || (n_shapes > 0 && (!shapes || !vertices || !triangles))) {
+        g_err = "smplhost_shape_meshes: bad argument";
+        return SMPLGPU_ERR_INVALID;
+    }
+    std::vector<double> v;
+    std::vector<int32_t> t;
+    for (int i = 0; i < n_shapes; ++i) {
+        const double* s = shapes + 16 * (size_t)i;
+        if (!smplhost::AppendShapeMesh((int)s[0], s + 1, s + 4, v, t)) {
+            g_err = "smplhost_shape_meshes: unknown shape kind";
+            return SMPLGPU_ERR_INVALID;
+        }
+    }
+    std::copy(v.begin(), v.end(), vertices);
+    std::copy(t.begin(), t.end(), triangles);
+    return (int)(t.size() / 3);
+}
+
 int smplhost_box_meshes(const double* boxes, int n_boxes, double* vertices, int32_t* triangles)
 {
     if (n_boxes < 0 || (n_boxes > 0 && (!boxes || !vertices || !triangles))) {

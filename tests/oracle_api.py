@@ -252,6 +252,18 @@ def voxelize_box(which, size, pose3x4, res, voxel_origin=None, fill=False):
         cap = -n
 
 
+def shape_mesh(which, kind, dims):
+    """geometry::CreateIndexed{Box,Sphere,Cylinder,Cone}Mesh (kind 0..3) at the origin: (vertices, triangles)."""
+    L, pre = _vox_lib(which)
+    d = np.zeros(3, np.float64)
+    d[:len(dims)] = dims
+    v = np.zeros((64, 3), np.float64)
+    t = np.zeros(3 * 128, np.int32)
+    ni = C.c_int(0)
+    nv = getattr(L, pre + "shape_mesh")(int(kind), _dp(d), _dp(v), _ip(t), C.byref(ni))
+    return v[:nv].copy(), t[:ni.value].reshape(-1, 3).copy()
+
+
 def box_mesh(which, size):
     """geometry::CreateIndexedBoxMesh: (vertices[8][3], triangles[12][3])."""
     L, pre = _vox_lib(which)

@@ -42,6 +42,18 @@ def test_triangle_soups_equal_oracle(ctx):
     assert total > 5000
 
 
+@pytest.mark.parametrize("kind,dims", [(1, (0.17, 0, 0)), (2, (0.09, 0.42, 0)), (3, (0.12, 0.3, 0))])
+def test_sphere_cylinder_cone_voxels_equal_oracle(ctx, kind, dims):
+    rng = np.random.default_rng(kind)
+    from test_oracle_voxelize import random_pose
+    for res, origin in ((0.02, (-0.5, -1.0, 0.0)), (0.025 / np.sqrt(2), (0.0, 0.0, 0.0)), (0.01, None)):
+        pose = random_pose(rng, 0.5)
+        v, t = api.shape_meshes(np.concatenate([[kind], dims, pose.ravel()])[None, :])
+        got = ctx.voxelize_mesh(v, t, res, origin)
+        ref = voxelize_mesh("oracle", v, t, res, origin, False)
+        assert len(ref) > 100 and np.array_equal(got, ref)
+
+
 def test_degenerate_and_empty_meshes(ctx):
     v = np.array([[0.0, 0, 0], [1, 0, 0], [2, 0, 0], [0.5, 0, 0]])
     assert len(ctx.voxelize_mesh(v, [[0, 1, 2], [0, 0, 3]], 0.05, (0, 0, 0))) == 0      # colinear / repeated vertex

@@ -103,3 +103,33 @@ def test_golden_fixture_from_reference_build():
     for seed in range(N_SOUP):
         v, t, res, origin, fill = soup_case(seed)
         assert np.array_equal(voxelize_mesh("oracle", v, t, res, origin, fill), g["soup_%d" % seed]), seed
+
+
+SHAPES = [(0, (0.3, 0.2, 0.1)), (1, (0.17,)), (2, (0.09, 0.42)), (3, (0.12, 0.3))]
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,dims", SHAPES)
+def test_primitive_meshes_equal_reference(kind, dims):
+    """Oracle restatement AND the product's host-side builder (smplhost_shape_meshes) against the reference's
+    CreateIndexed*Mesh: same vertices (bitwise) and the same triangles in the same order."""
+    from oracle_api import shape_mesh
+    from smpl_b200 import api
+    v_ref, t_ref = shape_mesh("reference", kind, dims)
+    v_or, t_or = shape_mesh("oracle", kind, dims)
+    assert np.array_equal(v_ref, v_or) and np.array_equal(t_ref, t_or)
+    d = np.zeros(3)
+    d[:len(dims)] = dims
+    row = np.concatenate([[kind], d, np.eye(4)[:3].ravel()])
+    v, t = api.shape_meshes(row[None, :])
+    assert np.array_equal(v, v_ref) and np.array_equal(t, t_ref)
+    # two shapes in one call: the second one's triangles are offset by the first one's vertices, the pose moves it
+    pose = np.concatenate([np.eye(3), [[0.5], [-0.25], [1.0]]], axis=1)
+    v2, t2 = api.shape_meshes(np.stack([row, np.concatenate([[kind], d, pose.ravel()])]))
+    assert np.array_equal(v2[:len(v)], v_ref) and np.array_equal(v2[len(v):], v_ref + pose[:, 3])
+    assert np.array_equal(t2[len(t):], t_ref + len(v))
+    # VoxelizeSphere / VoxelizeCylinder / VoxelizeCone = this mesh through VoxelizeMesh
+    for res, origin in ((0.02, (-0.5, -1.0, 0.0)), (0.025 / np.sqrt(2), (0.0, 0.0, 0.0)), (0.01, None)):
+        vox_ref = voxelize_mesh("reference", v2[len(v):], t_ref, res, origin, False)
+        vox = voxelize_mesh("oracle", v2[len(v):], t_ref, res, origin, False)
+        assert len(vox_ref) > 100 and np.array_equal(vox, vox_ref)
