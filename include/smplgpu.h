@@ -299,6 +299,14 @@ int smplgpu_bfs_bank_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz);
 /* The same for n listed slots only (slots[n], seeds_xyz[n][3]); the other slots keep their distances, so a
  * finished query's slot can be handed to the next query while the rest keep searching */
 int smplgpu_bfs_bank_run_slots(smplgpu_ctx* ctx, const int32_t* slots, const int32_t* seeds_xyz, int n);
+/* The same without waiting: the run is queued on a stream of its own and the call returns, so expansion batches of
+ * the OTHER slots keep flowing while the newly admitted queries' BFS runs (BFS_3D runs in a background thread in the
+ * reference too, bfs3d.cpp:156-201).  One run in flight per context; the listed slots must not be read
+ * (smplgpu_expand_batch*, smplgpu_bfs_bank_distances) before smplgpu_bfs_bank_run_done returns 1 or
+ * smplgpu_bfs_bank_run_wait returns.  smplgpu_bfs_bank_run_done: 1 finished / nothing in flight, 0 still running. */
+int smplgpu_bfs_bank_run_slots_async(smplgpu_ctx* ctx, const int32_t* slots, const int32_t* seeds_xyz, int n);
+int smplgpu_bfs_bank_run_done(smplgpu_ctx* ctx);
+int smplgpu_bfs_bank_run_wait(smplgpu_ctx* ctx);
 /* BFS_3D::getDistance(cell) of slot[i] */
 int smplgpu_bfs_bank_distances(smplgpu_ctx* ctx, const int32_t* slot, const int32_t* cells_xyz, int n, int32_t* out);
 /* One ManipLattice::GetSuccs worth of device work for MANY expansions at once

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -96,6 +98,14 @@ struct smplgpu_ctx
     int64_t exp_resolved_total = 0;   // edges of expansion batches resolved in double, since creation
     cudaEvent_t ev_in[2] = { nullptr, nullptr };   // chunk b: inputs on the device
     cudaStream_t copy_stream = nullptr;
+    // asynchronous bank runs (smplgpu_bfs_bank_run_slots_async): their own stream, staging and seed counter
+    cudaStream_t bfs_stream = nullptr;
+    cudaEvent_t ev_bfs = nullptr;
+    void* d_bank_stage = nullptr; size_t bank_stage_cap = 0;
+    void* h_bank_stage = nullptr; size_t h_bank_stage_cap = 0;
+    int* d_bank_seed_count = nullptr;
+    int bank_run_state = 0;               // 0 none, 1 staged on the host (waiting for the device's turn), 2 queued
+    std::vector<int32_t> staged_slots, staged_seeds;
     unsigned long long* d_stats = nullptr;
     unsigned long long h_stats[4] = { 0, 0, 0, 0 };
 };
@@ -215,6 +225,9 @@ smplgpu_ctx* smplgpu_create(int device)
     if ((e = cudaMalloc(&ctx->d_seed_count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc(seed)", e);
     if ((e = cudaMalloc(&ctx->d_unc_count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc(unc)", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->bfs_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_bfs, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&ctx->d_bank_seed_count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc(seed)", e);
     for (int i = 0; i < 2; ++i) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
         if ((e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -262,6 +275,8 @@ static void free_bfs(smplgpu_ctx* ctx)
     ctx->has_bfs = false;
 }
 
+static int finish_bank_run(smplgpu_ctx* ctx);   // waits for an asynchronous bank run (defined with the bank)
+
 void smplgpu_destroy(smplgpu_ctx* ctx)
 {
     if (!ctx) {
@@ -269,6 +284,8 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
     }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    finish_bank_run(ctx);
+    if (ctx->bfs_stream) cudaStreamSynchronize(ctx->bfs_stream);
     free_bfs(ctx);
     free_grid(ctx->bank);
     free_tiles(ctx->bank_tiles);
@@ -287,6 +304,10 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
         cudaFree(ctx->d_exp[i]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->bfs_stream) cudaStreamDestroy(ctx->bfs_stream);
+    if (ctx->ev_bfs) cudaEventDestroy(ctx->ev_bfs);
+    cudaFree(ctx->d_bank_stage); cudaFree(ctx->d_bank_seed_count);
+    if (ctx->h_bank_stage) cudaFreeHost(ctx->h_bank_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx->h_model;
     delete ctx;
@@ -1552,8 +1573,11 @@ static int wall_threshold(const smplgpu_ctx* ctx, double inflation_radius)
 
 // reset + seed + all levels on one grid; seeds already on the device (padded-grid-free coordinates)
 static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_seeds, int n_seeds, int* levels_out,
-                    const uint8_t* d_slot_mask = nullptr, int slot_dz = 1)
+                    const uint8_t* d_slot_mask = nullptr, int slot_dz = 1, cudaStream_t stream = nullptr,
+                    int* d_seed_count = nullptr)
 {
+    if (stream == nullptr) stream = ctx->stream;
+    if (d_seed_count == nullptr) d_seed_count = ctx->d_seed_count;
     const int total = (int)words;
     BfsTiles& t = (&g == &ctx->bank) ? ctx->bank_tiles : ctx->bfs_tiles;
     // AUTO: the tile kernel for a single grid (bound by the per-level latency), the level kernel for the stacked
@@ -1563,24 +1587,24 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
     {
         // one warp per 32 bitmap words; at least one thread per row for the candidate stamps
         const long long threads = std::max<long long>(g.rows, std::min<long long>((long long)total, 148LL * 2048 * 4));
-        bfs_reset_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(g, d_slot_mask, slot_dz);
+        bfs_reset_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(g, d_slot_mask, slot_dz);
     }
     ++ctx->launches;
     if (tiles) {
-        bfs_tiles_reset_kernel<<<std::min((total + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(g, t, d_slot_mask, slot_dz);
+        bfs_tiles_reset_kernel<<<std::min((total + 255) / 256, 148 * 16), 256, 0, stream>>>(g, t, d_slot_mask, slot_dz);
         ++ctx->launches;
-        CU(cudaMemsetAsync(t.ver, 0, ((size_t)7 * t.ntiles + 16) * sizeof(uint32_t), ctx->stream));
+        CU(cudaMemsetAsync(t.ver, 0, ((size_t)7 * t.ntiles + 16) * sizeof(uint32_t), stream));
     }
     if (n_seeds <= 0) {
         CU(cudaGetLastError());
         return 0;
     }
-    CU(cudaMemsetAsync(ctx->d_seed_count, 0, sizeof(int), ctx->stream));
-    bfs_seed_kernel<<<(n_seeds + 127) / 128, 128, 0, ctx->stream>>>(g, d_seeds, n_seeds, ctx->d_seed_count);
+    CU(cudaMemsetAsync(d_seed_count, 0, sizeof(int), stream));
+    bfs_seed_kernel<<<(n_seeds + 127) / 128, 128, 0, stream>>>(g, d_seeds, n_seeds, d_seed_count);
     ++ctx->launches;
     long long cap = (long long)g.nx * g.ny * g.nz;
     if (tiles) {
-        bfs_tiles_seed_kernel<<<(n_seeds + 127) / 128, 128, 0, ctx->stream>>>(g, t, d_seeds, n_seeds);
+        bfs_tiles_seed_kernel<<<(n_seeds + 127) / 128, 128, 0, stream>>>(g, t, d_seeds, n_seeds);
         ++ctx->launches;
         // persistent cooperative kernel: TILE_K levels per grid barrier, one 1024-thread block per SM
         int per_sm = 0;
@@ -1589,7 +1613,7 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
         const int blocks = std::max(1, std::min(ctx->sm_count * per_sm, t.ntiles));
         int max_steps = (int)std::min<long long>(cap / TILE_K + 2, 0x7FFFFFFFLL / blocks - 1);
         void* args[] = { (void*)&g, (void*)&t, (void*)&max_steps };
-        CU(cudaLaunchCooperativeKernel((void*)bfs_tiles_kernel, dim3(blocks), dim3(TILE_THREADS), args, 0, ctx->stream));
+        CU(cudaLaunchCooperativeKernel((void*)bfs_tiles_kernel, dim3(blocks), dim3(TILE_THREADS), args, 0, stream));
         ++ctx->launches;
     } else {
         // persistent cooperative kernel, one block per SM (the grid barrier costs one arrival per block)
@@ -1597,15 +1621,19 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_levels_kernel, BFS_THREADS, 0));
         if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS kernel does not fit an SM");
         const int groups = (g.rows + 7) / 8;
-        const int blocks = std::max(1, std::min(ctx->sm_count, groups));
+        // A block of this kernel takes a whole SM (1024 threads x 62 registers).  A run queued behind the caller's
+        // back (smplgpu_bfs_bank_run_slots_async) leaves an eighth of the SMs to the expansion batches that are
+        // meant to keep flowing meanwhile; a synchronous run takes them all.
+        const int sms = stream == ctx->bfs_stream ? ctx->sm_count - std::max(1, ctx->sm_count / 8) : ctx->sm_count;
+        const int blocks = std::max(1, std::min(sms, groups));
         int max_levels = (int)std::min<long long>(cap, (1LL << 22));
         max_levels = (int)std::min<long long>(max_levels, 0x7FFFFFFFLL / blocks - 1);   // barrier target level * blocks
         void* args[] = { (void*)&g, (void*)&max_levels };
-        CU(cudaLaunchCooperativeKernel((void*)bfs_levels_kernel, dim3(blocks), dim3(BFS_THREADS), args, 0, ctx->stream));
+        CU(cudaLaunchCooperativeKernel((void*)bfs_levels_kernel, dim3(blocks), dim3(BFS_THREADS), args, 0, stream));
         ++ctx->launches;
     }
     if (levels_out) {
-        CU(cudaMemcpyAsync(levels_out, g.ctrl, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(levels_out, g.ctrl, sizeof(int), cudaMemcpyDeviceToHost, stream));
     }
     return 0;
 }
@@ -1824,6 +1852,10 @@ int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radi
 {
     if (!ctx || n_slots <= 0) return SMPLGPU_ERR_INVALID;
     if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "distance field not set");
+    {
+        const int fr = finish_bank_run(ctx);
+        if (fr) return fr;
+    }
     const int nx = ctx->grid.nx, ny = ctx->grid.ny, nz = ctx->grid.nz;
     const long long total_nz = (long long)n_slots * (nz + 2) - 2;
     if ((long long)(nx + 2) * (ny + 2) * (total_nz + 2) > 0x7FFFFFFFLL)
@@ -1856,44 +1888,172 @@ int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radi
     return (int)count;
 }
 
+// queues one bank run (walls of the listed slots from the field, reset, wavefront) on `stream`; the seeds and the
+// slot mask are staged in page-locked memory owned by the context, so nothing of the caller is read afterwards
+static int launch_bank_run(smplgpu_ctx* ctx, const int32_t* slots, const int32_t* seeds_xyz, int n, cudaStream_t stream,
+                           int* d_seed_count, int* n_seeds_out)
+{
+    const int nx = ctx->grid.nx, ny = ctx->grid.ny, nz = ctx->grid.nz;
+    const size_t seed_cap = ((size_t)n * 3 * sizeof(int) + 15) / 16 * 16;
+    const size_t need = seed_cap + (size_t)ctx->bank_slots + 64;
+    int r = grow(ctx, &ctx->d_bank_stage, &ctx->bank_stage_cap, need);
+    if (r) return r;
+    if (need > ctx->h_bank_stage_cap) {
+        if (ctx->h_bank_stage) { CU(cudaFreeHost(ctx->h_bank_stage)); ctx->h_bank_stage = nullptr; ctx->h_bank_stage_cap = 0; }
+        CU(cudaMallocHost(&ctx->h_bank_stage, need));
+        ctx->h_bank_stage_cap = need;
+    }
+    int* h_seeds = (int*)ctx->h_bank_stage;
+    uint8_t* h_mask = (uint8_t*)ctx->h_bank_stage + seed_cap;
+    memset(h_mask, 0, (size_t)ctx->bank_slots);
+    int n_in = 0;
+    for (int i = 0; i < n; ++i) {
+        const int s = slots[i];
+        if (s < 0 || s >= ctx->bank_slots) return fail(ctx, SMPLGPU_ERR_INVALID, "slot %d out of range", s);
+        if (h_mask[s]) return fail(ctx, SMPLGPU_ERR_INVALID, "slot %d listed twice", s);
+        h_mask[s] = 1;
+        const int x = seeds_xyz[3 * i], y = seeds_xyz[3 * i + 1], z = seeds_xyz[3 * i + 2];
+        if (x >= 0 && y >= 0 && z >= 0 && x < nx && y < ny && z < nz) {
+            h_seeds[3 * n_in] = x; h_seeds[3 * n_in + 1] = y; h_seeds[3 * n_in + 2] = s * ctx->bank_slot_dz + z;
+            ++n_in;
+        }
+    }
+    uint8_t* d_mask = (uint8_t*)ctx->d_bank_stage + seed_cap;
+    if (n_in > 0) {
+        CU(cudaMemcpyAsync(ctx->d_bank_stage, h_seeds, (size_t)n_in * 3 * sizeof(int), cudaMemcpyHostToDevice, stream));
+    }
+    CU(cudaMemcpyAsync(d_mask, h_mask, (size_t)ctx->bank_slots, cudaMemcpyHostToDevice, stream));
+    // every run starts from the scene's walls: a fresh BfsHeuristic per query (seeding a wall cell
+    // un-walls it for the lifetime of a BFS_3D object, bfs3d.cpp:181-187 -- not across queries here)
+    unsigned int* d_count = (unsigned int*)d_seed_count;
+    CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), stream));
+    bfs_walls_from_df_kernel<<<((int)ctx->bank_words + 255) / 256, 256, 0, stream>>>(
+        ctx->bank, ctx->d_df, ctx->bank_kmax, ctx->bank_slot_dz, d_count, d_mask);
+    ++ctx->launches;
+    r = run_grid(ctx, ctx->bank, ctx->bank_words, (const int*)ctx->d_bank_stage, n_in, nullptr, d_mask, ctx->bank_slot_dz, stream,
+                 d_seed_count);
+    if (r) return r;
+    *n_seeds_out = n_in;
+    return 0;
+}
+
+// A block of the wavefront kernel takes a whole SM and waits at grid barriers, so two bank runs queued at once
+// (several planner contexts share a GPU) would deal the second one's blocks onto the SMs the first one leaves to the
+// expansion batches and stall there.  Asynchronous runs therefore take turns: one per device in the GPU's queue;
+// the others stay staged on the host until the turn is free (checked whenever their owner polls).
+static std::atomic<int> g_bank_turn[64];   // per device: 1 while an asynchronous run is queued or running
+
+static int launch_staged_bank_run(smplgpu_ctx* ctx)
+{
+    // after whatever the caller queued on the main stream (e.g. the bank's creation)
+    CU(cudaEventRecord(ctx->ev_bfs, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->bfs_stream, ctx->ev_bfs, 0));
+    int n_in = 0;
+    int r = launch_bank_run(ctx, ctx->staged_slots.data(), ctx->staged_seeds.data(), (int)ctx->staged_slots.size(),
+                            ctx->bfs_stream, ctx->d_bank_seed_count, &n_in);
+    if (r) return r;
+    CU(cudaEventRecord(ctx->ev_bfs, ctx->bfs_stream));
+    ctx->bank_run_state = 2;
+    return 0;
+}
+
+static bool take_bank_turn(smplgpu_ctx* ctx)
+{
+    int expected = 0;
+    return g_bank_turn[ctx->device & 63].compare_exchange_strong(expected, 1);
+}
+
+static void release_bank_turn(smplgpu_ctx* ctx)
+{
+    g_bank_turn[ctx->device & 63].store(0);
+}
+
+// blocks until the context's asynchronous run (if any) has finished
+static int finish_bank_run(smplgpu_ctx* ctx)
+{
+    if (ctx->bank_run_state == 1) {
+        while (!take_bank_turn(ctx)) {
+            std::this_thread::yield();
+        }
+        const int r = launch_staged_bank_run(ctx);
+        if (r) {
+            ctx->bank_run_state = 0;
+            release_bank_turn(ctx);
+            return r;
+        }
+    }
+    if (ctx->bank_run_state == 2) {
+        const cudaError_t e = cudaEventSynchronize(ctx->ev_bfs);
+        ctx->bank_run_state = 0;
+        release_bank_turn(ctx);
+        if (e != cudaSuccess) return fail(ctx, SMPLGPU_ERR_CUDA, "bank run: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
 int smplgpu_bfs_bank_run_slots(smplgpu_ctx* ctx, const int32_t* slots, const int32_t* seeds_xyz, int n)
 {
     if (!ctx || n < 0 || (n > 0 && (!slots || !seeds_xyz))) return SMPLGPU_ERR_INVALID;
     if (!ctx->has_bank) return fail(ctx, SMPLGPU_ERR_STATE, "BFS bank not created");
     if (n == 0) return 0;
-    const int nx = ctx->grid.nx, ny = ctx->grid.ny, nz = ctx->grid.nz;
-    std::vector<int> inb;
-    std::vector<uint8_t> mask(ctx->bank_slots, 0);
+    int r = finish_bank_run(ctx);   // one run at a time: the staging buffers and the wavefront state are shared
+    if (r) return r;
+    int n_in = 0;
+    r = launch_bank_run(ctx, slots, seeds_xyz, n, ctx->stream, ctx->d_seed_count, &n_in);
+    if (r) return r;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return n_in;
+}
+
+int smplgpu_bfs_bank_run_slots_async(smplgpu_ctx* ctx, const int32_t* slots, const int32_t* seeds_xyz, int n)
+{
+    if (!ctx || n < 0 || (n > 0 && (!slots || !seeds_xyz))) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_bank) return fail(ctx, SMPLGPU_ERR_STATE, "BFS bank not created");
+    if (ctx->bank_run_state != 0) return fail(ctx, SMPLGPU_ERR_STATE, "a bank run is already in flight");
+    if (n == 0) return 0;
     for (int i = 0; i < n; ++i) {
-        const int s = slots[i];
-        if (s < 0 || s >= ctx->bank_slots) return fail(ctx, SMPLGPU_ERR_INVALID, "slot %d out of range", s);
-        if (mask[s]) return fail(ctx, SMPLGPU_ERR_INVALID, "slot %d listed twice", s);
-        mask[s] = 1;
-        const int x = seeds_xyz[3 * i], y = seeds_xyz[3 * i + 1], z = seeds_xyz[3 * i + 2];
-        if (x >= 0 && y >= 0 && z >= 0 && x < nx && y < ny && z < nz) {
-            inb.push_back(x); inb.push_back(y); inb.push_back(s * ctx->bank_slot_dz + z);
+        if (slots[i] < 0 || slots[i] >= ctx->bank_slots) return fail(ctx, SMPLGPU_ERR_INVALID, "slot %d out of range", slots[i]);
+    }
+    ctx->staged_slots.assign(slots, slots + n);
+    ctx->staged_seeds.assign(seeds_xyz, seeds_xyz + 3 * (size_t)n);
+    ctx->bank_run_state = 1;
+    if (take_bank_turn(ctx)) {
+        const int r = launch_staged_bank_run(ctx);
+        if (r) {
+            ctx->bank_run_state = 0;
+            release_bank_turn(ctx);
+            return r;
         }
     }
-    const int n_in = (int)inb.size() / 3;
-    const size_t seed_bytes = (inb.size() * sizeof(int) + 15) / 16 * 16;
-    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, seed_bytes + mask.size() + 64);
-    if (r) return r;
-    uint8_t* d_mask = (uint8_t*)ctx->d_misc + seed_bytes;
-    if (n_in > 0) {
-        CU(cudaMemcpyAsync(ctx->d_misc, inb.data(), inb.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    return n;
+}
+
+int smplgpu_bfs_bank_run_done(smplgpu_ctx* ctx)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    if (ctx->bank_run_state == 0) return 1;
+    if (ctx->bank_run_state == 1) {
+        if (!take_bank_turn(ctx)) return 0;   // another context's run has the GPU
+        const int r = launch_staged_bank_run(ctx);
+        if (r) {
+            ctx->bank_run_state = 0;
+            release_bank_turn(ctx);
+            return r;
+        }
+        return 0;
     }
-    CU(cudaMemcpyAsync(d_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, ctx->stream));
-    // every run starts from the scene's walls: a fresh BfsHeuristic per query (seeding a wall cell
-    // un-walls it for the lifetime of a BFS_3D object, bfs3d.cpp:181-187 -- not across queries here)
-    unsigned int* d_count = (unsigned int*)ctx->d_seed_count;
-    CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), ctx->stream));
-    bfs_walls_from_df_kernel<<<((int)ctx->bank_words + 255) / 256, 256, 0, ctx->stream>>>(
-        ctx->bank, ctx->d_df, ctx->bank_kmax, ctx->bank_slot_dz, d_count, d_mask);
-    ++ctx->launches;
-    r = run_grid(ctx, ctx->bank, ctx->bank_words, (const int*)ctx->d_misc, n_in, nullptr, d_mask, ctx->bank_slot_dz);
-    if (r) return r;
-    CU(cudaStreamSynchronize(ctx->stream));   // the host vectors above are read by the async copies
-    return n_in;
+    const cudaError_t e = cudaEventQuery(ctx->ev_bfs);
+    if (e == cudaErrorNotReady) return 0;
+    ctx->bank_run_state = 0;
+    release_bank_turn(ctx);
+    if (e != cudaSuccess) return fail(ctx, SMPLGPU_ERR_CUDA, "bank run: %s", cudaGetErrorString(e));
+    return 1;
+}
+
+int smplgpu_bfs_bank_run_wait(smplgpu_ctx* ctx)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    return finish_bank_run(ctx);
 }
 
 int smplgpu_bfs_bank_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz)

@@ -761,70 +761,104 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         return true;
     };
 
+    // Admission in two steps: (1) setGoal -- a free slot gets the query's goal and its BFS is queued on the device
+    // WITHOUT waiting (the reference's BFS_3D also searches in a background thread, bfs3d.cpp:156-201), the running
+    // searches keep expanding; (2) when that BFS is done, setStart (limits, validity, heuristic of the start state)
+    // and the queries join the rounds.  One group of pending slots at a time.
+    std::vector<int32_t> pending;           // slots whose BFS is in flight
+    std::vector<int32_t> seeds;
+    bool first_fill = true;
+
+    auto activate = [&]() -> bool {
+        // setStart uses the synchronous entry points: nothing of ours may be in flight
+        for (int gi = 0; gi < 2; ++gi) {
+            if (!absorb(gi)) return false;
+        }
+        m_stats.host_seconds += t.lap();
+        if (smplgpu_bfs_bank_run_wait(m_ctx) < 0) return false;
+        const int nn = (int)pending.size();
+        sq.resize((size_t)nn * dof);
+        for (int k = 0; k < nn; ++k) {
+            const int qi = S[pending[k]].index;
+            std::copy(starts + (size_t)qi * dof, starts + (size_t)(qi + 1) * dof, sq.begin() + (size_t)k * dof);
+        }
+        sv.resize(nn);
+        sh.resize(nn);
+        sgd.resize(nn);
+        soff.resize((size_t)nn * 3);
+        std::vector<uint8_t> dummy(nn);
+        if (smplgpu_is_states_valid(m_ctx, sq.data(), nn, sv.data()) < 0) return false;
+        if (smplgpu_expand_batch(m_ctx, sq.data(), sq.data(), pending.data(), nn, m_cfg.cost_per_cell,
+                                 dummy.data(), sh.data(), sgd.data(), soff.data()) < 0) return false;
+        m_stats.device_calls += 2;
+        {
+            const double dt = t.lap();
+            m_stats.device_seconds += dt;
+            m_stats.setup_seconds += dt;
+        }
+        std::vector<int> coord;
+        for (int k = 0; k < nn; ++k) {
+            Query& Q = S[pending[k]];
+            const double* qs = &sq[(size_t)k * dof];
+            G[pending[k] & 1].active.push_back(pending[k]);
+            if (!checkJointLimits(qs) || !sv[k]) {
+                finish(Q, false);   // retired by the group's next absorb
+                continue;
+            }
+            stateToCoord(qs, coord);
+            Q.lat.add(coord.data(), qs, sh[k], sgd[k], true, Lattice::hash(coord.data(), dof));
+            sstate(Q, 1);
+            touch(Q, 1);
+            touch(Q, 0);
+            Q.search[1].g = 0;
+            Q.search[1].f = computeKey(Q.search[1]);
+            heapPush(Q, 1);
+        }
+        pending.clear();
+        return true;
+    };
+
     while (finished < nq) {
-        // ---- hand free slots to waiting queries: setGoal (one BFS per query) + setStart ----
+        const bool idle = G[0].active.empty() && G[1].active.empty();
+        // ---- (2) the pending queries' BFS is done (or there is nothing else to do): setStart, join the rounds ----
+        if (!pending.empty() && (idle || smplgpu_bfs_bank_run_done(m_ctx) != 0)) {
+            if (!activate()) return fail_dev();
+            continue;
+        }
+        // ---- (1) hand free slots to waiting queries: setGoal (one BFS per query, queued) ----
         int n_free = 0;
         for (int s = 0; s < n_slots; ++s) n_free += occupied[s] ? 0 : 1;
-        const bool idle = G[0].active.empty() && G[1].active.empty();
-        if (next_query < nq && (n_free >= refill_min || idle)) {
-            // the refill uses the synchronous entry points: nothing may be in flight
-            for (int gi = 0; gi < 2; ++gi) {
-                if (!absorb(gi)) return fail_dev();
-            }
-            std::vector<int32_t> new_slots, seeds;
-            for (int s = 0; s < n_slots && next_query < nq; ++s) {
+        if (pending.empty() && next_query < nq && (n_free >= refill_min || idle)) {
+            // the first group is kept small so that the searches start while the other slots' BFS still runs
+            // (measured on one B200, 12 contexts x 171 slots: first group = 1/2 of the slots 1729 queries/s, 1/4 1655,
+            // 1/8 at every admission 1425 -- every bank run pays whole-bank passes; SMPLHOST_ADMIT_CHUNKS overrides)
+            static const int chunks = getenv("SMPLHOST_ADMIT_CHUNKS") ? std::max(1, atoi(getenv("SMPLHOST_ADMIT_CHUNKS"))) : 2;
+            const int take = (first_fill || chunks > 4) ? std::max(1, n_slots / chunks) : n_slots;
+            first_fill = false;
+            seeds.clear();
+            for (int s = 0; s < n_slots && next_query < nq && (int)pending.size() < take; ++s) {
                 if (occupied[s]) {
                     continue;
                 }
                 initQuery(S[s], next_query, s, goals + (size_t)next_query * 3);
                 ++next_query;
                 occupied[s] = 1;
-                new_slots.push_back(s);
+                pending.push_back(s);
                 int cell[3];
                 worldToGrid(S[s].goal, cell);
                 seeds.insert(seeds.end(), cell, cell + 3);
             }
-            const int nn = (int)new_slots.size();
             m_stats.host_seconds += t.lap();
-            if (smplgpu_bfs_bank_run_slots(m_ctx, new_slots.data(), seeds.data(), nn) < 0) return fail_dev();
+            if (smplgpu_bfs_bank_run_slots_async(m_ctx, pending.data(), seeds.data(), (int)pending.size()) < 0) return fail_dev();
             ++m_stats.bfs_runs;
-            // setStart: limits + validity, then heuristic / metric distance of the start state
-            sq.resize((size_t)nn * dof);
-            for (int k = 0; k < nn; ++k) {
-                const int qi = S[new_slots[k]].index;
-                std::copy(starts + (size_t)qi * dof, starts + (size_t)(qi + 1) * dof, sq.begin() + (size_t)k * dof);
-            }
-            sv.resize(nn);
-            sh.resize(nn);
-            sgd.resize(nn);
-            soff.resize((size_t)nn * 3);
-            std::vector<uint8_t> dummy(nn);
-            if (smplgpu_is_states_valid(m_ctx, sq.data(), nn, sv.data()) < 0) return fail_dev();
-            if (smplgpu_expand_batch(m_ctx, sq.data(), sq.data(), new_slots.data(), nn, m_cfg.cost_per_cell,
-                                     dummy.data(), sh.data(), sgd.data(), soff.data()) < 0) return fail_dev();
-            m_stats.device_calls += 3;
+            ++m_stats.device_calls;
             {
                 const double dt = t.lap();
                 m_stats.device_seconds += dt;
                 m_stats.setup_seconds += dt;
             }
-            std::vector<int> coord;
-            for (int k = 0; k < nn; ++k) {
-                Query& Q = S[new_slots[k]];
-                const double* qs = &sq[(size_t)k * dof];
-                G[new_slots[k] & 1].active.push_back(new_slots[k]);
-                if (!checkJointLimits(qs) || !sv[k]) {
-                    finish(Q, false);   // retired by the group's next absorb
-                    continue;
-                }
-                stateToCoord(qs, coord);
-                Q.lat.add(coord.data(), qs, sh[k], sgd[k], true, Lattice::hash(coord.data(), dof));
-                sstate(Q, 1);
-                touch(Q, 1);
-                touch(Q, 0);
-                Q.search[1].g = 0;
-                Q.search[1].f = computeKey(Q.search[1]);
-                heapPush(Q, 1);
+            if (G[0].active.empty() && G[1].active.empty()) {
+                continue;   // nothing to expand meanwhile: go and wait for it
             }
         }
 
