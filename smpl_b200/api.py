@@ -101,6 +101,9 @@ def gpu_lib():
         L.smplgpu_build_distance_field_from_meshes.argtypes = [vp, dp, i, ip, i, ip, i, i, i, i, dp, d, d, d]
         L.smplgpu_bfs_bank_run.argtypes = [vp, ip]
         L.smplgpu_bfs_bank_run_slots.argtypes = [vp, ip, ip, i]
+        L.smplgpu_bfs_bank_run_slots_async.argtypes = [vp, ip, ip, i]
+        L.smplgpu_bfs_bank_run_done.argtypes = [vp]
+        L.smplgpu_bfs_bank_run_wait.argtypes = [vp]
         L.smplgpu_bfs_bank_distances.argtypes = [vp, ip, ip, i, ip]
         L.smplgpu_expand_batch.argtypes = [vp, dp, dp, ip, i, i, bp, ip, ip, dp]
         _gpu = L
@@ -517,6 +520,18 @@ class GpuContext:
 
     def bfs_bank_max_slots(self):
         return self._ck(self.L.smplgpu_bfs_bank_max_slots(self.h), "bfs_bank_max_slots")
+
+    def bfs_bank_run_slots_async(self, slots, seeds):
+        """Queues the BFS of the listed slots and returns; poll bfs_bank_run_done() or call bfs_bank_run_wait()."""
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        s = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 3)
+        return self._ck(self.L.smplgpu_bfs_bank_run_slots_async(self.h, _ip(sl), _ip(s), len(sl)), "bfs_bank_run_slots_async")
+
+    def bfs_bank_run_done(self):
+        return self._ck(self.L.smplgpu_bfs_bank_run_done(self.h), "bfs_bank_run_done") == 1
+
+    def bfs_bank_run_wait(self):
+        self._ck(self.L.smplgpu_bfs_bank_run_wait(self.h), "bfs_bank_run_wait")
 
     def bfs_bank_run(self, seeds):
         s = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 3)

@@ -45,6 +45,44 @@ def test_bfs_bank_equals_single_runs(tabletop):
     assert np.all((d == -1) | (d == 0x7FFFFFFF))
 
 
+def test_asynchronous_bank_runs_equal_synchronous_ones(tabletop):
+    """smplgpu_bfs_bank_run_slots_async: same distances as the blocking call, other slots untouched, one run in
+    flight per context, and two contexts on one GPU take turns."""
+    scene, o, ctx, tables = tabletop
+    ctx.bfs_bank_create(4, scene.inflation_radius)
+    _, goals = scenes.tabletop_queries(6, seed=41)
+    seeds = api.world_to_grid(goals, scene.origin, scene.res).astype(np.int32)
+    rng = np.random.default_rng(6)
+    cells = rng.integers(0, np.asarray(scene.dims), (3000, 3)).astype(np.int32)
+    ctx.bfs_bank_run(seeds[:4])
+    want = [ctx.bfs_bank_distances(np.full(len(cells), s, np.int32), cells) for s in range(4)]
+    # re-run slots 1 and 3 with other goals, asynchronously
+    ctx.bfs_bank_run_slots_async([1, 3], seeds[4:6])
+    with pytest.raises(api.SmplGpuError):
+        ctx.bfs_bank_run_slots_async([0], seeds[:1])
+    ctx.bfs_bank_run_wait()
+    assert ctx.bfs_bank_run_done()
+    got = [ctx.bfs_bank_distances(np.full(len(cells), s, np.int32), cells) for s in range(4)]
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2])
+    ctx.bfs_bank_run_slots([1, 3], seeds[4:6])
+    for s in (1, 3):
+        assert np.array_equal(got[s], ctx.bfs_bank_distances(np.full(len(cells), s, np.int32), cells))
+        assert not np.array_equal(got[s], want[s])
+    # a second context on the same GPU: its run waits for its turn, both finish
+    other = api.clone_context(ctx, scene, tables)
+    try:
+        other.bfs_bank_create(2, scene.inflation_radius)
+        ctx.bfs_bank_run_slots_async([0, 1, 2, 3], seeds[:4])
+        other.bfs_bank_run_slots_async([0, 1], seeds[:2])
+        while not (ctx.bfs_bank_run_done() and other.bfs_bank_run_done()):
+            pass
+        for s in range(2):
+            assert np.array_equal(other.bfs_bank_distances(np.full(len(cells), s, np.int32), cells), want[s])
+        assert np.array_equal(ctx.bfs_bank_distances(np.full(len(cells), 3, np.int32), cells), want[3])
+    finally:
+        other.close()
+
+
 def test_bank_max_slots_bounds_the_stacked_grid(tabletop):
     """The stacked bank keeps BFS_3D's int node indices (bfs3d.h:213-220): the slot limit the planner clamps to."""
     scene, o, ctx, tables = tabletop
