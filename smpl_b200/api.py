@@ -521,6 +521,11 @@ class GpuContext:
     def bfs_bank_max_slots(self):
         return self._ck(self.L.smplgpu_bfs_bank_max_slots(self.h), "bfs_bank_max_slots")
 
+    def bfs_bank_run_slots(self, slots, seeds):
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        s = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 3)
+        return self._ck(self.L.smplgpu_bfs_bank_run_slots(self.h, _ip(sl), _ip(s), len(sl)), "bfs_bank_run_slots")
+
     def bfs_bank_run_slots_async(self, slots, seeds):
         """Queues the BFS of the listed slots and returns; poll bfs_bank_run_done() or call bfs_bank_run_wait()."""
         sl = np.ascontiguousarray(slots, dtype=np.int32)
