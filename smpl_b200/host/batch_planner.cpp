@@ -596,6 +596,13 @@ void BatchPlanner::absorbOne(Query& Q, const uint8_t* verdict, const int32_t* h,
             }
         }
     }
+    // the state this query expands next round (unless a better one arrives): start loading what expandOne reads
+    if (Q.open.size() > 1) {
+        const int next_id = Q.open[1].id;
+        __builtin_prefetch(&Q.search[next_id]);
+        __builtin_prefetch(Q.lat.q(next_id));
+        __builtin_prefetch(&Q.lat.gdist[next_id]);
+    }
     if (profile) g_abs_prof[3] += pt.lap();
 }
 
