@@ -108,7 +108,10 @@ __global__ void bfs_tiles_reset_kernel(BfsGrid g, BfsTiles t, const uint8_t* __r
     }
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 1)
+#ifndef TILE_BLOCKS_PER_SM
+#define TILE_BLOCKS_PER_SM 1
+#endif
+__global__ void __launch_bounds__(TILE_THREADS, TILE_BLOCKS_PER_SM)
 bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsTiles t, int max_supersteps)
 {
     __shared__ uint32_t sF[2][TILE_THREADS * 3];
