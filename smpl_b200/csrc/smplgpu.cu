@@ -49,6 +49,7 @@ struct smplgpu_ctx
     float* d_blob = nullptr; size_t blob_cap = 0;   // bytes
     int blob_words = 0;
     int v32_threads = V32_THREADS;
+    int v32_blocks_per_sm = 1;            // resident blocks of states_valid32_kernel per SM (persistent launch)
     int v32_slots = 0, v32_ptrees = 0;
     double e_pos = 0.0, eps_cells = 0.0;
     Grid32 grid32{};
@@ -223,7 +224,7 @@ smplgpu_ctx* smplgpu_create(int device)
     if ((e = cudaMalloc(&ctx->d_model, sizeof(DevModel))) != cudaSuccess) return bail("cudaMalloc(model)", e);
     if ((e = cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(stats)", e);
     if ((e = cudaMalloc(&ctx->d_seed_count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc(seed)", e);
-    if ((e = cudaMalloc(&ctx->d_unc_count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc(unc)", e);
+    if ((e = cudaMalloc(&ctx->d_unc_count, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc(unc)", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->bfs_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_bfs, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -627,6 +628,11 @@ static int build_model32(smplgpu_ctx* ctx)
     CU(cudaFuncSetAttribute(states_valid32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(edges_valid32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(fk_centers32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    {
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, states_valid32_kernel, threads, (size_t)smem));
+        ctx->v32_blocks_per_sm = std::max(1, per_sm);
+    }
     int r = grow(ctx, (void**)&ctx->d_blob, &ctx->blob_cap, (size_t)w * 4);
     if (r) return r;
     CU(cudaMemcpyAsync(ctx->d_blob, B.data(), (size_t)w * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1126,9 +1132,11 @@ static int launch_states(smplgpu_ctx* ctx, const double* dq, int n, uint8_t* dv)
     }
     int r = ensure_unc(ctx, (size_t)n);
     if (r) return r;
-    CU(cudaMemsetAsync(ctx->d_unc_count, 0, sizeof(int), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_unc_count, 0, 2 * sizeof(int), ctx->stream));   // [0] undecided items, [1] the work cursor
     const int t32 = ctx->v32_threads;
-    states_valid32_kernel<<<(n + t32 - 1) / t32, t32, v32_smem(ctx), ctx->stream>>>(
+    // one wave of resident blocks; their warps pull the states from the cursor
+    const int wave = std::max(1, ctx->v32_blocks_per_sm) * ctx->sm_count;
+    states_valid32_kernel<<<std::min((n + t32 - 1) / t32, wave), t32, v32_smem(ctx), ctx->stream>>>(
         ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq, n, dv, ctx->d_unc_list,
         ctx->d_unc_count, ctx->d_stats);
     const int blocks = std::max(1, std::min((n + vt - 1) / vt, 2 * ctx->sm_count));

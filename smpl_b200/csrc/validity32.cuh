@@ -460,15 +460,30 @@ states_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const De
     __syncthreads();
     const S32 S = view32(blob);
     float* slots = blob + blob_words;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     Counters cnt = { 0u, 0u, 0u };
-    int r = 0;
-    if (i < n) {
-        cnt.waypoints = 1;
-        r = check_state32(S, M->var_type, df, G, q + (size_t)i * S.h->dof, nullptr, 0.0, slots, cnt);
-        verdict[i] = r == 1 ? 1 : 0;
+    // Persistent warps: the grid is one wave of resident blocks and every warp pulls 32 consecutive states at a time
+    // from a global cursor (unc_count[1], zeroed with the count by the host).  A state check costs anything from one
+    // sphere test to the whole chain; with one state per thread a block keeps its registers and shared memory until
+    // its slowest warp is done, here a warp that finishes early simply takes the next 32 states.
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) {
+            base = atomicAdd(unc_count + 1, 32);
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) {
+            break;
+        }
+        const int i = base + lane;
+        int r = 0;
+        if (i < n) {
+            ++cnt.waypoints;
+            r = check_state32(S, M->var_type, df, G, q + (size_t)i * S.h->dof, nullptr, 0.0, slots, cnt);
+            verdict[i] = r == 1 ? 1 : 0;
+        }
+        append_uncertain(i < n && r == 2, i, unc_list, unc_count, stats);
     }
-    append_uncertain(i < n && r == 2, i, unc_list, unc_count, stats);
     flush_counters(cnt, stats);
 }
 
@@ -479,6 +494,7 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
                      int* __restrict__ unc_list, int* __restrict__ unc_count, unsigned long long* stats)
 {
     extern __shared__ float4 smem4[];
+    __shared__ int s_cursor;   // next unclaimed (edge, waypoint) item of round B
     float* blob = reinterpret_cast<float*>(smem4);
     copy_blob(blob, blob_g, blob_words);
     const int tid = threadIdx.x;
@@ -537,6 +553,7 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
     s_unc[tid] = unc;
     if (tid == 0) {
         s_off[0] = 0;
+        s_cursor = 0;
     }
     __syncthreads();
     for (int d = 1; d < (int)blockDim.x; d <<= 1) {
@@ -553,30 +570,43 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
     s_cnt[tid] = count;
     __syncthreads();
 
-    for (int item = tid; item < total; item += blockDim.x) {
-        int lo = 0, hi = blockDim.x;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_off[mid] <= item) {
-                lo = mid;
-            } else {
-                hi = mid;
+    // warps pull 32 consecutive items at a time from a block-wide cursor: a state check costs anything from one
+    // sphere test to the whole chain, so a fixed stride leaves warps waiting at the final barrier
+    const int lane = tid & 31;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) {
+            base = atomicAdd(&s_cursor, 32);
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) {
+            break;
+        }
+        const int item = base + lane;
+        if (item < total) {
+            int lo = 0, hi = blockDim.x;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= item) {
+                    lo = mid;
+                } else {
+                    hi = mid;
+                }
             }
-        }
-        const int e = lo;
-        if (s_ok[e] == 0) {
-            continue;
-        }
-        const int w = item - s_off[e] + 1;               // waypoint 0 was round A
-        const double inv = 1.0 / (double)(s_cnt[e] - 1); // m_waypoint_count_inv
-        const double alpha = (double)w * inv;
-        ++cnt.waypoints;
-        const int r = check_state32(S, M->var_type, df, G, q0 + (size_t)(first + e) * dof, q1 + (size_t)(first + e) * dof,
-                                    alpha, slots, cnt);
-        if (r == 0) {
-            s_ok[e] = 0;
-        } else if (r == 2) {
-            s_unc[e] = 1;
+            const int e = lo;
+            if (s_ok[e] != 0) {
+                const int w = item - s_off[e] + 1;               // waypoint 0 was round A
+                const double inv = 1.0 / (double)(s_cnt[e] - 1); // m_waypoint_count_inv
+                const double alpha = (double)w * inv;
+                ++cnt.waypoints;
+                const int r = check_state32(S, M->var_type, df, G, q0 + (size_t)(first + e) * dof, q1 + (size_t)(first + e) * dof,
+                                            alpha, slots, cnt);
+                if (r == 0) {
+                    s_ok[e] = 0;
+                } else if (r == 2) {
+                    s_unc[e] = 1;
+                }
+            }
         }
     }
     __syncthreads();
