@@ -325,7 +325,13 @@ states_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__
     extern __shared__ double smem[];
     const int total = list != nullptr ? min(*list_n, n) : n;
     Counters cnt = { 0u, 0u, 0u };
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+    // With a list (the few states the single-precision pass could not decide) the items are dealt one per WARP
+    // first: these states take different branches all along the chain and the descent, so 32 of them in one warp
+    // would run one after the other; spread out, a warp holds two or three.
+    const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
+    const int k0 = list != nullptr ? (int)(threadIdx.x & 31) * n_warps + (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5))
+                                   : (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    for (int k = k0; k < total; k += gridDim.x * blockDim.x) {
         const int i = list != nullptr ? list[k] : k;
         ++cnt.waypoints;
         const bool ok = check_state(M, df, G, q + (size_t)i * M->dof, nullptr, 0.0, smem, cnt);
