@@ -1,0 +1,4 @@
+// ORACLE (test infrastructure only).  Stand-in for an absent third-party header: just enough surface for the
+// reference's sbpl_collision_checking sources to compile where they lie (see oracle/Makefile, target ref).
+#pragma once
+#include <moveit_msgs/CollisionObject.h>

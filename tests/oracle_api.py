@@ -546,6 +546,138 @@ class OracleScene:
                     path_ids=path[:min(n, max_path)].copy(), num_states=int(summary[4]), seconds=float(secs))
 
 
+_REF_CC = None
+
+
+def ref_collision_lib():
+    """The reference's own collision checker (oracle/_ref/libref_collision.so, see oracle/ref_collision_shim.cpp), or None."""
+    global _REF_CC
+    if _REF_CC is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_collision.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.refcc_last_error.restype = C.c_char_p
+        R.refcc_create.restype = C.c_void_p
+        R.refcc_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, c_double_p, c_double_p, C.c_double, C.c_double]
+        _REF_CC = R
+    return _REF_CC
+
+
+class RefCollisionScene:
+    """Same driving surface as OracleScene, served by the reference's CollisionSpace."""
+
+    def __init__(self, robot_path, group, planning_joints, origin, size, res, max_dist):
+        R = ref_collision_lib()
+        self.R = R
+        o = np.asarray(origin, dtype=np.float64)
+        s = np.asarray(size, dtype=np.float64)
+        self.h = R.refcc_create(robot_path.encode(), group.encode(), ",".join(planning_joints).encode(),
+                                _dp(o), _dp(s), float(res), float(max_dist))
+        if not self.h:
+            raise RuntimeError("refcc_create: " + R.refcc_last_error().decode())
+        self.h = C.c_void_p(self.h)
+        self.dof = len(planning_joints)
+
+    def close(self):
+        if self.h:
+            self.R.refcc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_joint(self, name, value):
+        return self.R.refcc_set_joint(self.h, name.encode(), C.c_double(value))
+
+    def use_desc_acm(self):
+        self.R.refcc_use_desc_acm(self.h)
+
+    def acm_set(self, a, b, allowed):
+        self.R.refcc_acm_set(self.h, a.encode(), b.encode(), int(allowed))
+
+    def set_padding(self, p):
+        self.R.refcc_set_padding(self.h, C.c_double(p))
+
+    def add_cells(self, cells):
+        cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 3)
+        self.R.refcc_add_cells(self.h, _ip(cells), len(cells))
+
+    def add_points(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        self.R.refcc_add_points(self.h, _dp(pts), len(pts))
+
+    def insert_boxes(self, boxes):
+        b = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 15)
+        if self.R.refcc_insert_boxes(self.h, _dp(b), len(b)) != 0:
+            raise RuntimeError("insertObject failed")
+
+    def attach_box(self, body_id, link, size, pose3x4):
+        sz = np.ascontiguousarray(size, dtype=np.float64)
+        p = np.ascontiguousarray(pose3x4, dtype=np.float64).reshape(3, 4)
+        n = self.R.refcc_attach_box(self.h, body_id.encode(), link.encode(), _dp(sz), _dp(p))
+        if n < 0:
+            raise RuntimeError("attachObject failed")
+        return n
+
+    def detach(self, body_id):
+        return self.R.refcc_detach(self.h, body_id.encode())
+
+    def prime(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        self.R.refcc_prime(self.h, _dp(q))
+
+    def df_d2(self):
+        dims = np.zeros(3, np.int32)
+        self.R.refcc_grid_dims(self.h, _ip(dims))
+        out = np.zeros(int(dims[0]) * int(dims[1]) * int(dims[2]), np.int32)
+        self.R.refcc_df_d2(self.h, _ip(out))
+        return out.reshape(tuple(int(d) for d in dims))
+
+    def _q(self, q):
+        return np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.dof)
+
+    def is_states_valid(self, q):
+        q = self._q(q)
+        v = np.zeros(len(q), np.uint8)
+        self.R.refcc_is_states_valid(self.h, _dp(q), len(q), _bp(v))
+        return v
+
+    def is_edges_valid(self, q0, q1):
+        q0 = self._q(q0)
+        q1 = self._q(q1)
+        v = np.zeros(len(q0), np.uint8)
+        c = np.zeros(len(q0), np.int32)
+        self.R.refcc_is_edges_valid(self.h, _dp(q0), _dp(q1), len(q0), _bp(v), _ip(c))
+        return v, c
+
+    def edge_waypoints(self, q0, q1, max_wp=256):
+        q0 = np.ascontiguousarray(q0, dtype=np.float64)
+        q1 = np.ascontiguousarray(q1, dtype=np.float64)
+        out = np.zeros((max_wp, self.dof), np.float64)
+        n = self.R.refcc_edge_waypoints(self.h, _dp(q0), _dp(q1), _dp(out), max_wp)
+        return out[:n].copy()
+
+    def node_table(self, max_nodes=4096):
+        out = np.zeros((max_nodes, 8), np.float64)
+        n = self.R.refcc_node_table(self.h, _dp(out))
+        return out[:n].copy()
+
+    def sphere_centers(self, q, n_nodes):
+        q = self._q(q)
+        out = np.zeros((len(q), n_nodes, 3), np.float64)
+        self.R.refcc_sphere_centers(self.h, _dp(q), len(q), _dp(out))
+        return out
+
+    def motion_weights(self):
+        w = np.zeros(self.dof, np.float64)
+        self.R.refcc_motion_weights(self.h, _dp(w))
+        return w
+
+
 class _BfsBase:
     prefix = None
 
