@@ -111,11 +111,43 @@ def make_oracle(scene, prime_q):
     return o
 
 
-def cpu_validity_rate(scene, q, q0, q1, threads):
-    """Oracle (CPU port of the reference algorithm) on `threads` host threads; returns (units/s, units, seconds)."""
+def make_reference_checker(scene, prime_q):
+    """The reference's OWN collision checker (sbpl_collision_checking compiled from its sources into
+    oracle/_ref/libref_collision.so, see oracle/ref_collision_shim.cpp) set up for `scene`, or None when that library
+    was not built (then the CPU legs time the oracle port)."""
+    from oracle_api import RefCollisionScene, ref_collision_lib
+    if ref_collision_lib() is None or os.environ.get("SMPL_BENCH_CPU_PORT"):
+        return None
+    r = RefCollisionScene(scene.robot_path, scene.group, scene.planning_joints, scene.origin, scene.size, scene.res,
+                          scene.max_dist)
+    for k, v in scene.fixed_joints.items():
+        r.set_joint(k, v)
+    if scene.use_desc_acm:
+        r.use_desc_acm()
+    for a, b, allowed in scene.acm_extra:
+        r.acm_set(a, b, allowed)
+    if len(scene.cells):
+        r.add_cells(scene.cells)
+    if len(getattr(scene, "boxes", [])):
+        r.insert_boxes(scene.boxes)
+    r.prime(prime_q)
+    return r
+
+
+def make_cpu_checker(scene, prime_q):
+    """-> (checker, kind, description): the compiled reference when available ("reference"), else the port."""
+    r = make_reference_checker(scene, prime_q)
+    if r is not None:
+        return r, "reference", "the reference's own sbpl_collision_checking CollisionSpace (oracle/_ref/libref_collision.so)"
+    return make_oracle(scene, prime_q), "port", "oracle (CPU port of sbpl_collision_checking)"
+
+
+def cpu_validity_rate(scene, q, q0, q1, threads, checkers=None):
+    """The CPU checker (one instance per thread: CollisionSpace is not reentrant) on `threads` host threads;
+    returns (units/s, units, seconds)."""
     n = len(q)
     parts = np.array_split(np.arange(n), threads)
-    oracles = [make_oracle(scene, q[0]) for _ in range(threads)]
+    oracles = checkers if checkers is not None else [make_cpu_checker(scene, q[0])[0] for _ in range(threads)]
     units = [0] * threads
 
     def work(i):
@@ -192,7 +224,8 @@ def setup_shared_scene(scene, local_rank, rank, world, dev):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port) on all host threads."""
+    """--impl reference: the reference's own CPU collision checker (oracle/_ref/libref_collision.so; the oracle port
+    when that was not built) on all host threads, one CollisionSpace per thread."""
     if rank != 0:
         return
     from smpl_b200 import scenes
@@ -204,11 +237,13 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     q = scenes.random_states(n, lo, hi, cont, seed=20260101)
     q0, q1 = scenes.mprim_edges(q)
+    made = [make_cpu_checker(scene, q[0]) for _ in range(threads)]
+    checkers, kind, what = [m[0] for m in made], made[0][1], made[0][2]
     for _ in range(args.warmup):
-        cpu_validity_rate(scene, q[: n // 8], q0[: n // 8], q1[: n // 8], threads)
+        cpu_validity_rate(scene, q[: n // 8], q0[: n // 8], q1[: n // 8], threads, checkers)
     total_units, total_t = 0, 0.0
     for _ in range(args.steps):
-        _, u, dt = cpu_validity_rate(scene, q, q0, q1, threads)
+        _, u, dt = cpu_validity_rate(scene, q, q0, q1, threads, checkers)
         total_units += u
         total_t += dt
     value = total_units / total_t
@@ -218,8 +253,8 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "config[1] validity sweep: PR2 right arm states + mprim edges vs 2 m^3 clutter scene @ 2 cm",
                    "states_per_step": n, "edges_per_step": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d states + %d edges per step, oracle (CPU port of sbpl_collision_checking) on %d threads" % (n, n, threads)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": "%d states + %d edges per step, %s on %d threads" % (n, n, what, threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -382,6 +417,7 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * units_per_step * e2e_steps / (float(e2e_ms.item()) * 1e-3)
     assert torch.equal(hv.to(dev), d_v) and torch.equal(hev.to(dev), d_ev), "host-buffer path disagrees with resident path"
+    verdict_s, verdict_e, counts_e = hv.numpy().copy(), hev.numpy().copy(), d_cnt.cpu().numpy()
 
     # ---- BFS (config[2]): 400^3 cluttered occupancy, rank 0 only for the side metric ----
     bfs = None
@@ -508,18 +544,24 @@ def main():
     if not args.no_cpu:
         m = min(args.cpu_sample, n)
         o = make_oracle(scene, q[0])
-        t_s, _ = o.time_states_valid(q[:m])
-        t_e, _, c = o.time_edges_valid(q0[:m], q1[:m])
+        checker, cpu_kind, cpu_what = make_cpu_checker(scene, q[0])
+        t_s, v_s = checker.time_states_valid(q[:m])
+        t_e, v_e, c = checker.time_edges_valid(q0[:m], q1[:m])
         cpu_units = m + int(c.sum())
         cpu_rate = cpu_units / (t_s + t_e)
+        cpu_agree = None
+        if verdict_s is not None:      # the timed CPU run doubles as a parity check of the device verdicts
+            cpu_agree = {"states_differing": int((v_s != verdict_s[:m]).sum()), "edges_differing": int((v_e != verdict_e[:m]).sum()),
+                         "waypoint_counts_differing": int((c != counts_e[:m]).sum()), "of": m}
         # L-bar: DF lookups the reference semantics requires (no early-out), from the oracle on a sub-sample
         ms = min(m, 1 << 15)
         _, Ls, _, _ = o.report_states(q[:ms])
         _, _, Le = o.report_edges(q0[:ms], q1[:ms])
         Lbar_state, Lbar_edge = float(Ls.mean()), float(Le.mean())
-        cpu = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "%d states + %d edges of the same workload, oracle (CPU port of sbpl_collision_checking), 1 thread; "
-                         "states %.0f/s, edge waypoints %.0f/s" % (m, m, m / t_s, int(c.sum()) / t_e)}
+        cpu = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": cpu_kind,
+               "sample": "%d states + %d edges of the same workload, %s, 1 thread; "
+                         "states %.0f/s, edge waypoints %.0f/s" % (m, m, cpu_what, m / t_s, int(c.sum()) / t_e),
+               "device_verdicts_vs_this_run": cpu_agree}
         if plan is not None and args.plan_cpu_queries > 0:
             po = make_oracle(pscene, np.zeros(pscene.dof))
             po.init_kdl(pscene.chain_root, pscene.chain_tip, pscene.planning_link, pscene.T_kin_to_planning, pscene.xyz_offset)

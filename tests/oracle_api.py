@@ -501,6 +501,9 @@ class OracleScene:
         p = np.ascontiguousarray(pose3x4, dtype=np.float64).reshape(3, 4)
         return self.L.oracle_scene_attach_box(self.h, body_id.encode(), link.encode(), _dp(sz), _dp(p))
 
+    def detach(self, body_id):
+        return self.L.oracle_scene_detach(self.h, body_id.encode())
+
     def insert_boxes(self, boxes):
         """WorldCollisionModel::insertObject for box primitives: boxes[n][15] = size(3), pose 3x4 row-major."""
         b = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 15)
@@ -560,6 +563,8 @@ def ref_collision_lib():
         R.refcc_last_error.restype = C.c_char_p
         R.refcc_create.restype = C.c_void_p
         R.refcc_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, c_double_p, c_double_p, C.c_double, C.c_double]
+        R.refcc_time_states_valid.restype = C.c_double
+        R.refcc_time_edges_valid.restype = C.c_double
         _REF_CC = R
     return _REF_CC
 
@@ -654,6 +659,20 @@ class RefCollisionScene:
         self.R.refcc_is_edges_valid(self.h, _dp(q0), _dp(q1), len(q0), _bp(v), _ip(c))
         return v, c
 
+    def time_states_valid(self, q):
+        q = self._q(q)
+        v = np.zeros(len(q), np.uint8)
+        t = self.R.refcc_time_states_valid(self.h, _dp(q), len(q), _bp(v))
+        return t, v
+
+    def time_edges_valid(self, q0, q1):
+        q0 = self._q(q0)
+        q1 = self._q(q1)
+        v = np.zeros(len(q0), np.uint8)
+        c = np.zeros(len(q0), np.int32)
+        t = self.R.refcc_time_edges_valid(self.h, _dp(q0), _dp(q1), len(q0), _bp(v), _ip(c))
+        return t, v, c
+
     def edge_waypoints(self, q0, q1, max_wp=256):
         q0 = np.ascontiguousarray(q0, dtype=np.float64)
         q1 = np.ascontiguousarray(q1, dtype=np.float64)
@@ -676,6 +695,13 @@ class RefCollisionScene:
         w = np.zeros(self.dof, np.float64)
         self.R.refcc_motion_weights(self.h, _dp(w))
         return w
+
+    def limits(self):
+        lo = np.zeros(self.dof)
+        hi = np.zeros(self.dof)
+        c = np.zeros(self.dof, np.uint8)
+        self.R.refcc_limits(self.h, _dp(lo), _dp(hi), _bp(c))
+        return lo, hi, c
 
 
 class _BfsBase:
