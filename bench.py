@@ -568,10 +568,13 @@ def main():
             k = min(args.plan_cpu_queries, len(starts_all))
             secs, cexp = 0.0, 0
             same = 0
+            # the reference's own ManipLattice + BfsHeuristic + ARAStar + CollisionSpace (oracle/ref_planner_shim.cpp)
+            # when its build is there, else the oracle's restatement
+            pref = make_reference_checker(pscene, np.zeros(pscene.dof))
             for qi, (s_, g_) in enumerate(zip(starts_all[:k], goals_all[:k])):
                 po.heur_init(pscene.inflation_radius, pscene.cost_per_cell)
                 t0 = time.perf_counter()
-                pr = po.plan(s_, g_, pparams)
+                pr = pref.plan(pscene, s_, g_, pparams) if pref is not None else po.plan(s_, g_, pparams)
                 secs += time.perf_counter() - t0      # includes the per-query BFS, as the GPU figure does
                 cexp += pr["expansions"]
                 if world == 1 or qi % world == 0:     # rank 0 planned queries 0, world, 2 world, ...
@@ -584,7 +587,10 @@ def main():
             plan["parity_identical"] = same
             plan["cpu_queries_per_s"] = k / secs
             plan["cpu_expansions_per_s"] = cexp / secs
-            plan["cpu_sample"] = "first %d queries, oracle ManipLattice + ARA*, 1 thread" % k
+            plan["cpu_kind"] = "reference" if pref is not None else "port"
+            plan["cpu_sample"] = "first %d queries, %s, 1 thread" % (
+                k, "the reference's own ManipLattice + BfsHeuristic + ARAStar + CollisionSpace (oracle/_ref/libref_collision.so; "
+                   "RobotModel and action-space plug-ins from the oracle)" if pref is not None else "oracle ManipLattice + ARA*")
         if post is not None:
             k = min(args.post_cpu_paths, len(post_paths))
             t0 = time.perf_counter()

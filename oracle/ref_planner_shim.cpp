@@ -1,0 +1,255 @@
+// ORACLE (test infrastructure only -- never linked into the product path).
+//
+// One planning query through the REFERENCE's own planning stack, part of oracle/_ref/libref_collision.so:
+//   ManipLattice + RobotPlanningSpace   smpl/src/graph/manip_lattice.cpp, robot_planning_space.cpp
+//   BfsHeuristic + BFS_3D               smpl/src/heuristic/bfs_heuristic.cpp, robot_heuristic.cpp, smpl/src/bfs3d.cpp
+//   ARAStar                             smpl/src/search/arastar.cpp
+//   CollisionSpace                      the collision checker of ref_collision_shim.cpp
+// all compiled where they lie (SBPL's base-class declarations: oracle/ref_stubs/sbpl).  It pins oracle/lattice.cpp
+// and the BfsHeuristic of oracle/kdl_model.cpp: same path (state ids), cost, expansion count, lattice size and
+// extracted joint path (tests/test_oracle_planner_reference.py, tests/golden/plans_reference.json).
+//
+// Two plug-ins of the reference are NOT its own code here, and say so:
+//  * the RobotModel.  The reference's KDLRobotModel needs orocos_kdl / kdl_parser / urdf (absent).  ShimRobotModel
+//    implements the reference's RobotModel + ForwardKinematicsInterface (+ an InverseKinematicsInterface that always
+//    fails: ManipLattice::init insists on one, manip_lattice.cpp:100-104) over oracle::KDLRobotModel (liboracle.so),
+//    the restatement of kdl_robot_model.cpp + KDL that the product's planning_fk kernels are tested against.
+//  * the ActionSpace.  This fork's ManipLatticeActionSpace reads a motion-primitive format its own files do not have
+//    and rotates joints 0/1 by joint 3 (SURVEY 8a defect 2); like oracle/lattice.cpp, ShimActionSpace follows the
+//    documented behaviour: every primitive is one waypoint parent + delta, weight 1, long primitives unless
+//    use_short_dist and BfsHeuristic::getMetricGoalDistance(planning link position) <= threshold
+//    (manip_lattice_action_space.cpp:376-449, 662-691), IK snap primitives off.
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <smpl/debug/visualize.h>
+#include <smpl/graph/manip_lattice.h>
+#include <smpl/heuristic/bfs_heuristic.h>
+#include <smpl/search/arastar.h>
+
+#include "kdl_model.h"
+#include "ref_collision_scene.h"
+
+using namespace sbpl;
+using namespace sbpl::motion;
+
+// smpl/src/debug/visualize.cpp (marker publishing) is not compiled: visualisation is off
+namespace sbpl {
+namespace visual {
+void visualize(Level, const Marker&) { }
+void visualize(Level, const std::vector<Marker>&) { }
+void visualize(Level, const visualization_msgs::Marker&) { }
+void visualize(Level, const visualization_msgs::MarkerArray&) { }
+void InitializeVizLocation(VizLocation* loc, const std::string&, Level level)
+{
+    loc->level = level;
+    loc->enabled = false;
+    loc->initialized = true;
+    loc->handle = nullptr;
+    loc->next = nullptr;
+}
+} // namespace visual
+} // namespace sbpl
+
+namespace {
+
+class ShimRobotModel :
+    public virtual RobotModel,
+    public ForwardKinematicsInterface,
+    public InverseKinematicsInterface
+{
+public:
+
+    oracle::KDLRobotModel kdl;
+
+    double minPosLimit(int jidx) const override { return kdl.min_limits[jidx]; }
+    double maxPosLimit(int jidx) const override { return kdl.max_limits[jidx]; }
+    bool hasPosLimit(int jidx) const override { return !kdl.continuous[jidx]; }   // kdl_robot_model.cpp:262-266
+    bool isContinuous(int jidx) const override { return kdl.continuous[jidx]; }
+    double velLimit(int) const override { return 0.0; }
+    double accLimit(int) const override { return 0.0; }
+    bool checkJointLimits(const RobotState& state, bool = false) override { return kdl.checkJointLimits(state); }
+
+    bool computeFK(const RobotState&, const std::string&, std::vector<double>&) override { return false; }
+    bool computePlanningLinkFK(const RobotState& state, std::vector<double>& pose) override
+    {
+        return kdl.computePlanningLinkFK(state, pose);
+    }
+
+    bool computeIK(const std::vector<double>&, const RobotState&, RobotState&, ik_option::IkOption) override { return false; }
+    bool computeIK(const std::vector<double>&, const RobotState&, std::vector<RobotState>&, ik_option::IkOption) override { return false; }
+
+    Extension* getExtension(size_t class_code) override
+    {
+        if (class_code == GetClassCode<RobotModel>()) return static_cast<RobotModel*>(this);
+        if (class_code == GetClassCode<ForwardKinematicsInterface>()) return static_cast<ForwardKinematicsInterface*>(this);
+        if (class_code == GetClassCode<InverseKinematicsInterface>()) return static_cast<InverseKinematicsInterface*>(this);
+        return nullptr;
+    }
+};
+
+class ShimActionSpace : public ActionSpace
+{
+public:
+
+    std::vector<std::vector<double>> deltas;   // file order, converse after each primitive (add_converse)
+    std::vector<bool> is_short;
+    bool use_short_dist = false;
+    double short_dist_thresh = 0.0;
+    ForwardKinematicsInterface* fk = nullptr;
+
+    bool apply(const RobotState& parent, std::vector<Action>& actions) override
+    {
+        ActionsWeight w;
+        return apply(parent, actions, w, -1);
+    }
+
+    bool apply(const RobotState& parent, std::vector<Action>& actions, ActionsWeight& weights, int) override
+    {
+        std::vector<double> pose;
+        if (!fk->computePlanningLinkFK(parent, pose)) {
+            return false;
+        }
+        // manip_lattice_action_space.cpp:385-396: distance of the planning link to the goal, from the first heuristic
+        double goal_dist = 0.0;
+        if (planningSpace()->numHeuristics() > 0) {
+            goal_dist = planningSpace()->heuristic(0)->getMetricGoalDistance(pose[0], pose[1], pose[2]);
+        }
+        const bool near_goal = goal_dist <= short_dist_thresh;
+        for (size_t p = 0; p < deltas.size(); ++p) {
+            const bool active = is_short[p] ? (use_short_dist && near_goal) : !(use_short_dist && near_goal);
+            if (!active) continue;
+            Action action(1, parent);
+            for (size_t j = 0; j < parent.size(); ++j) {
+                action[0][j] = deltas[p][j] + parent[j];
+            }
+            actions.push_back(std::move(action));
+            weights.push_back(1.0);
+        }
+        return true;
+    }
+
+    bool applyPredActions(const RobotState&, std::vector<Action>&, ActionsWeight&, int) override { return false; }
+    void setMotionPlanRequestType(int) override { }
+};
+
+} // namespace
+
+extern "C" {
+
+/// same arguments and summary as oracle_plan (oracle/oracle_capi.cpp): out_summary = success, expansions, cost,
+/// path length, lattice states created, extracted path length.  chain_* / T_kin_to_planning / xyz_offset as
+/// oracle_scene_init_kdl.  Returns 0, or a negative step number when the reference refuses a step.
+int refcc_plan(refcc_scene* s, const char* chain_root, const char* chain_tip, const char* planning_link,
+               const double* T_kin_to_planning /*3x4*/, const double* xyz_offset,
+               double inflation_radius, int cost_per_cell,
+               const double* start, const double* goal_xyz,
+               const double* resolutions, const double* mprims, const uint8_t* short_flags, int n_prims,
+               int use_short_dist, double short_dist_thresh, double epsilon, int max_expansions,
+               const double* xyz_tolerance, int32_t* out_summary, int32_t* path_ids, int max_path,
+               double* path_states /* nullable: [max_path][dof] */)
+{
+    std::memset(out_summary, 0, 6 * sizeof(int32_t));
+    const int dof = s->dof;
+
+    ShimRobotModel robot;
+    std::string err;
+    if (!robot.kdl.init(s->desc, s->planning_joints, chain_root, chain_tip, &err)) return -1;
+    oracle::KdlFrame f = oracle::KdlFrame::Identity();
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) f.M[3 * r + c] = T_kin_to_planning[4 * r + c];
+        f.p[r] = T_kin_to_planning[4 * r + 3];
+    }
+    robot.kdl.setKinematicsToPlanningTransform(f);
+    if (!robot.kdl.setPlanningLink(planning_link)) return -2;
+    robot.setPlanningJoints(s->planning_joints);
+
+    PlanningParams params;
+    params.cost_per_cell = cost_per_cell;
+    params.planning_link_sphere_radius = inflation_radius;
+
+    ShimActionSpace actions;
+    actions.fk = &robot;
+    actions.use_short_dist = use_short_dist != 0;
+    actions.short_dist_thresh = short_dist_thresh;
+    for (int p = 0; p < n_prims; ++p) {   // ManipLatticeActionSpace::addMotionPrim with add_converse (:201-228)
+        std::vector<double> d(mprims + (size_t)p * dof, mprims + (size_t)(p + 1) * dof);
+        actions.deltas.push_back(d);
+        actions.is_short.push_back(short_flags[p] != 0);
+        for (double& v : d) v = -v;
+        actions.deltas.push_back(d);
+        actions.is_short.push_back(short_flags[p] != 0);
+    }
+
+    ManipLattice space;
+    const std::vector<double> res(resolutions, resolutions + dof);
+    if (!space.init(&robot, s->cc.get(), &params, res, &actions)) return -3;
+    if (!actions.init(&space)) return -4;
+
+    BfsHeuristic heur;
+    heur.setCostPerCell(cost_per_cell);
+    heur.setInflationRadius(inflation_radius);
+    if (!heur.init(&space, s->grid.get())) return -5;
+    if (!space.insertHeuristic(&heur)) return -6;
+
+    GoalConstraint goal;
+    goal.type = GoalType::XYZ_GOAL;
+    goal.pose.assign(6, 0.0);
+    goal.tgt_off_pose.assign(6, 0.0);
+    for (int i = 0; i < 3; ++i) {
+        goal.pose[i] = goal_xyz[i];
+        goal.tgt_off_pose[i] = goal_xyz[i];
+        goal.xyz_offset[i] = xyz_offset[i];
+        goal.xyz_tolerance[i] = xyz_tolerance[i];
+        goal.rpy_tolerance[i] = 0.0;
+    }
+    if (!space.setGoal(goal)) return -7;
+
+    const RobotState st(start, start + dof);
+    if (!space.setStart(st)) {
+        out_summary[4] = (int)space.m_states.size();
+        return 0;   // start outside the limits or in collision: no plan (PlannerInterface gives up the same way)
+    }
+
+    ARAStar search(&space, &heur);
+    search.set_initialsolution_eps(epsilon);
+    if (search.set_start(space.getStartStateID()) == 0) return -8;
+    if (search.set_goal(space.getGoalStateID()) == 0) return -9;
+    ARAStar::TimeParameters tp;
+    tp.bounded = true;
+    tp.improve = false;
+    tp.type = ARAStar::TimeParameters::EXPANSIONS;
+    tp.max_expansions_init = max_expansions;
+    tp.max_expansions = max_expansions;
+    tp.max_allowed_time_init = sbpl::clock::duration::zero();
+    tp.max_allowed_time = sbpl::clock::duration::zero();
+    std::vector<int> solution;
+    int solcost = 0;
+    const int ret = search.replan(tp, &solution, &solcost);
+    out_summary[1] = search.get_n_expands();
+    out_summary[4] = (int)space.m_states.size();
+    if (!ret || solcost >= INFINITECOST) {
+        return 0;
+    }
+    out_summary[0] = 1;
+    out_summary[2] = solcost;
+    out_summary[3] = (int)solution.size();
+    for (int i = 0; i < (int)solution.size() && i < max_path; ++i) {
+        path_ids[i] = solution[i];
+    }
+    if (path_states) {
+        std::vector<RobotState> path;
+        if (space.extractPath(solution, path)) {
+            out_summary[5] = (int)path.size();
+            for (int i = 0; i < (int)path.size() && i < max_path; ++i) {
+                for (int d = 0; d < dof; ++d) path_states[(size_t)i * dof + d] = path[i][d];
+            }
+        }
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -4,7 +4,7 @@
 #ifndef STUB_ROS_TIME_H
 #define STUB_ROS_TIME_H
 namespace ros {
-struct Time { double t = 0.0; static Time now() { return Time(); } Time() { } explicit Time(double s) : t(s) { } };
-struct Duration { double d = 0.0; Duration() { } explicit Duration(double s) : d(s) { } };
+struct Time { double t = 0.0; static Time now() { return Time(); } Time() { } explicit Time(double s) : t(s) { } double toSec() const { return t; } };
+struct Duration { double d = 0.0; Duration() { } explicit Duration(double s) : d(s) { } double toSec() const { return d; } };
 } // namespace ros
 #endif

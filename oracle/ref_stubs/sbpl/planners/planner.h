@@ -12,11 +12,39 @@
 
 #define INFINITECOST 1000000000
 
+#include <cstdio>
+
+#define NUMOFINDICES_STATEID2IND 2
+
+struct MDPConfig { int startstateid; int goalstateid; };
+class CMDPSTATE;
+
+// The virtuals RobotPlanningSpace overrides (smpl/graph/robot_planning_space.h:115-180, 211-214): SBPL's
+// DiscreteSpaceInformation plus the ...ByGroup / ...WithExpansion entries of the author's SBPL fork.  Declarations
+// only; StateID2IndexMapping is the per-state scratch array SBPL planners index by state id.
 class DiscreteSpaceInformation
 {
 public:
-    virtual ~DiscreteSpaceInformation() { }
+    std::vector<int*> StateID2IndexMapping;
+
+    virtual ~DiscreteSpaceInformation() { for (int* p : StateID2IndexMapping) delete[] p; }
+    virtual bool InitializeEnv(const char*) { return false; }
+    virtual bool InitializeMDPCfg(MDPConfig*) { return false; }
+    virtual int GetFromToHeuristic(int, int) { return 0; }
+    virtual int GetGoalHeuristic(int) { return 0; }
+    virtual int GetStartHeuristic(int) { return 0; }
     virtual void GetSuccs(int SourceStateID, std::vector<int>* SuccIDV, std::vector<int>* CostV) = 0;
+    virtual void GetPreds(int, std::vector<int>*, std::vector<int>*) { }
+    virtual void GetLazySuccs(int, std::vector<int>*, std::vector<int>*, std::vector<bool>*) { }
+    virtual int GetTrueCost(int, int) { return -1; }
+    virtual void GetSuccsByGroup(int, std::vector<int>*, std::vector<int>*, std::vector<int>*, int) { }
+    virtual void GetSuccsByGroupAndExpansion(int, std::vector<int>*, std::vector<int>*, int, int) { }
+    virtual void GetSuccsWithExpansion(int, std::vector<int>*, std::vector<int>*, int) { }
+    virtual void GetPredsByGroupAndExpansion(int, std::vector<int>*, std::vector<int>*, std::vector<int>*, int, int, int) { }
+    virtual bool updateMultipleStartStates(std::vector<int>*, std::vector<double>*, int) { return false; }
+    virtual void SetAllActionsandAllOutcomes(CMDPSTATE*) { }
+    virtual int SizeofCreatedEnv() { return 0; }
+    virtual void PrintState(int, bool, FILE* = nullptr) { }
 };
 
 class StateChangeQuery

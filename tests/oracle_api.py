@@ -703,6 +703,33 @@ class RefCollisionScene:
         self.R.refcc_limits(self.h, _dp(lo), _dp(hi), _bp(c))
         return lo, hi, c
 
+    def plan(self, scene, start, goal_xyz, params, max_path=4096):
+        """One query through the reference's ManipLattice + BfsHeuristic + ARAStar (oracle/ref_planner_shim.cpp);
+        same result dict as OracleScene.plan."""
+        start = np.ascontiguousarray(start, dtype=np.float64)
+        goal = np.ascontiguousarray(goal_xyz, dtype=np.float64)
+        res = np.ascontiguousarray(params.resolutions, dtype=np.float64)
+        prims = np.ascontiguousarray(params.mprims, dtype=np.float64)
+        flags = np.ascontiguousarray(params.short_flags, dtype=np.uint8)
+        tol = np.ascontiguousarray(params.xyz_tolerance, dtype=np.float64)
+        T = np.ascontiguousarray(np.asarray(scene.T_kin_to_planning, np.float64).reshape(3, 4))
+        off = np.ascontiguousarray(scene.xyz_offset, dtype=np.float64)
+        summary = np.zeros(8, np.int32)
+        path = np.zeros(max_path, np.int32)
+        pstates = np.zeros((max_path, len(start)), np.float64)
+        rc = self.R.refcc_plan(self.h, scene.chain_root.encode(), scene.chain_tip.encode(), scene.planning_link.encode(),
+                               _dp(T), _dp(off), C.c_double(scene.inflation_radius), int(scene.cost_per_cell),
+                               _dp(start), _dp(goal), _dp(res), _dp(prims), _bp(flags), len(prims),
+                               int(params.use_short_dist), C.c_double(params.short_dist_thresh),
+                               C.c_double(params.epsilon), int(params.max_expansions), _dp(tol),
+                               _ip(summary), _ip(path), max_path, _dp(pstates))
+        if rc != 0:
+            raise RuntimeError("refcc_plan: the reference refused step %d" % -rc)
+        n = int(summary[3])
+        return dict(path_states=pstates[:min(int(summary[5]), max_path)].copy(), success=bool(summary[0]),
+                    expansions=int(summary[1]), cost=int(summary[2]), path_ids=path[:min(n, max_path)].copy(),
+                    num_states=int(summary[4]))
+
 
 class _BfsBase:
     prefix = None

@@ -90,8 +90,8 @@ def make_reference(scene, attach):
     return r
 
 
-def make_restatement(scene, attach):
-    o = make_oracle(scene, with_kdl=False)
+def make_restatement(scene, attach, with_kdl=False):
+    o = make_oracle(scene, with_kdl=with_kdl)
     if attach is not None:
         assert o.attach_box(*attach) > 0
     return o

@@ -1,0 +1,81 @@
+"""Pins the query level -- oracle/lattice.cpp (ManipLattice bookkeeping), the BfsHeuristic of oracle/kdl_model.cpp and
+oracle/arastar.h working together -- against the REFERENCE's own planning stack: ManipLattice, RobotPlanningSpace,
+BfsHeuristic + BFS_3D, ARAStar and CollisionSpace compiled where they lie (oracle/ref_planner_shim.cpp, part of
+oracle/_ref/libref_collision.so).  The RobotModel plug-in (KDL is absent) and the action space (fork defect 2) are the
+shim's, as its header explains.  Same success flag, expansion count, cost, lattice size, state-id path and extracted
+joint path.
+
+tests/golden/plans_reference.json holds the reference build's results (tools/gen_golden_plans_reference.py); the
+restatement is checked against it where oracle/_ref is absent, and tests/golden/pr2_tabletop_plans.json -- the plans the
+GPU batch planner has to reproduce (tests/test_gpu_planner.py) -- is checked to be what the reference build returns.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from helpers import make_oracle
+from oracle_api import ref_collision_lib
+from smpl_b200 import scenes
+from test_oracle_collision import UBR1_BOX, make_reference, make_restatement
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+needs_ref = pytest.mark.skipif(ref_collision_lib() is None, reason="oracle/_ref/libref_collision.so not built")
+
+
+def plan_cases():
+    """name -> (scene, attach, params, starts, goals)"""
+    pr2 = scenes.pr2_tabletop_scene()
+    p1 = scenes.PlanParams(pr2.dof)
+    p1.max_expansions = 2000
+    s1, g1 = scenes.tabletop_queries(8, seed=3)
+    ubr1 = scenes.ubr1_tabletop_scene()          # config 4 shape: extra ACM entries, grasped object
+    ubr1.attached = None                          # ... attached through attachObject / attach_box on both sides
+    attach = ("object", "wrist_roll_link") + UBR1_BOX
+    p2 = scenes.PlanParams(ubr1.dof)
+    p2.max_expansions = 800
+    s2, g2 = scenes.ubr1_tabletop_queries(6, seed=31)
+    return {"pr2_tabletop": (pr2, None, p1, s1, g1), "ubr1_tabletop": (ubr1, attach, p2, s2, g2)}
+
+
+def summary(p):
+    return [int(p["success"]), int(p["expansions"]), int(p["cost"]), int(p["num_states"]), [int(i) for i in p["path_ids"]]]
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["pr2_tabletop", "ubr1_tabletop"])
+def test_restatement_plans_equal_reference_build(name):
+    scene, attach, params, starts, goals = plan_cases()[name]
+    o = make_restatement(scene, attach, with_kdl=True)
+    r = make_reference(scene, attach)
+    solved = 0
+    for s, g in zip(starts, goals):
+        o.heur_init(scene.inflation_radius, scene.cost_per_cell)
+        a = o.plan(s, g, params)
+        b = r.plan(scene, s, g, params)
+        assert summary(a) == summary(b)
+        assert np.array_equal(a["path_states"], b["path_states"])
+        solved += a["success"]
+    assert solved >= 2
+
+
+@needs_ref
+def test_committed_golden_plans_are_the_reference_builds():
+    gold = json.load(open(os.path.join(GOLD, "pr2_tabletop_plans.json")))
+    scene = scenes.pr2_tabletop_scene()
+    r = make_reference(scene, None)
+    params = scenes.PlanParams(scene.dof)
+    params.max_expansions = gold["max_expansions"]
+    for s, g, res in zip(gold["starts"], gold["goals"], gold["results"]):
+        assert summary(r.plan(scene, np.array(s), np.array(g), params)) == res[:5]
+
+
+def test_restatement_plans_equal_golden_reference_outputs():
+    gold = json.load(open(os.path.join(GOLD, "plans_reference.json")))
+    for name, (scene, attach, params, starts, goals) in plan_cases().items():
+        o = make_restatement(scene, attach, with_kdl=True)
+        for s, g, res in zip(starts, goals, gold[name]):
+            o.heur_init(scene.inflation_radius, scene.cost_per_cell)
+            assert summary(o.plan(s, g, params)) == res
