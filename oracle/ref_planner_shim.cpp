@@ -28,6 +28,7 @@
 #include <smpl/debug/visualize.h>
 #include <smpl/graph/manip_lattice.h>
 #include <smpl/heuristic/bfs_heuristic.h>
+#include <smpl/post_processing.h>
 #include <smpl/search/arastar.h>
 
 #include "kdl_model.h"
@@ -250,6 +251,34 @@ int refcc_plan(refcc_scene* s, const char* chain_root, const char* chain_tip, co
         }
     }
     return 0;
+}
+
+/// ShortcutPath(rm, cc, pin, pout, type) / InterpolatePath(cc, path) of smpl/src/post_processing.cpp on a joint-space
+/// path (n x dof): kind 0 = JOINT_SPACE, 1 = JOINT_POSITION_VELOCITY_SPACE, 2 = InterpolatePath.  out: [max_out][dof];
+/// returns the number of points (negative: too many for max_out, or the reference reported failure).
+int refcc_post_process(refcc_scene* s, const char* chain_root, const char* chain_tip, const char* planning_link,
+                       const double* path, int n, int kind, double* out, int max_out)
+{
+    const int dof = s->dof;
+    ShimRobotModel robot;
+    std::string err;
+    if (!robot.kdl.init(s->desc, s->planning_joints, chain_root, chain_tip, &err)) return -1;
+    if (!robot.kdl.setPlanningLink(planning_link)) return -2;
+    robot.setPlanningJoints(s->planning_joints);
+    std::vector<RobotState> pin(n), pout;
+    for (int i = 0; i < n; ++i) pin[i].assign(path + (size_t)i * dof, path + (size_t)(i + 1) * dof);
+    if (kind == 2) {
+        pout = pin;
+        if (!InterpolatePath(*s->cc, pout)) return -3;
+    } else {
+        ShortcutPath(&robot, s->cc.get(), pin, pout,
+                     kind == 0 ? ShortcutType::JOINT_SPACE : ShortcutType::JOINT_POSITION_VELOCITY_SPACE);
+    }
+    if ((int)pout.size() > max_out) return -(int)pout.size();
+    for (size_t i = 0; i < pout.size(); ++i) {
+        for (int d = 0; d < dof; ++d) out[i * dof + d] = pout[i][d];
+    }
+    return (int)pout.size();
 }
 
 } // extern "C"

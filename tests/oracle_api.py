@@ -703,6 +703,19 @@ class RefCollisionScene:
         self.R.refcc_limits(self.h, _dp(lo), _dp(hi), _bp(c))
         return lo, hi, c
 
+    def post_process(self, scene, path, kind, max_points=1 << 16):
+        """ShortcutPath (kind 0 JOINT_SPACE, 1 JOINT_POSITION_VELOCITY_SPACE) / InterpolatePath (kind 2) of the
+        reference's post_processing.cpp; returns the points, or None when the reference reports failure."""
+        path = self._q(path)
+        out = np.zeros((max_points, self.dof), np.float64)
+        n = self.R.refcc_post_process(self.h, scene.chain_root.encode(), scene.chain_tip.encode(),
+                                      scene.planning_link.encode(), _dp(path), len(path), int(kind), _dp(out), max_points)
+        if n == -3:
+            return None
+        if n < 0:
+            raise RuntimeError("refcc_post_process: %d" % n)
+        return out[:n].copy()
+
     def plan(self, scene, start, goal_xyz, params, max_path=4096):
         """One query through the reference's ManipLattice + BfsHeuristic + ARAStar (oracle/ref_planner_shim.cpp);
         same result dict as OracleScene.plan."""

@@ -79,3 +79,58 @@ def test_restatement_plans_equal_golden_reference_outputs():
         for s, g, res in zip(starts, goals, gold[name]):
             o.heur_init(scene.inflation_radius, scene.cost_per_cell)
             assert summary(o.plan(s, g, params)) == res
+
+
+def _wandering_paths(anchors, n_paths, dof, seed):
+    """random walks, jittered lines and detours between valid states (20 to 60 points)"""
+    rng = np.random.default_rng(seed)
+    paths = []
+    for p in range(n_paths):
+        m = int(rng.integers(20, 61))
+        a, b = anchors[rng.integers(0, len(anchors), 2)]
+        if p % 3 == 0:
+            pts = a + np.cumsum(rng.normal(0.0, 0.06, (m, dof)), axis=0)
+        elif p % 3 == 1:
+            pts = a + np.linspace(0.0, 1.0, m)[:, None] * (b - a) * 0.5 + rng.normal(0.0, 0.02, (m, dof))
+        else:
+            t = np.concatenate([np.linspace(0, 1, m // 2 + 1), np.linspace(1, 0.2, m - m // 2 - 1)])[:, None]
+            pts = a + t * (b - a) * 0.4
+        paths.append(np.ascontiguousarray(pts[:m]))
+    return paths
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", [0, 1])
+def test_shortcut_paths_equal_reference_post_processing(kind):
+    """ShortcutPath(rm, cc, pin, pout, JOINT_SPACE / JOINT_POSITION_VELOCITY_SPACE) of the reference's
+    own post_processing.cpp (generators, cost functions and shortcut templates, over its own CollisionSpace) against
+    oracle/shortcut.h: the same points."""
+    scene = scenes.pr2_clutter_scene()
+    o = make_oracle(scene)
+    r = make_reference(scene, None)
+    lo, hi, cont = o.joint_limits()
+    q = scenes.random_states(4000, lo, hi, cont, seed=8)
+    anchors = q[o.is_states_valid(q) == 1]
+    shortened = 0
+    for p in _wandering_paths(anchors, 30, scene.dof, seed=4):
+        idx, _ = o.shortcut_path(p, cont, kind=kind)
+        ref = r.post_process(scene, p, kind)
+        assert ref.shape == p[idx].shape and np.array_equal(ref, p[idx])
+        shortened += len(idx) < len(p)
+    assert shortened >= 20
+
+
+@needs_ref
+def test_reference_interpolate_path_rejects_legal_paths():
+    """Fork defect 7 (collision_space.cpp:592-597), observed on the reference build itself: InterpolatePath fails on a
+    path whose points are all within the joint limits, which is why oracle and product leave that test out."""
+    scene = scenes.pr2_clutter_scene()
+    o = make_oracle(scene)
+    r = make_reference(scene, None)
+    lo, hi, cont = o.joint_limits()
+    q = scenes.random_states(2000, lo, hi, cont, seed=8)
+    a = q[o.is_states_valid(q) == 1][0]
+    path = np.stack([a, a + 0.05, a + 0.1])
+    assert o.check_joint_limits(path).all()
+    assert r.post_process(scene, path, 2) is None
+    assert len(o.interpolate_path(path)) >= 3
