@@ -1,0 +1,81 @@
+// ORACLE (test infrastructure only).  The action-space plug-in shared by ref_planner_shim.cpp and ref_dropin_shim.cpp:
+// this fork's ManipLatticeActionSpace reads a motion-primitive format its own files do not have and rotates joints 0/1
+// by joint 3 (SURVEY 8a defect 2); like oracle/lattice.cpp, ShimActionSpace follows the documented behaviour: every
+// primitive is one waypoint parent + delta, weight 1, long primitives unless use_short_dist and
+// RobotHeuristic::getMetricGoalDistance(planning link position) <= threshold (manip_lattice_action_space.cpp:376-449,
+// 662-691), IK snap primitives off.
+#ifndef ORACLE_REF_PLANNER_PLUGINS_H
+#define ORACLE_REF_PLANNER_PLUGINS_H
+
+#include <vector>
+
+#include <smpl/graph/action_space.h>
+#include <smpl/graph/robot_planning_space.h>
+#include <smpl/heuristic/robot_heuristic.h>
+#include <smpl/robot_model.h>
+
+namespace {
+
+using namespace sbpl::motion;
+
+class ShimActionSpace : public ActionSpace
+{
+public:
+
+    std::vector<std::vector<double>> deltas;   // file order, converse after each primitive (add_converse)
+    std::vector<bool> is_short;
+    bool use_short_dist = false;
+    double short_dist_thresh = 0.0;
+    ForwardKinematicsInterface* fk = nullptr;
+
+    bool apply(const RobotState& parent, std::vector<Action>& actions) override
+    {
+        ActionsWeight w;
+        return apply(parent, actions, w, -1);
+    }
+
+    bool apply(const RobotState& parent, std::vector<Action>& actions, ActionsWeight& weights, int) override
+    {
+        std::vector<double> pose;
+        if (!fk->computePlanningLinkFK(parent, pose)) {
+            return false;
+        }
+        // manip_lattice_action_space.cpp:385-396: distance of the planning link to the goal, from the first heuristic
+        double goal_dist = 0.0;
+        if (planningSpace()->numHeuristics() > 0) {
+            goal_dist = planningSpace()->heuristic(0)->getMetricGoalDistance(pose[0], pose[1], pose[2]);
+        }
+        const bool near_goal = goal_dist <= short_dist_thresh;
+        for (size_t p = 0; p < deltas.size(); ++p) {
+            const bool active = is_short[p] ? (use_short_dist && near_goal) : !(use_short_dist && near_goal);
+            if (!active) continue;
+            Action action(1, parent);
+            for (size_t j = 0; j < parent.size(); ++j) {
+                action[0][j] = deltas[p][j] + parent[j];
+            }
+            actions.push_back(std::move(action));
+            weights.push_back(1.0);
+        }
+        return true;
+    }
+
+    bool applyPredActions(const RobotState&, std::vector<Action>&, ActionsWeight&, int) override { return false; }
+    void setMotionPlanRequestType(int) override { }
+};
+
+/// ManipLatticeActionSpace::addMotionPrim with add_converse (:201-228): the converse follows each primitive
+inline void FillPrimitives(ShimActionSpace& actions, const double* mprims, const uint8_t* short_flags, int n_prims, int dof)
+{
+    for (int p = 0; p < n_prims; ++p) {
+        std::vector<double> d(mprims + (size_t)p * dof, mprims + (size_t)(p + 1) * dof);
+        actions.deltas.push_back(d);
+        actions.is_short.push_back(short_flags[p] != 0);
+        for (double& v : d) v = -v;
+        actions.deltas.push_back(d);
+        actions.is_short.push_back(short_flags[p] != 0);
+    }
+}
+
+} // namespace
+
+#endif

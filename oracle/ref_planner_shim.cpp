@@ -32,6 +32,7 @@
 #include <smpl/search/arastar.h>
 
 #include "kdl_model.h"
+#include "ref_planner_plugins.h"
 #include "ref_collision_scene.h"
 
 using namespace sbpl;
@@ -92,51 +93,6 @@ public:
     }
 };
 
-class ShimActionSpace : public ActionSpace
-{
-public:
-
-    std::vector<std::vector<double>> deltas;   // file order, converse after each primitive (add_converse)
-    std::vector<bool> is_short;
-    bool use_short_dist = false;
-    double short_dist_thresh = 0.0;
-    ForwardKinematicsInterface* fk = nullptr;
-
-    bool apply(const RobotState& parent, std::vector<Action>& actions) override
-    {
-        ActionsWeight w;
-        return apply(parent, actions, w, -1);
-    }
-
-    bool apply(const RobotState& parent, std::vector<Action>& actions, ActionsWeight& weights, int) override
-    {
-        std::vector<double> pose;
-        if (!fk->computePlanningLinkFK(parent, pose)) {
-            return false;
-        }
-        // manip_lattice_action_space.cpp:385-396: distance of the planning link to the goal, from the first heuristic
-        double goal_dist = 0.0;
-        if (planningSpace()->numHeuristics() > 0) {
-            goal_dist = planningSpace()->heuristic(0)->getMetricGoalDistance(pose[0], pose[1], pose[2]);
-        }
-        const bool near_goal = goal_dist <= short_dist_thresh;
-        for (size_t p = 0; p < deltas.size(); ++p) {
-            const bool active = is_short[p] ? (use_short_dist && near_goal) : !(use_short_dist && near_goal);
-            if (!active) continue;
-            Action action(1, parent);
-            for (size_t j = 0; j < parent.size(); ++j) {
-                action[0][j] = deltas[p][j] + parent[j];
-            }
-            actions.push_back(std::move(action));
-            weights.push_back(1.0);
-        }
-        return true;
-    }
-
-    bool applyPredActions(const RobotState&, std::vector<Action>&, ActionsWeight&, int) override { return false; }
-    void setMotionPlanRequestType(int) override { }
-};
-
 } // namespace
 
 extern "C" {
@@ -176,14 +132,7 @@ int refcc_plan(refcc_scene* s, const char* chain_root, const char* chain_tip, co
     actions.fk = &robot;
     actions.use_short_dist = use_short_dist != 0;
     actions.short_dist_thresh = short_dist_thresh;
-    for (int p = 0; p < n_prims; ++p) {   // ManipLatticeActionSpace::addMotionPrim with add_converse (:201-228)
-        std::vector<double> d(mprims + (size_t)p * dof, mprims + (size_t)(p + 1) * dof);
-        actions.deltas.push_back(d);
-        actions.is_short.push_back(short_flags[p] != 0);
-        for (double& v : d) v = -v;
-        actions.deltas.push_back(d);
-        actions.is_short.push_back(short_flags[p] != 0);
-    }
+    FillPrimitives(actions, mprims, short_flags, n_prims, dof);
 
     ManipLattice space;
     const std::vector<double> res(resolutions, resolutions + dof);

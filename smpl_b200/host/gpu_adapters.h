@@ -18,7 +18,15 @@
 
 #include "../../include/smplgpu.h"
 #include "robot_tables.h"
+#ifdef SMPLHOST_REFERENCE_HEADERS
+// built inside the reference's tree: the reference's own interface headers
+#include <smpl/collision_checker.h>
+#include <smpl/robot_model.h>
+#include <smpl/heuristic/robot_heuristic.h>
+#else
+// stand-alone build: the same interfaces restated (names, signatures, defaults as in the reference)
 #include "smpl/interfaces.h"
+#endif
 
 namespace smplhost {
 

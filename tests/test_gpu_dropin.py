@@ -1,0 +1,73 @@
+"""The drop-in claim, run literally (BASELINE north_star: "existing planners link unchanged"): the REFERENCE's own
+ManipLattice + RobotPlanningSpace + ARAStar, compiled from /root/reference, plan queries with the product's plug-ins
+behind the reference's own interfaces -- GpuCollisionSpace as CollisionChecker, GpuRobotModel as RobotModel +
+ForwardKinematicsInterface, GpuBfsHeuristic as RobotHeuristic (smpl_b200/host/gpu_adapters.cpp compiled against the
+reference's real headers) -- so every isStateToStateValid / GetGoalHeuristic / computePlanningLinkFK / checkJointLimits
+call of the reference's search is answered by a CUDA kernel through the C ABI (oracle/ref_dropin_shim.cpp ->
+oracle/_ref/libref_dropin.so).  The plans must equal the all-reference run's (tests/golden/plans_reference.json, written
+by the reference's own CollisionSpace + BfsHeuristic + BFS_3D): success, expansions, cost, lattice size, id path."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from smpl_b200 import api
+from test_oracle_planner_reference import plan_cases
+
+pytestmark = pytest.mark.gpu
+
+LIB = os.path.join(ROOT, "oracle", "_ref", "libref_dropin.so")
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def dropin_plan(lib, ctx, scene, start, goal, params, max_path=4096):
+    dof = scene.dof
+    start = np.ascontiguousarray(start, np.float64)
+    goal = np.ascontiguousarray(goal, np.float64)
+    origin = np.ascontiguousarray(scene.origin, np.float64)
+    dims = np.ascontiguousarray(scene.dims, np.int32)
+    off = np.ascontiguousarray(scene.xyz_offset, np.float64)
+    res = np.ascontiguousarray(params.resolutions, np.float64)
+    prims = np.ascontiguousarray(params.mprims, np.float64)
+    flags = np.ascontiguousarray(params.short_flags, np.uint8)
+    tol = np.ascontiguousarray(params.xyz_tolerance, np.float64)
+    summary = np.zeros(8, np.int32)
+    path = np.zeros(max_path, np.int32)
+    pstates = np.zeros((max_path, dof), np.float64)
+    rc = lib.refdrop_plan(ctx.h, scene.robot_path.encode(), scene.group.encode(), ",".join(scene.planning_joints).encode(),
+                          scene.planning_link.encode(), _p(origin, C.c_double), C.c_double(scene.res), _p(dims, C.c_int32),
+                          C.c_double(scene.inflation_radius), int(scene.cost_per_cell),
+                          _p(start, C.c_double), _p(goal, C.c_double), _p(off, C.c_double),
+                          _p(res, C.c_double), _p(prims, C.c_double), _p(flags, C.c_uint8), len(prims),
+                          int(params.use_short_dist), C.c_double(params.short_dist_thresh), C.c_double(params.epsilon),
+                          int(params.max_expansions), _p(tol, C.c_double), _p(summary, C.c_int32), _p(path, C.c_int32),
+                          max_path, _p(pstates, C.c_double))
+    assert rc == 0, "refdrop_plan refused step %d: %s" % (-rc, ctx.L.smplgpu_last_error(ctx.h))
+    n = int(summary[3])
+    return [int(summary[0]), int(summary[1]), int(summary[2]), int(summary[4]), [int(i) for i in path[:n]]]
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libref_dropin.so not built")
+def test_reference_planner_over_gpu_plugins_returns_the_reference_plans():
+    lib = C.CDLL(LIB)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "plans_reference.json")))
+    scene, attach, params, starts, goals = plan_cases()["pr2_tabletop"]
+    assert attach is None
+    ctx, tables = api.setup_context(scene)
+    try:
+        launches0 = ctx.launch_count()
+        solved = 0
+        for s, g, want in zip(starts, goals, gold["pr2_tabletop"]):
+            got = dropin_plan(lib, ctx, scene, s, g, params)
+            assert got == want
+            solved += got[0]
+        assert solved >= 4
+        assert ctx.launch_count() - launches0 > 10000     # the reference's search really ran on the device
+    finally:
+        ctx.close()
