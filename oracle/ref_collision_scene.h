@@ -14,6 +14,7 @@ namespace sbpl { class EuclidDistanceMap; }   // euclid_distance_map.h has no in
 
 struct refcc_scene
 {
+    std::string robot_path;
     oracle::RobotDesc desc;
     urdf::ModelInterface urdf;
     sbpl::collision::CollisionModelConfig config;

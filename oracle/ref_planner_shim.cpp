@@ -9,16 +9,12 @@
 // and the BfsHeuristic of oracle/kdl_model.cpp: same path (state ids), cost, expansion count, lattice size and
 // extracted joint path (tests/test_oracle_planner_reference.py, tests/golden/plans_reference.json).
 //
-// Two plug-ins of the reference are NOT its own code here, and say so:
-//  * the RobotModel.  The reference's KDLRobotModel needs orocos_kdl / kdl_parser / urdf (absent).  ShimRobotModel
-//    implements the reference's RobotModel + ForwardKinematicsInterface (+ an InverseKinematicsInterface that always
-//    fails: ManipLattice::init insists on one, manip_lattice.cpp:100-104) over oracle::KDLRobotModel (liboracle.so),
-//    the restatement of kdl_robot_model.cpp + KDL that the product's planning_fk kernels are tested against.
-//  * the ActionSpace.  This fork's ManipLatticeActionSpace reads a motion-primitive format its own files do not have
-//    and rotates joints 0/1 by joint 3 (SURVEY 8a defect 2); like oracle/lattice.cpp, ShimActionSpace follows the
-//    documented behaviour: every primitive is one waypoint parent + delta, weight 1, long primitives unless
-//    use_short_dist and BfsHeuristic::getMetricGoalDistance(planning link position) <= threshold
-//    (manip_lattice_action_space.cpp:376-449, 662-691), IK snap primitives off.
+// The RobotModel is the reference's own KDLRobotModel (sbpl_kdl_robot_model/src/kdl_robot_model.cpp, compiled where it
+// lies against the KDL / kdl_parser stand-ins of oracle/ref_stubs/collision/kdl: KDL's arithmetic restated from its
+// published sources, the reference's control flow its own).  One plug-in is NOT the reference's code, and says so:
+//  * the ActionSpace (oracle/ref_planner_plugins.h).  This fork's ManipLatticeActionSpace reads a motion-primitive
+//    format its own files do not have and rotates joints 0/1 by joint 3 (SURVEY 8a defect 2); like oracle/lattice.cpp,
+//    ShimActionSpace follows the documented behaviour.
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -31,7 +27,8 @@
 #include <smpl/post_processing.h>
 #include <smpl/search/arastar.h>
 
-#include "kdl_model.h"
+#include <sbpl_kdl_robot_model/kdl_robot_model.h>
+
 #include "ref_planner_plugins.h"
 #include "ref_collision_scene.h"
 
@@ -58,40 +55,23 @@ void InitializeVizLocation(VizLocation* loc, const std::string&, Level level)
 
 namespace {
 
-class ShimRobotModel :
-    public virtual RobotModel,
-    public ForwardKinematicsInterface,
-    public InverseKinematicsInterface
+/// the reference's own KDLRobotModel (sbpl_kdl_robot_model/src/kdl_robot_model.cpp over the KDL stand-in), set up as
+/// call_planner.cpp does: init(urdf, planning joints, chain root, chain tip), kinematics -> planning transform,
+/// planning link
+bool SetupRobotModel(sbpl::motion::KDLRobotModel& robot, refcc_scene* s, const char* chain_root, const char* chain_tip,
+                     const char* planning_link, const double* T_kin_to_planning /*3x4, nullable*/)
 {
-public:
-
-    oracle::KDLRobotModel kdl;
-
-    double minPosLimit(int jidx) const override { return kdl.min_limits[jidx]; }
-    double maxPosLimit(int jidx) const override { return kdl.max_limits[jidx]; }
-    bool hasPosLimit(int jidx) const override { return !kdl.continuous[jidx]; }   // kdl_robot_model.cpp:262-266
-    bool isContinuous(int jidx) const override { return kdl.continuous[jidx]; }
-    double velLimit(int) const override { return 0.0; }
-    double accLimit(int) const override { return 0.0; }
-    bool checkJointLimits(const RobotState& state, bool = false) override { return kdl.checkJointLimits(state); }
-
-    bool computeFK(const RobotState&, const std::string&, std::vector<double>&) override { return false; }
-    bool computePlanningLinkFK(const RobotState& state, std::vector<double>& pose) override
-    {
-        return kdl.computePlanningLinkFK(state, pose);
+    if (!robot.init(s->robot_path, s->planning_joints, chain_root, chain_tip)) return false;
+    if (T_kin_to_planning) {
+        KDL::Frame f;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) f.M.data[3 * r + c] = T_kin_to_planning[4 * r + c];
+            f.p.data[r] = T_kin_to_planning[4 * r + 3];
+        }
+        robot.setKinematicsToPlanningTransform(f, "planning");
     }
-
-    bool computeIK(const std::vector<double>&, const RobotState&, RobotState&, ik_option::IkOption) override { return false; }
-    bool computeIK(const std::vector<double>&, const RobotState&, std::vector<RobotState>&, ik_option::IkOption) override { return false; }
-
-    Extension* getExtension(size_t class_code) override
-    {
-        if (class_code == GetClassCode<RobotModel>()) return static_cast<RobotModel*>(this);
-        if (class_code == GetClassCode<ForwardKinematicsInterface>()) return static_cast<ForwardKinematicsInterface*>(this);
-        if (class_code == GetClassCode<InverseKinematicsInterface>()) return static_cast<InverseKinematicsInterface*>(this);
-        return nullptr;
-    }
-};
+    return robot.setPlanningLink(planning_link);
+}
 
 } // namespace
 
@@ -112,17 +92,8 @@ int refcc_plan(refcc_scene* s, const char* chain_root, const char* chain_tip, co
     std::memset(out_summary, 0, 6 * sizeof(int32_t));
     const int dof = s->dof;
 
-    ShimRobotModel robot;
-    std::string err;
-    if (!robot.kdl.init(s->desc, s->planning_joints, chain_root, chain_tip, &err)) return -1;
-    oracle::KdlFrame f = oracle::KdlFrame::Identity();
-    for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 3; ++c) f.M[3 * r + c] = T_kin_to_planning[4 * r + c];
-        f.p[r] = T_kin_to_planning[4 * r + 3];
-    }
-    robot.kdl.setKinematicsToPlanningTransform(f);
-    if (!robot.kdl.setPlanningLink(planning_link)) return -2;
-    robot.setPlanningJoints(s->planning_joints);
+    KDLRobotModel robot;
+    if (!SetupRobotModel(robot, s, chain_root, chain_tip, planning_link, T_kin_to_planning)) return -1;
 
     PlanningParams params;
     params.cost_per_cell = cost_per_cell;
@@ -202,6 +173,36 @@ int refcc_plan(refcc_scene* s, const char* chain_root, const char* chain_tip, co
     return 0;
 }
 
+/// KDLRobotModel::computePlanningLinkFK (kdl_robot_model.cpp:400-423) and checkJointLimits (:326-337) for n states:
+/// pose6 [n][6] = x y z roll pitch yaw, within [n]
+int refcc_kdl_fk_and_limits(refcc_scene* s, const char* chain_root, const char* chain_tip, const char* planning_link,
+                            const double* T_kin_to_planning, const double* q, int n, double* pose6, uint8_t* within)
+{
+    KDLRobotModel robot;
+    if (!SetupRobotModel(robot, s, chain_root, chain_tip, planning_link, T_kin_to_planning)) return -1;
+    std::vector<double> pose;
+    for (int i = 0; i < n; ++i) {
+        const RobotState st(q + (size_t)i * s->dof, q + (size_t)(i + 1) * s->dof);
+        if (!robot.computePlanningLinkFK(st, pose)) return -2;
+        for (int k = 0; k < 6; ++k) pose6[(size_t)i * 6 + k] = pose[k];
+        within[i] = robot.checkJointLimits(st) ? 1 : 0;
+    }
+    return 0;
+}
+
+/// limits as the planner sees them (KDLRobotModel::minPosLimit / maxPosLimit / isContinuous)
+int refcc_kdl_limits(refcc_scene* s, const char* chain_root, const char* chain_tip, double* lo, double* hi, uint8_t* continuous)
+{
+    KDLRobotModel robot;
+    if (!robot.init(s->robot_path, s->planning_joints, chain_root, chain_tip)) return -1;
+    for (int i = 0; i < s->dof; ++i) {
+        lo[i] = robot.minPosLimit(i);
+        hi[i] = robot.maxPosLimit(i);
+        continuous[i] = robot.isContinuous(i) ? 1 : 0;
+    }
+    return 0;
+}
+
 /// ShortcutPath(rm, cc, pin, pout, type) / InterpolatePath(cc, path) of smpl/src/post_processing.cpp on a joint-space
 /// path (n x dof): kind 0 = JOINT_SPACE, 1 = JOINT_POSITION_VELOCITY_SPACE, 2 = InterpolatePath.  out: [max_out][dof];
 /// returns the number of points (negative: too many for max_out, or the reference reported failure).
@@ -209,11 +210,8 @@ int refcc_post_process(refcc_scene* s, const char* chain_root, const char* chain
                        const double* path, int n, int kind, double* out, int max_out)
 {
     const int dof = s->dof;
-    ShimRobotModel robot;
-    std::string err;
-    if (!robot.kdl.init(s->desc, s->planning_joints, chain_root, chain_tip, &err)) return -1;
-    if (!robot.kdl.setPlanningLink(planning_link)) return -2;
-    robot.setPlanningJoints(s->planning_joints);
+    KDLRobotModel robot;
+    if (!SetupRobotModel(robot, s, chain_root, chain_tip, planning_link, nullptr)) return -1;
     std::vector<RobotState> pin(n), pout;
     for (int i = 0; i < n; ++i) pin[i].assign(path + (size_t)i * dof, path + (size_t)(i + 1) * dof);
     if (kind == 2) {

@@ -6,5 +6,6 @@
 namespace ros {
 struct Time { double t = 0.0; static Time now() { return Time(); } Time() { } explicit Time(double s) : t(s) { } double toSec() const { return t; } };
 struct Duration { double d = 0.0; Duration() { } explicit Duration(double s) : d(s) { } double toSec() const { return d; } };
+inline Duration operator-(const Time& a, const Time& b) { return Duration(a.t - b.t); }
 } // namespace ros
 #endif

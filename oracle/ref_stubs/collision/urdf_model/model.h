@@ -83,6 +83,9 @@ public:
     std::string name_;
     boost::shared_ptr<Link> root_link_;
 };
-// urdf::Model (the XML parser) is not available: models are built programmatically by ref_collision_shim.cpp
-class Model : public ModelInterface { public: bool initString(const std::string&) { return false; } };
+// urdf::Model (the XML parser) is not available: initString takes the PATH of the robot description fixture and the
+// model is built programmatically by ref_collision_shim.cpp (OracleRefUrdfFromFile)
+class ModelInterface;
+bool OracleRefUrdfFromFile(const std::string& path, ModelInterface& model);
+class Model : public ModelInterface { public: bool initString(const std::string& s) { return OracleRefUrdfFromFile(s, *this); } };
 } // namespace urdf

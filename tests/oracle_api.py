@@ -703,6 +703,27 @@ class RefCollisionScene:
         self.R.refcc_limits(self.h, _dp(lo), _dp(hi), _bp(c))
         return lo, hi, c
 
+    def kdl_fk_and_limits(self, scene, q):
+        """KDLRobotModel::computePlanningLinkFK + checkJointLimits of the reference's own kdl_robot_model.cpp (over the
+        KDL stand-in): (pose6[n][6], within[n])"""
+        q = self._q(q)
+        T = np.ascontiguousarray(np.asarray(scene.T_kin_to_planning, np.float64).reshape(3, 4))
+        pose = np.zeros((len(q), 6), np.float64)
+        ok = np.zeros(len(q), np.uint8)
+        rc = self.R.refcc_kdl_fk_and_limits(self.h, scene.chain_root.encode(), scene.chain_tip.encode(),
+                                            scene.planning_link.encode(), _dp(T), _dp(q), len(q), _dp(pose), _bp(ok))
+        if rc != 0:
+            raise RuntimeError("refcc_kdl_fk_and_limits: %d" % rc)
+        return pose, ok
+
+    def kdl_limits(self, scene):
+        lo = np.zeros(self.dof)
+        hi = np.zeros(self.dof)
+        c = np.zeros(self.dof, np.uint8)
+        if self.R.refcc_kdl_limits(self.h, scene.chain_root.encode(), scene.chain_tip.encode(), _dp(lo), _dp(hi), _bp(c)) != 0:
+            raise RuntimeError("refcc_kdl_limits")
+        return lo, hi, c
+
     def post_process(self, scene, path, kind, max_points=1 << 16):
         """ShortcutPath (kind 0 JOINT_SPACE, 1 JOINT_POSITION_VELOCITY_SPACE) / InterpolatePath (kind 2) of the
         reference's post_processing.cpp; returns the points, or None when the reference reports failure."""

@@ -134,3 +134,25 @@ def test_reference_interpolate_path_rejects_legal_paths():
     assert o.check_joint_limits(path).all()
     assert r.post_process(scene, path, 2) is None
     assert len(o.interpolate_path(path)) >= 3
+
+
+@needs_ref
+@pytest.mark.parametrize("robot", ["pr2", "ubr1"])
+def test_kdl_robot_model_equals_reference_build(robot):
+    """the reference's own kdl_robot_model.cpp (compiled against the KDL / kdl_parser
+    stand-ins of oracle/ref_stubs/collision/kdl) against oracle/kdl_model.cpp: the limits the planner sees, the
+    planning-link pose (x y z roll pitch yaw, bit for bit -- including the segment-index quirk of
+    computePlanningLinkFK) and checkJointLimits for states inside, outside and several turns away from the limits."""
+    scene = scenes.pr2_tabletop_scene() if robot == "pr2" else scenes.ubr1_tabletop_scene(attach=False)
+    o = make_oracle(scene)
+    r = make_reference(scene, None)
+    lo, hi, cont = o.joint_limits()
+    rlo, rhi, rcont = r.kdl_limits(scene)
+    assert np.array_equal(lo, rlo) and np.array_equal(hi, rhi) and np.array_equal(cont, rcont)
+    rng = np.random.default_rng(5)
+    q = scenes.random_states(3000, lo, hi, cont, seed=12)
+    q[::3] += rng.normal(0.0, 2.5, q[::3].shape)
+    pose, ok = r.kdl_fk_and_limits(scene, q)
+    assert np.array_equal(o.planning_frame_fk(q), pose)
+    assert np.array_equal(o.check_joint_limits(q), ok)
+    assert 0.2 < ok.mean() < 0.9
