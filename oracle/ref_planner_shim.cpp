@@ -173,6 +173,58 @@ int refcc_plan(refcc_scene* s, const char* chain_root, const char* chain_tip, co
     return 0;
 }
 
+/// BfsHeuristic::GetGoalHeuristic (bfs_heuristic.cpp:148-163, 355-366) of the reference for n joint states: each state
+/// becomes a lattice state of the reference's ManipLattice (getOrCreateState), the goal is set through
+/// ManipLattice::setGoal -> BfsHeuristic::updateGoal -> BFS_3D::run, and the heuristic is asked by state id; h[n] is
+/// followed by the value of the goal state itself (h[n]).  Also returns getMetricGoalDistance of every state's planning
+/// frame position in metric[n].
+int refcc_goal_heuristics(refcc_scene* s, const char* chain_root, const char* chain_tip, const char* planning_link,
+                          const double* T_kin_to_planning, const double* xyz_offset, double inflation_radius,
+                          int cost_per_cell, const double* goal_xyz, const double* resolutions,
+                          const double* q, int n, int32_t* h, double* metric)
+{
+    const int dof = s->dof;
+    KDLRobotModel robot;
+    if (!SetupRobotModel(robot, s, chain_root, chain_tip, planning_link, T_kin_to_planning)) return -1;
+    PlanningParams params;
+    params.cost_per_cell = cost_per_cell;
+    ShimActionSpace actions;
+    actions.fk = &robot;
+    ManipLattice space;
+    const std::vector<double> res(resolutions, resolutions + dof);
+    if (!space.init(&robot, s->cc.get(), &params, res, &actions)) return -3;
+    if (!actions.init(&space)) return -4;
+    BfsHeuristic heur;
+    heur.setCostPerCell(cost_per_cell);
+    heur.setInflationRadius(inflation_radius);
+    if (!heur.init(&space, s->grid.get())) return -5;
+    if (!space.insertHeuristic(&heur)) return -6;
+    GoalConstraint goal;
+    goal.type = GoalType::XYZ_GOAL;
+    goal.pose.assign(6, 0.0);
+    goal.tgt_off_pose.assign(6, 0.0);
+    for (int i = 0; i < 3; ++i) {
+        goal.pose[i] = goal_xyz[i];
+        goal.tgt_off_pose[i] = goal_xyz[i];
+        goal.xyz_offset[i] = xyz_offset[i];
+        goal.xyz_tolerance[i] = 0.015;
+        goal.rpy_tolerance[i] = 0.0;
+    }
+    if (!space.setGoal(goal)) return -7;
+    RobotCoord coord(dof);
+    std::vector<double> pose;
+    for (int i = 0; i < n; ++i) {
+        const RobotState st(q + (size_t)i * dof, q + (size_t)(i + 1) * dof);
+        space.stateToCoord(st, coord);
+        const int id = space.createHashEntry(coord, st);   // one lattice state per input state, whatever its cell
+        h[i] = heur.GetGoalHeuristic(id);
+        if (!space.computePlanningFrameFK(st, pose)) return -8;
+        metric[i] = heur.getMetricGoalDistance(pose[0], pose[1], pose[2]);
+    }
+    h[n] = heur.GetGoalHeuristic(space.getGoalStateID());
+    return 0;
+}
+
 /// KDLRobotModel::computePlanningLinkFK (kdl_robot_model.cpp:400-423) and checkJointLimits (:326-337) for n states:
 /// pose6 [n][6] = x y z roll pitch yaw, within [n]
 int refcc_kdl_fk_and_limits(refcc_scene* s, const char* chain_root, const char* chain_tip, const char* planning_link,

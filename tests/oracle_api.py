@@ -716,6 +716,24 @@ class RefCollisionScene:
             raise RuntimeError("refcc_kdl_fk_and_limits: %d" % rc)
         return pose, ok
 
+    def goal_heuristics(self, scene, goal_xyz, resolutions, q):
+        """BfsHeuristic::GetGoalHeuristic of the reference for joint states q (by lattice state id) -> (h[n], h of the
+        goal state, getMetricGoalDistance[n])"""
+        q = self._q(q)
+        T = np.ascontiguousarray(np.asarray(scene.T_kin_to_planning, np.float64).reshape(3, 4))
+        off = np.ascontiguousarray(scene.xyz_offset, dtype=np.float64)
+        goal = np.ascontiguousarray(goal_xyz, dtype=np.float64)
+        res = np.ascontiguousarray(resolutions, dtype=np.float64)
+        h = np.zeros(len(q) + 1, np.int32)
+        metric = np.zeros(len(q), np.float64)
+        rc = self.R.refcc_goal_heuristics(self.h, scene.chain_root.encode(), scene.chain_tip.encode(),
+                                          scene.planning_link.encode(), _dp(T), _dp(off),
+                                          C.c_double(scene.inflation_radius), int(scene.cost_per_cell), _dp(goal), _dp(res),
+                                          _dp(q), len(q), _ip(h), _dp(metric))
+        if rc != 0:
+            raise RuntimeError("refcc_goal_heuristics: %d" % rc)
+        return h[:-1].copy(), int(h[-1]), metric
+
     def kdl_limits(self, scene):
         lo = np.zeros(self.dof)
         hi = np.zeros(self.dof)

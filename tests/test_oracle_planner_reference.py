@@ -156,3 +156,28 @@ def test_kdl_robot_model_equals_reference_build(robot):
     assert np.array_equal(o.planning_frame_fk(q), pose)
     assert np.array_equal(o.check_joint_limits(q), ok)
     assert 0.2 < ok.mean() < 0.9
+
+
+@needs_ref
+def test_goal_heuristic_values_equal_reference_bfs_heuristic():
+    """SURVEY 8a row a13: BfsHeuristic::GetGoalHeuristic of the reference, asked by lattice state id on the reference's
+    own ManipLattice after ManipLattice::setGoal -> updateGoal -> BFS_3D::run, against the oracle's heuristic on the
+    same joint states: cost_per_cell * distance, Infinity (32767) for planning-frame positions in walls or outside
+    the grid, and cost_per_cell * (-1) -- negative -- for free cells the wavefront never reached (goal buried in the
+    table).  (An out-of-bounds goal makes the reference's BFS_3D throw std::system_error, fork defect 6: not pinned.)"""
+    scene = scenes.pr2_tabletop_scene()
+    o = make_oracle(scene)
+    r = make_reference(scene, None)
+    lo, hi, cont = o.joint_limits()
+    q = scenes.random_states(4000, lo, hi, cont, seed=21)
+    res = scenes.PlanParams(scene.dof).resolutions
+    seen_negative = seen_infinity = False
+    for goal in ((0.4, -0.2, 0.9), (0.6, 0.3, 0.75), (0.55, 0.0, 0.6)):     # two free cells, one inside the table top
+        o.heur_init(scene.inflation_radius, scene.cost_per_cell)
+        o.heur_set_goal(*goal)
+        h_ref, h_goal_state, _ = r.goal_heuristics(scene, goal, res, q)
+        assert np.array_equal(o.goal_heuristics(q), h_ref)
+        assert h_goal_state == 0
+        seen_negative |= bool((h_ref < 0).any())
+        seen_infinity |= bool((h_ref == 32767).any())
+    assert seen_negative and seen_infinity
