@@ -447,7 +447,7 @@ def main():
     post_paths = None
     if rank == 0 and args.post_paths > 0:
         post_paths = wandering_paths(q[d_v.cpu().numpy().astype(bool)], args.post_paths, dof, seed=5)
-        api.shortcut_paths(ctx, tables, post_paths[:8], kind=0)
+        api.shortcut_paths(ctx, tables, post_paths, kind=0)     # warm-up at full size (buffers, lazily loaded kernels)
         t0 = time.perf_counter()
         short, pst = api.shortcut_paths(ctx, tables, post_paths, kind=0)
         dt = time.perf_counter() - t0
@@ -595,20 +595,33 @@ def main():
             k = min(args.post_cpu_paths, len(post_paths))
             t0 = time.perf_counter()
             same = 0
-            for p_, g_ in zip(post_paths[:k], post["_short"][:k]):
-                ref_idx, _ = o.shortcut_path(p_, cont, kind=0)
-                same += int(np.array_equal(ref_idx, g_))
+            # the reference's own ShortcutPath (post_processing.cpp over its CollisionSpace) when its build is there
+            if cpu_kind == "reference":
+                for p_, g_ in zip(post_paths[:k], post["_short"][:k]):
+                    same += int(np.array_equal(checker.post_process(scene, p_, 0), p_[g_]))
+            else:
+                for p_, g_ in zip(post_paths[:k], post["_short"][:k]):
+                    ref_idx, _ = o.shortcut_path(p_, cont, kind=0)
+                    same += int(np.array_equal(ref_idx, g_))
             dt = time.perf_counter() - t0
             post["cpu_paths_per_s"] = k / dt
-            post["cpu_sample"] = "first %d paths, oracle ShortcutPath (one isStateToStateValid per request), 1 thread" % k
+            post["cpu_kind"] = cpu_kind
+            post["cpu_sample"] = "first %d paths, %s ShortcutPath JOINT_SPACE (one isStateToStateValid per request), 1 thread" % (
+                k, "the reference's own" if cpu_kind == "reference" else "oracle")
             post["parity_identical"] = "%d / %d" % (same, k)
         if ingest is not None:
             t0 = time.perf_counter()
-            io = make_oracle(ingest["_scene"], np.zeros(dof))     # VoxelizeBox per object + addPointsToField + propagation
+            io = make_reference_checker(ingest["_scene"], np.zeros(dof))   # WorldCollisionModel::insertObject per box
+            ingest_kind = "reference"
+            if io is None:
+                io = make_oracle(ingest["_scene"], np.zeros(dof))  # VoxelizeBox per object + addPointsToField + propagation
+                ingest_kind = "port"
             dt = time.perf_counter() - t0
             ref_d2 = io.df_d2()
             ingest["cpu_ms"] = dt * 1e3
-            ingest["cpu_sample"] = "oracle: scene construction incl. VoxelizeBox + DistanceMap propagation, 1 thread"
+            ingest["cpu_kind"] = ingest_kind
+            ingest["cpu_sample"] = "%s: scene construction incl. insertObject (VoxelizeBox + addPointsToField) + DistanceMap propagation, 1 thread" % (
+                "the reference's own CollisionSpace + OccupancyGrid" if ingest_kind == "reference" else "oracle")
             ingest["occupied_cells_identical"] = bool(np.array_equal(ref_d2 == 0, ingest["_d2"] == 0))
             ingest["cells_where_reference_propagation_is_inexact"] = int((ref_d2 != ingest["_d2"]).sum())
         if bfs is not None:

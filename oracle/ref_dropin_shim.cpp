@@ -50,6 +50,67 @@ public:
     }
 };
 
+/// INTEGRATION.md section 4, as a subclass instead of an edit: the reference's ManipLattice with GetSuccs collecting
+/// every single-waypoint action first and checking them in ONE GpuCollisionSpace::isEdgesValid call (one launch per
+/// expansion instead of one per successor).  Everything else -- stateToCoord, getOrCreateState, isGoal, cost, the
+/// order successors are emitted in -- is the reference's own code (manip_lattice.cpp:219-313, 1511-1580), reached
+/// through -fno-access-control.
+class BatchedManipLattice : public ManipLattice
+{
+public:
+    smplhost::GpuCollisionSpace* gpu = nullptr;
+    long long batched_calls = 0, edges_submitted = 0;
+
+    void GetSuccs(int state_id, std::vector<int>* succs, std::vector<int>* costs) override
+    {
+        if (!gpu) {
+            ManipLattice::GetSuccs(state_id, succs, costs);   // the reference's own loop: one call per successor
+            return;
+        }
+        if (state_id == m_goal_state_id) {
+            return;   // goal state is absorbing
+        }
+        ManipLatticeState* parent_entry = m_states[state_id];
+        std::vector<Action> actions;
+        ActionsWeight weights;
+        if (!m_actions->apply(parent_entry->state, actions, weights, -1)) {
+            return;
+        }
+        // checkAction, first half: joint limits of every waypoint; multi-waypoint actions (none of the motion
+        // primitives) would keep the per-action path
+        std::vector<size_t> kept;
+        std::vector<RobotState> starts, finishes;
+        for (size_t i = 0; i < actions.size(); ++i) {
+            if (actions[i].size() != 1 || !robot()->checkJointLimits(actions[i][0])) {
+                continue;
+            }
+            kept.push_back(i);
+            starts.push_back(parent_entry->state);
+            finishes.push_back(actions[i][0]);
+        }
+        // checkAction, second half: the edges parent -> waypoint, all at once
+        std::vector<uint8_t> ok;
+        if (!starts.empty() && !gpu->isEdgesValid(starts, finishes, ok)) {
+            return;
+        }
+        ++batched_calls;
+        edges_submitted += (long long)starts.size();
+        RobotCoord succ_coord(robot()->jointVariableCount(), 0);
+        for (size_t k = 0; k < kept.size(); ++k) {
+            if (!ok[k]) {
+                continue;
+            }
+            const Action& action = actions[kept[k]];
+            stateToCoord(action.back(), succ_coord);
+            const int succ_state_id = getOrCreateState(succ_coord, action.back());
+            ManipLatticeState* succ_entry = getHashEntry(succ_state_id);
+            const bool is_goal_succ = isGoal(action.back());
+            succs->push_back(is_goal_succ ? m_goal_state_id : succ_state_id);
+            costs->push_back(cost(parent_entry, succ_entry, weights[kept[k]], is_goal_succ));
+        }
+    }
+};
+
 std::vector<std::string> SplitCsv(const char* s)
 {
     std::vector<std::string> out;
@@ -70,6 +131,8 @@ std::vector<std::string> SplitCsv(const char* s)
 
 extern "C" {
 
+/// batched_get_succs != 0 runs the reference's lattice with the INTEGRATION.md section-4 edit (BatchedManipLattice);
+/// out_summary[6], [7] then hold the number of batched calls and of edges submitted.
 /// ctx: a smplgpu context that already holds the robot tables, the distance field and the planning chain (set up
 /// through the ABI by the caller).  Arguments and summary as refcc_plan / oracle_plan.  Returns 0, or a negative
 /// step number when a step is refused.
@@ -80,9 +143,9 @@ int refdrop_plan(smplgpu_ctx* ctx, const char* robot_path, const char* group, co
                  const double* resolutions, const double* mprims, const uint8_t* short_flags, int n_prims,
                  int use_short_dist, double short_dist_thresh, double epsilon, int max_expansions,
                  const double* xyz_tolerance, int32_t* out_summary, int32_t* path_ids, int max_path,
-                 double* path_states /* nullable */)
+                 double* path_states /* nullable */, int batched_get_succs)
 {
-    std::memset(out_summary, 0, 6 * sizeof(int32_t));
+    std::memset(out_summary, 0, 8 * sizeof(int32_t));
     const std::vector<std::string> joints = SplitCsv(planning_joints_csv);
     const int dof = (int)joints.size();
 
@@ -106,7 +169,9 @@ int refdrop_plan(smplgpu_ctx* ctx, const char* robot_path, const char* group, co
     actions.short_dist_thresh = short_dist_thresh;
     FillPrimitives(actions, mprims, short_flags, n_prims, dof);
 
-    ManipLattice space;
+    // batched_get_succs: the reference's lattice with the section-4 edit (BatchedManipLattice) instead of the plain one
+    BatchedManipLattice space;
+    space.gpu = batched_get_succs ? &checker : nullptr;
     const std::vector<double> res(resolutions, resolutions + dof);
     if (!space.init(&robot, &checker, &params, res, &actions)) return -3;
     if (!actions.init(&space)) return -4;
@@ -159,6 +224,8 @@ int refdrop_plan(smplgpu_ctx* ctx, const char* robot_path, const char* group, co
     const int ret = search.replan(tp, &solution, &solcost);
     out_summary[1] = search.get_n_expands();
     out_summary[4] = (int)space.m_states.size();
+    out_summary[6] = (int)space.batched_calls;
+    out_summary[7] = (int)space.edges_submitted;
     if (!ret || solcost >= INFINITECOST) {
         return 0;
     }

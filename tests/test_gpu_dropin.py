@@ -26,7 +26,7 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def dropin_plan(lib, ctx, scene, start, goal, params, max_path=4096):
+def dropin_plan(lib, ctx, scene, start, goal, params, max_path=4096, batched=False):
     dof = scene.dof
     start = np.ascontiguousarray(start, np.float64)
     goal = np.ascontiguousarray(goal, np.float64)
@@ -47,9 +47,10 @@ def dropin_plan(lib, ctx, scene, start, goal, params, max_path=4096):
                           _p(res, C.c_double), _p(prims, C.c_double), _p(flags, C.c_uint8), len(prims),
                           int(params.use_short_dist), C.c_double(params.short_dist_thresh), C.c_double(params.epsilon),
                           int(params.max_expansions), _p(tol, C.c_double), _p(summary, C.c_int32), _p(path, C.c_int32),
-                          max_path, _p(pstates, C.c_double))
+                          max_path, _p(pstates, C.c_double), int(batched))
     assert rc == 0, "refdrop_plan refused step %d: %s" % (-rc, ctx.L.smplgpu_last_error(ctx.h))
     n = int(summary[3])
+    dropin_plan.last_batched = (int(summary[6]), int(summary[7]))
     return [int(summary[0]), int(summary[1]), int(summary[2]), int(summary[4]), [int(i) for i in path[:n]]]
 
 
@@ -69,5 +70,37 @@ def test_reference_planner_over_gpu_plugins_returns_the_reference_plans():
             solved += got[0]
         assert solved >= 4
         assert ctx.launch_count() - launches0 > 10000     # the reference's search really ran on the device
+    finally:
+        ctx.close()
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libref_dropin.so not built")
+def test_reference_lattice_with_batched_get_succs_returns_the_same_plans():
+    """INTEGRATION.md section 4 on the reference's own lattice: GetSuccs collects the successors of an expansion and
+    checks them in one GpuCollisionSpace::isEdgesValid call (BatchedManipLattice in oracle/ref_dropin_shim.cpp, every
+    other line of the expansion is the reference's).  Same plans with fewer device calls: the edge checks shrink to
+    one launch group per expansion; what remains are the reference's per-state calls (checkJointLimits and
+    computePlanningLinkFK per successor, GetGoalHeuristic per new state), which only a caller that batches those too --
+    smplgpu_expand_batch behind smplhost_plan_batch -- gets rid of."""
+    import time
+    lib = C.CDLL(LIB)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "plans_reference.json")))
+    scene, attach, params, starts, goals = plan_cases()["pr2_tabletop"]
+    ctx, tables = api.setup_context(scene)
+    try:
+        secs = {}
+        for batched in (False, True):
+            t0 = time.perf_counter()
+            l0 = ctx.launch_count()
+            for s, g, want in zip(starts, goals, gold["pr2_tabletop"]):
+                assert dropin_plan(lib, ctx, scene, s, g, params, batched=batched) == want
+                if batched:
+                    calls, edges = dropin_plan.last_batched
+                    assert calls == want[1] or not want[0] or calls <= want[1]   # at most one call per expansion
+                    assert edges >= calls
+            secs[batched] = (time.perf_counter() - t0, ctx.launch_count() - l0)
+        print("reference lattice over the GPU plug-ins, 8 queries: per-successor calls %.2f s (%d launches), "
+              "batched GetSuccs %.2f s (%d launches)" % (secs[False] + secs[True]))
+        assert secs[True][1] < 0.75 * secs[False][1]
     finally:
         ctx.close()
