@@ -620,6 +620,12 @@ class RefCollisionScene:
         if self.R.refcc_insert_boxes(self.h, _dp(b), len(b)) != 0:
             raise RuntimeError("insertObject failed")
 
+    def insert_shapes(self, rows):
+        """rows[n][16] = kind (0 box, 1 sphere, 2 cylinder, 3 cone), 3 dimensions, pose 3x4: insertObject per shape"""
+        r = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 16)
+        if self.R.refcc_insert_shapes(self.h, _dp(r), len(r)) != 0:
+            raise RuntimeError("insertObject failed")
+
     def attach_box(self, body_id, link, size, pose3x4):
         sz = np.ascontiguousarray(size, dtype=np.float64)
         p = np.ascontiguousarray(pose3x4, dtype=np.float64).reshape(3, 4)

@@ -176,3 +176,36 @@ def test_restatement_equals_golden_reference_outputs():
         assert np.array_equal(e, g[name + "/edges_valid"])
         assert np.array_equal(n, g[name + "/waypoint_counts"])
         assert int(o.df_d2().astype(np.int64).sum()) == int(g[name + "/df_d2_sum"])
+
+
+@needs_ref
+def test_shape_objects_occupy_the_cells_of_the_reference_insert_object():
+    """SURVEY 8f row 3 for every primitive shape: boxes, spheres, cylinders and cones at arbitrary poses inserted through
+    the reference's CollisionSpace::insertObject (VoxelizeObject -> VoxelizeShape -> geometry::Voxelize{Box,Sphere,
+    Cylinder,Cone} -> addPointsToField) occupy exactly the cells that the product's host mesh builders
+    (smplhost_shape_meshes = CreateIndexed*Mesh + TransformVertices) followed by the voxeliser give -- the meshes the
+    device voxeliser is fed (tests/test_gpu_scene_ingest.py checks the device against the same oracle voxeliser)."""
+    from smpl_b200 import api
+    from oracle_api import voxelize_mesh
+    from test_oracle_voxelize import random_pose
+    scene = scenes.pr2_clutter_scene()
+    rng = np.random.default_rng(3)
+    rows = []
+    for kind, dims in ((0, (0.3, 0.2, 0.1)), (1, (0.17, 0, 0)), (2, (0.09, 0.42, 0)), (3, (0.12, 0.3, 0)),
+                       (1, (0.05, 0, 0)), (2, (0.2, 0.05, 0)), (3, (0.3, 0.1, 0)), (0, (0.02, 0.5, 0.5))):
+        pose = random_pose(rng, 0.4)
+        pose[:, 3] += (0.5, 0.0, 1.0)
+        rows.append(np.concatenate([[kind], dims, pose.ravel()]))
+    rows = np.array(rows)
+    r = RefCollisionScene(scene.robot_path, scene.group, scene.planning_joints, scene.origin, scene.size, scene.res,
+                          scene.max_dist)
+    r.insert_shapes(rows)
+    occupied_ref = r.df_d2() == 0
+    occupied = np.zeros_like(occupied_ref)
+    for row in rows:
+        v, t = api.shape_meshes(row[None, :])
+        g = api.world_to_grid(voxelize_mesh("oracle", v, t, scene.res, scene.origin, False), scene.origin, scene.res)
+        inside = np.all((g >= 0) & (g < np.asarray(scene.dims)), axis=1)
+        occupied[tuple(g[inside].T)] = True
+    assert occupied_ref.sum() > 4000
+    assert np.array_equal(occupied, occupied_ref)
