@@ -382,6 +382,7 @@ def main():
     gpu_stats["f64_resolved_edges_last_launch"] = ctx.last_f64_resolved()
     cert_in_use, e_pos, eps_cells = ctx.certified_bounds()
     gpu_stats["certified_f32"] = {"in_use": cert_in_use, "e_pos_m": e_pos, "eps_cells": eps_cells}
+    df_lookup_peak = ctx.probe_df_lookup_rate() if rank == 0 else None   # independent random lookups/s on this field
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
     hq = torch.from_numpy(q).pin_memory()
@@ -655,6 +656,16 @@ def main():
                 "note": "issue/latency bound (FK arithmetic + dependent L2 lookups), not HBM bound: the HBM fraction is reported "
                         "as the contract asks; see DESIGN.md and profiles/ for pipe utilisation and stall reasons",
                 "other_kernel": other}
+    # SURVEY 8d's two fractions for the dominant kernel: HBM = streamed bytes only; L2 = the lookups the reference
+    # semantics requires (one 32-byte sector each) against the measured rate of INDEPENDENT random lookups on the
+    # same field (smplgpu_probe_df_lookup_rate): the kernels' lookups are dependent, so this ceiling is not reachable
+    if df_lookup_peak:
+        Lb, per_item = (Lbar_edge, 16 * dof + 1) if dom is k_edges else (Lbar_state, 8 * dof + 1)
+        roofline["hbm_frac_streamed_bytes"] = n * per_item / (dom["ms"] * 1e-3) / 1e9 / peak
+        roofline["l2"] = {"required_lookups_per_launch": n * Lb, "achieved_glookups_s": n * Lb / (dom["ms"] * 1e-3) / 1e9,
+                          "peak_glookups_s": df_lookup_peak / 1e9, "frac": n * Lb / (dom["ms"] * 1e-3) / df_lookup_peak,
+                          "achieved_gbs": 32 * n * Lb / (dom["ms"] * 1e-3) / 1e9, "peak_gbs": 32 * df_lookup_peak / 1e9,
+                          "peak_source": "measured live: independent random lookups on the loaded field, 8 in flight per thread"}
     if bfs is not None:
         roofline["bfs"] = {"bound": "hbm", "achieved": bfs["achieved_gbs"], "peak": peak, "unit": "GB/s",
                            "frac": bfs["achieved_gbs"] / peak}

@@ -281,6 +281,10 @@ int smplgpu_set_precision_mode(smplgpu_ctx* ctx, int mode);
 int smplgpu_certified_bounds(smplgpu_ctx* ctx, double* e_pos, double* eps_cells);
 /* items (states / edges) of the last validity call that the double-precision kernels had to resolve */
 int smplgpu_last_f64_resolved(smplgpu_ctx* ctx, int64_t* items);
+/* Diagnostic (bench.py's roofline): independent random lookups per second this device sustains on the loaded distance
+ * field (one 32-byte sector each, field cache resident) -- the ceiling of the validity kernels' dependent lookups.
+ * New API, nothing in the reference corresponds to it. */
+int smplgpu_probe_df_lookup_rate(smplgpu_ctx* ctx, double* lookups_per_s);
 /* sphere centres as the single-precision path computes them, float out[n][n_nodes][3] (error-bound test) */
 int smplgpu_fk_sphere_centers_f32(smplgpu_ctx* ctx, const double* q, int n, float* out);
 

@@ -94,6 +94,7 @@ def gpu_lib():
         L.smplgpu_bfs_set_mode.argtypes = [vp, i]
         L.smplgpu_certified_bounds.argtypes = [vp, dp, dp]
         L.smplgpu_last_f64_resolved.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.smplgpu_probe_df_lookup_rate.argtypes = [vp, C.POINTER(C.c_double)]
         L.smplgpu_fk_sphere_centers_f32.argtypes = [vp, dp, i, C.POINTER(C.c_float)]
         L.smplgpu_bfs_bank_create.argtypes = [vp, i, d]
         L.smplgpu_bfs_bank_max_slots.argtypes = [vp]
@@ -438,6 +439,12 @@ class GpuContext:
         a, b = C.c_double(), C.c_double()
         r = self._ck(self.L.smplgpu_certified_bounds(self.h, C.byref(a), C.byref(b)), "certified_bounds")
         return bool(r), a.value, b.value
+
+    def probe_df_lookup_rate(self):
+        """independent random distance-field lookups per second (roofline of the validity kernels' lookups)"""
+        r = C.c_double()
+        self._ck(self.L.smplgpu_probe_df_lookup_rate(self.h, C.byref(r)), "probe_df_lookup_rate")
+        return r.value
 
     def last_f64_resolved(self):
         n = C.c_int64()

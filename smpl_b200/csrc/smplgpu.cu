@@ -1437,6 +1437,53 @@ int smplgpu_certified_bounds(smplgpu_ctx* ctx, double* e_pos, double* eps_cells)
     return ctx->has_model32 ? 1 : 0;
 }
 
+// Roofline probe for the validity kernels: how many INDEPENDENT random distance-field lookups per second this device
+// sustains on the loaded field (uint16 cells, one 32-byte sector per lookup, the field L2 / L1 resident as in the real
+// kernels).  Each thread walks its own LCG sequence of cell indices, eight loads in flight per thread, the whole
+// machine occupied; the kernels' lookups are dependent (a descent), so this is their ceiling, not their target.
+__global__ void df_gather_probe_kernel(const uint16_t* __restrict__ df, unsigned int n_cells, int iters,
+                                       unsigned int* __restrict__ sink)
+{
+    unsigned int x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    unsigned int acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        unsigned int idx[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x = x * 1664525u + 1013904223u;
+            idx[k] = (unsigned int)(((unsigned long long)x * n_cells) >> 32);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += __ldg(&df[idx[k]]);
+    }
+    if (acc == 0xFFFFFFFFu) sink[0] = acc;   // keeps the loads alive
+}
+
+int smplgpu_probe_df_lookup_rate(smplgpu_ctx* ctx, double* lookups_per_s)
+{
+    if (!ctx || !lookups_per_s) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    const unsigned int n_cells = (unsigned int)((size_t)ctx->grid.nx * ctx->grid.ny * ctx->grid.nz);
+    const int blocks = 16 * ctx->sm_count, threads = 256, iters = 256;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    for (int pass = 0; pass < 2; ++pass) {   // the first pass warms the caches
+        CU(cudaEventRecord(e0, ctx->stream));
+        df_gather_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->d_df, n_cells, iters, (unsigned int*)ctx->d_stats);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ++ctx->launches;
+    }
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *lookups_per_s = (double)blocks * threads * iters * 8.0 / ((double)ms * 1e-3);
+    return 0;
+}
+
 int smplgpu_last_f64_resolved(smplgpu_ctx* ctx, int64_t* items)
 {
     if (!ctx || !items) return SMPLGPU_ERR_INVALID;
