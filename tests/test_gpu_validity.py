@@ -252,3 +252,17 @@ def test_missing_scene_is_an_error_not_a_fallback():
         ctx.dof = 7
         ctx.is_states_valid(np.zeros((4, 7)))
     ctx.close()
+
+
+def test_df_lookup_rate_probe():
+    """bench.py's L2 roofline denominator: needs a scene, reports a plausible rate."""
+    scene = scenes.pr2_clutter_scene()
+    ctx, _ = api.setup_context(scene)
+    try:
+        assert 1e10 < ctx.probe_df_lookup_rate() < 1e13
+    finally:
+        ctx.close()
+    bare = api.GpuContext(0)
+    with pytest.raises(api.SmplGpuError):
+        bare.probe_df_lookup_rate()
+    bare.close()
