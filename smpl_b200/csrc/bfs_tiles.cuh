@@ -123,7 +123,6 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int ry = tid & (TILE_E - 1), rz = tid >> 5;   // TILE_E == 32: a warp is one z-row of the extended tile
-    const bool rim = ry == 0 || ry == TILE_E - 1 || rz == 0 || rz == TILE_E - 1;
     const bool interior_row = ry >= TILE_K && ry < TILE_K + TILE_Y && rz >= TILE_K && rz < TILE_K + TILE_Y;
     // rows away from the interior (0 inside); a halo row j rows out can reach the interior by level TILE_K only
     // through levels <= TILE_K - j, so level s needs just the rows with j <= TILE_K - s

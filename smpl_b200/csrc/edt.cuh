@@ -58,7 +58,6 @@ __global__ void edt_pass_axis_kernel(const uint16_t* __restrict__ in, int nx, in
     if (idx >= total) {
         return;
     }
-    const int z = (int)(idx % nz);
     const int y = (int)((idx / nz) % ny);
     const int x = (int)(idx / ((size_t)nz * ny));
     const int p = axis == 1 ? y : x;
