@@ -53,3 +53,36 @@ def test_cuda_verdicts_equal_reference_build(name):
             assert int((e != g[name + "/edges_valid"]).sum()) <= budget
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("name", ["pr2_tabletop", "ubr1_tabletop"])
+def test_batch_planner_returns_the_reference_builds_plans(name):
+    """smplhost_plan_batch (many ARA* searches in lock step over smplgpu_expand_batch) against
+    tests/golden/plans_reference.json -- plans of the reference's own ManipLattice + BfsHeuristic + ARAStar +
+    CollisionSpace + KDLRobotModel (oracle/ref_planner_shim.cpp): PR2 tabletop (config 1) and UBR1 with a box attached
+    through attachObject and extra ACM entries (config 4 shape).  Same success flag, expansions, cost, lattice size
+    and state-id path, whatever the concurrency."""
+    import json
+    from conftest import ROOT
+    from test_oracle_planner_reference import plan_cases
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "plans_reference.json")))[name]
+    scene, attach, params, starts, goals = plan_cases()[name]
+    ctx = api.GpuContext(0)
+    try:
+        tables = api.build_tables(scene)
+        if attach is not None:
+            body_id, link, size, pose = attach
+            assert tables.attach_box(ctx, body_id, link, size, pose) > 0
+            for a, b, allowed in scene.acm_extra:
+                if body_id in (a, b):
+                    tables.set_acm_entry(a, b, allowed)
+        ctx.set_robot(tables)
+        ctx.build_distance_field(api.scene_cells(scene, tables), scene.dims, scene.origin, scene.res, scene.max_dist,
+                                 scene.padding)
+        for conc in (3, 64):
+            got, _ = api.plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=conc)
+            for g, want in zip(got, gold):
+                assert [int(g["success"]), g["expansions"], g["cost"], g["num_states"],
+                        [int(i) for i in g["path_ids"]]] == want
+    finally:
+        ctx.close()
