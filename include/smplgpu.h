@@ -332,7 +332,9 @@ int64_t smplgpu_expand_batch_resolved(const smplgpu_ctx* ctx);
 int smplgpu_expand_batch_reserve(smplgpu_ctx* ctx, int max_n);
 /* The same in two halves, so the host can prepare / absorb one batch while the device works on another:
  * submit copies the inputs and queues the work on the context's stream and returns at once; wait blocks until
- * that batch is done and copies the results out (returns n).  buffer = 0 or 1: two batches may be in flight. */
+ * that batch is done and copies the results out (returns n).  buffer = 0 .. SMPLGPU_EXPAND_BUFFERS - 1: that many
+ * batches may be in flight (they run in submission order on the context's stream). */
+#define SMPLGPU_EXPAND_BUFFERS 4
 int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double* q1, const int32_t* slot, int n,
                                 int cost_per_cell, int buffer);
 int smplgpu_expand_batch_wait(smplgpu_ctx* ctx, int buffer, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells,

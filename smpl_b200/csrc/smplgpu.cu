@@ -91,11 +91,12 @@ struct smplgpu_ctx
     void* pinned_out[2] = { nullptr, nullptr }; size_t pinned_out_cap = 0;
     cudaEvent_t ev[2] = { nullptr, nullptr };      // chunk b: kernels + result copies done
     // two expansion batches may be in flight (smplgpu_expand_batch_submit / _wait)
-    void* exp_in[2] = { nullptr, nullptr }; size_t exp_in_cap[2] = { 0, 0 };     // pinned
-    void* exp_out[2] = { nullptr, nullptr }; size_t exp_out_cap[2] = { 0, 0 };   // pinned
-    void* d_exp[2] = { nullptr, nullptr }; size_t d_exp_cap[2] = { 0, 0 };
-    cudaEvent_t ev_exp[2] = { nullptr, nullptr };
-    int exp_n[2] = { -1, -1 };
+    // expansion batches in flight (smplgpu_expand_batch_submit / _wait): SMPLGPU_EXPAND_BUFFERS of them
+    void* exp_in[SMPLGPU_EXPAND_BUFFERS] = { }; size_t exp_in_cap[SMPLGPU_EXPAND_BUFFERS] = { };     // pinned
+    void* exp_out[SMPLGPU_EXPAND_BUFFERS] = { }; size_t exp_out_cap[SMPLGPU_EXPAND_BUFFERS] = { };   // pinned
+    void* d_exp[SMPLGPU_EXPAND_BUFFERS] = { }; size_t d_exp_cap[SMPLGPU_EXPAND_BUFFERS] = { };
+    cudaEvent_t ev_exp[SMPLGPU_EXPAND_BUFFERS] = { };
+    int exp_n[SMPLGPU_EXPAND_BUFFERS] = { -1, -1, -1, -1 };
     int64_t exp_resolved_total = 0;   // edges of expansion batches resolved in double, since creation
     cudaEvent_t ev_in[2] = { nullptr, nullptr };   // chunk b: inputs on the device
     cudaStream_t copy_stream = nullptr;
@@ -232,6 +233,8 @@ smplgpu_ctx* smplgpu_create(int device)
     for (int i = 0; i < 2; ++i) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
         if ((e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
+    for (int i = 0; i < SMPLGPU_EXPAND_BUFFERS; ++i) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev_exp[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
     ctx->h_model = new DevModel;
@@ -299,6 +302,8 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
         if (ctx->pinned_out[i]) cudaFreeHost(ctx->pinned_out[i]);
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+    }
+    for (int i = 0; i < SMPLGPU_EXPAND_BUFFERS; ++i) {
         if (ctx->ev_exp[i]) cudaEventDestroy(ctx->ev_exp[i]);
         if (ctx->exp_in[i]) cudaFreeHost(ctx->exp_in[i]);
         if (ctx->exp_out[i]) cudaFreeHost(ctx->exp_out[i]);
@@ -2178,7 +2183,7 @@ int smplgpu_expand_batch_reserve(smplgpu_ctx* ctx, int max_n)
 {
     if (!ctx || max_n < 0) return SMPLGPU_ERR_INVALID;
     if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set");
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < SMPLGPU_EXPAND_BUFFERS; ++b) {
         if (ctx->exp_n[b] >= 0) return fail(ctx, SMPLGPU_ERR_STATE, "expansion buffer %d is in flight", b);
         int r = reserve_expand(ctx, b, std::max(max_n, 1));
         if (r) return r;
@@ -2191,7 +2196,7 @@ int64_t smplgpu_expand_batch_resolved(const smplgpu_ctx* ctx) { return ctx ? ctx
 int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double* q1, const int32_t* slot, int n,
                                 int cost_per_cell, int buffer)
 {
-    if (!ctx || n < 0 || buffer < 0 || buffer > 1) return SMPLGPU_ERR_INVALID;
+    if (!ctx || n < 0 || buffer < 0 || buffer >= SMPLGPU_EXPAND_BUFFERS) return SMPLGPU_ERR_INVALID;
     int r = need_scene(ctx);
     if (r) return r;
     if (!ctx->has_bank) return fail(ctx, SMPLGPU_ERR_STATE, "BFS bank not created");
@@ -2239,7 +2244,7 @@ int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double
 int smplgpu_expand_batch_wait(smplgpu_ctx* ctx, int buffer, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells,
                               double* offset_xyz)
 {
-    if (!ctx || buffer < 0 || buffer > 1) return SMPLGPU_ERR_INVALID;
+    if (!ctx || buffer < 0 || buffer >= SMPLGPU_EXPAND_BUFFERS) return SMPLGPU_ERR_INVALID;
     const int n = ctx->exp_n[buffer];
     if (n < 0) return fail(ctx, SMPLGPU_ERR_STATE, "expansion buffer %d has nothing in flight", buffer);
     ctx->exp_n[buffer] = -1;

@@ -646,8 +646,12 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
     // refill in groups so that one bank run (one wavefront launch sequence) serves several new queries
     const int refill_min = std::max(1, n_slots / 4);
 
-    // The active queries work in two groups (slot parity).  While the device expands one group's batch the
-    // host absorbs the other group's results and prepares its next batch, so host and device overlap.
+    // The active queries work in NG groups (slot modulo NG).  While the device expands one group's batch the
+    // host absorbs the other groups' results and prepares their next batches, so host and device overlap.  Two
+    // groups is the measured optimum (SMPLHOST_PLAN_GROUPS, 2 .. SMPLGPU_EXPAND_BUFFERS: 12 planner threads on one
+    // B200 reach 1651 queries/s with 2 groups, 1346 with 3, 1056 with 4): the host does wait for the device a fifth
+    // of the time, but more groups mean more and smaller batches, and the device side of a batch is a fixed-latency
+    // chain (copy in, three kernels, copy out) that twelve contexts already queue behind one another.
     struct Group
     {
         std::vector<int> active;            // occupied slots of this group with a search in progress
@@ -657,7 +661,18 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         bool in_flight = false;
         int ne = 0;
     };
-    Group G[2];
+    static const int NG = [] {
+        const char* e = getenv("SMPLHOST_PLAN_GROUPS");
+        const int v = e ? atoi(e) : 2;
+        return std::min(std::max(v, 2), (int)SMPLGPU_EXPAND_BUFFERS);
+    }();
+    std::vector<Group> G(NG);
+    auto all_idle = [&]() {
+        for (const Group& g : G) {
+            if (!g.active.empty()) return false;
+        }
+        return true;
+    };
     // SMPLHOST_PLAN_PROFILE=1: where the host time of this planner thread goes (printed to stderr at the end)
     static const bool profile = getenv("SMPLHOST_PLAN_PROFILE") != nullptr;
     double prof[6] = { 0, 0, 0, 0, 0, 0 };  // absorb, retire, expand, pack, submit, refill
@@ -778,7 +793,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
 
     auto activate = [&]() -> bool {
         // setStart uses the synchronous entry points: nothing of ours may be in flight
-        for (int gi = 0; gi < 2; ++gi) {
+        for (int gi = 0; gi < NG; ++gi) {
             if (!absorb(gi)) return false;
         }
         m_stats.host_seconds += t.lap();
@@ -807,7 +822,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         for (int k = 0; k < nn; ++k) {
             Query& Q = S[pending[k]];
             const double* qs = &sq[(size_t)k * dof];
-            G[pending[k] & 1].active.push_back(pending[k]);
+            G[pending[k] % NG].active.push_back(pending[k]);
             if (!checkJointLimits(qs) || !sv[k]) {
                 finish(Q, false);   // retired by the group's next absorb
                 continue;
@@ -826,7 +841,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
     };
 
     while (finished < nq) {
-        const bool idle = G[0].active.empty() && G[1].active.empty();
+        const bool idle = all_idle();
         // ---- (2) the pending queries' BFS is done (or there is nothing else to do): setStart, join the rounds ----
         if (!pending.empty() && (idle || smplgpu_bfs_bank_run_done(m_ctx) != 0)) {
             if (!activate()) return fail_dev();
@@ -864,13 +879,13 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
                 m_stats.device_seconds += dt;
                 m_stats.setup_seconds += dt;
             }
-            if (G[0].active.empty() && G[1].active.empty()) {
+            if (all_idle()) {
                 continue;   // nothing to expand meanwhile: go and wait for it
             }
         }
 
         // ---- one pipelined round: each group absorbs its previous batch and submits the next ----
-        for (int gi = 0; gi < 2; ++gi) {
+        for (int gi = 0; gi < NG; ++gi) {
             if (!absorb(gi)) return fail_dev();
             if (!expand(gi)) return fail_dev();
         }
@@ -888,7 +903,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
     m_stats.edges_resolved_f64 = smplgpu_expand_batch_resolved(m_ctx) - resolved0;
     // nothing can be in flight here: a group's queries finish in absorb or expand, and a batch is only
     // submitted for queries that are not done; drain defensively anyway
-    for (int gi = 0; gi < 2; ++gi) {
+    for (int gi = 0; gi < NG; ++gi) {
         if (G[gi].in_flight) {
             if (smplgpu_expand_batch_wait(m_ctx, gi, G[gi].verdict.data(), G[gi].h.data(), G[gi].gd.data(), G[gi].off.data()) < 0) return fail_dev();
         }
