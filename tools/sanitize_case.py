@@ -30,4 +30,10 @@ pctx, pt = api.setup_context(ps)
 pp = scenes.PlanParams(7); pp.max_expansions = 60
 st, g = scenes.tabletop_queries(6, seed=13)
 res, stats = api.plan_batch(pctx, ps, pt, pp, st, g, max_concurrent=4, n_threads=2)
+pctx.probe_df_lookup_rate()
+# scene ingest (voxeliser + EDT) and the indexed-edge batch of path shortcutting
+ictx, it = api.setup_context(scenes.pr2_shelf_objects_scene())
+paths = [q[:12].copy(), q[20:40].copy()]
+api.shortcut_paths(ictx, it, paths, kind=0)
+ictx.close()
 print("sanitize case ok:", int(v.sum()), int(e.sum()), [r["expansions"] for r in res])
