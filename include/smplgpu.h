@@ -340,6 +340,36 @@ int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double
 int smplgpu_expand_batch_wait(smplgpu_ctx* ctx, int buffer, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells,
                               double* offset_xyz);
 
+/* ---- one expansion at a time, for UNCHANGED callers (ManipLattice::GetSuccs + ARAStar::expand) ---- */
+/* The reference's search asks its plug-ins ~65 questions per expansion, one virtual call each
+ * (manip_lattice_action_space.cpp:385-396; manip_lattice.cpp:1520, 1549, 1582-1640; arastar.cpp:613-618).
+ * smplgpu_expand_state answers all of them for one parent state in ONE launch: for the parent (info[0]) and for
+ * every successor parent + deltas[k] (info[1 + k]) of the table given to smplgpu_set_motion_primitives.  The
+ * adapters of smpl_b200/host/gpu_adapters.cpp call it on a cache miss and serve the following virtual calls
+ * from the record. */
+#define SMPLGPU_MAX_DOF 16
+typedef struct smplgpu_succ_info {
+    double  state[SMPLGPU_MAX_DOF]; /* info[0]: the parent; info[1+k]: deltas[k][j] + parent[j] (one IEEE addition) */
+    double  pose[6];                /* computePlanningLinkFK + getTargetOffsetPose of `state`: x y z roll pitch yaw */
+    double  link_xyz[3];            /* position of the planning link itself (what getMetricGoalDistance is given) */
+    int32_t h;                      /* BfsHeuristic::GetGoalHeuristic(state); 0 when no BFS has been set up */
+    int32_t goal_dist_cells;        /* BFS_3D::getDistance at link_xyz's cell; SMPLGPU_BFS_OUT_OF_BOUNDS outside */
+    int32_t waypoints;              /* waypoint count of the edge parent -> state (0 for info[0]) */
+    uint8_t edge_valid;             /* isStateToStateValid(parent, state); info[0]: isStateValid(parent) */
+    uint8_t limits_ok;              /* KDLRobotModel::checkJointLimits(state) */
+    uint8_t state_valid;            /* info[0] only: isStateValid(parent) */
+    uint8_t is_parent;              /* 1 for info[0] */
+} smplgpu_succ_info;
+/* the motion-primitive table, deltas[n_prims][dof] (converses included, as ManipLatticeActionSpace::addMotionPrim
+ * stores them, manip_lattice_action_space.cpp:201-228); resident until replaced */
+int smplgpu_set_motion_primitives(smplgpu_ctx* ctx, const double* deltas, int n_prims);
+/* *info points at n_prims + 1 records in page-locked memory owned by the context, valid until the next call.
+ * Uses the single BFS grid of smplgpu_bfs_run (h = 0, goal_dist_cells = WALL when none is set). */
+int smplgpu_expand_state(smplgpu_ctx* ctx, const double* parent, int cost_per_cell, const smplgpu_succ_info** info);
+/* changes whenever an earlier answer may no longer hold (robot tables, distance field, BFS walls or run):
+ * host-side caches of smplgpu_expand_state records compare it */
+int64_t smplgpu_scene_epoch(const smplgpu_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

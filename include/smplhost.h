@@ -111,6 +111,13 @@ smplhost_adapters* smplhost_adapters_create(smplgpu_ctx* ctx, smplhost_tables* t
                                             const double origin[3], double res, const int32_t dims[3],
                                             double inflation_radius, int cost_per_cell);
 void smplhost_adapters_destroy(smplhost_adapters* a);
+/* smplhost::ExpansionCache behind the three adapters: given the action space's motion primitives
+ * (deltas[n_prims][dof], converses included), the first virtual call about a state the adapters hold no record
+ * for triggers ONE smplgpu_expand_state launch, and the ~65 calls the reference's GetSuccs + ARA* expand make about
+ * that state and its successors (manip_lattice.cpp:219-313, 1511-1580; arastar.cpp:613-618) are answered from its
+ * record.  n_prims = 0 switches back to one device call per virtual.  deltas = NULL only reads the counters
+ * (counters[2], nullable: launches, hits). */
+int smplhost_adapters_enable_expansion_cache(smplhost_adapters* a, const double* deltas, int n_prims, int64_t* counters);
 /* CollisionChecker::isStateValid / isStateToStateValid (collision_checker.h:62-88): 1 valid, 0 invalid */
 int smplhost_cc_is_state_valid(smplhost_adapters* a, const double* q);
 int smplhost_cc_is_state_to_state_valid(smplhost_adapters* a, const double* q0, const double* q1);

@@ -14,6 +14,7 @@
 // (manip_lattice.cpp:100-104), which the hot path never calls; DropInRobotModel adds one that always fails.
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -131,8 +132,11 @@ std::vector<std::string> SplitCsv(const char* s)
 
 extern "C" {
 
-/// batched_get_succs != 0 runs the reference's lattice with the INTEGRATION.md section-4 edit (BatchedManipLattice);
+/// batched_get_succs == 1 runs the reference's lattice with the INTEGRATION.md section-4 edit (BatchedManipLattice);
 /// out_summary[6], [7] then hold the number of batched calls and of edges submitted.
+/// batched_get_succs == 2 runs the UNCHANGED reference lattice (one virtual call per question) with the adapters
+/// sharing a smplhost::ExpansionCache built from the action space's primitive table: one speculative launch per
+/// expansion answers all of its questions; out_summary[6], [7] = cache launches, cache hits.
 /// ctx: a smplgpu context that already holds the robot tables, the distance field and the planning chain (set up
 /// through the ABI by the caller).  Arguments and summary as refcc_plan / oracle_plan.  Returns 0, or a negative
 /// step number when a step is refused.
@@ -170,8 +174,19 @@ int refdrop_plan(smplgpu_ctx* ctx, const char* robot_path, const char* group, co
     FillPrimitives(actions, mprims, short_flags, n_prims, dof);
 
     // batched_get_succs: the reference's lattice with the section-4 edit (BatchedManipLattice) instead of the plain one
+    // mode 2: the adapters answer from one smplgpu_expand_state record per expansion
+    std::vector<double> flat;
+    for (const auto& d : actions.deltas) flat.insert(flat.end(), d.begin(), d.end());
+    std::unique_ptr<smplhost::ExpansionCache> cache;
+    if (batched_get_succs == 2) {
+        cache.reset(new smplhost::ExpansionCache(ctx, dof, flat.data(), (int)actions.deltas.size(), cost_per_cell));
+        if (!cache->ok()) return -11;
+        robot.setExpansionCache(cache.get());
+        checker.setExpansionCache(cache.get());
+    }
+
     BatchedManipLattice space;
-    space.gpu = batched_get_succs ? &checker : nullptr;
+    space.gpu = batched_get_succs == 1 ? &checker : nullptr;
     const std::vector<double> res(resolutions, resolutions + dof);
     if (!space.init(&robot, &checker, &params, res, &actions)) return -3;
     if (!actions.init(&space)) return -4;
@@ -180,6 +195,7 @@ int refdrop_plan(smplgpu_ctx* ctx, const char* robot_path, const char* group, co
     smplhost::GpuBfsHeuristic heur(ctx, grid_origin, grid_res, dims);
     heur.setCostPerCell(cost_per_cell);
     heur.setInflationRadius(inflation_radius);
+    if (batched_get_succs == 2) heur.setExpansionCache(cache.get());
     if (!heur.RobotHeuristic::init(&space)) return -5;
     if (!heur.init([&space](int id, RobotState& q) {
             if (id < 0 || id >= (int)space.m_states.size() || !space.m_states[id]) return false;
@@ -224,8 +240,8 @@ int refdrop_plan(smplgpu_ctx* ctx, const char* robot_path, const char* group, co
     const int ret = search.replan(tp, &solution, &solcost);
     out_summary[1] = search.get_n_expands();
     out_summary[4] = (int)space.m_states.size();
-    out_summary[6] = (int)space.batched_calls;
-    out_summary[7] = (int)space.edges_submitted;
+    out_summary[6] = cache ? (int)cache->launches() : (int)space.batched_calls;
+    out_summary[7] = cache ? (int)cache->hits() : (int)space.edges_submitted;
     if (!ret || solcost >= INFINITECOST) {
         return 0;
     }

@@ -36,6 +36,13 @@ def _bp(a):
     return a.ctypes.data_as(c_uint8_p)
 
 
+class SuccInfoC(C.Structure):
+    """smplgpu_succ_info (include/smplgpu.h)."""
+    _fields_ = [("state", C.c_double * 16), ("pose", C.c_double * 6), ("link_xyz", C.c_double * 3), ("h", C.c_int32),
+                ("goal_dist_cells", C.c_int32), ("waypoints", C.c_int32), ("edge_valid", C.c_uint8),
+                ("limits_ok", C.c_uint8), ("state_valid", C.c_uint8), ("is_parent", C.c_uint8)]
+
+
 class PlanParamsC(C.Structure):
     """smplhost_plan_params (include/smplhost.h)."""
     _fields_ = [("dof", C.c_int), ("resolutions", c_double_p), ("mprims", c_double_p), ("short_flags", c_uint8_p),
@@ -107,6 +114,10 @@ def gpu_lib():
         L.smplgpu_bfs_bank_run_wait.argtypes = [vp]
         L.smplgpu_bfs_bank_distances.argtypes = [vp, ip, ip, i, ip]
         L.smplgpu_expand_batch.argtypes = [vp, dp, dp, ip, i, i, bp, ip, ip, dp]
+        L.smplgpu_set_motion_primitives.argtypes = [vp, dp, i]
+        L.smplgpu_expand_state.argtypes = [vp, dp, i, C.POINTER(C.POINTER(SuccInfoC))]
+        L.smplgpu_scene_epoch.restype = C.c_int64
+        L.smplgpu_scene_epoch.argtypes = [vp]
         _gpu = L
     return _gpu
 
@@ -566,6 +577,35 @@ class GpuContext:
         return v, h, g, off
 
 
+    def set_motion_primitives(self, deltas):
+        d = np.ascontiguousarray(deltas, dtype=np.float64)
+        self._n_prims = len(d)
+        self._ck(self.L.smplgpu_set_motion_primitives(self.h, _dp(d), len(d)), "set_motion_primitives")
+
+    def expand_state(self, parent, cost_per_cell):
+        """One launch: the records of `parent` (index 0) and of parent + every primitive, as a dict of arrays."""
+        q = np.ascontiguousarray(parent, dtype=np.float64)
+        info = C.POINTER(SuccInfoC)()
+        self._ck(self.L.smplgpu_expand_state(self.h, _dp(q), int(cost_per_cell), C.byref(info)), "expand_state")
+        n = self._n_prims + 1
+        dof = len(q)
+        return {
+            "state": np.array([list(info[k].state)[:dof] for k in range(n)]),
+            "pose": np.array([list(info[k].pose) for k in range(n)]),
+            "link_xyz": np.array([list(info[k].link_xyz) for k in range(n)]),
+            "h": np.array([info[k].h for k in range(n)], np.int32),
+            "goal_dist_cells": np.array([info[k].goal_dist_cells for k in range(n)], np.int32),
+            "waypoints": np.array([info[k].waypoints for k in range(n)], np.int32),
+            "edge_valid": np.array([info[k].edge_valid for k in range(n)], np.uint8),
+            "limits_ok": np.array([info[k].limits_ok for k in range(n)], np.uint8),
+            "state_valid": np.array([info[k].state_valid for k in range(n)], np.uint8),
+            "is_parent": np.array([info[k].is_parent for k in range(n)], np.uint8),
+        }
+
+    def scene_epoch(self):
+        return int(self.L.smplgpu_scene_epoch(self.h))
+
+
 class Adapters:
     """The C++ drop-in adapters (GpuCollisionSpace / GpuRobotModel / GpuBfsHeuristic) driven one virtual call
     at a time, as the reference's planner drives its plugins."""
@@ -589,6 +629,19 @@ class Adapters:
 
     def _v(self, q):
         return np.ascontiguousarray(q, dtype=np.float64)
+
+    def enable_expansion_cache(self, deltas):
+        """ExpansionCache: one smplgpu_expand_state launch per expanded state answers the per-call virtuals."""
+        d = np.ascontiguousarray(deltas, dtype=np.float64).reshape(-1, self.dof)
+        self.H.smplhost_adapters_enable_expansion_cache.argtypes = [C.c_void_p, c_double_p, C.c_int, C.POINTER(C.c_int64)]
+        if self.H.smplhost_adapters_enable_expansion_cache(self.h, _dp(d), len(d), None) != 0:
+            raise SmplGpuError("expansion cache: " + self.H.smplhost_last_error().decode())
+
+    def expansion_cache_counters(self):
+        c = (C.c_int64 * 2)()
+        self.H.smplhost_adapters_enable_expansion_cache.argtypes = [C.c_void_p, c_double_p, C.c_int, C.POINTER(C.c_int64)]
+        self.H.smplhost_adapters_enable_expansion_cache(self.h, None, 0, c)
+        return int(c[0]), int(c[1])
 
     def is_state_valid(self, q):
         return self.H.smplhost_cc_is_state_valid(self.h, _dp(self._v(q)))

@@ -42,7 +42,8 @@ struct BfsGrid
     uint32_t* cand0;          // [rows] neighbour-row mask (bits 0-8) | published words mod 16 (bits 9-24)
     uint32_t* cand1;
     int* dist;             // [DZ*DY*DX]
-    int* ctrl;             // [0] = levels run, [4..5] = 64-bit grid barrier word (arrivals | blocks with new cells << 32)
+    int* ctrl;             // [16]: [0] = levels run, [4..5] = 64-bit grid barrier word (arrivals), [8..11] = per-level
+                           // "a block found new cells" flags of bfs_levels_kernel (index level & 3)
 };
 
 
@@ -127,7 +128,7 @@ __global__ void bfs_reset_kernel(BfsGrid g, const uint8_t* __restrict__ slot_mas
         g.cand0[tid] = 0;
         g.cand1[tid] = 0;
     }
-    if (tid < 8) {
+    if (tid < 16) {
         g.ctrl[tid] = 0;
     }
     const int lane = threadIdx.x & 31;
@@ -211,25 +212,24 @@ constexpr int BFS_THREADS = 1024;      // one block per SM
 constexpr int BFS_ROWS_PER_THREAD = 2; // candidate words a thread fetches per batch (issued together)
 constexpr int BFS_ITEM_CAP = 5120;     // (row, word) work items a block holds at a time
 
-// Grid-wide barrier for a cooperative (co-resident) launch with one block per SM.  One 64-bit counter
-// carries the arrivals (low word) and the number of blocks that discovered cells at this level (high
-// word), so leaving the barrier also answers "did anything happen" without another round trip.
-__device__ __forceinline__ unsigned long long grid_barrier(unsigned long long* counter, unsigned int target, bool block_new)
+// Grid-wide barrier for a cooperative (co-resident) launch with one block per SM: one arrival counter that only
+// grows (target = barrier number * blocks).  Whether anything happened at a level is NOT carried in this word: a
+// block still spinning at barrier L may read the counter after faster blocks arrived at barrier L + 1, so anything
+// packed next to the arrivals would mix levels.  bfs_levels_kernel keeps per-level flags instead (news[level & 3]:
+// raised before the arrival at `level`, read after it, cleared two levels ahead by block 0).
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned int target)
 {
-    __shared__ unsigned long long s_seen;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(counter, 1ull | ((unsigned long long)(block_new ? 1u : 0u) << 32));
+        atomicAdd(counter, 1ull);
         unsigned long long v;
         do {
             v = *((volatile unsigned long long*)counter);
         } while ((unsigned int)v < target);
         __threadfence();
-        s_seen = v;
     }
     __syncthreads();
-    return s_seen;
 }
 
 // All levels in one cooperative launch, one block per SM.
@@ -264,7 +264,7 @@ bfs_levels_kernel(const __grid_constant__ BfsGrid g, int max_levels)
     const int slots = (groups + (int)gridDim.x - 1) / (int)gridDim.x * 8;   // row slots of this block
     const uint32_t wmask_all = g.W >= 16 ? 0xFFFFu : ((1u << g.W) - 1u);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(&g.ctrl[4]);
-    unsigned int news_before = 0;
+    int* news = &g.ctrl[8];   // [4] per-level flags, see grid_barrier
 
     uint32_t level = 1;
     for (; level <= (uint32_t)max_levels; ++level) {
@@ -413,12 +413,20 @@ bfs_levels_kernel(const __grid_constant__ BfsGrid g, int max_levels)
             }
         }
         const bool block_new = __syncthreads_or(any_new ? 1 : 0) != 0;
-        const unsigned long long seen = grid_barrier(bar, level * gridDim.x, block_new);
-        const unsigned int news = (unsigned int)(seen >> 32);
-        if (news == news_before) {
-            break;   // no block discovered anything at this level
+        if (threadIdx.x == 0) {
+            if (block_new) {
+                atomicExch(&news[level & 3], 1);
+            }
+            if (blockIdx.x == 0) {
+                // slot of level + 2: its last readers (level - 2) all arrived at barrier level - 1, which this block
+                // has left; its next writers (level + 2) start after barrier level + 1, which needs this block
+                atomicExch(&news[(level + 2) & 3], 0);
+            }
         }
-        news_before = news;
+        grid_barrier(bar, level * gridDim.x);
+        if (__ldcg(&news[level & 3]) == 0) {
+            break;   // no block discovered anything at this level (every block reads the same flag)
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         g.ctrl[0] = (int)level;

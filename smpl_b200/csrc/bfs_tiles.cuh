@@ -118,7 +118,10 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
     __shared__ uint8_t sAny[2][TILE_THREADS];        // which words of the row have frontier bits (per buffer)
     __shared__ uint8_t sZ[2][TILE_E];                // z-row (= warp) has frontier bits (per buffer)
     __shared__ unsigned int s_act;                   // which of the 27 neighbour directions get activated
-    __shared__ int s_next;                           // next queue position of this block
+    __shared__ int s_next[2];                        // next queue position of this block, double-buffered by tile
+                                                     // count: thread 0 writes slot k & 1 for tile k before that tile's
+                                                     // first barrier, everyone reads it after one; slot k & 1 is written
+                                                     // again for tile k + 2, i.e. after tile k + 1's barriers
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -157,11 +160,12 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
         {
             // the first tile by block id, the following ones pulled from a shared cursor as blocks become free
             // (tiles differ a lot in cost: a face across x keeps all 1024 rows busy, most others a few)
-            for (int a = blockIdx.x; a < q_len;) {
+            int k = 0;   // tiles this block has taken in this super-step
+            for (int a = blockIdx.x; a < q_len; ++k) {
                 const int tile = __ldcg(&t.queue[(size_t)qi * t.ntiles + a]);
                 if (tid == 0) {
                     t.flag[(size_t)qi * t.ntiles + tile] = 0;   // consumed
-                    s_next = (int)gridDim.x + atomicAdd(&t.qn[3 + qi], 1);   // next queue position, fetched while this tile runs
+                    s_next[k & 1] = (int)gridDim.x + atomicAdd(&t.qn[3 + qi], 1);   // next queue position, fetched while this tile runs
                 }
 #ifdef SMPLGPU_BFS_STATS
                 const long long c0 = clock64();
@@ -198,8 +202,11 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                 if (tid == 0) {
                     s_act = 0;
                 }
-                if (!__syncthreads_or(any ? 1 : 0)) {
-                    a = s_next;   // (block-uniform) the barrier above also protects the shared buffers
+                const int idle = !__syncthreads_or(any ? 1 : 0);
+                a = s_next[k & 1];   // (block-uniform) written before the barrier above
+                if (idle) {
+                    // nothing else was written to shared memory that the next tile's loads could overtake: sF / sAny /
+                    // sZ are rewritten by the thread that wrote them, s_act by thread 0 alone
                     continue;
                 }
 #ifdef SMPLGPU_BFS_STATS
@@ -358,7 +365,6 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                     }
                 }
                 __syncthreads();   // shared buffers are reused by the next tile
-                a = s_next;
 #ifdef SMPLGPU_BFS_STATS
                 if (tid == 0) {
                     const long long c3 = clock64();
@@ -372,7 +378,7 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
 #ifdef SMPLGPU_BFS_STATS
         const long long b0 = clock64();
 #endif
-        grid_barrier(bar, (unsigned int)(n + 1) * gridDim.x, false);
+        grid_barrier(bar, (unsigned int)(n + 1) * gridDim.x);
 #ifdef SMPLGPU_BFS_STATS
         if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(t.qn + 14), (unsigned long long)(clock64() - b0));
 #endif

@@ -22,6 +22,7 @@
 #include "model.cuh"
 #include "validity.cuh"
 #include "validity32.cuh"
+#include "expand1.cuh"
 
 using namespace smplgpu;
 
@@ -110,6 +111,14 @@ struct smplgpu_ctx
     std::vector<int32_t> staged_slots, staged_seeds;
     unsigned long long* d_stats = nullptr;
     unsigned long long h_stats[4] = { 0, 0, 0, 0 };
+    // bumped whenever an answer of the validity / heuristic entry points may change (robot, field, walls, BFS run):
+    // host-side caches of such answers (smplhost::ExpansionCache) compare it
+    int64_t scene_epoch = 0;
+    // smplgpu_expand_state: primitive table, page-locked record array + completion flag, arrival counter
+    double* d_x1_deltas = nullptr; int x1_prims = -1;
+    smplgpu_succ_info* x1_out = nullptr; size_t x1_out_cap = 0;   // records; the flag word follows them
+    unsigned int* d_x1_done = nullptr;
+    unsigned long long x1_seq = 0;
 };
 
 static int fail(smplgpu_ctx* ctx, int code, const char* fmt, ...)
@@ -313,6 +322,8 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
     if (ctx->bfs_stream) cudaStreamDestroy(ctx->bfs_stream);
     if (ctx->ev_bfs) cudaEventDestroy(ctx->ev_bfs);
     cudaFree(ctx->d_bank_stage); cudaFree(ctx->d_bank_seed_count);
+    cudaFree(ctx->d_x1_deltas); cudaFree(ctx->d_x1_done);
+    if (ctx->x1_out) cudaFreeHost(ctx->x1_out);
     if (ctx->h_bank_stage) cudaFreeHost(ctx->h_bank_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx->h_model;
@@ -348,6 +359,8 @@ int smplgpu_synchronize(smplgpu_ctx* ctx)
 }
 
 int64_t smplgpu_launch_count(const smplgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t smplgpu_scene_epoch(const smplgpu_ctx* ctx) { return ctx ? ctx->scene_epoch : -1; }
 
 ///////////////////////////////////////////////////////////////////////////////
 // robot
@@ -826,8 +839,13 @@ int smplgpu_set_robot(smplgpu_ctx* ctx, const smplgpu_robot_desc* d)
         CU(cudaFuncSetAttribute(states_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
         CU(cudaFuncSetAttribute(edges_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
         CU(cudaFuncSetAttribute(fk_centers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
+        const size_t smem_x1 = (size_t)slots * 12 * sizeof(double) * EXPAND1_THREADS;
+        if (smem_x1 <= smem_max - 1024) {
+            CU(cudaFuncSetAttribute(expand_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem_x1, (size_t)1024)));
+        }
     }
     ctx->has_robot = true;
+    ++ctx->scene_epoch;
     return upload_model(ctx);
 }
 
@@ -839,6 +857,17 @@ static int set_df_common(smplgpu_ctx* ctx, int nx, int ny, int nz, const double 
 {
     if (nx <= 0 || ny <= 0 || nz <= 0 || !(res > 0.0) || dmax_sq < 0 || dmax_sq > 65534)
         return fail(ctx, SMPLGPU_ERR_INVALID, "bad distance field parameters");
+    // a bank run queued behind the caller's back still reads the field; a bank (and the walls derived from the
+    // field) of another shape would be indexed with the wrong strides
+    {
+        const int fr = finish_bank_run(ctx);
+        if (fr) return fr;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->has_df && (ctx->grid.nx != nx || ctx->grid.ny != ny || ctx->grid.nz != nz)) {
+        ctx->has_bank = false;   // re-create with smplgpu_bfs_bank_create
+    }
+    ++ctx->scene_epoch;
     const size_t cells = (size_t)nx * ny * nz;
     if (cells != ctx->df_cells) {
         if (ctx->d_df) { CU(cudaFree(ctx->d_df)); ctx->d_df = nullptr; }
@@ -1599,7 +1628,7 @@ static int alloc_grid(smplgpu_ctx* ctx, BfsGrid& g, int nx, int ny, int nz, size
     CU(cudaMalloc(&g.cand0, (size_t)g.rows * sizeof(uint32_t)));
     CU(cudaMalloc(&g.cand1, (size_t)g.rows * sizeof(uint32_t)));
     CU(cudaMalloc(&g.dist, *cells * sizeof(int)));
-    CU(cudaMalloc(&g.ctrl, 8 * sizeof(int)));
+    CU(cudaMalloc(&g.ctrl, 16 * sizeof(int)));
     return 0;
 }
 
@@ -1711,6 +1740,7 @@ int smplgpu_bfs_set_walls_dev(smplgpu_ctx* ctx, int nx, int ny, int nz, const ui
     if (!ctx || !walls_dev) return SMPLGPU_ERR_INVALID;
     int r = alloc_bfs(ctx, nx, ny, nz);
     if (r) return r;
+    ++ctx->scene_epoch;
     const int total = (int)ctx->bfs_words;
     bfs_walls_from_bytes_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->bfs, walls_dev);
     ++ctx->launches;
@@ -1737,6 +1767,7 @@ int smplgpu_bfs_set_walls_from_df(smplgpu_ctx* ctx, double inflation_radius)
     if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "distance field not set");
     int r = alloc_bfs(ctx, ctx->grid.nx, ctx->grid.ny, ctx->grid.nz);
     if (r) return r;
+    ++ctx->scene_epoch;
     const int kmax = wall_threshold(ctx, inflation_radius);
     unsigned int* d_count = (unsigned int*)ctx->d_seed_count;
     CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), ctx->stream));
@@ -1770,6 +1801,7 @@ int smplgpu_bfs_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz, int n_seeds)
         CU(cudaMemcpyAsync(ctx->d_misc, inb.data(), inb.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
     ctx->bfs_levels = 0;
+    ++ctx->scene_epoch;
     int r = run_grid(ctx, g, ctx->bfs_words, (const int*)ctx->d_misc, n_in, &ctx->bfs_levels);
     if (r) return r;
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1837,6 +1869,9 @@ int smplgpu_goal_heuristics_dev(smplgpu_ctx* ctx, const double* q_dev, int n, in
     if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set");
     if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "distance field (grid geometry) not set");
     if (!ctx->has_bfs) return fail(ctx, SMPLGPU_ERR_STATE, "BFS walls not set");
+    if (ctx->bfs.nx != ctx->grid.nx || ctx->bfs.ny != ctx->grid.ny || ctx->bfs.nz != ctx->grid.nz)
+        return fail(ctx, SMPLGPU_ERR_STATE, "BFS grid (%dx%dx%d) does not match the distance field (%dx%dx%d): set the walls again",
+                    ctx->bfs.nx, ctx->bfs.ny, ctx->bfs.nz, ctx->grid.nx, ctx->grid.ny, ctx->grid.nz);
     if (n == 0) return 0;
     if (!q_dev || !h_dev) return fail(ctx, SMPLGPU_ERR_INVALID, "null device pointer");
     goal_heuristic_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(
@@ -2202,8 +2237,13 @@ int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double
     if (!ctx->has_bank) return fail(ctx, SMPLGPU_ERR_STATE, "BFS bank not created");
     if (ctx->exp_n[buffer] >= 0) return fail(ctx, SMPLGPU_ERR_STATE, "expansion buffer %d is still in flight", buffer);
     if (n > 0 && (!q0 || !q1 || !slot)) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
-    ctx->exp_n[buffer] = n;
-    if (n == 0) return 0;
+    for (int i = 0; i < n; ++i) {
+        if (slot[i] < 0 || slot[i] >= ctx->bank_slots) return fail(ctx, SMPLGPU_ERR_INVALID, "edge %d: slot %d out of range", i, slot[i]);
+    }
+    if (n == 0) {
+        ctx->exp_n[buffer] = 0;
+        return 0;
+    }
     const int b = buffer;
     const int dof = ctx->h_model->dof;
     const size_t row = (size_t)dof * sizeof(double);
@@ -2238,6 +2278,7 @@ int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double
     CU(cudaMemcpyAsync((uint8_t*)ctx->exp_out[b] + (out_bytes + 15) / 16 * 16, ctx->d_stats + 3, sizeof(unsigned long long),
                        cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ctx->ev_exp[b], ctx->stream));
+    ctx->exp_n[buffer] = n;   // in flight only once everything is queued: an error above leaves the buffer free
     return 0;
 }
 
@@ -2273,6 +2314,73 @@ int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, c
     if (r < 0) return r;
     r = smplgpu_expand_batch_wait(ctx, 0, verdict, h, goal_dist_cells, offset_xyz);
     return r < 0 ? r : 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// one expansion at a time (unchanged callers)
+///////////////////////////////////////////////////////////////////////////////
+
+int smplgpu_set_motion_primitives(smplgpu_ctx* ctx, const double* deltas, int n_prims)
+{
+    if (!ctx || n_prims < 0 || (n_prims > 0 && !deltas)) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set (smplgpu_set_robot)");
+    if (n_prims > 4096) return fail(ctx, SMPLGPU_ERR_LIMIT, "%d motion primitives", n_prims);
+    const int dof = ctx->h_model->dof;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_x1_deltas) { CU(cudaFree(ctx->d_x1_deltas)); ctx->d_x1_deltas = nullptr; }
+    ctx->x1_prims = -1;
+    CU(cudaMalloc(&ctx->d_x1_deltas, std::max<size_t>(1, (size_t)n_prims * dof) * sizeof(double)));
+    if (n_prims > 0) {
+        CU(cudaMemcpy(ctx->d_x1_deltas, deltas, (size_t)n_prims * dof * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if ((size_t)n_prims + 1 > ctx->x1_out_cap) {
+        if (ctx->x1_out) { CU(cudaFreeHost(ctx->x1_out)); ctx->x1_out = nullptr; ctx->x1_out_cap = 0; }
+        CU(cudaHostAlloc((void**)&ctx->x1_out, ((size_t)n_prims + 1) * sizeof(smplgpu_succ_info) + 64, cudaHostAllocMapped));
+        ctx->x1_out_cap = (size_t)n_prims + 1;
+    }
+    if (!ctx->d_x1_done) {
+        CU(cudaMalloc(&ctx->d_x1_done, sizeof(unsigned int)));
+        CU(cudaMemset(ctx->d_x1_done, 0, sizeof(unsigned int)));
+    }
+    ctx->x1_prims = n_prims;
+    ++ctx->scene_epoch;
+    return 0;
+}
+
+int smplgpu_expand_state(smplgpu_ctx* ctx, const double* parent, int cost_per_cell, const smplgpu_succ_info** info)
+{
+    if (!ctx || !parent || !info) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (ctx->x1_prims < 0) return fail(ctx, SMPLGPU_ERR_STATE, "motion primitives not set (smplgpu_set_motion_primitives)");
+    const bool bfs_ok = ctx->has_bfs && ctx->bfs.nx == ctx->grid.nx && ctx->bfs.ny == ctx->grid.ny && ctx->bfs.nz == ctx->grid.nz;
+    Expand1Parent p;
+    const int dof = ctx->h_model->dof;
+    for (int v = 0; v < MAX_DOF; ++v) p.q[v] = v < dof ? parent[v] : 0.0;
+    unsigned long long* flag = reinterpret_cast<unsigned long long*>(ctx->x1_out + ctx->x1_out_cap);
+    volatile unsigned long long* vflag = flag;
+    const unsigned long long seq = ++ctx->x1_seq;
+    const size_t smem = (size_t)ctx->h_model->n_slots * 12 * sizeof(double) * EXPAND1_THREADS;
+    if (smem > (size_t)226 * 1024) return fail(ctx, SMPLGPU_ERR_LIMIT, "%d link slots do not fit the expansion kernel", ctx->h_model->n_slots);
+    expand_state_kernel<<<ctx->x1_prims + 1, EXPAND1_THREADS, smem, ctx->stream>>>(
+        ctx->d_model, ctx->d_df, ctx->grid, bfs_ok ? ctx->bfs.dist : nullptr, ctx->bfs.DX, ctx->bfs.DY, ctx->bfs.DZ, p,
+        ctx->d_x1_deltas, cost_per_cell, ctx->x1_out, ctx->d_x1_done, flag, seq);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    // the kernel's last block publishes `seq` behind the records; spinning on it costs less than a stream
+    // synchronisation, which stays the fallback (and the way errors surface)
+    for (int spin = 0; spin < (1 << 22) && *vflag != seq; ++spin) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (*vflag != seq) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (*vflag != seq) return fail(ctx, SMPLGPU_ERR_CUDA, "expansion record was not published");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    *info = ctx->x1_out;
+    return 0;
 }
 
 } // extern "C"

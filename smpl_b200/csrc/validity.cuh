@@ -527,14 +527,9 @@ fk_centers_kernel(const DevModel* __restrict__ M, const double* __restrict__ q, 
     }
 }
 
-// KDLRobotModel::checkJointLimits (kdl_robot_model.cpp:173-189, 210-235, 326-337)
-__global__ void joint_limits_kernel(const DevModel* __restrict__ M, const double* __restrict__ q, int n,
-                                    uint8_t* __restrict__ ok)
+// KDLRobotModel::checkJointLimits (kdl_robot_model.cpp:173-189, 210-235, 326-337) for one state
+__device__ __forceinline__ bool joint_limits_ok(const DevModel* __restrict__ M, const double* q)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) {
-        return;
-    }
     const double PI = 3.14159265358979323846;
     const int dof = M->dof;
     bool good = true;
@@ -544,7 +539,7 @@ __global__ void joint_limits_kernel(const DevModel* __restrict__ M, const double
         }
     }
     for (int v = 0; v < dof && good; ++v) {
-        double a = q[(size_t)i * dof + v];
+        double a = q[v];
         const double a_min = M->var_min[v];
         const double a_max = M->var_min_norm[v]; // the reference passes normalize_angle(min) as a_max (:227-228)
         if (fabs(a) > 2.0 * PI) {
@@ -560,7 +555,17 @@ __global__ void joint_limits_kernel(const DevModel* __restrict__ M, const double
             good = false;
         }
     }
-    ok[i] = good ? 1 : 0;
+    return good;
+}
+
+__global__ void joint_limits_kernel(const DevModel* __restrict__ M, const double* __restrict__ q, int n,
+                                    uint8_t* __restrict__ ok)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    ok[i] = joint_limits_ok(M, q + (size_t)i * M->dof) ? 1 : 0;
 }
 
 } // namespace smplgpu

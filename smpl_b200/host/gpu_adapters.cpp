@@ -3,8 +3,10 @@
 // lives here: verdicts, heuristics and FK come from the device.
 #include "gpu_adapters.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 
 namespace smplhost {
@@ -12,6 +14,135 @@ namespace smplhost {
 using sbpl::motion::Extension;
 using sbpl::motion::GetClassCode;
 using sbpl::motion::RobotState;
+
+///////////////////////////////////////////////////////////////////////////////
+// ExpansionCache
+///////////////////////////////////////////////////////////////////////////////
+
+ExpansionCache::ExpansionCache(smplgpu_ctx* ctx, int dof, const double* deltas, int n_prims, int cost_per_cell) :
+    m_ctx(ctx), m_dof(dof), m_prims(n_prims), m_cost_per_cell(cost_per_cell),
+    m_deltas(deltas, deltas + (size_t)std::max(0, n_prims) * (size_t)std::max(0, dof))
+{
+    m_ok = ctx != nullptr && dof > 0 && dof <= SMPLGPU_MAX_DOF && n_prims >= 0 &&
+           smplgpu_set_motion_primitives(ctx, m_deltas.data(), n_prims) == 0;
+}
+
+bool ExpansionCache::valid()
+{
+    if (!m_ok) {
+        return false;
+    }
+    if (m_n > 0 && smplgpu_scene_epoch(m_ctx) != m_epoch) {
+        m_n = 0;   // the scene, the walls or the goal changed: earlier answers may no longer hold
+    }
+    return true;
+}
+
+bool ExpansionCache::expand(const double* q)
+{
+    m_n = 0;
+    const smplgpu_succ_info* info = nullptr;
+    if (smplgpu_expand_state(m_ctx, q, m_cost_per_cell, &info) != 0 || info == nullptr) {
+        return false;
+    }
+    ++m_launches;
+    m_info = info;
+    m_n = m_prims + 1;
+    m_hint = 0;
+    m_epoch = smplgpu_scene_epoch(m_ctx);
+    return true;
+}
+
+const smplgpu_succ_info* ExpansionCache::find(const double* q)
+{
+    if (!valid() || m_n == 0) {
+        return nullptr;
+    }
+    const size_t bytes = (size_t)m_dof * sizeof(double);
+    // the caller walks the successors in table order: try where the last hit was first, then onwards
+    for (int k = 0; k < m_n; ++k) {
+        const int i = (m_hint + k) % m_n;
+        if (std::memcmp(m_info[i].state, q, bytes) == 0) {
+            m_hint = i;
+            ++m_hits;
+            return &m_info[i];
+        }
+    }
+    return nullptr;
+}
+
+const smplgpu_succ_info* ExpansionCache::get(const double* q)
+{
+    if (const smplgpu_succ_info* r = find(q)) {
+        return r;
+    }
+    if (!m_ok || !expand(q)) {
+        return nullptr;
+    }
+    return &m_info[0];
+}
+
+const smplgpu_succ_info* ExpansionCache::parent(const double* q)
+{
+    if (!valid()) {
+        return nullptr;
+    }
+    if (m_n > 0 && std::memcmp(m_info[0].state, q, (size_t)m_dof * sizeof(double)) == 0) {
+        ++m_hits;
+        return &m_info[0];
+    }
+    return expand(q) ? &m_info[0] : nullptr;
+}
+
+const smplgpu_succ_info* ExpansionCache::edge(const double* a, const double* b)
+{
+    if (!valid()) {
+        return nullptr;
+    }
+    const size_t bytes = (size_t)m_dof * sizeof(double);
+    if (m_n == 0 || std::memcmp(m_info[0].state, a, bytes) != 0) {
+        // a is not the current parent: expanding it pays off only if b is one of its successors, i.e.
+        // b == a + delta for some primitive (the addition the device will do)
+        bool is_succ = false;
+        for (int p = 0; p < m_prims && !is_succ; ++p) {
+            const double* d = &m_deltas[(size_t)p * m_dof];
+            bool same = true;
+            for (int j = 0; j < m_dof && same; ++j) {
+                const double s = d[j] + a[j];
+                same = std::memcmp(&s, &b[j], sizeof(double)) == 0;
+            }
+            is_succ = same;
+        }
+        if (!is_succ || !expand(a)) {
+            return nullptr;
+        }
+    }
+    for (int k = 0; k < m_prims; ++k) {
+        const int i = 1 + (std::max(0, m_hint - 1) + k) % m_prims;
+        if (std::memcmp(m_info[i].state, b, bytes) == 0) {
+            m_hint = i;
+            ++m_hits;
+            return &m_info[i];
+        }
+    }
+    return nullptr;
+}
+
+const smplgpu_succ_info* ExpansionCache::findLink(double x, double y, double z)
+{
+    if (!valid() || m_n == 0) {
+        return nullptr;
+    }
+    const double p[3] = { x, y, z };
+    for (int k = 0; k < m_n; ++k) {
+        const int i = (m_hint + k) % m_n;
+        if (std::memcmp(m_info[i].link_xyz, p, sizeof(p)) == 0) {
+            ++m_hits;
+            return &m_info[i];
+        }
+    }
+    return nullptr;
+}
 
 ///////////////////////////////////////////////////////////////////////////////
 // GpuCollisionSpace
@@ -22,6 +153,11 @@ bool GpuCollisionSpace::isStateValid(const RobotState& state, bool)
 {
     if ((int)state.size() != m_dof) {
         return false;
+    }
+    if (m_cache) {
+        if (const smplgpu_succ_info* r = m_cache->parent(state.data())) {
+            return r->state_valid != 0;
+        }
     }
     uint8_t v = 0;
     if (smplgpu_is_states_valid(m_ctx, state.data(), 1, &v) != 0) {
@@ -43,6 +179,11 @@ bool GpuCollisionSpace::isStateToStateValid(const RobotState& start, const Robot
 {
     if ((int)start.size() != m_dof || (int)finish.size() != m_dof) {
         return false;
+    }
+    if (m_cache) {
+        if (const smplgpu_succ_info* r = m_cache->edge(start.data(), finish.data())) {
+            return r->edge_valid != 0;
+        }
     }
     uint8_t v = 0;
     if (smplgpu_is_edges_valid(m_ctx, start.data(), finish.data(), 1, &v, nullptr) != 0) {
@@ -75,8 +216,10 @@ static double normalizeAngle(double angle)
 
 // CollisionSpace::interpolatePath (collision_space.cpp:583-612): the waypoints isStateToStateValid checks
 // (robot_motion_collision_model.h:173-181, 224-249, 297-321; .cpp:371-407).  Post-processing only, so it
-// stays on the host.  The reference's limit test is inverted (it rejects motions WITHIN the limits,
-// SURVEY.md section 8a defect 7); the intended test is applied here.
+// stays on the host.  The reference's limit test is inverted (it rejects every motion whose end points are
+// WITHIN the limits, collision_space.cpp:591-596, SURVEY.md section 8a defect 7, so its InterpolatePath fails on
+// every legal path); NO limit test is made here -- a deliberate deviation, recorded in DESIGN.md -- callers that
+// need one ask GpuRobotModel::checkJointLimits.
 bool GpuCollisionSpace::interpolatePath(const RobotState& start, const RobotState& finish,
                                         std::vector<RobotState>& path)
 {
@@ -177,6 +320,11 @@ bool GpuRobotModel::checkJointLimits(const RobotState& state, bool)
     if (state.size() != m_min.size()) {
         return false;
     }
+    if (m_cache) {
+        if (const smplgpu_succ_info* r = m_cache->get(state.data())) {
+            return r->limits_ok != 0;
+        }
+    }
     uint8_t ok = 0;
     if (smplgpu_check_joint_limits(m_ctx, state.data(), 1, &ok) != 0) {
         return false;
@@ -200,6 +348,12 @@ bool GpuRobotModel::computePlanningLinkFK(const RobotState& state, std::vector<d
         return false;
     }
     pose.resize(6);
+    if (m_cache) {
+        if (const smplgpu_succ_info* r = m_cache->get(state.data())) {
+            std::copy(r->pose, r->pose + 6, pose.begin());
+            return true;
+        }
+    }
     return smplgpu_planning_frame_fk(m_ctx, state.data(), 1, pose.data()) == 0;
 }
 
@@ -271,8 +425,9 @@ int GpuBfsHeuristic::cellCost(const int cell[3])
     return d;
 }
 
-// bfs_heuristic.cpp:103-125 needs the start state's projection, which only the planning space knows; the
-// hot path never calls it (ARA* uses the goal heuristic)
+// bfs_heuristic.cpp:103-125 needs the start state's projection, which only the planning space knows.
+// ManipLatticeActionSpace::apply does call it on every expansion (manip_lattice_action_space.cpp:396), but this
+// fork never uses the result (its only reader, the near_start test, is commented out), so 0 changes nothing.
 double GpuBfsHeuristic::getMetricStartDistance(double, double, double)
 {
     return 0.0;
@@ -281,9 +436,15 @@ double GpuBfsHeuristic::getMetricStartDistance(double, double, double)
 // bfs_heuristic.cpp:127-138
 double GpuBfsHeuristic::getMetricGoalDistance(double x, double y, double z)
 {
-    int cell[3];
-    worldToGrid(x, y, z, cell);
-    const int d = cellCost(cell);
+    int d;
+    const smplgpu_succ_info* r = m_cache ? m_cache->findLink(x, y, z) : nullptr;
+    if (r != nullptr) {
+        d = r->goal_dist_cells;   // the BFS value at the cell of the planning link of a state in the record
+    } else {
+        int cell[3];
+        worldToGrid(x, y, z, cell);
+        d = cellCost(cell);
+    }
     if (d == -2) {
         return (double)0x7FFFFFFF * m_res;
     }
@@ -305,6 +466,11 @@ int GpuBfsHeuristic::GetGoalHeuristic(int state_id)
     RobotState q;
     if (!m_lookup || !m_lookup(state_id, q)) {
         return 0;
+    }
+    if (m_cache && (int)q.size() <= SMPLGPU_MAX_DOF) {
+        if (const smplgpu_succ_info* r = m_cache->get(q.data())) {
+            return r->h;
+        }
     }
     int32_t h = 0;
     if (smplgpu_goal_heuristics(m_ctx, q.data(), 1, m_cost_per_cell, &h) != 0) {

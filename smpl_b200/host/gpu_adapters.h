@@ -30,6 +30,52 @@
 
 namespace smplhost {
 
+/// Answers of the device for ONE expansion of the reference's search, shared by the three adapters.
+///
+/// An unchanged caller (ManipLattice::GetSuccs + ARAStar::expand, manip_lattice.cpp:219-313, arastar.cpp:531-568)
+/// asks its plug-ins ~65 questions per expansion, one virtual call each: FK + metric goal distance of the parent,
+/// joint limits + edge validity per action, FK per valid successor (isGoal), goal heuristic per new state.  One
+/// launch and one PCIe round trip each would make the device SLOWER than the reference's CPU.  The adapters are
+/// given the motion-primitive table instead (the same table the action space was built from) and, on the first
+/// question about a state they hold no record for, have smplgpu_expand_state answer everything about that state
+/// and its successors in one launch; the following calls are served from the record.  Same answers, callers
+/// untouched; one launch per expansion.  The record is dropped whenever smplgpu_scene_epoch changes (robot, field,
+/// walls, BFS run).
+class ExpansionCache
+{
+public:
+    /// deltas[n_prims][dof]: every primitive the action space may apply (converses included)
+    ExpansionCache(smplgpu_ctx* ctx, int dof, const double* deltas, int n_prims, int cost_per_cell);
+    bool ok() const { return m_ok; }
+    void setCostPerCell(int c) { if (c != m_cost_per_cell) { m_cost_per_cell = c; m_n = 0; } }
+
+    /// record of `q` if it is the current parent or one of its successors, else nullptr
+    const smplgpu_succ_info* find(const double* q);
+    /// find(q), or expand q as a new parent and return its own record (nullptr on a device error)
+    const smplgpu_succ_info* get(const double* q);
+    /// record of q AS A PARENT (the only record that carries isStateValid(q)), expanding q if need be
+    const smplgpu_succ_info* parent(const double* q);
+    /// record of the edge a -> b when b is a + a primitive (expanding a if need be), else nullptr
+    const smplgpu_succ_info* edge(const double* a, const double* b);
+    /// record whose planning-link position is exactly (x, y, z), else nullptr
+    const smplgpu_succ_info* findLink(double x, double y, double z);
+
+    long long launches() const { return m_launches; }
+    long long hits() const { return m_hits; }
+
+private:
+    smplgpu_ctx* m_ctx;
+    int m_dof, m_prims, m_cost_per_cell;
+    bool m_ok = false;
+    std::vector<double> m_deltas;
+    const smplgpu_succ_info* m_info = nullptr;   // [m_n] records of the current parent, owned by the context
+    int m_n = 0, m_hint = 0;
+    int64_t m_epoch = -1;
+    long long m_launches = 0, m_hits = 0;
+    bool valid();
+    bool expand(const double* q);
+};
+
 class GpuCollisionSpace : public sbpl::motion::CollisionChecker
 {
 public:
@@ -51,6 +97,9 @@ public:
     bool isEdgesValid(const std::vector<sbpl::motion::RobotState>& starts,
                       const std::vector<sbpl::motion::RobotState>& finishes, std::vector<uint8_t>& valid);
 
+    /// answer the per-call virtuals from one speculative launch per expansion (see ExpansionCache); not owned
+    void setExpansionCache(ExpansionCache* cache) { m_cache = cache; }
+
     /// joint kinds of the planning variables, needed by interpolatePath (continuous => shortest arc)
     void setVariableInfo(const std::vector<int>& continuous, const std::vector<double>& motion_weights,
                          const std::vector<int>& var_types)
@@ -62,6 +111,7 @@ private:
     std::vector<int> m_continuous, m_types;
     std::vector<double> m_weights;
     std::vector<double> m_buf0, m_buf1;
+    ExpansionCache* m_cache = nullptr;
 };
 
 class GpuRobotModel : public sbpl::motion::ForwardKinematicsInterface
@@ -79,8 +129,10 @@ public:
     bool computeFK(const sbpl::motion::RobotState& state, const std::string& name, std::vector<double>& pose) override;
     bool computePlanningLinkFK(const sbpl::motion::RobotState& state, std::vector<double>& pose) override;
     sbpl::motion::Extension* getExtension(size_t class_code) override;
+    void setExpansionCache(ExpansionCache* cache) { m_cache = cache; }
 private:
     smplgpu_ctx* m_ctx;
+    ExpansionCache* m_cache = nullptr;
     std::string m_planning_link;
     std::vector<double> m_min, m_max;
     std::vector<int> m_cont;
@@ -96,7 +148,8 @@ public:
     GpuBfsHeuristic(smplgpu_ctx* ctx, const double origin[3], double res, const int dims[3]);
     bool init(StateLookup lookup, int goal_state_id);   // BfsHeuristic::init -> syncGridAndBfs
     void setInflationRadius(double r) { m_inflation_radius = r; }
-    void setCostPerCell(int c) { m_cost_per_cell = c; }
+    void setCostPerCell(int c) { m_cost_per_cell = c; if (m_cache) m_cache->setCostPerCell(c); }
+    void setExpansionCache(ExpansionCache* cache) { m_cache = cache; if (cache) cache->setCostPerCell(m_cost_per_cell); }
 
     double getMetricStartDistance(double x, double y, double z) override;
     double getMetricGoalDistance(double x, double y, double z) override;
@@ -118,6 +171,7 @@ private:
     int m_cost_per_cell = 1;
     int m_walls = 0;
     StateLookup m_lookup;
+    ExpansionCache* m_cache = nullptr;
     int m_goal_state_id = -1;
     double m_goal_xyz[3] = { 0, 0, 0 };
     void worldToGrid(double x, double y, double z, int cell[3]) const;

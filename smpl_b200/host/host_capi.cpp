@@ -395,6 +395,9 @@ struct smplhost_adapters
     std::unique_ptr<smplhost::GpuBfsHeuristic> heur;
     std::vector<sbpl::motion::RobotState> states; // the "lattice": state id -> joint state; id 0 = goal state
     int dof = 0;
+    smplgpu_ctx* ctx = nullptr;
+    int cost_per_cell = 1;
+    std::unique_ptr<smplhost::ExpansionCache> cache;
 };
 
 smplhost_adapters* smplhost_adapters_create(smplgpu_ctx* ctx, smplhost_tables* tables, const char* planning_link,
@@ -408,6 +411,8 @@ smplhost_adapters* smplhost_adapters_create(smplgpu_ctx* ctx, smplhost_tables* t
     std::unique_ptr<smplhost_adapters> a(new smplhost_adapters);
     const smplgpu_robot_desc* d = tables->t.desc();
     a->dof = d->dof;
+    a->ctx = ctx;
+    a->cost_per_cell = cost_per_cell;
     a->cc.reset(new smplhost::GpuCollisionSpace(ctx, d->dof));
     std::vector<int> types(d->var_type, d->var_type + d->dof);
     std::vector<double> weights(d->var_motion_weight, d->var_motion_weight + d->dof);
@@ -432,6 +437,35 @@ smplhost_adapters* smplhost_adapters_create(smplgpu_ctx* ctx, smplhost_tables* t
 }
 
 void smplhost_adapters_destroy(smplhost_adapters* a) { delete a; }
+
+int smplhost_adapters_enable_expansion_cache(smplhost_adapters* a, const double* deltas, int n_prims, int64_t* counters)
+{
+    if (!a) return -1;
+    if (counters && a->cache) {
+        counters[0] = a->cache->launches();
+        counters[1] = a->cache->hits();
+    }
+    if (!deltas) {
+        return a->cache ? 0 : -1;   // counters only
+    }
+    a->cc->setExpansionCache(nullptr);
+    a->rm->setExpansionCache(nullptr);
+    a->heur->setExpansionCache(nullptr);
+    a->cache.reset();
+    if (n_prims <= 0) {
+        return 0;
+    }
+    a->cache.reset(new smplhost::ExpansionCache(a->ctx, a->dof, deltas, n_prims, a->cost_per_cell));
+    if (!a->cache->ok()) {
+        g_err = smplgpu_last_error(a->ctx);
+        a->cache.reset();
+        return -1;
+    }
+    a->cc->setExpansionCache(a->cache.get());
+    a->rm->setExpansionCache(a->cache.get());
+    a->heur->setExpansionCache(a->cache.get());
+    return 0;
+}
 
 static sbpl::motion::RobotState to_state(const smplhost_adapters* a, const double* q)
 {

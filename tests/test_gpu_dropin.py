@@ -104,3 +104,38 @@ def test_reference_lattice_with_batched_get_succs_returns_the_same_plans():
         assert secs[True][1] < 0.75 * secs[False][1]
     finally:
         ctx.close()
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libref_dropin.so not built")
+def test_unchanged_reference_planner_with_expansion_cache_is_one_launch_per_expansion():
+    """The UNCHANGED reference lattice (ManipLattice::GetSuccs as shipped, one virtual call per question) with the
+    adapters sharing a smplhost::ExpansionCache: the first question about a state triggers one smplgpu_expand_state
+    launch, the other ~65 calls of the expansion are served from its record.  Same plans as the all-reference run; at
+    most ~one launch per expansion (plus the goal / start set-up), and the wall time is printed beside the per-call
+    path's (11.7 s for these eight queries in round 1; the reference's own CPU stack needs ~0.6 s)."""
+    import time
+    lib = C.CDLL(LIB)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "plans_reference.json")))
+    scene, attach, params, starts, goals = plan_cases()["pr2_tabletop"]
+    ctx, tables = api.setup_context(scene)
+    try:
+        dropin_plan(lib, ctx, scene, starts[0], goals[0], params, batched=2)     # warm-up (allocations, module load)
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        expansions = cache_launches = 0
+        for s, g, want in zip(starts, goals, gold["pr2_tabletop"]):
+            got = dropin_plan(lib, ctx, scene, s, g, params, batched=2)
+            assert got == want
+            expansions += got[1]
+            cache_launches += dropin_plan.last_batched[0]
+        secs = time.perf_counter() - t0
+        launches = ctx.launch_count() - l0
+        print("unchanged reference planner over cached GPU plug-ins, 8 queries: %d expansions in %.3f s "
+              "(%.0f expansions/s), %d launches (%d by the cache)" % (expansions, secs, expansions / secs, launches,
+                                                                      cache_launches))
+        # per query: walls + BFS (a handful of launches) + one record per expanded state (+ start, + goal-state h, + the
+        # few states ARA* asks about out of expansion order: 6616 records for 6491 expansions on the B200)
+        assert cache_launches <= 1.05 * expansions + 4 * len(starts)
+        assert launches <= cache_launches + 40 * len(starts)
+    finally:
+        ctx.close()
