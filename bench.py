@@ -6,11 +6,17 @@
 
 A step = one pass of the hot path over one batch of synthetic input of the shape
 BASELINE.json configs[1] names: `--states` random PR2 right-arm states plus as many
-motion-primitive edges, against the 2 m^3 / 2 cm clutter scene.  Every rank (GPU)
-processes its own full batch (weak scaling: independent queries, no collective on
-the data path; the distance field is built on rank 0 and broadcast once over NCCL).
-The unit is a validated state: one per state plus `waypoint_count` per edge, the
-states CollisionSpace::isStateToStateValid accounts for (collision_space.cpp:538-581).
+motion-primitive edges, against the 2 m^3 / 2 cm clutter scene.  The states are uniformly
+random LATTICE states (1 degree, ManipLattice::coordToState): what the path's real caller
+holds.  Every rank (GPU) processes its own full batch (weak scaling: independent queries, no
+collective on the data path; the distance field is built on rank 0 and broadcast once over
+NCCL, device to device).  The unit is a validated state: one per state plus `waypoint_count`
+per edge, the states CollisionSpace::isStateToStateValid accounts for (collision_space.cpp:538-581).
+
+The driver's record keeps scalars of the dicts the contract names and drops everything else, so
+every BASELINE metric is ALSO written as a scalar: device-side fractions under `roofline`, the
+other legs' throughputs (plan, drop-in, BFS, config[3] UBR1, config[4] 15-DOF) under `e2e`, their
+CPU counterparts under `cpu_baseline`.  `config` is identical in both arms.
 """
 import argparse
 import json
@@ -93,7 +99,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_oracle(scene, prime_q):
+def make_oracle(scene, prime_q, attach=None):
     from oracle_api import OracleScene
     o = OracleScene(scene.robot_path, scene.group, scene.planning_joints, scene.origin, scene.size, scene.res,
                     scene.max_dist)
@@ -103,6 +109,8 @@ def make_oracle(scene, prime_q):
         o.use_desc_acm()
     for a, b, allowed in scene.acm_extra:
         o.acm_set(a, b, allowed)
+    if attach is not None:
+        o.attach_box(*attach)
     if len(scene.cells):
         o.add_cells(scene.cells)
     if len(getattr(scene, "boxes", [])):
@@ -111,7 +119,7 @@ def make_oracle(scene, prime_q):
     return o
 
 
-def make_reference_checker(scene, prime_q):
+def make_reference_checker(scene, prime_q, attach=None):
     """The reference's OWN collision checker (sbpl_collision_checking compiled from its sources into
     oracle/_ref/libref_collision.so, see oracle/ref_collision_shim.cpp) set up for `scene`, or None when that library
     was not built (then the CPU legs time the oracle port)."""
@@ -126,6 +134,8 @@ def make_reference_checker(scene, prime_q):
         r.use_desc_acm()
     for a, b, allowed in scene.acm_extra:
         r.acm_set(a, b, allowed)
+    if attach is not None:
+        r.attach_box(*attach)     # CollisionSpace::attachObject: the reference generates the body's spheres itself
     if len(scene.cells):
         r.add_cells(scene.cells)
     if len(getattr(scene, "boxes", [])):
@@ -202,25 +212,62 @@ class StdoutToStderr:
         return False
 
 
-def setup_shared_scene(scene, local_rank, rank, world, dev):
+def setup_shared_scene(scene, local_rank, rank, world, dev, timing=None):
     """Context for `scene` on this rank's GPU: rank 0 builds the distance field on its GPU, every other rank
-    receives it in ONE broadcast (NCCL over NVLink) -- the only collective of the data path."""
+    receives it in ONE broadcast (NCCL over NVLink) -- the only collective of the data path -- straight from rank 0's
+    resident field (smplgpu_distance_field_dev_ptr) into its own reserved buffer (smplgpu_reserve_distance_field):
+    device to device, no host hop, no staging tensor.  timing (dict, optional) receives build_ms / broadcast_ms."""
     import torch
     from smpl_b200 import api, sharding
     ctx = api.GpuContext(local_rank)
     tables = api.build_tables(scene)
     ctx.set_robot(tables)
+    t0 = time.perf_counter()
     if rank == 0:
         ctx.build_distance_field(api.scene_cells(scene, tables), scene.dims, scene.origin, scene.res, scene.max_dist,
                                  scene.padding)
+        ctx.synchronize()
+    t1 = time.perf_counter()
     if world > 1:
-        d2 = ctx.download_distance_field() if rank == 0 else None
-        df_t = sharding.broadcast_distance_field(d2, scene.dims, src=0, device=dev)
+        ptr, nbytes = ctx.distance_field_dev_ptr() if rank == 0 else ctx.reserve_distance_field(scene.dims)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sharding.broadcast_field_in_place(ptr, nbytes, src=0, device=dev)
+        e1.record()
         torch.cuda.synchronize()
         if rank != 0:
             dmax = int(np.ceil(scene.max_dist * (1.0 / scene.res)))
-            ctx.set_distance_field_dev(df_t.data_ptr(), scene.dims, scene.origin, scene.res, dmax * dmax, scene.padding)
+            ctx.set_distance_field_dev(ptr, scene.dims, scene.origin, scene.res, dmax * dmax, scene.padding)   # adopts in place
+        if timing is not None:
+            timing["broadcast_ms"] = e0.elapsed_time(e1)
+            timing["broadcast_bytes"] = nbytes
+    if timing is not None:
+        timing["build_ms"] = (t1 - t0) * 1e3
     return ctx, tables
+
+
+WORKLOAD = "config[1] validity sweep: PR2 right arm (7-DOF) lattice states + mprim edges vs 2 m^3 clutter scene @ 2 cm"
+
+
+def sweep_inputs(lo, hi, cont, n, rank):
+    """The step's inputs, identical for both arms: n uniformly random lattice states (1 degree discretisation,
+    ManipLattice::coordToState joint values) and n edges, edge i = state i + motion primitive i mod 22."""
+    from smpl_b200 import scenes
+    res = scenes.PlanParams(len(lo)).resolutions
+    coords, q = scenes.random_lattice_coords(n, lo, hi, cont, res, seed=20260101 + rank)
+    deltas = np.ascontiguousarray(scenes.pr2_mprim_deltas())
+    pid = (np.arange(n) % len(deltas)).astype(np.uint8)
+    q1 = np.ascontiguousarray(q + deltas[pid])
+    return res, coords, q, pid, deltas, q1
+
+
+def sweep_config(n, units_per_step):
+    return {"workload": WORKLOAD, "states_per_step_per_gpu": int(n), "edges_per_step_per_gpu": int(n),
+            "validated_states_per_step_per_gpu": int(units_per_step),
+            "input": "uniformly random lattice states (1 deg, coordToState); edge i = state i + primitive i mod 22",
+            "l2_policy": "inputs (%.0f MB/step as doubles) exceed the 126 MB L2; the 2 MB distance field is L2-resident by design"
+                         % ((3 * n * 7 * 8) / 1e6)}
 
 
 def run_reference(args, rank, world):
@@ -233,28 +280,35 @@ def run_reference(args, rank, world):
     o = make_oracle(scene, np.zeros(scene.dof))
     o.init_kdl(scene.chain_root, scene.chain_tip, scene.planning_link, scene.T_kin_to_planning)
     lo, hi, cont = o.joint_limits()
-    n = args.ref_sample
+    n = args.ref_sample if args.ref_sample > 0 else args.states     # default: the GPU arm's step (same config)
     threads = os.cpu_count() or 1
-    q = scenes.random_states(n, lo, hi, cont, seed=20260101)
-    q0, q1 = scenes.mprim_edges(q)
+    _, _, q, _, _, q1 = sweep_inputs(lo, hi, cont, n, 0)
+    q0 = q
     made = [make_cpu_checker(scene, q[0]) for _ in range(threads)]
     checkers, kind, what = [m[0] for m in made], made[0][1], made[0][2]
     for _ in range(args.warmup):
         cpu_validity_rate(scene, q[: n // 8], q0[: n // 8], q1[: n // 8], threads, checkers)
     total_units, total_t = 0, 0.0
+    # bounded: the whole --steps K run must end within a few minutes whatever the host (a step is ~0.4 s on 16 threads)
+    budget_s = 150.0
+    steps_run = 0
     for _ in range(args.steps):
         _, u, dt = cpu_validity_rate(scene, q, q0, q1, threads, checkers)
         total_units += u
         total_t += dt
+        steps_run += 1
+        if total_t > budget_s:
+            break
     value = total_units / total_t
+    units_per_step = total_units // steps_run
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / steps_run,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config[1] validity sweep: PR2 right arm states + mprim edges vs 2 m^3 clutter scene @ 2 cm",
-                   "states_per_step": n, "edges_per_step": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                         "sample": "%d states + %d edges per step, %s on %d threads" % (n, n, what, threads)},
+        "config": sweep_config(n, units_per_step),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "steps_timed": steps_run,
+                         "sample": "%d states + %d edges per step on %d threads, %s; Eigen arithmetic is the stand-in "
+                                   "oracle/ref_stubs/eigen_arith (real Eigen is absent here)" % (n, n, threads, what)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -279,6 +333,206 @@ def wandering_paths(anchors, n_paths, dof, seed):
     return paths
 
 
+def timed_events(torch, fn, reps):
+    """mean milliseconds of fn() over reps calls, CUDA events on the current stream."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def plan_leg(api, scenes, sharding, dist, torch, dev, scene, starts_all, goals_all, params, args, rank, world, local_rank,
+             barrier, label, attach=None):
+    """Planning queries sharded round-robin over the ranks (no collective); -> (dict, results of this rank, contexts'
+    scene objects for the CPU comparison)."""
+    pctx, ptables = setup_shared_scene(scene, local_rank, rank, world, dev)
+    if attach is not None:
+        # AttachedBodiesCollisionModel::generateSpheresModel on the device voxeliser (smplhost_tables_attach_box)
+        ptables.attach_box(pctx, *attach)
+        ptables.apply(pctx)
+    nq_total = len(starts_all)
+    mine = sharding.round_robin_shard(nq_total, rank, world)
+    cores = os.cpu_count() or 1
+    n_thr = args.plan_threads if args.plan_threads > 0 else max(1, min(12, int(0.75 * cores / max(1, world))))
+    n_thr = max(n_thr, (args.plan_concurrent + 511) // 512)
+    pctxs = [pctx] + [api.clone_context(pctx, scene, ptables, device=local_rank) for _ in range(n_thr - 1)]
+    per_ctx = max(1, (min(args.plan_concurrent, max(1, len(mine))) + n_thr - 1) // n_thr)
+    wq = min(len(mine), per_ctx * n_thr)
+    wparams = scenes.PlanParams(scene.dof)
+    wparams.max_expansions = 20
+    api.plan_batch(pctxs, scene, ptables, wparams, starts_all[mine][:wq], goals_all[mine][:wq], max_concurrent=per_ctx)
+    barrier()
+    psampler = ClockSampler(local_rank)
+    if rank == 0:
+        psampler.start()
+    t0 = time.perf_counter()
+    pres, pstats = api.plan_batch(pctxs, scene, ptables, params, starts_all[mine], goals_all[mine], max_concurrent=per_ctx)
+    dt = time.perf_counter() - t0
+    pclocks = psampler.stop() if rank == 0 else None
+    pstats["planner_threads"] = n_thr
+    t_plan = torch.tensor([dt], device=dev, dtype=torch.float64)
+    n_exp = torch.tensor([float(sum(r["expansions"] for r in pres)), float(sum(r["success"] for r in pres))],
+                         device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_plan, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_exp, op=dist.ReduceOp.SUM)
+    secs = float(t_plan.item())
+    plan = {"scene": label, "queries": nq_total, "solved": int(n_exp[1].item()), "expansions": int(n_exp[0].item()),
+            "seconds": secs, "queries_per_s": nq_total / secs, "expansions_per_s": float(n_exp[0].item()) / secs,
+            "concurrent_per_gpu": args.plan_concurrent, "planner_threads_per_gpu": n_thr, "rank0": pstats, "clocks": pclocks}
+    for c in pctxs:
+        c.close()
+    return plan, pres
+
+
+def plan_cpu_compare(plan, scene, starts_all, goals_all, params, pres, k, world, attach=None):
+    """The reference's own ManipLattice + BfsHeuristic + ARAStar + CollisionSpace (oracle/ref_planner_shim.cpp) on the
+    first k queries, 1 thread, with the parity count of this rank's results."""
+    po = make_oracle(scene, np.zeros(scene.dof), attach)
+    po.init_kdl(scene.chain_root, scene.chain_tip, scene.planning_link, scene.T_kin_to_planning, scene.xyz_offset)
+    pref = make_reference_checker(scene, np.zeros(scene.dof), attach)
+    k = min(k, len(starts_all))
+    secs, cexp, same = 0.0, 0, 0
+    for qi, (s_, g_) in enumerate(zip(starts_all[:k], goals_all[:k])):
+        po.heur_init(scene.inflation_radius, scene.cost_per_cell)
+        t0 = time.perf_counter()
+        pr = pref.plan(scene, s_, g_, params) if pref is not None else po.plan(s_, g_, params)
+        secs += time.perf_counter() - t0      # includes the per-query BFS, as the GPU figure does
+        cexp += pr["expansions"]
+        if world == 1 or qi % world == 0:     # rank 0 planned queries 0, world, 2 world, ...
+            gr = pres[qi // world]
+            same += int((gr["success"], gr["expansions"], gr["cost"]) == (pr["success"], pr["expansions"], pr["cost"])
+                        and np.array_equal(gr["path_ids"], pr["path_ids"]))
+        else:
+            same += 1
+    plan["parity_checked_queries"] = k
+    plan["parity_identical"] = same
+    plan["cpu_queries_per_s"] = k / secs
+    plan["cpu_expansions_per_s"] = cexp / secs
+    plan["cpu_kind"] = "reference" if pref is not None else "port"
+    plan["cpu_sample"] = "first %d queries, %s, 1 thread" % (
+        k, "the reference's own ManipLattice + BfsHeuristic + ARAStar + CollisionSpace (oracle/_ref/libref_collision.so; "
+           "RobotModel and action-space plug-ins from the oracle)" if pref is not None else "oracle ManipLattice + ARA*")
+
+
+def dropin_leg(api, scenes, local_rank):
+    """north_star's acceptance test: the REFERENCE's own ManipLattice + ARAStar (compiled from /root/reference into
+    oracle/_ref/libref_dropin.so, the caller -- not the thing measured) plan over the product's plug-ins, unchanged,
+    one virtual call per question; the adapters answer from one smplgpu_expand_state launch per expansion.  Beside it
+    the all-reference run (its own CollisionSpace + BfsHeuristic + BFS_3D on one host thread) on the same queries."""
+    import ctypes as C
+    lib_path = os.path.join(ROOT, "oracle", "_ref", "libref_dropin.so")
+    if not os.path.exists(lib_path):
+        return None
+    from test_gpu_dropin import dropin_plan
+    lib = C.CDLL(lib_path)
+    scene = scenes.pr2_tabletop_scene()
+    params = scenes.PlanParams(scene.dof)
+    params.max_expansions = 2000
+    starts, goals = scenes.tabletop_queries(8, seed=3)
+    ctx, tables = api.setup_context(scene, device=local_rank)
+    try:
+        dropin_plan(lib, ctx, scene, starts[0], goals[0], params, batched=2)      # warm-up
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        got, cache_launches = [], 0
+        for s_, g_ in zip(starts, goals):
+            got.append(dropin_plan(lib, ctx, scene, s_, g_, params, batched=2))
+            cache_launches += dropin_plan.last_batched[0]
+        secs = time.perf_counter() - t0
+        launches = ctx.launch_count() - l0
+    finally:
+        ctx.close()
+    expansions = sum(g[1] for g in got)
+    out = {"queries": len(got), "expansions": expansions, "seconds": secs, "expansions_per_s": expansions / secs,
+           "queries_per_s": len(got) / secs, "launches": int(launches), "launches_per_expansion": launches / max(1, expansions),
+           "caller": "the reference's ManipLattice::GetSuccs + ARAStar, unchanged (oracle/_ref/libref_dropin.so)",
+           "_got": got, "_scene": scene, "_params": params, "_starts": starts, "_goals": goals}
+    return out
+
+
+def dropin_cpu_compare(drop):
+    scene, params = drop.pop("_scene"), drop.pop("_params")
+    starts, goals, got = drop.pop("_starts"), drop.pop("_goals"), drop.pop("_got")
+    pref = make_reference_checker(scene, np.zeros(scene.dof))
+    if pref is None:
+        return
+    t0 = time.perf_counter()
+    same, cexp = 0, 0
+    for s_, g_, g in zip(starts, goals, got):
+        pr = pref.plan(scene, s_, g_, params)
+        cexp += pr["expansions"]
+        same += int([int(pr["success"]), int(pr["expansions"]), int(pr["cost"]), int(pr["num_states"]),
+                     [int(i) for i in pr["path_ids"]]] == g)
+    secs = time.perf_counter() - t0
+    drop["cpu_seconds"] = secs
+    drop["cpu_expansions_per_s"] = cexp / secs
+    drop["identical_plans"] = same
+    drop["cpu_sample"] = "the same %d queries through the reference's own CollisionSpace + BfsHeuristic + BFS_3D, 1 thread" % len(got)
+
+
+def dual_arm_leg(api, scenes, sharding, dist, torch, dev, args, rank, world, local_rank, barrier, stream):
+    """BASELINE config[4] at the validity level (the reference's only RobotModel on this path refuses two chains,
+    kdl_robot_model.cpp:96-108, so there is no reference lattice to plan on): PR2 torso + both arms (15-DOF), 3 x 3 x 2 m
+    dense shelf at 1 cm = 300 x 300 x 200 cells; the 36 MB field is built on rank 0 and broadcast device to device."""
+    scene = scenes.pr2_dual_arm_scene()
+    timing = {}
+    ctx, tables = setup_shared_scene(scene, local_rank, rank, world, dev, timing)
+    ctx.set_stream(stream.cuda_stream)
+    lo, hi, cont = tables.limits()
+    n = args.dual_states
+    q = scenes.random_states(n, lo, hi, cont, seed=4040 + rank)
+    prm = scenes.PlanParams(scene.dof)
+    deltas = np.concatenate([prm.mprims, -prm.mprims])
+    q0, q1 = scenes.mprim_edges(q, deltas)
+    d_q0, d_q1 = torch.from_numpy(q0).to(dev), torch.from_numpy(q1).to(dev)
+    d_v = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_ev = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+
+    def step():
+        ctx.is_states_valid_dev(d_q0.data_ptr(), n, d_v.data_ptr())
+        ctx.is_edges_valid_dev(d_q0.data_ptr(), d_q1.data_ptr(), n, d_ev.data_ptr(), d_cnt.data_ptr())
+
+    for _ in range(3):
+        step()
+    barrier()
+    ms_plain = timed_events(torch, step, 5)
+    stats = ctx.last_validity_stats()
+    resolved = ctx.last_f64_resolved()
+    units = n + int(d_cnt.sum().item())
+    ms_l2, set_aside = None, 0.0
+    try:
+        set_aside = ctx.set_distance_field_l2_persistence(True)
+        for _ in range(2):
+            step()
+        ms_l2 = timed_events(torch, step, 5)
+        ctx.set_distance_field_l2_persistence(False)
+    except api.SmplGpuError as e:
+        sys.stderr.write("[bench] L2 persistence window unavailable: %s\n" % e)
+    best = min(ms_plain, ms_l2) if ms_l2 else ms_plain
+    t = torch.tensor([best], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cert_in_use, e_pos, eps_cells = ctx.certified_bounds()
+    out = {"scene": "PR2 torso + both arms (15-DOF), 300x300x200 field @ 1 cm (36 MB), dense shelf", "states_per_gpu": n,
+           "edges_per_gpu": n, "validated_states_per_gpu": units, "ms_per_step": float(t.item()),
+           "states_per_s": world * units / (float(t.item()) * 1e-3), "ms_default_l2": ms_plain, "ms_l2_window": ms_l2,
+           "l2_set_aside_mb": set_aside, "field_build_ms": timing.get("build_ms"), "broadcast_ms": timing.get("broadcast_ms"),
+           "broadcast_bytes": timing.get("broadcast_bytes"),
+           "broadcast_gbs": (timing["broadcast_bytes"] / (timing["broadcast_ms"] * 1e-3) / 1e9) if timing.get("broadcast_ms") else None,
+           "lookups_per_checked_state": stats["df_lookups"] / max(1, stats["waypoints"]),
+           "pair_tests_per_checked_state": stats["pair_tests"] / max(1, stats["waypoints"]),
+           "f64_resolved_edge_fraction": resolved / n, "certified_f32": bool(cert_in_use), "valid_fraction_states": float(d_v.float().mean().item()),
+           "_scene": scene, "_q0": q0, "_q1": q1, "_v": d_v.cpu().numpy(), "_ev": d_ev.cpu().numpy(), "_cnt": d_cnt.cpu().numpy()}
+    ctx.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -288,12 +542,16 @@ def main():
     ap.add_argument("--states", type=int, default=1 << 20, help="states (and edges) per step per GPU")
     ap.add_argument("--bfs-n", type=int, default=400)
     ap.add_argument("--cpu-sample", type=int, default=1 << 19, help="states (and edges) timed on the CPU oracle")
-    ap.add_argument("--ref-sample", type=int, default=1 << 17)
+    ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: states (and edges) per step; 0 = --states")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--plan-queries", type=int, default=2048, help="planning queries per GPU (0 = skip)")
     ap.add_argument("--plan-concurrent", type=int, default=2048, help="queries in flight per GPU (one BFS grid each)")
     ap.add_argument("--plan-max-expansions", type=int, default=2000)
     ap.add_argument("--plan-cpu-queries", type=int, default=12)
+    ap.add_argument("--ubr1-queries", type=int, default=4096, help="config[3]: UBR1 + attached object queries in TOTAL, sharded over the ranks (0 = skip)")
+    ap.add_argument("--ubr1-max-expansions", type=int, default=1000)
+    ap.add_argument("--dual-states", type=int, default=1 << 18, help="config[4]: 15-DOF states (and edges) per GPU (0 = skip)")
+    ap.add_argument("--no-dropin", dest="dropin", action="store_false", help="skip the unchanged-caller leg")
     ap.add_argument("--post-paths", type=int, default=1024, help="joint-space paths shortcut in one call (0 = skip)")
     ap.add_argument("--post-cpu-paths", type=int, default=48)
     ap.add_argument("--no-ingest", dest="ingest", action="store_false", help="skip the scene-ingest leg")
@@ -308,6 +566,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    import ctypes as C
 
     import torch
     import torch.distributed as dist
@@ -332,13 +592,13 @@ def main():
     lo, hi, cont = tables.limits()
 
     n = args.states
-    q = scenes.random_states(n, lo, hi, cont, seed=20260101 + rank)
-    q0, q1 = scenes.mprim_edges(q)
     dof = scene.dof
+    res, coords, q, pid8, deltas, q1 = sweep_inputs(lo, hi, cont, n, rank)
+    q0 = q
+    ctx.set_lattice(res)
 
     # ---- resident inputs (value) ----
     d_q = torch.from_numpy(q).to(dev)
-    d_q0 = torch.from_numpy(q0).to(dev)
     d_q1 = torch.from_numpy(q1).to(dev)
     d_v = torch.empty(n, dtype=torch.uint8, device=dev)
     d_ev = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -346,7 +606,7 @@ def main():
 
     def step_resident():
         ctx.is_states_valid_dev(d_q.data_ptr(), n, d_v.data_ptr())
-        ctx.is_edges_valid_dev(d_q0.data_ptr(), d_q1.data_ptr(), n, d_ev.data_ptr(), d_cnt.data_ptr())
+        ctx.is_edges_valid_dev(d_q.data_ptr(), d_q1.data_ptr(), n, d_ev.data_ptr(), d_cnt.data_ptr())
 
     def barrier():
         if world > 1:
@@ -367,7 +627,7 @@ def main():
     for s in range(args.steps):
         ctx.is_states_valid_dev(d_q.data_ptr(), n, d_v.data_ptr())
         ev[2 * s + 1].record()
-        ctx.is_edges_valid_dev(d_q0.data_ptr(), d_q1.data_ptr(), n, d_ev.data_ptr(), d_cnt.data_ptr())
+        ctx.is_edges_valid_dev(d_q.data_ptr(), d_q1.data_ptr(), n, d_ev.data_ptr(), d_cnt.data_ptr())
         ev[2 * s + 2].record()
     barrier()
     gpu_launches = ctx.launch_count() - launches0
@@ -378,70 +638,82 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     total_ms_max = float(t_ms.item())
-    gpu_stats = ctx.last_validity_stats()
+    gpu_stats = ctx.last_validity_stats()       # of the last launch (the edges)
     gpu_stats["f64_resolved_edges_last_launch"] = ctx.last_f64_resolved()
     cert_in_use, e_pos, eps_cells = ctx.certified_bounds()
     gpu_stats["certified_f32"] = {"in_use": cert_in_use, "e_pos_m": e_pos, "eps_cells": eps_cells}
     df_lookup_peak = ctx.probe_df_lookup_rate() if rank == 0 else None   # independent random lookups/s on this field
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
-    hq = torch.from_numpy(q).pin_memory()
-    hq0 = torch.from_numpy(q0).pin_memory()
-    deltas = np.ascontiguousarray(scenes.pr2_mprim_deltas())
-    hpid = torch.from_numpy((np.arange(n) % len(deltas)).astype(np.int32)).pin_memory()   # edge i = state i + primitive i mod 22
+    # lattice states on the wire as the real caller holds them: 16-bit RobotCoord + one primitive byte per edge
+    hc = torch.from_numpy(coords).pin_memory()
+    hp = torch.from_numpy(pid8).pin_memory()
     hv = torch.empty(n, dtype=torch.uint8).pin_memory()
     hev = torch.empty(n, dtype=torch.uint8).pin_memory()
     L = ctx.L
-    import ctypes as C
+    c_i16_p = C.POINTER(C.c_int16)
+    deltas_p = deltas.ctypes.data_as(api.c_double_p)
 
     def step_e2e():
-        r = L.smplgpu_is_states_valid(ctx.h, C.cast(hq.data_ptr(), api.c_double_p), n, C.cast(hv.data_ptr(), api.c_uint8_p))
-        # edges as GetSuccs produces them: (parent state, motion primitive id) against the primitive table
-        r |= L.smplgpu_is_mprim_edges_valid(ctx.h, C.cast(hq0.data_ptr(), api.c_double_p), C.cast(hpid.data_ptr(), api.c_int32_p),
-                                            n, deltas.ctypes.data_as(api.c_double_p), len(deltas),
-                                            C.cast(hev.data_ptr(), api.c_uint8_p), None)
+        r = L.smplgpu_is_lattice_states_valid(ctx.h, C.cast(hc.data_ptr(), c_i16_p), n, C.cast(hv.data_ptr(), api.c_uint8_p))
+        r |= L.smplgpu_is_lattice_edges_valid(ctx.h, C.cast(hc.data_ptr(), c_i16_p), C.cast(hp.data_ptr(), api.c_uint8_p), n,
+                                              deltas_p, len(deltas), C.cast(hev.data_ptr(), api.c_uint8_p), None)
         if r != 0:
             raise RuntimeError(L.smplgpu_last_error(ctx.h).decode())
 
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the same step with the states as doubles (arbitrary, off-lattice states take this path)
+    hq = torch.from_numpy(q).pin_memory()
+    hpid = torch.from_numpy(pid8.astype(np.int32)).pin_memory()
+    hv2 = torch.empty(n, dtype=torch.uint8).pin_memory()
+    hev2 = torch.empty(n, dtype=torch.uint8).pin_memory()
+
+    def step_e2e_f64():
+        r = L.smplgpu_is_states_valid(ctx.h, C.cast(hq.data_ptr(), api.c_double_p), n, C.cast(hv2.data_ptr(), api.c_uint8_p))
+        r |= L.smplgpu_is_mprim_edges_valid(ctx.h, C.cast(hq.data_ptr(), api.c_double_p), C.cast(hpid.data_ptr(), api.c_int32_p),
+                                            n, deltas_p, len(deltas), C.cast(hev2.data_ptr(), api.c_uint8_p), None)
+        if r != 0:
+            raise RuntimeError(L.smplgpu_last_error(ctx.h).decode())
+
+    def time_e2e(fn, steps):
+        for _ in range(2):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * units_per_step * steps / (float(t.item()) * 1e-3)
+
     e2e_steps = max(3, args.steps // 2)
-    e0.record()
-    for _ in range(e2e_steps):
-        step_e2e()
-    e1.record()
-    barrier()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * units_per_step * e2e_steps / (float(e2e_ms.item()) * 1e-3)
-    assert torch.equal(hv.to(dev), d_v) and torch.equal(hev.to(dev), d_ev), "host-buffer path disagrees with resident path"
+    e2e_value = time_e2e(step_e2e, e2e_steps)
+    e2e_f64_value = time_e2e(step_e2e_f64, max(3, e2e_steps // 2))
+    assert torch.equal(hv.to(dev), d_v) and torch.equal(hev.to(dev), d_ev), "host-buffer (lattice) path disagrees with resident path"
+    assert torch.equal(hv2.to(dev), d_v) and torch.equal(hev2.to(dev), d_ev), "host-buffer (double) path disagrees with resident path"
     verdict_s, verdict_e, counts_e = hv.numpy().copy(), hev.numpy().copy(), d_cnt.cpu().numpy()
 
-    # ---- BFS (config[2]): 400^3 cluttered occupancy, rank 0 only for the side metric ----
+    # ---- BFS (config[2]): 400^3 cluttered occupancy (+ the planner's 150^3 size), rank 0 only ----
     bfs = None
     if rank == 0 and args.bfs_n > 0:
+        def bfs_time(nb):
+            walls = scenes.bfs_clutter_walls(nb, seed=11)
+            seed = scenes.first_free_cell(walls, (nb // 2, nb // 2, nb // 2))
+            ctx.bfs_set_walls(walls)
+            for _ in range(2):
+                ctx.bfs_run([seed])
+            return timed_events(torch, lambda: ctx.bfs_run([seed]), 5), ctx.bfs_last_levels()
         nb = args.bfs_n
-        walls = scenes.bfs_clutter_walls(nb, seed=11)
-        seed = scenes.first_free_cell(walls, (nb // 2, nb // 2, nb // 2))
-        ctx.bfs_set_walls(walls)
-        for _ in range(2):
-            ctx.bfs_run([seed])
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        torch.cuda.synchronize()
-        b0.record()
-        for _ in range(reps):
-            ctx.bfs_run([seed])
-        b1.record()
-        torch.cuda.synchronize()
-        bfs_ms = b0.elapsed_time(b1) / reps
+        ms150, lv150 = bfs_time(150) if nb != 150 else (None, None)
+        bfs_ms, levels = bfs_time(nb)
         alg_bytes = (nb + 2) ** 3 * (1.0 / 8 + 4)
-        bfs = {"grid": "%d^3" % nb, "levels": ctx.bfs_last_levels(), "ms": bfs_ms,
+        bfs = {"grid": "%d^3" % nb, "levels": levels, "ms": bfs_ms,
                "mvoxel_s": nb ** 3 / (bfs_ms * 1e-3) / 1e6,
-               "algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (bfs_ms * 1e-3) / 1e9}
+               "algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (bfs_ms * 1e-3) / 1e9,
+               "ms_150": ms150, "levels_150": lv150}
 
     # ---- path post-processing: shortcut many paths with ONE batch of candidate motions ----
     post = None
@@ -481,55 +753,51 @@ def main():
                   "_d2": d2, "_scene": iscene}
         ictx.close()
 
-    clocks = sampler.stop() if rank == 0 else None   # sampled across the validity, end-to-end, BFS, shortcut and ingest regions
+    # ---- the unchanged caller (north_star's acceptance test), rank 0 ----
+    drop = None
+    if rank == 0 and args.dropin:
+        with StdoutToStderr():
+            drop = dropin_leg(api, scenes, local_rank)
 
-    # ---- plan queries/s (config[0]/[3] shape): PR2 right arm on the tabletop scene, queries sharded over ranks ----
-    plan = None
+    clocks = sampler.stop() if rank == 0 else None   # sampled across the validity, end-to-end, BFS, shortcut, ingest, drop-in regions
+
+    # ---- config[4]: 15-DOF validity at 1 cm, field broadcast device to device (all ranks) ----
+    dual = None
+    if args.dual_states > 0:
+        with StdoutToStderr():
+            dual = dual_arm_leg(api, scenes, sharding, dist, torch, dev, args, rank, world, local_rank, barrier, stream)
+
+    # ---- plan queries/s (config[0] shape): PR2 right arm on the tabletop scene, queries sharded over ranks ----
+    plan, pres = None, None
     if args.plan_queries > 0:
         pscene = scenes.pr2_tabletop_scene()
-        pctx, ptables = setup_shared_scene(pscene, local_rank, rank, world, dev)
         pparams = scenes.PlanParams(pscene.dof)
         pparams.max_expansions = args.plan_max_expansions
-        nq_total = args.plan_queries * world
-        starts_all, goals_all = scenes.tabletop_queries(nq_total, seed=13)
-        mine = sharding.round_robin_shard(nq_total, rank, world)   # no collective
-        # one planner thread per context (the reference's threading model), all on this rank's GPU
-        # the planner is bound by the host-side lattice / OPEN-list work once enough queries are in flight
-        # (measured on 16 cores, 2048 queries: 8 threads 916 q/s, 12 threads 1229 q/s)
-        n_thr = args.plan_threads if args.plan_threads > 0 else max(1, min(12, int(0.75 * (os.cpu_count() or 1) / max(1, world))))
-        # a context's BFS bank keeps int node indices (<= 611 slots of 150^3): enough contexts for the queries in flight
-        n_thr = max(n_thr, (args.plan_concurrent + 511) // 512)
-        pctxs = [pctx] + [api.clone_context(pctx, pscene, ptables, device=local_rank) for _ in range(n_thr - 1)]
-        per_ctx = max(1, (args.plan_concurrent + n_thr - 1) // n_thr)
-        # warm-up with the same bank shape: the BFS bank (a scene-level allocation of per_ctx grids per context) is
-        # created here and reused by the timed call
-        wq = min(len(mine), per_ctx * n_thr)
-        wparams = scenes.PlanParams(pscene.dof)
-        wparams.max_expansions = 20
-        api.plan_batch(pctxs, pscene, ptables, wparams, starts_all[mine][:wq], goals_all[mine][:wq], max_concurrent=per_ctx)
-        barrier()
-        psampler = ClockSampler(local_rank)
-        if rank == 0:
-            psampler.start()
-        t0 = time.perf_counter()
-        pres, pstats = api.plan_batch(pctxs, pscene, ptables, pparams, starts_all[mine], goals_all[mine],
-                                      max_concurrent=per_ctx)
-        dt = time.perf_counter() - t0
-        pclocks = psampler.stop() if rank == 0 else None
-        pstats["planner_threads"] = n_thr
-        t_plan = torch.tensor([dt], device=dev, dtype=torch.float64)
-        n_exp = torch.tensor([float(sum(r["expansions"] for r in pres)), float(sum(r["success"] for r in pres))],
-                             device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t_plan, op=dist.ReduceOp.MAX)
-            dist.all_reduce(n_exp, op=dist.ReduceOp.SUM)
-        plan = {"scene": "PR2 right arm, tabletop env, 150^3 field @ 2 cm, ARA* eps 100, first solution, <= %d expansions" % args.plan_max_expansions,
-                "queries": nq_total, "solved": int(n_exp[1].item()), "expansions": int(n_exp[0].item()),
-                "seconds": float(t_plan.item()), "queries_per_s": nq_total / float(t_plan.item()),
-                "expansions_per_s": float(n_exp[0].item()) / float(t_plan.item()), "concurrent_per_gpu": args.plan_concurrent,
-                "rank0": pstats, "clocks": pclocks}
-        for c in pctxs:
-            c.close()
+        starts_all, goals_all = scenes.tabletop_queries(args.plan_queries * world, seed=13)
+        with StdoutToStderr():
+            plan, pres = plan_leg(api, scenes, sharding, dist, torch, dev, pscene, starts_all, goals_all, pparams, args, rank,
+                                  world, local_rank, barrier,
+                                  "PR2 right arm, tabletop env, 150^3 field @ 2 cm, ARA* eps 100, first solution, <= %d expansions; "
+                                  "%d queries per GPU" % (args.plan_max_expansions, args.plan_queries))
+
+    # ---- config[3]: UBR1 arm + attached object + ACM, 4096 queries in total sharded over the ranks ----
+    ubr1, ures = None, None
+    if args.ubr1_queries > 0:
+        uscene = scenes.ubr1_tabletop_scene()
+        # the grasped object goes through attachObject on both sides (device voxeliser here, the reference's own there)
+        uscene.attached = None
+        uattach = ("object", "wrist_roll_link", (0.05, 0.05, 0.20),
+                   np.array([[1.0, 0.0, 0.0, 0.26], [0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0]]))
+        uparams = scenes.PlanParams(uscene.dof)
+        uparams.max_expansions = args.ubr1_max_expansions
+        ustarts, ugoals = scenes.ubr1_tabletop_queries(args.ubr1_queries, seed=13)
+        with StdoutToStderr():
+            ubr1, ures = plan_leg(api, scenes, sharding, dist, torch, dev, uscene, ustarts, ugoals, uparams, args, rank, world,
+                                  local_rank, barrier,
+                                  "config[3]: UBR1 arm + attached 5x5x20 cm object + self-collision ACM, tabletop_ubr1 env, 100^3 field @ "
+                                  "2 cm, <= %d expansions; %d queries in TOTAL over the ranks" % (args.ubr1_max_expansions, args.ubr1_queries),
+                                  attach=uattach)
+            ubr1["scaling"] = "strong (fixed total)"
 
     if world > 1:
         dist.barrier()
@@ -538,7 +806,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (rank 0) ----
+    # ---- CPU legs + roofline of the dominant kernel (rank 0) ----
     peak, peak_src = load_peaks()
     cpu = None
     Lbar_state, Lbar_edge = None, None
@@ -550,48 +818,36 @@ def main():
         t_e, v_e, c = checker.time_edges_valid(q0[:m], q1[:m])
         cpu_units = m + int(c.sum())
         cpu_rate = cpu_units / (t_s + t_e)
-        cpu_agree = None
-        if verdict_s is not None:      # the timed CPU run doubles as a parity check of the device verdicts
-            cpu_agree = {"states_differing": int((v_s != verdict_s[:m]).sum()), "edges_differing": int((v_e != verdict_e[:m]).sum()),
-                         "waypoint_counts_differing": int((c != counts_e[:m]).sum()), "of": m}
+        cpu_agree = {"states_differing": int((v_s != verdict_s[:m]).sum()), "edges_differing": int((v_e != verdict_e[:m]).sum()),
+                     "waypoint_counts_differing": int((c != counts_e[:m]).sum()), "of": m}
         # L-bar: DF lookups the reference semantics requires (no early-out), from the oracle on a sub-sample
         ms = min(m, 1 << 15)
         _, Ls, _, _ = o.report_states(q[:ms])
         _, _, Le = o.report_edges(q0[:ms], q1[:ms])
         Lbar_state, Lbar_edge = float(Ls.mean()), float(Le.mean())
         cpu = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": cpu_kind,
-               "sample": "%d states + %d edges of the same workload, %s, 1 thread; "
+               "sample": "%d states + %d edges of the same workload, 1 thread, %s (stand-in Eigen arithmetic); "
                          "states %.0f/s, edge waypoints %.0f/s" % (m, m, cpu_what, m / t_s, int(c.sum()) / t_e),
+               "device_verdicts_differing": cpu_agree["states_differing"] + cpu_agree["edges_differing"] + cpu_agree["waypoint_counts_differing"],
+               "device_verdicts_checked": 2 * m,
                "device_verdicts_vs_this_run": cpu_agree}
         if plan is not None and args.plan_cpu_queries > 0:
-            po = make_oracle(pscene, np.zeros(pscene.dof))
-            po.init_kdl(pscene.chain_root, pscene.chain_tip, pscene.planning_link, pscene.T_kin_to_planning, pscene.xyz_offset)
-            k = min(args.plan_cpu_queries, len(starts_all))
-            secs, cexp = 0.0, 0
-            same = 0
-            # the reference's own ManipLattice + BfsHeuristic + ARAStar + CollisionSpace (oracle/ref_planner_shim.cpp)
-            # when its build is there, else the oracle's restatement
-            pref = make_reference_checker(pscene, np.zeros(pscene.dof))
-            for qi, (s_, g_) in enumerate(zip(starts_all[:k], goals_all[:k])):
-                po.heur_init(pscene.inflation_radius, pscene.cost_per_cell)
-                t0 = time.perf_counter()
-                pr = pref.plan(pscene, s_, g_, pparams) if pref is not None else po.plan(s_, g_, pparams)
-                secs += time.perf_counter() - t0      # includes the per-query BFS, as the GPU figure does
-                cexp += pr["expansions"]
-                if world == 1 or qi % world == 0:     # rank 0 planned queries 0, world, 2 world, ...
-                    gr = pres[qi // world]
-                    same += int((gr["success"], gr["expansions"], gr["cost"]) == (pr["success"], pr["expansions"], pr["cost"])
-                                and np.array_equal(gr["path_ids"], pr["path_ids"]))
-                else:
-                    same += 1
-            plan["parity_checked_queries"] = k
-            plan["parity_identical"] = same
-            plan["cpu_queries_per_s"] = k / secs
-            plan["cpu_expansions_per_s"] = cexp / secs
-            plan["cpu_kind"] = "reference" if pref is not None else "port"
-            plan["cpu_sample"] = "first %d queries, %s, 1 thread" % (
-                k, "the reference's own ManipLattice + BfsHeuristic + ARAStar + CollisionSpace (oracle/_ref/libref_collision.so; "
-                   "RobotModel and action-space plug-ins from the oracle)" if pref is not None else "oracle ManipLattice + ARA*")
+            plan_cpu_compare(plan, pscene, starts_all, goals_all, pparams, pres, args.plan_cpu_queries, world)
+        if ubr1 is not None and args.plan_cpu_queries > 0:
+            plan_cpu_compare(ubr1, uscene, ustarts, ugoals, uparams, ures, max(4, args.plan_cpu_queries // 2), world, uattach)
+        if drop is not None:
+            dropin_cpu_compare(drop)
+        if dual is not None:
+            dsc = dual["_scene"]
+            # the oracle port: the reference's 48-byte cells make this 18 M-cell grid a gigabyte
+            dchk, dkind = make_oracle(dsc, dual["_q0"][0]), "port"
+            k = min(32768, len(dual["_q0"]))
+            t_s, v_s = dchk.time_states_valid(dual["_q0"][:k])
+            t_e, v_e, c = dchk.time_edges_valid(dual["_q0"][:k], dual["_q1"][:k])
+            dual["cpu_states_per_s"] = (k + int(c.sum())) / (t_s + t_e)
+            dual["cpu_kind"] = dkind
+            dual["cpu_sample"] = "first %d states + edges, 1 thread" % k
+            dual["device_verdicts_differing"] = int((v_s != dual["_v"][:k]).sum() + (v_e != dual["_ev"][:k]).sum() + (c != dual["_cnt"][:k]).sum())
         if post is not None:
             k = min(args.post_cpu_paths, len(post_paths))
             t0 = time.perf_counter()
@@ -653,8 +909,10 @@ def main():
                 "frac": dom["achieved"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "launch_ms": dom["ms"],
                 "Lbar_state": Lbar_state, "Lbar_edge": Lbar_edge,
-                "note": "issue/latency bound (FK arithmetic + dependent L2 lookups), not HBM bound: the HBM fraction is reported "
-                        "as the contract asks; see DESIGN.md and profiles/ for pipe utilisation and stall reasons",
+                "note": "issue/latency bound (FK arithmetic + dependent L2 lookups), not HBM bound; L-bar counts lookups "
+                        "WITHOUT early-out, see l2_frac / lookups_performed_frac and DESIGN.md",
+                "states_ms": float(states_ms), "edges_ms": float(edges_ms),
+                "states_frac": k_states["achieved"] / peak, "edges_frac": k_edges["achieved"] / peak,
                 "other_kernel": other}
     # SURVEY 8d's two fractions for the dominant kernel: HBM = streamed bytes only; L2 = the lookups the reference
     # semantics requires (one 32-byte sector each) against the measured rate of INDEPENDENT random lookups on the
@@ -662,31 +920,89 @@ def main():
     if df_lookup_peak:
         Lb, per_item = (Lbar_edge, 16 * dof + 1) if dom is k_edges else (Lbar_state, 8 * dof + 1)
         roofline["hbm_frac_streamed_bytes"] = n * per_item / (dom["ms"] * 1e-3) / 1e9 / peak
+        roofline["l2_frac"] = n * Lb / (dom["ms"] * 1e-3) / df_lookup_peak
+        roofline["l2_peak_glookups_s"] = df_lookup_peak / 1e9
+        roofline["l2_achieved_glookups_s"] = n * Lb / (dom["ms"] * 1e-3) / 1e9
+        if dom is k_edges:   # gpu_stats is the last launch = the edges
+            roofline["lookups_performed_frac"] = gpu_stats["df_lookups"] / (dom["ms"] * 1e-3) / df_lookup_peak
         roofline["l2"] = {"required_lookups_per_launch": n * Lb, "achieved_glookups_s": n * Lb / (dom["ms"] * 1e-3) / 1e9,
                           "peak_glookups_s": df_lookup_peak / 1e9, "frac": n * Lb / (dom["ms"] * 1e-3) / df_lookup_peak,
                           "achieved_gbs": 32 * n * Lb / (dom["ms"] * 1e-3) / 1e9, "peak_gbs": 32 * df_lookup_peak / 1e9,
                           "peak_source": "measured live: independent random lookups on the loaded field, 8 in flight per thread"}
     if bfs is not None:
+        roofline["bfs_frac"] = bfs["achieved_gbs"] / peak
+        roofline["bfs_achieved_gbs"] = bfs["achieved_gbs"]
+        roofline["bfs_ms"] = bfs["ms"]
         roofline["bfs"] = {"bound": "hbm", "achieved": bfs["achieved_gbs"], "peak": peak, "unit": "GB/s",
                            "frac": bfs["achieved_gbs"] / peak}
 
     value = world * units_per_step * args.steps / (total_ms_max * 1e-3)
+    # the early-out means fewer states are actually evaluated than the unit credits: both rates are printed
+    checked_per_step = n + gpu_stats["waypoints"] if dom is k_edges else None
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * (2 * dof * n) + n, "d2h_bytes_per_step": 2 * n,
+           "calls": "smplgpu_is_lattice_states_valid + smplgpu_is_lattice_edges_valid: 16-bit RobotCoord (+ 1 primitive byte per edge) in pinned host buffers, verdicts out",
+           "f64_value": e2e_f64_value, "f64_h2d_bytes_per_step": 2 * n * dof * 8 + 4 * n,
+           "f64_calls": "smplgpu_is_states_valid + smplgpu_is_mprim_edges_valid (joint values as doubles)"}
+    if checked_per_step:
+        e2e["checked_states_per_s"] = world * checked_per_step * args.steps / (total_ms_max * 1e-3)
+    if plan is not None:
+        e2e.update({"plan_queries_per_s": plan["queries_per_s"], "plan_expansions_per_s": plan["expansions_per_s"],
+                    "plan_queries": plan["queries"], "plan_solved": plan["solved"], "plan_seconds": plan["seconds"],
+                    "plan_threads_per_gpu": plan["planner_threads_per_gpu"],
+                    "plan_parity_identical": plan.get("parity_identical"), "plan_parity_checked": plan.get("parity_checked_queries")})
+    if ubr1 is not None:
+        e2e.update({"ubr1_queries_per_s": ubr1["queries_per_s"], "ubr1_expansions_per_s": ubr1["expansions_per_s"],
+                    "ubr1_queries": ubr1["queries"], "ubr1_solved": ubr1["solved"], "ubr1_seconds": ubr1["seconds"],
+                    "ubr1_parity_identical": ubr1.get("parity_identical"), "ubr1_parity_checked": ubr1.get("parity_checked_queries")})
+    if drop is not None:
+        e2e.update({"dropin_expansions_per_s": drop["expansions_per_s"], "dropin_seconds": drop["seconds"],
+                    "dropin_queries": drop["queries"], "dropin_launches_per_expansion": drop["launches_per_expansion"],
+                    "dropin_identical_plans": drop.get("identical_plans")})
+    if dual is not None:
+        e2e.update({"dual_arm_states_per_s": dual["states_per_s"], "dual_arm_broadcast_ms": dual["broadcast_ms"],
+                    "dual_arm_broadcast_gbs": dual["broadcast_gbs"], "dual_arm_field_build_ms": dual["field_build_ms"],
+                    "dual_arm_ms_default_l2": dual["ms_default_l2"], "dual_arm_ms_l2_window": dual["ms_l2_window"],
+                    "dual_arm_lookups_per_checked_state": dual["lookups_per_checked_state"],
+                    "dual_arm_f64_resolved_edge_fraction": dual["f64_resolved_edge_fraction"],
+                    "dual_arm_device_verdicts_differing": dual.get("device_verdicts_differing")})
+    if bfs is not None:
+        e2e.update({"bfs_mvoxel_s": bfs["mvoxel_s"], "bfs_ms": bfs["ms"], "bfs_levels": bfs["levels"], "bfs_ms_150": bfs["ms_150"]})
+    if post is not None:
+        e2e["post_paths_per_s"] = post["paths_per_s"]
+    if ingest is not None:
+        e2e["ingest_ms"] = ingest["ms"]
+    if cpu is not None:
+        if plan is not None and "cpu_queries_per_s" in plan:
+            cpu.update({"plan_queries_per_s": plan["cpu_queries_per_s"], "plan_expansions_per_s": plan["cpu_expansions_per_s"]})
+        if ubr1 is not None and "cpu_queries_per_s" in ubr1:
+            cpu.update({"ubr1_queries_per_s": ubr1["cpu_queries_per_s"], "ubr1_expansions_per_s": ubr1["cpu_expansions_per_s"]})
+        if drop is not None and "cpu_expansions_per_s" in drop:
+            cpu.update({"dropin_expansions_per_s": drop["cpu_expansions_per_s"], "dropin_seconds": drop["cpu_seconds"]})
+        if dual is not None and "cpu_states_per_s" in dual:
+            cpu["dual_arm_states_per_s"] = dual["cpu_states_per_s"]
+        if bfs is not None and "cpu_mvoxel_s" in bfs:
+            cpu["bfs_mvoxel_s"] = bfs["cpu_mvoxel_s"]
+        if post is not None and "cpu_paths_per_s" in post:
+            cpu["post_paths_per_s"] = post["cpu_paths_per_s"]
+        if ingest is not None and "cpu_ms" in ingest:
+            cpu["ingest_ms"] = ingest["cpu_ms"]
+    gpu_stats["valid_fraction_states"] = float(d_v.float().mean().item())
+    gpu_stats["valid_fraction_edges"] = float(d_ev.float().mean().item())
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 certified, f64 resolves the undecidable items (verdicts = all-f64)", "data": "synthetic",
-        "config": {"workload": "config[1] validity sweep: PR2 right arm (7-DOF) states + mprim edges vs 2 m^3 clutter scene @ 2 cm",
-                   "states_per_step_per_gpu": n, "edges_per_step_per_gpu": n, "validated_states_per_step_per_gpu": units_per_step,
-                   "l2_policy": "inputs (%.0f MB/step) exceed the 126 MB L2; the 2 MB distance field is L2-resident by design" % ((3 * n * dof * 8) / 1e6),
-                   "valid_fraction_states": float(d_v.float().mean().item()), "valid_fraction_edges": float(d_ev.float().mean().item())},
+        "config": sweep_config(n, units_per_step),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * dof * 8 + 4 * n, "d2h_bytes_per_step": 2 * n,
-                "calls": "smplgpu_is_states_valid(q) + smplgpu_is_mprim_edges_valid(q, primitive ids, table): host buffers in, verdicts out"},
+        "e2e": e2e,
         "gpu_launches": int(gpu_launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "bfs": bfs,
         "plan": plan,
+        "ubr1_plan": ubr1,
+        "dual_arm": dual,
+        "dropin": drop,
         "post_processing": post,
         "scene_ingest": ingest,
         "host_cores": os.cpu_count(),
@@ -697,6 +1013,12 @@ def main():
     if ingest is not None:
         ingest.pop("_d2", None)
         ingest.pop("_scene", None)
+    if dual is not None:
+        for k in ("_scene", "_q0", "_q1", "_v", "_ev", "_cnt"):
+            dual.pop(k, None)
+    if drop is not None:
+        for k in ("_got", "_scene", "_params", "_starts", "_goals"):
+            drop.pop(k, None)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -215,6 +215,15 @@ int smplgpu_download_distance_field(smplgpu_ctx* ctx, uint16_t* d2_out);
 /* device pointer + byte size of the resident field, for a torch.distributed broadcast */
 int smplgpu_distance_field_dev_ptr(smplgpu_ctx* ctx, void** ptr, int64_t* bytes);
 
+/* Room for an nx*ny*nz field on the device WITHOUT contents, so that a peer's field can be received straight into
+ * it (one NCCL broadcast per scene update, SURVEY.md section 8e: no host hop, no staging copy); follow with
+ * smplgpu_set_distance_field_dev(ctx, *ptr, ...), which then adopts the buffer in place. */
+int smplgpu_reserve_distance_field(smplgpu_ctx* ctx, int nx, int ny, int nz, void** ptr, int64_t* bytes);
+/* Pin the field in L2 with an access-policy window on the context's current stream (on = 1) or drop the window
+ * (on = 0): for fields of tens of MB (the 36 MB 1 cm field of BASELINE config 4) while hundreds of MB of states
+ * stream through the same cache.  set_aside_mb (nullable) receives the persisting carve-out. */
+int smplgpu_set_distance_field_l2_persistence(smplgpu_ctx* ctx, int on, double* set_aside_mb);
+
 /* ---- validity (CollisionChecker) ------------------------------------------ */
 /* CollisionSpace::isStateValid batched (collision_space.cpp:532-536 -> 479-488);
  * verdict[i] = 1 valid / 0 invalid */
@@ -339,6 +348,21 @@ int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double
                                 int cost_per_cell, int buffer);
 int smplgpu_expand_batch_wait(smplgpu_ctx* ctx, int buffer, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells,
                               double* offset_xyz);
+
+/* ---- lattice states on the wire as 16-bit coordinates ---- */
+/* The real caller of the validity path, ManipLattice, holds a state as dof small integers (RobotCoord) and forms the
+ * joint values with coordToState (manip_lattice.cpp:1245-1261).  These entry points take the coordinates and do
+ * that on the device with the reference's expression (coord * delta, + min limit for bounded variables), so a state
+ * costs 2 dof bytes on the bus instead of 8 dof, an edge one more byte (its motion primitive).  Verdicts equal
+ * smplgpu_is_states_valid / smplgpu_is_mprim_edges_valid on coordToState(coords); arbitrary (off-lattice) states keep
+ * using those. */
+/* ManipLattice::init discretisation (manip_lattice.cpp:125-139) from resolutions[dof] and the robot's limits;
+ * coord_vals[dof] (nullable) receives the number of lattice values per variable */
+int smplgpu_set_lattice(smplgpu_ctx* ctx, const double* resolutions, int32_t* coord_vals);
+int smplgpu_is_lattice_states_valid(smplgpu_ctx* ctx, const int16_t* coords, int n, uint8_t* verdict);
+/* edge i: coordToState(parent_coords[i]) -> that + deltas[prim_id[i]] (prim_id >= n_prims: zero-length edge) */
+int smplgpu_is_lattice_edges_valid(smplgpu_ctx* ctx, const int16_t* parent_coords, const uint8_t* prim_id, int n,
+                                   const double* deltas, int n_prims, uint8_t* verdict, int32_t* waypoint_counts);
 
 /* ---- one expansion at a time, for UNCHANGED callers (ManipLattice::GetSuccs + ARAStar::expand) ---- */
 /* The reference's search asks its plug-ins ~65 questions per expansion, one virtual call each

@@ -115,6 +115,11 @@ def gpu_lib():
         L.smplgpu_bfs_bank_distances.argtypes = [vp, ip, ip, i, ip]
         L.smplgpu_expand_batch.argtypes = [vp, dp, dp, ip, i, i, bp, ip, ip, dp]
         L.smplgpu_set_motion_primitives.argtypes = [vp, dp, i]
+        L.smplgpu_set_lattice.argtypes = [vp, dp, ip]
+        L.smplgpu_reserve_distance_field.argtypes = [vp, i, i, i, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.smplgpu_set_distance_field_l2_persistence.argtypes = [vp, i, dp]
+        L.smplgpu_is_lattice_states_valid.argtypes = [vp, C.POINTER(C.c_int16), i, bp]
+        L.smplgpu_is_lattice_edges_valid.argtypes = [vp, C.POINTER(C.c_int16), bp, i, dp, i, bp, ip]
         L.smplgpu_expand_state.argtypes = [vp, dp, i, C.POINTER(C.POINTER(SuccInfoC))]
         L.smplgpu_scene_epoch.restype = C.c_int64
         L.smplgpu_scene_epoch.argtypes = [vp]
@@ -380,6 +385,18 @@ class GpuContext:
         return p.value, n.value
 
     # ---- validity ----
+    def reserve_distance_field(self, dims):
+        """Device room for a field of `dims` (contents to be received from a peer); -> (pointer, bytes)."""
+        ptr, nb = C.c_void_p(), C.c_int64()
+        self._ck(self.L.smplgpu_reserve_distance_field(self.h, int(dims[0]), int(dims[1]), int(dims[2]), C.byref(ptr),
+                                                       C.byref(nb)), "reserve_distance_field")
+        return ptr.value, nb.value
+
+    def set_distance_field_l2_persistence(self, on):
+        mb = C.c_double()
+        self._ck(self.L.smplgpu_set_distance_field_l2_persistence(self.h, int(bool(on)), C.byref(mb)), "l2_persistence")
+        return mb.value
+
     def _q(self, q):
         return np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.dof)
 
@@ -576,6 +593,31 @@ class GpuContext:
                                              _ip(g), _dp(off)), "expand_batch")
         return v, h, g, off
 
+
+    def set_lattice(self, resolutions):
+        """ManipLattice::init discretisation; returns the number of lattice values per variable."""
+        r = np.ascontiguousarray(resolutions, dtype=np.float64)
+        vals = np.zeros(len(r), np.int32)
+        self._ck(self.L.smplgpu_set_lattice(self.h, _dp(r), _ip(vals)), "set_lattice")
+        return vals
+
+    def is_lattice_states_valid(self, coords):
+        c = np.ascontiguousarray(coords, dtype=np.int16)
+        v = np.zeros(len(c), np.uint8)
+        self._ck(self.L.smplgpu_is_lattice_states_valid(self.h, c.ctypes.data_as(C.POINTER(C.c_int16)), len(c), _bp(v)),
+                 "is_lattice_states_valid")
+        return v
+
+    def is_lattice_edges_valid(self, coords, prim_id, deltas, want_counts=True):
+        c = np.ascontiguousarray(coords, dtype=np.int16)
+        p = np.ascontiguousarray(prim_id, dtype=np.uint8)
+        d = np.ascontiguousarray(deltas, dtype=np.float64)
+        v = np.zeros(len(c), np.uint8)
+        cnt = np.zeros(len(c), np.int32) if want_counts else None
+        self._ck(self.L.smplgpu_is_lattice_edges_valid(self.h, c.ctypes.data_as(C.POINTER(C.c_int16)), _bp(p), len(c), _dp(d),
+                                                       len(d), _bp(v), _ip(cnt) if want_counts else None),
+                 "is_lattice_edges_valid")
+        return (v, cnt) if want_counts else v
 
     def set_motion_primitives(self, deltas):
         d = np.ascontiguousarray(deltas, dtype=np.float64)

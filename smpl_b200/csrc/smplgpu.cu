@@ -114,6 +114,12 @@ struct smplgpu_ctx
     // bumped whenever an answer of the validity / heuristic entry points may change (robot, field, walls, BFS run):
     // host-side caches of such answers (smplhost::ExpansionCache) compare it
     int64_t scene_epoch = 0;
+    // lattice discretisation (smplgpu_set_lattice) and staging of 16-bit coordinates / 8-bit primitive ids
+    bool has_lattice = false;
+    LatticeParams lattice{};
+    int lattice_vals[MAX_DOF] = { };
+    int16_t* d_coord = nullptr; size_t coord_cap = 0;   // bytes, two chunks
+    uint8_t* d_prim8 = nullptr; size_t prim8_cap = 0;
     // smplgpu_expand_state: primitive table, page-locked record array + completion flag, arrival counter
     double* d_x1_deltas = nullptr; int x1_prims = -1;
     smplgpu_succ_info* x1_out = nullptr; size_t x1_out_cap = 0;   // records; the flag word follows them
@@ -323,6 +329,7 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
     if (ctx->ev_bfs) cudaEventDestroy(ctx->ev_bfs);
     cudaFree(ctx->d_bank_stage); cudaFree(ctx->d_bank_seed_count);
     cudaFree(ctx->d_x1_deltas); cudaFree(ctx->d_x1_done);
+    cudaFree(ctx->d_coord); cudaFree(ctx->d_prim8);
     if (ctx->x1_out) cudaFreeHost(ctx->x1_out);
     if (ctx->h_bank_stage) cudaFreeHost(ctx->h_bank_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1117,6 +1124,63 @@ int smplgpu_distance_field_dev_ptr(smplgpu_ctx* ctx, void** ptr, int64_t* bytes)
     return 0;
 }
 
+int smplgpu_reserve_distance_field(smplgpu_ctx* ctx, int nx, int ny, int nz, void** ptr, int64_t* bytes)
+{
+    if (!ctx || !ptr || !bytes) return SMPLGPU_ERR_INVALID;
+    if (nx <= 0 || ny <= 0 || nz <= 0) return fail(ctx, SMPLGPU_ERR_INVALID, "bad distance field dimensions");
+    {
+        const int fr = finish_bank_run(ctx);
+        if (fr) return fr;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    const size_t cells = (size_t)nx * ny * nz;
+    if (cells != ctx->df_cells) {
+        ctx->has_df = false;
+        ctx->has_bank = false;
+        if (ctx->d_df) { CU(cudaFree(ctx->d_df)); ctx->d_df = nullptr; ctx->df_cells = 0; }
+        CU(cudaMalloc(&ctx->d_df, cells * sizeof(uint16_t)));
+        ctx->df_cells = cells;
+    }
+    ++ctx->scene_epoch;
+    *ptr = ctx->d_df;
+    *bytes = (int64_t)(cells * sizeof(uint16_t));
+    return 0;
+}
+
+int smplgpu_set_distance_field_l2_persistence(smplgpu_ctx* ctx, int on, double* set_aside_mb)
+{
+    if (!ctx) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "no distance field");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    double mb = 0.0;
+    if (on) {
+        const size_t bytes = ctx->df_cells * sizeof(uint16_t);
+        const size_t set_aside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes);
+        if (set_aside == 0) return fail(ctx, SMPLGPU_ERR_LIMIT, "device has no persisting L2");
+        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+        const size_t window = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+        attr.accessPolicyWindow.base_ptr = ctx->d_df;
+        attr.accessPolicyWindow.num_bytes = window;
+        attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)window);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        mb = (double)set_aside / 1e6;
+    } else {
+        attr.accessPolicyWindow.num_bytes = 0;   // disables the window
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    CU(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    if (!on) {
+        CU(cudaCtxResetPersistingL2Cache());
+    }
+    if (set_aside_mb) *set_aside_mb = mb;
+    return 0;
+}
+
 ///////////////////////////////////////////////////////////////////////////////
 // validity
 ///////////////////////////////////////////////////////////////////////////////
@@ -1244,6 +1308,106 @@ static bool is_pinned_host(const void* p)
     return a.type == cudaMemoryTypeHost;
 }
 
+// The same pipeline for lattice states: item i is dof 16-bit coordinates (ManipLattice::coordToState gives the
+// joint values on the device), an edge adds one byte of motion-primitive id.  29 bytes per (state + edge) pair
+// cross the bus instead of 116.
+static int run_host_batched_lattice(smplgpu_ctx* ctx, const int16_t* coords, const uint8_t* prim8, bool edges, int n,
+                                    uint8_t* verdict, int32_t* counts, const double* d_deltas, int n_prims)
+{
+    const int dof = ctx->h_model->dof;
+    static const int chunk = [] {
+        const char* e = getenv("SMPLGPU_HOST_CHUNK");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1024 ? v : (1 << 18);
+    }();
+    const int cn = std::min(n, chunk);
+    int r = ensure_state_buffers(ctx, (size_t)cn * 2, dof, edges);
+    if (r) return r;
+    const size_t row = (size_t)dof * sizeof(int16_t);
+    if ((r = grow(ctx, (void**)&ctx->d_coord, &ctx->coord_cap, (size_t)cn * 2 * row))) return r;
+    if (edges && (r = grow(ctx, (void**)&ctx->d_prim8, &ctx->prim8_cap, (size_t)cn * 2))) return r;
+    const bool in_direct = is_pinned_host(coords) && (!edges || is_pinned_host(prim8));
+    const bool out_direct = is_pinned_host(verdict) && (!counts || is_pinned_host(counts));
+    if (!in_direct) {
+        if ((r = grow_pinned(ctx, ctx->pinned, &ctx->pinned_cap, (size_t)cn * (row + 1)))) return r;
+    }
+    if (!out_direct) {
+        if ((r = grow_pinned(ctx, ctx->pinned_out, &ctx->pinned_out_cap, (size_t)cn * (1 + (counts ? sizeof(int) : 0)) + 16))) return r;
+    }
+    CU(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaEventRecord(ctx->ev_in[0], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_in[0], 0));
+    const int nchunks = (n + chunk - 1) / chunk;
+    auto drain = [&](int c) -> int {
+        const int b = c & 1;
+        const int off = c * chunk;
+        const int m = std::min(chunk, n - off);
+        CU(cudaEventSynchronize(ctx->ev[b]));
+        memcpy(verdict + off, ctx->pinned_out[b], (size_t)m);
+        if (counts) {
+            memcpy(counts + off, (uint8_t*)ctx->pinned_out[b] + (((size_t)m + 15) / 16) * 16, (size_t)m * sizeof(int));
+        }
+        return 0;
+    };
+    for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1;
+        const int off = c * chunk;
+        const int m = std::min(chunk, n - off);
+        double* dq0 = ctx->d_q0 + (size_t)b * cn * dof;
+        double* dq1 = ctx->d_q1 + (size_t)b * cn * dof;
+        uint8_t* dv = ctx->d_verdict + (size_t)b * cn;
+        int* dc = ctx->d_counts + (size_t)b * cn;
+        int16_t* dcoord = ctx->d_coord + (size_t)b * cn * dof;
+        uint8_t* dprim = edges ? ctx->d_prim8 + (size_t)b * cn : nullptr;
+        if (c >= 2) {
+            if (!out_direct) {
+                if ((r = drain(c - 2))) return r;
+            } else if (!in_direct) {
+                CU(cudaEventSynchronize(ctx->ev[b]));
+            }
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[b], 0));
+        }
+        const void* s0 = coords + (size_t)off * dof;
+        const void* s1 = edges ? prim8 + off : nullptr;
+        if (!in_direct) {
+            uint8_t* pin = (uint8_t*)ctx->pinned[b];
+            memcpy(pin, s0, (size_t)m * row);
+            s0 = pin;
+            if (edges) {
+                memcpy(pin + (size_t)cn * row, s1, (size_t)m);
+                s1 = pin + (size_t)cn * row;
+            }
+        }
+        CU(cudaMemcpyAsync(dcoord, s0, (size_t)m * row, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (edges) {
+            CU(cudaMemcpyAsync(dprim, s1, (size_t)m, cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+        CU(cudaEventRecord(ctx->ev_in[b], ctx->copy_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        const size_t total = (size_t)m * dof;
+        lattice_states_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+            dcoord, dprim, d_deltas, n_prims, ctx->lattice, dof, m, dq0, edges ? dq1 : nullptr);
+        ++ctx->launches;
+        r = edges ? launch_edges(ctx, dq0, dq1, m, dv, counts ? dc : nullptr) : launch_states(ctx, dq0, m, dv);
+        if (r) return r;
+        uint8_t* ov = out_direct ? verdict + off : (uint8_t*)ctx->pinned_out[b];
+        CU(cudaMemcpyAsync(ov, dv, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (counts) {
+            void* oc = out_direct ? (void*)(counts + off) : (void*)((uint8_t*)ctx->pinned_out[b] + (((size_t)m + 15) / 16) * 16);
+            CU(cudaMemcpyAsync(oc, dc, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CU(cudaEventRecord(ctx->ev[b], ctx->stream));
+    }
+    if (!out_direct) {
+        for (int c = std::max(0, nchunks - 2); c < nchunks; ++c) {
+            if ((r = drain(c))) return r;
+        }
+    }
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // Host-pointer entry points.  The batch is cut into chunks; the host->device copy of chunk k+1 runs on a
 // second stream while the kernels of chunk k run, and verdicts stream back behind the kernels.  Page-locked
 // caller buffers are used as DMA source / target directly; pageable ones go through pinned staging.
@@ -1251,9 +1415,13 @@ static bool is_pinned_host(const void* p)
 // the bus, the successors are formed on the device from the primitive table `d_deltas`.
 static int run_host_batched(smplgpu_ctx* ctx, const double* q0, const double* q1, int n,
                             uint8_t* verdict, int32_t* counts, const int32_t* prim_id = nullptr,
-                            const double* d_deltas = nullptr, int n_prims = 0)
+                            const double* d_deltas = nullptr, int n_prims = 0,
+                            const int16_t* coords = nullptr, const uint8_t* prim8 = nullptr, bool coord_edges = false)
 {
     const int dof = ctx->h_model->dof;
+    if (coords != nullptr) {
+        return run_host_batched_lattice(ctx, coords, prim8, coord_edges, n, verdict, counts, d_deltas, n_prims);
+    }
     const bool by_prim = prim_id != nullptr;
     const bool edges = q1 != nullptr || by_prim;
     static const int chunk = [] {
@@ -2314,6 +2482,73 @@ int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, c
     if (r < 0) return r;
     r = smplgpu_expand_batch_wait(ctx, 0, verdict, h, goal_dist_cells, offset_xyz);
     return r < 0 ? r : 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// lattice states: 16-bit coordinates on the wire
+///////////////////////////////////////////////////////////////////////////////
+
+int smplgpu_set_lattice(smplgpu_ctx* ctx, const double* resolutions, int32_t* coord_vals)
+{
+    if (!ctx || !resolutions) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set (smplgpu_set_robot)");
+    const DevModel& m = *ctx->h_model;
+    ctx->has_lattice = false;
+    for (int v = 0; v < m.dof; ++v) {
+        const double res = resolutions[v];
+        if (!(res > 0.0)) return fail(ctx, SMPLGPU_ERR_INVALID, "resolution of variable %d is not positive", v);
+        int vals;
+        double delta;
+        if (m.var_type[v] == SMPLGPU_VAR_CONTINUOUS) {          // manip_lattice.cpp:127-129
+            vals = (int)std::round((2.0 * M_PI) / res);
+            delta = (2.0 * M_PI) / (double)vals;
+            ctx->lattice.bounded[v] = 0;
+            ctx->lattice.base[v] = 0.0;
+        } else {                                                 // :130-133 (every KDL planning variable has limits)
+            const double span = std::fabs(m.var_max[v] - m.var_min[v]);
+            vals = std::max(1, (int)std::round(span / res));
+            delta = span / (double)vals;
+            ctx->lattice.bounded[v] = 1;
+            ctx->lattice.base[v] = m.var_min[v];
+        }
+        if (vals > 32767) return fail(ctx, SMPLGPU_ERR_LIMIT, "variable %d has %d lattice values: more than 16-bit coordinates hold", v, vals);
+        ctx->lattice.delta[v] = delta;
+        ctx->lattice_vals[v] = vals;
+        if (coord_vals) coord_vals[v] = vals;
+    }
+    ctx->has_lattice = true;
+    return 0;
+}
+
+int smplgpu_is_lattice_states_valid(smplgpu_ctx* ctx, const int16_t* coords, int n, uint8_t* verdict)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (!ctx->has_lattice) return fail(ctx, SMPLGPU_ERR_STATE, "lattice resolutions not set (smplgpu_set_lattice)");
+    if (n == 0) return 0;
+    if (!coords || !verdict) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    return run_host_batched(ctx, nullptr, nullptr, n, verdict, nullptr, nullptr, nullptr, 0, coords, nullptr, false);
+}
+
+int smplgpu_is_lattice_edges_valid(smplgpu_ctx* ctx, const int16_t* parent_coords, const uint8_t* prim_id, int n,
+                                   const double* deltas, int n_prims, uint8_t* verdict, int32_t* waypoint_counts)
+{
+    if (!ctx || n < 0 || n_prims < 0 || n_prims > 255) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (!ctx->has_lattice) return fail(ctx, SMPLGPU_ERR_STATE, "lattice resolutions not set (smplgpu_set_lattice)");
+    if (n == 0) return 0;
+    if (!parent_coords || !prim_id || !verdict || (n_prims > 0 && !deltas)) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    const size_t bytes = (size_t)std::max(1, n_prims) * ctx->h_model->dof * sizeof(double);
+    r = grow(ctx, (void**)&ctx->d_deltas, &ctx->deltas_cap, bytes);
+    if (r) return r;
+    if (n_prims > 0) {
+        CU(cudaMemcpyAsync(ctx->d_deltas, deltas, (size_t)n_prims * ctx->h_model->dof * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return run_host_batched(ctx, nullptr, nullptr, n, verdict, waypoint_counts, nullptr, ctx->d_deltas, n_prims, parent_coords,
+                            prim_id, true);
 }
 
 ///////////////////////////////////////////////////////////////////////////////

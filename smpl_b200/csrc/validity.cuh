@@ -471,6 +471,36 @@ __global__ void apply_mprims_kernel(const double* __restrict__ q0, const int* __
     q1[i] = (p >= 0 && p < n_prims) ? deltas[(size_t)p * dof + v] + a : a;
 }
 
+// ManipLattice::coordToState (manip_lattice.cpp:1245-1261) for a batch of lattice coordinates, and -- for edges --
+// the successor parent + delta of the edge's motion primitive: a lattice state crosses the bus as dof 16-bit
+// coordinates (plus one byte of primitive id per edge) instead of dof doubles.
+struct LatticeParams
+{
+    double base[MAX_DOF];    // m_min_limits for bounded variables, 0 for continuous ones
+    double delta[MAX_DOF];   // m_coord_deltas
+    int bounded[MAX_DOF];    // adds `base` (the reference's two branches differ in the addition only)
+};
+
+__global__ void lattice_states_kernel(const int16_t* __restrict__ coords, const uint8_t* __restrict__ prim,
+                                      const double* __restrict__ deltas, int n_prims, LatticeParams L, int dof, int n,
+                                      double* __restrict__ q0, double* __restrict__ q1)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * dof) {
+        return;
+    }
+    const int e = (int)(i / dof), v = (int)(i - (size_t)e * dof);
+    const int c = coords[i];
+    // state[i] = coord[i] * m_coord_deltas[i]   |   m_min_limits[i] + coord[i] * m_coord_deltas[i]
+    const double prod = (double)c * L.delta[v];
+    const double a = L.bounded[v] ? L.base[v] + prod : prod;
+    q0[i] = a;
+    if (q1 != nullptr) {
+        const int p = prim[e];
+        q1[i] = p < n_prims ? deltas[(size_t)p * dof + v] + a : a;
+    }
+}
+
 // Edges between rows of a point table (path post-processing: every (i, j) pair of a path's points is a candidate
 // shortcut, post_processing.cpp:99-121): q0[e] = points[a[e]], q1[e] = points[b[e]]
 __global__ void gather_edges_kernel(const double* __restrict__ points, const int* __restrict__ a,

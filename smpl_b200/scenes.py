@@ -349,3 +349,37 @@ def ubr1_tabletop_queries(n, seed=13):
     goals = lo + rng.random((n, 3)) * np.array([0.6, 1.0, 0.5])
     starts = np.tile(np.array(UBR1_DEMO_START, np.float64), (n, 1))
     return np.ascontiguousarray(starts), np.ascontiguousarray(goals)
+
+
+def lattice_discretisation(lo, hi, cont, resolutions):
+    """ManipLattice::init (manip_lattice.cpp:125-139): (coord_vals, coord_deltas, base) per planning variable."""
+    vals, deltas, base = [], [], []
+    for a, b, c, r in zip(lo, hi, cont, resolutions):
+        if c:
+            v = int(round((2.0 * math.pi) / r))
+            vals.append(v)
+            deltas.append((2.0 * math.pi) / float(v))
+            base.append(None)
+        else:
+            span = abs(b - a)
+            v = max(1, int(round(span / r)))
+            vals.append(v)
+            deltas.append(span / float(v))
+            base.append(a)
+    return np.array(vals, np.int32), np.array(deltas), base
+
+
+def random_lattice_coords(n, lo, hi, cont, resolutions, seed):
+    """n uniformly random lattice states as ManipLattice holds them (RobotCoord, 16-bit here) and their joint values
+    by ManipLattice::coordToState (manip_lattice.cpp:1245-1261): coord * delta (+ min limit for bounded variables)."""
+    vals, deltas, base = lattice_discretisation(lo, hi, cont, resolutions)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    coords = np.empty((n, len(vals)), np.int16)
+    q = np.empty((n, len(vals)), np.float64)
+    for v in range(len(vals)):
+        # bounded variables: 0 .. vals inclusive (both limits are lattice states); continuous: 0 .. vals - 1
+        c = rng.integers(0, vals[v] + (0 if base[v] is None else 1), n)
+        coords[:, v] = c
+        prod = c.astype(np.float64) * deltas[v]
+        q[:, v] = prod if base[v] is None else base[v] + prod
+    return coords, q

@@ -34,6 +34,34 @@ def broadcast_distance_field(d2, dims, src=0, device=None):
     return t
 
 
+class _DevicePointer:
+    """A raw device allocation as a zero-copy torch tensor (CUDA array interface, bytes)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def wrap_pointer(ptr, nbytes, device=None):
+    """uint8 tensor over `nbytes` at `ptr` without a copy: device memory when `device` is a CUDA device, else host
+    memory (the gloo tests)."""
+    import torch
+    if device is not None and torch.device(device).type == "cuda":
+        return torch.as_tensor(_DevicePointer(ptr, nbytes), device=device)
+    import ctypes
+    buf = (ctypes.c_uint8 * int(nbytes)).from_address(int(ptr))
+    return torch.from_numpy(np.frombuffer(buf, dtype=np.uint8))
+
+
+def broadcast_field_in_place(ptr, nbytes, src=0, device=None):
+    """The one collective of a scene update, device to device: rank `src`'s resident field (its own buffer, e.g.
+    smplgpu_distance_field_dev_ptr) is broadcast straight into every other rank's reserved buffer
+    (smplgpu_reserve_distance_field) -- no host hop, no staging tensor.  Returns the wrapped tensor."""
+    import torch.distributed as dist
+    t = wrap_pointer(ptr, nbytes, device)
+    dist.broadcast(t, src=src)
+    return t
+
+
 def gather_counts(local_value, device=None):
     """Sum of a per-rank scalar (units processed) and max of a per-rank time, as bench.py reports them."""
     import torch

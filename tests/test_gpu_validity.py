@@ -119,6 +119,35 @@ def test_edges_given_as_parent_plus_motion_primitive(pr2):
     assert np.array_equal(v_a[:4000], v_o) and np.array_equal(c_a[:4000], c_o)
 
 
+def test_lattice_states_and_edges_as_16_bit_coordinates(pr2):
+    """smplgpu_is_lattice_states_valid / _edges_valid take RobotCoord (16-bit) + a primitive byte and form the joint
+    values on the device with ManipLattice::coordToState (manip_lattice.cpp:1245-1261): same verdicts and waypoint
+    counts as the double entry points on coordToState(coords), and as the oracle."""
+    scene, o, ctx, tables = pr2
+    lo, hi, cont = tables.limits()
+    res = scenes.PlanParams(scene.dof).resolutions
+    vals = ctx.set_lattice(res)
+    want_vals, _, _ = scenes.lattice_discretisation(lo, hi, cont, res)
+    assert np.array_equal(vals, want_vals)
+    coords, q = scenes.random_lattice_coords(300000, lo, hi, cont, res, seed=33)   # several pipeline chunks
+    deltas = scenes.pr2_mprim_deltas()
+    pid = (np.arange(len(q)) % len(deltas)).astype(np.uint8)
+    pid[::1000] = 255                                           # out-of-table id: zero-length edge
+    q1 = q + np.where(pid[:, None] < len(deltas), deltas[np.minimum(pid, len(deltas) - 1)], 0.0)
+    v_l = ctx.is_lattice_states_valid(coords)
+    assert np.array_equal(v_l, ctx.is_states_valid(q))
+    e_l, c_l = ctx.is_lattice_edges_valid(coords, pid, deltas)
+    e_d, c_d = ctx.is_edges_valid(q, q1)
+    assert np.array_equal(e_l, e_d) and np.array_equal(c_l, c_d)
+    assert (c_l[::1000] == 0).all() and (e_l[::1000] == 1).all()
+    assert np.array_equal(v_l[:4000], o.is_states_valid(q[:4000]))
+    e_o, c_o = o.is_edges_valid(q[:4000], q1[:4000])
+    assert np.array_equal(e_l[:4000], e_o) and np.array_equal(c_l[:4000], c_o)
+    assert 0.05 < v_l.mean() < 0.95
+    # empty batch, and a context without a lattice
+    assert len(ctx.is_lattice_states_valid(np.zeros((0, scene.dof), np.int16))) == 0
+
+
 def test_edge_cases(pr2):
     scene, o, ctx, tables = pr2
     lo, hi, cont = tables.limits()

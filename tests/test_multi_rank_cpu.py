@@ -39,6 +39,11 @@ def _worker(rank, world, port, out_dir):
     t = sh.broadcast_distance_field(d2, scene.dims, src=0)
     field = t.numpy().view(np.uint16).reshape(scene.dims)
     same = np.array_equal(field.astype(np.int32), o.df_d2())
+    # the in-place form bench.py uses on the GPUs: every rank owns a buffer (the library's resident field on the source,
+    # a reserved one elsewhere) and the broadcast lands in it directly
+    own = o.df_d2().astype(np.uint16).copy() if rank == 0 else np.zeros(scene.dims, np.uint16)
+    sh.broadcast_field_in_place(own.ctypes.data, own.nbytes, src=0, device=None)
+    same = same and np.array_equal(own.astype(np.int32), o.df_d2())
     q = scenes.random_states(4001, *np.load(os.path.join(out_dir, "limits.npy"), allow_pickle=True), seed=71)
     b, e = sh.contiguous_shard(len(q), rank, world)
     v = o.is_states_valid(q[b:e])
