@@ -349,6 +349,48 @@ int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double
 int smplgpu_expand_batch_wait(smplgpu_ctx* ctx, int buffer, uint8_t* verdict, int32_t* h, int32_t* goal_dist_cells,
                               double* offset_xyz);
 
+/* ---- the lattice of many concurrent queries, resident on the device ---- */
+/* What ManipLattice::GetSuccs does besides the edge check -- apply the active motion primitives, joint limits,
+ * stateToCoord, getOrCreateState (the coordinate hash table), isGoal -- and the per-successor GetGoalHeuristic run on
+ * the device for every query in flight (manip_lattice.cpp:219-313, 1263-1356, 1511-1580, 1673-1687;
+ * manip_lattice_action_space.cpp:376-449, 662-691; arastar.cpp:613-618).  A round ships 8 bytes per expansion (bank
+ * slot, state id) and returns one word pair per successor.  State ids are handed out in the reference's creation
+ * order (id 0 = the goal state, 1 = the start state), so the host's ARA* -- OPEN list and search states indexed by
+ * these ids -- returns the reference's paths, costs and expansion counts.  One lattice per BFS bank slot. */
+typedef struct smplgpu_lattice_params {
+    const double*  resolutions;      /* [dof] ManipLattice::init discretisation (manip_lattice.cpp:125-139) */
+    const double*  deltas;           /* [n_prims][dof], converses included, table order */
+    const uint8_t* prim_short;       /* [n_prims] 1 = short-distance primitive */
+    int32_t n_prims;
+    int32_t use_short_dist;
+    double  short_dist_thresh;       /* metres (mprimActive, manip_lattice_action_space.cpp:674-687) */
+    double  xyz_tolerance[3];        /* GoalConstraint::xyz_tolerance */
+    int32_t cost_per_cell;
+    int32_t max_states;              /* room per query; a query creates at most 2 + expansions * stride states */
+} smplgpu_lattice_params;
+#define SMPLGPU_LATTICE_GOAL_FLAG (1 << 30)   /* in a successor word: the action reaches the goal region */
+/* largest n_slots smplgpu_lattice_create can hold in the free device memory */
+int smplgpu_lattice_max_slots(smplgpu_ctx* ctx, int max_states);
+/* returns the stride: successor words per expansion = max(#long, #short primitives) */
+int smplgpu_lattice_create(smplgpu_ctx* ctx, const smplgpu_lattice_params* params, int n_slots);
+/* setGoal + setStart bookkeeping for n queries: slot[i] gets an empty lattice, goal position goals_xyz[i] and start
+ * state starts[i] (id 1) whose metric goal distance is start_goal_dist_cells[i] (smplgpu_expand_batch reports it).
+ * The slot's BFS (smplgpu_bfs_bank_run_slots*) must have run. */
+int smplgpu_lattice_begin(smplgpu_ctx* ctx, const int32_t* slots, const double* starts,
+                          const int32_t* start_goal_dist_cells, const double* goals_xyz, int n);
+/* One round: expansion i expands state parent_id[i] of the query in slot[i] (at most one expansion per slot and
+ * round).  submit queues the work and returns; wait blocks and hands out pointers into page-locked memory valid
+ * until the next submit on `buffer` (0 .. SMPLGPU_EXPAND_BUFFERS - 1):
+ *   succ[i * stride + j]  id of the j-th active primitive's successor | SMPLGPU_LATTICE_GOAL_FLAG, or -1 when the
+ *                         primitive is inactive, leaves the joint limits or its edge is in collision
+ *   h[i * stride + j]     BfsHeuristic::GetGoalHeuristic of that successor
+ *   count[i]              lattice size of the query after this expansion */
+int smplgpu_lattice_expand_submit(smplgpu_ctx* ctx, const int32_t* slot, const int32_t* parent_id, int n, int buffer);
+int smplgpu_lattice_expand_wait(smplgpu_ctx* ctx, int buffer, const int32_t** succ, const int32_t** h,
+                                const int32_t** count);
+/* joint values of lattice states (ManipLattice::extractPath): q_out[i] = state id[i] of slot[i] */
+int smplgpu_lattice_states(smplgpu_ctx* ctx, const int32_t* slot, const int32_t* id, int n, double* q_out);
+
 /* ---- lattice states on the wire as 16-bit coordinates ---- */
 /* The real caller of the validity path, ManipLattice, holds a state as dof small integers (RobotCoord) and forms the
  * joint values with coordToState (manip_lattice.cpp:1245-1261).  These entry points take the coordinates and do

@@ -44,7 +44,6 @@ struct LatticeBank
     const double* deltas;     // [n_prims][dof]
     const int* long_list;     // primitive indices in table order
     const int* short_list;
-    int* overflow;    // set when a slot ran out of room
 };
 
 // ManipLattice::stateToCoord (manip_lattice.cpp:1263-1289; every KDL planning variable is continuous or bounded)
@@ -122,9 +121,12 @@ __global__ void lattice_begin_kernel(const DevModel* __restrict__ M, LatticeBank
 // edge kernels) and are flagged.
 __global__ void lattice_gen_kernel(const DevModel* __restrict__ M, LatticeBank B, const int* __restrict__ slot,
                                    const int* __restrict__ parent, int n, double* __restrict__ q0,
-                                   double* __restrict__ q1, uint8_t* __restrict__ active)
+                                   double* __restrict__ q1, uint8_t* __restrict__ active, unsigned long long* stats)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 4) {
+        stats[t] = 0;   // counters of the edge kernels that follow (saves a memset call per round)
+    }
     if (t >= n * B.stride) {
         return;
     }
@@ -163,7 +165,8 @@ lattice_commit_kernel(const DevModel* __restrict__ M, GridParams G, LatticeBank 
                       const int* __restrict__ bfs, int dimx, int dimy, int slot_dimz,
                       const int* __restrict__ slot, int n, const double* __restrict__ q1,
                       const uint8_t* __restrict__ active, const uint8_t* __restrict__ verdict,
-                      int* __restrict__ out_succ, int* __restrict__ out_h, int* __restrict__ out_count)
+                      int* __restrict__ out_succ, int* __restrict__ out_h, int* __restrict__ out_count,
+                      const unsigned long long* __restrict__ stats)
 {
     const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -194,6 +197,7 @@ lattice_commit_kernel(const DevModel* __restrict__ M, GridParams G, LatticeBank 
         hv = coord_hash(c, dof);
     }
     int id = -1;
+    bool full = false;
     unsigned int todo = __ballot_sync(0xffffffffu, valid);
     int* table = B.table + (size_t)s * B.table_size;
     const unsigned int mask = (unsigned int)(B.table_size - 1);
@@ -221,7 +225,7 @@ lattice_commit_kernel(const DevModel* __restrict__ M, GridParams G, LatticeBank 
             if (id < 0) {
                 const int fresh = B.count[s];
                 if (fresh >= B.cap) {
-                    *B.overflow = 1;
+                    full = true;
                 } else {
                     B.count[s] = fresh + 1;
                     double* qq = B.q + ((size_t)s * B.cap + fresh) * dof;
@@ -242,9 +246,14 @@ lattice_commit_kernel(const DevModel* __restrict__ M, GridParams G, LatticeBank 
         out_succ[t] = id < 0 ? -1 : (id | (is_goal ? LATTICE_GOAL_FLAG : 0));
         out_h[t] = h;
     }
-    __syncwarp();
+    full = __any_sync(0xffffffffu, full);
     if (lane == 0) {
-        out_count[i] = B.count[s];
+        out_count[i] = full ? -1 : B.count[s];   // -1: the query ran out of room (the caller sized it too small)
+    }
+    if (i == 0 && lane == 0) {
+        // edges of this round that the double-precision pass resolved, behind the counts (8-byte slot)
+        unsigned long long* tail = reinterpret_cast<unsigned long long*>(out_count + ((n + 1) & ~1));
+        *tail = stats[3];
     }
 }
 

@@ -23,6 +23,7 @@
 #include "validity.cuh"
 #include "validity32.cuh"
 #include "expand1.cuh"
+#include "lattice.cuh"
 
 using namespace smplgpu;
 
@@ -120,6 +121,17 @@ struct smplgpu_ctx
     int lattice_vals[MAX_DOF] = { };
     int16_t* d_coord = nullptr; size_t coord_cap = 0;   // bytes, two chunks
     uint8_t* d_prim8 = nullptr; size_t prim8_cap = 0;
+    // device-resident lattices (smplgpu_lattice_*): one per bank slot
+    bool has_lat = false;
+    LatticeBank lat{};
+    LatticeParams lat_params{};
+    LatticeVals lat_vals{};
+    void* d_lat_aux = nullptr;              // deltas | long list | short list
+    void* lat_in[SMPLGPU_EXPAND_BUFFERS] = { };  size_t lat_in_cap[SMPLGPU_EXPAND_BUFFERS] = { };   // pinned, mapped: slot | parent
+    void* lat_out[SMPLGPU_EXPAND_BUFFERS] = { }; size_t lat_out_cap[SMPLGPU_EXPAND_BUFFERS] = { };  // pinned, mapped: succ | h | count | resolved
+    void* d_lat[SMPLGPU_EXPAND_BUFFERS] = { };   size_t d_lat_cap[SMPLGPU_EXPAND_BUFFERS] = { };    // q0 | q1 | active | verdict
+    int lat_n[SMPLGPU_EXPAND_BUFFERS] = { -1, -1, -1, -1 };
+    int lat_max_n = 0;
     // smplgpu_expand_state: primitive table, page-locked record array + completion flag, arrival counter
     double* d_x1_deltas = nullptr; int x1_prims = -1;
     smplgpu_succ_info* x1_out = nullptr; size_t x1_out_cap = 0;   // records; the flag word follows them
@@ -296,6 +308,24 @@ static void free_bfs(smplgpu_ctx* ctx)
 
 static int finish_bank_run(smplgpu_ctx* ctx);   // waits for an asynchronous bank run (defined with the bank)
 
+static void free_lattice(smplgpu_ctx* ctx)
+{
+    cudaFree(ctx->lat.q); cudaFree(ctx->lat.coord); cudaFree(ctx->lat.gdist); cudaFree(ctx->lat.table);
+    cudaFree(ctx->lat.count); cudaFree(ctx->lat.goal); cudaFree(ctx->d_lat_aux);
+    memset(&ctx->lat, 0, sizeof(ctx->lat));
+    ctx->d_lat_aux = nullptr;
+    for (int b = 0; b < SMPLGPU_EXPAND_BUFFERS; ++b) {
+        if (ctx->lat_in[b]) cudaFreeHost(ctx->lat_in[b]);
+        if (ctx->lat_out[b]) cudaFreeHost(ctx->lat_out[b]);
+        cudaFree(ctx->d_lat[b]);
+        ctx->lat_in[b] = ctx->lat_out[b] = ctx->d_lat[b] = nullptr;
+        ctx->lat_in_cap[b] = ctx->lat_out_cap[b] = ctx->d_lat_cap[b] = 0;
+        ctx->lat_n[b] = -1;
+    }
+    ctx->has_lat = false;
+    ctx->lat_max_n = 0;
+}
+
 void smplgpu_destroy(smplgpu_ctx* ctx)
 {
     if (!ctx) {
@@ -330,6 +360,7 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
     cudaFree(ctx->d_bank_stage); cudaFree(ctx->d_bank_seed_count);
     cudaFree(ctx->d_x1_deltas); cudaFree(ctx->d_x1_done);
     cudaFree(ctx->d_coord); cudaFree(ctx->d_prim8);
+    free_lattice(ctx);
     if (ctx->x1_out) cudaFreeHost(ctx->x1_out);
     if (ctx->h_bank_stage) cudaFreeHost(ctx->h_bank_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -2482,6 +2513,256 @@ int smplgpu_expand_batch(smplgpu_ctx* ctx, const double* q0, const double* q1, c
     if (r < 0) return r;
     r = smplgpu_expand_batch_wait(ctx, 0, verdict, h, goal_dist_cells, offset_xyz);
     return r < 0 ? r : 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// device-resident lattices
+///////////////////////////////////////////////////////////////////////////////
+
+static size_t lattice_bytes_per_slot(int dof, int cap, int table_size)
+{
+    return (size_t)cap * dof * (sizeof(double) + sizeof(int)) + (size_t)cap * sizeof(int) + (size_t)table_size * sizeof(int) +
+           sizeof(int) + 3 * sizeof(double);
+}
+
+static int lattice_table_size(int cap)
+{
+    int t = 256;
+    while (t < 2 * cap) t <<= 1;
+    return t;
+}
+
+int smplgpu_lattice_max_slots(smplgpu_ctx* ctx, int max_states)
+{
+    if (!ctx || max_states < 2) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_robot) return fail(ctx, SMPLGPU_ERR_STATE, "robot tables not set");
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    size_t have = free_b;
+    if (ctx->has_lat) {
+        have += (size_t)ctx->lat.n_slots * lattice_bytes_per_slot(ctx->h_model->dof, ctx->lat.cap, ctx->lat.table_size);
+    }
+    const size_t per = lattice_bytes_per_slot(ctx->h_model->dof, max_states, lattice_table_size(max_states));
+    return (int)std::max<size_t>(1, std::min<size_t>((size_t)(0.4 * (double)have) / per, (size_t)1 << 20));
+}
+
+int smplgpu_lattice_create(smplgpu_ctx* ctx, const smplgpu_lattice_params* p, int n_slots)
+{
+    if (!ctx || !p || n_slots <= 0) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (!p->resolutions || p->n_prims <= 0 || !p->deltas || !p->prim_short || p->max_states < 2)
+        return fail(ctx, SMPLGPU_ERR_INVALID, "incomplete lattice parameters");
+    const int dof = ctx->h_model->dof;
+    r = smplgpu_set_lattice(ctx, p->resolutions, nullptr);   // discretisation (also used by the 16-bit entry points)
+    if (r) return r;
+    std::vector<int> long_list, short_list;
+    for (int k = 0; k < p->n_prims; ++k) {
+        (p->prim_short[k] ? short_list : long_list).push_back(k);
+    }
+    const int stride = (int)std::max(long_list.size(), p->use_short_dist ? short_list.size() : (size_t)0);
+    if (stride < 1 || stride > LATTICE_MAX_STRIDE)
+        return fail(ctx, SMPLGPU_ERR_LIMIT, "%d active motion primitives per expansion (limit %d)", stride, LATTICE_MAX_STRIDE);
+    for (int b = 0; b < SMPLGPU_EXPAND_BUFFERS; ++b) {
+        if (ctx->lat_n[b] >= 0) return fail(ctx, SMPLGPU_ERR_STATE, "lattice buffer %d is in flight", b);
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int cap = p->max_states;
+    const int tsize = lattice_table_size(cap);
+    const bool same_shape = ctx->has_lat && ctx->lat.n_slots == n_slots && ctx->lat.cap == cap && ctx->lat.stride == stride;
+    if (!same_shape) {
+        // the lattices are a scene-level allocation (gigabytes for thousands of queries): kept across calls
+        free_lattice(ctx);
+        LatticeBank& B = ctx->lat;
+        B.n_slots = n_slots; B.cap = cap; B.table_size = tsize; B.stride = stride;
+        CU(cudaMalloc(&B.q, (size_t)n_slots * cap * dof * sizeof(double)));
+        CU(cudaMalloc(&B.coord, (size_t)n_slots * cap * dof * sizeof(int)));
+        CU(cudaMalloc(&B.gdist, (size_t)n_slots * cap * sizeof(int)));
+        CU(cudaMalloc(&B.table, (size_t)n_slots * tsize * sizeof(int)));
+        CU(cudaMalloc(&B.count, (size_t)n_slots * sizeof(int)));
+        CU(cudaMalloc(&B.goal, (size_t)n_slots * 3 * sizeof(double)));
+        CU(cudaMemset(B.count, 0, (size_t)n_slots * sizeof(int)));
+    }
+    LatticeBank& B = ctx->lat;
+    B.n_long = (int)long_list.size();
+    B.n_short = (int)short_list.size();
+    B.use_short_dist = p->use_short_dist ? 1 : 0;
+    B.short_dist_thresh = p->short_dist_thresh;
+    B.res = ctx->res;
+    B.cost_per_cell = p->cost_per_cell;
+    for (int a = 0; a < 3; ++a) B.tol[a] = p->xyz_tolerance[a];
+    // deltas | long list | short list
+    const size_t db = (size_t)p->n_prims * dof * sizeof(double);
+    const size_t lb = ((size_t)p->n_prims * sizeof(int) + 7) / 8 * 8;
+    if (ctx->d_lat_aux) { CU(cudaFree(ctx->d_lat_aux)); ctx->d_lat_aux = nullptr; }
+    CU(cudaMalloc(&ctx->d_lat_aux, db + 2 * lb + 64));
+    uint8_t* aux = (uint8_t*)ctx->d_lat_aux;
+    CU(cudaMemset(aux, 0, db + 2 * lb + 64));
+    CU(cudaMemcpy(aux, p->deltas, db, cudaMemcpyHostToDevice));
+    if (!long_list.empty()) CU(cudaMemcpy(aux + db, long_list.data(), long_list.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!short_list.empty()) CU(cudaMemcpy(aux + db + lb, short_list.data(), short_list.size() * sizeof(int), cudaMemcpyHostToDevice));
+    B.deltas = (const double*)aux;
+    B.long_list = (const int*)(aux + db);
+    B.short_list = (const int*)(aux + db + lb);
+    ctx->lat_params = ctx->lattice;
+    for (int v = 0; v < MAX_DOF; ++v) ctx->lat_vals.v[v] = ctx->lattice_vals[v];
+    // round buffers for up to one expansion per slot: every allocation happens here, not while planners run
+    const int max_n = n_slots;
+    const size_t ne = (size_t)max_n * stride;
+    for (int b = 0; b < SMPLGPU_EXPAND_BUFFERS; ++b) {
+        const size_t in_bytes = 2 * (size_t)max_n * sizeof(int) + 64;
+        const size_t out_bytes = (2 * ne + (size_t)max_n + 2) * sizeof(int) + 64;   // succ | h | count | resolved (8 B)
+        const size_t dev_bytes = 2 * ne * dof * sizeof(double) + 2 * ((ne + 63) / 64 * 64) + 256;
+        if (in_bytes > ctx->lat_in_cap[b]) {
+            if (ctx->lat_in[b]) { CU(cudaFreeHost(ctx->lat_in[b])); ctx->lat_in[b] = nullptr; ctx->lat_in_cap[b] = 0; }
+            CU(cudaHostAlloc(&ctx->lat_in[b], in_bytes, cudaHostAllocMapped));
+            ctx->lat_in_cap[b] = in_bytes;
+        }
+        if (out_bytes > ctx->lat_out_cap[b]) {
+            if (ctx->lat_out[b]) { CU(cudaFreeHost(ctx->lat_out[b])); ctx->lat_out[b] = nullptr; ctx->lat_out_cap[b] = 0; }
+            CU(cudaHostAlloc(&ctx->lat_out[b], out_bytes, cudaHostAllocMapped));
+            ctx->lat_out_cap[b] = out_bytes;
+        }
+        if ((r = grow(ctx, &ctx->d_lat[b], &ctx->d_lat_cap[b], dev_bytes))) return r;
+    }
+    if ((r = ensure_unc(ctx, ne))) return r;
+    ctx->lat_max_n = max_n;
+    ctx->has_lat = true;
+    return stride;
+}
+
+int smplgpu_lattice_begin(smplgpu_ctx* ctx, const int32_t* slots, const double* starts, const int32_t* start_gd,
+                          const double* goals_xyz, int n)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_lat) return fail(ctx, SMPLGPU_ERR_STATE, "lattices not created (smplgpu_lattice_create)");
+    if (n == 0) return 0;
+    if (!slots || !starts || !start_gd || !goals_xyz) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    for (int i = 0; i < n; ++i) {
+        if (slots[i] < 0 || slots[i] >= ctx->lat.n_slots) return fail(ctx, SMPLGPU_ERR_INVALID, "slot %d out of range", slots[i]);
+    }
+    const int dof = ctx->h_model->dof;
+    const size_t sb = ((size_t)n * sizeof(int) + 7) / 8 * 8, qb = (size_t)n * dof * sizeof(double), gb = (size_t)n * 3 * sizeof(double);
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, 2 * sb + qb + gb + 64);
+    if (r) return r;
+    uint8_t* base = (uint8_t*)ctx->d_misc;
+    double* d_starts = (double*)base;
+    double* d_goals = (double*)(base + qb);
+    int* d_slots = (int*)(base + qb + gb);
+    int* d_gd = (int*)(base + qb + gb + sb);
+    CU(cudaMemcpyAsync(d_starts, starts, qb, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_goals, goals_xyz, gb, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_slots, slots, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_gd, start_gd, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t total = (size_t)n * ctx->lat.table_size;
+    lattice_clear_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(ctx->lat, d_slots, n);
+    lattice_begin_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_model, ctx->lat, ctx->lat_params, ctx->lat_vals, d_slots,
+                                                                  d_starts, d_gd, d_goals, n);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));   // the inputs may be pageable
+    return 0;
+}
+
+int smplgpu_lattice_expand_submit(smplgpu_ctx* ctx, const int32_t* slot, const int32_t* parent_id, int n, int buffer)
+{
+    if (!ctx || n < 0 || buffer < 0 || buffer >= SMPLGPU_EXPAND_BUFFERS) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_lat) return fail(ctx, SMPLGPU_ERR_STATE, "lattices not created (smplgpu_lattice_create)");
+    if (!ctx->has_bank) return fail(ctx, SMPLGPU_ERR_STATE, "BFS bank not created");
+    if (ctx->lat.n_slots > ctx->bank_slots) return fail(ctx, SMPLGPU_ERR_STATE, "more lattices than BFS bank slots");
+    if (ctx->lat_n[buffer] >= 0) return fail(ctx, SMPLGPU_ERR_STATE, "lattice buffer %d is still in flight", buffer);
+    if (n > ctx->lat_max_n) return fail(ctx, SMPLGPU_ERR_LIMIT, "%d expansions in a round, room for %d", n, ctx->lat_max_n);
+    if (n > 0 && (!slot || !parent_id)) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    if (n == 0) {
+        ctx->lat_n[buffer] = 0;
+        return 0;
+    }
+    const int b = buffer;
+    const int dof = ctx->h_model->dof;
+    const LatticeBank& B = ctx->lat;
+    int* in_slot = (int*)ctx->lat_in[b];
+    int* in_parent = in_slot + n;
+    for (int i = 0; i < n; ++i) {
+        if (slot[i] < 0 || slot[i] >= B.n_slots) return fail(ctx, SMPLGPU_ERR_INVALID, "expansion %d: slot %d out of range", i, slot[i]);
+        if (parent_id[i] < 1 || parent_id[i] >= B.cap) return fail(ctx, SMPLGPU_ERR_INVALID, "expansion %d: state id %d out of range", i, parent_id[i]);
+        in_slot[i] = slot[i];
+        in_parent[i] = parent_id[i];
+    }
+    const size_t ne = (size_t)n * B.stride;
+    const size_t nep = (ne + 63) / 64 * 64;
+    uint8_t* dbase = (uint8_t*)ctx->d_lat[b];
+    double* dq0 = (double*)dbase;
+    double* dq1 = dq0 + ne * dof;
+    uint8_t* dactive = (uint8_t*)(dq1 + ne * dof);
+    uint8_t* dverdict = dactive + nep;
+    int* out_succ = (int*)ctx->lat_out[b];
+    int* out_h = out_succ + ne;
+    int* out_count = out_h + ne;
+    // the kernels read the (slot, state id) pairs from, and write the results to, page-locked host memory directly
+    lattice_gen_kernel<<<(unsigned)((ne + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_model, B, in_slot, in_parent, n, dq0, dq1, dactive,
+                                                                              ctx->d_stats);
+    ++ctx->launches;
+    int r = launch_edges(ctx, dq0, dq1, (int)ne, dverdict, nullptr);
+    if (r) return r;
+    lattice_commit_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+        ctx->d_model, ctx->grid, B, ctx->lat_params, ctx->lat_vals, ctx->bank.dist, ctx->bank.DX, ctx->bank.DY, ctx->bank_slot_dz,
+        in_slot, n, dq1, dactive, dverdict, out_succ, out_h, out_count, ctx->d_stats);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev_exp[b], ctx->stream));
+    ctx->lat_n[buffer] = n;
+    return 0;
+}
+
+int smplgpu_lattice_expand_wait(smplgpu_ctx* ctx, int buffer, const int32_t** succ, const int32_t** h, const int32_t** count)
+{
+    if (!ctx || buffer < 0 || buffer >= SMPLGPU_EXPAND_BUFFERS) return SMPLGPU_ERR_INVALID;
+    const int n = ctx->lat_n[buffer];
+    if (n < 0) return fail(ctx, SMPLGPU_ERR_STATE, "lattice buffer %d has nothing in flight", buffer);
+    ctx->lat_n[buffer] = -1;
+    if (n == 0) return 0;
+    if (!succ || !h || !count) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    CU(cudaEventSynchronize(ctx->ev_exp[buffer]));
+    const size_t ne = (size_t)n * ctx->lat.stride;
+    const int* out = (const int*)ctx->lat_out[buffer];
+    *succ = out;
+    *h = out + ne;
+    *count = out + 2 * ne;
+    unsigned long long resolved = 0;
+    memcpy(&resolved, out + 2 * ne + ((n + 1) & ~1), sizeof(resolved));
+    ctx->exp_resolved_total += (int64_t)resolved;
+    for (int i = 0; i < n; ++i) {
+        if ((*count)[i] < 0) return fail(ctx, SMPLGPU_ERR_LIMIT, "a lattice ran out of room (%d states per query)", ctx->lat.cap);
+    }
+    return n;
+}
+
+int smplgpu_lattice_states(smplgpu_ctx* ctx, const int32_t* slot, const int32_t* id, int n, double* q_out)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_lat) return fail(ctx, SMPLGPU_ERR_STATE, "lattices not created");
+    if (n == 0) return 0;
+    if (!slot || !id || !q_out) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    for (int i = 0; i < n; ++i) {
+        if (slot[i] < 0 || slot[i] >= ctx->lat.n_slots || id[i] < 0 || id[i] >= ctx->lat.cap)
+            return fail(ctx, SMPLGPU_ERR_INVALID, "state %d: (slot %d, id %d) out of range", i, slot[i], id[i]);
+    }
+    const int dof = ctx->h_model->dof;
+    const size_t ib = ((size_t)n * sizeof(int) + 7) / 8 * 8, ob = (size_t)n * dof * sizeof(double);
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, 2 * ib + ob + 64);
+    if (r) return r;
+    uint8_t* base = (uint8_t*)ctx->d_misc;
+    double* d_out = (double*)base;
+    int* d_slot = (int*)(base + ob);
+    int* d_id = (int*)(base + ob + ib);
+    CU(cudaMemcpyAsync(d_slot, slot, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_id, id, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    lattice_gather_kernel<<<(n * dof + 127) / 128, 128, 0, ctx->stream>>>(ctx->lat, dof, d_slot, d_id, n, d_out);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(q_out, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 ///////////////////////////////////////////////////////////////////////////////

@@ -41,124 +41,24 @@ double normalizeAngle(double angle)
 }
 } // namespace
 
-// A table slot holds (low 32 hash bits << 32 | state id): a probe is decided from the slot alone unless the tag
-// matches, so the coordinate array (another cache miss) is only read for a state that is almost surely the one
-int BatchPlanner::Lattice::find(const int* c, uint64_t hv) const
-{
-    if (table.empty()) {
-        return -1;
-    }
-    const size_t mask = table.size() - 1;
-    const uint32_t tag = (uint32_t)hv;
-    for (size_t i = (size_t)tag & mask;; i = (i + 1) & mask) {
-        const uint64_t slot = table[i];
-        if (slot == EMPTY) {
-            return -1;
-        }
-        if ((uint32_t)(slot >> 32) == tag) {
-            const int id = (int)(uint32_t)slot;
-            if (std::equal(c, c + dof, &coords[(size_t)id * dof])) {
-                return id;
-            }
-        }
-    }
-}
-
-void BatchPlanner::Lattice::enter(uint32_t tag, int id)
-{
-    const size_t mask = table.size() - 1;
-    size_t i = (size_t)tag & mask;
-    while (table[i] != EMPTY) {
-        i = (i + 1) & mask;
-    }
-    table[i] = ((uint64_t)tag << 32) | (uint32_t)id;
-}
-
-void BatchPlanner::Lattice::grow(uint32_t new_tag, int new_id)
-{
-    // the tags carry every hash bit a table of up to 2^32 slots needs: re-enter the old slots without reading
-    // a single coordinate, then the state that triggered the growth
-    std::vector<uint64_t> old;
-    old.swap(table);
-    table.assign(old.empty() ? 256 : old.size() * 2, EMPTY);
-    for (const uint64_t slot : old) {
-        if (slot != EMPTY) {
-            enter((uint32_t)(slot >> 32), (int)(uint32_t)slot);
-        }
-    }
-    enter(new_tag, new_id);
-}
-
-int BatchPlanner::Lattice::add(const int* c, const double* q, int hval, int gd, bool index, uint64_t hv)
-{
-    const int id = size();
-    if (c != nullptr) {
-        coords.insert(coords.end(), c, c + dof);
-        qs.insert(qs.end(), q, q + dof);
-    } else {
-        coords.insert(coords.end(), dof, 0);
-        qs.insert(qs.end(), dof, 0.0);
-    }
-    h.push_back(hval);
-    gdist.push_back(gd);
-    if (index) {
-        if ((size_t)(id + 1) * 2 > table.size()) {
-            grow((uint32_t)hv, id);
-        } else {
-            enter((uint32_t)hv, id);
-        }
-    }
-    return id;
-}
-
 BatchPlanner::BatchPlanner(smplgpu_ctx* ctx, const PlannerConfig& cfg, int max_concurrent) :
     m_ctx(ctx), m_cfg(cfg), m_max_concurrent(std::max(1, max_concurrent))
 {
     const int dof = cfg.dof;
     const int n_prims = (int)cfg.short_flags.size();
-    // ManipLatticeActionSpace::addMotionPrim(..., add_converse = true)
+    // ManipLatticeActionSpace::addMotionPrim(..., add_converse = true): the converse follows each primitive
+    int n_long = 0, n_short = 0;
     for (int p = 0; p < n_prims; ++p) {
-        std::vector<double> d(cfg.mprims.begin() + (size_t)p * dof, cfg.mprims.begin() + (size_t)(p + 1) * dof);
-        m_prim_deltas.push_back(d);
-        m_prim_short.push_back(cfg.short_flags[p] != 0);
-        for (double& v : d) v *= -1.0;
-        m_prim_deltas.push_back(d);
-        m_prim_short.push_back(cfg.short_flags[p] != 0);
-    }
-    // ManipLattice::init discretisation (manip_lattice.cpp:125-139)
-    m_coord_vals.resize(dof);
-    m_coord_deltas.resize(dof);
-    for (int v = 0; v < dof; ++v) {
-        const double res = cfg.resolutions[v];
-        if (cfg.var_continuous[v]) {
-            m_coord_vals[v] = (int)std::round((2.0 * M_PI) / res);
-            m_coord_deltas[v] = (2.0 * M_PI) / (double)m_coord_vals[v];
-        } else {
-            const double span = std::fabs(cfg.var_max[v] - cfg.var_min[v]);
-            m_coord_vals[v] = std::max(1, (int)std::round(span / res));
-            m_coord_deltas[v] = span / (double)m_coord_vals[v];
+        for (int sign = 0; sign < 2; ++sign) {
+            for (int j = 0; j < dof; ++j) {
+                const double d = cfg.mprims[(size_t)p * dof + j];
+                m_prim_deltas.push_back(sign == 0 ? d : d * -1.0);
+            }
+            m_prim_short.push_back(cfg.short_flags[p] != 0 ? 1 : 0);
+            (cfg.short_flags[p] != 0 ? n_short : n_long) += 1;
         }
     }
-}
-
-// manip_lattice.cpp:1263-1289 (every KDL planning variable is either continuous or bounded)
-void BatchPlanner::stateToCoord(const double* q, std::vector<int>& coord) const
-{
-    coord.resize(m_cfg.dof);
-    for (int i = 0; i < m_cfg.dof; ++i) {
-        if (m_cfg.var_continuous[i]) {
-            double pos = normalizeAngle(q[i]);
-            if (pos < 0.0) {
-                pos += 2.0 * M_PI;
-            }
-            coord[i] = (int)((pos + m_coord_deltas[i] * 0.5) / m_coord_deltas[i]);
-            if (coord[i] == m_coord_vals[i]) {
-                coord[i] = 0;
-            }
-        } else {
-            coord[i] = (int)(((q[i] - m_cfg.var_min[i]) / m_coord_deltas[i]) + 0.5);
-        }
-    }
+    m_stride = std::max(n_long, cfg.use_short_dist ? n_short : 0);
 }
 
 // KDLRobotModel::checkJointLimits -> normalizeAnglesIntoRange (kdl_robot_model.cpp:173-235, 326-337)
@@ -218,12 +118,12 @@ BatchPlanner::SState& BatchPlanner::sstate(Query& Q, int id)
 }
 
 // ARAStar::reinitSearchState (arastar.cpp:613-627); one search call per query, so "reinit" == first touch
-void BatchPlanner::touch(Query& Q, int id)
+void BatchPlanner::touch(Query& Q, int id, int h)
 {
     SState& s = sstate(Q, id);
     if (!s.touched) {
         s.g = INFINITECOST;
-        s.h = (id == 0) ? Q.goal_h : Q.lat.h[id];
+        s.h = (id == 0) ? Q.goal_h : h;   // GetGoalHeuristic(id), computed on the device when the state was created
         s.f = INFINITECOST;
         s.eg = INFINITECOST;
         s.iteration_closed = 0;
@@ -292,7 +192,7 @@ void BatchPlanner::heapPop(Query& Q)
 void BatchPlanner::finish(Query& Q, bool found)
 {
     Q.done = true;
-    Q.result.num_states = Q.lat.size();
+    Q.result.num_states = Q.num_states;
     if (!found || Q.search.empty() || Q.search[0].g >= (unsigned int)INFINITECOST) {
         return;
     }
@@ -302,13 +202,20 @@ void BatchPlanner::finish(Query& Q, bool found)
     std::reverse(Q.result.path_ids.begin(), Q.result.path_ids.end());
     Q.result.cost = Q.search[0].g;
     Q.result.success = true;
-    // ManipLattice::extractPath (manip_lattice.cpp:2018-2160)
+}
+
+// ManipLattice::extractPath (manip_lattice.cpp:2018-2160): the joint values of the path's states, read from the
+// device lattice while the query still owns its slot; the goal id stands for "any state satisfying the goal" and
+// is replaced by the first valid goal-reaching successor of its predecessor
+bool BatchPlanner::fetchPathStates(Query& Q, std::string* err)
+{
     const int dof = m_cfg.dof;
     const std::vector<int>& ids = Q.result.path_ids;
-    Q.result.path_states.assign(ids.size() * (size_t)dof, 0.0);
-    for (size_t i = 0; i < ids.size(); ++i) {
+    std::vector<int32_t> real(ids.size()), slots(ids.size(), Q.slot);
+    size_t n = 0;
+    for (size_t i = 0; i < ids.size(); ++i, ++n) {
         int id = ids[i];
-        if (id == 0) {   // the goal state id stands for "any state satisfying the goal"
+        if (id == 0) {
             id = -1;
             if (i > 0) {
                 for (const std::pair<int, int>& gs : Q.goal_succ) {
@@ -319,12 +226,17 @@ void BatchPlanner::finish(Query& Q, bool found)
                 }
             }
             if (id < 0) {
-                Q.result.path_states.resize(i * (size_t)dof);   // cannot happen for a found path; keep what is known
-                break;
+                break;   // cannot happen for a found path; keep what is known
             }
         }
-        std::copy(Q.lat.q(id), Q.lat.q(id) + dof, Q.result.path_states.begin() + i * (size_t)dof);
+        real[i] = id;
     }
+    Q.result.path_states.assign(n * (size_t)dof, 0.0);
+    if (n > 0 && smplgpu_lattice_states(m_ctx, slots.data(), real.data(), (int)n, Q.result.path_states.data()) < 0) {
+        if (err) *err = smplgpu_last_error(m_ctx);
+        return false;
+    }
+    return true;
 }
 
 ///////////////////////////////////////////////////////////////////////////////
@@ -413,41 +325,21 @@ void BatchPlanner::initQuery(Query& Q, int index, int slot, const double* goal)
     // keep the slot's allocations from the query it served before (growing a multi-megabyte vector means mmap +
     // copy + munmap, and every munmap interrupts all planner threads); a fresh slot reserves room up front
     Query fresh = Query();
-    std::swap(fresh.lat.coords, Q.lat.coords);
-    std::swap(fresh.lat.qs, Q.lat.qs);
-    std::swap(fresh.lat.h, Q.lat.h);
-    std::swap(fresh.lat.gdist, Q.lat.gdist);
-    std::swap(fresh.lat.table, Q.lat.table);
     std::swap(fresh.search, Q.search);
     std::swap(fresh.open, Q.open);
-    std::swap(fresh.succ_q1, Q.succ_q1);
-    std::swap(fresh.succ_coord, Q.succ_coord);
-    std::swap(fresh.succ_hslot, Q.succ_hslot);
-    std::swap(fresh.succ_id, Q.succ_id);
-    fresh.lat.coords.clear();
-    fresh.lat.qs.clear();
-    fresh.lat.h.clear();
-    fresh.lat.gdist.clear();
-    fresh.lat.table.clear();
     fresh.search.clear();
     fresh.open.clear();
     Q = std::move(fresh);
     {
-        const size_t per_expansion = std::max<size_t>(1, m_prim_deltas.size() / 2);
-        const size_t n = std::min<size_t>(2 + (size_t)std::max(0, m_cfg.max_expansions) * per_expansion, (size_t)1 << 15);
-        const size_t dofs = (size_t)m_cfg.dof;
-        Q.lat.coords.reserve(n * dofs);
-        Q.lat.qs.reserve(n * dofs);
-        Q.lat.h.reserve(n);
-        Q.lat.gdist.reserve(n);
+        const size_t n = std::min<size_t>(2 + (size_t)std::max(0, m_cfg.max_expansions) * (size_t)std::max(1, m_stride), (size_t)1 << 15);
         Q.search.reserve(n);
     }
     Q.index = index;
     Q.slot = slot;
     Q.done = false;
     Q.expanding = -1;
-    Q.n_succ = 0;
     Q.edge_begin = 0;
+    Q.num_states = 1;   // id 0 = the goal state (manip_lattice.cpp:122)
     for (int a = 0; a < 3; ++a) Q.goal[a] = goal[a];
     int cell[3];
     worldToGrid(Q.goal, cell);
@@ -456,18 +348,12 @@ void BatchPlanner::initQuery(Query& Q, int index, int slot, const double* goal)
     // the seed cell holds distance 0 even if it was a wall (bfs3d.cpp:181-187)
     Q.goal_h = inb ? 0 : SMPLGPU_HEURISTIC_INFINITY;
     Q.open.assign(1, Query::HeapEntry{ 0u, -1 });
-    Q.lat.dof = m_cfg.dof;
-    Q.lat.add(nullptr, nullptr, 0, 0, false, 0); // id 0 = the goal state (manip_lattice.cpp:122)
 }
 
-// ARAStar::improvePath loop head (arastar.cpp:486-527) + ManipLatticeActionSpace::apply + the joint-limit
-// part of ManipLattice::checkAction
+// ARAStar::improvePath loop head (arastar.cpp:486-527): the state this query expands this round
 void BatchPlanner::expandOne(Query& Q)
 {
-    const int dof = m_cfg.dof;
     Q.expanding = -1;
-    Q.n_succ = 0;
-    Q.succ_q1.clear();
     if (Q.open.size() <= 1) {
         finish(Q, false);
         return;
@@ -486,102 +372,36 @@ void BatchPlanner::expandOne(Query& Q)
     Q.search[min_id].eg = Q.search[min_id].g;
     Q.expanding = min_id;
     ++Q.result.expansions;
-
-    const double* Pq = Q.lat.q(min_id);
-    const double goal_dist = (double)Q.lat.gdist[min_id] * m_cfg.res;
-    const bool near_goal = goal_dist <= m_cfg.short_dist_thresh;
-    for (size_t p = 0; p < m_prim_deltas.size(); ++p) {
-        const bool active_prim = m_prim_short[p] ? (m_cfg.use_short_dist && near_goal)
-                                                 : !(m_cfg.use_short_dist && near_goal);
-        if (!active_prim) {
-            continue;
-        }
-        const size_t base = Q.succ_q1.size();
-        Q.succ_q1.resize(base + dof);
-        for (int j = 0; j < dof; ++j) {
-            Q.succ_q1[base + j] = m_prim_deltas[p][j] + Pq[j];
-        }
-        if (!checkJointLimits(&Q.succ_q1[base])) { // checkAction: joint limits first
-            Q.succ_q1.resize(base);
-            continue;
-        }
-        ++Q.n_succ;
-    }
 }
 
-// GetSuccs bookkeeping + ARAStar::expand relaxations (arastar.cpp:531-568) for this query's edges, in
-// submission (= primitive) order
-static thread_local double g_abs_prof[4] = { 0, 0, 0, 0 };   // SMPLHOST_PLAN_PROFILE: coord+hash, prefetch pass, lookup, relax
-
-void BatchPlanner::absorbOne(Query& Q, const uint8_t* verdict, const int32_t* h, const int32_t* gd, const double* off)
+// ARAStar::expand relaxations (arastar.cpp:531-568) over the successors the device returned for this query's
+// expansion, in primitive order: succ[j] = lattice id | goal flag, or -1 (inactive primitive, joint limit, collision)
+void BatchPlanner::absorbOne(Query& Q, const int32_t* succ, const int32_t* h, int count)
 {
-    const int dof = m_cfg.dof;
-    static const bool profile = getenv("SMPLHOST_PLAN_PROFILE") != nullptr;
-    Timer pt;
-    std::vector<int> coord;
-    // The lattice of a query is megabytes of hash table, coordinates and search states, and hundreds of queries
-    // take turns on one thread: every lookup below misses the caches.  Two prefetch-only passes (they decide
-    // nothing) start those loads for all successors of this expansion before the sequential relaxation runs.
-    Q.succ_coord.resize((size_t)Q.n_succ * dof);
-    Q.succ_hslot.resize(Q.n_succ);
-    const size_t mask = Q.lat.table.empty() ? 0 : Q.lat.table.size() - 1;
-    for (int e = 0; e < Q.n_succ; ++e) {
-        if (!verdict[e]) {
-            continue;
-        }
-        stateToCoord(&Q.succ_q1[(size_t)e * dof], coord);
-        std::copy(coord.begin(), coord.end(), Q.succ_coord.begin() + (size_t)e * dof);
-        Q.succ_hslot[e] = Lattice::hash(coord.data(), dof);
-        if (!Q.lat.table.empty()) {
-            __builtin_prefetch(&Q.lat.table[(size_t)Q.succ_hslot[e] & mask]);
-        }
-    }
-    if (profile) g_abs_prof[0] += pt.lap();
-    for (int e = 0; e < Q.n_succ; ++e) {
-        if (!verdict[e] || Q.lat.table.empty()) {
-            continue;
-        }
-        const uint64_t slot = Q.lat.table[(size_t)Q.succ_hslot[e] & mask];
-        const int id = slot == Lattice::EMPTY ? -1 : (int)(uint32_t)slot;
-        if (id >= 0) {
-            __builtin_prefetch(&Q.lat.coords[(size_t)id * dof]);
+    Q.num_states = count;
+    // the search states of the successors are scattered over a megabyte-sized array: start the loads first
+    for (int e = 0; e < m_stride; ++e) {
+        if (succ[e] >= 0) {
+            const int id = succ[e] & ~SMPLGPU_LATTICE_GOAL_FLAG;
             if ((size_t)id < Q.search.size()) {
                 __builtin_prefetch(&Q.search[id]);
             }
         }
     }
-    if (profile) g_abs_prof[1] += pt.lap();
-    Q.succ_id.resize(Q.n_succ);
-    int* ids = Q.succ_id.data();   // lattice id of successor e
-    for (int e = 0; e < Q.n_succ; ++e) {
-        if (!verdict[e]) {
+    for (int e = 0; e < m_stride; ++e) {
+        if (succ[e] < 0) {
             continue;
         }
-        const int* c = &Q.succ_coord[(size_t)e * dof];
-        int succ_id = Q.lat.find(c, Q.succ_hslot[e]);
-        if (succ_id < 0) {
-            succ_id = Q.lat.add(c, &Q.succ_q1[(size_t)e * dof], h[e], gd[e], true, Q.succ_hslot[e]);
-        }
-        ids[e] = succ_id;
-    }
-    if (profile) g_abs_prof[2] += pt.lap();
-    for (int e = 0; e < Q.n_succ; ++e) {
-        if (!verdict[e]) {
-            continue;
-        }
-        const int succ_id = ids[e];
-        // ManipLattice::isGoal, XYZ_GOAL (manip_lattice.cpp:1673-1687)
-        const bool is_goal = std::fabs(off[3 * e] - Q.goal[0]) <= m_cfg.xyz_tolerance[0] &&
-                             std::fabs(off[3 * e + 1] - Q.goal[1]) <= m_cfg.xyz_tolerance[1] &&
-                             std::fabs(off[3 * e + 2] - Q.goal[2]) <= m_cfg.xyz_tolerance[2];
+        const bool is_goal = (succ[e] & SMPLGPU_LATTICE_GOAL_FLAG) != 0;   // ManipLattice::isGoal, on the device
+        const int succ_id = succ[e] & ~SMPLGPU_LATTICE_GOAL_FLAG;
         if (is_goal && (Q.goal_succ.empty() || Q.goal_succ.back().first != Q.expanding)) {
             Q.goal_succ.emplace_back(Q.expanding, succ_id);   // first valid goal action of this expansion
         }
         const int target = is_goal ? 0 : succ_id;
         sstate(Q, target);
-        touch(Q, target);
+        touch(Q, target, h[e]);
         SState& ss = Q.search[target];
-        const int new_cost = Q.search[Q.expanding].eg + (int)(1000 * 1.0);
+        const int new_cost = Q.search[Q.expanding].eg + (int)(1000 * 1.0);   // cost = DefaultCostMultiplier * weight (1)
         if ((unsigned int)new_cost < ss.g) {   // int vs unsigned, compared as unsigned (arastar.cpp:545-548)
             ss.g = new_cost;
             ss.bp = Q.expanding;
@@ -596,14 +416,10 @@ void BatchPlanner::absorbOne(Query& Q, const uint8_t* verdict, const int32_t* h,
             }
         }
     }
-    // the state this query expands next round (unless a better one arrives): start loading what expandOne reads
+    // the state this query expands next round (unless a better one arrives)
     if (Q.open.size() > 1) {
-        const int next_id = Q.open[1].id;
-        __builtin_prefetch(&Q.search[next_id]);
-        __builtin_prefetch(Q.lat.q(next_id));
-        __builtin_prefetch(&Q.lat.gdist[next_id]);
+        __builtin_prefetch(&Q.search[Q.open[1].id]);
     }
-    if (profile) g_abs_prof[3] += pt.lap();
 }
 
 ///////////////////////////////////////////////////////////////////////////////
@@ -624,14 +440,37 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         return false;
     };
     const long long resolved0 = smplgpu_expand_batch_resolved(m_ctx);
-    // the bank keeps the reference's int node indices and has to fit in device memory: clamp the concurrency to it
+    // a query creates at most (its expansions) x (successors per expansion) states besides the goal and the start
+    const long long want_states = 2 + (long long)std::max(0, m_cfg.max_expansions) * std::max(1, m_stride);
+    const int max_states = (int)std::min<long long>(want_states, 1LL << 26);
+    // the BFS bank keeps the reference's int node indices, and bank and lattices have to fit in device memory
     const int max_slots = smplgpu_bfs_bank_max_slots(m_ctx);
     if (max_slots < 0) return fail_dev();
-    const int n_slots = std::min(std::min(m_max_concurrent, nq), max_slots);
+    const int max_lat = smplgpu_lattice_max_slots(m_ctx, max_states);
+    if (max_lat < 0) return fail_dev();
+    const int n_slots = std::min(std::min(std::min(m_max_concurrent, nq), max_slots), max_lat);
     if (smplgpu_bfs_bank_create(m_ctx, n_slots, m_cfg.inflation_radius) < 0) return fail_dev();
     // every device / pinned allocation happens here: allocating while other planner threads run would stall
     // their streams (allocation synchronises the device)
-    if (smplgpu_expand_batch_reserve(m_ctx, (n_slots + 1) * (int)m_prim_deltas.size()) < 0) return fail_dev();
+    {
+        smplgpu_lattice_params lp;
+        lp.resolutions = m_cfg.resolutions.data();
+        lp.deltas = m_prim_deltas.data();
+        lp.prim_short = m_prim_short.data();
+        lp.n_prims = (int)m_prim_short.size();
+        lp.use_short_dist = m_cfg.use_short_dist ? 1 : 0;
+        lp.short_dist_thresh = m_cfg.short_dist_thresh;
+        for (int a = 0; a < 3; ++a) lp.xyz_tolerance[a] = m_cfg.xyz_tolerance[a];
+        lp.cost_per_cell = m_cfg.cost_per_cell;
+        lp.max_states = max_states;
+        const int stride = smplgpu_lattice_create(m_ctx, &lp, n_slots);
+        if (stride < 0) return fail_dev();
+        if (stride != m_stride) {
+            if (err) *err = "lattice stride mismatch";
+            return false;
+        }
+    }
+    if (smplgpu_expand_batch_reserve(m_ctx, n_slots + 1) < 0) return fail_dev();   // setStart's batch
     ++m_stats.device_calls;
     {
         const double dt = t.lap();
@@ -646,18 +485,16 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
     // refill in groups so that one bank run (one wavefront launch sequence) serves several new queries
     const int refill_min = std::max(1, n_slots / 4);
 
-    // The active queries work in NG groups (slot modulo NG).  While the device expands one group's batch the
-    // host absorbs the other groups' results and prepares their next batches, so host and device overlap.  Two
-    // groups is the measured optimum (SMPLHOST_PLAN_GROUPS, 2 .. SMPLGPU_EXPAND_BUFFERS: 12 planner threads on one
-    // B200 reach 1651 queries/s with 2 groups, 1346 with 3, 1056 with 4): the host does wait for the device a fifth
-    // of the time, but more groups mean more and smaller batches, and the device side of a batch is a fixed-latency
-    // chain (copy in, three kernels, copy out) that twelve contexts already queue behind one another.
+    // The active queries work in NG groups (slot modulo NG).  While the device expands one group's round the host
+    // absorbs the other groups' results and pops their next states, so host and device overlap.
     struct Group
     {
         std::vector<int> active;            // occupied slots of this group with a search in progress
-        std::vector<double> q0, q1, off;
-        std::vector<int32_t> slot, h, gd;
-        std::vector<uint8_t> verdict;
+        std::vector<int32_t> slot, parent;  // this round's expansions
+        std::vector<int> owner;             // expansion -> index into `active`
+        const int32_t* succ = nullptr;      // results of the round in flight (page-locked memory of the context)
+        const int32_t* h = nullptr;
+        const int32_t* count = nullptr;
         bool in_flight = false;
         int ne = 0;
     };
@@ -682,28 +519,24 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
     std::vector<uint8_t> sv;
     std::vector<double> soff;
 
-    // wait for a group's batch, relax its queries, retire the finished ones
+    // wait for a group's round, relax its queries, retire the finished ones
     auto absorb = [&](int gi) -> bool {
         Group& g = G[gi];
         if (g.in_flight) {
             m_stats.host_seconds += t.lap();
-            if (smplgpu_expand_batch_wait(m_ctx, gi, g.verdict.data(), g.h.data(), g.gd.data(), g.off.data()) < 0) return false;
+            if (smplgpu_lattice_expand_wait(m_ctx, gi, &g.succ, &g.h, &g.count) < 0) return false;
             {
                 const double dt = t.lap();
                 m_stats.device_seconds += dt;
                 m_stats.max_wait_seconds = std::max(m_stats.max_wait_seconds, dt);
             }
             g.in_flight = false;
-            const int na = (int)g.active.size();
+            const int ne = g.ne;
             pt.lap();
             pool.run([&](int tid) {
-                for (int k = tid; k < na; k += pool.size()) {
-                    Query& Q = S[g.active[k]];
-                    if (Q.done || Q.n_succ == 0) {
-                        continue;
-                    }
-                    absorbOne(Q, g.verdict.data() + Q.edge_begin, g.h.data() + Q.edge_begin, g.gd.data() + Q.edge_begin,
-                              g.off.data() + (size_t)Q.edge_begin * 3);
+                for (int k = tid; k < ne; k += pool.size()) {
+                    Query& Q = S[g.active[g.owner[k]]];
+                    absorbOne(Q, g.succ + (size_t)k * m_stride, g.h + (size_t)k * m_stride, g.count[k]);
                 }
             });
             prof[0] += pt.lap();
@@ -713,6 +546,12 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         for (size_t k = 0; k < g.active.size(); ++k) {
             const int s = g.active[k];
             if (S[s].done) {
+                if (S[s].result.success && m_cfg.want_path_states) {
+                    m_stats.host_seconds += t.lap();
+                    if (!fetchPathStates(S[s], err)) return false;   // while the query still owns its slot
+                    m_stats.device_seconds += t.lap();
+                    ++m_stats.device_calls;
+                }
                 out[S[s].index] = S[s].result;
                 occupied[s] = 0;
                 ++finished;
@@ -725,7 +564,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         return true;
     };
 
-    // every active query of the group pops one state and generates its successors; one device batch
+    // every active query of the group pops one state; one device round expands them all
     auto expand = [&](int gi) -> bool {
         Group& g = G[gi];
         const int na = (int)g.active.size();
@@ -742,51 +581,37 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
             }
         });
         prof[2] += pt.lap();
-        int ne = 0;
+        g.slot.clear();
+        g.parent.clear();
+        g.owner.clear();
         for (int k = 0; k < na; ++k) {
             Query& Q = S[g.active[k]];
-            Q.edge_begin = ne;
-            ne += Q.done ? 0 : Q.n_succ;
-        }
-        g.ne = ne;
-        if (ne == 0) {
-            return true;   // finished / successor-less queries are retired by the next absorb
-        }
-        g.q0.resize((size_t)ne * dof);
-        g.q1.resize((size_t)ne * dof);
-        g.slot.resize(ne);
-        pool.run([&](int tid) {
-            for (int k = tid; k < na; k += pool.size()) {
-                const Query& Q = S[g.active[k]];
-                if (Q.done || Q.n_succ == 0) {
-                    continue;
-                }
-                const double* pq = Q.lat.q(Q.expanding);
-                for (int e = 0; e < Q.n_succ; ++e) {
-                    std::copy(pq, pq + dof, g.q0.begin() + (size_t)(Q.edge_begin + e) * dof);
-                    g.slot[Q.edge_begin + e] = Q.slot;
-                }
-                std::copy(Q.succ_q1.begin(), Q.succ_q1.end(), g.q1.begin() + (size_t)Q.edge_begin * dof);
+            if (Q.done) {
+                continue;   // retired by the next absorb
             }
-        });
-        g.verdict.resize(ne);
-        g.h.resize(ne);
-        g.gd.resize(ne);
-        g.off.resize((size_t)ne * 3);
+            Q.edge_begin = (int)g.slot.size();
+            g.slot.push_back(Q.slot);
+            g.parent.push_back(Q.expanding);
+            g.owner.push_back(k);
+        }
+        g.ne = (int)g.slot.size();
         prof[3] += pt.lap();
-        if (smplgpu_expand_batch_submit(m_ctx, g.q0.data(), g.q1.data(), g.slot.data(), ne, m_cfg.cost_per_cell, gi) < 0) return false;
+        if (g.ne == 0) {
+            return true;
+        }
+        if (smplgpu_lattice_expand_submit(m_ctx, g.slot.data(), g.parent.data(), g.ne, gi) < 0) return false;
         prof[4] += pt.lap();
         g.in_flight = true;
         ++m_stats.device_calls;
         ++m_stats.rounds;
-        m_stats.edges_submitted += ne;
+        m_stats.edges_submitted += (long long)g.ne * m_stride;
         return true;
     };
 
     // Admission in two steps: (1) setGoal -- a free slot gets the query's goal and its BFS is queued on the device
     // WITHOUT waiting (the reference's BFS_3D also searches in a background thread, bfs3d.cpp:156-201), the running
-    // searches keep expanding; (2) when that BFS is done, setStart (limits, validity, heuristic of the start state)
-    // and the queries join the rounds.  One group of pending slots at a time.
+    // searches keep expanding; (2) when that BFS is done, setStart (limits, validity, heuristic of the start state,
+    // a fresh device lattice holding it) and the queries join the rounds.  One group of pending slots at a time.
     std::vector<int32_t> pending;           // slots whose BFS is in flight
     std::vector<int32_t> seeds;
     bool first_fill = true;
@@ -813,12 +638,9 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         if (smplgpu_expand_batch(m_ctx, sq.data(), sq.data(), pending.data(), nn, m_cfg.cost_per_cell,
                                  dummy.data(), sh.data(), sgd.data(), soff.data()) < 0) return false;
         m_stats.device_calls += 2;
-        {
-            const double dt = t.lap();
-            m_stats.device_seconds += dt;
-            m_stats.setup_seconds += dt;
-        }
-        std::vector<int> coord;
+        // the valid starts become state 1 of a fresh lattice in their slot
+        std::vector<int32_t> bslot, bgd;
+        std::vector<double> bq, bgoal;
         for (int k = 0; k < nn; ++k) {
             Query& Q = S[pending[k]];
             const double* qs = &sq[(size_t)k * dof];
@@ -827,14 +649,26 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
                 finish(Q, false);   // retired by the group's next absorb
                 continue;
             }
-            stateToCoord(qs, coord);
-            Q.lat.add(coord.data(), qs, sh[k], sgd[k], true, Lattice::hash(coord.data(), dof));
+            bslot.push_back(pending[k]);
+            bgd.push_back(sgd[k]);
+            bq.insert(bq.end(), qs, qs + dof);
+            bgoal.insert(bgoal.end(), Q.goal, Q.goal + 3);
+            Q.num_states = 2;
             sstate(Q, 1);
-            touch(Q, 1);
-            touch(Q, 0);
+            touch(Q, 1, sh[k]);
+            touch(Q, 0, 0);
             Q.search[1].g = 0;
             Q.search[1].f = computeKey(Q.search[1]);
             heapPush(Q, 1);
+        }
+        if (!bslot.empty()) {
+            if (smplgpu_lattice_begin(m_ctx, bslot.data(), bq.data(), bgd.data(), bgoal.data(), (int)bslot.size()) < 0) return false;
+            ++m_stats.device_calls;
+        }
+        {
+            const double dt = t.lap();
+            m_stats.device_seconds += dt;
+            m_stats.setup_seconds += dt;
         }
         pending.clear();
         return true;
@@ -852,8 +686,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         for (int s = 0; s < n_slots; ++s) n_free += occupied[s] ? 0 : 1;
         if (pending.empty() && next_query < nq && (n_free >= refill_min || idle)) {
             // the first group is kept small so that the searches start while the other slots' BFS still runs
-            // (measured on one B200, 12 contexts x 171 slots: first group = 1/2 of the slots 1729 queries/s, 1/4 1655,
-            // 1/8 at every admission 1425 -- every bank run pays whole-bank passes; SMPLHOST_ADMIT_CHUNKS overrides)
+            // (SMPLHOST_ADMIT_CHUNKS overrides)
             static const int chunks = getenv("SMPLHOST_ADMIT_CHUNKS") ? std::max(1, atoi(getenv("SMPLHOST_ADMIT_CHUNKS"))) : 2;
             const int take = (first_fill || chunks > 4) ? std::max(1, n_slots / chunks) : n_slots;
             first_fill = false;
@@ -884,7 +717,7 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
             }
         }
 
-        // ---- one pipelined round: each group absorbs its previous batch and submits the next ----
+        // ---- one pipelined round: each group absorbs its previous round and submits the next ----
         for (int gi = 0; gi < NG; ++gi) {
             if (!absorb(gi)) return fail_dev();
             if (!expand(gi)) return fail_dev();
@@ -892,20 +725,17 @@ bool BatchPlanner::plan(const double* starts, const double* goals, int nq, std::
         m_stats.host_seconds += t.lap();
     }
     if (profile) {
-        fprintf(stderr, "[plan profile] rounds %d edges %lld expansions/ctx: absorb %.3f retire %.3f expand %.3f pack %.3f submit %.3f | "
+        fprintf(stderr, "[plan profile] rounds %d successor slots %lld: absorb %.3f retire %.3f pop %.3f pack %.3f submit %.3f | "
                         "device wait %.3f setup %.3f host %.3f s\n", m_stats.rounds, m_stats.edges_submitted, prof[0], prof[1],
                 prof[2], prof[3], prof[4], m_stats.device_seconds - m_stats.setup_seconds, m_stats.setup_seconds,
                 m_stats.host_seconds);
-        fprintf(stderr, "[plan profile]   absorb: coord+hash %.3f prefetch %.3f lookup/insert %.3f relax/heap %.3f s\n",
-                g_abs_prof[0], g_abs_prof[1], g_abs_prof[2], g_abs_prof[3]);
-        for (double& v : g_abs_prof) v = 0.0;
     }
     m_stats.edges_resolved_f64 = smplgpu_expand_batch_resolved(m_ctx) - resolved0;
-    // nothing can be in flight here: a group's queries finish in absorb or expand, and a batch is only
-    // submitted for queries that are not done; drain defensively anyway
+    // nothing can be in flight here: a group's queries finish in absorb or expand, and a round is only submitted for
+    // queries that are not done; drain defensively anyway
     for (int gi = 0; gi < NG; ++gi) {
         if (G[gi].in_flight) {
-            if (smplgpu_expand_batch_wait(m_ctx, gi, G[gi].verdict.data(), G[gi].h.data(), G[gi].gd.data(), G[gi].off.data()) < 0) return fail_dev();
+            if (smplgpu_lattice_expand_wait(m_ctx, gi, &G[gi].succ, &G[gi].h, &G[gi].count) < 0) return fail_dev();
         }
     }
     return true;

@@ -1,7 +1,10 @@
 // Host side of the caller of the hot path, B200-first: MANY independent ARA* searches on the
-// manipulation lattice advance in lock step, and every round submits the successors of all of
-// them to the device in ONE smplgpu_expand_batch call (edge validity + heuristic + goal test
-// inputs), so the per-launch batch is (active queries x ~8-22 edges) instead of one edge.
+// manipulation lattice advance in lock step, and every round submits ONE expansion per active
+// query to the device (smplgpu_lattice_expand_*): 8 bytes go out per expansion (bank slot, state
+// id), one word pair per successor comes back (state id | goal flag, heuristic).  Successor
+// generation, joint limits, edge validity, stateToCoord, the coordinate hash table
+// (getOrCreateState), the goal test and the heuristic run on the device (csrc/lattice.cuh); the
+// host keeps ARA* -- the OPEN lists and the search states -- indexed by the device's state ids.
 //
 // It mirrors, per query, the reference's
 //   ManipLattice::GetSuccs / checkAction / isGoal / stateToCoord   smpl/src/graph/manip_lattice.cpp:219-313, 1263-1289, 1511-1580, 1673-1687
@@ -10,8 +13,9 @@
 //   intrusive_heap                                                 smpl/include/smpl/detail/intrusive_heap.hpp
 // so that each query returns the same path, cost and expansion count as the reference-shaped
 // sequential planner (first solution at the initial epsilon; see SURVEY.md section 8 defect 2 for
-// the motion-primitive format and goal type decisions).  The OPEN lists, hash tables and the
-// lattice stay on the host, as BASELINE.json's north_star prescribes.
+// the motion-primitive format and goal type decisions).  Round 1 kept the hash tables and the lattice states on
+// the host as well; with hundreds of megabyte-sized lattices taking turns on a core, their cache misses bounded
+// plan queries/s by the host cores, so they moved next to the kernels that fill them.
 #ifndef SMPLHOST_BATCH_PLANNER_H
 #define SMPLHOST_BATCH_PLANNER_H
 
@@ -48,9 +52,11 @@ struct PlannerConfig
     double origin[3] = { 0, 0, 0 };
     double res = 0.02;
     int dims[3] = { 0, 0, 0 };
-    // host threads for the per-query work (successor generation, hashing, OPEN list updates); queries are
-    // independent, so the result does not depend on this
+    // host threads for the per-query work (OPEN list updates); queries are independent, so the result does not
+    // depend on this
     int n_threads = 1;
+    // fetch the joint values along every found path from the device (ManipLattice::extractPath)
+    bool want_path_states = true;
 };
 
 struct QueryResult
@@ -89,31 +95,6 @@ public:
     const BatchStats& stats() const { return m_stats; }
 
 private:
-    // Lattice states of one query, flat (no per-state allocation): state id -> coord[dof], q[dof], h, gdist,
-    // and an open-addressing hash table coord -> id (the role of ManipLattice's m_state_to_id, manip_lattice.h)
-    struct Lattice
-    {
-        int dof = 0;
-        std::vector<int> coords;
-        std::vector<double> qs;
-        std::vector<int> h, gdist;
-        std::vector<uint64_t> table; // size is a power of two; slot = low 32 hash bits << 32 | state id, EMPTY = all ones
-        static constexpr uint64_t EMPTY = ~0ull;
-        int size() const { return (int)h.size(); }
-        const double* q(int id) const { return &qs[(size_t)id * dof]; }
-        static uint64_t hash(const int* c, int dof)
-        {
-            uint64_t x = 0x9E3779B97F4A7C15ull;
-            for (int i = 0; i < dof; ++i) {
-                x ^= (uint64_t)(uint32_t)c[i] + 0x9E3779B97F4A7C15ull + (x << 6) + (x >> 2);
-            }
-            return x;
-        }
-        int find(const int* c, uint64_t hv) const;
-        int add(const int* c, const double* q, int hval, int gd, bool index, uint64_t hv);   // index = enter it in the table
-        void grow(uint32_t new_tag, int new_id);
-        void enter(uint32_t tag, int id);
-    };
     // g, h, f, eg are unsigned as in the reference's ARAStar::SearchState (arastar.h:176-187): a negative heuristic
     // (unreachable BFS cell: cost_per_cell * -1) sorts last in OPEN
     struct SState { unsigned int g, h, f, eg; int iteration_closed, bp, heap_index; bool touched; };
@@ -123,7 +104,7 @@ private:
         int slot;
         double goal[3];
         int goal_h;
-        Lattice lat;
+        int num_states;        // lattice size on the device (ids handed out so far, goal and start included)
         std::vector<SState> search;
         // 1-based binary heap of (f, state id): the key travels with the entry so that sifting reads one
         // contiguous array instead of one search state per comparison (same comparisons as intrusive_heap.h)
@@ -135,13 +116,7 @@ private:
         // (expanded state, lattice id of its first valid successor that satisfied the goal): what extractPath's
         // "cheapest valid goal action" search finds, every action costing the same (manip_lattice.cpp:2098-2124)
         std::vector<std::pair<int, int>> goal_succ;
-        // this round's successors (filled by expandOne, consumed by absorbOne)
-        std::vector<double> succ_q1;
-        std::vector<int> succ_coord;   // absorbOne scratch: lattice coordinates / table slots of the valid successors
-        std::vector<uint64_t> succ_hslot;   // full hash of successor e
-        std::vector<int> succ_id;
-        int n_succ;
-        int edge_begin;
+        int edge_begin;        // index of this query's expansion in its group's round
     };
 
     // minimal fork-join pool: run(f) calls f(tid) on every thread (the caller is tid 0)
@@ -168,26 +143,25 @@ private:
     smplgpu_ctx* m_ctx;
     PlannerConfig m_cfg;
     int m_max_concurrent;
-    std::vector<std::vector<double>> m_prim_deltas;
-    std::vector<bool> m_prim_short;
-    std::vector<double> m_coord_deltas;
-    std::vector<int> m_coord_vals;
+    std::vector<double> m_prim_deltas;     // [n_prims][dof], converses included
+    std::vector<uint8_t> m_prim_short;
+    int m_stride = 0;                      // successor words per expansion
     BatchStats m_stats;
 
-    void stateToCoord(const double* q, std::vector<int>& coord) const;
     bool checkJointLimits(const double* q) const;
     void worldToGrid(const double* p, int* cell) const;
     int computeKey(const SState& s) const;
     SState& sstate(Query& Q, int id);
-    void touch(Query& Q, int id);
+    void touch(Query& Q, int id, int h);
     void heapPush(Query& Q, int id);
     void heapPop(Query& Q);
     void percolateUp(Query& Q, size_t pivot);
     void percolateDown(Query& Q, size_t pivot);
     void finish(Query& Q, bool found);
     void initQuery(Query& Q, int index, int slot, const double* goal);
-    void expandOne(Query& Q);   // pop the next state and generate its in-limit successors (no device work)
-    void absorbOne(Query& Q, const uint8_t* verdict, const int32_t* h, const int32_t* gd, const double* off);
+    void expandOne(Query& Q);   // pop the next state (no device work)
+    void absorbOne(Query& Q, const int32_t* succ, const int32_t* h, int count);
+    bool fetchPathStates(Query& Q, std::string* err);
 };
 
 } // namespace smplhost

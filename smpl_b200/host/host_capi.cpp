@@ -261,6 +261,7 @@ int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* p, const d
     cfg.var_continuous.assign(p->var_continuous, p->var_continuous + p->dof);
     cfg.res = p->res;
     cfg.n_threads = p->n_threads > 0 ? p->n_threads : 1;
+    cfg.want_path_states = path_states != nullptr;
     for (int a = 0; a < 3; ++a) {
         cfg.xyz_tolerance[a] = p->xyz_tolerance[a];
         cfg.origin[a] = p->origin[a];
