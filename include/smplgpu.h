@@ -154,6 +154,11 @@ typedef struct smplgpu_robot_desc {
     const int32_t* seg_var;          /* [n_segments] planning variable or -1 */
     const double*  T_kin_to_planning;/* [12] */
     double xyz_offset[3];            /* GoalConstraint::xyz_offset (manip_lattice.cpp:2297-2312) */
+
+    /* the first n_robot_trees trees belong to robot links, the rest to attached bodies (0 = all of them are robot
+     * trees).  Only smplgpu_collision_distance tells them apart: the reference's clearance query covers the robot's
+     * trees alone (self_collision_model.cpp:1497-1510). */
+    int32_t n_robot_trees;
 } smplgpu_robot_desc;
 
 typedef struct smplgpu_ctx smplgpu_ctx;
@@ -235,6 +240,12 @@ int smplgpu_is_edges_valid(smplgpu_ctx* ctx, const double* q0, const double* q1,
                            uint8_t* verdict, int32_t* waypoint_counts);
 int smplgpu_is_edges_valid_dev(smplgpu_ctx* ctx, const double* q0_dev, const double* q1_dev, int n,
                                uint8_t* verdict_dev, int32_t* waypoint_counts_dev);
+/* CollisionSpace::collisionDistance batched (collision_space.cpp:496-500 -> SelfCollisionModelImpl::collisionDistance,
+ * self_collision_model.cpp:503-531, 1386-1468): the reference's clearance estimate per state, in metres -- the
+ * order-dependent branch-and-bound descent of the robot's sphere trees against the field (bound halves at every
+ * sphere that undercuts it), restated visit for visit; out[i] equals the reference build's value bit for bit
+ * (including its quirk: the sphere-pair term contributes the constant 1.0). */
+int smplgpu_collision_distance(smplgpu_ctx* ctx, const double* q, int n, double* out);
 /* kernel (1) alone: sphere centres of every tree node, double out[n][n_nodes][3]
  * (RobotCollisionState::updateSphereStates, robot_collision_state.h:546-581) */
 int smplgpu_fk_sphere_centers(smplgpu_ctx* ctx, const double* q, int n, double* out);

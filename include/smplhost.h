@@ -95,9 +95,12 @@ int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* params, co
                         int max_path, double* stats, double* path_states);
 
 /* The same with one planner thread per context (the reference's threading model: one CollisionSpace per planner
- * thread): queries are dealt round-robin to n_ctx contexts on the same GPU, each driven by its own host thread
- * with its own stream, BFS bank and lock-step pipeline, so the host-side lattice / OPEN-list work runs in
- * parallel without a barrier per round.  Every context must hold the same robot and distance field.
+ * thread): queries are dealt round-robin to n_ctx contexts, each driven by its own host thread (bound to its
+ * context's device with smplgpu_bind_thread) with its own stream, BFS bank, device lattices and lock-step pipeline,
+ * so the host-side OPEN-list work runs in parallel without a barrier per round.  The contexts may sit on the same
+ * GPU or on DIFFERENT GPUs of the box: one process drives all eight B200s without torchrun (the field of one context
+ * reaches the others with smplgpu_distance_field_dev_ptr + smplgpu_set_distance_field_dev; cudaMemcpy between peers).
+ * Every context must hold the same robot and distance field.
  * stats: sums over the contexts, except the seconds entries (maximum). */
 int smplhost_plan_batch_multi(smplgpu_ctx* const* ctxs, int n_ctx, const smplhost_plan_params* params,
                               const double* starts, const double* goals, int nq, int max_concurrent_per_ctx,
@@ -126,6 +129,10 @@ int smplhost_cc_interpolate_path(smplhost_adapters* a, const double* q0, const d
 /* GpuCollisionSpace::isStatesValid / isEdgesValid (the batched entry points behind the same object) */
 int smplhost_cc_is_states_valid(smplhost_adapters* a, const double* q, int n, uint8_t* valid);
 int smplhost_cc_is_edges_valid(smplhost_adapters* a, const double* q0, const double* q1, int n, uint8_t* valid);
+/* CollisionDistanceExtension::distanceToCollision (collision_checker.h:132-144) through getExtension: q1 = NULL is the
+ * state form = CollisionSpace::collisionDistance (collision_space.cpp:496-500); with q1 the minimum over the
+ * waypoints of the motion.  -1 on a missing extension. */
+double smplhost_cc_distance_to_collision(smplhost_adapters* a, const double* q0, const double* q1);
 /* RobotModel::checkJointLimits, ForwardKinematicsInterface::computePlanningLinkFK (robot_model.h:50-110) */
 int smplhost_rm_check_joint_limits(smplhost_adapters* a, const double* q);
 int smplhost_rm_compute_planning_link_fk(smplhost_adapters* a, const double* q, double* pose6);

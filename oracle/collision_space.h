@@ -50,6 +50,8 @@ struct OccupancyGrid
     explicit OccupancyGrid(EuclidDistanceMap* df) : m_grid(df) { }
     double getSquaredDist(double x, double y, double z) const { return m_grid->getMetricSquaredDistance(x, y, z); }
     double getDistance(int x, int y, int z) const { return m_grid->getDistance(x, y, z); }
+    /// OccupancyGrid::getDistanceFromPoint (occupancy_grid.h:228-231) -> getMetricDistance (distance_map.hpp:281-286)
+    double getDistanceFromPoint(double x, double y, double z) const { return m_grid->getDistance(x, y, z); }
     void addPointsToField(const std::vector<Vec3>& p) { m_grid->addPointsToMap(p); }
     void removePointsFromField(const std::vector<Vec3>& p) { m_grid->removePointsFromMap(p); }
     EuclidDistanceMap* m_grid;
@@ -93,6 +95,9 @@ public:
     bool isStateValid(const std::vector<double>& state);
     /// collision_space.cpp:538-581
     bool isStateToStateValid(const std::vector<double>& start, const std::vector<double>& finish, int* waypoint_count = nullptr);
+    /// CollisionSpace::collisionDistance (collision_space.cpp:496-500) -> SelfCollisionModelImpl::collisionDistance
+    /// (self_collision_model.cpp:503-531, 1386-1468, 1512-1642)
+    double collisionDistance(const std::vector<double>& state);
     /// same verdict, every waypoint visited in index order without early-out
     bool isStateToStateValidExhaustive(const std::vector<double>& start, const std::vector<double>& finish,
                                        int* waypoint_count, int* required_lookups);

@@ -238,6 +238,16 @@ int oracle_is_states_valid(oracle_scene* s, const double* q, int n, uint8_t* ver
     return 0;
 }
 
+int oracle_collision_distance(oracle_scene* s, const double* q, int n, double* out)
+{
+    std::vector<double> st(s->dof);
+    for (int i = 0; i < n; ++i) {
+        st.assign(q + (size_t)i * s->dof, q + (size_t)(i + 1) * s->dof);
+        out[i] = s->cc->collisionDistance(st);
+    }
+    return 0;
+}
+
 int oracle_report_states(oracle_scene* s, const double* q, int n, uint8_t* verdict,
                          int32_t* required_lookups, double* cell_margin, double* pair_margin)
 {

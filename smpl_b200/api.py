@@ -83,6 +83,7 @@ def gpu_lib():
         L.smplgpu_is_edges_valid_dev.argtypes = [vp, vp, vp, i, vp, vp]
         L.smplgpu_fk_sphere_centers.argtypes = [vp, dp, i, dp]
         L.smplgpu_check_joint_limits.argtypes = [vp, dp, i, bp]
+        L.smplgpu_collision_distance.argtypes = [vp, dp, i, dp]
         L.smplgpu_last_validity_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.smplgpu_bfs_set_walls_from_df.argtypes = [vp, d]
         L.smplgpu_bfs_set_walls.argtypes = [vp, i, i, i, bp]
@@ -451,6 +452,13 @@ class GpuContext:
         self._ck(self.L.smplgpu_fk_sphere_centers(self.h, _dp(q), len(q), _dp(out)), "fk_sphere_centers")
         return out
 
+    def collision_distance(self, q):
+        """CollisionSpace::collisionDistance per state (metres)."""
+        q = self._q(q)
+        out = np.zeros(len(q), np.float64)
+        self._ck(self.L.smplgpu_collision_distance(self.h, _dp(q), len(q), _dp(out)), "collision_distance")
+        return out
+
     def check_joint_limits(self, q):
         q = self._q(q)
         ok = np.zeros(len(q), np.uint8)
@@ -709,6 +717,11 @@ class Adapters:
         if self.H.smplhost_cc_is_edges_valid(self.h, _dp(q0), _dp(q1), len(q0), _bp(v)) != 0:
             raise SmplGpuError("isEdgesValid failed")
         return v
+
+    def distance_to_collision(self, q0, q1=None):
+        self.H.smplhost_cc_distance_to_collision.restype = C.c_double
+        self.H.smplhost_cc_distance_to_collision.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        return self.H.smplhost_cc_distance_to_collision(self.h, _dp(self._v(q0)), _dp(self._v(q1)) if q1 is not None else None)
 
     def check_joint_limits(self, q):
         return self.H.smplhost_rm_check_joint_limits(self.h, _dp(self._v(q)))

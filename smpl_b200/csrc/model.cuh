@@ -18,6 +18,7 @@ constexpr int MAX_TREE_DEPTH = 48;   // DFS stack bound (checked on the host)
 struct DevModel
 {
     int dof, n_links, n_nodes, n_trees, n_pairs, n_allowed, n_slots, n_segments;
+    int n_robot_trees, n_robot_pairs;   // trees of robot links come first; pairs with both trees among them
 
     // links, topological order
     int link_parent[MAX_LINKS];

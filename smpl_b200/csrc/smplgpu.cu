@@ -748,6 +748,11 @@ int smplgpu_set_robot(smplgpu_ctx* ctx, const smplgpu_robot_desc* d)
     m.n_nodes = d->n_nodes;
     m.n_trees = d->n_trees;
     m.n_pairs = d->n_pairs;
+    m.n_robot_trees = (d->n_robot_trees > 0 && d->n_robot_trees <= d->n_trees) ? d->n_robot_trees : d->n_trees;
+    m.n_robot_pairs = 0;
+    for (int k = 0; k < d->n_pairs; ++k) {
+        if (d->pair_a[k] < m.n_robot_trees && d->pair_b[k] < m.n_robot_trees) ++m.n_robot_pairs;
+    }
     m.n_allowed = d->n_allowed_leaf_pairs;
     m.n_segments = d->n_segments;
 
@@ -1776,6 +1781,28 @@ int smplgpu_fk_sphere_centers(smplgpu_ctx* ctx, const double* q, int n, double* 
     const int vt = ctx->validity_threads;
     fk_centers_kernel<<<(n + vt - 1) / vt, vt, validity_smem(ctx), ctx->stream>>>(
         ctx->d_model, dq, n, dout);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int smplgpu_collision_distance(smplgpu_ctx* ctx, const double* q, int n, double* out)
+{
+    if (!ctx || n < 0) return SMPLGPU_ERR_INVALID;
+    int r = need_scene(ctx);
+    if (r) return r;
+    if (n == 0) return 0;
+    if (!q || !out) return fail(ctx, SMPLGPU_ERR_INVALID, "null pointer");
+    const int dof = ctx->h_model->dof;
+    const size_t qb = (size_t)n * dof * sizeof(double), ob = (size_t)n * sizeof(double);
+    r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, qb + ob + 64);
+    if (r) return r;
+    double* dq = (double*)ctx->d_misc;
+    double* dout = dq + (size_t)n * dof;
+    CU(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, ctx->stream));
+    collision_distance_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(ctx->d_model, ctx->d_df, ctx->grid, ctx->res, ctx->padding, dq, n, dout);
     ++ctx->launches;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, ctx->stream));

@@ -557,6 +557,78 @@ fk_centers_kernel(const DevModel* __restrict__ M, const double* __restrict__ q, 
     }
 }
 
+// CollisionSpace::collisionDistance (collision_space.cpp:496-500 -> self_collision_model.cpp:503-531), one thread per
+// state, IEEE double, the reference's visit order (the result depends on it):
+//   robotVoxelsCollisionDistance (:1386-1468): roots of the ROBOT's trees pushed in group order, popped from the back;
+//     clearance = res * sqrt(d2(cell)) - (r + padding) (SphereCollisionDistance, collision_operations.h:81-89; 0 field
+//     distance outside the grid); a sphere undercutting the bound d halves into it, d = max(0, 0.5 * clearance), and
+//     splits, the child with the larger radius visited first; d == 0 ends the descent.
+//   attached-body terms: "TODO: implement" in the reference, +infinity.
+//   robotSpheresCollisionDistance (:1470-1487, 1512-1642): every checked robot pair contributes `return true` = 1.0.
+__global__ void collision_distance_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ df, GridParams G,
+                                          double res, double padding, const double* __restrict__ q, int n,
+                                          double* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const double* qa = q + (size_t)i * M->dof;
+    Xf T[MAX_LINKS];   // per-thread (local memory): every link transform, the descent visits trees in stack order
+    for (int l = 0; l < M->n_links; ++l) {
+        const int v = M->link_var[l];
+        const double val = v >= 0 ? qa[v] : M->link_const[l];
+        Xf J, P;
+        joint_transform(M, l, val, J);
+        const int p = M->link_parent[l];
+        if (p < 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) P.m[k] = M->link_base[l][k];
+        } else {
+            P = T[p];
+        }
+        xf_mul(P, J, T[l]);
+    }
+    int stack[MAX_TREES + MAX_TREE_DEPTH];
+    int sp = 0;
+    for (int t = 0; t < M->n_robot_trees; ++t) {
+        stack[sp++] = M->tree_root[t];
+    }
+    double d = __longlong_as_double(0x7FF0000000000000LL);   // +infinity
+    while (sp > 0) {
+        const int node = stack[--sp];
+        double x, y, z;
+        xf_point(T[M->node_link[node]], M->node_center[node][0], M->node_center[node][1], M->node_center[node][2], x, y, z);
+        const int d2 = df_lookup(df, G, x, y, z);            // 0 outside the grid, like getMetricDistance
+        const double dist = res * sqrt((double)d2);          // m_sqrt_table (distance_map.hpp:142-146)
+        const double effective_radius = M->node_radius[node] + padding;
+        const double obs_dist = dist - effective_radius;
+        if (obs_dist >= d) {
+            continue;
+        }
+        d = fmax(0.0, (1.0 - 0.5) * obs_dist);
+        if (d == 0.0) {
+            break;
+        }
+        const int left = M->node_left[node];
+        if (left < 0) {
+            continue;
+        }
+        const int right = M->node_right[node];
+        if (M->node_radius[left] > M->node_radius[right]) {
+            stack[sp++] = right;
+            stack[sp++] = left;
+        } else {
+            stack[sp++] = left;
+            stack[sp++] = right;
+        }
+    }
+    if (M->n_robot_pairs > 0 && 1.0 < d) {
+        d = 1.0;
+    }
+    out[i] = d;
+}
+
 // KDLRobotModel::checkJointLimits (kdl_robot_model.cpp:173-189, 210-235, 326-337) for one state
 __device__ __forceinline__ bool joint_limits_ok(const DevModel* __restrict__ M, const double* q)
 {

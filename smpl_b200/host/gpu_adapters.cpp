@@ -259,9 +259,43 @@ bool GpuCollisionSpace::interpolatePath(const RobotState& start, const RobotStat
 Extension* GpuCollisionSpace::getExtension(size_t class_code)
 {
     if (class_code == GetClassCode<sbpl::motion::CollisionChecker>()) {
-        return this;
+        return static_cast<sbpl::motion::CollisionChecker*>(this);
+    }
+    if (class_code == GetClassCode<sbpl::motion::CollisionDistanceExtension>()) {
+        return static_cast<sbpl::motion::CollisionDistanceExtension*>(this);
     }
     return nullptr;
+}
+
+// CollisionSpace::collisionDistance (collision_space.cpp:496-500); errors give 0 (no clearance), never exceptions
+double GpuCollisionSpace::distanceToCollision(const RobotState& state)
+{
+    if ((int)state.size() != m_dof) {
+        return 0.0;
+    }
+    double d = 0.0;
+    if (smplgpu_collision_distance(m_ctx, state.data(), 1, &d) != 0) {
+        return 0.0;
+    }
+    return d;
+}
+
+double GpuCollisionSpace::distanceToCollision(const RobotState& start, const RobotState& finish)
+{
+    std::vector<RobotState> path;
+    if (!interpolatePath(start, finish, path)) {
+        return 0.0;
+    }
+    if (path.empty()) {
+        return distanceToCollision(start);   // zero-length motion
+    }
+    std::vector<double> d;
+    if (!collisionDistances(path, d)) {
+        return 0.0;
+    }
+    double best = d[0];
+    for (double v : d) best = std::min(best, v);
+    return best;
 }
 
 static bool flatten(const std::vector<RobotState>& states, int dof, std::vector<double>& buf)
@@ -286,6 +320,18 @@ bool GpuCollisionSpace::isStatesValid(const std::vector<RobotState>& states, std
         return false;
     }
     return smplgpu_is_states_valid(m_ctx, m_buf0.data(), (int)states.size(), valid.data()) == 0;
+}
+
+bool GpuCollisionSpace::collisionDistances(const std::vector<RobotState>& states, std::vector<double>& dist)
+{
+    dist.assign(states.size(), 0.0);
+    if (states.empty()) {
+        return true;
+    }
+    if (!flatten(states, m_dof, m_buf0)) {
+        return false;
+    }
+    return smplgpu_collision_distance(m_ctx, m_buf0.data(), (int)states.size(), dist.data()) == 0;
 }
 
 bool GpuCollisionSpace::isEdgesValid(const std::vector<RobotState>& starts, const std::vector<RobotState>& finishes,

@@ -76,7 +76,7 @@ private:
     bool expand(const double* q);
 };
 
-class GpuCollisionSpace : public sbpl::motion::CollisionChecker
+class GpuCollisionSpace : public sbpl::motion::CollisionChecker, public sbpl::motion::CollisionDistanceExtension
 {
 public:
     GpuCollisionSpace(smplgpu_ctx* ctx, int dof) : m_ctx(ctx), m_dof(dof) { }
@@ -91,6 +91,16 @@ public:
     bool interpolatePath(const sbpl::motion::RobotState& start, const sbpl::motion::RobotState& finish,
                          std::vector<sbpl::motion::RobotState>& path) override;
     sbpl::motion::Extension* getExtension(size_t class_code) override;
+
+    // ---- sbpl::motion::CollisionDistanceExtension (collision_checker.h:132-144) ----
+    /// CollisionSpace::collisionDistance(state) (collision_space.cpp:496-500): the reference's clearance estimate
+    double distanceToCollision(const sbpl::motion::RobotState& state) override;
+    /// No class of the reference implements the motion form; here: the minimum of distanceToCollision over the
+    /// waypoints isStateToStateValid checks (interpolatePath), all of them in one device call
+    double distanceToCollision(const sbpl::motion::RobotState& start, const sbpl::motion::RobotState& finish) override;
+    /// CollisionSpace::collisionDistance, as the reference names it
+    double collisionDistance(const sbpl::motion::RobotState& state) { return distanceToCollision(state); }
+    bool collisionDistances(const std::vector<sbpl::motion::RobotState>& states, std::vector<double>& dist);
 
     // ---- batched entry points: one GetSuccs submits every successor / edge at once ----
     bool isStatesValid(const std::vector<sbpl::motion::RobotState>& states, std::vector<uint8_t>& valid);

@@ -525,6 +525,15 @@ int smplhost_cc_is_edges_valid(smplhost_adapters* a, const double* q0, const dou
     return 0;
 }
 
+double smplhost_cc_distance_to_collision(smplhost_adapters* a, const double* q0, const double* q1)
+{
+    if (!a || !q0) return -1.0;
+    auto* ext = a->cc->getExtension(sbpl::motion::GetClassCode<sbpl::motion::CollisionDistanceExtension>());
+    auto* cd = dynamic_cast<sbpl::motion::CollisionDistanceExtension*>(ext);
+    if (!cd) return -1.0;
+    return q1 ? cd->distanceToCollision(to_state(a, q0), to_state(a, q1)) : cd->distanceToCollision(to_state(a, q0));
+}
+
 int smplhost_rm_check_joint_limits(smplhost_adapters* a, const double* q)
 {
     if (!a || !q) return -1;

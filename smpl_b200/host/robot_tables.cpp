@@ -1044,6 +1044,7 @@ void RobotTables::rebuild()
     m_desc.node_left = o_node_left.data();
     m_desc.node_right = o_node_right.data();
     m_desc.n_trees = (int)o_tree_root.size();
+    m_desc.n_robot_trees = n_robot_trees;
     m_desc.tree_root = o_tree_root.data();
     m_desc.n_pairs = (int)o_pair_a.size();
     m_desc.pair_a = o_pair_a.data();

@@ -78,6 +78,15 @@ public:
     virtual void setClearanceThreshold(double) { }
 };
 
+/// smpl/collision_checker.h:132-144
+class CollisionDistanceExtension : public virtual Extension
+{
+public:
+    virtual ~CollisionDistanceExtension() { }
+    virtual double distanceToCollision(const RobotState& state) = 0;
+    virtual double distanceToCollision(const RobotState& start, const RobotState& finish) = 0;
+};
+
 class RobotModel : public virtual Extension
 {
 public:

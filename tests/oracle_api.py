@@ -422,6 +422,13 @@ class OracleScene:
         self.L.oracle_sphere_centers(self.h, _dp(q), len(q), _dp(out))
         return out
 
+    def collision_distance(self, q):
+        """CollisionSpace::collisionDistance per state."""
+        q = self._q(q)
+        out = np.zeros(len(q), np.float64)
+        self.L.oracle_collision_distance(self.h, _dp(q), len(q), _dp(out))
+        return out
+
     def node_table(self):
         nn = self.num_nodes()
         out = np.zeros((nn, 8), np.float64)
@@ -685,6 +692,13 @@ class RefCollisionScene:
         out = np.zeros((max_wp, self.dof), np.float64)
         n = self.R.refcc_edge_waypoints(self.h, _dp(q0), _dp(q1), _dp(out), max_wp)
         return out[:n].copy()
+
+    def collision_distance(self, q):
+        """the reference's own CollisionSpace::collisionDistance per state."""
+        q = self._q(q)
+        out = np.zeros(len(q), np.float64)
+        self.R.refcc_collision_distance(self.h, _dp(q), len(q), _dp(out))
+        return out
 
     def node_table(self, max_nodes=4096):
         out = np.zeros((max_nodes, 8), np.float64)

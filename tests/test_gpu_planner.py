@@ -185,6 +185,38 @@ def test_one_planner_thread_per_context_gives_the_same_plans(tabletop):
         c.close()
 
 
+def _device_count():
+    import ctypes as C
+    n = C.c_int(0)
+    try:
+        rt = C.CDLL("libcudart.so")
+        return n.value if rt.cudaGetDeviceCount(C.byref(n)) == 0 else 0
+    except OSError:
+        import torch
+        return torch.cuda.device_count()
+
+
+@pytest.mark.skipif(_device_count() < 2, reason="needs two GPUs in one process")
+def test_contexts_on_different_gpus_in_one_process_give_the_same_plans(tabletop):
+    """smplhost_plan_batch_multi with contexts on DIFFERENT devices: a C++ caller uses an 8-GPU box from one process
+    (one planner thread per context, each bound to its context's device) without torchrun."""
+    scene, o, ctx, tables = tabletop
+    params = scenes.PlanParams(scene.dof)
+    params.max_expansions = 800
+    starts, goals = scenes.tabletop_queries(30, seed=17)
+    single, _ = api.plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=8)
+    other, _ = api.setup_context(scene, device=1)
+    ctxs = [ctx, other, api.clone_context(other, scene, tables, device=1)]
+    multi, stats = api.plan_batch(ctxs, scene, tables, params, starts, goals, max_concurrent=4)
+    for a, b in zip(single, multi):
+        assert (a["success"], a["expansions"], a["cost"], a["num_states"]) == \
+               (b["success"], b["expansions"], b["cost"], b["num_states"])
+        assert np.array_equal(a["path_ids"], b["path_ids"])
+    for c in ctxs[1:]:
+        c.close()
+    ctx.L.smplgpu_bind_thread(ctx.h)   # creating a context on device 1 made it this thread's current device
+
+
 def test_ubr1_with_attached_object_queries_match_oracle():
     """Config 4 shape: UBR1 arm, attached box, extra ACM entries; queries dealt round-robin as on 2 GPUs."""
     from smpl_b200 import sharding

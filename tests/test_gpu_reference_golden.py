@@ -86,3 +86,31 @@ def test_batch_planner_returns_the_reference_builds_plans(name):
                         [int(i) for i in g["path_ids"]]] == want
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("name", ["pr2_tabletop", "pr2_clutter", "pr2_clutter_padded", "ubr1_attached_box", "pr2_dual_arm_15dof"])
+def test_collision_distance_equals_the_reference_builds(name):
+    """smplgpu_collision_distance = CollisionSpace::collisionDistance (collision_space.cpp:496-500): the clearance of
+    1500 states per scene, bit for bit the values the reference build returned (tools/gen_golden_collision_distance.py);
+    and through the adapter's CollisionDistanceExtension (collision_checker.h:132-144)."""
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "collision_distance_reference.npz"))
+    scene, attach = case_scene(name)
+    ctx, tables = api.setup_context(scene)
+    try:
+        if attach is not None:
+            tables.attach_box(ctx, *attach)
+            tables.apply(ctx)
+        q, want = g[name + "/q"], g[name + "/distance"]
+        got = ctx.collision_distance(q)
+        assert np.array_equal(got, want)
+        ad = api.Adapters(ctx, scene, tables)
+        for i in (0, 1, 2, len(q) // 2):
+            assert ad.distance_to_collision(q[i]) == want[i]
+        # motion form: the minimum over the waypoints of the motion
+        a, b = q[3], q[3] + 0.2
+        wp = ad.interpolate_path(a, b)
+        assert ad.distance_to_collision(a, b) == ctx.collision_distance(wp).min()
+        ad.close()
+        assert len(ctx.collision_distance(np.zeros((0, scene.dof)))) == 0
+    finally:
+        ctx.close()

@@ -209,3 +209,31 @@ def test_shape_objects_occupy_the_cells_of_the_reference_insert_object():
         occupied[tuple(g[inside].T)] = True
     assert occupied_ref.sum() > 4000
     assert np.array_equal(occupied, occupied_ref)
+
+
+DIST_CASES = ["pr2_tabletop", "pr2_clutter", "pr2_clutter_padded", "ubr1_attached_box", "pr2_dual_arm_15dof"]
+
+
+@needs_ref
+@pytest.mark.parametrize("name", DIST_CASES)
+def test_collision_distance_equals_reference_build(name):
+    """CollisionSpace::collisionDistance (collision_space.cpp:496-500; self_collision_model.cpp:503-531, 1386-1468): the
+    order-dependent clearance descent, restated visit for visit -- equal to the reference build bit for bit, including
+    its quirk (every checked sphere-tree pair contributes `return true` = 1.0, :1640-1642)."""
+    scene, attach = case_scene(name)
+    o = make_restatement(scene, attach)
+    r = make_reference(scene, attach)
+    q, _, _ = case_inputs(scene, r, 2000, 10, seed=5)
+    d_o, d_r = o.collision_distance(q), r.collision_distance(q)
+    assert np.array_equal(d_o, d_r)
+    # a clearance of 0 is what an invalid state gets from the field term (a failing leaf has obs_dist < 0)
+    v = o.is_states_valid(q)
+    assert (d_o >= 0).all() and (d_o[v == 0] <= 1.0).all()
+
+
+@pytest.mark.parametrize("name", DIST_CASES)
+def test_collision_distance_golden_from_reference_build(name):
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "collision_distance_reference.npz"))
+    scene, attach = case_scene(name)
+    o = make_restatement(scene, attach)
+    assert np.array_equal(o.collision_distance(g[name + "/q"]), g[name + "/distance"])
