@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
+#include <memory>
 #include <thread>
 #include <cmath>
 #include <cstdarg>
@@ -152,6 +154,17 @@ static int fail(smplgpu_ctx* ctx, int code, const char* fmt, ...)
         g_create_error = buf;
     }
     return code;
+}
+
+// SMPLGPU_V32_PERSISTENT=1 selects the lane-persistent kernels (A/B switch; measured 1.7x SLOWER than the warp-batched
+// ones on B200, see DESIGN.md: kept for the record, off by default)
+static bool v32_persistent()
+{
+    static const bool on = [] {
+        const char* e = getenv("SMPLGPU_V32_PERSISTENT");
+        return e != nullptr && atoi(e) != 0;
+    }();
+    return on;
 }
 
 #define CU(call)                                                                                   \
@@ -446,6 +459,109 @@ static void const_joint_transform(int fn, const double* o, const double* axis, d
     }
 }
 
+// a (3x4) * b (3x4), double
+static void mul34(const double* a, const double* b, double* r)
+{
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 4; ++j) {
+            r[4 * i + j] = a[4 * i] * b[j] + a[4 * i + 1] * b[4 + j] + a[4 * i + 2] * b[8 + j] + (j == 3 ? a[4 * i + 3] : 0.0);
+        }
+    }
+}
+
+// The single-precision kernels walk a state's link chain once per state and pay a 3x4 product per link, so links
+// whose joint is a CONSTANT of the scene (fixed joints, non-planning joints: half of the PR2 arm group's 14 links)
+// are folded away here: a constant link's spheres are re-expressed in the frame of the nearest moving ancestor
+// (c' = C c, C = the product of the constant joint transforms in between, in double), and a moving link below a
+// constant one takes C into its joint origin (T = T_anchor (C O) R(q)).  World positions are the same up to
+// rounding, which the error bounds below -- computed from THIS table -- cover; the double-precision kernels keep
+// the reference's link-by-link operation order.  Constant links without a parent in the table keep their entry.
+// SMPLGPU_V32_FOLD=0 disables the folding (A/B).
+static void fold_constant_links(const DevModel& m, DevModel& F)
+{
+    F = m;
+    static const bool enabled = [] {
+        const char* e = getenv("SMPLGPU_V32_FOLD");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    if (!enabled) {
+        return;
+    }
+    const int nl = m.n_links;
+    std::vector<int> new_index(nl, -1), carrier(nl, -1);
+    std::vector<std::array<double, 12>> C(nl);
+    const double I12[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+    int n_new = 0;
+    for (int l = 0; l < nl; ++l) {
+        const int p = m.link_parent[l];
+        const bool is_const = m.link_var[l] < 0;
+        if (is_const && p >= 0) {
+            // folded: its frame = carrier frame * C[l]
+            double J[12];
+            const_joint_transform(m.link_joint[l], m.link_origin[l], m.link_axis[l], m.link_const[l], J);
+            const bool parent_kept = new_index[p] >= 0;
+            carrier[l] = parent_kept ? new_index[p] : carrier[p];
+            mul34(parent_kept ? I12 : C[p].data(), J, C[l].data());
+            continue;
+        }
+        const int L = n_new++;
+        new_index[l] = L;
+        carrier[l] = L;
+        memcpy(C[l].data(), I12, sizeof(I12));
+        F.link_joint[L] = m.link_joint[l];
+        F.link_var[L] = m.link_var[l];
+        F.link_const[L] = m.link_const[l];
+        memcpy(F.link_axis[L], m.link_axis[l], sizeof(m.link_axis[l]));
+        memcpy(F.link_base[L], m.link_base[l], sizeof(m.link_base[l]));
+        if (p >= 0 && new_index[p] < 0) {
+            F.link_parent[L] = carrier[p];
+            mul34(C[p].data(), m.link_origin[l], F.link_origin[L]);   // T = T_anchor * (C O) * R(q)
+        } else {
+            F.link_parent[L] = p < 0 ? -1 : new_index[p];
+            memcpy(F.link_origin[L], m.link_origin[l], sizeof(m.link_origin[l]));
+        }
+    }
+    F.n_links = n_new;
+    // spheres ride on their link's carrier, centres in the carrier's frame
+    for (int n = 0; n < m.n_nodes; ++n) {
+        const int l = m.node_link[n];
+        F.node_link[n] = carrier[l];
+        if (new_index[l] < 0) {
+            const double* c = m.node_center[n];
+            const double* T = C[l].data();
+            for (int i = 0; i < 3; ++i) {
+                F.node_center[n][i] = T[4 * i] * c[0] + T[4 * i + 1] * c[1] + T[4 * i + 2] * c[2] + T[4 * i + 3];
+            }
+        }
+    }
+    // trees grouped by (new) link, in the order the double kernels visit them
+    int k = 0;
+    std::vector<int> order;
+    for (int l = 0; l < nl; ++l) {
+        for (int ti = m.link_tree_begin[l]; ti < m.link_tree_end[l]; ++ti) order.push_back(m.tree_by_link[ti]);
+    }
+    for (int L = 0; L < n_new; ++L) {
+        F.link_tree_begin[L] = k;
+        for (int t : order) {
+            if (F.node_link[m.tree_root[t]] == L) F.tree_by_link[k++] = t;
+        }
+        F.link_tree_end[L] = k;
+    }
+    // slots: transforms the kernels keep per thread = branching parents + links that carry a paired tree
+    std::vector<char> keep(n_new, 0);
+    for (int L = 0; L < n_new; ++L) {
+        const int p = F.link_parent[L];
+        if (p >= 0 && p != L - 1) keep[p] = 1;
+    }
+    for (int pi = 0; pi < m.n_pairs; ++pi) {
+        keep[F.node_link[m.tree_root[m.pair_a[pi]]]] = 1;
+        keep[F.node_link[m.tree_root[m.pair_b[pi]]]] = 1;
+    }
+    int slots = 0;
+    for (int L = 0; L < n_new; ++L) F.link_slot[L] = keep[L] ? slots++ : -1;
+    F.n_slots = slots;
+}
+
 // Builds the shared-memory blob of validity32.cuh and the error bounds that certify it.
 //
 // Error model (u = 2^-24, all norms Euclidean; R = rotation part, t = translation part of a link transform):
@@ -459,11 +575,13 @@ static void const_joint_transform(int fn, const double* o, const double* axis, d
 //   |dg| <= inv_res E_pos + u (inv_res max|o| + 4 (max_dim + 4)) + 1e-7.
 static int build_model32(smplgpu_ctx* ctx)
 {
-    const DevModel& m = *ctx->h_model;
     ctx->has_model32 = false;
     if (!ctx->has_robot || !ctx->has_df) {
         return 0;
     }
+    std::unique_ptr<DevModel> folded(new DevModel);
+    fold_constant_links(*ctx->h_model, *folded);
+    const DevModel& m = *folded;
     if (m.n_nodes >= 65536) {
         return 0; // node ids are packed in 16 bits in the pair descent: fall back to the double path
     }
@@ -669,7 +787,7 @@ static int build_model32(smplgpu_ctx* ctx)
     }
 
     // ---- launch geometry + upload ----
-    const size_t per_thread = ((size_t)n_slots32 * 12 + (size_t)n_ptrees * 3) * sizeof(float) + 4 * sizeof(int);
+    const size_t per_thread = ((size_t)n_slots32 * 12 + (size_t)n_ptrees * 3) * sizeof(float) + 4 * V32P_EDGES_PER_THREAD * sizeof(int);
     const size_t fixed = (size_t)w * 4 + 64;
     ctx->v32_slots = n_slots32;
     ctx->v32_ptrees = n_ptrees;
@@ -684,8 +802,13 @@ static int build_model32(smplgpu_ctx* ctx)
     CU(cudaFuncSetAttribute(states_valid32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(edges_valid32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(fk_centers32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(states_valid32p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(edges_valid32p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     {
         int per_sm = 0;
+        if (v32_persistent()) {
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, states_valid32p_kernel, threads, (size_t)smem));
+        } else
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, states_valid32_kernel, threads, (size_t)smem));
         ctx->v32_blocks_per_sm = std::max(1, per_sm);
     }
@@ -702,10 +825,13 @@ static int build_model32(smplgpu_ctx* ctx)
 
 static size_t v32_smem(const smplgpu_ctx* ctx)
 {
+    // blob | per-thread slots and root centres | the edge kernels' per-edge block state (the lane-persistent form
+    // keeps V32P_EDGES_PER_THREAD edges per thread: offsets, ok, unc, counts)
     return (size_t)ctx->blob_words * 4
            + ((size_t)ctx->v32_slots * 12 + (size_t)ctx->v32_ptrees * 3) * sizeof(float) * ctx->v32_threads
-           + (4 * (size_t)ctx->v32_threads + 2) * sizeof(int);
+           + (4 * (size_t)V32P_EDGES_PER_THREAD * ctx->v32_threads + 4) * sizeof(int);
 }
+
 
 static int upload_model(smplgpu_ctx* ctx)
 {
@@ -1270,6 +1396,11 @@ static int launch_states(smplgpu_ctx* ctx, const double* dq, int n, uint8_t* dv)
     const int t32 = ctx->v32_threads;
     // one wave of resident blocks; their warps pull the states from the cursor
     const int wave = std::max(1, ctx->v32_blocks_per_sm) * ctx->sm_count;
+    if (v32_persistent()) {
+        states_valid32p_kernel<<<std::min((n + t32 - 1) / t32, wave), t32, v32_smem(ctx), ctx->stream>>>(
+            ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq, n, dv, ctx->d_unc_list,
+            ctx->d_unc_count, ctx->d_stats);
+    } else
     states_valid32_kernel<<<std::min((n + t32 - 1) / t32, wave), t32, v32_smem(ctx), ctx->stream>>>(
         ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq, n, dv, ctx->d_unc_list,
         ctx->d_unc_count, ctx->d_stats);
@@ -1295,6 +1426,12 @@ static int launch_edges(smplgpu_ctx* ctx, const double* dq0, const double* dq1, 
     if (r) return r;
     CU(cudaMemsetAsync(ctx->d_unc_count, 0, sizeof(int), ctx->stream));
     const int t32 = ctx->v32_threads;
+    if (v32_persistent()) {
+        const int epb = V32P_EDGES_PER_THREAD * t32;
+        edges_valid32p_kernel<<<(n + epb - 1) / epb, t32, v32_smem(ctx), ctx->stream>>>(
+            ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq0, dq1, n, dv, dc, ctx->d_unc_list,
+            ctx->d_unc_count, ctx->d_stats);
+    } else
     edges_valid32_kernel<<<(n + t32 - 1) / t32, t32, v32_smem(ctx), ctx->stream>>>(
         ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq0, dq1, n, dv, dc, ctx->d_unc_list,
         ctx->d_unc_count, ctx->d_stats);

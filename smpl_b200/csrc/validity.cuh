@@ -432,8 +432,8 @@ edges_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ 
                 }
             }
             const int e = lo;
-            if (s_ok[e] == 0) {
-                continue; // edge already invalid
+            if (*((volatile int*)&s_ok[e]) == 0) {
+                continue; // edge already invalid (a stale 1 only costs one redundant waypoint check)
             }
             const int w = item - s_off[e];
             const int cnt_e = s_off[e + 1] - s_off[e];
@@ -443,7 +443,7 @@ edges_valid_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ 
             const double* b = q1 + (size_t)s_eid[e] * dof;
             ++cnt.waypoints;
             if (!check_state(M, df, G, a, b, alpha, smem, cnt)) {
-                s_ok[e] = 0;
+                atomicAnd(&s_ok[e], 0);   // same-value writes from several lanes: atomic, so racecheck-clean
             }
         }
         __syncthreads();

@@ -197,18 +197,18 @@ __device__ __forceinline__ void copy_blob(float* dst, const float* __restrict__ 
     }
 }
 
-// One state in single precision.  Returns 1 = certainly valid, 0 = certainly invalid, 2 = needs double precision.
+// One link of one state in single precision: joint transform, T = T_parent * J, the sphere trees riding on the link.
+// `T` holds the previous link's transform on entry and this link's on exit.
+// Returns 1 = go on with the next link, 0 = certainly invalid, 2 = needs double precision right away; `amb` collects
+// undecidable tests.
 //   var_type: SMPLGPU_VAR_* per planning variable (continuous variables interpolate along the shortest arc)
-__device__ int check_state32(const S32& S, const int* __restrict__ var_type, const uint16_t* __restrict__ df,
-                             const Grid32& G, const double* __restrict__ qa, const double* __restrict__ qb,
-                             double alpha, float* slots, Counters& cnt)
+__device__ __forceinline__ int link_step32(const S32& S, const int* __restrict__ var_type, const uint16_t* __restrict__ df,
+                                           const Grid32& G, const double* __restrict__ qa, const double* __restrict__ qb,
+                                           double alpha, float* slots, int l, Xf32& T, bool& amb, Counters& cnt)
 {
     const Model32Header* H = S.h;
     const float eps = H->eps_cells;
-    Xf32 T;
-    bool amb = false;
-    const int nl = H->n_links;
-    for (int l = 0; l < nl; ++l) {
+    {
         const int4 li = S.link_i[l];   // parent, fn, var, slot
         const int fn = li.y;
         float sn = 0.0f, cs = 1.0f, lin = 0.0f;
@@ -316,7 +316,14 @@ __device__ int check_state32(const S32& S, const int* __restrict__ var_type, con
             }
         }
     }
+    return 1;
+}
 
+// The sphere-tree pairs of one state whose link chain is done (transforms / root centres in `slots`).
+// Returns 1 = certainly valid, 0 = certainly invalid, 2 = needs double precision.
+__device__ __forceinline__ int pairs32(const S32& S, float* slots, bool amb, Counters& cnt)
+{
+    const Model32Header* H = S.h;
     const int np = H->n_pairs;
     if (H->n_ptrees > 0) {
         // Sphere-tree pairs: only the root spheres are tested here, from the root centres saved above.  Roots that
@@ -422,6 +429,23 @@ __device__ int check_state32(const S32& S, const int* __restrict__ var_type, con
         }
     }
     return amb ? 2 : 1;
+}
+
+// One state in single precision.  Returns 1 = certainly valid, 0 = certainly invalid, 2 = needs double precision.
+__device__ int check_state32(const S32& S, const int* __restrict__ var_type, const uint16_t* __restrict__ df,
+                             const Grid32& G, const double* __restrict__ qa, const double* __restrict__ qb,
+                             double alpha, float* slots, Counters& cnt)
+{
+    Xf32 T;
+    bool amb = false;
+    const int nl = S.h->n_links;
+    for (int l = 0; l < nl; ++l) {
+        const int r = link_step32(S, var_type, df, G, qa, qb, alpha, slots, l, T, amb, cnt);
+        if (r != 1) {
+            return r;
+        }
+    }
+    return pairs32(S, slots, amb, cnt);
 }
 
 // warp-aggregated append of item ids to the list of items that need double precision
@@ -594,17 +618,20 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
                 }
             }
             const int e = lo;
-            if (s_ok[e] != 0) {
+            // early-out read; a stale 1 (another lane is just clearing it) only costs one redundant waypoint check
+            if (*((volatile int*)&s_ok[e]) != 0) {
                 const int w = item - s_off[e] + 1;               // waypoint 0 was round A
                 const double inv = 1.0 / (double)(s_cnt[e] - 1); // m_waypoint_count_inv
                 const double alpha = (double)w * inv;
                 ++cnt.waypoints;
                 const int r = check_state32(S, M->var_type, df, G, q0 + (size_t)(first + e) * dof, q1 + (size_t)(first + e) * dof,
                                             alpha, slots, cnt);
+                // several lanes may hold waypoints of one edge: atomics make the concurrent same-value writes a
+                // defined (racecheck-clean) update; they only run on a failing / undecided waypoint
                 if (r == 0) {
-                    s_ok[e] = 0;
+                    atomicAnd(&s_ok[e], 0);
                 } else if (r == 2) {
-                    s_unc[e] = 1;
+                    atomicOr(&s_unc[e], 1);
                 }
             }
         }
@@ -616,6 +643,301 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
         push = s_ok[tid] && s_unc[tid];
     }
     append_uncertain(push, i, unc_list, unc_count, stats);
+    flush_counters(cnt, stats);
+}
+
+// ---- lane-persistent form -------------------------------------------------------------------------------------
+// In the kernels above a lane whose state dies at link 3 idles until the slowest lane of its warp has walked the
+// whole chain: ncu counted 14 (states) / 19 (edges) active lanes per issued instruction.  Here the link index is
+// DATA, not control flow: every lane runs one loop whose body is "process link l of my item", and a lane whose item
+// is decided takes the next item from the cursor at the top of the same loop, while its neighbours are in the middle
+// of theirs.  All lanes stay on one instruction stream (the loop body); what still diverges is the per-link joint
+// kind, the length of a link's tree descent and the pair phase of the survivors.
+//
+//   cursor, n_items   the pool (global for the state kernel, the block's for the edge kernel)
+//   item_fn(i, qa, qb, alpha) -> false to skip item i (its edge is already known to be invalid)
+//   live_fn(i)        polled once per link: false abandons the item (another lane just invalidated its edge)
+//   done_fn(fin, i, r)  called by ALL lanes once per loop iteration: fin = this lane's item i was decided now with
+//                     result r (1 valid, 0 invalid, 2 undecided)
+template <class ItemFn, class LiveFn, class DoneFn>
+__device__ __forceinline__ void persistent_items32(const S32& S, const int* __restrict__ var_type,
+                                                   const uint16_t* __restrict__ df, const Grid32& G, float* slots,
+                                                   int* cursor, int n_items, ItemFn item_fn, LiveFn live_fn, DoneFn done_fn,
+                                                   Counters& cnt)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int nl = S.h->n_links;
+    int item = -1, l = 0;
+    bool amb = false, exhausted = false;
+    const double* qa = nullptr;
+    const double* qb = nullptr;
+    double alpha = 0.0;
+    Xf32 T;
+    for (;;) {
+        const unsigned need = __ballot_sync(FULL, item < 0 && !exhausted);
+        if (need != 0u) {
+            const int leader = __ffs(need) - 1;
+            int base = 0;
+            if (lane == leader) {
+                base = atomicAdd(cursor, __popc(need));
+            }
+            base = __shfl_sync(FULL, base, leader);
+            if (item < 0 && !exhausted) {
+                const int mine = base + __popc(need & ((1u << lane) - 1u));
+                if (mine < n_items) {
+                    if (item_fn(mine, qa, qb, alpha)) {
+                        item = mine;
+                        l = 0;
+                        amb = false;
+                        ++cnt.waypoints;
+                    }
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (__all_sync(FULL, item < 0)) {
+            if (__all_sync(FULL, exhausted)) {
+                break;
+            }
+            done_fn(false, 0, 0);
+            continue;
+        }
+        bool fin = false;
+        int res = 0;
+        const int cur = item;
+        if (item >= 0) {
+            if (!live_fn(item)) {
+                item = -1;                       // abandoned: its edge is invalid anyway, nothing to report
+            } else {
+                int r = link_step32(S, var_type, df, G, qa, qb, alpha, slots, l, T, amb, cnt);
+                if (r == 1 && ++l == nl) {
+                    r = pairs32(S, slots, amb, cnt);
+                    fin = true;
+                    res = r;
+                } else if (r != 1) {
+                    fin = true;
+                    res = r;
+                }
+                if (fin) {
+                    item = -1;
+                }
+            }
+        }
+        done_fn(fin, cur, res);
+    }
+}
+
+__global__ void __launch_bounds__(V32_THREADS)
+states_valid32p_kernel(const float* __restrict__ blob_g, int blob_words, const DevModel* __restrict__ M,
+                       const uint16_t* __restrict__ df, Grid32 G, const double* __restrict__ q, int n,
+                       uint8_t* __restrict__ verdict, int* __restrict__ unc_list, int* __restrict__ unc_count,
+                       unsigned long long* stats)
+{
+    extern __shared__ float4 smem4[];
+    float* blob = reinterpret_cast<float*>(smem4);
+    copy_blob(blob, blob_g, blob_words);
+    __syncthreads();
+    const S32 S = view32(blob);
+    float* slots = blob + blob_words;
+    Counters cnt = { 0u, 0u, 0u };
+    const int dof = S.h->dof;
+    persistent_items32(
+        S, M->var_type, df, G, slots, unc_count + 1, n,
+        [&](int i, const double*& qa, const double*& qb, double& alpha) {
+            qa = q + (size_t)i * dof;
+            qb = nullptr;
+            alpha = 0.0;
+            return true;
+        },
+        [](int) { return true; },
+        [&](bool fin, int i, int r) {
+            if (fin) {
+                verdict[i] = r == 1 ? 1 : 0;
+            }
+            append_uncertain(fin && r == 2, i, unc_list, unc_count, stats);
+        },
+        cnt);
+    flush_counters(cnt, stats);
+}
+
+// Edges, lane-persistent: a block takes EPB = V32P_EDGES_PER_THREAD * blockDim edges.  Round A checks the first
+// waypoint of every edge (the reference's first check: an edge that starts in collision costs one state check),
+// round B the remaining waypoints of the survivors; both rounds hand their items to the lanes one at a time.
+constexpr int V32P_EDGES_PER_THREAD = 4;
+
+__global__ void __launch_bounds__(V32_THREADS)
+edges_valid32p_kernel(const float* __restrict__ blob_g, int blob_words, const DevModel* __restrict__ M,
+                      const uint16_t* __restrict__ df, Grid32 G, const double* __restrict__ q0,
+                      const double* __restrict__ q1, int n, uint8_t* __restrict__ verdict, int* __restrict__ counts,
+                      int* __restrict__ unc_list, int* __restrict__ unc_count, unsigned long long* stats)
+{
+    extern __shared__ float4 smem4[];
+    __shared__ int s_cursor[2];
+    __shared__ int s_warp_tot[V32_THREADS / 32];
+    float* blob = reinterpret_cast<float*>(smem4);
+    copy_blob(blob, blob_g, blob_words);
+    const int tid = threadIdx.x;
+    const int epb = V32P_EDGES_PER_THREAD * (int)blockDim.x;
+    const int first = blockIdx.x * epb;
+    const int dof = M->dof;
+    Counters cnt = { 0u, 0u, 0u };
+    __syncthreads();   // blob copied
+    const S32 S = view32(blob);
+    float* slots = blob + blob_words;
+    // per-edge block state behind the per-thread slots: offsets (epb + 1), ok, unc, waypoint counts
+    int* s_off = reinterpret_cast<int*>(slots + ((size_t)S.h->n_slots * 12 + (size_t)S.h->n_ptrees * 3) * blockDim.x);
+    int* s_ok = s_off + epb + 1;
+    int* s_unc = s_ok + epb;
+    int* s_cnt = s_unc + epb;
+
+    // waypoint counts, in double exactly as the reference computes them
+    for (int e = tid; e < epb; e += blockDim.x) {
+        const int i = first + e;
+        int count = 0;
+        if (i < n) {
+            const double* a = q0 + (size_t)i * dof;
+            const double* b = q1 + (size_t)i * dof;
+            double motion = 0.0;
+            for (int v = 0; v < dof; ++v) {
+                const int ty = M->var_type[v];
+                double dist;
+                if (ty == 1) {
+                    dist = fabs(normalize_angle(b[v] - a[v]));
+                    motion += M->var_weight[v] * dist;
+                } else if (ty == 0) {
+                    dist = fabs(b[v] - a[v]);
+                    motion += M->var_weight[v] * dist;
+                } else {
+                    dist = fabs(b[v] - a[v]);
+                    motion += dist;
+                }
+            }
+            if (motion != 0.0) {
+                count = max(2, (int)ceil(motion / 0.05) + 1);
+            }
+            if (counts != nullptr) {
+                counts[i] = count;
+            }
+        }
+        s_cnt[e] = count;
+        s_ok[e] = 1;
+        s_unc[e] = 0;
+    }
+    if (tid == 0) {
+        s_cursor[0] = 0;
+        s_cursor[1] = 0;
+    }
+    __syncthreads();
+
+    // Round A: waypoint 0 (alpha = 0 is exactly q0) of every edge that has waypoints
+    persistent_items32(
+        S, M->var_type, df, G, slots, &s_cursor[0], epb,
+        [&](int e, const double*& qa, const double*& qb, double& alpha) {
+            if (s_cnt[e] == 0) {
+                return false;
+            }
+            qa = q0 + (size_t)(first + e) * dof;
+            qb = q1 + (size_t)(first + e) * dof;
+            alpha = 0.0;
+            return true;
+        },
+        [](int) { return true; },
+        [&](bool fin, int e, int r) {
+            if (fin) {
+                s_ok[e] = r != 0;       // one item per edge in this round: no other writer
+                s_unc[e] = r == 2;
+            }
+        },
+        cnt);
+    __syncthreads();
+
+    // Round B: the remaining waypoints of the surviving edges, flattened (exclusive scan of the per-edge rests)
+    {
+        int rest[V32P_EDGES_PER_THREAD];
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < V32P_EDGES_PER_THREAD; ++k) {
+            const int e = tid * V32P_EDGES_PER_THREAD + k;
+            rest[k] = s_ok[e] ? max(s_cnt[e] - 1, 0) : 0;
+            mine += rest[k];
+        }
+        const int lane = tid & 31, warp = tid >> 5;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) {
+            s_warp_tot[warp] = incl;
+        }
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < warp; ++w) base += s_warp_tot[w];
+        int off = base + incl - mine;
+#pragma unroll
+        for (int k = 0; k < V32P_EDGES_PER_THREAD; ++k) {
+            s_off[tid * V32P_EDGES_PER_THREAD + k] = off;
+            off += rest[k];
+        }
+        if (tid == (int)blockDim.x - 1) {
+            s_off[epb] = off;
+        }
+        __syncthreads();
+    }
+    const int total = s_off[epb];
+    auto edge_of = [&](int item) {
+        int lo = 0, hi = epb;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= item) {
+                lo = mid;
+            } else {
+                hi = mid;
+            }
+        }
+        return lo;
+    };
+    // the edge of a lane's current item (items are handed out once, so the lookup is done at pull time)
+    int my_edge = 0;
+    persistent_items32(
+        S, M->var_type, df, G, slots, &s_cursor[1], total,
+        [&](int item, const double*& qa, const double*& qb, double& alpha) {
+            const int e = edge_of(item);
+            if (*((volatile int*)&s_ok[e]) == 0) {
+                return false;             // its edge died meanwhile
+            }
+            my_edge = e;
+            const int w = item - s_off[e] + 1;                      // waypoint 0 was round A
+            const double inv = 1.0 / (double)(s_cnt[e] - 1);       // m_waypoint_count_inv
+            alpha = (double)w * inv;
+            qa = q0 + (size_t)(first + e) * dof;
+            qb = q1 + (size_t)(first + e) * dof;
+            return true;
+        },
+        [&](int) { return *((volatile int*)&s_ok[my_edge]) != 0; },
+        [&](bool fin, int, int r) {
+            if (fin) {
+                if (r == 0) {
+                    atomicAnd(&s_ok[my_edge], 0);
+                } else if (r == 2) {
+                    atomicOr(&s_unc[my_edge], 1);
+                }
+            }
+        },
+        cnt);
+    __syncthreads();
+    for (int e = tid; e < epb; e += blockDim.x) {
+        const int i = first + e;
+        bool push = false;
+        if (i < n) {
+            verdict[i] = s_ok[e] ? 1 : 0;
+            push = s_ok[e] && s_unc[e];
+        }
+        append_uncertain(push, i, unc_list, unc_count, stats);
+    }
     flush_counters(cnt, stats);
 }
 
