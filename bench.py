@@ -357,7 +357,10 @@ def plan_leg(api, scenes, sharding, dist, torch, dev, scene, starts_all, goals_a
     nq_total = len(starts_all)
     mine = sharding.round_robin_shard(nq_total, rank, world)
     cores = os.cpu_count() or 1
-    n_thr = args.plan_threads if args.plan_threads > 0 else max(1, min(12, int(0.75 * cores / max(1, world))))
+    # planner threads (= contexts) per GPU: host work per query is light since the lattices moved to the device, and
+    # more contexts mean more and smaller rounds (measured on one B200, 2048 queries: 4 threads 1810-1930 q/s, 6: 1940-2000,
+    # 8: 1610, 12: 1470); the 8-GPU box has 4 cores per GPU
+    n_thr = args.plan_threads if args.plan_threads > 0 else max(1, min(6, int(0.75 * cores / max(1, world))))
     n_thr = max(n_thr, (args.plan_concurrent + 511) // 512)
     pctxs = [pctx] + [api.clone_context(pctx, scene, ptables, device=local_rank) for _ in range(n_thr - 1)]
     per_ctx = max(1, (min(args.plan_concurrent, max(1, len(mine))) + n_thr - 1) // n_thr)
@@ -555,7 +558,7 @@ def main():
     ap.add_argument("--post-paths", type=int, default=1024, help="joint-space paths shortcut in one call (0 = skip)")
     ap.add_argument("--post-cpu-paths", type=int, default=48)
     ap.add_argument("--no-ingest", dest="ingest", action="store_false", help="skip the scene-ingest leg")
-    ap.add_argument("--plan-threads", type=int, default=0, help="planner threads (= contexts) per GPU; 0 = 75 %% of the rank's cores, at most 12")
+    ap.add_argument("--plan-threads", type=int, default=0, help="planner threads (= contexts) per GPU; 0 = 75 %% of the rank's cores, at most 6")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "smpl_b200" else args.warmup
 

@@ -20,6 +20,7 @@
 #include "heuristic.cuh"
 #include "model.cuh"
 #include "validity.cuh"
+#include "validity32.cuh"
 
 namespace smplgpu {
 
@@ -155,33 +156,21 @@ __global__ void lattice_gen_kernel(const DevModel* __restrict__ M, LatticeBank B
     active[t] = on ? 1 : 0;
 }
 
-// Round, step 3 (after the edge kernels): one warp per expansion, lane j = successor j.  Valid successors get their
-// planning-frame pose (goal test, heuristic, metric goal distance), their coordinates and hash in parallel; then
-// they are looked up / entered ONE AFTER THE OTHER in primitive order, so ids come out in the reference's
-// creation order.  out_succ[i][j] = id | LATTICE_GOAL_FLAG, or -1; out_h[i][j] = GetGoalHeuristic(successor);
-// out_count[i] = lattice size of the query afterwards.
-__global__ void __launch_bounds__(128)
-lattice_commit_kernel(const DevModel* __restrict__ M, GridParams G, LatticeBank B, LatticeParams L, LatticeVals V,
-                      const int* __restrict__ bfs, int dimx, int dimy, int slot_dimz,
-                      const int* __restrict__ slot, int n, const double* __restrict__ q1,
-                      const uint8_t* __restrict__ active, const uint8_t* __restrict__ verdict,
-                      int* __restrict__ out_succ, int* __restrict__ out_h, int* __restrict__ out_count,
-                      const unsigned long long* __restrict__ stats)
+// The commit step of one expansion, by ONE warp, lane j = successor j.  Valid successors get their planning-frame pose
+// (goal test, heuristic, metric goal distance), their coordinates and hash in parallel; then they are looked up /
+// entered ONE AFTER THE OTHER in primitive order, so ids come out in the reference's creation order.
+// succ_out[j] = id | LATTICE_GOAL_FLAG, or -1; h_out[j] = GetGoalHeuristic(successor); *count_out = lattice size of the
+// query afterwards (-1: out of room).
+__device__ __forceinline__ void lattice_commit_warp(const DevModel* __restrict__ M, const GridParams& G, const LatticeBank& B,
+                                                    const LatticeParams& L, const LatticeVals& V, const int* __restrict__ bfs,
+                                                    int dimx, int dimy, int slot_dimz, int s, int lane, bool valid,
+                                                    const double* q, int* succ_out, int* h_out, int* count_out)
 {
-    const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (i >= n) {
-        return;
-    }
-    const int s = slot[i];
     const int dof = M->dof;
-    const int t = i * B.stride + lane;
-    const bool valid = lane < B.stride && active[t] != 0 && verdict[t] != 0;
     int c[MAX_DOF];
     unsigned int hv = 0;
     int h = 0, gd = 0;
     bool is_goal = false;
-    const double* q = q1 + (size_t)t * dof;
     if (valid) {
         double pose[6], link[3];
         planning_frame_fk(M, q, pose, link);
@@ -243,17 +232,183 @@ lattice_commit_kernel(const DevModel* __restrict__ M, GridParams G, LatticeBank 
         __syncwarp();
     }
     if (lane < B.stride) {
-        out_succ[t] = id < 0 ? -1 : (id | (is_goal ? LATTICE_GOAL_FLAG : 0));
-        out_h[t] = h;
+        succ_out[lane] = id < 0 ? -1 : (id | (is_goal ? LATTICE_GOAL_FLAG : 0));
+        h_out[lane] = h;
     }
     full = __any_sync(0xffffffffu, full);
     if (lane == 0) {
-        out_count[i] = full ? -1 : B.count[s];   // -1: the query ran out of room (the caller sized it too small)
+        *count_out = full ? -1 : B.count[s];
     }
-    if (i == 0 && lane == 0) {
-        // edges of this round that the double-precision pass resolved, behind the counts (8-byte slot)
-        unsigned long long* tail = reinterpret_cast<unsigned long long*>(out_count + ((n + 1) & ~1));
-        *tail = stats[3];
+}
+
+// Round, step 3 of the three-kernel form (after the edge kernels): one warp per expansion.
+__global__ void __launch_bounds__(128)
+lattice_commit_kernel(const DevModel* __restrict__ M, GridParams G, LatticeBank B, LatticeParams L, LatticeVals V,
+                      const int* __restrict__ bfs, int dimx, int dimy, int slot_dimz,
+                      const int* __restrict__ slot, int n, const double* __restrict__ q1,
+                      const uint8_t* __restrict__ active, const uint8_t* __restrict__ verdict,
+                      int* __restrict__ out_succ, int* __restrict__ out_h, int* __restrict__ out_count,
+                      const unsigned long long* __restrict__ stats, unsigned long long* resolved_total)
+{
+    const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) {
+        return;
+    }
+    const int t = i * B.stride + lane;
+    const bool valid = lane < B.stride && active[t] != 0 && verdict[t] != 0;
+    lattice_commit_warp(M, G, B, L, V, bfs, dimx, dimy, slot_dimz, slot[i], lane, valid, q1 + (size_t)t * M->dof,
+                        out_succ + (size_t)i * B.stride, out_h + (size_t)i * B.stride, out_count + i);
+    if (i == 0 && lane == 0 && stats[3] != 0) {
+        atomicAdd(resolved_total, stats[3]);   // edges of this round that the double-precision pass resolved
+    }
+}
+
+// ONE KERNEL PER ROUND (SMPLGPU_LATTICE_FUSED=1; off by default): a block per expansion does everything the
+// three-kernel form does -- successor generation and joint limits (threads 0 .. stride-1), the edges' waypoints in
+// certified single precision spread over the block, the undecided edges again in double by warp 0 (rare: ~0.4 % of
+// edges), then the commit step by warp 0 -- so a round is one launch, not a chain of five.
+// Measured on one B200 (2048 PR2 tabletop queries): it wins only when many contexts share the GPU and the
+// chain is launch bound (12 planner threads: 2240 vs 1470 queries/s); with the 4-6 contexts that are the optimum of the
+// three-kernel form it LOSES (1540-1600 vs 1810-2000 queries/s, UBR1 3050 vs 4540): a block per expansion keeps
+// ~56 of its 128 threads busy for one waypoint each and then waits for one warp's commit, where the chain packs all
+// rounds' waypoints densely; and its longer-lived blocks delay the cooperative BFS launches of newly admitted queries.
+// dynamic shared memory: blob | per-thread f32 slots + root centres | f64 slots of ONE warp (32 columns)
+constexpr int LROUND_THREADS = 128;
+
+__global__ void __launch_bounds__(LROUND_THREADS)
+lattice_round_kernel(const float* __restrict__ blob_g, int blob_words, const DevModel* __restrict__ M,
+                     const uint16_t* __restrict__ df, Grid32 G32, GridParams G, LatticeBank B, LatticeParams L, LatticeVals V,
+                     const int* __restrict__ bfs, int dimx, int dimy, int slot_dimz,
+                     const int* __restrict__ slot, const int* __restrict__ parent, int n,
+                     int* __restrict__ out_succ, int* __restrict__ out_h, int* __restrict__ out_count,
+                     unsigned long long* resolved_total)
+{
+    extern __shared__ float4 smem4[];
+    __shared__ double s_q0[MAX_DOF];
+    __shared__ double s_q1[LATTICE_MAX_STRIDE][MAX_DOF];
+    __shared__ int s_cnt[LATTICE_MAX_STRIDE], s_off[LATTICE_MAX_STRIDE + 1], s_ok[LATTICE_MAX_STRIDE], s_unc[LATTICE_MAX_STRIDE];
+    __shared__ int s_active[LATTICE_MAX_STRIDE];
+    const int i = blockIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = slot[i], p = parent[i];
+    const int dof = M->dof;
+    float* blob = reinterpret_cast<float*>(smem4);
+    copy_blob(blob, blob_g, blob_words);
+    if (tid < dof) {
+        s_q0[tid] = B.q[((size_t)s * B.cap + p) * dof + tid];
+    }
+    __syncthreads();
+    const S32 S = view32(blob);
+    float* slots32 = blob + blob_words;
+    double* slots64 = reinterpret_cast<double*>(slots32 + ((size_t)S.h->n_slots * 12 + (size_t)S.h->n_ptrees * 3) * blockDim.x);
+
+    // ---- successors (ManipLatticeActionSpace::apply + the joint-limit half of checkAction) and waypoint counts ----
+    if (tid < B.stride) {
+        const int j = tid;
+        const double goal_dist = (double)B.gdist[(size_t)s * B.cap + p] * B.res;
+        const bool near_goal = B.use_short_dist && goal_dist <= B.short_dist_thresh;
+        const int cnt = near_goal ? B.n_short : B.n_long;
+        bool on = j < cnt;
+        if (on) {
+            const int prim = near_goal ? B.short_list[j] : B.long_list[j];
+            for (int v = 0; v < dof; ++v) {
+                s_q1[j][v] = B.deltas[(size_t)prim * dof + v] + s_q0[v];
+            }
+            on = joint_limits_ok(M, s_q1[j]);
+        }
+        int count = 0;
+        if (on) {
+            double motion = 0.0;
+            for (int v = 0; v < dof; ++v) {
+                const int ty = M->var_type[v];
+                if (ty == 1) {
+                    motion += M->var_weight[v] * fabs(normalize_angle(s_q1[j][v] - s_q0[v]));
+                } else if (ty == 0) {
+                    motion += M->var_weight[v] * fabs(s_q1[j][v] - s_q0[v]);
+                } else {
+                    motion += fabs(s_q1[j][v] - s_q0[v]);
+                }
+            }
+            if (motion != 0.0) {
+                count = max(2, (int)ceil(motion / 0.05) + 1);
+            }
+        }
+        s_active[j] = on ? 1 : 0;
+        s_cnt[j] = count;
+        s_ok[j] = on ? 1 : 0;     // an edge without waypoints is valid without a check
+        s_unc[j] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int j = 0; j < B.stride; ++j) {
+            s_off[j] = acc;
+            acc += s_cnt[j];
+        }
+        s_off[B.stride] = acc;
+    }
+    __syncthreads();
+    const int total = s_off[B.stride];
+    auto edge_of = [&](int item) {
+        int e = 0;
+        while (e + 1 < B.stride && s_off[e + 1] <= item) {
+            ++e;
+        }
+        return e;
+    };
+
+    // ---- CollisionSpace::isStateToStateValid of every successor: waypoints over the block, certified f32 ----
+    Counters cnt = { 0u, 0u, 0u };
+    for (int item = tid; item < total; item += blockDim.x) {
+        const int e = edge_of(item);
+        if (*((volatile int*)&s_ok[e]) == 0) {
+            continue;
+        }
+        const int w = item - s_off[e];
+        const double alpha = (double)w * (1.0 / (double)(s_cnt[e] - 1));
+        const int r = check_state32(S, M->var_type, df, G32, s_q0, s_q1[e], alpha, slots32, cnt);
+        if (r == 0) {
+            atomicAnd(&s_ok[e], 0);
+        } else if (r == 2) {
+            atomicOr(&s_unc[e], 1);
+        }
+    }
+    __syncthreads();
+
+    // ---- the undecided edges, exactly, by warp 0 (every waypoint, as the double-precision kernel does) ----
+    if (warp == 0) {
+        int n_res = 0;
+        for (int e = 0; e < B.stride; ++e) {
+            if (!(s_ok[e] != 0 && s_unc[e] != 0)) {   // warp-uniform
+                continue;
+            }
+            ++n_res;
+            bool ok = true;
+            const double inv = 1.0 / (double)(s_cnt[e] - 1);
+            for (int w0 = 0; w0 < s_cnt[e] && ok; w0 += 32) {
+                const int w = w0 + lane;
+                bool mine = true;
+                if (w < s_cnt[e]) {
+                    mine = check_state(M, df, G, s_q0, s_q1[e], (double)w * inv, slots64, cnt, 32, lane);
+                }
+                ok = __all_sync(0xffffffffu, mine);
+            }
+            if (lane == 0 && !ok) {
+                s_ok[e] = 0;
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && n_res > 0) {
+            atomicAdd(resolved_total, (unsigned long long)n_res);
+        }
+        // ---- commit ----
+        const bool valid = lane < B.stride && s_active[lane] != 0 && s_ok[lane] != 0;
+        lattice_commit_warp(M, G, B, L, V, bfs, dimx, dimy, slot_dimz, s, lane, valid, s_q1[lane < B.stride ? lane : 0],
+                            out_succ + (size_t)i * B.stride, out_h + (size_t)i * B.stride, out_count + i);
     }
 }
 

@@ -134,6 +134,9 @@ struct smplgpu_ctx
     void* d_lat[SMPLGPU_EXPAND_BUFFERS] = { };   size_t d_lat_cap[SMPLGPU_EXPAND_BUFFERS] = { };    // q0 | q1 | active | verdict
     int lat_n[SMPLGPU_EXPAND_BUFFERS] = { -1, -1, -1, -1 };
     int lat_max_n = 0;
+    unsigned long long* lat_resolved = nullptr;   // pinned, mapped: edges the rounds resolved in double (running total)
+    bool lat_fused = false;                        // one kernel per round (lattice_round_kernel)
+    size_t lat_round_smem = 0;
     // smplgpu_expand_state: primitive table, page-locked record array + completion flag, arrival counter
     double* d_x1_deltas = nullptr; int x1_prims = -1;
     smplgpu_succ_info* x1_out = nullptr; size_t x1_out_cap = 0;   // records; the flag word follows them
@@ -325,6 +328,8 @@ static void free_lattice(smplgpu_ctx* ctx)
 {
     cudaFree(ctx->lat.q); cudaFree(ctx->lat.coord); cudaFree(ctx->lat.gdist); cudaFree(ctx->lat.table);
     cudaFree(ctx->lat.count); cudaFree(ctx->lat.goal); cudaFree(ctx->d_lat_aux);
+    if (ctx->lat_resolved) cudaFreeHost(ctx->lat_resolved);
+    ctx->lat_resolved = nullptr;
     memset(&ctx->lat, 0, sizeof(ctx->lat));
     ctx->d_lat_aux = nullptr;
     for (int b = 0; b < SMPLGPU_EXPAND_BUFFERS; ++b) {
@@ -2604,7 +2609,13 @@ int smplgpu_expand_batch_reserve(smplgpu_ctx* ctx, int max_n)
     return ensure_unc(ctx, (size_t)std::max(max_n, 1));
 }
 
-int64_t smplgpu_expand_batch_resolved(const smplgpu_ctx* ctx) { return ctx ? ctx->exp_resolved_total : 0; }
+int64_t smplgpu_expand_batch_resolved(const smplgpu_ctx* ctx)
+{
+    if (!ctx) return 0;
+    // + the lattice rounds' running total (written by the device into page-locked memory; exact once the rounds
+    // in flight have been waited for)
+    return ctx->exp_resolved_total + (ctx->lat_resolved ? (int64_t)*((volatile unsigned long long*)ctx->lat_resolved) : 0);
+}
 
 int smplgpu_expand_batch_submit(smplgpu_ctx* ctx, const double* q0, const double* q1, const int32_t* slot, int n,
                                 int cost_per_cell, int buffer)
@@ -2805,6 +2816,27 @@ int smplgpu_lattice_create(smplgpu_ctx* ctx, const smplgpu_lattice_params* p, in
         if ((r = grow(ctx, &ctx->d_lat[b], &ctx->d_lat_cap[b], dev_bytes))) return r;
     }
     if ((r = ensure_unc(ctx, ne))) return r;
+    if (!ctx->lat_resolved) {
+        CU(cudaHostAlloc((void**)&ctx->lat_resolved, 64, cudaHostAllocMapped));
+        *ctx->lat_resolved = 0;
+    }
+    // SMPLGPU_LATTICE_FUSED=1: one kernel per round (lattice_round_kernel; measured slower at the default number of
+    // planner contexts, see lattice.cuh) when the single-precision model is in use and a block's shared memory holds
+    // the blob, the per-thread f32 state and one warp's double-precision slots
+    {
+        static const bool want = [] {
+            const char* e = getenv("SMPLGPU_LATTICE_FUSED");
+            return e != nullptr && atoi(e) != 0;
+        }();
+        const size_t smem = (size_t)ctx->blob_words * 4
+                            + ((size_t)ctx->v32_slots * 12 + (size_t)ctx->v32_ptrees * 3) * sizeof(float) * LROUND_THREADS
+                            + (size_t)ctx->h_model->n_slots * 12 * sizeof(double) * 32 + 64;
+        ctx->lat_fused = want && use_f32(ctx) && smem <= (size_t)200 * 1024;
+        ctx->lat_round_smem = smem;
+        if (ctx->lat_fused) {
+            CU(cudaFuncSetAttribute(lattice_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
+        }
+    }
     ctx->lat_max_n = max_n;
     ctx->has_lat = true;
     return stride;
@@ -2878,6 +2910,17 @@ int smplgpu_lattice_expand_submit(smplgpu_ctx* ctx, const int32_t* slot, const i
     int* out_h = out_succ + ne;
     int* out_count = out_h + ne;
     // the kernels read the (slot, state id) pairs from, and write the results to, page-locked host memory directly
+    if (ctx->lat_fused) {
+        lattice_round_kernel<<<n, LROUND_THREADS, ctx->lat_round_smem, ctx->stream>>>(
+            ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, ctx->grid, B, ctx->lat_params, ctx->lat_vals,
+            ctx->bank.dist, ctx->bank.DX, ctx->bank.DY, ctx->bank_slot_dz, in_slot, in_parent, n, out_succ, out_h, out_count,
+            ctx->lat_resolved);
+        ++ctx->launches;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev_exp[b], ctx->stream));
+        ctx->lat_n[buffer] = n;
+        return 0;
+    }
     lattice_gen_kernel<<<(unsigned)((ne + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_model, B, in_slot, in_parent, n, dq0, dq1, dactive,
                                                                               ctx->d_stats);
     ++ctx->launches;
@@ -2885,7 +2928,7 @@ int smplgpu_lattice_expand_submit(smplgpu_ctx* ctx, const int32_t* slot, const i
     if (r) return r;
     lattice_commit_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(
         ctx->d_model, ctx->grid, B, ctx->lat_params, ctx->lat_vals, ctx->bank.dist, ctx->bank.DX, ctx->bank.DY, ctx->bank_slot_dz,
-        in_slot, n, dq1, dactive, dverdict, out_succ, out_h, out_count, ctx->d_stats);
+        in_slot, n, dq1, dactive, dverdict, out_succ, out_h, out_count, ctx->d_stats, ctx->lat_resolved);
     ++ctx->launches;
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev_exp[b], ctx->stream));
@@ -2907,9 +2950,6 @@ int smplgpu_lattice_expand_wait(smplgpu_ctx* ctx, int buffer, const int32_t** su
     *succ = out;
     *h = out + ne;
     *count = out + 2 * ne;
-    unsigned long long resolved = 0;
-    memcpy(&resolved, out + 2 * ne + ((n + 1) & ~1), sizeof(resolved));
-    ctx->exp_resolved_total += (int64_t)resolved;
     for (int i = 0; i < n; ++i) {
         if ((*count)[i] < 0) return fail(ctx, SMPLGPU_ERR_LIMIT, "a lattice ran out of room (%d states per query)", ctx->lat.cap);
     }

@@ -154,25 +154,28 @@ struct Counters { unsigned int lookups, pairs, waypoints; };
 
 // per-thread slot storage in shared memory: element e of slot s of thread t
 // lives at smem[(s * 12 + e) * blockDim + t]  (conflict-free for a warp)
-__device__ __forceinline__ void slot_store(double* smem, int slot, const Xf& t)
+// (stride, idx) = (threads sharing the slot storage, this thread's column); 0 = the whole block, threadIdx.x
+__device__ __forceinline__ void slot_store(double* smem, int slot, const Xf& t, int stride = 0, int idx = 0)
 {
-    double* p = smem + (size_t)slot * 12 * blockDim.x + threadIdx.x;
+    const int st = stride > 0 ? stride : (int)blockDim.x;
+    double* p = smem + (size_t)slot * 12 * st + (stride > 0 ? idx : (int)threadIdx.x);
 #pragma unroll
-    for (int e = 0; e < 12; ++e) p[e * blockDim.x] = t.m[e];
+    for (int e = 0; e < 12; ++e) p[e * st] = t.m[e];
 }
 
-__device__ __forceinline__ void slot_load(const double* smem, int slot, Xf& t)
+__device__ __forceinline__ void slot_load(const double* smem, int slot, Xf& t, int stride = 0, int idx = 0)
 {
-    const double* p = smem + (size_t)slot * 12 * blockDim.x + threadIdx.x;
+    const int st = stride > 0 ? stride : (int)blockDim.x;
+    const double* p = smem + (size_t)slot * 12 * st + (stride > 0 ? idx : (int)threadIdx.x);
 #pragma unroll
-    for (int e = 0; e < 12; ++e) t.m[e] = p[e * blockDim.x];
+    for (int e = 0; e < 12; ++e) t.m[e] = p[e * st];
 }
 
 __device__ __forceinline__ void node_pos(const DevModel* __restrict__ M, const double* smem, int node,
-                                         double& x, double& y, double& z)
+                                         double& x, double& y, double& z, int stride = 0, int idx = 0)
 {
     Xf t;
-    slot_load(smem, M->link_slot[M->node_link[node]], t);
+    slot_load(smem, M->link_slot[M->node_link[node]], t, stride, idx);
     xf_point(t, M->node_center[node][0], M->node_center[node][1], M->node_center[node][2], x, y, z);
 }
 
@@ -182,7 +185,7 @@ __device__ __forceinline__ void node_pos(const DevModel* __restrict__ M, const d
 //       qb == nullptr ? qa[v] : qa[v] + alpha * diff(v)     (MotionInterpolation::interpolate)
 __device__ bool check_state(const DevModel* __restrict__ M, const uint16_t* __restrict__ df, const GridParams& G,
                             const double* __restrict__ qa, const double* __restrict__ qb, double alpha,
-                            double* smem, Counters& cnt)
+                            double* smem, Counters& cnt, int sstride = 0, int sidx = 0)
 {
     Xf T;  // transform of the previously processed link
     int stack[MAX_TREE_DEPTH];
@@ -214,12 +217,12 @@ __device__ bool check_state(const DevModel* __restrict__ M, const uint16_t* __re
         } else if (p == l - 1) {
             P = T;
         } else {
-            slot_load(smem, M->link_slot[p], P);
+            slot_load(smem, M->link_slot[p], P, sstride, sidx);
         }
         xf_mul(P, J, T);
         const int slot = M->link_slot[l];
         if (slot >= 0) {
-            slot_store(smem, slot, T);
+            slot_store(smem, slot, T, sstride, sidx);
         }
 
         // sphere trees rooted on this link vs the distance field
@@ -254,8 +257,8 @@ __device__ bool check_state(const DevModel* __restrict__ M, const uint16_t* __re
             const int packed = stack[--sp];
             const int n1 = packed >> 16, n2 = packed & 0xFFFF;
             double x1, y1, z1, x2, y2, z2;
-            node_pos(M, smem, n1, x1, y1, z1);
-            node_pos(M, smem, n2, x2, y2, z2);
+            node_pos(M, smem, n1, x1, y1, z1, sstride, sidx);
+            node_pos(M, smem, n2, x2, y2, z2, sstride, sidx);
             ++cnt.pairs;
             const double dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
             const double cd2 = (dx * dx + dy * dy) + dz * dz;
