@@ -792,7 +792,8 @@ static int build_model32(smplgpu_ctx* ctx)
     }
 
     // ---- launch geometry + upload ----
-    const size_t per_thread = ((size_t)n_slots32 * 12 + (size_t)n_ptrees * 3) * sizeof(float) + 4 * V32P_EDGES_PER_THREAD * sizeof(int);
+    const size_t per_thread = ((size_t)n_slots32 * 12 + (size_t)n_ptrees * 3) * sizeof(float) +
+                              4 * (v32_persistent() ? V32P_EDGES_PER_THREAD : 1) * sizeof(int);
     const size_t fixed = (size_t)w * 4 + 64;
     ctx->v32_slots = n_slots32;
     ctx->v32_ptrees = n_ptrees;
@@ -834,7 +835,7 @@ static size_t v32_smem(const smplgpu_ctx* ctx)
     // keeps V32P_EDGES_PER_THREAD edges per thread: offsets, ok, unc, counts)
     return (size_t)ctx->blob_words * 4
            + ((size_t)ctx->v32_slots * 12 + (size_t)ctx->v32_ptrees * 3) * sizeof(float) * ctx->v32_threads
-           + (4 * (size_t)V32P_EDGES_PER_THREAD * ctx->v32_threads + 4) * sizeof(int);
+           + (4 * (size_t)(v32_persistent() ? V32P_EDGES_PER_THREAD : 1) * ctx->v32_threads + 4) * sizeof(int);
 }
 
 

@@ -37,6 +37,12 @@
 namespace smplgpu {
 
 constexpr int V32_THREADS = 128;
+// -DV32_MIN_BLOCKS=n asks ptxas for n resident blocks per SM (tuning experiments; the default lets it choose)
+#ifdef V32_MIN_BLOCKS
+#define V32_BOUNDS __launch_bounds__(V32_THREADS, V32_MIN_BLOCKS)
+#else
+#define V32_BOUNDS __launch_bounds__(V32_THREADS)
+#endif
 constexpr float V32_MAX_ANGLE = 64.0f;   // beyond this the hi/lo split no longer keeps the sin/cos argument exact enough
 
 // Compact single-precision model: a blob of 4-byte words copied into shared memory by every block.
@@ -472,7 +478,7 @@ __device__ __forceinline__ void append_uncertain(bool push, int item, int* __res
 
 // dynamic shared memory: blob | slots (n_slots * 12 * blockDim floats) | root centres (n_ptrees * 3 * blockDim floats)
 //                        | edges: (blockDim + 1) offsets, blockDim ok, blockDim unc, blockDim counts
-__global__ void __launch_bounds__(V32_THREADS)
+__global__ void V32_BOUNDS
 states_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const DevModel* __restrict__ M,
                       const uint16_t* __restrict__ df, Grid32 G, const double* __restrict__ q, int n,
                       uint8_t* __restrict__ verdict, int* __restrict__ unc_list, int* __restrict__ unc_count,
@@ -511,7 +517,7 @@ states_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const De
     flush_counters(cnt, stats);
 }
 
-__global__ void __launch_bounds__(V32_THREADS)
+__global__ void V32_BOUNDS
 edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const DevModel* __restrict__ M,
                      const uint16_t* __restrict__ df, Grid32 G, const double* __restrict__ q0,
                      const double* __restrict__ q1, int n, uint8_t* __restrict__ verdict, int* __restrict__ counts,
