@@ -13,16 +13,18 @@
 // instead call smplgpu_expand_state on the first question about a state they have no answers for, and serve the
 // following calls from the record this kernel leaves behind.  Same answers, callers untouched.
 //
-// Latency, not throughput, is what matters for one expansion (~25 edges of 2-6 waypoints): the kernel runs the
-// exact double-precision path directly (no single-precision pass + resolve chain), one block per successor --
+// Latency, not throughput, is what matters for one expansion (~25 edges of 2-6 waypoints): one block per successor --
 // warp 0 checks the edge parent -> successor, one waypoint per lane, ANDed with a warp vote; lane 0 of warp 1
 // does the successor's joint limits, planning-frame FK and BFS lookups meanwhile -- plus one block for the
-// parent itself.  The last block to finish publishes a sequence number the host spins on.
+// parent itself.  A waypoint is checked in certified single precision (validity32.cuh: 7 folded links in float
+// instead of 14 in double) and, in the same lane and right away, in double when that cannot decide it: no resolve
+// pass, no second launch.  The last block to finish publishes a sequence number the host spins on.
 #pragma once
 
 #include "heuristic.cuh"
 #include "model.cuh"
 #include "validity.cuh"
+#include "validity32.cuh"
 
 namespace smplgpu {
 
@@ -32,8 +34,11 @@ struct Expand1Parent { double q[MAX_DOF]; };
 
 static_assert(SMPLGPU_MAX_DOF == MAX_DOF, "smplgpu_succ_info::state and the device tables disagree on the dof bound");
 
+// dynamic shared memory: double-precision slots (n_slots * 12 * blockDim doubles) | with a single-precision model:
+// its blob | per-thread f32 slots and root centres
 __global__ void __launch_bounds__(EXPAND1_THREADS)
 expand_state_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ df, GridParams G,
+                    const float* __restrict__ blob_g, int blob_words, Grid32 G32,
                     const int* __restrict__ bfs, int dimx, int dimy, int dimz,
                     Expand1Parent parent, const double* __restrict__ deltas, int cost_per_cell,
                     smplgpu_succ_info* out, unsigned int* done, unsigned long long* flag, unsigned long long seq)
@@ -41,6 +46,10 @@ expand_state_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__
     extern __shared__ double smem[];
     __shared__ double s_q0[MAX_DOF], s_q1[MAX_DOF];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* blob = reinterpret_cast<float*>(smem + (size_t)M->n_slots * 12 * blockDim.x);
+    if (blob_g != nullptr) {
+        copy_blob(blob, blob_g, blob_words);
+    }
     const int b = blockIdx.x;            // 0 = the parent itself, b >= 1 = motion primitive b - 1
     const int dof = M->dof;
     if (tid < dof) {
@@ -79,11 +88,26 @@ expand_state_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__
         }
     } else {
         Counters cnt = { 0u, 0u, 0u };
+        S32 S;
+        float* slots32 = blob + blob_words;
+        if (blob_g != nullptr) {
+            S = view32(blob);
+        }
+        // one state: certified single precision first, double in the same lane when that cannot decide
+        auto state_ok = [&](const double* qa, const double* qb, double alpha) {
+            if (blob_g != nullptr) {
+                const int r = check_state32(S, M->var_type, df, G32, qa, qb, alpha, slots32, cnt);
+                if (r != 2) {
+                    return r == 1;
+                }
+            }
+            return check_state(M, df, G, qa, qb, alpha, smem, cnt);
+        };
         if (b == 0) {
             // CollisionSpace::isStateValid(parent)
             bool ok = true;
             if (lane == 0) {
-                ok = check_state(M, df, G, s_q1, nullptr, 0.0, smem, cnt);
+                ok = state_ok(s_q1, nullptr, 0.0);
             }
             ok = __all_sync(0xffffffffu, ok);
             if (lane == 0) {
@@ -115,7 +139,7 @@ expand_state_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__
                     const int w = w0 + lane;
                     bool mine = true;
                     if (w < count) {
-                        mine = check_state(M, df, G, s_q0, s_q1, (double)w * inv, smem, cnt);
+                        mine = state_ok(s_q0, s_q1, (double)w * inv);
                     }
                     ok = __all_sync(0xffffffffu, mine);
                 }

@@ -142,6 +142,7 @@ struct smplgpu_ctx
     smplgpu_succ_info* x1_out = nullptr; size_t x1_out_cap = 0;   // records; the flag word follows them
     unsigned int* d_x1_done = nullptr;
     unsigned long long x1_seq = 0;
+    size_t x1_smem_set = 0;
 };
 
 static int fail(smplgpu_ctx* ctx, int code, const char* fmt, ...)
@@ -3096,10 +3097,19 @@ int smplgpu_expand_state(smplgpu_ctx* ctx, const double* parent, int cost_per_ce
     unsigned long long* flag = reinterpret_cast<unsigned long long*>(ctx->x1_out + ctx->x1_out_cap);
     volatile unsigned long long* vflag = flag;
     const unsigned long long seq = ++ctx->x1_seq;
-    const size_t smem = (size_t)ctx->h_model->n_slots * 12 * sizeof(double) * EXPAND1_THREADS;
+    size_t smem = (size_t)ctx->h_model->n_slots * 12 * sizeof(double) * EXPAND1_THREADS;
+    const bool f32 = use_f32(ctx);
+    if (f32) {
+        smem += (size_t)ctx->blob_words * 4 + ((size_t)ctx->v32_slots * 12 + (size_t)ctx->v32_ptrees * 3) * sizeof(float) * EXPAND1_THREADS + 16;
+    }
     if (smem > (size_t)226 * 1024) return fail(ctx, SMPLGPU_ERR_LIMIT, "%d link slots do not fit the expansion kernel", ctx->h_model->n_slots);
+    if (smem > ctx->x1_smem_set) {
+        CU(cudaFuncSetAttribute(expand_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
+        ctx->x1_smem_set = smem;
+    }
     expand_state_kernel<<<ctx->x1_prims + 1, EXPAND1_THREADS, smem, ctx->stream>>>(
-        ctx->d_model, ctx->d_df, ctx->grid, bfs_ok ? ctx->bfs.dist : nullptr, ctx->bfs.DX, ctx->bfs.DY, ctx->bfs.DZ, p,
+        ctx->d_model, ctx->d_df, ctx->grid, f32 ? ctx->d_blob : nullptr, f32 ? ctx->blob_words : 0, ctx->grid32,
+        bfs_ok ? ctx->bfs.dist : nullptr, ctx->bfs.DX, ctx->bfs.DY, ctx->bfs.DZ, p,
         ctx->d_x1_deltas, cost_per_cell, ctx->x1_out, ctx->d_x1_done, flag, seq);
     ++ctx->launches;
     CU(cudaGetLastError());
