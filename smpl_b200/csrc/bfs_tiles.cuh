@@ -108,33 +108,66 @@ __global__ void bfs_tiles_reset_kernel(BfsGrid g, BfsTiles t, const uint8_t* __r
     }
 }
 
-#ifndef TILE_BLOCKS_PER_SM
-#define TILE_BLOCKS_PER_SM 1
-#endif
-__global__ void __launch_bounds__(TILE_THREADS, TILE_BLOCKS_PER_SM)
+// A row of the extended tile as ONE 48-bit word: 8 halo cells | the 32 interior cells | 8 halo cells (bit p <-> cell
+// x0 - 8 + p).  TILE_K levels can only carry information TILE_K cells far, so 8 cells of the neighbouring bitmap words
+// are all a row needs in x -- the first version kept the whole neighbouring words (3 x 32 bits per row, three of
+// everything per level).  ncu (profiles/r02b_bfs_metrics.csv) showed that kernel waiting at barriers 54 % of the time:
+// per level the whole block waits for the few z-rows that hold the wavefront, each ONE warp walking ~500 dependent
+// instructions (27 shared loads, three words of logic); with packed rows a level is 9 shared 64-bit loads and a dozen
+// logic operations per active lane.
+__device__ __forceinline__ unsigned long long pack_row(uint32_t left, uint32_t mid, uint32_t right)
+{
+    return (unsigned long long)(left >> 24) | ((unsigned long long)mid << 8) | ((unsigned long long)(right & 0xFFu) << 40);
+}
+
+constexpr unsigned long long ROW_MASK = 0xFFFFFFFFFFFFull;   // 48 cells
+constexpr int TILE_RPT_LARGE = 4;                             // extended z-rows per warp on large grids
+
+// One block = one tile at a time; a warp owns TILE_RPT z-rows of the extended tile (interleaved, so that the few
+// adjacent z-rows a wavefront occupies fall to different warps), lane = y-row.
+//   TILE_RPT = 1: 1024 threads, one block per SM.  A tile is finished soonest (every z-row has its own warp): the
+//     choice for grids with few tiles per super-step, where the chain of dependent tile steps bounds the run
+//     (150^3: 0.43 ms against 0.55-0.61 ms with TILE_RPT = 4).
+//   TILE_RPT = 4: 256 threads, four blocks per SM.  With one thread per row a level costs ~1600 cycles however
+//     little there is to do -- 32 warps each walk the "nothing here" path and meet at a barrier; here an idle z-row
+//     is one flag test, the barrier has 8 participants, one tile's loads, barriers and write-back hide behind the
+//     levels of the other three, and the super-step's tiles are dealt in units a quarter as coarse (the grid barrier
+//     waits for the slowest block).  The choice for large grids (400^3: 2.74 ms against 3.17 ms).
+template <int TILE_RPT>
+__global__ void __launch_bounds__(TILE_THREADS / TILE_RPT, TILE_RPT)
 bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsTiles t, int max_supersteps)
 {
-    __shared__ uint32_t sF[2][TILE_THREADS * 3];
-    __shared__ uint8_t sAny[2][TILE_THREADS];        // which words of the row have frontier bits (per buffer)
-    __shared__ uint8_t sZ[2][TILE_E];                // z-row (= warp) has frontier bits (per buffer)
-    __shared__ unsigned int s_act;                   // which of the 27 neighbour directions get activated
-    __shared__ int s_next[2];                        // next queue position of this block, double-buffered by tile
-                                                     // count: thread 0 writes slot k & 1 for tile k before that tile's
-                                                     // first barrier, everyone reads it after one; slot k & 1 is written
-                                                     // again for tile k + 2, i.e. after tile k + 1's barriers
+    __shared__ unsigned long long sF[2][TILE_THREADS];   // frontier rows, double-buffered by level
+    __shared__ uint8_t sZ[2][TILE_E + 2];                // z-row has frontier cells (per buffer); [0] and [33] stay 0
+    __shared__ unsigned int s_act;                       // which of the 27 neighbour directions get activated
+    __shared__ int s_next[2];                            // next queue position of this block, double-buffered by tile
+                                                         // count: thread 0 writes slot k & 1 for tile k before that tile's
+                                                         // first barrier, everyone reads it after one; slot k & 1 is written
+                                                         // again for tile k + 2, i.e. after tile k + 1's barriers
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int ry = tid & (TILE_E - 1), rz = tid >> 5;   // TILE_E == 32: a warp is one z-row of the extended tile
-    const bool interior_row = ry >= TILE_K && ry < TILE_K + TILE_Y && rz >= TILE_K && rz < TILE_K + TILE_Y;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int ry = lane;                                 // TILE_E == 32: a warp's lanes are the y-rows of a z-row
     // rows away from the interior (0 inside); a halo row j rows out can reach the interior by level TILE_K only
     // through levels <= TILE_K - j, so level s needs just the rows with j <= TILE_K - s
     const int jy = ry < TILE_K ? TILE_K - ry : (ry >= TILE_K + TILE_Y ? ry - (TILE_K + TILE_Y - 1) : 0);
-    const int jz = rz < TILE_K ? TILE_K - rz : (rz >= TILE_K + TILE_Y ? rz - (TILE_K + TILE_Y - 1) : 0);
-    const int row_out = max(jy, jz);
+    const bool interior_y = ry >= TILE_K && ry < TILE_K + TILE_Y;
+    int jz[TILE_RPT], row_out[TILE_RPT];
+    bool interior_row[TILE_RPT];
+#pragma unroll
+    for (int r = 0; r < TILE_RPT; ++r) {
+        const int rz = warp + (TILE_E / TILE_RPT) * r;
+        jz[r] = rz < TILE_K ? TILE_K - rz : (rz >= TILE_K + TILE_Y ? rz - (TILE_K + TILE_Y - 1) : 0);
+        row_out[r] = max(jy, jz[r]);
+        interior_row[r] = interior_y && rz >= TILE_K && rz < TILE_K + TILE_Y;
+    }
     const int xwords = (g.DX + 31) / 32;                // words that hold cells
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(&g.ctrl[4]);
     int max_level = 0;
+    if (tid < 2 * (TILE_E + 2)) {
+        (&sZ[0][0])[tid] = 0;
+    }
+    __syncthreads();
 
     int n = 0;
     for (; n < max_supersteps; ++n) {
@@ -143,7 +176,7 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
         uint32_t* __restrict__ fnext = p ? g.front0 : g.front1;
         const int qi = n % 3, qi_next = (n + 1) % 3, qi_free = (n + 2) % 3;
         const int level0 = n * TILE_K;
-        // the active tiles of this super-step, dealt to the blocks by queue position (balanced counts)
+        // the active tiles of this super-step, dealt to the blocks by queue position
         const int q_len = __ldcg(&t.qn[qi]);
 #ifdef SMPLGPU_BFS_STATS
         if (blockIdx.x == 0 && tid == 0) atomicAdd(&g.ctrl[3], q_len);
@@ -152,174 +185,171 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
             break;   // no tile has a frontier left (every block reads the same length)
         }
         if (blockIdx.x == 0 && tid == 0) {
-            t.qn[qi_free] = 0;   // its readers ran before the last barrier, its writers start after the next one
-        }
-        if (blockIdx.x == 0 && tid == 0) {
+            t.qn[qi_free] = 0;       // its readers ran before the last barrier, its writers start after the next one
             t.qn[3 + qi_free] = 0;   // pull cursor of that queue
         }
         {
             // the first tile by block id, the following ones pulled from a shared cursor as blocks become free
-            // (tiles differ a lot in cost: a face across x keeps all 1024 rows busy, most others a few)
+            // (tiles differ a lot in cost)
             int k = 0;   // tiles this block has taken in this super-step
             for (int a = blockIdx.x; a < q_len; ++k) {
                 const int tile = __ldcg(&t.queue[(size_t)qi * t.ntiles + a]);
                 if (tid == 0) {
                     t.flag[(size_t)qi * t.ntiles + tile] = 0;   // consumed
                     s_next[k & 1] = (int)gridDim.x + atomicAdd(&t.qn[3 + qi], 1);   // next queue position, fetched while this tile runs
+                    s_act = 0;
                 }
 #ifdef SMPLGPU_BFS_STATS
                 const long long c0 = clock64();
 #endif
                 const int tx = tile % t.ntx, ty = (tile / t.ntx) % t.nty, tz = tile / (t.ntx * t.nty);
-                const int gy = ty * TILE_Y - TILE_K + ry, gz = tz * TILE_Y - TILE_K + rz;
-                const bool row_in = gy >= 0 && gy < g.DY && gz >= 0 && gz < g.DZ;
-                const size_t grow = (size_t)(row_in ? gz * g.DY + gy : 0);
+                const int gy = ty * TILE_Y - TILE_K + ry;
+                bool row_in[TILE_RPT];
+                size_t grow[TILE_RPT];
+                int gz[TILE_RPT];
 
-                // ---- load the frontier of this thread's row (3 words); a tile with no frontier cell in reach
-                //      has nothing to do (flags are raised conservatively) ----
-                unsigned wm = 0;   // which of the row's three words hold frontier cells
+                // ---- the frontier of this thread's rows: the interior word and 8 cells of each neighbour ----
+                uint32_t fw[TILE_RPT][3];
 #pragma unroll
-                for (int w = 0; w < 3; ++w) {
-                    const int gw = tx - 1 + w;
-                    uint32_t f = 0;
-                    if (row_in && gw >= 0 && gw < xwords) {
-                        f = __ldcg(&fcur[grow * g.W + gw]);
+                for (int r = 0; r < TILE_RPT; ++r) {
+                    const int rz = warp + (TILE_E / TILE_RPT) * r;
+                    gz[r] = tz * TILE_Y - TILE_K + rz;
+                    row_in[r] = gy >= 0 && gy < g.DY && gz[r] >= 0 && gz[r] < g.DZ;
+                    grow[r] = (size_t)(row_in[r] ? gz[r] * g.DY + gy : 0);
+#pragma unroll
+                    for (int w = 0; w < 3; ++w) {
+                        const int gw = tx - 1 + w;
+                        fw[r][w] = 0;
+                        if (row_in[r] && gw >= 0 && gw < xwords) {
+                            fw[r][w] = __ldcg(&fcur[grow[r] * g.W + gw]);
+                        }
                     }
-                    sF[0][tid * 3 + w] = f;
-                    sF[1][tid * 3 + w] = 0;
-                    wm |= (f != 0 ? 1u : 0u) << w;
                 }
-                const bool any = wm != 0;
-                sAny[0][tid] = (uint8_t)wm;
-                sAny[1][tid] = 0;
-                {
-                    const bool zany = __any_sync(0xffffffffu, any);
+                bool any0 = false;
+#pragma unroll
+                for (int r = 0; r < TILE_RPT; ++r) {
+                    const int rz = warp + (TILE_E / TILE_RPT) * r;
+                    const unsigned long long f0 = pack_row(fw[r][0], fw[r][1], fw[r][2]);
+                    sF[0][rz * TILE_E + lane] = f0;
+                    sF[1][rz * TILE_E + lane] = 0;
+                    const bool zany = __any_sync(0xffffffffu, f0 != 0);
                     if (lane == 0) {
-                        sZ[0][rz] = zany ? 1 : 0;
-                        sZ[1][rz] = 0;
+                        sZ[0][rz + 1] = zany ? 1 : 0;
+                        sZ[1][rz + 1] = 0;
                     }
+                    any0 |= zany;
                 }
-                if (tid == 0) {
-                    s_act = 0;
-                }
-                const int idle = !__syncthreads_or(any ? 1 : 0);
+                const int idle = !__syncthreads_or(any0 ? 1 : 0);
                 a = s_next[k & 1];   // (block-uniform) written before the barrier above
                 if (idle) {
-                    // nothing else was written to shared memory that the next tile's loads could overtake: sF / sAny /
-                    // sZ are rewritten by the thread that wrote them, s_act by thread 0 alone
+                    // a tile with no frontier cell in reach has nothing to do (flags are raised conservatively); what
+                    // was written to shared memory is rewritten by the same threads for the next tile
                     continue;
                 }
 #ifdef SMPLGPU_BFS_STATS
                 if (tid == 0) atomicAdd(&g.ctrl[6], 1);
 #endif
-                // ---- blocked words (registers), from the copy each owner tile committed last ----
-                uint32_t blk[3];
+                // ---- blocked cells of the rows (registers), from the copy each owner tile committed last ----
+                unsigned long long blk[TILE_RPT];
+                {
+                    uint32_t bw[TILE_RPT][3];
 #pragma unroll
-                for (int w = 0; w < 3; ++w) {
-                    const int gw = tx - 1 + w;
-                    uint32_t bb = 0xFFFFFFFFu;
-                    if (row_in && gw >= 0 && gw < xwords) {
-                        const int owner = ((gz / TILE_Y) * t.nty + gy / TILE_Y) * t.ntx + gw;
-                        const uint32_t* src = tile_copy(t, owner, n) ? t.blocked1 : g.blocked;
-                        bb = __ldcg(&src[grow * g.W + gw]);
+                    for (int r = 0; r < TILE_RPT; ++r) {
+#pragma unroll
+                        for (int w = 0; w < 3; ++w) {
+                            const int gw = tx - 1 + w;
+                            uint32_t bb = 0xFFFFFFFFu;
+                            if (row_in[r] && gw >= 0 && gw < xwords) {
+                                const int owner = ((gz[r] / TILE_Y) * t.nty + gy / TILE_Y) * t.ntx + gw;
+                                const uint32_t* src = tile_copy(t, owner, n) ? t.blocked1 : g.blocked;
+                                bb = __ldcg(&src[grow[r] * g.W + gw]);
+                            }
+                            bw[r][w] = bb;
+                        }
                     }
-                    blk[w] = bb;
+#pragma unroll
+                    for (int r = 0; r < TILE_RPT; ++r) {
+                        blk[r] = pack_row(bw[r][0], bw[r][1], bw[r][2]);
+                    }
                 }
-
 #ifdef SMPLGPU_BFS_STATS
                 __syncthreads();
                 const long long c1 = clock64();
 #endif
                 // ---- TILE_K levels in shared memory ----
-                bool changed = false;      // this thread's interior word gained cells
-                uint32_t last = 0;         // interior frontier word after the last level run
+                bool changed = false;              // one of this thread's interior words gained cells
+                uint32_t last[TILE_RPT] = { };     // interior frontier words after the last level run
                 int cur = 0, s = 1;
                 for (; s <= TILE_K; ++s) {
-                    uint32_t fresh[3] = { 0, 0, 0 };
-                    bool got = false;
-                    // a warp is one z-row of the tile: nothing to do unless this or an adjacent z-row has frontier
-                    const bool zact = jz <= TILE_K - s && (sZ[cur][rz - 1] | sZ[cur][rz] | sZ[cur][rz + 1]);
-                    const bool zstale = sZ[cur ^ 1][rz] != 0;   // the buffer written now held cells two levels ago
-                    if (zact && row_out <= TILE_K - s) {
-                        // any frontier in the 3 x 3 rows around this one?
-                        const uint8_t* A = sAny[cur];
-                        // words of the 3 x 3 rows around this one that hold frontier cells (a wavefront face across x
-                        // touches one word per row: only that word is gathered)
-                        const unsigned near = A[tid - 33] | A[tid - 32] | A[tid - 31] | A[tid - 1] | A[tid] | A[tid + 1] |
-                                              A[tid + 31] | A[tid + 32] | A[tid + 33];
-                        if (near) {
-                            const uint32_t* F = sF[cur];
-                            uint32_t m[3];
+                    bool any_fresh = false;
 #pragma unroll
-                            for (int w = 0; w < 3; ++w) {
-                                m[w] = 0;
-                                if ((near >> w) & 1u) {
-                                    m[w] = F[(tid - 33) * 3 + w] | F[(tid - 32) * 3 + w] | F[(tid - 31) * 3 + w] |
-                                           F[(tid - 1) * 3 + w] | F[tid * 3 + w] | F[(tid + 1) * 3 + w] |
-                                           F[(tid + 31) * 3 + w] | F[(tid + 32) * 3 + w] | F[(tid + 33) * 3 + w];
+                    for (int r = 0; r < TILE_RPT; ++r) {
+                        const int rz = warp + (TILE_E / TILE_RPT) * r;
+                        // nothing to do unless this or an adjacent z-row has frontier cells
+                        const bool zact = jz[r] <= TILE_K - s && (sZ[cur][rz] | sZ[cur][rz + 1] | sZ[cur][rz + 2]);
+                        const bool zstale = sZ[cur ^ 1][rz + 1] != 0;   // the buffer written now held cells two levels ago
+                        if (!zact && !zstale) {                         // warp-uniform
+                            if (interior_row[r]) last[r] = 0;
+                            continue;
+                        }
+                        const int row = rz * TILE_E + lane;
+                        unsigned long long fresh = 0;
+                        if (zact && row_out[r] <= TILE_K - s) {
+                            // the z-rows below / above the extended tile do not exist: rz - 1 < 0 or rz + 1 > 31 only for
+                            // rows with jz = TILE_K, which no level computes (jz <= TILE_K - s < TILE_K); the same for y
+                            const unsigned long long* F = sF[cur];
+                            const unsigned long long m = F[row - 33] | F[row - 32] | F[row - 31] | F[row - 1] | F[row] | F[row + 1] |
+                                                         F[row + 31] | F[row + 32] | F[row + 33];
+                            fresh = (m | (m << 1) | (m >> 1)) & ~blk[r] & ROW_MASK;
+                            blk[r] |= fresh;
+                        }
+                        const bool zgot = __any_sync(0xffffffffu, fresh != 0);
+                        sF[cur ^ 1][row] = fresh;      // the whole z-row is rewritten, so a clear flag means clear rows
+                        if (lane == 0) {
+                            sZ[cur ^ 1][rz + 1] = zgot ? 1 : 0;
+                        }
+                        any_fresh |= zgot;
+                        const uint32_t fresh_in = (uint32_t)(fresh >> 8);
+                        if (interior_row[r]) {
+                            last[r] = fresh_in;
+                            if (fresh_in) {
+                                changed = true;
+                                max_level = max(max_level, level0 + s);
+                            }
+                        }
+                        // distances of the interior word: a row with a few new cells (a wavefront face across x) stores
+                        // them itself; dense rows (faces along x) go out warp-wide, lanes = bits, one 128-byte store per row
+                        if (zgot && rz >= TILE_K && rz < TILE_K + TILE_Y) {
+                            const bool mine = interior_row[r] && fresh_in != 0;
+                            const bool dense = mine && __popc(fresh_in) > 4;
+                            if (mine && !dense) {
+                                int* d = g.dist + ((size_t)gz[r] * g.DY + gy) * g.DX + (size_t)tx * 32;
+                                uint32_t f = fresh_in;
+                                while (f) {
+                                    d[__ffs(f) - 1] = level0 + s;
+                                    f &= f - 1;
                                 }
                             }
-                            const uint32_t d0 = m[0] | (m[0] << 1) | (m[0] >> 1) | (m[1] << 31);
-                            const uint32_t d1 = m[1] | (m[1] << 1) | (m[1] >> 1) | (m[0] >> 31) | (m[2] << 31);
-                            const uint32_t d2 = m[2] | (m[2] << 1) | (m[2] >> 1) | (m[1] >> 31);
-                            fresh[0] = d0 & ~blk[0];
-                            fresh[1] = d1 & ~blk[1];
-                            fresh[2] = d2 & ~blk[2];
-                            blk[0] |= fresh[0];
-                            blk[1] |= fresh[1];
-                            blk[2] |= fresh[2];
-                            got = (fresh[0] | fresh[1] | fresh[2]) != 0;
+                            uint32_t todo = __ballot_sync(0xffffffffu, dense);
+                            while (todo) {
+                                const int rr = __ffs(todo) - 1;
+                                todo &= todo - 1;
+                                const uint32_t wk = __shfl_sync(0xffffffffu, fresh_in, rr);
+                                const int y2 = ty * TILE_Y - TILE_K + rr;
+                                if ((wk >> lane) & 1u) {
+                                    g.dist[((size_t)gz[r] * g.DY + y2) * g.DX + (size_t)tx * 32 + lane] = level0 + s;
+                                }
+                            }
                         }
                     }
-                    // rows that had cells in the target buffer two levels ago must be cleared
-                    if (got || (zstale && sAny[cur ^ 1][tid])) {
-                        sF[cur ^ 1][tid * 3] = fresh[0];
-                        sF[cur ^ 1][tid * 3 + 1] = fresh[1];
-                        sF[cur ^ 1][tid * 3 + 2] = fresh[2];
-                        sAny[cur ^ 1][tid] = (uint8_t)((fresh[0] != 0 ? 1u : 0u) | (fresh[1] != 0 ? 2u : 0u) | (fresh[2] != 0 ? 4u : 0u));
-                    }
-                    const bool zgot = __any_sync(0xffffffffu, got);
-                    if (lane == 0 && (zgot || zstale)) {
-                        sZ[cur ^ 1][rz] = zgot ? 1 : 0;
-                    }
-                    if (interior_row) {
-                        last = fresh[1];
-                        if (fresh[1]) {
-                            changed = true;
-                            max_level = max(max_level, level0 + s);
-                        }
-                    }
-                    const int alive = __syncthreads_or(got ? 1 : 0);
+                    const int alive = __syncthreads_or(any_fresh ? 1 : 0);
                     cur ^= 1;
 #ifdef SMPLGPU_BFS_STATS
                     if (tid == 0) atomicAdd(&g.ctrl[7], 1);
 #endif
-                    // distances of the interior word: a row with a few new cells (a wavefront face across x) stores
-                    // them itself; dense rows (faces along x) go out warp-wide, lanes = bits, one 128-byte store per row
-                    if (zgot && rz >= TILE_K && rz < TILE_K + TILE_Y) {
-                        const bool mine = interior_row && fresh[1] != 0;
-                        const bool dense = mine && __popc(fresh[1]) > 4;
-                        if (mine && !dense) {
-                            int* d = g.dist + ((size_t)gz * g.DY + gy) * g.DX + (size_t)tx * 32;
-                            uint32_t f = fresh[1];
-                            while (f) {
-                                d[__ffs(f) - 1] = level0 + s;
-                                f &= f - 1;
-                            }
-                        }
-                        uint32_t todo = __ballot_sync(0xffffffffu, dense);
-                        while (todo) {
-                            const int r = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            const uint32_t wk = __shfl_sync(0xffffffffu, fresh[1], r);
-                            const int y2 = ty * TILE_Y - TILE_K + r;
-                            if ((wk >> lane) & 1u) {
-                                g.dist[((size_t)gz * g.DY + y2) * g.DX + (size_t)tx * 32 + lane] = level0 + s;
-                            }
-                        }
-                    }
                     if (!alive) {
-                        last = 0;   // nothing was found at level s: the frontier is empty from here on
+#pragma unroll
+                        for (int r = 0; r < TILE_RPT; ++r) last[r] = 0;   // nothing was found at level s: the frontier is empty from here on
                         break;
                     }
                 }
@@ -331,34 +361,43 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                 if (__syncthreads_or(changed ? 1 : 0)) {
                     const uint32_t v = tile_copy(t, tile, n);
                     uint32_t* dst = v ? g.blocked : t.blocked1;
-                    if (interior_row && row_in && tx < xwords) {
-                        dst[grow * g.W + tx] = blk[1];
+#pragma unroll
+                    for (int r = 0; r < TILE_RPT; ++r) {
+                        if (interior_row[r] && row_in[r] && tx < xwords) {
+                            dst[grow[r] * g.W + tx] = (uint32_t)(blk[r] >> 8);
+                        }
                     }
                     if (tid == 0) {
                         t.ver[tile] = ((uint32_t)(n + 1) << 1) | (v ^ 1u);
                     }
                 }
-                if (interior_row && row_in && tx < xwords) {
-                    fnext[grow * g.W + tx] = last;
-                }
-                // tiles whose interior is within TILE_K cells of a remaining frontier cell run next super-step
-                if (interior_row && last != 0) {
-                    const int iy = ry - TILE_K, iz = rz - TILE_K;
-                    const unsigned xs = 2u | ((last & 0x000000FFu) ? 1u : 0u) | ((last & 0xFF000000u) ? 4u : 0u);   // bit dx+1
-                    const unsigned ys = 2u | (iy < TILE_K ? 1u : 0u) | (iy >= TILE_Y - TILE_K ? 4u : 0u);
-                    const unsigned zs = 2u | (iz < TILE_K ? 1u : 0u) | (iz >= TILE_Y - TILE_K ? 4u : 0u);
-                    unsigned act = 0;
+                unsigned act = 0;
 #pragma unroll
-                    for (int c = 0; c < 27; ++c) {
-                        if (((xs >> (c % 3)) & 1u) && ((ys >> ((c / 3) % 3)) & 1u) && ((zs >> (c / 9)) & 1u)) {
-                            act |= 1u << c;
+                for (int r = 0; r < TILE_RPT; ++r) {
+                    if (interior_row[r] && row_in[r] && tx < xwords) {
+                        fnext[grow[r] * g.W + tx] = last[r];
+                    }
+                    // tiles whose interior is within TILE_K cells of a remaining frontier cell run next super-step
+                    if (interior_row[r] && last[r] != 0) {
+                        const int rz = warp + (TILE_E / TILE_RPT) * r;
+                        const int iy = ry - TILE_K, iz = rz - TILE_K;
+                        const unsigned xs = 2u | ((last[r] & 0x000000FFu) ? 1u : 0u) | ((last[r] & 0xFF000000u) ? 4u : 0u);   // bit dx+1
+                        const unsigned ys = 2u | (iy < TILE_K ? 1u : 0u) | (iy >= TILE_Y - TILE_K ? 4u : 0u);
+                        const unsigned zs = 2u | (iz < TILE_K ? 1u : 0u) | (iz >= TILE_Y - TILE_K ? 4u : 0u);
+#pragma unroll
+                        for (int c = 0; c < 27; ++c) {
+                            if (((xs >> (c % 3)) & 1u) && ((ys >> ((c / 3) % 3)) & 1u) && ((zs >> (c / 9)) & 1u)) {
+                                act |= 1u << c;
+                            }
                         }
                     }
+                }
+                if (act != 0) {
                     atomicOr(&s_act, act);
                 }
                 __syncthreads();
-                const unsigned act = s_act;
-                if (tid < 27 && ((act >> tid) & 1u)) {
+                const unsigned acts = s_act;
+                if (tid < 27 && ((acts >> tid) & 1u)) {
                     const int ax = tx + tid % 3 - 1, ay = ty + (tid / 3) % 3 - 1, az = tz + tid / 9 - 1;
                     if (ax >= 0 && ay >= 0 && az >= 0 && ax < t.ntx && ay < t.nty && az < t.ntz) {
                         tile_enqueue(t, (az * t.nty + ay) * t.ntx + ax, qi_next);

@@ -2080,14 +2080,20 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
     if (tiles) {
         bfs_tiles_seed_kernel<<<(n_seeds + 127) / 128, 128, 0, stream>>>(g, t, d_seeds, n_seeds);
         ++ctx->launches;
-        // persistent cooperative kernel: TILE_K levels per grid barrier, one 1024-thread block per SM
+        // persistent cooperative kernel, TILE_K levels per grid barrier: 1024-thread blocks, one per SM, for grids with
+        // few tiles; 256-thread blocks, four per SM, for large ones (bfs_tiles.cuh; SMPLGPU_BFS_TILE_RPT forces 1 or 4)
+        static const int forced = getenv("SMPLGPU_BFS_TILE_RPT") ? atoi(getenv("SMPLGPU_BFS_TILE_RPT")) : 0;
+        const bool large = forced > 0 ? forced >= TILE_RPT_LARGE : t.ntiles >= 4096;
+        const void* kern = large ? (const void*)bfs_tiles_kernel<TILE_RPT_LARGE> : (const void*)bfs_tiles_kernel<1>;
+        const int threads = large ? TILE_THREADS / TILE_RPT_LARGE : TILE_THREADS;
         int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_tiles_kernel, TILE_THREADS, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
         if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS tile kernel does not fit an SM");
+        per_sm = std::min(per_sm, large ? TILE_RPT_LARGE : 1);
         const int blocks = std::max(1, std::min(ctx->sm_count * per_sm, t.ntiles));
         int max_steps = (int)std::min<long long>(cap / TILE_K + 2, 0x7FFFFFFFLL / blocks - 1);
         void* args[] = { (void*)&g, (void*)&t, (void*)&max_steps };
-        CU(cudaLaunchCooperativeKernel((void*)bfs_tiles_kernel, dim3(blocks), dim3(TILE_THREADS), args, 0, stream));
+        CU(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(threads), args, 0, stream));
         ++ctx->launches;
     } else {
         // persistent cooperative kernel, one block per SM (the grid barrier costs one arrival per block)
