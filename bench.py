@@ -558,6 +558,7 @@ def main():
     ap.add_argument("--post-paths", type=int, default=1024, help="joint-space paths shortcut in one call (0 = skip)")
     ap.add_argument("--post-cpu-paths", type=int, default=48)
     ap.add_argument("--no-ingest", dest="ingest", action="store_false", help="skip the scene-ingest leg")
+    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads (= contexts) of the end-to-end leg; 0 = min(8, cores per rank)")
     ap.add_argument("--plan-threads", type=int, default=0, help="planner threads (= contexts) per GPU; 0 = 75 %% of the rank's cores, at most 6")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "smpl_b200" else args.warmup
@@ -693,10 +694,61 @@ def main():
         return world * units_per_step * steps / (float(t.item()) * 1e-3)
 
     e2e_steps = max(3, args.steps // 2)
-    e2e_value = time_e2e(step_e2e, e2e_steps)
+    e2e_single = time_e2e(step_e2e, e2e_steps)
     e2e_f64_value = time_e2e(step_e2e_f64, max(3, e2e_steps // 2))
     assert torch.equal(hv.to(dev), d_v) and torch.equal(hev.to(dev), d_ev), "host-buffer (lattice) path disagrees with resident path"
     assert torch.equal(hv2.to(dev), d_v) and torch.equal(hev2.to(dev), d_ev), "host-buffer (double) path disagrees with resident path"
+
+    # The headline e2e: the same step issued the way the reference is used at scale -- K host threads, one context each
+    # (its CollisionSpace is one-per-thread too; `--impl reference` runs one per host thread), thread k validating the
+    # k-th share of the step's states and edges from the same pinned buffers.  The callers' copies and kernels overlap.
+    # Timed by the host clock between a barrier in front of the K synchronous callers and the join behind them.
+    e2e_threads = args.e2e_threads if args.e2e_threads > 0 else max(1, min(8, (os.cpu_count() or 1) // max(1, world)))
+    hv.zero_()
+    hev.zero_()
+    ectxs = [ctx] + [api.clone_context(ctx, scene, tables, device=local_rank) for _ in range(e2e_threads - 1)]
+    for c in ectxs[1:]:
+        c.set_lattice(res)
+    bounds = np.linspace(0, n, e2e_threads + 1).astype(np.int64)
+    gate = threading.Barrier(e2e_threads + 1)
+    e2e_errors = []
+
+    def e2e_worker(k):
+        c = ectxs[k]
+        L.smplgpu_bind_thread(c.h)
+        b, e = int(bounds[k]), int(bounds[k + 1])
+        pc = C.cast(hc.data_ptr() + b * dof * 2, c_i16_p)
+        pp = C.cast(hp.data_ptr() + b, api.c_uint8_p)
+        pv = C.cast(hv.data_ptr() + b, api.c_uint8_p)
+        pe = C.cast(hev.data_ptr() + b, api.c_uint8_p)
+        for it in range(e2e_steps + 2):
+            if it == 2:
+                gate.wait()
+            r = L.smplgpu_is_lattice_states_valid(c.h, pc, e - b, pv)
+            r |= L.smplgpu_is_lattice_edges_valid(c.h, pc, pp, e - b, deltas_p, len(deltas), pe, None)
+            if r != 0:
+                e2e_errors.append(L.smplgpu_last_error(c.h).decode())
+                break
+
+    workers = [threading.Thread(target=e2e_worker, args=(k,)) for k in range(e2e_threads)]
+    for w in workers:
+        w.start()
+    barrier()
+    gate.wait()
+    t0 = time.perf_counter()
+    for w in workers:
+        w.join()
+    e2e_wall = time.perf_counter() - t0
+    if e2e_errors:
+        raise RuntimeError(e2e_errors[0])
+    t_e2e = torch.tensor([e2e_wall], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * units_per_step * e2e_steps / float(t_e2e.item())
+    for c in ectxs[1:]:
+        c.close()
+    L.smplgpu_bind_thread(ctx.h)
+    assert torch.equal(hv.to(dev), d_v) and torch.equal(hev.to(dev), d_ev), "multi-context host-buffer path disagrees with resident path"
     verdict_s, verdict_e, counts_e = hv.numpy().copy(), hev.numpy().copy(), d_cnt.cpu().numpy()
 
     # ---- BFS (config[2]): 400^3 cluttered occupancy (+ the planner's 150^3 size), rank 0 only ----
@@ -944,6 +996,8 @@ def main():
     checked_per_step = n + gpu_stats["waypoints"] if dom is k_edges else None
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * (2 * dof * n) + n, "d2h_bytes_per_step": 2 * n,
            "calls": "smplgpu_is_lattice_states_valid + smplgpu_is_lattice_edges_valid: 16-bit RobotCoord (+ 1 primitive byte per edge) in pinned host buffers, verdicts out",
+           "host_threads": e2e_threads, "timing": "host clock around K synchronous callers (one context per thread), max over ranks",
+           "single_context_value": e2e_single,
            "f64_value": e2e_f64_value, "f64_h2d_bytes_per_step": 2 * n * dof * 8 + 4 * n,
            "f64_calls": "smplgpu_is_states_valid + smplgpu_is_mprim_edges_valid (joint values as doubles)"}
     if checked_per_step:
