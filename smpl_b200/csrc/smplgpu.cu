@@ -2054,8 +2054,11 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
     if (d_seed_count == nullptr) d_seed_count = ctx->d_seed_count;
     const int total = (int)words;
     BfsTiles& t = (&g == &ctx->bank) ? ctx->bank_tiles : ctx->bfs_tiles;
-    // AUTO: the tile kernel for a single grid (bound by the per-level latency), the level kernel for the stacked
-    // banks (many wavefronts at once: throughput bound); see bfs_tiles.cuh
+    // AUTO: the tile kernel for a single grid, the level kernel for the stacked planner banks.  In isolation the tile
+    // kernel now does a bank query in 0.089 ms against the level kernel's 0.148 ms (tools/bank_bfs_time.py), but inside
+    // the planner -- bank runs of several contexts taking turns while the other contexts' expansion rounds share the
+    // SMs -- it gained nothing at 6 contexts (1808 vs 1940 queries/s) and at 4 contexts a cooperative launch of 444
+    // resident blocks waited seconds for room (setup 3.4 s): its blocks fill the register file of every SM they sit on.
     const bool single = &g != &ctx->bank;
     const bool tiles = ctx->bfs_mode == SMPLGPU_BFS_TILES || (ctx->bfs_mode == SMPLGPU_BFS_AUTO && single);
     {
@@ -2090,7 +2093,13 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
         if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS tile kernel does not fit an SM");
         per_sm = std::min(per_sm, large ? TILE_RPT_LARGE : 1);
-        const int blocks = std::max(1, std::min(ctx->sm_count * per_sm, t.ntiles));
+        // A run queued behind the caller's back (smplgpu_bfs_bank_run_slots_async) leaves room for the expansion
+        // rounds that are meant to keep flowing meanwhile: three of the four block slots of every SM (large grids), or
+        // seven eighths of the SMs (1024-thread blocks); a synchronous run takes the whole machine.
+        const bool async_run = stream == ctx->bfs_stream;
+        if (async_run && large) per_sm = std::max(1, per_sm - 1);
+        const int sms = (async_run && !large) ? ctx->sm_count - std::max(1, ctx->sm_count / 8) : ctx->sm_count;
+        const int blocks = std::max(1, std::min(sms * per_sm, t.ntiles));
         int max_steps = (int)std::min<long long>(cap / TILE_K + 2, 0x7FFFFFFFLL / blocks - 1);
         void* args[] = { (void*)&g, (void*)&t, (void*)&max_steps };
         CU(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(threads), args, 0, stream));

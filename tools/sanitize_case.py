@@ -22,6 +22,16 @@ ctx.fk_sphere_centers(q[:64]); ctx.fk_sphere_centers_f32(q[:64]); ctx.check_join
 ctx.bfs_set_walls_from_df(scene.inflation_radius)
 ctx.bfs_run([api.world_to_grid([[0.4, -0.2, 0.8]], scene.origin, scene.res)[0]])
 ctx.goal_heuristics(q[:256], 100)
+# round-2 entry points: one-launch expansion records, lattice states as 16-bit coordinates, clearance
+pr = scenes.PlanParams(scene.dof)
+ctx.set_motion_primitives(np.concatenate([pr.mprims, -pr.mprims]))
+for k in range(8):
+    ctx.expand_state(q[k], 100)
+ctx.set_lattice(pr.resolutions)
+lc, lq = scenes.random_lattice_coords(3000, lo, hi, cont, pr.resolutions, seed=4)
+assert np.array_equal(ctx.is_lattice_states_valid(lc), ctx.is_states_valid(lq))
+ctx.is_lattice_edges_valid(lc, (np.arange(len(lc)) % len(d)).astype(np.uint8), d)
+ctx.collision_distance(q[:256])
 walls = scenes.bfs_clutter_walls(48, seed=5)
 ctx.bfs_set_walls(walls); ctx.bfs_run([scenes.first_free_cell(walls, (24, 24, 24))]); ctx.bfs_download()
 ctx.close()
