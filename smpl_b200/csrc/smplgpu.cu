@@ -24,6 +24,7 @@
 #include "model.cuh"
 #include "validity.cuh"
 #include "validity32.cuh"
+#include "validity_warp.cuh"
 #include "expand1.cuh"
 #include "lattice.cuh"
 
@@ -171,6 +172,16 @@ static bool v32_persistent()
     return on;
 }
 
+// SMPLGPU_WARP_RESOLVE=0 selects the thread-per-item double-precision resolve kernels of round 1 (A/B switch)
+static bool warp_resolve()
+{
+    static const bool on = [] {
+        const char* e = getenv("SMPLGPU_WARP_RESOLVE");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    return on;
+}
+
 #define CU(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -283,6 +294,10 @@ smplgpu_ctx* smplgpu_create(int device)
     }
     ctx->h_model = new DevModel;
     memset(ctx->h_model, 0, sizeof(DevModel));
+    if (const char* e = getenv("SMPLGPU_BFS_MODE")) {   // experiments: 0 tiles, 1 levels, 2 auto (smplgpu_bfs_set_mode)
+        const int m = atoi(e);
+        if (m >= 0 && m <= 2) ctx->bfs_mode = m;
+    }
     return ctx;
 }
 
@@ -1411,9 +1426,16 @@ static int launch_states(smplgpu_ctx* ctx, const double* dq, int n, uint8_t* dv)
     states_valid32_kernel<<<std::min((n + t32 - 1) / t32, wave), t32, v32_smem(ctx), ctx->stream>>>(
         ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq, n, dv, ctx->d_unc_list,
         ctx->d_unc_count, ctx->d_stats);
-    const int blocks = std::max(1, std::min((n + vt - 1) / vt, 2 * ctx->sm_count));
-    states_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
-        ctx->d_model, ctx->d_df, ctx->grid, dq, n, dv, nullptr, ctx->d_unc_list, ctx->d_unc_count);
+    if (warp_resolve()) {
+        // the undecided states, a warp each (validity_warp.cuh): the list is a fraction of a percent of the batch
+        const int blocks = std::max(1, std::min((n / 64 + RESOLVE_WARPS - 1) / RESOLVE_WARPS + 1, 8 * ctx->sm_count));
+        states_resolve_kernel<<<blocks, 32 * RESOLVE_WARPS, 0, ctx->stream>>>(
+            ctx->d_model, ctx->d_df, ctx->grid, dq, n, dv, ctx->d_unc_list, ctx->d_unc_count);
+    } else {
+        const int blocks = std::max(1, std::min((n + vt - 1) / vt, 2 * ctx->sm_count));
+        states_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
+            ctx->d_model, ctx->d_df, ctx->grid, dq, n, dv, nullptr, ctx->d_unc_list, ctx->d_unc_count);
+    }
     ctx->launches += 2;
     CU(cudaGetLastError());
     return 0;
@@ -1442,10 +1464,16 @@ static int launch_edges(smplgpu_ctx* ctx, const double* dq0, const double* dq1, 
     edges_valid32_kernel<<<(n + t32 - 1) / t32, t32, v32_smem(ctx), ctx->stream>>>(
         ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq0, dq1, n, dv, dc, ctx->d_unc_list,
         ctx->d_unc_count, ctx->d_stats);
-    const int per_block = std::max(1, vt / 4);
-    const int blocks = std::max(1, std::min((n + per_block - 1) / per_block, 2 * ctx->sm_count));
-    edges_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
-        ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, n, dv, nullptr, nullptr, ctx->d_unc_list, ctx->d_unc_count);
+    if (warp_resolve()) {
+        const int blocks = std::max(1, std::min((n / 64 + RESOLVE_WARPS - 1) / RESOLVE_WARPS + 1, 8 * ctx->sm_count));
+        edges_resolve_kernel<<<blocks, 32 * RESOLVE_WARPS, 0, ctx->stream>>>(
+            ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, n, dv, ctx->d_unc_list, ctx->d_unc_count);
+    } else {
+        const int per_block = std::max(1, vt / 4);
+        const int blocks = std::max(1, std::min((n + per_block - 1) / per_block, 2 * ctx->sm_count));
+        edges_valid_kernel<<<blocks, vt, validity_smem(ctx), ctx->stream>>>(
+            ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, n, dv, nullptr, nullptr, ctx->d_unc_list, ctx->d_unc_count);
+    }
     ctx->launches += 2;
     CU(cudaGetLastError());
     return 0;
