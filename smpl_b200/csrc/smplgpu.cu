@@ -135,11 +135,12 @@ struct smplgpu_ctx
     void* d_lat[SMPLGPU_EXPAND_BUFFERS] = { };   size_t d_lat_cap[SMPLGPU_EXPAND_BUFFERS] = { };    // q0 | q1 | active | verdict
     int lat_n[SMPLGPU_EXPAND_BUFFERS] = { -1, -1, -1, -1 };
     int lat_max_n = 0;
+    int lat_dof = 0;                               // dof the lattice arrays were sized for
     unsigned long long* lat_resolved = nullptr;   // pinned, mapped: edges the rounds resolved in double (running total)
     bool lat_fused = false;                        // one kernel per round (lattice_round_kernel)
     size_t lat_round_smem = 0;
     // smplgpu_expand_state: primitive table, page-locked record array + completion flag, arrival counter
-    double* d_x1_deltas = nullptr; int x1_prims = -1;
+    double* d_x1_deltas = nullptr; int x1_prims = -1; int x1_dof = 0;
     smplgpu_succ_info* x1_out = nullptr; size_t x1_out_cap = 0;   // records; the flag word follows them
     unsigned int* d_x1_done = nullptr;
     unsigned long long x1_seq = 0;
@@ -1037,6 +1038,13 @@ int smplgpu_set_robot(smplgpu_ctx* ctx, const smplgpu_robot_desc* d)
     }
     ctx->has_robot = true;
     ++ctx->scene_epoch;
+    // what was derived from the previous robot: lattice discretisation, primitive table, device lattices
+    ctx->has_lattice = false;
+    if (ctx->x1_dof != m.dof) ctx->x1_prims = -1;
+    if (ctx->has_lat && ctx->lat_dof != m.dof) {
+        for (int b = 0; b < SMPLGPU_EXPAND_BUFFERS; ++b) ctx->lat_n[b] = -1;
+        free_lattice(ctx);
+    }
     return upload_model(ctx);
 }
 
@@ -1073,6 +1081,7 @@ static int set_df_common(smplgpu_ctx* ctx, int nx, int ny, int nz, const double 
     ctx->res = res;
     ctx->padding = padding;
     ctx->dmax_sq = dmax_sq;
+    ctx->lat.res = res;   // mprimActive's metric goal distance = BFS cells * resolution
     memcpy(ctx->origin, origin, 3 * sizeof(double));
     return 0;
 }
@@ -2804,12 +2813,14 @@ int smplgpu_lattice_create(smplgpu_ctx* ctx, const smplgpu_lattice_params* p, in
     CU(cudaStreamSynchronize(ctx->stream));
     const int cap = p->max_states;
     const int tsize = lattice_table_size(cap);
-    const bool same_shape = ctx->has_lat && ctx->lat.n_slots == n_slots && ctx->lat.cap == cap && ctx->lat.stride == stride;
+    const bool same_shape = ctx->has_lat && ctx->lat.n_slots == n_slots && ctx->lat.cap == cap && ctx->lat.stride == stride &&
+                            ctx->lat_dof == dof;
     if (!same_shape) {
         // the lattices are a scene-level allocation (gigabytes for thousands of queries): kept across calls
         free_lattice(ctx);
         LatticeBank& B = ctx->lat;
         B.n_slots = n_slots; B.cap = cap; B.table_size = tsize; B.stride = stride;
+        ctx->lat_dof = dof;
         CU(cudaMalloc(&B.q, (size_t)n_slots * cap * dof * sizeof(double)));
         CU(cudaMalloc(&B.coord, (size_t)n_slots * cap * dof * sizeof(int)));
         CU(cudaMalloc(&B.gdist, (size_t)n_slots * cap * sizeof(int)));
@@ -3123,6 +3134,7 @@ int smplgpu_set_motion_primitives(smplgpu_ctx* ctx, const double* deltas, int n_
         CU(cudaMemset(ctx->d_x1_done, 0, sizeof(unsigned int)));
     }
     ctx->x1_prims = n_prims;
+    ctx->x1_dof = dof;
     ++ctx->scene_epoch;
     return 0;
 }
@@ -3132,7 +3144,8 @@ int smplgpu_expand_state(smplgpu_ctx* ctx, const double* parent, int cost_per_ce
     if (!ctx || !parent || !info) return SMPLGPU_ERR_INVALID;
     int r = need_scene(ctx);
     if (r) return r;
-    if (ctx->x1_prims < 0) return fail(ctx, SMPLGPU_ERR_STATE, "motion primitives not set (smplgpu_set_motion_primitives)");
+    if (ctx->x1_prims < 0 || ctx->x1_dof != ctx->h_model->dof)
+        return fail(ctx, SMPLGPU_ERR_STATE, "motion primitives not set for this robot (smplgpu_set_motion_primitives)");
     const bool bfs_ok = ctx->has_bfs && ctx->bfs.nx == ctx->grid.nx && ctx->bfs.ny == ctx->grid.ny && ctx->bfs.nz == ctx->grid.nz;
     Expand1Parent p;
     const int dof = ctx->h_model->dof;

@@ -51,3 +51,31 @@ def test_null_context_is_rejected():
     assert L.smplgpu_synchronize(None) < 0
     assert L.smplgpu_bfs_last_levels(None) < 0
     assert L.smplgpu_is_states_valid(None, None, 0, None) < 0
+
+
+def test_round2_entry_points_reject_a_null_context():
+    """the entry points added in round 2 follow the same convention: negative code, no crash, no fallback"""
+    L = api.gpu_lib()
+    assert L.smplgpu_set_motion_primitives(None, None, 0) < 0
+    assert L.smplgpu_expand_state(None, None, 0, None) < 0
+    assert L.smplgpu_scene_epoch(None) < 0
+    assert L.smplgpu_set_lattice(None, None, None) < 0
+    assert L.smplgpu_is_lattice_states_valid(None, None, 0, None) < 0
+    assert L.smplgpu_is_lattice_edges_valid(None, None, None, 0, None, 0, None, None) < 0
+    assert L.smplgpu_collision_distance(None, None, 0, None) < 0
+    assert L.smplgpu_reserve_distance_field(None, 1, 1, 1, None, None) < 0
+    assert L.smplgpu_set_distance_field_l2_persistence(None, 1, None) < 0
+    for name in ("smplgpu_lattice_max_slots", "smplgpu_lattice_create", "smplgpu_lattice_begin", "smplgpu_lattice_expand_submit",
+                 "smplgpu_lattice_expand_wait", "smplgpu_lattice_states"):
+        assert hasattr(L, name)
+    L.smplgpu_lattice_max_slots.argtypes = [C.c_void_p, C.c_int]
+    assert L.smplgpu_lattice_max_slots(None, 100) < 0
+    L.smplgpu_lattice_expand_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    assert L.smplgpu_lattice_expand_submit(None, None, None, 0, 0) < 0
+
+
+def test_succ_info_layout_matches_the_header():
+    """api.SuccInfoC mirrors smplgpu_succ_info (include/smplgpu.h): 16 + 6 + 3 doubles, 3 ints, 4 bytes"""
+    assert C.sizeof(api.SuccInfoC) == 25 * 8 + 3 * 4 + 4
+    src = open(os.path.join(ROOT, "include", "smplgpu.h")).read()
+    assert "#define SMPLGPU_MAX_DOF 16" in src
