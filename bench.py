@@ -714,27 +714,33 @@ def main():
     e2e_errors = []
 
     def e2e_worker(k):
-        c = ectxs[k]
-        L.smplgpu_bind_thread(c.h)
-        b, e = int(bounds[k]), int(bounds[k + 1])
-        pc = C.cast(hc.data_ptr() + b * dof * 2, c_i16_p)
-        pp = C.cast(hp.data_ptr() + b, api.c_uint8_p)
-        pv = C.cast(hv.data_ptr() + b, api.c_uint8_p)
-        pe = C.cast(hev.data_ptr() + b, api.c_uint8_p)
-        for it in range(e2e_steps + 2):
-            if it == 2:
-                gate.wait()
-            r = L.smplgpu_is_lattice_states_valid(c.h, pc, e - b, pv)
-            r |= L.smplgpu_is_lattice_edges_valid(c.h, pc, pp, e - b, deltas_p, len(deltas), pe, None)
-            if r != 0:
-                e2e_errors.append(L.smplgpu_last_error(c.h).decode())
-                break
+        try:
+            c = ectxs[k]
+            L.smplgpu_bind_thread(c.h)
+            b, e = int(bounds[k]), int(bounds[k + 1])
+            pc = C.cast(hc.data_ptr() + b * dof * 2, c_i16_p)
+            pp = C.cast(hp.data_ptr() + b, api.c_uint8_p)
+            pv = C.cast(hv.data_ptr() + b, api.c_uint8_p)
+            pe = C.cast(hev.data_ptr() + b, api.c_uint8_p)
+            for it in range(e2e_steps + 2):
+                if it == 2:
+                    gate.wait(timeout=300)
+                r = L.smplgpu_is_lattice_states_valid(c.h, pc, e - b, pv)
+                r |= L.smplgpu_is_lattice_edges_valid(c.h, pc, pp, e - b, deltas_p, len(deltas), pe, None)
+                if r != 0:
+                    raise RuntimeError(L.smplgpu_last_error(c.h).decode())
+        except Exception as ex:   # a failing caller must not leave the others (or the main thread) at the barrier
+            e2e_errors.append(repr(ex))
+            gate.abort()
 
     workers = [threading.Thread(target=e2e_worker, args=(k,)) for k in range(e2e_threads)]
     for w in workers:
         w.start()
     barrier()
-    gate.wait()
+    try:
+        gate.wait(timeout=300)
+    except threading.BrokenBarrierError:
+        pass
     t0 = time.perf_counter()
     for w in workers:
         w.join()

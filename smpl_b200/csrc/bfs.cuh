@@ -251,6 +251,164 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
 // Frontier words are only current for the words a row published; a stale word holds cells discovered two
 // levels earlier, whose neighbours are all discovered already, so whatever it contributes is removed by
 // `& ~blocked`.
+// One BFS level over this block's share of the rows (see bfs_levels_kernel for the data flow).  Returns whether this
+// THREAD discovered cells.
+__device__ __forceinline__ bool bfs_level_body(const BfsGrid& g, uint32_t level, uint32_t* s_item, uint32_t* s_info,
+                                               int* s_warp_sum, int* s_total_p)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int groups = (g.rows + 7) / 8;                         // groups of 8 consecutive rows
+    const int slots = (groups + (int)gridDim.x - 1) / (int)gridDim.x * 8;   // row slots of this block
+    const uint32_t wmask_all = g.W >= 16 ? 0xFFFFu : ((1u << g.W) - 1u);
+    int& s_total = *s_total_p;
+    const bool odd = level & 1;
+    const uint32_t* __restrict__ fcur = odd ? g.front0 : g.front1;
+    uint32_t* __restrict__ fnext = odd ? g.front1 : g.front0;
+    uint32_t* __restrict__ cand_in = odd ? g.cand0 : g.cand1;
+    uint32_t* __restrict__ cand_out = odd ? g.cand1 : g.cand0;
+    bool any_new = false;
+
+    for (int t0 = 0; t0 < slots; t0 += BFS_THREADS * BFS_ROWS_PER_THREAD) {
+        // ---- fetch this thread's candidate words (independent loads, one latency) ----
+        int rows[BFS_ROWS_PER_THREAD];
+        uint32_t words[BFS_ROWS_PER_THREAD];
+#pragma unroll
+        for (int u = 0; u < BFS_ROWS_PER_THREAD; ++u) {
+            const int t = t0 + u * BFS_THREADS + threadIdx.x;
+            const int gi = blockIdx.x + (t >> 3) * gridDim.x;
+            rows[u] = gi * 8 + (t & 7);
+            words[u] = 0;
+            if (t < slots && gi < groups && rows[u] < g.rows) {
+                words[u] = __ldcg(&cand_in[rows[u]]);
+            }
+        }
+        // ---- items per candidate row: published words dilated by one ----
+        uint32_t dmask[BFS_ROWS_PER_THREAD];
+        int mine = 0;
+#pragma unroll
+        for (int u = 0; u < BFS_ROWS_PER_THREAD; ++u) {
+            dmask[u] = 0;
+            if (words[u] != 0) {
+                cand_in[rows[u]] = 0;   // consumed; this array is written again two levels from now
+                const int z = rows[u] / g.DY, y = rows[u] - z * g.DY;
+                if (!(z == 0 || z == g.DZ - 1 || y == 0 || y == g.DY - 1)) {   // border shell rows are all wall
+                    const uint32_t wm = (words[u] >> 9) & 0xFFFFu;
+                    // word index is kept mod 16: with more than 16 words per row bit 15 neighbours bit 0
+                    uint32_t d = wm | (wm << 1) | (wm >> 1);
+                    if (g.W > 16) {
+                        d |= (wm >> 15) | (wm << 15);
+                    }
+                    dmask[u] = d & wmask_all;
+                }
+            }
+            // with W > 16 every word congruent to a set bit becomes an item
+            int n = __popc(dmask[u]);
+            if (g.W > 16) {
+                n = 0;
+                for (int w = 0; w < g.W; ++w) n += (dmask[u] >> (w & 15)) & 1u;
+            }
+            mine += n;
+        }
+        // ---- block-wide exclusive scan of `mine` ----
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) {
+            s_warp_sum[warp] = incl;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int v = s_warp_sum[lane];
+            int inc2 = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int x = __shfl_up_sync(0xffffffffu, inc2, o);
+                if (lane >= o) inc2 += x;
+            }
+            s_warp_sum[lane] = inc2 - v;
+            if (lane == 31) {
+                s_total = inc2;
+            }
+        }
+        __syncthreads();
+        const int my_off = s_warp_sum[warp] + incl - mine;
+        const int total = s_total;
+
+        // ---- rounds of at most BFS_ITEM_CAP items ----
+        for (int r0 = 0; r0 < total; r0 += BFS_ITEM_CAP) {
+            int pos = my_off;
+#pragma unroll
+            for (int u = 0; u < BFS_ROWS_PER_THREAD; ++u) {
+                if (dmask[u] == 0) {
+                    continue;
+                }
+                const uint32_t wm = (words[u] >> 9) & 0xFFFFu;
+                const uint32_t nb = words[u] & 0x1FFu;
+                for (int w = 0; w < g.W; ++w) {
+                    if (!((dmask[u] >> (w & 15)) & 1u)) {
+                        continue;
+                    }
+                    if (pos >= r0 && pos < r0 + BFS_ITEM_CAP) {
+                        const uint32_t hl = (w > 0 && ((wm >> ((w - 1) & 15)) & 1u)) ? 1u : 0u;
+                        const uint32_t hr = (w + 1 < g.W && ((wm >> ((w + 1) & 15)) & 1u)) ? 1u : 0u;
+                        const uint32_t hs = (wm >> (w & 15)) & 1u;
+                        s_item[pos - r0] = (uint32_t)rows[u];
+                        s_info[pos - r0] = (uint32_t)w | (nb << 8) | (hl << 17) | (hr << 18) | (hs << 19);
+                    }
+                    ++pos;
+                }
+            }
+            __syncthreads();
+            const int n_items = min(BFS_ITEM_CAP, total - r0);
+            for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+                const int row = (int)s_item[i];
+                const uint32_t info = s_info[i];
+                const int w = info & 0xFFu;
+                const uint32_t nb = (info >> 8) & 0x1FFu;
+                const bool hl = (info >> 17) & 1u, hr = (info >> 18) & 1u, hs = (info >> 19) & 1u;
+                const int z = row / g.DY, y = row - z * g.DY;
+                const size_t idx = (size_t)row * g.W + w;
+                const uint32_t blk = __ldcg(&g.blocked[idx]);
+                uint32_t m = 0, ml = 0, mr = 0;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    if (nb & (1u << k)) {
+                        const uint32_t* fr = fcur + (size_t)((z + k / 3 - 1) * g.DY + (y + k % 3 - 1)) * g.W + w;
+                        if (hs) m |= __ldcg(fr);
+                        if (hl) ml |= __ldcg(fr - 1);
+                        if (hr) mr |= __ldcg(fr + 1);
+                    }
+                }
+                const uint32_t dil = m | (m << 1) | (m >> 1) | (ml >> 31) | (mr << 31);
+                uint32_t fresh = dil & ~blk;
+                fnext[idx] = fresh;
+                if (fresh) {
+                    g.blocked[idx] = blk | fresh;
+                    any_new = true;
+                    const uint32_t pub = 1u << (9 + (w & 15));
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        // this row is neighbour k of row (z - dz, y - dy)
+                        atomicOr(&cand_out[(z - (k / 3 - 1)) * g.DY + (y - (k % 3 - 1))], pub | (1u << k));
+                    }
+                    int* d = g.dist + (size_t)row * g.DX + (size_t)w * 32;
+                    while (fresh) {
+                        const int b = __ffs(fresh) - 1;
+                        fresh &= fresh - 1;
+                        d[b] = (int)level;
+                    }
+                }
+            }
+            __syncthreads();   // the list is rebuilt by the next round / batch
+        }
+    }
+    return any_new;
+}
+
 __global__ void __launch_bounds__(BFS_THREADS, 1)
 bfs_levels_kernel(const __grid_constant__ BfsGrid g, int max_levels)
 {
@@ -258,160 +416,12 @@ bfs_levels_kernel(const __grid_constant__ BfsGrid g, int max_levels)
     __shared__ uint32_t s_info[BFS_ITEM_CAP];   // word | nbrmask << 8 | has_left << 17 | has_right << 18
     __shared__ int s_warp_sum[BFS_THREADS / 32];
     __shared__ int s_total;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int groups = (g.rows + 7) / 8;                         // groups of 8 consecutive rows
-    const int slots = (groups + (int)gridDim.x - 1) / (int)gridDim.x * 8;   // row slots of this block
-    const uint32_t wmask_all = g.W >= 16 ? 0xFFFFu : ((1u << g.W) - 1u);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(&g.ctrl[4]);
     int* news = &g.ctrl[8];   // [4] per-level flags, see grid_barrier
 
     uint32_t level = 1;
     for (; level <= (uint32_t)max_levels; ++level) {
-        const bool odd = level & 1;
-        const uint32_t* __restrict__ fcur = odd ? g.front0 : g.front1;
-        uint32_t* __restrict__ fnext = odd ? g.front1 : g.front0;
-        uint32_t* __restrict__ cand_in = odd ? g.cand0 : g.cand1;
-        uint32_t* __restrict__ cand_out = odd ? g.cand1 : g.cand0;
-        bool any_new = false;
-
-        for (int t0 = 0; t0 < slots; t0 += BFS_THREADS * BFS_ROWS_PER_THREAD) {
-            // ---- fetch this thread's candidate words (independent loads, one latency) ----
-            int rows[BFS_ROWS_PER_THREAD];
-            uint32_t words[BFS_ROWS_PER_THREAD];
-#pragma unroll
-            for (int u = 0; u < BFS_ROWS_PER_THREAD; ++u) {
-                const int t = t0 + u * BFS_THREADS + threadIdx.x;
-                const int gi = blockIdx.x + (t >> 3) * gridDim.x;
-                rows[u] = gi * 8 + (t & 7);
-                words[u] = 0;
-                if (t < slots && gi < groups && rows[u] < g.rows) {
-                    words[u] = __ldcg(&cand_in[rows[u]]);
-                }
-            }
-            // ---- items per candidate row: published words dilated by one ----
-            uint32_t dmask[BFS_ROWS_PER_THREAD];
-            int mine = 0;
-#pragma unroll
-            for (int u = 0; u < BFS_ROWS_PER_THREAD; ++u) {
-                dmask[u] = 0;
-                if (words[u] != 0) {
-                    cand_in[rows[u]] = 0;   // consumed; this array is written again two levels from now
-                    const int z = rows[u] / g.DY, y = rows[u] - z * g.DY;
-                    if (!(z == 0 || z == g.DZ - 1 || y == 0 || y == g.DY - 1)) {   // border shell rows are all wall
-                        const uint32_t wm = (words[u] >> 9) & 0xFFFFu;
-                        // word index is kept mod 16: with more than 16 words per row bit 15 neighbours bit 0
-                        uint32_t d = wm | (wm << 1) | (wm >> 1);
-                        if (g.W > 16) {
-                            d |= (wm >> 15) | (wm << 15);
-                        }
-                        dmask[u] = d & wmask_all;
-                    }
-                }
-                // with W > 16 every word congruent to a set bit becomes an item
-                int n = __popc(dmask[u]);
-                if (g.W > 16) {
-                    n = 0;
-                    for (int w = 0; w < g.W; ++w) n += (dmask[u] >> (w & 15)) & 1u;
-                }
-                mine += n;
-            }
-            // ---- block-wide exclusive scan of `mine` ----
-            int incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (lane == 31) {
-                s_warp_sum[warp] = incl;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                int v = s_warp_sum[lane];
-                int inc2 = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int x = __shfl_up_sync(0xffffffffu, inc2, o);
-                    if (lane >= o) inc2 += x;
-                }
-                s_warp_sum[lane] = inc2 - v;
-                if (lane == 31) {
-                    s_total = inc2;
-                }
-            }
-            __syncthreads();
-            const int my_off = s_warp_sum[warp] + incl - mine;
-            const int total = s_total;
-
-            // ---- rounds of at most BFS_ITEM_CAP items ----
-            for (int r0 = 0; r0 < total; r0 += BFS_ITEM_CAP) {
-                int pos = my_off;
-#pragma unroll
-                for (int u = 0; u < BFS_ROWS_PER_THREAD; ++u) {
-                    if (dmask[u] == 0) {
-                        continue;
-                    }
-                    const uint32_t wm = (words[u] >> 9) & 0xFFFFu;
-                    const uint32_t nb = words[u] & 0x1FFu;
-                    for (int w = 0; w < g.W; ++w) {
-                        if (!((dmask[u] >> (w & 15)) & 1u)) {
-                            continue;
-                        }
-                        if (pos >= r0 && pos < r0 + BFS_ITEM_CAP) {
-                            const uint32_t hl = (w > 0 && ((wm >> ((w - 1) & 15)) & 1u)) ? 1u : 0u;
-                            const uint32_t hr = (w + 1 < g.W && ((wm >> ((w + 1) & 15)) & 1u)) ? 1u : 0u;
-                            const uint32_t hs = (wm >> (w & 15)) & 1u;
-                            s_item[pos - r0] = (uint32_t)rows[u];
-                            s_info[pos - r0] = (uint32_t)w | (nb << 8) | (hl << 17) | (hr << 18) | (hs << 19);
-                        }
-                        ++pos;
-                    }
-                }
-                __syncthreads();
-                const int n_items = min(BFS_ITEM_CAP, total - r0);
-                for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
-                    const int row = (int)s_item[i];
-                    const uint32_t info = s_info[i];
-                    const int w = info & 0xFFu;
-                    const uint32_t nb = (info >> 8) & 0x1FFu;
-                    const bool hl = (info >> 17) & 1u, hr = (info >> 18) & 1u, hs = (info >> 19) & 1u;
-                    const int z = row / g.DY, y = row - z * g.DY;
-                    const size_t idx = (size_t)row * g.W + w;
-                    const uint32_t blk = __ldcg(&g.blocked[idx]);
-                    uint32_t m = 0, ml = 0, mr = 0;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        if (nb & (1u << k)) {
-                            const uint32_t* fr = fcur + (size_t)((z + k / 3 - 1) * g.DY + (y + k % 3 - 1)) * g.W + w;
-                            if (hs) m |= __ldcg(fr);
-                            if (hl) ml |= __ldcg(fr - 1);
-                            if (hr) mr |= __ldcg(fr + 1);
-                        }
-                    }
-                    const uint32_t dil = m | (m << 1) | (m >> 1) | (ml >> 31) | (mr << 31);
-                    uint32_t fresh = dil & ~blk;
-                    fnext[idx] = fresh;
-                    if (fresh) {
-                        g.blocked[idx] = blk | fresh;
-                        any_new = true;
-                        const uint32_t pub = 1u << (9 + (w & 15));
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) {
-                            // this row is neighbour k of row (z - dz, y - dy)
-                            atomicOr(&cand_out[(z - (k / 3 - 1)) * g.DY + (y - (k % 3 - 1))], pub | (1u << k));
-                        }
-                        int* d = g.dist + (size_t)row * g.DX + (size_t)w * 32;
-                        while (fresh) {
-                            const int b = __ffs(fresh) - 1;
-                            fresh &= fresh - 1;
-                            d[b] = (int)level;
-                        }
-                    }
-                }
-                __syncthreads();   // the list is rebuilt by the next round / batch
-            }
-        }
+        const bool any_new = bfs_level_body(g, level, s_item, s_info, s_warp_sum, &s_total);
         const bool block_new = __syncthreads_or(any_new ? 1 : 0) != 0;
         if (threadIdx.x == 0) {
             if (block_new) {
@@ -430,6 +440,47 @@ bfs_levels_kernel(const __grid_constant__ BfsGrid g, int max_levels)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         g.ctrl[0] = (int)level;
+    }
+}
+
+// The same wavefront as ONE LAUNCH PER LEVEL, for the planner's banks when they are run behind the caller's back
+// (smplgpu_bfs_bank_run_slots_async) while other contexts' expansion rounds share the GPU.  A cooperative launch
+// starts only when ALL its blocks fit at once; with five other contexts feeding small kernels without pause that
+// moment can be seconds away (measured: a 2 s stall in one of six runs).  Launches of one level
+// need no co-residency, interleave with anything, and cost ~2 us each against tens of milliseconds per bank run.
+// ctrl[12] = sticky "finished" flag (set by the first level that finds the previous one empty), mirrored into
+// *done_host (page-locked) so that the host can poll without a synchronisation; ctrl[0] = levels run.
+__global__ void __launch_bounds__(BFS_THREADS, 1)
+bfs_level_step_kernel(const __grid_constant__ BfsGrid g, uint32_t level, volatile int* done_host)
+{
+    __shared__ uint32_t s_item[BFS_ITEM_CAP];
+    __shared__ uint32_t s_info[BFS_ITEM_CAP];
+    __shared__ int s_warp_sum[BFS_THREADS / 32];
+    __shared__ int s_total;
+    int* news = &g.ctrl[8];
+    if (__ldcg(&g.ctrl[12]) != 0) {
+        return;   // finished at an earlier level
+    }
+    if (level > 1 && __ldcg(&news[(level - 1) & 3]) == 0) {
+        // the previous level discovered nothing: done (every block of this launch sees the same flag)
+        if (threadIdx.x == 0 && blockIdx.x == 0) {
+            g.ctrl[0] = (int)level - 1;
+            g.ctrl[12] = 1;
+            if (done_host != nullptr) {
+                *done_host = 1;
+            }
+        }
+        return;
+    }
+    const bool any_new = bfs_level_body(g, level, s_item, s_info, s_warp_sum, &s_total);
+    const bool block_new = __syncthreads_or(any_new ? 1 : 0) != 0;
+    if (threadIdx.x == 0) {
+        if (block_new) {
+            atomicExch(&news[level & 3], 1);
+        }
+        if (blockIdx.x == 0) {
+            atomicExch(&news[(level + 2) & 3], 0);   // stream order: level + 2 is launched after this launch ends
+        }
     }
 }
 

@@ -112,6 +112,11 @@ struct smplgpu_ctx
     void* h_bank_stage = nullptr; size_t h_bank_stage_cap = 0;
     int* d_bank_seed_count = nullptr;
     int bank_run_state = 0;               // 0 none, 1 staged on the host (waiting for the device's turn), 2 queued
+    // asynchronous bank runs go level by level (bfs_level_step_kernel): launched in chunks, continued when a chunk
+    // ends without the device having raised *bank_done (page-locked, mapped)
+    volatile int* bank_done = nullptr;
+    int bank_next_level = 0;              // first level of the next chunk; 0 = the run in flight is a cooperative one
+    long long bank_level_cap = 0;
     std::vector<int32_t> staged_slots, staged_seeds;
     unsigned long long* d_stats = nullptr;
     unsigned long long h_stats[4] = { 0, 0, 0, 0 };
@@ -283,7 +288,13 @@ smplgpu_ctx* smplgpu_create(int device)
     if ((e = cudaMalloc(&ctx->d_seed_count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc(seed)", e);
     if ((e = cudaMalloc(&ctx->d_unc_count, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc(unc)", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&ctx->bfs_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    {
+        // the stream of the bank runs queued behind the caller's back: highest priority, so that the block scheduler
+        // prefers a waiting wavefront kernel's blocks to the next expansion round's when an SM drains
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if ((e = cudaStreamCreateWithPriority(&ctx->bfs_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    }
     if ((e = cudaEventCreateWithFlags(&ctx->ev_bfs, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->d_bank_seed_count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc(seed)", e);
     for (int i = 0; i < 2; ++i) {
@@ -393,6 +404,7 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
     if (ctx->bfs_stream) cudaStreamDestroy(ctx->bfs_stream);
     if (ctx->ev_bfs) cudaEventDestroy(ctx->ev_bfs);
     cudaFree(ctx->d_bank_stage); cudaFree(ctx->d_bank_seed_count);
+    if (ctx->bank_done) cudaFreeHost((void*)ctx->bank_done);
     cudaFree(ctx->d_x1_deltas); cudaFree(ctx->d_x1_done);
     cudaFree(ctx->d_coord); cudaFree(ctx->d_prim8);
     free_lattice(ctx);
@@ -2082,6 +2094,37 @@ static int wall_threshold(const smplgpu_ctx* ctx, double inflation_radius)
     return kmax;
 }
 
+// Asynchronous bank runs are one cooperative launch per run, taking turns per device (default), or -- with
+// SMPLGPU_BANK_STEPWISE=1 -- one launch per level (bfs_level_step_kernel): no co-residency needed, the contexts' runs
+// overlap.  Measured on one B200, 6 contexts x 342 queries: cooperative 1750-2050 plan queries/s
+// and 3800-4900 UBR1 queries/s, with ONE run in about ten stalling for 2 s (a cooperative launch starts only when all
+// its blocks fit at once, and five other contexts keep feeding small kernels); level by level 1340-2010 and 3000-3470
+// with a worst stall of 0.9 s.  The cooperative form stays the default for its average; its stream has high priority.
+static bool bank_stepwise()
+{
+    static const bool on = [] {
+        const char* e = getenv("SMPLGPU_BANK_STEPWISE");
+        return e != nullptr && atoi(e) != 0;
+    }();
+    return on;
+}
+
+constexpr int BANK_LEVEL_CHUNK = 128;   // level launches queued at a time (a 150^3 tabletop bank needs ~140 levels)
+
+static int launch_bank_level_chunk(smplgpu_ctx* ctx, cudaStream_t stream)
+{
+    BfsGrid& g = ctx->bank;
+    const int groups = (g.rows + 7) / 8;
+    const int blocks = std::max(1, std::min(groups, 2 * ctx->sm_count));
+    for (int k = 0; k < BANK_LEVEL_CHUNK; ++k) {
+        bfs_level_step_kernel<<<blocks, BFS_THREADS, 0, stream>>>(g, (uint32_t)(ctx->bank_next_level + k), ctx->bank_done);
+    }
+    ctx->launches += BANK_LEVEL_CHUNK;
+    ctx->bank_next_level += BANK_LEVEL_CHUNK;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // reset + seed + all levels on one grid; seeds already on the device (padded-grid-free coordinates)
 static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_seeds, int n_seeds, int* levels_out,
                     const uint8_t* d_slot_mask = nullptr, int slot_dz = 1, cudaStream_t stream = nullptr,
@@ -2141,6 +2184,19 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
         void* args[] = { (void*)&g, (void*)&t, (void*)&max_steps };
         CU(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(threads), args, 0, stream));
         ++ctx->launches;
+    } else if (&g == &ctx->bank && stream == ctx->bfs_stream && bank_stepwise()) {
+        // behind the caller's back: one launch per level (bfs_level_step_kernel), first chunk here, the rest from
+        // smplgpu_bfs_bank_run_done / _wait
+        if (!ctx->bank_done) {
+            int* p = nullptr;
+            CU(cudaHostAlloc((void**)&p, 64, cudaHostAllocMapped));
+            ctx->bank_done = p;
+        }
+        *ctx->bank_done = 0;
+        ctx->bank_next_level = 1;
+        ctx->bank_level_cap = std::min<long long>(cap, 1LL << 22);
+        const int r = launch_bank_level_chunk(ctx, stream);
+        if (r) return r;
     } else {
         // persistent cooperative kernel, one block per SM (the grid barrier costs one arrival per block)
         int per_sm = 0;
@@ -2426,6 +2482,7 @@ static int launch_bank_run(smplgpu_ctx* ctx, const int32_t* slots, const int32_t
                            int* d_seed_count, int* n_seeds_out)
 {
     const int nx = ctx->grid.nx, ny = ctx->grid.ny, nz = ctx->grid.nz;
+    ctx->bank_next_level = 0;   // set again by run_grid when this run goes level by level
     const size_t seed_cap = ((size_t)n * 3 * sizeof(int) + 15) / 16 * 16;
     const size_t need = seed_cap + (size_t)ctx->bank_slots + 64;
     int r = grow(ctx, &ctx->d_bank_stage, &ctx->bank_stage_cap, need);
@@ -2491,8 +2548,24 @@ static int launch_staged_bank_run(smplgpu_ctx* ctx)
 
 static bool take_bank_turn(smplgpu_ctx* ctx)
 {
+    if (bank_stepwise()) {
+        return true;   // level-by-level runs need no co-residency: the contexts' runs simply overlap
+    }
     int expected = 0;
     return g_bank_turn[ctx->device & 63].compare_exchange_strong(expected, 1);
+}
+
+// A level-by-level run whose last chunk has ended without the device raising the flag gets its next chunk.
+// Returns 1 when the run is complete, 0 when more levels were queued, negative on error.
+static int continue_bank_levels(smplgpu_ctx* ctx)
+{
+    if (ctx->bank_next_level == 0 || *ctx->bank_done != 0 || ctx->bank_next_level > ctx->bank_level_cap) {
+        return 1;
+    }
+    const int r = launch_bank_level_chunk(ctx, ctx->bfs_stream);
+    if (r) return r;
+    CU(cudaEventRecord(ctx->ev_bfs, ctx->bfs_stream));
+    return 0;
 }
 
 static void release_bank_turn(smplgpu_ctx* ctx)
@@ -2515,10 +2588,25 @@ static int finish_bank_run(smplgpu_ctx* ctx)
         }
     }
     if (ctx->bank_run_state == 2) {
-        const cudaError_t e = cudaEventSynchronize(ctx->ev_bfs);
+        for (;;) {
+            const cudaError_t e = cudaEventSynchronize(ctx->ev_bfs);
+            if (e != cudaSuccess) {
+                ctx->bank_run_state = 0;
+                release_bank_turn(ctx);
+                return fail(ctx, SMPLGPU_ERR_CUDA, "bank run: %s", cudaGetErrorString(e));
+            }
+            const int c = continue_bank_levels(ctx);
+            if (c < 0) {
+                ctx->bank_run_state = 0;
+                release_bank_turn(ctx);
+                return c;
+            }
+            if (c == 1) {
+                break;
+            }
+        }
         ctx->bank_run_state = 0;
         release_bank_turn(ctx);
-        if (e != cudaSuccess) return fail(ctx, SMPLGPU_ERR_CUDA, "bank run: %s", cudaGetErrorString(e));
     }
     return 0;
 }
@@ -2576,6 +2664,15 @@ int smplgpu_bfs_bank_run_done(smplgpu_ctx* ctx)
     }
     const cudaError_t e = cudaEventQuery(ctx->ev_bfs);
     if (e == cudaErrorNotReady) return 0;
+    if (e == cudaSuccess) {
+        const int c = continue_bank_levels(ctx);
+        if (c == 0) return 0;        // more levels queued
+        if (c < 0) {
+            ctx->bank_run_state = 0;
+            release_bank_turn(ctx);
+            return c;
+        }
+    }
     ctx->bank_run_state = 0;
     release_bank_turn(ctx);
     if (e != cudaSuccess) return fail(ctx, SMPLGPU_ERR_CUDA, "bank run: %s", cudaGetErrorString(e));
