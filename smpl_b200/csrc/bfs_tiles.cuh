@@ -42,7 +42,13 @@ constexpr int TILE_THREADS = TILE_E * TILE_E; // one thread per extended row (10
 struct BfsTiles
 {
     int ntx, nty, ntz, ntiles;   // tiles per axis (x in words)
-    uint32_t* blocked1;          // second copy of the blocked bitmap
+    // Tile-major bitmaps, private to the tile kernels: tile (tx, ty, tz) owns 256 consecutive words, word
+    // (z & 15) * 16 + (y & 15) = bitmap word tx of row (y, z).  A warp that fetches the 32 y-rows of an extended tile's
+    // z-row reads 8 + 16 + 8 consecutive words of three tiles -- four 32-byte sectors per request where the row-major
+    // bitmaps (stride W words between y-rows) cost 32, and a tile plus halo is 768 sectors instead of 6144.  Rows
+    // beyond DY / DZ inside the last tiles are padding: blocked = all ones, frontier = 0.
+    uint32_t* tb[2];             // the two copies of the blocked bitmap
+    uint32_t* tf[2];             // frontier at the start of super-step n: tf[n & 1]
     uint32_t* ver;               // [ntiles] (super-step of the last flip + 1) << 1 | copy holding the tile's interior
     uint32_t* flag;              // [3][ntiles] tile is queued for super-step n (index n % 3)
     int* queue;                  // [3][ntiles] tiles to run in super-step n (index n % 3)
@@ -54,6 +60,14 @@ __device__ __forceinline__ uint32_t tile_copy(const BfsTiles& t, int tile, int n
 {
     const uint32_t v = __ldcg(&t.ver[tile]);
     return ((v >> 1) == (uint32_t)(n + 1)) ? ((v & 1u) ^ 1u) : (v & 1u);
+}
+
+constexpr int TILE_NONE = -0x40000000;         // "no such tile" (tile index - 1 can be -1 for a real row)
+constexpr int TILE_WORDS = TILE_Y * TILE_Y;   // words of one tile in the tile-major bitmaps
+
+__device__ __forceinline__ size_t tile_word(int tile, int zi, int yi)
+{
+    return (size_t)tile * TILE_WORDS + zi * TILE_Y + yi;
 }
 
 // queue `tile` for the super-step whose queue index is qi (once)
@@ -76,9 +90,11 @@ __global__ void bfs_tiles_seed_kernel(BfsGrid g, BfsTiles t, const int* __restri
         return;
     }
     const int px = x + 1, py = y + 1, pz = z + 1;
-    const size_t word = (size_t)(pz * g.DY + py) * g.W + (px >> 5);
-    atomicOr(&t.blocked1[word], 1u << (px & 31));
     const int tx = px >> 5, ty = py / TILE_Y, tz = pz / TILE_Y;
+    const size_t word = tile_word((tz * t.nty + ty) * t.ntx + tx, pz % TILE_Y, py % TILE_Y);
+    atomicOr(&t.tb[0][word], 1u << (px & 31));
+    atomicOr(&t.tb[1][word], 1u << (px & 31));
+    atomicOr(&t.tf[0][word], 1u << (px & 31));
     for (int dz = -1; dz <= 1; ++dz) {
         for (int dy = -1; dy <= 1; ++dy) {
             for (int dx = -1; dx <= 1; ++dx) {
@@ -91,20 +107,23 @@ __global__ void bfs_tiles_seed_kernel(BfsGrid g, BfsTiles t, const int* __restri
     }
 }
 
-// second blocked copy = walls (run after bfs_reset_kernel, same slot mask)
+// both blocked copies = walls, both frontiers empty (run after bfs_reset_kernel, same slot mask).  Padding rows and the
+// slots of a stacked bank that are not re-run hold "everything blocked": nothing to discover there.
 __global__ void bfs_tiles_reset_kernel(BfsGrid g, BfsTiles t, const uint8_t* __restrict__ slot_mask, int slot_dz)
 {
-    const int total = g.rows * g.W;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const bool on = slot_mask == nullptr || slot_mask[(idx / g.W / g.DY) / slot_dz] != 0;
-        if (on) {
-            t.blocked1[idx] = g.wall[idx];
-        } else {
-            // a slot that is not re-run keeps its distances; clear its frontiers so that a tile shared with a
-            // re-run slot finds nothing to expand there
-            g.front0[idx] = 0;
-            g.front1[idx] = 0;
+    const size_t total = (size_t)t.ntiles * TILE_WORDS;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int tile = (int)(idx / TILE_WORDS), in = (int)(idx % TILE_WORDS);
+        const int tx = tile % t.ntx, ty = (tile / t.ntx) % t.nty, tz = tile / (t.ntx * t.nty);
+        const int gy = ty * TILE_Y + in % TILE_Y, gz = tz * TILE_Y + in / TILE_Y;
+        uint32_t w = 0xFFFFFFFFu;
+        if (gy < g.DY && gz < g.DZ && (slot_mask == nullptr || slot_mask[gz / slot_dz] != 0)) {
+            w = g.wall[(size_t)(gz * g.DY + gy) * g.W + tx];
         }
+        t.tb[0][idx] = w;
+        t.tb[1][idx] = w;
+        t.tf[0][idx] = 0;
+        t.tf[1][idx] = 0;
     }
 }
 
@@ -161,7 +180,6 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
         row_out[r] = max(jy, jz[r]);
         interior_row[r] = interior_y && rz >= TILE_K && rz < TILE_K + TILE_Y;
     }
-    const int xwords = (g.DX + 31) / 32;                // words that hold cells
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(&g.ctrl[4]);
     int max_level = 0;
     if (tid < 2 * (TILE_E + 2)) {
@@ -172,8 +190,8 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
     int n = 0;
     for (; n < max_supersteps; ++n) {
         const int p = n & 1;
-        const uint32_t* __restrict__ fcur = p ? g.front1 : g.front0;
-        uint32_t* __restrict__ fnext = p ? g.front0 : g.front1;
+        const uint32_t* __restrict__ fcur = t.tf[p];
+        uint32_t* __restrict__ fnext = t.tf[p ^ 1];
         const int qi = n % 3, qi_next = (n + 1) % 3, qi_free = (n + 2) % 3;
         const int level0 = n * TILE_K;
         // the active tiles of this super-step, dealt to the blocks by queue position
@@ -204,8 +222,10 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
 #endif
                 const int tx = tile % t.ntx, ty = (tile / t.ntx) % t.nty, tz = tile / (t.ntx * t.nty);
                 const int gy = ty * TILE_Y - TILE_K + ry;
-                bool row_in[TILE_RPT];
-                size_t grow[TILE_RPT];
+                // the tile that owns this thread's rows (y part) and the rows' place in its 16 x 16 block
+                const int oty = ty + (ry < TILE_K ? -1 : (ry >= TILE_K + TILE_Y ? 1 : 0));
+                const int yi = (ry + TILE_K) & (TILE_Y - 1);
+                int own[TILE_RPT];       // owner tile of the row in x-column tx - 1 (+1, +2 for the other two), or TILE_NONE
                 int gz[TILE_RPT];
 
                 // ---- the frontier of this thread's rows: the interior word and 8 cells of each neighbour ----
@@ -214,14 +234,16 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                 for (int r = 0; r < TILE_RPT; ++r) {
                     const int rz = warp + (TILE_E / TILE_RPT) * r;
                     gz[r] = tz * TILE_Y - TILE_K + rz;
-                    row_in[r] = gy >= 0 && gy < g.DY && gz[r] >= 0 && gz[r] < g.DZ;
-                    grow[r] = (size_t)(row_in[r] ? gz[r] * g.DY + gy : 0);
+                    const int otz = tz + (rz < TILE_K ? -1 : (rz >= TILE_K + TILE_Y ? 1 : 0));
+                    const bool in = oty >= 0 && oty < t.nty && otz >= 0 && otz < t.ntz;
+                    own[r] = in ? (otz * t.nty + oty) * t.ntx + tx - 1 : TILE_NONE;
+                    const int wi = ((rz + TILE_K) & (TILE_Y - 1)) * TILE_Y + yi;
 #pragma unroll
                     for (int w = 0; w < 3; ++w) {
                         const int gw = tx - 1 + w;
                         fw[r][w] = 0;
-                        if (row_in[r] && gw >= 0 && gw < xwords) {
-                            fw[r][w] = __ldcg(&fcur[grow[r] * g.W + gw]);
+                        if (in && gw >= 0 && gw < t.ntx) {
+                            fw[r][w] = __ldcg(&fcur[(size_t)(own[r] + w) * TILE_WORDS + wi]);
                         }
                     }
                 }
@@ -255,14 +277,15 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                     uint32_t bw[TILE_RPT][3];
 #pragma unroll
                     for (int r = 0; r < TILE_RPT; ++r) {
+                        const int rz = warp + (TILE_E / TILE_RPT) * r;
+                        const int wi = ((rz + TILE_K) & (TILE_Y - 1)) * TILE_Y + yi;
 #pragma unroll
                         for (int w = 0; w < 3; ++w) {
                             const int gw = tx - 1 + w;
                             uint32_t bb = 0xFFFFFFFFu;
-                            if (row_in[r] && gw >= 0 && gw < xwords) {
-                                const int owner = ((gz[r] / TILE_Y) * t.nty + gy / TILE_Y) * t.ntx + gw;
-                                const uint32_t* src = tile_copy(t, owner, n) ? t.blocked1 : g.blocked;
-                                bb = __ldcg(&src[grow[r] * g.W + gw]);
+                            if (own[r] != TILE_NONE && gw >= 0 && gw < t.ntx) {
+                                const int owner = own[r] + w;
+                                bb = __ldcg(&t.tb[tile_copy(t, owner, n)][(size_t)owner * TILE_WORDS + wi]);
                             }
                             bw[r][w] = bb;
                         }
@@ -360,11 +383,12 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                 // ---- write back the interior: blocked into the other copy, frontier for the next super-step ----
                 if (__syncthreads_or(changed ? 1 : 0)) {
                     const uint32_t v = tile_copy(t, tile, n);
-                    uint32_t* dst = v ? g.blocked : t.blocked1;
+                    uint32_t* dst = t.tb[v ^ 1u];
 #pragma unroll
                     for (int r = 0; r < TILE_RPT; ++r) {
-                        if (interior_row[r] && row_in[r] && tx < xwords) {
-                            dst[grow[r] * g.W + tx] = (uint32_t)(blk[r] >> 8);
+                        if (interior_row[r]) {
+                            const int rz = warp + (TILE_E / TILE_RPT) * r;
+                            dst[tile_word(tile, rz - TILE_K, ry - TILE_K)] = (uint32_t)(blk[r] >> 8);
                         }
                     }
                     if (tid == 0) {
@@ -374,8 +398,9 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                 unsigned act = 0;
 #pragma unroll
                 for (int r = 0; r < TILE_RPT; ++r) {
-                    if (interior_row[r] && row_in[r] && tx < xwords) {
-                        fnext[grow[r] * g.W + tx] = last[r];
+                    if (interior_row[r]) {
+                        const int rz = warp + (TILE_E / TILE_RPT) * r;
+                        fnext[tile_word(tile, rz - TILE_K, ry - TILE_K)] = last[r];
                     }
                     // tiles whose interior is within TILE_K cells of a remaining frontier cell run next super-step
                     if (interior_row[r] && last[r] != 0) {
@@ -423,6 +448,294 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
 #endif
     }
     // levels run = deepest level that discovered a cell, + 1 (as bfs_levels_kernel reports it)
+    for (int o = 16; o > 0; o >>= 1) {
+        max_level = max(max_level, __shfl_xor_sync(0xffffffffu, max_level, o));
+    }
+    if (lane == 0 && max_level > 0) {
+        atomicMax(&g.ctrl[0], max_level + 1);
+    }
+}
+
+// ONE WARP PER TILE, the extended tile in registers: lane = y-row, register index = z-row (the z loop is unrolled), a
+// level is  m = F[z-1] | F[z] | F[z+1];  m |= shfl_up(m) | shfl_down(m);  fresh = (m | m << 1 | m >> 1) & ~B[z]  -- no
+// shared memory and NO block barrier.  ncu on bfs_tiles_kernel<4> (profiles/r02c_bfs_metrics.csv): 18.6 of the stall
+// cycles per issued instruction are block barriers -- eight warps meeting once per level although a level is a few
+// dozen instructions of work per z-row.  Here the frontier is updated in place (ascending z, the old value of the
+// previous z-row carried in a register), an idle z-row costs one vote, twelve tiles are in flight per SM instead of
+// four, and the tiles of a super-step are dealt warp by warp.  Protocol between the tiles (queues, flags, the two
+// blocked copies and their version stamps): exactly bfs_tiles_kernel's, see the head of this file.
+constexpr int WTILE_WARPS = 4;        // warps per block
+constexpr int WTILE_BLOCKS_PER_SM = 2;
+constexpr int WTILE_GROUP = 8;      // z-rows handled as one straight-line group
+
+__global__ void __launch_bounds__(WTILE_WARPS * 32, WTILE_BLOCKS_PER_SM)
+bfs_warp_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsTiles t, int max_supersteps)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * WTILE_WARPS + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * WTILE_WARPS;
+    const int ry = lane;
+    const int jy = ry < TILE_K ? TILE_K - ry : (ry >= TILE_K + TILE_Y ? ry - (TILE_K + TILE_Y - 1) : 0);
+    const bool interior_y = ry >= TILE_K && ry < TILE_K + TILE_Y;
+    const int oy = ry < TILE_K ? 0 : (ry < TILE_K + TILE_Y ? 1 : 2);   // which of the three tiles in y owns this row
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(&g.ctrl[4]);
+    int max_level = 0;
+
+    int n = 0;
+    for (; n < max_supersteps; ++n) {
+        const int p = n & 1;
+        const uint32_t* __restrict__ fcur = t.tf[p];
+        uint32_t* __restrict__ fnext = t.tf[p ^ 1];
+        const int qi = n % 3, qi_next = (n + 1) % 3, qi_free = (n + 2) % 3;
+        const int level0 = n * TILE_K;
+        const int q_len = __ldcg(&t.qn[qi]);
+        if (q_len == 0) {
+            break;
+        }
+        if (gwarp == 0 && lane == 0) {
+            t.qn[qi_free] = 0;
+            t.qn[3 + qi_free] = 0;
+        }
+        for (int a = gwarp; a < q_len;) {
+            const int tile = __ldcg(&t.queue[(size_t)qi * t.ntiles + a]);
+            {
+                int nxt = 0;
+                if (lane == 0) {
+                    t.flag[(size_t)qi * t.ntiles + tile] = 0;               // consumed
+                    nxt = nwarps + atomicAdd(&t.qn[3 + qi], 1);             // next queue position of this warp
+                }
+                a = __shfl_sync(FULL, nxt, 0);
+            }
+#ifdef SMPLGPU_BFS_STATS
+            const long long c0 = clock64();
+            if (lane == 0) atomicAdd(&g.ctrl[3], 1);
+#endif
+            const int tx = tile % t.ntx, ty = (tile / t.ntx) % t.nty, tz = tile / (t.ntx * t.nty);
+            const int gy = ty * TILE_Y - TILE_K + ry;
+            const int gz0 = tz * TILE_Y - TILE_K;
+            // the tile that owns this lane's rows in y, and the rows' place in its 16 x 16 block
+            const int oty = ty + oy - 1;
+            const bool y_in = oty >= 0 && oty < t.nty;
+            const int yi = (ry + TILE_K) & (TILE_Y - 1);
+
+            // ---- frontier rows ----
+            unsigned long long F[TILE_E];
+            bool anyf = false;
+#pragma unroll
+            for (int z = 0; z < TILE_E; ++z) {
+                const int otz = tz + (z < TILE_K ? -1 : (z < TILE_K + TILE_Y ? 0 : 1));
+                const bool row_in = y_in && otz >= 0 && otz < t.ntz;
+                const size_t base = (size_t)(row_in ? (otz * t.nty + oty) * t.ntx + tx : 0) * TILE_WORDS +
+                                    ((z + TILE_K) & (TILE_Y - 1)) * TILE_Y + yi;
+                uint32_t w0 = 0, w1 = 0, w2 = 0;
+                if (row_in) {
+                    if (tx >= 1) w0 = __ldcg(&fcur[base - TILE_WORDS]);
+                    w1 = __ldcg(&fcur[base]);
+                    if (tx + 1 < t.ntx) w2 = __ldcg(&fcur[base + TILE_WORDS]);
+                }
+                F[z] = pack_row(w0, w1, w2);
+                anyf |= F[z] != 0;
+            }
+            if (!__any_sync(FULL, anyf)) {
+                continue;   // no frontier cell in reach (flags are raised conservatively)
+            }
+
+            // ---- blocked rows, each from the copy its owner tile committed last (27 owners: one lane each) ----
+            unsigned long long B[TILE_E];
+            {
+                unsigned copy_bit = 0;
+                if (lane < 27) {
+                    const int ax = tx + lane % 3 - 1, ay = ty + (lane / 3) % 3 - 1, az = tz + lane / 9 - 1;
+                    if (ax >= 0 && ay >= 0 && az >= 0 && ax < t.ntx && ay < t.nty && az < t.ntz) {
+                        copy_bit = tile_copy(t, (az * t.nty + ay) * t.ntx + ax, n);
+                    }
+                }
+                const unsigned copies = __ballot_sync(FULL, copy_bit != 0);   // bit (oz * 3 + oy) * 3 + ox
+#pragma unroll
+                for (int z = 0; z < TILE_E; ++z) {
+                    const int oz = z < TILE_K ? 0 : (z < TILE_K + TILE_Y ? 1 : 2);
+                    const int otz = tz + oz - 1;
+                    const bool row_in = y_in && otz >= 0 && otz < t.ntz;
+                    const size_t base = (size_t)(row_in ? (otz * t.nty + oty) * t.ntx + tx : 0) * TILE_WORDS +
+                                        ((z + TILE_K) & (TILE_Y - 1)) * TILE_Y + yi;
+                    const unsigned sel = copies >> ((oz * 3 + oy) * 3);
+                    uint32_t w0 = 0xFFFFFFFFu, w1 = 0xFFFFFFFFu, w2 = 0xFFFFFFFFu;
+                    if (row_in) {
+                        if (tx >= 1) w0 = __ldcg(&t.tb[sel & 1u][base - TILE_WORDS]);
+                        w1 = __ldcg(&t.tb[(sel >> 1) & 1u][base]);
+                        if (tx + 1 < t.ntx) w2 = __ldcg(&t.tb[(sel >> 2) & 1u][base + TILE_WORDS]);
+                    }
+                    B[z] = pack_row(w0, w1, w2);
+                }
+            }
+
+#ifdef SMPLGPU_BFS_STATS
+            const long long c1 = clock64();
+            if (lane == 0) atomicAdd(&g.ctrl[6], 1);
+#endif
+            // ---- TILE_K levels in registers ----
+            // z-rows in groups of WTILE_GROUP: one vote decides whether a group has anything in reach, and inside an
+            // active group everything is straight-line code -- the eight rows' ORs, shuffles and shifts are independent
+            // chains a single warp can keep in flight (with a branch per z-row a level cost 32 dependent vote -> shuffle
+            // -> logic chains in sequence: 5.8 ms at 400^3 against bfs_tiles_kernel's 2.76 ms)
+            bool changed = false;
+#pragma unroll 1
+            for (int s = 1; s <= TILE_K; ++s) {
+                bool any_fresh = false;
+                unsigned long long prev = 0;   // the row below the group, as it was before this level
+#pragma unroll
+                for (int z0 = 0; z0 < TILE_E; z0 += WTILE_GROUP) {
+                    unsigned long long reach = prev;
+#pragma unroll
+                    for (int k = 0; k < WTILE_GROUP; ++k) {
+                        reach |= F[z0 + k];
+                    }
+                    if (z0 + WTILE_GROUP < TILE_E) {
+                        reach |= F[z0 + WTILE_GROUP];
+                    }
+                    if (!__any_sync(FULL, reach != 0)) {   // warp-uniform
+                        prev = 0;   // = F[z0 + WTILE_GROUP - 1]; the group's rows are zero and stay zero
+                        continue;
+                    }
+                    unsigned long long fresh[WTILE_GROUP];
+                    uint32_t fresh_any_in = 0;
+#pragma unroll
+                    for (int k = 0; k < WTILE_GROUP; ++k) {
+                        const int z = z0 + k;
+                        const int jz = z < TILE_K ? TILE_K - z : (z >= TILE_K + TILE_Y ? z - (TILE_K + TILE_Y - 1) : 0);
+                        unsigned long long m = (k == 0 ? prev : F[z - 1]) | F[z];
+                        if (z + 1 < TILE_E) {
+                            m |= F[z + 1];
+                        }
+                        // lanes 0 and 31 get their own value back from the shuffle: no row beyond the extended tile
+                        m |= __shfl_up_sync(FULL, m, 1) | __shfl_down_sync(FULL, m, 1);
+                        unsigned long long f = (m | (m << 1) | (m >> 1)) & ~B[z] & ROW_MASK;
+                        // a halo row j rows out can reach the interior by level TILE_K only through levels <= TILE_K - j
+                        if (max(jy, jz) > TILE_K - s) {
+                            f = 0;
+                        }
+                        fresh[k] = f;
+                        if (z >= TILE_K && z < TILE_K + TILE_Y && interior_y) {
+                            fresh_any_in |= (uint32_t)(f >> 8);
+                        }
+                    }
+                    prev = F[z0 + WTILE_GROUP - 1];
+                    unsigned long long got = 0;
+#pragma unroll
+                    for (int k = 0; k < WTILE_GROUP; ++k) {
+                        B[z0 + k] |= fresh[k];
+                        F[z0 + k] = fresh[k];
+                        got |= fresh[k];
+                    }
+                    any_fresh |= got != 0;
+                    if (z0 + WTILE_GROUP > TILE_K && z0 < TILE_K + TILE_Y) {
+                        // distances of the interior words: sparse rows store their cells themselves, dense rows go out
+                        // warp-wide (lanes = bits, one 128-byte store per row)
+                        if (fresh_any_in) {
+                            changed = true;
+                            max_level = max(max_level, level0 + s);
+                        }
+                        if (__any_sync(FULL, fresh_any_in != 0)) {
+#pragma unroll
+                            for (int k = 0; k < WTILE_GROUP; ++k) {
+                                const int z = z0 + k;
+                                if (z >= TILE_K && z < TILE_K + TILE_Y) {
+                                    const int gz = gz0 + z;
+                                    const uint32_t fresh_in = interior_y ? (uint32_t)(fresh[k] >> 8) : 0u;
+                                    const bool dense = __popc(fresh_in) > 4;
+                                    if (fresh_in != 0 && !dense) {
+                                        int* d = g.dist + ((size_t)gz * g.DY + gy) * g.DX + (size_t)tx * 32;
+                                        uint32_t f = fresh_in;
+                                        while (f) {
+                                            d[__ffs(f) - 1] = level0 + s;
+                                            f &= f - 1;
+                                        }
+                                    }
+                                    uint32_t todo = __ballot_sync(FULL, dense);
+                                    while (todo) {
+                                        const int rr = __ffs(todo) - 1;
+                                        todo &= todo - 1;
+                                        const uint32_t wk = __shfl_sync(FULL, fresh_in, rr);
+                                        const int y2 = ty * TILE_Y - TILE_K + rr;
+                                        if ((wk >> lane) & 1u) {
+                                            g.dist[((size_t)gz * g.DY + y2) * g.DX + (size_t)tx * 32 + lane] = level0 + s;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+#ifdef SMPLGPU_BFS_STATS
+                if (lane == 0) atomicAdd(&g.ctrl[7], 1);
+#endif
+                if (!__any_sync(FULL, any_fresh)) {
+                    break;   // nothing found at level s: every F[z] is zero, the frontier is empty from here on
+                }
+            }
+
+#ifdef SMPLGPU_BFS_STATS
+            const long long c2 = clock64();
+#endif
+            // ---- write back the interior: blocked into the other copy, frontier for the next super-step ----
+            const bool tile_changed = __any_sync(FULL, changed);
+            uint32_t* dst = nullptr;
+            if (tile_changed) {
+                const uint32_t v = tile_copy(t, tile, n);
+                dst = t.tb[v ^ 1u];
+                if (lane == 0) {
+                    t.ver[tile] = ((uint32_t)(n + 1) << 1) | (v ^ 1u);
+                }
+            }
+            unsigned act = 0;
+            if (interior_y) {
+#pragma unroll
+                for (int z = TILE_K; z < TILE_K + TILE_Y; ++z) {
+                    {
+                        const size_t idx = tile_word(tile, z - TILE_K, ry - TILE_K);
+                        if (tile_changed) {
+                            dst[idx] = (uint32_t)(B[z] >> 8);
+                        }
+                        const uint32_t last = (uint32_t)(F[z] >> 8);
+                        fnext[idx] = last;
+                        if (last != 0) {
+                            // tiles whose interior is within TILE_K cells of a remaining frontier cell run next
+                            const int iy = ry - TILE_K, iz = z - TILE_K;
+                            const unsigned xs = 2u | ((last & 0x000000FFu) ? 1u : 0u) | ((last & 0xFF000000u) ? 4u : 0u);
+                            const unsigned ys = 2u | (iy < TILE_K ? 1u : 0u) | (iy >= TILE_Y - TILE_K ? 4u : 0u);
+                            const unsigned zs = 2u | (iz < TILE_K ? 1u : 0u) | (iz >= TILE_Y - TILE_K ? 4u : 0u);
+                            // bit (dz * 3 + dy) * 3 + dx: the outer product of the three 3-bit sets
+                            const unsigned xy = (ys & 1u ? xs : 0u) | (ys & 2u ? xs << 3 : 0u) | (ys & 4u ? xs << 6 : 0u);
+                            act |= (zs & 1u ? xy : 0u) | (zs & 2u ? xy << 9 : 0u) | (zs & 4u ? xy << 18 : 0u);
+                        }
+                    }
+                }
+            }
+            act = __reduce_or_sync(FULL, act);
+            if (lane < 27 && ((act >> lane) & 1u)) {
+                const int ax = tx + lane % 3 - 1, ay = ty + (lane / 3) % 3 - 1, az = tz + lane / 9 - 1;
+                if (ax >= 0 && ay >= 0 && az >= 0 && ax < t.ntx && ay < t.nty && az < t.ntz) {
+                    tile_enqueue(t, (az * t.nty + ay) * t.ntx + ax, qi_next);
+                }
+            }
+#ifdef SMPLGPU_BFS_STATS
+            if (lane == 0) {
+                const long long c3 = clock64();
+                atomicAdd(reinterpret_cast<unsigned long long*>(t.qn + 8), (unsigned long long)(c1 - c0));
+                atomicAdd(reinterpret_cast<unsigned long long*>(t.qn + 10), (unsigned long long)(c2 - c1));
+                atomicAdd(reinterpret_cast<unsigned long long*>(t.qn + 12), (unsigned long long)(c3 - c2));
+            }
+#endif
+        }
+#ifdef SMPLGPU_BFS_STATS
+        const long long b0 = clock64();
+#endif
+        grid_barrier(bar, (unsigned int)(n + 1) * gridDim.x);
+#ifdef SMPLGPU_BFS_STATS
+        if (threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(t.qn + 14), (unsigned long long)(clock64() - b0));
+#endif
+    }
     for (int o = 16; o > 0; o >>= 1) {
         max_level = max(max_level, __shfl_xor_sync(0xffffffffu, max_level, o));
     }

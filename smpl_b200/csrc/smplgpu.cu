@@ -315,7 +315,7 @@ smplgpu_ctx* smplgpu_create(int device)
 
 static void free_tiles(BfsTiles& t)
 {
-    cudaFree(t.blocked1); cudaFree(t.ver);
+    cudaFree(t.tb[0]); cudaFree(t.ver);
     memset(&t, 0, sizeof(t));
 }
 
@@ -326,7 +326,15 @@ static int alloc_tiles(smplgpu_ctx* ctx, const BfsGrid& g, BfsTiles& t, size_t w
     t.nty = (g.DY + TILE_Y - 1) / TILE_Y;
     t.ntz = (g.DZ + TILE_Y - 1) / TILE_Y;
     t.ntiles = t.ntx * t.nty * t.ntz;
-    CU(cudaMalloc(&t.blocked1, words * sizeof(uint32_t)));
+    (void)words;
+    {
+        // the four tile-major bitmaps (two blocked copies, two frontiers) in one allocation
+        const size_t tw = (size_t)t.ntiles * TILE_WORDS;
+        CU(cudaMalloc(&t.tb[0], 4 * tw * sizeof(uint32_t)));
+        t.tb[1] = t.tb[0] + tw;
+        t.tf[0] = t.tb[0] + 2 * tw;
+        t.tf[1] = t.tb[0] + 3 * tw;
+    }
     // ver[ntiles] | flag[3][ntiles] | queue[3][ntiles] | qn[3] (+ pad), all 32-bit
     CU(cudaMalloc(&t.ver, ((size_t)7 * t.ntiles + 16) * sizeof(uint32_t)));
     t.flag = t.ver + t.ntiles;
@@ -2147,8 +2155,12 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
         bfs_reset_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(g, d_slot_mask, slot_dz);
     }
     ++ctx->launches;
+    if (tiles && t.tb[0] == nullptr) {
+        const int r = alloc_tiles(ctx, g, t, words);
+        if (r) return r;
+    }
     if (tiles) {
-        bfs_tiles_reset_kernel<<<std::min((total + 255) / 256, 148 * 16), 256, 0, stream>>>(g, t, d_slot_mask, slot_dz);
+        bfs_tiles_reset_kernel<<<(unsigned)std::min<long long>(((long long)t.ntiles * TILE_WORDS + 255) / 256, 148 * 16), 256, 0, stream>>>(g, t, d_slot_mask, slot_dz);
         ++ctx->launches;
         CU(cudaMemsetAsync(t.ver, 0, ((size_t)7 * t.ntiles + 16) * sizeof(uint32_t), stream));
     }
@@ -2166,20 +2178,23 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
         // persistent cooperative kernel, TILE_K levels per grid barrier: 1024-thread blocks, one per SM, for grids with
         // few tiles; 256-thread blocks, four per SM, for large ones (bfs_tiles.cuh; SMPLGPU_BFS_TILE_RPT forces 1 or 4)
         static const int forced = getenv("SMPLGPU_BFS_TILE_RPT") ? atoi(getenv("SMPLGPU_BFS_TILE_RPT")) : 0;
+        const bool warp_tiles = forced == 32;   // bfs_warp_tiles_kernel: one warp per tile, rows in registers
         const bool large = forced > 0 ? forced >= TILE_RPT_LARGE : t.ntiles >= 4096;
-        const void* kern = large ? (const void*)bfs_tiles_kernel<TILE_RPT_LARGE> : (const void*)bfs_tiles_kernel<1>;
-        const int threads = large ? TILE_THREADS / TILE_RPT_LARGE : TILE_THREADS;
+        const void* kern = warp_tiles ? (const void*)bfs_warp_tiles_kernel
+                                      : (large ? (const void*)bfs_tiles_kernel<TILE_RPT_LARGE> : (const void*)bfs_tiles_kernel<1>);
+        const int threads = warp_tiles ? WTILE_WARPS * 32 : (large ? TILE_THREADS / TILE_RPT_LARGE : TILE_THREADS);
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
         if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS tile kernel does not fit an SM");
-        per_sm = std::min(per_sm, large ? TILE_RPT_LARGE : 1);
+        per_sm = std::min(per_sm, warp_tiles ? WTILE_BLOCKS_PER_SM : (large ? TILE_RPT_LARGE : 1));
         // A run queued behind the caller's back (smplgpu_bfs_bank_run_slots_async) leaves room for the expansion
         // rounds that are meant to keep flowing meanwhile: three of the four block slots of every SM (large grids), or
         // seven eighths of the SMs (1024-thread blocks); a synchronous run takes the whole machine.
         const bool async_run = stream == ctx->bfs_stream;
-        if (async_run && large) per_sm = std::max(1, per_sm - 1);
-        const int sms = (async_run && !large) ? ctx->sm_count - std::max(1, ctx->sm_count / 8) : ctx->sm_count;
-        const int blocks = std::max(1, std::min(sms * per_sm, t.ntiles));
+        if (async_run && (large || warp_tiles)) per_sm = std::max(1, per_sm - 1);
+        const int sms = (async_run && !large && !warp_tiles) ? ctx->sm_count - std::max(1, ctx->sm_count / 8) : ctx->sm_count;
+        const int tiles_per_block = warp_tiles ? WTILE_WARPS : 1;
+        const int blocks = std::max(1, std::min(sms * per_sm, (t.ntiles + tiles_per_block - 1) / tiles_per_block));
         int max_steps = (int)std::min<long long>(cap / TILE_K + 2, 0x7FFFFFFFLL / blocks - 1);
         void* args[] = { (void*)&g, (void*)&t, (void*)&max_steps };
         CU(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(threads), args, 0, stream));
@@ -2456,8 +2471,7 @@ int smplgpu_bfs_bank_create(smplgpu_ctx* ctx, int n_slots, double inflation_radi
     if (!same_shape) {
         int r = alloc_grid(ctx, ctx->bank, nx, ny, (int)total_nz, &ctx->bank_words, &ctx->bank_cells);
         if (r) return r;
-        r = alloc_tiles(ctx, ctx->bank, ctx->bank_tiles, ctx->bank_words);
-        if (r) return r;
+        free_tiles(ctx->bank_tiles);   // allocated by the first run that uses the tile kernel on the bank (run_grid)
     }
     ctx->bank_slots = n_slots;
     ctx->bank_slot_dz = nz + 2;
