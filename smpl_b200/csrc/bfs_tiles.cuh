@@ -140,6 +140,9 @@ __device__ __forceinline__ unsigned long long pack_row(uint32_t left, uint32_t m
 }
 
 constexpr unsigned long long ROW_MASK = 0xFFFFFFFFFFFFull;   // 48 cells
+#ifdef SMPLGPU_BFS_STATS
+__device__ unsigned long long bfs_dbg[4][2048];   // per super-step: queue length, slowest block's busy cycles, most tiles a block took, sum of busy cycles
+#endif
 constexpr int TILE_RPT_LARGE = 4;                             // extended z-rows per warp on large grids
 
 // One block = one tile at a time; a warp owns TILE_RPT z-rows of the extended tile (interleaved, so that the few
@@ -158,6 +161,12 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
 {
     __shared__ unsigned long long sF[2][TILE_THREADS];   // frontier rows, double-buffered by level
     __shared__ uint8_t sZ[2][TILE_E + 2];                // z-row has frontier cells (per buffer); [0] and [33] stay 0
+    // Distances leave the tile AFTER its levels: cells found this super-step (sNew) and the level of each, minus one, as
+    // three bit planes (sLev), per interior row.  Storing them level by level -- per-lane loops for rows with a few new
+    // cells, warp-wide stores for dense rows, all between two block barriers -- cost 0.8 of 2.6 ms at 400^3: the slowest
+    // warp's stores were on the critical path of every level of every tile.
+    __shared__ uint32_t sNew[TILE_WORDS];
+    __shared__ uint32_t sLev[3][TILE_WORDS];
     __shared__ unsigned int s_act;                       // which of the 27 neighbour directions get activated
     __shared__ int s_next[2];                            // next queue position of this block, double-buffered by tile
                                                          // count: thread 0 writes slot k & 1 for tile k before that tile's
@@ -171,7 +180,7 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
     // through levels <= TILE_K - j, so level s needs just the rows with j <= TILE_K - s
     const int jy = ry < TILE_K ? TILE_K - ry : (ry >= TILE_K + TILE_Y ? ry - (TILE_K + TILE_Y - 1) : 0);
     const bool interior_y = ry >= TILE_K && ry < TILE_K + TILE_Y;
-    int jz[TILE_RPT], row_out[TILE_RPT];
+    int jz[TILE_RPT], row_out[TILE_RPT], irow[TILE_RPT];
     bool interior_row[TILE_RPT];
 #pragma unroll
     for (int r = 0; r < TILE_RPT; ++r) {
@@ -179,6 +188,7 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
         jz[r] = rz < TILE_K ? TILE_K - rz : (rz >= TILE_K + TILE_Y ? rz - (TILE_K + TILE_Y - 1) : 0);
         row_out[r] = max(jy, jz[r]);
         interior_row[r] = interior_y && rz >= TILE_K && rz < TILE_K + TILE_Y;
+        irow[r] = (rz - TILE_K) * TILE_Y + (ry - TILE_K);
     }
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(&g.ctrl[4]);
     int max_level = 0;
@@ -198,6 +208,8 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
         const int q_len = __ldcg(&t.qn[qi]);
 #ifdef SMPLGPU_BFS_STATS
         if (blockIdx.x == 0 && tid == 0) atomicAdd(&g.ctrl[3], q_len);
+        const long long ss0 = clock64();
+        int taken = 0;
 #endif
         if (q_len == 0) {
             break;   // no tile has a frontier left (every block reads the same length)
@@ -219,21 +231,19 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                 }
 #ifdef SMPLGPU_BFS_STATS
                 const long long c0 = clock64();
+                ++taken;
 #endif
                 const int tx = tile % t.ntx, ty = (tile / t.ntx) % t.nty, tz = tile / (t.ntx * t.nty);
-                const int gy = ty * TILE_Y - TILE_K + ry;
                 // the tile that owns this thread's rows (y part) and the rows' place in its 16 x 16 block
                 const int oty = ty + (ry < TILE_K ? -1 : (ry >= TILE_K + TILE_Y ? 1 : 0));
                 const int yi = (ry + TILE_K) & (TILE_Y - 1);
                 int own[TILE_RPT];       // owner tile of the row in x-column tx - 1 (+1, +2 for the other two), or TILE_NONE
-                int gz[TILE_RPT];
 
                 // ---- the frontier of this thread's rows: the interior word and 8 cells of each neighbour ----
                 uint32_t fw[TILE_RPT][3];
 #pragma unroll
                 for (int r = 0; r < TILE_RPT; ++r) {
                     const int rz = warp + (TILE_E / TILE_RPT) * r;
-                    gz[r] = tz * TILE_Y - TILE_K + rz;
                     const int otz = tz + (rz < TILE_K ? -1 : (rz >= TILE_K + TILE_Y ? 1 : 0));
                     const bool in = oty >= 0 && oty < t.nty && otz >= 0 && otz < t.ntz;
                     own[r] = in ? (otz * t.nty + oty) * t.ntx + tx - 1 : TILE_NONE;
@@ -254,6 +264,12 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                     const unsigned long long f0 = pack_row(fw[r][0], fw[r][1], fw[r][2]);
                     sF[0][rz * TILE_E + lane] = f0;
                     sF[1][rz * TILE_E + lane] = 0;
+                    if (interior_row[r]) {
+                        sNew[irow[r]] = 0;
+                        sLev[0][irow[r]] = 0;
+                        sLev[1][irow[r]] = 0;
+                        sLev[2][irow[r]] = 0;
+                    }
                     const bool zany = __any_sync(0xffffffffu, f0 != 0);
                     if (lane == 0) {
                         sZ[0][rz + 1] = zany ? 1 : 0;
@@ -336,32 +352,14 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                         if (interior_row[r]) {
                             last[r] = fresh_in;
                             if (fresh_in) {
+                                // the level of every new cell, bit-sliced (only this thread touches its rows' words
+                                // until the barrier after the last level)
                                 changed = true;
                                 max_level = max(max_level, level0 + s);
-                            }
-                        }
-                        // distances of the interior word: a row with a few new cells (a wavefront face across x) stores
-                        // them itself; dense rows (faces along x) go out warp-wide, lanes = bits, one 128-byte store per row
-                        if (zgot && rz >= TILE_K && rz < TILE_K + TILE_Y) {
-                            const bool mine = interior_row[r] && fresh_in != 0;
-                            const bool dense = mine && __popc(fresh_in) > 4;
-                            if (mine && !dense) {
-                                int* d = g.dist + ((size_t)gz[r] * g.DY + gy) * g.DX + (size_t)tx * 32;
-                                uint32_t f = fresh_in;
-                                while (f) {
-                                    d[__ffs(f) - 1] = level0 + s;
-                                    f &= f - 1;
-                                }
-                            }
-                            uint32_t todo = __ballot_sync(0xffffffffu, dense);
-                            while (todo) {
-                                const int rr = __ffs(todo) - 1;
-                                todo &= todo - 1;
-                                const uint32_t wk = __shfl_sync(0xffffffffu, fresh_in, rr);
-                                const int y2 = ty * TILE_Y - TILE_K + rr;
-                                if ((wk >> lane) & 1u) {
-                                    g.dist[((size_t)gz[r] * g.DY + y2) * g.DX + (size_t)tx * 32 + lane] = level0 + s;
-                                }
+                                sNew[irow[r]] |= fresh_in;
+                                if ((s - 1) & 1) sLev[0][irow[r]] |= fresh_in;
+                                if ((s - 1) & 2) sLev[1][irow[r]] |= fresh_in;
+                                if ((s - 1) & 4) sLev[2][irow[r]] |= fresh_in;
                             }
                         }
                     }
@@ -382,6 +380,26 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
 #endif
                 // ---- write back the interior: blocked into the other copy, frontier for the next super-step ----
                 if (__syncthreads_or(changed ? 1 : 0)) {
+                    {
+                        // distances: a warp takes 8 * TILE_RPT interior rows; lanes = cells, one store of up to 128 bytes
+                        // per row that gained cells
+                        constexpr int ROWS_PER_WARP = TILE_WORDS / (TILE_THREADS / TILE_RPT / 32);
+                        const int first = warp * ROWS_PER_WARP;
+                        const uint32_t mine = lane < ROWS_PER_WARP ? sNew[first + lane] : 0u;
+                        uint32_t todo = __ballot_sync(0xffffffffu, mine != 0);
+                        while (todo) {
+                            const int rr = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const int ir = first + rr;
+                            const uint32_t nw = __shfl_sync(0xffffffffu, mine, rr);
+                            const uint32_t l0 = sLev[0][ir], l1 = sLev[1][ir], l2 = sLev[2][ir];
+                            if ((nw >> lane) & 1u) {
+                                const int lev = 1 + (int)(((l0 >> lane) & 1u) | (((l1 >> lane) & 1u) << 1) | (((l2 >> lane) & 1u) << 2));
+                                const int y2 = ty * TILE_Y + (ir % TILE_Y), z2 = tz * TILE_Y + ir / TILE_Y;
+                                g.dist[((size_t)z2 * g.DY + y2) * g.DX + (size_t)tx * 32 + lane] = level0 + lev;
+                            }
+                        }
+                    }
                     const uint32_t v = tile_copy(t, tile, n);
                     uint32_t* dst = t.tb[v ^ 1u];
 #pragma unroll
@@ -441,6 +459,12 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
         }
 #ifdef SMPLGPU_BFS_STATS
         const long long b0 = clock64();
+        if (tid == 0 && n < 2048) {
+            bfs_dbg[0][n] = (unsigned long long)q_len;
+            atomicMax(&bfs_dbg[1][n], (unsigned long long)(b0 - ss0));
+            atomicMax(&bfs_dbg[2][n], (unsigned long long)taken);
+            atomicAdd(&bfs_dbg[3][n], (unsigned long long)(b0 - ss0));
+        }
 #endif
         grid_barrier(bar, (unsigned int)(n + 1) * gridDim.x);
 #ifdef SMPLGPU_BFS_STATS

@@ -2179,14 +2179,16 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
         // few tiles; 256-thread blocks, four per SM, for large ones (bfs_tiles.cuh; SMPLGPU_BFS_TILE_RPT forces 1 or 4)
         static const int forced = getenv("SMPLGPU_BFS_TILE_RPT") ? atoi(getenv("SMPLGPU_BFS_TILE_RPT")) : 0;
         const bool warp_tiles = forced == 32;   // bfs_warp_tiles_kernel: one warp per tile, rows in registers
-        const bool large = forced > 0 ? forced >= TILE_RPT_LARGE : t.ntiles >= 4096;
+        const bool large = forced > 0 ? forced >= 2 : t.ntiles >= 4096;
+        const int rpt = forced == 2 ? 2 : TILE_RPT_LARGE;
         const void* kern = warp_tiles ? (const void*)bfs_warp_tiles_kernel
-                                      : (large ? (const void*)bfs_tiles_kernel<TILE_RPT_LARGE> : (const void*)bfs_tiles_kernel<1>);
-        const int threads = warp_tiles ? WTILE_WARPS * 32 : (large ? TILE_THREADS / TILE_RPT_LARGE : TILE_THREADS);
+                                      : (large ? (rpt == 2 ? (const void*)bfs_tiles_kernel<2> : (const void*)bfs_tiles_kernel<TILE_RPT_LARGE>)
+                                               : (const void*)bfs_tiles_kernel<1>);
+        const int threads = warp_tiles ? WTILE_WARPS * 32 : (large ? TILE_THREADS / rpt : TILE_THREADS);
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
         if (per_sm < 1) return fail(ctx, SMPLGPU_ERR_CUDA, "BFS tile kernel does not fit an SM");
-        per_sm = std::min(per_sm, warp_tiles ? WTILE_BLOCKS_PER_SM : (large ? TILE_RPT_LARGE : 1));
+        per_sm = std::min(per_sm, warp_tiles ? WTILE_BLOCKS_PER_SM : (large ? rpt : 1));
         // A run queued behind the caller's back (smplgpu_bfs_bank_run_slots_async) leaves room for the expansion
         // rounds that are meant to keep flowing meanwhile: three of the four block slots of every SM (large grids), or
         // seven eighths of the SMs (1024-thread blocks); a synchronous run takes the whole machine.
@@ -2323,6 +2325,19 @@ int smplgpu_bfs_run(smplgpu_ctx* ctx, const int32_t* seeds_xyz, int n_seeds)
             cudaMemcpy(tt, ctx->bfs_tiles.qn + 8, sizeof(tt), cudaMemcpyDeviceToHost);
             fprintf(stderr, "[bfs stats] block-cycles: load %.1f M, levels %.1f M, write-back %.1f M, grid barrier %.1f M\n",
                     tt[0] * 1e-6, tt[1] * 1e-6, tt[2] * 1e-6, tt[3] * 1e-6);
+            static unsigned long long dbg[4][2048];
+            cudaMemcpyFromSymbol(dbg, bfs_dbg, sizeof(dbg));
+            unsigned long long sum_max = 0, sum_all = 0, multi = 0, steps = 0, sum_q = 0;
+            for (int i = 0; i < 2048; ++i) {
+                if (dbg[0][i] == 0) continue;
+                ++steps; sum_max += dbg[1][i]; sum_all += dbg[3][i]; sum_q += dbg[0][i];
+                if (dbg[2][i] > 1) ++multi;
+                if (getenv("SMPLGPU_BFS_STATS_STEPS")) fprintf(stderr, "  step %d: queue %llu, slowest block %llu cycles, most tiles per block %llu, mean busy %llu\n", i, dbg[0][i], dbg[1][i], dbg[2][i], dbg[3][i] / 592);
+            }
+            fprintf(stderr, "[bfs stats] %llu super-steps, %llu tiles queued, sum of slowest-block cycles %.2f M, sum of all busy cycles %.1f M, super-steps where a block took > 1 tile: %llu\n",
+                    steps, sum_q, sum_max * 1e-6, sum_all * 1e-6, multi);
+            static unsigned long long zero[4][2048];
+            cudaMemcpyToSymbol(bfs_dbg, zero, sizeof(zero));
         }
     }
 #endif
