@@ -241,6 +241,8 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
 
                 // ---- the frontier of this thread's rows: the interior word and 8 cells of each neighbour ----
                 uint32_t fw[TILE_RPT][3];
+                unsigned cps = 0;   // bit 3 r + w: which blocked copy the owner of row r, x-column w committed last (the
+                                    // version words are fetched with the frontier, one L2 round trip ahead of the blocked rows)
 #pragma unroll
                 for (int r = 0; r < TILE_RPT; ++r) {
                     const int rz = warp + (TILE_E / TILE_RPT) * r;
@@ -254,6 +256,7 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                         fw[r][w] = 0;
                         if (in && gw >= 0 && gw < t.ntx) {
                             fw[r][w] = __ldcg(&fcur[(size_t)(own[r] + w) * TILE_WORDS + wi]);
+                            cps |= tile_copy(t, own[r] + w, n) << (3 * r + w);
                         }
                     }
                 }
@@ -300,8 +303,7 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                             const int gw = tx - 1 + w;
                             uint32_t bb = 0xFFFFFFFFu;
                             if (own[r] != TILE_NONE && gw >= 0 && gw < t.ntx) {
-                                const int owner = own[r] + w;
-                                bb = __ldcg(&t.tb[tile_copy(t, owner, n)][(size_t)owner * TILE_WORDS + wi]);
+                                bb = __ldcg(&t.tb[(cps >> (3 * r + w)) & 1u][(size_t)(own[r] + w) * TILE_WORDS + wi]);
                             }
                             bw[r][w] = bb;
                         }
@@ -333,14 +335,18 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
                         }
                         const int row = rz * TILE_E + lane;
                         unsigned long long fresh = 0;
-                        if (zact && row_out[r] <= TILE_K - s) {
-                            // the z-rows below / above the extended tile do not exist: rz - 1 < 0 or rz + 1 > 31 only for
-                            // rows with jz = TILE_K, which no level computes (jz <= TILE_K - s < TILE_K); the same for y
+                        if (zact) {   // warp-uniform
+                            // dilation in z from shared memory (three rows), in y by shuffles, in x by shifts -- nine
+                            // 64-bit shared loads per row kept the shared-memory pipe busy 576 cycles per level of a
+                            // fully active tile.  zact implies 0 < rz < 31 (the rim rows have jz = TILE_K, which no
+                            // level computes); lanes 0 and 31 get their own value back from the shuffles.
                             const unsigned long long* F = sF[cur];
-                            const unsigned long long m = F[row - 33] | F[row - 32] | F[row - 31] | F[row - 1] | F[row] | F[row + 1] |
-                                                         F[row + 31] | F[row + 32] | F[row + 33];
-                            fresh = (m | (m << 1) | (m >> 1)) & ~blk[r] & ROW_MASK;
-                            blk[r] |= fresh;
+                            unsigned long long m = F[row - TILE_E] | F[row] | F[row + TILE_E];
+                            m |= __shfl_up_sync(0xffffffffu, m, 1) | __shfl_down_sync(0xffffffffu, m, 1);
+                            if (row_out[r] <= TILE_K - s) {
+                                fresh = (m | (m << 1) | (m >> 1)) & ~blk[r] & ROW_MASK;
+                                blk[r] |= fresh;
+                            }
                         }
                         const bool zgot = __any_sync(0xffffffffu, fresh != 0);
                         sF[cur ^ 1][row] = fresh;      // the whole z-row is rewritten, so a clear flag means clear rows
