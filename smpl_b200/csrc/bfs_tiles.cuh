@@ -8,8 +8,8 @@
 //     frontier' = dilate26(frontier) & ~blocked;   blocked |= frontier'
 // Row r of the extended tile is exact for as many levels as it is rows away from the tile's rim (a cell's
 // level-s value depends on cells at most s away), so the 16 x 16 interior rows are exact for all TILE_K levels;
-// only they are written back (new blocked bits, the frontier after the last level, and the distances, level
-// by level).  The result is the level-synchronous BFS, bit for bit.
+// only they are written back (new blocked bits, the frontier after the last level, and the distances of the
+// cells found, each with its level).  The result is the level-synchronous BFS, bit for bit.
 //
 // Between super-steps (TILE_K levels) the tiles talk through global memory:
 //   * `front[p]`: the frontier at the start of super-step n (p = n & 1), written by the previous super-step;
@@ -23,11 +23,12 @@
 // by then, so whatever they contribute is removed by `& ~blocked` (same argument as in bfs.cuh).
 // One grid barrier per super-step; the search ends when a queue comes up empty.
 //
-// Measured on B200 (tools/bfs_only.py, tools/bank_bfs_time.py): single grids run faster than with
-// bfs_levels_kernel (64^3: 0.19 vs 0.35 ms, 150^3: 0.44 vs 0.99 ms, 400^3: 3.7 vs 4.3 ms) because they are
-// bound by the per-level latency; the stacked planner banks (many wavefronts at once: 0.18 vs 0.15 ms per
-// query) are throughput bound and the tile kernel's halo recomputation costs more than the barriers it saves.
-// smplgpu.cu picks the kernel accordingly unless smplgpu_bfs_set_mode forces one.
+// Measured on B200 (tools/bfs_only.py, tools/bank_bfs_time.py; end of round 2): single grids run faster than
+// with bfs_levels_kernel (64^3: 0.16 vs 0.37 ms, 150^3: 0.29 vs 1.05 ms, 400^3: 2.06 vs 4.56 ms) because they
+// are bound by the per-level latency.  On the stacked planner banks the tile kernel is faster in isolation too
+// (0.087 vs 0.158 ms per query) but not inside the planner, where its cooperative launch has to find room next
+// to the other contexts' expansion rounds, so smplgpu.cu uses it for single grids and
+// the level kernel for the banks unless smplgpu_bfs_set_mode forces one.
 #pragma once
 
 #include "bfs.cuh"

@@ -75,7 +75,10 @@ def sass():
     cur, name = [], None
     def flush():
         if name and cur:
-            short = re.sub(r"[^A-Za-z0-9_]", "", name)
+            # "void bfs_tiles_kernel<4>" -> bfs_tiles_kernel_rpt4
+            short = re.sub(r"^void\s+", "", name)
+            short = re.sub(r"<(\d+)>", r"_rpt\1", short)
+            short = re.sub(r"[^A-Za-z0-9_]", "", short)
             with open(os.path.join(d, short + ".sass"), "w") as f:
                 f.write("\n".join(cur) + "\n")
     for line in out.splitlines():
