@@ -130,6 +130,10 @@ std::vector<std::string> SplitCsv(const char* s)
 
 } // namespace
 
+// set by *_plan_lazy around a call of *_plan: the search is the reference's LazyARAStar over GetLazySuccs / GetTrueCost
+static thread_local bool tl_lazy = false;
+static thread_local int tl_lazy_evaluations = 0;
+
 extern "C" {
 
 /// batched_get_succs == 1 runs the reference's lattice with the INTEGRATION.md section-4 edit (BatchedManipLattice);
@@ -223,27 +227,42 @@ int refdrop_plan(smplgpu_ctx* ctx, const char* robot_path, const char* group, co
         return 0;
     }
 
-    ARAStar search(&space, &heur);
-    search.set_initialsolution_eps(epsilon);
-    if (search.set_start(space.getStartStateID()) == 0) return -9;
-    if (search.set_goal(space.getGoalStateID()) == 0) return -10;
-    ARAStar::TimeParameters tp;
-    tp.bounded = true;
-    tp.improve = false;
-    tp.type = ARAStar::TimeParameters::EXPANSIONS;
-    tp.max_expansions_init = max_expansions;
-    tp.max_expansions = max_expansions;
-    tp.max_allowed_time_init = sbpl::clock::duration::zero();
-    tp.max_allowed_time = sbpl::clock::duration::zero();
     std::vector<int> solution;
     int solcost = 0;
-    const int ret = search.replan(tp, &solution, &solcost);
-    out_summary[1] = search.get_n_expands();
-    out_summary[4] = (int)space.m_states.size();
-    out_summary[6] = cache ? (int)cache->launches() : (int)space.batched_calls;
-    out_summary[7] = cache ? (int)cache->hits() : (int)space.edges_submitted;
-    if (!ret || solcost >= INFINITECOST) {
-        return 0;
+    if (tl_lazy) {
+        // the reference's lazy successors (GetLazySuccs / GetTrueCost) under its in-tree LazyARAStar
+        int expansions = 0;
+        tl_lazy_evaluations = 0;
+        const bool found = RunLazyARAStar(&space, &heur, epsilon, space.getStartStateID(), space.getGoalStateID(),
+                                          max_expansions, solution, solcost, expansions, tl_lazy_evaluations);
+        out_summary[1] = expansions;
+        out_summary[4] = (int)space.m_states.size();
+        out_summary[6] = cache ? (int)cache->launches() : 0;
+        out_summary[7] = cache ? (int)cache->hits() : 0;
+        if (!found) {
+            return 0;
+        }
+    } else {
+        ARAStar search(&space, &heur);
+        search.set_initialsolution_eps(epsilon);
+        if (search.set_start(space.getStartStateID()) == 0) return -9;
+        if (search.set_goal(space.getGoalStateID()) == 0) return -10;
+        ARAStar::TimeParameters tp;
+        tp.bounded = true;
+        tp.improve = false;
+        tp.type = ARAStar::TimeParameters::EXPANSIONS;
+        tp.max_expansions_init = max_expansions;
+        tp.max_expansions = max_expansions;
+        tp.max_allowed_time_init = sbpl::clock::duration::zero();
+        tp.max_allowed_time = sbpl::clock::duration::zero();
+        const int ret = search.replan(tp, &solution, &solcost);
+        out_summary[1] = search.get_n_expands();
+        out_summary[4] = (int)space.m_states.size();
+        out_summary[6] = cache ? (int)cache->launches() : (int)space.batched_calls;
+        out_summary[7] = cache ? (int)cache->hits() : (int)space.edges_submitted;
+        if (!ret || solcost >= INFINITECOST) {
+            return 0;
+        }
     }
     out_summary[0] = 1;
     out_summary[2] = solcost;
@@ -261,6 +280,31 @@ int refdrop_plan(smplgpu_ctx* ctx, const char* robot_path, const char* group, co
         }
     }
     return 0;
+}
+
+/// refdrop_plan with the reference's lazy successors (GetLazySuccs / GetTrueCost) under its in-tree LazyARAStar, the
+/// lattice and the search untouched, every question answered by the adapters (see refcc_plan_lazy).
+int refdrop_plan_lazy(smplgpu_ctx* ctx, const char* robot_path, const char* group, const char* planning_joints_csv,
+                      const char* planning_link, const double* grid_origin, double grid_res, const int32_t* grid_dims,
+                      double inflation_radius, int cost_per_cell,
+                      const double* start, const double* goal_xyz, const double* xyz_offset,
+                      const double* resolutions, const double* mprims, const uint8_t* short_flags, int n_prims,
+                      int use_short_dist, double short_dist_thresh, double epsilon, int max_expansions,
+                      const double* xyz_tolerance, int32_t* out_summary, int32_t* path_ids, int max_path,
+                      double* path_states, int batched_get_succs)
+{
+    tl_lazy = true;
+    const int r = refdrop_plan(ctx, robot_path, group, planning_joints_csv, planning_link, grid_origin, grid_res, grid_dims,
+                               inflation_radius, cost_per_cell, start, goal_xyz, xyz_offset, resolutions, mprims, short_flags,
+                               n_prims, use_short_dist, short_dist_thresh, epsilon, max_expansions, xyz_tolerance, out_summary,
+                               path_ids, max_path, path_states, batched_get_succs);
+    tl_lazy = false;
+    return r;
+}
+
+int refdrop_last_lazy_evaluations(void)
+{
+    return tl_lazy_evaluations;
 }
 
 } // extern "C"

@@ -13,6 +13,7 @@
 #include <smpl/graph/robot_planning_space.h>
 #include <smpl/heuristic/robot_heuristic.h>
 #include <smpl/robot_model.h>
+#include <smpl/search/lazy_arastar.h>
 
 namespace {
 
@@ -74,6 +75,59 @@ inline void FillPrimitives(ShimActionSpace& actions, const double* mprims, const
         actions.deltas.push_back(d);
         actions.is_short.push_back(short_flags[p] != 0);
     }
+}
+
+/// The reference's in-tree lazy search (smpl/src/search/lazy_arastar.cpp) asks an sbpl::ILazySuccFun
+/// (search/lazy_search_interface.h:54-65); no class of the reference implements it, so this is the adapter a user of
+/// LazyARAStar writes: RobotPlanningSpace::GetLazySuccs / GetTrueCost (manip_lattice.cpp:1012-1167) as they are.
+/// LazyARAStar has no expansion bound of its own: after `max_expansions` expansions this adapter returns no successors
+/// and refuses evaluations, which drains OPEN (the same bound in the all-reference and the drop-in run).
+struct LatticeLazySuccFun : public sbpl::ILazySuccFun
+{
+    RobotPlanningSpace* space = nullptr;
+    int max_expansions = 0;
+    int expansions = 0;
+    int evaluations = 0;
+
+    void GetLazySuccs(int state_id, std::vector<int>& succs, std::vector<int>& costs, std::vector<bool>& true_costs) override
+    {
+        if (expansions >= max_expansions) {
+            return;
+        }
+        ++expansions;
+        space->GetLazySuccs(state_id, &succs, &costs, &true_costs);
+    }
+
+    int GetSuccTrueCost(int state_id, int succ_id) override
+    {
+        if (expansions >= max_expansions) {
+            return -1;
+        }
+        ++evaluations;
+        return space->GetTrueCost(state_id, succ_id);
+    }
+};
+
+/// one LazyARAStar query; returns true and fills solution / cost when the goal was reached
+inline bool RunLazyARAStar(RobotPlanningSpace* space, RobotHeuristic* heur, double epsilon, int start_id, int goal_id,
+                           int max_expansions, std::vector<int>& solution, int& cost, int& expansions, int& evaluations)
+{
+    LatticeLazySuccFun fun;
+    fun.space = space;
+    fun.max_expansions = max_expansions;
+    sbpl::LazyARAStar search;
+    search.eps_ = epsilon;
+    bool found = false;
+    if (sbpl::Init(search, &fun, heur)) {
+        found = sbpl::Replan(search, start_id, goal_id, solution, cost) == 0;
+    }
+    expansions = fun.expansions;
+    evaluations = fun.evaluations;
+    for (auto* st : search.states_) {
+        delete st;   // Clear() of lazy_arastar.cpp runs at the start of a query only
+    }
+    search.states_.clear();
+    return found;
 }
 
 } // namespace

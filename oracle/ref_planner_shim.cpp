@@ -75,6 +75,10 @@ bool SetupRobotModel(sbpl::motion::KDLRobotModel& robot, refcc_scene* s, const c
 
 } // namespace
 
+// set by *_plan_lazy around a call of *_plan: the search is the reference's LazyARAStar over GetLazySuccs / GetTrueCost
+static thread_local bool tl_lazy = false;
+static thread_local int tl_lazy_evaluations = 0;
+
 extern "C" {
 
 /// same arguments and summary as oracle_plan (oracle/oracle_capi.cpp): out_summary = success, expansions, cost,
@@ -135,25 +139,38 @@ int refcc_plan(refcc_scene* s, const char* chain_root, const char* chain_tip, co
         return 0;   // start outside the limits or in collision: no plan (PlannerInterface gives up the same way)
     }
 
-    ARAStar search(&space, &heur);
-    search.set_initialsolution_eps(epsilon);
-    if (search.set_start(space.getStartStateID()) == 0) return -8;
-    if (search.set_goal(space.getGoalStateID()) == 0) return -9;
-    ARAStar::TimeParameters tp;
-    tp.bounded = true;
-    tp.improve = false;
-    tp.type = ARAStar::TimeParameters::EXPANSIONS;
-    tp.max_expansions_init = max_expansions;
-    tp.max_expansions = max_expansions;
-    tp.max_allowed_time_init = sbpl::clock::duration::zero();
-    tp.max_allowed_time = sbpl::clock::duration::zero();
     std::vector<int> solution;
     int solcost = 0;
-    const int ret = search.replan(tp, &solution, &solcost);
-    out_summary[1] = search.get_n_expands();
-    out_summary[4] = (int)space.m_states.size();
-    if (!ret || solcost >= INFINITECOST) {
-        return 0;
+    if (tl_lazy) {
+        // the reference's lazy successors (GetLazySuccs / GetTrueCost) under its in-tree LazyARAStar
+        int expansions = 0;
+        tl_lazy_evaluations = 0;
+        const bool found = RunLazyARAStar(&space, &heur, epsilon, space.getStartStateID(), space.getGoalStateID(),
+                                          max_expansions, solution, solcost, expansions, tl_lazy_evaluations);
+        out_summary[1] = expansions;
+        out_summary[4] = (int)space.m_states.size();
+        if (!found) {
+            return 0;
+        }
+    } else {
+        ARAStar search(&space, &heur);
+        search.set_initialsolution_eps(epsilon);
+        if (search.set_start(space.getStartStateID()) == 0) return -8;
+        if (search.set_goal(space.getGoalStateID()) == 0) return -9;
+        ARAStar::TimeParameters tp;
+        tp.bounded = true;
+        tp.improve = false;
+        tp.type = ARAStar::TimeParameters::EXPANSIONS;
+        tp.max_expansions_init = max_expansions;
+        tp.max_expansions = max_expansions;
+        tp.max_allowed_time_init = sbpl::clock::duration::zero();
+        tp.max_allowed_time = sbpl::clock::duration::zero();
+        const int ret = search.replan(tp, &solution, &solcost);
+        out_summary[1] = search.get_n_expands();
+        out_summary[4] = (int)space.m_states.size();
+        if (!ret || solcost >= INFINITECOST) {
+            return 0;
+        }
     }
     out_summary[0] = 1;
     out_summary[2] = solcost;
@@ -171,6 +188,32 @@ int refcc_plan(refcc_scene* s, const char* chain_root, const char* chain_tip, co
         }
     }
     return 0;
+}
+
+/// refcc_plan with the reference's lazy successors: ManipLattice::GetLazySuccs / GetTrueCost (manip_lattice.cpp:1012-1167)
+/// under the in-tree LazyARAStar (search/lazy_arastar.cpp, weight `epsilon`, one pass).  out_summary[1] = expansions
+/// (GetLazySuccs calls); refcc_last_lazy_evaluations() = GetTrueCost calls of the last query on this thread.
+int refcc_plan_lazy(refcc_scene* s, const char* chain_root, const char* chain_tip, const char* planning_link,
+                    const double* T_kin_to_planning, const double* xyz_offset,
+                    double inflation_radius, int cost_per_cell,
+                    const double* start, const double* goal_xyz,
+                    const double* resolutions, const double* mprims, const uint8_t* short_flags, int n_prims,
+                    int use_short_dist, double short_dist_thresh, double epsilon, int max_expansions,
+                    const double* xyz_tolerance, int32_t* out_summary, int32_t* path_ids, int max_path,
+                    double* path_states)
+{
+    tl_lazy = true;
+    const int r = refcc_plan(s, chain_root, chain_tip, planning_link, T_kin_to_planning, xyz_offset, inflation_radius,
+                             cost_per_cell, start, goal_xyz, resolutions, mprims, short_flags, n_prims, use_short_dist,
+                             short_dist_thresh, epsilon, max_expansions, xyz_tolerance, out_summary, path_ids, max_path,
+                             path_states);
+    tl_lazy = false;
+    return r;
+}
+
+int refcc_last_lazy_evaluations(void)
+{
+    return tl_lazy_evaluations;
 }
 
 /// BfsHeuristic::GetGoalHeuristic (bfs_heuristic.cpp:148-163, 355-366) of the reference for n joint states: each state

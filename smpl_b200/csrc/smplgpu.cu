@@ -54,6 +54,7 @@ struct smplgpu_ctx
     float* d_blob = nullptr; size_t blob_cap = 0;   // bytes
     int blob_words = 0;
     int v32_threads = V32_THREADS;
+    int v32_edge_batch_blocks_per_sm = 0;   // 0: the batched edge kernel does not fit
     int v32_blocks_per_sm = 1;            // resident blocks of states_valid32_kernel per SM (persistent launch)
     int v32_slots = 0, v32_ptrees = 0;
     double e_pos = 0.0, eps_cells = 0.0;
@@ -844,6 +845,23 @@ static int build_model32(smplgpu_ctx* ctx)
     const int smem = (int)std::max(fixed + per_thread * threads, (size_t)1024);
     CU(cudaFuncSetAttribute(states_valid32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(edges_valid32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ctx->v32_edge_batch_blocks_per_sm = 0;
+    {
+        const size_t smem_b = (size_t)w * 4 + ((size_t)n_slots32 * 12 + (size_t)n_ptrees * 3) * sizeof(float) * threads +
+                              (2 * (size_t)V32_EDGE_EPT * threads + 4) * sizeof(int);   // == v32_smem_edge_batch once blob_words is set
+        if (smem_b <= smem_max) {
+            CU(cudaFuncSetAttribute(edges_valid32b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+            int per_sm = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edges_valid32b_kernel, threads, smem_b));
+            ctx->v32_edge_batch_blocks_per_sm = per_sm;
+            if (getenv("SMPLGPU_V32_VERBOSE")) {
+                int per_sm_old = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_old, edges_valid32_kernel, threads, (size_t)smem);
+                fprintf(stderr, "[smplgpu] edge kernels: %d threads, shared memory %d B (block form, %d blocks/SM) / %zu B (batched, %d blocks/SM)\n",
+                        threads, smem, per_sm_old, smem_b, per_sm);
+            }
+        }
+    }
     CU(cudaFuncSetAttribute(fk_centers32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(states_valid32p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaFuncSetAttribute(edges_valid32p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -864,6 +882,24 @@ static int build_model32(smplgpu_ctx* ctx)
     ctx->grid32.ox = (float)ctx->grid.ox; ctx->grid32.oy = (float)ctx->grid.oy; ctx->grid32.oz = (float)ctx->grid.oz;
     ctx->has_model32 = true;
     return 0;
+}
+
+// SMPLGPU_V32_EDGE_BATCH=0: the block-per-blockDim-edges form of the edge kernel (edges_valid32_kernel)
+static bool v32_edge_batch()
+{
+    static const bool on = [] {
+        const char* e = getenv("SMPLGPU_V32_EDGE_BATCH");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    return on;
+}
+
+// the batched edge kernel keeps V32_EDGE_EPT edges per thread in shared memory: offsets, ok, unc, counts
+static size_t v32_smem_edge_batch(const smplgpu_ctx* ctx)
+{
+    return (size_t)ctx->blob_words * 4
+           + ((size_t)ctx->v32_slots * 12 + (size_t)ctx->v32_ptrees * 3) * sizeof(float) * ctx->v32_threads
+           + (2 * (size_t)V32_EDGE_EPT * ctx->v32_threads + 4) * sizeof(int);
 }
 
 static size_t v32_smem(const smplgpu_ctx* ctx)
@@ -1482,8 +1518,15 @@ static int launch_edges(smplgpu_ctx* ctx, const double* dq0, const double* dq1, 
     }
     int r = ensure_unc(ctx, (size_t)n);
     if (r) return r;
-    CU(cudaMemsetAsync(ctx->d_unc_count, 0, sizeof(int), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_unc_count, 0, 2 * sizeof(int), ctx->stream));   // [0] undecided items, [1] the batch cursor
     const int t32 = ctx->v32_threads;
+    if (!v32_persistent() && v32_edge_batch() && ctx->v32_edge_batch_blocks_per_sm > 0) {
+        const int epb = V32_EDGE_EPT * t32;
+        const int wave = ctx->v32_edge_batch_blocks_per_sm * ctx->sm_count;
+        edges_valid32b_kernel<<<std::min((n + epb - 1) / epb, wave), t32, v32_smem_edge_batch(ctx), ctx->stream>>>(
+            ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq0, dq1, n, dv, dc, ctx->d_unc_list,
+            ctx->d_unc_count, ctx->d_stats);
+    } else
     if (v32_persistent()) {
         const int epb = V32P_EDGES_PER_THREAD * t32;
         edges_valid32p_kernel<<<(n + epb - 1) / epb, t32, v32_smem(ctx), ctx->stream>>>(

@@ -652,6 +652,201 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
     flush_counters(cnt, stats);
 }
 
+// ---- batched persistent form of the edge kernel ----------------------------------------------------------------
+// edges_valid32_kernel gives a block blockDim edges: ~300 round-B items for four warps, so every warp ends its block
+// waiting up to one state check (a third of its round B) for the last puller, and the verdicts leave only after that
+// barrier -- ncu (profiles/r02d_metrics.csv) counts 20 % of the stall samples at block barriers.  Here the grid is one
+// wave of resident blocks that pull BATCHES of V32_EDGE_EPT * blockDim edges from a global cursor (unc_count[1]):
+// round A is pulled 32 edges at a time too, the pool of round B is V32_EDGE_EPT times deeper (the wait for the last
+// puller is the same one state check, now against V32_EDGE_EPT times the work), and there is no tail of half-empty
+// blocks at the end of the grid.  Same verdicts, counts and undecided list (in a different order) as the form above.
+#ifndef V32_EDGE_EPT_N
+#define V32_EDGE_EPT_N 4
+#endif
+constexpr int V32_EDGE_EPT = V32_EDGE_EPT_N;
+constexpr int EDGE_OK = 1 << 30, EDGE_UNC = 1 << 29, EDGE_COUNT = EDGE_UNC - 1;
+
+__global__ void V32_BOUNDS
+edges_valid32b_kernel(const float* __restrict__ blob_g, int blob_words, const DevModel* __restrict__ M,
+                      const uint16_t* __restrict__ df, Grid32 G, const double* __restrict__ q0,
+                      const double* __restrict__ q1, int n, uint8_t* __restrict__ verdict, int* __restrict__ counts,
+                      int* __restrict__ unc_list, int* __restrict__ unc_count, unsigned long long* stats)
+{
+    extern __shared__ float4 smem4[];
+    __shared__ int s_first;      // first edge of the batch
+    __shared__ int s_cursor_a;   // next unclaimed edge of round A
+    __shared__ int s_cursor;     // next unclaimed (edge, waypoint) item of round B
+    __shared__ int s_wsum[32];
+    float* blob = reinterpret_cast<float*>(smem4);
+    copy_blob(blob, blob_g, blob_words);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int dof = M->dof;
+    const int E = V32_EDGE_EPT * (int)blockDim.x;
+    Counters cnt = { 0u, 0u, 0u };
+    __syncthreads();   // blob copied
+    const S32 S = view32(blob);
+    float* slots = blob + blob_words;
+    int* s_off = reinterpret_cast<int*>(slots + ((size_t)S.h->n_slots * 12 + (size_t)S.h->n_ptrees * 3) * blockDim.x);
+    // per edge ONE word: waypoint count | EDGE_OK | EDGE_UNC (shared memory per block decides how many blocks an SM holds,
+    // and these kernels live on resident warps)
+    int* s_edge = s_off + E + 1;
+
+    for (;;) {
+        if (tid == 0) {
+            s_first = atomicAdd(unc_count + 1, E);
+            s_cursor_a = 0;
+            s_cursor = 0;
+            s_off[0] = 0;
+        }
+        __syncthreads();   // also: everyone is done with the previous batch's arrays
+        const int first = s_first;
+        if (first >= n) {
+            break;
+        }
+        const int nb = min(E, n - first);
+
+        // waypoint counts, in double exactly as the reference computes them
+        for (int e = tid; e < E; e += blockDim.x) {
+            int count = 0;
+            if (e < nb) {
+                const double* a = q0 + (size_t)(first + e) * dof;
+                const double* b = q1 + (size_t)(first + e) * dof;
+                double motion = 0.0;
+                for (int v = 0; v < dof; ++v) {
+                    const int ty = M->var_type[v];
+                    double dist;
+                    if (ty == 1) {
+                        dist = fabs(normalize_angle(b[v] - a[v]));
+                        motion += M->var_weight[v] * dist;
+                    } else if (ty == 0) {
+                        dist = fabs(b[v] - a[v]);
+                        motion += M->var_weight[v] * dist;
+                    } else {
+                        dist = fabs(b[v] - a[v]);
+                        motion += dist;
+                    }
+                }
+                if (motion != 0.0) {
+                    count = max(2, (int)ceil(motion / 0.05) + 1);
+                }
+                if (counts != nullptr) {
+                    counts[first + e] = count;
+                }
+            }
+            s_edge[e] = count | EDGE_OK;
+            s_off[e + 1] = 0;
+        }
+        __syncthreads();
+
+        // Round A: the first waypoint of every edge (alpha = 0 is exactly q0), the one the reference checks first too
+        // (collision_space.cpp:561-577), so an edge that starts in collision costs one state check, not `count`
+        for (;;) {
+            int base = 0;
+            if (lane == 0) {
+                base = atomicAdd(&s_cursor_a, 32);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= nb) {
+                break;
+            }
+            const int e = base + lane;
+            const int count = e < nb ? (s_edge[e] & EDGE_COUNT) : 0;
+            if (count > 0) {
+                ++cnt.waypoints;
+                const int r = check_state32(S, M->var_type, df, G, q0 + (size_t)(first + e) * dof,
+                                            q1 + (size_t)(first + e) * dof, 0.0, slots, cnt);
+                s_edge[e] = count | (r != 0 ? EDGE_OK : 0) | (r == 2 ? EDGE_UNC : 0);
+                s_off[e + 1] = r != 0 ? count - 1 : 0;
+            }
+        }
+        __syncthreads();
+
+        // inclusive scan of the survivors' remaining waypoints: V32_EDGE_EPT consecutive entries per thread
+        {
+            int v[V32_EDGE_EPT];
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < V32_EDGE_EPT; ++k) {
+                sum += s_off[1 + tid * V32_EDGE_EPT + k];
+                v[k] = sum;
+            }
+            int x = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) {
+                    x += y;
+                }
+            }
+            if (lane == 31) {
+                s_wsum[warp] = x;
+            }
+            __syncthreads();
+            int woff = 0;
+            for (int w = 0; w < warp; ++w) {
+                woff += s_wsum[w];
+            }
+            const int excl = woff + x - sum;
+#pragma unroll
+            for (int k = 0; k < V32_EDGE_EPT; ++k) {
+                s_off[1 + tid * V32_EDGE_EPT + k] = excl + v[k];
+            }
+        }
+        __syncthreads();
+        const int total = s_off[E];
+
+        // Round B: the remaining waypoints of the surviving edges, flattened over the batch, 32 consecutive items per pull
+        for (;;) {
+            int base = 0;
+            if (lane == 0) {
+                base = atomicAdd(&s_cursor, 32);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= total) {
+                break;
+            }
+            const int item = base + lane;
+            if (item < total) {
+                int lo = 0, hi = E;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_off[mid] <= item) {
+                        lo = mid;
+                    } else {
+                        hi = mid;
+                    }
+                }
+                const int e = lo;
+                // early-out read; a stale 1 (another lane is just clearing it) only costs one redundant waypoint check
+                const int word = *((volatile int*)&s_edge[e]);
+                if (word & EDGE_OK) {
+                    const int w = item - s_off[e] + 1;               // waypoint 0 was round A
+                    const double inv = 1.0 / (double)((word & EDGE_COUNT) - 1); // m_waypoint_count_inv
+                    const double alpha = (double)w * inv;
+                    ++cnt.waypoints;
+                    const int r = check_state32(S, M->var_type, df, G, q0 + (size_t)(first + e) * dof,
+                                                q1 + (size_t)(first + e) * dof, alpha, slots, cnt);
+                    if (r == 0) {
+                        atomicAnd(&s_edge[e], ~EDGE_OK);
+                    } else if (r == 2) {
+                        atomicOr(&s_edge[e], EDGE_UNC);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < E; e += blockDim.x) {
+            bool push = false;
+            if (e < nb) {
+                const int word = s_edge[e];
+                verdict[first + e] = (word & EDGE_OK) ? 1 : 0;
+                push = (word & EDGE_OK) && (word & EDGE_UNC);
+            }
+            append_uncertain(push, first + e, unc_list, unc_count, stats);
+        }
+    }
+    flush_counters(cnt, stats);
+}
+
 // ---- lane-persistent form -------------------------------------------------------------------------------------
 // In the kernels above a lane whose state dies at link 3 idles until the slowest lane of its warp has walked the
 // whole chain: ncu counted 14 (states) / 19 (edges) active lanes per issued instruction.  Here the link index is

@@ -775,9 +775,10 @@ class RefCollisionScene:
             raise RuntimeError("refcc_post_process: %d" % n)
         return out[:n].copy()
 
-    def plan(self, scene, start, goal_xyz, params, max_path=4096):
+    def plan(self, scene, start, goal_xyz, params, max_path=4096, lazy=False):
         """One query through the reference's ManipLattice + BfsHeuristic + ARAStar (oracle/ref_planner_shim.cpp);
-        same result dict as OracleScene.plan."""
+        same result dict as OracleScene.plan.  lazy: GetLazySuccs / GetTrueCost under the reference's LazyARAStar
+        instead (the dict then also holds `evaluations`, the GetTrueCost calls)."""
         start = np.ascontiguousarray(start, dtype=np.float64)
         goal = np.ascontiguousarray(goal_xyz, dtype=np.float64)
         res = np.ascontiguousarray(params.resolutions, dtype=np.float64)
@@ -789,7 +790,8 @@ class RefCollisionScene:
         summary = np.zeros(8, np.int32)
         path = np.zeros(max_path, np.int32)
         pstates = np.zeros((max_path, len(start)), np.float64)
-        rc = self.R.refcc_plan(self.h, scene.chain_root.encode(), scene.chain_tip.encode(), scene.planning_link.encode(),
+        fn = self.R.refcc_plan_lazy if lazy else self.R.refcc_plan
+        rc = fn(self.h, scene.chain_root.encode(), scene.chain_tip.encode(), scene.planning_link.encode(),
                                _dp(T), _dp(off), C.c_double(scene.inflation_radius), int(scene.cost_per_cell),
                                _dp(start), _dp(goal), _dp(res), _dp(prims), _bp(flags), len(prims),
                                int(params.use_short_dist), C.c_double(params.short_dist_thresh),
@@ -798,9 +800,12 @@ class RefCollisionScene:
         if rc != 0:
             raise RuntimeError("refcc_plan: the reference refused step %d" % -rc)
         n = int(summary[3])
-        return dict(path_states=pstates[:min(int(summary[5]), max_path)].copy(), success=bool(summary[0]),
-                    expansions=int(summary[1]), cost=int(summary[2]), path_ids=path[:min(n, max_path)].copy(),
-                    num_states=int(summary[4]))
+        out = dict(path_states=pstates[:min(int(summary[5]), max_path)].copy(), success=bool(summary[0]),
+                   expansions=int(summary[1]), cost=int(summary[2]), path_ids=path[:min(n, max_path)].copy(),
+                   num_states=int(summary[4]))
+        if lazy:
+            out["evaluations"] = int(self.R.refcc_last_lazy_evaluations())
+        return out
 
 
 class _BfsBase:

@@ -26,7 +26,7 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def dropin_plan(lib, ctx, scene, start, goal, params, max_path=4096, batched=False):
+def dropin_plan(lib, ctx, scene, start, goal, params, max_path=4096, batched=False, lazy=False):
     dof = scene.dof
     start = np.ascontiguousarray(start, np.float64)
     goal = np.ascontiguousarray(goal, np.float64)
@@ -40,7 +40,8 @@ def dropin_plan(lib, ctx, scene, start, goal, params, max_path=4096, batched=Fal
     summary = np.zeros(8, np.int32)
     path = np.zeros(max_path, np.int32)
     pstates = np.zeros((max_path, dof), np.float64)
-    rc = lib.refdrop_plan(ctx.h, scene.robot_path.encode(), scene.group.encode(), ",".join(scene.planning_joints).encode(),
+    fn = lib.refdrop_plan_lazy if lazy else lib.refdrop_plan
+    rc = fn(ctx.h, scene.robot_path.encode(), scene.group.encode(), ",".join(scene.planning_joints).encode(),
                           scene.planning_link.encode(), _p(origin, C.c_double), C.c_double(scene.res), _p(dims, C.c_int32),
                           C.c_double(scene.inflation_radius), int(scene.cost_per_cell),
                           _p(start, C.c_double), _p(goal, C.c_double), _p(off, C.c_double),
@@ -51,6 +52,7 @@ def dropin_plan(lib, ctx, scene, start, goal, params, max_path=4096, batched=Fal
     assert rc == 0, "refdrop_plan refused step %d: %s" % (-rc, ctx.L.smplgpu_last_error(ctx.h))
     n = int(summary[3])
     dropin_plan.last_batched = (int(summary[6]), int(summary[7]))
+    dropin_plan.last_evaluations = int(lib.refdrop_last_lazy_evaluations()) if lazy else 0
     return [int(summary[0]), int(summary[1]), int(summary[2]), int(summary[4]), [int(i) for i in path[:n]]]
 
 
@@ -137,5 +139,38 @@ def test_unchanged_reference_planner_with_expansion_cache_is_one_launch_per_expa
         # few states ARA* asks about out of expansion order: 6616 records for 6491 expansions on the B200)
         assert cache_launches <= 1.05 * expansions + 4 * len(starts)
         assert launches <= cache_launches + 40 * len(starts)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libref_dropin.so not built")
+def test_reference_lazy_planner_over_gpu_plugins_returns_the_reference_plans():
+    """SURVEY 8f row 2, second half: the reference's LAZY successors -- ManipLattice::GetLazySuccs / GetTrueCost
+    (manip_lattice.cpp:1012-1167) under its in-tree LazyARAStar (search/lazy_arastar.cpp), all compiled from the
+    reference -- with the product's adapters answering, first call by call, then with the shared ExpansionCache (a
+    GetTrueCost on a parent expanded earlier re-runs that parent's record: one launch per evaluated edge group).  Plans,
+    expansion and evaluation counts must equal the all-reference run's (tests/golden/plans_reference_lazy.json)."""
+    import time
+    lib = C.CDLL(LIB)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "plans_reference_lazy.json")))
+    scene, attach, params, starts, goals = plan_cases()["pr2_tabletop"]
+    ctx, tables = api.setup_context(scene)
+    try:
+        for mode in (0, 2):
+            dropin_plan(lib, ctx, scene, starts[1], goals[1], params, batched=mode, lazy=True)   # warm-up
+            l0 = ctx.launch_count()
+            t0 = time.perf_counter()
+            expansions = evaluations = solved = 0
+            for s, g, want in zip(starts, goals, gold["pr2_tabletop"]):
+                got = dropin_plan(lib, ctx, scene, s, g, params, batched=mode, lazy=True)
+                assert got + [dropin_plan.last_evaluations] == want
+                expansions += got[1]
+                evaluations += dropin_plan.last_evaluations
+                solved += got[0]
+            secs = time.perf_counter() - t0
+            print("reference LazyARAStar over the GPU plug-ins (%s), 8 queries: %d expansions + %d edge evaluations in "
+                  "%.3f s, %d launches" % ("expansion cache" if mode == 2 else "one call per question", expansions,
+                                           evaluations, secs, ctx.launch_count() - l0))
+            assert solved >= 4
     finally:
         ctx.close()

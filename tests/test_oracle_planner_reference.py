@@ -72,6 +72,24 @@ def test_committed_golden_plans_are_the_reference_builds():
         assert summary(r.plan(scene, np.array(s), np.array(g), params)) == res[:5]
 
 
+@needs_ref
+def test_committed_lazy_golden_plans_are_the_reference_builds():
+    """The reference's lazy successors -- ManipLattice::GetLazySuccs / GetTrueCost (manip_lattice.cpp:1012-1167) under its
+    in-tree LazyARAStar (search/lazy_arastar.cpp), compiled from the reference's sources -- reproduce the committed
+    fixture (tools/gen_golden_plans_reference.py).  The GPU side of this row is tests/test_gpu_dropin.py: the same
+    reference code with the product's adapters answering."""
+    gold = json.load(open(os.path.join(GOLD, "plans_reference_lazy.json")))
+    scene, attach, params, starts, goals = plan_cases()["pr2_tabletop"]
+    r = make_reference(scene, attach)
+    lazier = 0
+    for s, g, want in list(zip(starts, goals, gold["pr2_tabletop"]))[:4]:
+        p = r.plan(scene, s, g, params, lazy=True)
+        assert summary(p) + [p["evaluations"]] == want
+        # laziness: far fewer edges evaluated than an eager expansion generates (~65 per expansion)
+        lazier += p["evaluations"] < 4 * max(1, p["expansions"])
+    assert lazier == 4
+
+
 def test_restatement_plans_equal_golden_reference_outputs():
     gold = json.load(open(os.path.join(GOLD, "plans_reference.json")))
     for name, (scene, attach, params, starts, goals) in plan_cases().items():
