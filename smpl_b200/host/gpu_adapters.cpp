@@ -49,8 +49,26 @@ bool ExpansionCache::expand(const double* q)
     m_info = info;
     m_n = m_prims + 1;
     m_hint = 0;
+    m_has_pending = false;
     m_epoch = smplgpu_scene_epoch(m_ctx);
     return true;
+}
+
+// b == a + delta for some primitive (the addition the device does)
+bool ExpansionCache::isSuccessorOf(const double* a, const double* b) const
+{
+    for (int p = 0; p < m_prims; ++p) {
+        const double* d = &m_deltas[(size_t)p * m_dof];
+        bool same = true;
+        for (int j = 0; j < m_dof && same; ++j) {
+            const double s = d[j] + a[j];
+            same = std::memcmp(&s, &b[j], sizeof(double)) == 0;
+        }
+        if (same) {
+            return true;
+        }
+    }
+    return false;
 }
 
 const smplgpu_succ_info* ExpansionCache::find(const double* q)
@@ -65,6 +83,10 @@ const smplgpu_succ_info* ExpansionCache::find(const double* q)
         if (std::memcmp(m_info[i].state, q, bytes) == 0) {
             m_hint = i;
             ++m_hits;
+            if (i > 0) {
+                m_pending.assign(q, q + m_dof);
+                m_has_pending = true;
+            }
             return &m_info[i];
         }
     }
@@ -76,7 +98,23 @@ const smplgpu_succ_info* ExpansionCache::get(const double* q)
     if (const smplgpu_succ_info* r = find(q)) {
         return r;
     }
-    if (!m_ok || !expand(q)) {
+    if (!m_ok) {
+        return nullptr;
+    }
+    // A search that expands a state right after its parent asks about that state first -- answered from the parent's
+    // record, as a successor entry -- and then about ITS successors, which no record holds yet: the state to expand is
+    // the one found last, not the successor asked about (a lazy search asks nothing else in between: without this,
+    // GetLazySuccs cost one launch per successor).
+    if (m_has_pending && isSuccessorOf(m_pending.data(), q)) {
+        const std::vector<double> parent_state = m_pending;
+        if (!expand(parent_state.data())) {
+            return nullptr;
+        }
+        if (const smplgpu_succ_info* r = find(q)) {
+            return r;
+        }
+    }
+    if (!expand(q)) {
         return nullptr;
     }
     return &m_info[0];
@@ -103,16 +141,7 @@ const smplgpu_succ_info* ExpansionCache::edge(const double* a, const double* b)
     if (m_n == 0 || std::memcmp(m_info[0].state, a, bytes) != 0) {
         // a is not the current parent: expanding it pays off only if b is one of its successors, i.e.
         // b == a + delta for some primitive (the addition the device will do)
-        bool is_succ = false;
-        for (int p = 0; p < m_prims && !is_succ; ++p) {
-            const double* d = &m_deltas[(size_t)p * m_dof];
-            bool same = true;
-            for (int j = 0; j < m_dof && same; ++j) {
-                const double s = d[j] + a[j];
-                same = std::memcmp(&s, &b[j], sizeof(double)) == 0;
-            }
-            is_succ = same;
-        }
+        const bool is_succ = isSuccessorOf(a, b);
         if (!is_succ || !expand(a)) {
             return nullptr;
         }

@@ -70,6 +70,9 @@ private:
     std::vector<double> m_deltas;
     const smplgpu_succ_info* m_info = nullptr;   // [m_n] records of the current parent, owned by the context
     int m_n = 0, m_hint = 0;
+    std::vector<double> m_pending;   // the last state found as a SUCCESSOR entry: the likely next parent (see get())
+    bool m_has_pending = false;
+    bool isSuccessorOf(const double* a, const double* b) const;
     int64_t m_epoch = -1;
     long long m_launches = 0, m_hits = 0;
     bool valid();
