@@ -364,10 +364,11 @@ def plan_leg(api, scenes, sharding, dist, torch, dev, scene, starts_all, goals_a
     n_thr = max(n_thr, (args.plan_concurrent + 511) // 512)
     pctxs = [pctx] + [api.clone_context(pctx, scene, ptables, device=local_rank) for _ in range(n_thr - 1)]
     per_ctx = max(1, (min(args.plan_concurrent, max(1, len(mine))) + n_thr - 1) // n_thr)
+    # warm-up = the same call on the first batch of queries, with the SAME expansion bound: the lattices and the BFS bank
+    # are scene-level allocations sized by (concurrent queries, expansion bound) and kept across calls; a warm-up with a
+    # smaller bound made the timed call re-allocate ~5 GB per context (0.1 to 1.2 s of its "setup", run to run)
     wq = min(len(mine), per_ctx * n_thr)
-    wparams = scenes.PlanParams(scene.dof)
-    wparams.max_expansions = 20
-    api.plan_batch(pctxs, scene, ptables, wparams, starts_all[mine][:wq], goals_all[mine][:wq], max_concurrent=per_ctx)
+    api.plan_batch(pctxs, scene, ptables, params, starts_all[mine][:wq], goals_all[mine][:wq], max_concurrent=per_ctx)
     barrier()
     psampler = ClockSampler(local_rank)
     if rank == 0:

@@ -445,9 +445,9 @@ bfs_levels_kernel(const __grid_constant__ BfsGrid g, int max_levels)
 
 // The same wavefront as ONE LAUNCH PER LEVEL, for the planner's banks when they are run behind the caller's back
 // (smplgpu_bfs_bank_run_slots_async) while other contexts' expansion rounds share the GPU.  A cooperative launch
-// starts only when ALL its blocks fit at once; with five other contexts feeding small kernels without pause that
-// moment can be seconds away (measured: a 2 s stall in one of six runs).  Launches of one level
-// need no co-residency, interleave with anything, and cost ~2 us each against tens of milliseconds per bank run.
+// starts only when ALL its blocks fit at once; launches of one level need no co-residency, interleave with anything,
+// and cost ~2 us each against tens of milliseconds per bank run.  (Opt-in, SMPLGPU_BANK_STEPWISE=1 with the level
+// kernel forced: the banks run on the tile kernel, whose asynchronous form is stepwise by default.)
 // ctrl[12] = sticky "finished" flag (set by the first level that finds the previous one empty), mirrored into
 // *done_host (page-locked) so that the host can poll without a synchronisation; ctrl[0] = levels run.
 __global__ void __launch_bounds__(BFS_THREADS, 1)

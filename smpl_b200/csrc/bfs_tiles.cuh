@@ -158,7 +158,8 @@ constexpr int TILE_RPT_LARGE = 4;                             // extended z-rows
 //     waits for the slowest block).  The choice for large grids (400^3: 2.74 ms against 3.17 ms).
 template <int TILE_RPT>
 __global__ void __launch_bounds__(TILE_THREADS / TILE_RPT, TILE_RPT)
-bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsTiles t, int max_supersteps)
+bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsTiles t, int max_supersteps, int first_step,
+                 int stepwise, volatile int* done_host)
 {
     __shared__ unsigned long long sF[2][TILE_THREADS];   // frontier rows, double-buffered by level
     __shared__ uint8_t sZ[2][TILE_E + 2];                // z-row has frontier cells (per buffer); [0] and [33] stay 0
@@ -198,7 +199,15 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
     }
     __syncthreads();
 
-    int n = 0;
+    // stepwise: ONE super-step per launch (first_step), no grid barrier and therefore no need for all blocks to be
+    // resident at once -- for runs queued behind the caller's back while other contexts' kernels share the GPU (a
+    // cooperative launch waits until every block fits at the same moment).  Same planner throughput as the cooperative
+    // form (2320-2460 vs 2370-2410 queries/s), ~19 launches per 150^3 bank run.
+    // ctrl[12] = sticky "finished" flag, mirrored into *done_host (page-locked) for the host's poll.
+    if (stepwise && __ldcg(&g.ctrl[12]) != 0) {
+        return;
+    }
+    int n = first_step;
     for (; n < max_supersteps; ++n) {
         const int p = n & 1;
         const uint32_t* __restrict__ fcur = t.tf[p];
@@ -213,6 +222,12 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
         int taken = 0;
 #endif
         if (q_len == 0) {
+            if (stepwise && blockIdx.x == 0 && tid == 0) {
+                g.ctrl[12] = 1;
+                if (done_host != nullptr) {
+                    *done_host = 1;
+                }
+            }
             break;   // no tile has a frontier left (every block reads the same length)
         }
         if (blockIdx.x == 0 && tid == 0) {
@@ -473,6 +488,9 @@ bfs_tiles_kernel(const __grid_constant__ BfsGrid g, const __grid_constant__ BfsT
             atomicAdd(&bfs_dbg[3][n], (unsigned long long)(b0 - ss0));
         }
 #endif
+        if (stepwise) {
+            break;   // the next launch is the barrier
+        }
         grid_barrier(bar, (unsigned int)(n + 1) * gridDim.x);
 #ifdef SMPLGPU_BFS_STATS
         if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(t.qn + 14), (unsigned long long)(clock64() - b0));

@@ -116,8 +116,10 @@ struct smplgpu_ctx
     // asynchronous bank runs go level by level (bfs_level_step_kernel): launched in chunks, continued when a chunk
     // ends without the device having raised *bank_done (page-locked, mapped)
     volatile int* bank_done = nullptr;
-    int bank_next_level = 0;              // first level of the next chunk; 0 = the run in flight is a cooperative one
+    int bank_next_level = 0;              // first level / super-step of the next chunk; 0 = the run in flight is a cooperative one
     long long bank_level_cap = 0;
+    int bank_step_tiles = 0;              // the stepwise run in flight: 0 = one level per launch, else the tile kernel's TILE_RPT
+    int bank_step_blocks = 0;
     std::vector<int32_t> staged_slots, staged_seeds;
     unsigned long long* d_stats = nullptr;
     unsigned long long h_stats[4] = { 0, 0, 0, 0 };
@@ -2147,12 +2149,11 @@ static int wall_threshold(const smplgpu_ctx* ctx, double inflation_radius)
     return kmax;
 }
 
-// Asynchronous bank runs are one cooperative launch per run, taking turns per device (default), or -- with
-// SMPLGPU_BANK_STEPWISE=1 -- one launch per level (bfs_level_step_kernel): no co-residency needed, the contexts' runs
-// overlap.  Measured on one B200, 6 contexts x 342 queries: cooperative 1750-2050 plan queries/s
-// and 3800-4900 UBR1 queries/s, with ONE run in about ten stalling for 2 s (a cooperative launch starts only when all
-// its blocks fit at once, and five other contexts keep feeding small kernels); level by level 1340-2010 and 3000-3470
-// with a worst stall of 0.9 s.  The cooperative form stays the default for its average; its stream has high priority.
+// With the LEVEL kernel forced for the banks (smplgpu_bfs_set_mode / SMPLGPU_BFS_MODE=1), asynchronous bank runs are one
+// cooperative launch per run, taking turns per device, or -- with SMPLGPU_BANK_STEPWISE=1 -- one launch per level
+// (bfs_level_step_kernel).  Measured on one B200, 6 contexts x 342 queries: cooperative 1960-2040 plan queries/s, level
+// by level 1340-2010 (142 launches per run and context).  The default for the banks is the tile kernel, one launch per
+// super-step (run_grid): 2320-2460.
 static bool bank_stepwise()
 {
     static const bool on = [] {
@@ -2163,10 +2164,29 @@ static bool bank_stepwise()
 }
 
 constexpr int BANK_LEVEL_CHUNK = 128;   // level launches queued at a time (a 150^3 tabletop bank needs ~140 levels)
+constexpr int BANK_TILE_CHUNK = 24;     // super-step launches queued at a time (TILE_K levels each)
 
 static int launch_bank_level_chunk(smplgpu_ctx* ctx, cudaStream_t stream)
 {
     BfsGrid& g = ctx->bank;
+    if (ctx->bank_step_tiles != 0) {
+        // the tile kernel, one super-step per launch; bank_next_level counts super-steps from 1
+        const BfsTiles& t = ctx->bank_tiles;
+        const bool large = ctx->bank_step_tiles == TILE_RPT_LARGE;
+        const int threads = large ? TILE_THREADS / TILE_RPT_LARGE : TILE_THREADS;
+        for (int k = 0; k < BANK_TILE_CHUNK; ++k) {
+            const int step = ctx->bank_next_level - 1 + k;
+            if (large) {
+                bfs_tiles_kernel<TILE_RPT_LARGE><<<ctx->bank_step_blocks, threads, 0, stream>>>(g, t, step + 1, step, 1, ctx->bank_done);
+            } else {
+                bfs_tiles_kernel<1><<<ctx->bank_step_blocks, threads, 0, stream>>>(g, t, step + 1, step, 1, ctx->bank_done);
+            }
+        }
+        ctx->launches += BANK_TILE_CHUNK;
+        ctx->bank_next_level += BANK_TILE_CHUNK;
+        CU(cudaGetLastError());
+        return 0;
+    }
     const int groups = (g.rows + 7) / 8;
     const int blocks = std::max(1, std::min(groups, 2 * ctx->sm_count));
     for (int k = 0; k < BANK_LEVEL_CHUNK; ++k) {
@@ -2178,6 +2198,20 @@ static int launch_bank_level_chunk(smplgpu_ctx* ctx, cudaStream_t stream)
     return 0;
 }
 
+// which kernel a bank run uses (a single grid always takes the tile kernel unless a mode is forced)
+static bool bank_uses_tiles(const smplgpu_ctx* ctx)
+{
+    return ctx->bfs_mode == SMPLGPU_BFS_TILES || ctx->bfs_mode == SMPLGPU_BFS_AUTO;
+}
+
+// asynchronous bank runs launch step by step (no co-residency needed, the contexts' runs overlap): always with the tile
+// kernel, with the level kernel only on request (SMPLGPU_BANK_STEPWISE=1)
+static bool bank_async_stepwise(const smplgpu_ctx* ctx)
+{
+    static const bool cooperative = getenv("SMPLGPU_BANK_COOPERATIVE") != nullptr && atoi(getenv("SMPLGPU_BANK_COOPERATIVE")) != 0;
+    return (bank_uses_tiles(ctx) && !cooperative) || (!bank_uses_tiles(ctx) && bank_stepwise());
+}
+
 // reset + seed + all levels on one grid; seeds already on the device (padded-grid-free coordinates)
 static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_seeds, int n_seeds, int* levels_out,
                     const uint8_t* d_slot_mask = nullptr, int slot_dz = 1, cudaStream_t stream = nullptr,
@@ -2187,13 +2221,14 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
     if (d_seed_count == nullptr) d_seed_count = ctx->d_seed_count;
     const int total = (int)words;
     BfsTiles& t = (&g == &ctx->bank) ? ctx->bank_tiles : ctx->bfs_tiles;
-    // AUTO: the tile kernel for a single grid, the level kernel for the stacked planner banks.  In isolation the tile
-    // kernel now does a bank query in 0.089 ms against the level kernel's 0.148 ms (tools/bank_bfs_time.py), but inside
-    // the planner -- bank runs of several contexts taking turns while the other contexts' expansion rounds share the
-    // SMs -- it gained nothing at 6 contexts (1808 vs 1940 queries/s) and at 4 contexts a cooperative launch of 444
-    // resident blocks waited seconds for room (setup 3.4 s): its blocks fill the register file of every SM they sit on.
+    // AUTO: the tile kernel everywhere.  For the stacked planner banks it does a query in 0.085 ms against the level
+    // kernel's 0.157 ms (tools/bank_bfs_time.py) and, inside the planner, 2320-2460 against 1960-2040 plan queries/s
+    // (DESIGN.md section 7).  A run queued behind the caller's back goes ONE SUPER-STEP PER LAUNCH: a cooperative launch
+    // of blocks that fill the register file of every SM they sit on has to wait until all of them fit at once, which
+    // nothing guarantees while other contexts' expansion rounds keep arriving; SMPLGPU_BANK_COOPERATIVE=1 restores the
+    // single cooperative launch (same throughput: 2370-2410).
     const bool single = &g != &ctx->bank;
-    const bool tiles = ctx->bfs_mode == SMPLGPU_BFS_TILES || (ctx->bfs_mode == SMPLGPU_BFS_AUTO && single);
+    const bool tiles = single ? ctx->bfs_mode != SMPLGPU_BFS_LEVELS : bank_uses_tiles(ctx);
     {
         // one warp per 32 bitmap words; at least one thread per row for the candidate stamps
         const long long threads = std::max<long long>(g.rows, std::min<long long>((long long)total, 148LL * 2048 * 4));
@@ -2243,9 +2278,28 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
         const int tiles_per_block = warp_tiles ? WTILE_WARPS : 1;
         const int blocks = std::max(1, std::min(sms * per_sm, (t.ntiles + tiles_per_block - 1) / tiles_per_block));
         int max_steps = (int)std::min<long long>(cap / TILE_K + 2, 0x7FFFFFFFLL / blocks - 1);
-        void* args[] = { (void*)&g, (void*)&t, (void*)&max_steps };
-        CU(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(threads), args, 0, stream));
-        ++ctx->launches;
+        if (async_run && &g == &ctx->bank && !warp_tiles && rpt != 2 && bank_async_stepwise(ctx)) {
+            // behind the caller's back: one launch per super-step, first chunk here, the rest from
+            // smplgpu_bfs_bank_run_done / _wait
+            if (!ctx->bank_done) {
+                int* p = nullptr;
+                CU(cudaHostAlloc((void**)&p, 64, cudaHostAllocMapped));
+                ctx->bank_done = p;
+            }
+            *ctx->bank_done = 0;
+            ctx->bank_next_level = 1;
+            ctx->bank_level_cap = max_steps;
+            ctx->bank_step_tiles = large ? TILE_RPT_LARGE : 1;
+            ctx->bank_step_blocks = std::max(1, std::min(ctx->sm_count * (large ? TILE_RPT_LARGE : 1), t.ntiles));
+            const int r = launch_bank_level_chunk(ctx, stream);
+            if (r) return r;
+        } else {
+            int first_step = 0, stepwise = 0;
+            volatile int* no_flag = nullptr;
+            void* args[] = { (void*)&g, (void*)&t, (void*)&max_steps, (void*)&first_step, (void*)&stepwise, (void*)&no_flag };
+            CU(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(threads), args, 0, stream));
+            ++ctx->launches;
+        }
     } else if (&g == &ctx->bank && stream == ctx->bfs_stream && bank_stepwise()) {
         // behind the caller's back: one launch per level (bfs_level_step_kernel), first chunk here, the rest from
         // smplgpu_bfs_bank_run_done / _wait
@@ -2257,6 +2311,7 @@ static int run_grid(smplgpu_ctx* ctx, BfsGrid& g, size_t words, const int* d_see
         *ctx->bank_done = 0;
         ctx->bank_next_level = 1;
         ctx->bank_level_cap = std::min<long long>(cap, 1LL << 22);
+        ctx->bank_step_tiles = 0;
         const int r = launch_bank_level_chunk(ctx, stream);
         if (r) return r;
     } else {
@@ -2622,8 +2677,8 @@ static int launch_staged_bank_run(smplgpu_ctx* ctx)
 
 static bool take_bank_turn(smplgpu_ctx* ctx)
 {
-    if (bank_stepwise()) {
-        return true;   // level-by-level runs need no co-residency: the contexts' runs simply overlap
+    if (bank_async_stepwise(ctx)) {
+        return true;   // step-by-step runs need no co-residency: the contexts' runs simply overlap
     }
     int expected = 0;
     return g_bank_turn[ctx->device & 63].compare_exchange_strong(expected, 1);
