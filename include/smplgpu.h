@@ -53,7 +53,7 @@ extern "C" {
 /* Which wavefront kernel runs BFS_3D (smplgpu_bfs_set_mode); distances are identical. */
 #define SMPLGPU_BFS_TILES  0   /* 8 levels per grid barrier on shared-memory tiles (bfs_tiles.cuh): latency-bound grids */
 #define SMPLGPU_BFS_LEVELS 1   /* one level per grid barrier, sparse (row, word) items (bfs.cuh): throughput-bound grids */
-#define SMPLGPU_BFS_AUTO   2   /* default: tiles for a single grid, levels for the stacked planner banks */
+#define SMPLGPU_BFS_AUTO   2   /* default: the tile kernel (bank runs queued asynchronously: one launch per super-step) */
 
 #define SMPLGPU_PRECISION_CERTIFIED_F32 0   /* default */
 #define SMPLGPU_PRECISION_EXACT_F64     1

@@ -62,6 +62,7 @@ struct smplgpu_ctx
     int* d_prim = nullptr; size_t prim_cap = 0;     // bytes; primitive ids of two chunks in flight
     double* d_deltas = nullptr; size_t deltas_cap = 0;
     int* d_unc_list = nullptr; size_t unc_cap = 0;  // ints
+    int* d_unc_mask = nullptr;                      // [unc_cap] per edge: which waypoints are undecided (edges_valid32_kernel)
     int* d_unc_count = nullptr;
 
     // distance field
@@ -396,7 +397,7 @@ void smplgpu_destroy(smplgpu_ctx* ctx)
     free_grid(ctx->bank);
     free_tiles(ctx->bank_tiles);
     cudaFree(ctx->d_model); cudaFree(ctx->d_stats); cudaFree(ctx->d_seed_count); cudaFree(ctx->d_df);
-    cudaFree(ctx->d_blob); cudaFree(ctx->d_unc_list); cudaFree(ctx->d_unc_count);
+    cudaFree(ctx->d_blob); cudaFree(ctx->d_unc_list); cudaFree(ctx->d_unc_mask); cudaFree(ctx->d_unc_count);
     cudaFree(ctx->d_prim); cudaFree(ctx->d_deltas);
     cudaFree(ctx->d_q0); cudaFree(ctx->d_q1); cudaFree(ctx->d_verdict); cudaFree(ctx->d_counts); cudaFree(ctx->d_misc); cudaFree(ctx->d_vox);
     for (int i = 0; i < 2; ++i) {
@@ -1458,8 +1459,10 @@ static int ensure_unc(smplgpu_ctx* ctx, size_t n)
         return 0;
     }
     if (ctx->d_unc_list) { CU(cudaFree(ctx->d_unc_list)); ctx->d_unc_list = nullptr; ctx->unc_cap = 0; }
+    if (ctx->d_unc_mask) { CU(cudaFree(ctx->d_unc_mask)); ctx->d_unc_mask = nullptr; }
     const size_t cap = std::max(n, (size_t)1 << 16);
     CU(cudaMalloc(&ctx->d_unc_list, cap * sizeof(int)));
+    CU(cudaMalloc(&ctx->d_unc_mask, cap * sizeof(int)));
     ctx->unc_cap = cap;
     return 0;
 }
@@ -1524,6 +1527,7 @@ static int launch_edges(smplgpu_ctx* ctx, const double* dq0, const double* dq1, 
     if (r) return r;
     CU(cudaMemsetAsync(ctx->d_unc_count, 0, 2 * sizeof(int), ctx->stream));   // [0] undecided items, [1] the batch cursor
     const int t32 = ctx->v32_threads;
+    bool masked = false;   // the kernel recorded which waypoints of an undecided edge are undecided
     if (!v32_persistent() && v32_edge_batch() && ctx->v32_edge_batch_blocks_per_sm > 0) {
         const int epb = V32_EDGE_EPT * t32;
         const int wave = ctx->v32_edge_batch_blocks_per_sm * ctx->sm_count;
@@ -1537,13 +1541,17 @@ static int launch_edges(smplgpu_ctx* ctx, const double* dq0, const double* dq1, 
             ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq0, dq1, n, dv, dc, ctx->d_unc_list,
             ctx->d_unc_count, ctx->d_stats);
     } else
-    edges_valid32_kernel<<<(n + t32 - 1) / t32, t32, v32_smem(ctx), ctx->stream>>>(
-        ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq0, dq1, n, dv, dc, ctx->d_unc_list,
-        ctx->d_unc_count, ctx->d_stats);
+    {
+        edges_valid32_kernel<<<(n + t32 - 1) / t32, t32, v32_smem(ctx), ctx->stream>>>(
+            ctx->d_blob, ctx->blob_words, ctx->d_model, ctx->d_df, ctx->grid32, dq0, dq1, n, dv, dc, ctx->d_unc_list,
+            ctx->d_unc_count, ctx->d_stats, ctx->d_unc_mask);
+        masked = true;
+    }
     if (warp_resolve()) {
         const int blocks = std::max(1, std::min((n / 64 + RESOLVE_WARPS - 1) / RESOLVE_WARPS + 1, 8 * ctx->sm_count));
         edges_resolve_kernel<<<blocks, 32 * RESOLVE_WARPS, 0, ctx->stream>>>(
-            ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, n, dv, ctx->d_unc_list, ctx->d_unc_count);
+            ctx->d_model, ctx->d_df, ctx->grid, dq0, dq1, n, dv, ctx->d_unc_list, ctx->d_unc_count,
+            masked ? ctx->d_unc_mask : nullptr);
     } else {
         const int per_block = std::max(1, vt / 4);
         const int blocks = std::max(1, std::min((n + per_block - 1) / per_block, 2 * ctx->sm_count));

@@ -521,7 +521,8 @@ __global__ void V32_BOUNDS
 edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const DevModel* __restrict__ M,
                      const uint16_t* __restrict__ df, Grid32 G, const double* __restrict__ q0,
                      const double* __restrict__ q1, int n, uint8_t* __restrict__ verdict, int* __restrict__ counts,
-                     int* __restrict__ unc_list, int* __restrict__ unc_count, unsigned long long* stats)
+                     int* __restrict__ unc_list, int* __restrict__ unc_count, unsigned long long* stats,
+                     int* __restrict__ unc_mask)
 {
     extern __shared__ float4 smem4[];
     __shared__ int s_cursor;   // next unclaimed (edge, waypoint) item of round B
@@ -637,7 +638,7 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
                 if (r == 0) {
                     atomicAnd(&s_ok[e], 0);
                 } else if (r == 2) {
-                    atomicOr(&s_unc[e], 1);
+                    atomicOr(&s_unc[e], 1 << min(w, 31));   // WHICH waypoints the double pass has to look at (31: "31 and up")
                 }
             }
         }
@@ -647,6 +648,9 @@ edges_valid32_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
     if (i < n) {
         verdict[i] = s_ok[tid] ? 1 : 0;
         push = s_ok[tid] && s_unc[tid];
+        if (push && unc_mask != nullptr) {
+            unc_mask[i] = s_unc[tid];
+        }
     }
     append_uncertain(push, i, unc_list, unc_count, stats);
     flush_counters(cnt, stats);

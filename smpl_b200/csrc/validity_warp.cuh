@@ -174,11 +174,14 @@ states_resolve_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict
     }
 }
 
-// the edges on `list`, a warp each: every waypoint in turn until one fails (collision_space.cpp:538-581)
+// the edges on `list`, a warp each: the waypoints the single-precision pass could not decide (bit min(w, 31) of
+// unc_mask[edge]; every waypoint when there is no mask), in turn until one fails (collision_space.cpp:538-581) -- the
+// others were found valid there, or the edge would not be on the list
 __global__ void __launch_bounds__(32 * RESOLVE_WARPS)
 edges_resolve_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict__ df, GridParams G,
                      const double* __restrict__ q0, const double* __restrict__ q1, int n,
-                     uint8_t* __restrict__ verdict, const int* __restrict__ list, const int* __restrict__ list_n)
+                     uint8_t* __restrict__ verdict, const int* __restrict__ list, const int* __restrict__ list_n,
+                     const int* __restrict__ unc_mask)
 {
     __shared__ double sT[RESOLVE_WARPS][MAX_LINKS * 12];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -187,6 +190,7 @@ edges_resolve_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict_
     const int dof = M->dof;
     for (int k = (int)blockIdx.x * RESOLVE_WARPS + warp; k < total; k += n_warps) {
         const int i = list[k];
+        const unsigned mask = unc_mask != nullptr ? (unsigned)unc_mask[i] : 0xFFFFFFFFu;
         const double* a = q0 + (size_t)i * dof;
         const double* b = q1 + (size_t)i * dof;
         // RobotMotionCollisionModel::getMaxSphereMotion + setWaypointCount (every lane, same value)
@@ -208,6 +212,9 @@ edges_resolve_kernel(const DevModel* __restrict__ M, const uint16_t* __restrict_
         bool ok = true;
         const double inv = count > 1 ? 1.0 / (double)(count - 1) : 0.0;
         for (int w = 0; w < count && ok; ++w) {
+            if (!((mask >> min(w, 31)) & 1u)) {
+                continue;   // decided (valid) in single precision
+            }
             ok = check_state_warp(M, df, G, a, b, (double)w * inv, sT[warp], lane);
             __syncwarp();
         }
