@@ -76,6 +76,8 @@ def gpu_lib():
         L.smplgpu_set_distance_field_dev.argtypes = [vp, vp, i, i, i, dp, d, i, d]
         L.smplgpu_build_distance_field.argtypes = [vp, ip, i, i, i, i, dp, d, d, d]
         L.smplgpu_download_distance_field.argtypes = [vp, c_uint16_p]
+        L.smplgpu_distance_field_add_cells.argtypes = [vp, c_int32_p, C.c_int]
+        L.smplgpu_distance_field_remove_cells.argtypes = [vp, c_int32_p, C.c_int]
         L.smplgpu_distance_field_dev_ptr.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.smplgpu_is_states_valid.argtypes = [vp, dp, i, bp]
         L.smplgpu_is_states_valid_dev.argtypes = [vp, vp, i, vp]
@@ -373,6 +375,16 @@ class GpuContext:
             if n <= cap:
                 return out[:n].copy()
             cap = n
+
+    def distance_field_add_cells(self, cells):
+        """OccupancyGrid::addPointsToField on the resident field (grid coordinates)."""
+        cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 3)
+        self._ck(self.L.smplgpu_distance_field_add_cells(self.h, _ip(cells), len(cells)), "distance_field_add_cells")
+
+    def distance_field_remove_cells(self, cells):
+        """OccupancyGrid::removePointsFromField on the resident field (grid coordinates)."""
+        cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 3)
+        self._ck(self.L.smplgpu_distance_field_remove_cells(self.h, _ip(cells), len(cells)), "distance_field_remove_cells")
 
     def download_distance_field(self):
         out = np.zeros(self.df_dims, np.uint16)

@@ -25,6 +25,30 @@ __global__ void edt_scatter_kernel(const int* __restrict__ cells, int n, int nx,
     occ[((size_t)x * ny + y) * nz + z] = 1;
 }
 
+// value = 1: cells enter the obstacle set, value = 0: they leave it
+__global__ void edt_scatter_value_kernel(const int* __restrict__ cells, int n, int nx, int ny, int nz, uint8_t value,
+                                         uint8_t* __restrict__ occ)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const int x = cells[3 * i], y = cells[3 * i + 1], z = cells[3 * i + 2];
+    if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) {
+        return;
+    }
+    occ[((size_t)x * ny + y) * nz + z] = value;
+}
+
+// the obstacle set of a field: the cells at distance 0 (the border the reference treats as obstacles lies outside)
+__global__ void edt_occ_from_field_kernel(const uint16_t* __restrict__ d2, size_t cells, uint8_t* __restrict__ occ)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cells) {
+        occ[i] = d2[i] == 0 ? 1 : 0;
+    }
+}
+
 // pass 1: 1-D distance along z to the nearest occupied cell or border (z = -1, z = nz)
 __global__ void edt_pass_z_kernel(const uint8_t* __restrict__ occ, int nx, int ny, int nz, int dmax,
                                   uint16_t* __restrict__ g)

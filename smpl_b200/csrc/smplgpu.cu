@@ -1360,6 +1360,54 @@ static int build_distance_field_impl(smplgpu_ctx* ctx, const double* vertices, i
     return ctx->has_robot ? upload_model(ctx) : 0;
 }
 
+// OccupancyGrid::addPointsToField / removePointsFromField on the resident field: the obstacle set is read back from the
+// field itself (distance 0), changed, and the exact transform recomputed
+static int update_distance_field_cells(smplgpu_ctx* ctx, const int32_t* cells_xyz, int n, uint8_t value)
+{
+    if (!ctx || n < 0 || (n > 0 && !cells_xyz)) return SMPLGPU_ERR_INVALID;
+    if (!ctx->has_df) return fail(ctx, SMPLGPU_ERR_STATE, "no distance field");
+    if (n == 0) return 0;
+    {
+        const int fr = finish_bank_run(ctx);   // a bank run queued behind the caller's back still reads the field
+        if (fr) return fr;
+    }
+    const int nx = ctx->grid.nx, ny = ctx->grid.ny, nz = ctx->grid.nz;
+    const int dmax_sq = ctx->dmax_sq;
+    int dmax = (int)std::sqrt((double)dmax_sq);
+    while (dmax * dmax < dmax_sq) ++dmax;
+    while (dmax > 0 && (dmax - 1) * (dmax - 1) >= dmax_sq) --dmax;
+    const size_t cells = ctx->df_cells;
+    const size_t need = cells + 2 * cells * sizeof(uint16_t) + (size_t)n * 3 * sizeof(int) + 64;
+    int r = grow(ctx, &ctx->d_misc, &ctx->misc_cap, need);
+    if (r) return r;
+    uint8_t* occ = (uint8_t*)ctx->d_misc;
+    uint16_t* g1 = (uint16_t*)(occ + ((cells + 15) / 16) * 16);
+    uint16_t* g2 = g1 + cells;
+    int* d_cells = (int*)(g2 + cells + (cells & 1));
+    const unsigned blocks = (unsigned)((cells + 255) / 256);
+    edt_occ_from_field_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_df, cells, occ);
+    CU(cudaMemcpyAsync(d_cells, cells_xyz, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    edt_scatter_value_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_cells, n, nx, ny, nz, value, occ);
+    edt_pass_z_kernel<<<(nx * ny + 127) / 128, 128, 0, ctx->stream>>>(occ, nx, ny, nz, dmax, g1);
+    edt_pass_axis_kernel<<<blocks, 256, 0, ctx->stream>>>(g1, nx, ny, nz, 1, dmax, dmax_sq, true, g2);
+    edt_pass_axis_kernel<<<blocks, 256, 0, ctx->stream>>>(g2, nx, ny, nz, 0, dmax, dmax_sq, false, ctx->d_df);
+    ctx->launches += 5;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    ++ctx->scene_epoch;   // records of the old scene are stale (smplhost::ExpansionCache)
+    return 0;
+}
+
+int smplgpu_distance_field_add_cells(smplgpu_ctx* ctx, const int32_t* cells_xyz, int n)
+{
+    return update_distance_field_cells(ctx, cells_xyz, n, 1);
+}
+
+int smplgpu_distance_field_remove_cells(smplgpu_ctx* ctx, const int32_t* cells_xyz, int n)
+{
+    return update_distance_field_cells(ctx, cells_xyz, n, 0);
+}
+
 int smplgpu_download_distance_field(smplgpu_ctx* ctx, uint16_t* out)
 {
     if (!ctx || !out) return SMPLGPU_ERR_INVALID;

@@ -148,3 +148,59 @@ def test_attached_box_sphere_model_generated_from_voxels():
         assert 0.02 < v.mean() < 0.9
     finally:
         c.close()
+
+
+def test_incremental_add_and_remove_on_the_resident_field():
+    """OccupancyGrid::addPointsToField / removePointsFromField (occupancy_grid.cpp:357-410 -> distance_map.hpp:305-367)
+    on the device: cells leave and enter the obstacle set of the resident field (objects removed from / inserted into
+    the scene).  Checked against the oracle's restatement of the reference's incremental propagation (pinned to the
+    reference build in tests/test_oracle_distance_map.py) with the same exactness caveat as the bulk build, against a
+    fresh device build of the final set (bit for bit), on a field uploaded from outside, and through the verdicts."""
+    scene = scenes.pr2_tabletop_env_scene()
+    o = make_oracle(scene, with_kdl=False)
+    c, tables = api.setup_context(scene)
+    try:
+        dims, origin, res, dmax_sq = o.grid_info()
+        rng = np.random.default_rng(21)
+        occ = np.argwhere(o.df_d2() == 0)
+        gone = occ[rng.choice(len(occ), len(occ) // 3, replace=False)]          # an object taken away ...
+        new = np.stack([rng.integers(-2, d + 2, 400) for d in dims], axis=1)    # ... clutter added (some cells outside)
+        new[:, 0] = rng.integers(2 * dims[0] // 3, dims[0] + 2, len(new))       # in the far third of the workspace
+        new = np.concatenate([new, new[:100], occ[:50]])                        # duplicates, cells that are obstacles already
+        world = lambda cells: np.asarray(origin) + np.asarray(cells) * res      # cell centres, as gridToWorld defines them
+        lo, hi, cont = tables.limits()
+        q = scenes.random_states(20000, lo, hi, cont, seed=5)
+        v_before = c.is_states_valid(q)
+        o.remove_points(world(gone))
+        c.distance_field_remove_cells(gone)
+        o.add_points(world(new))
+        c.distance_field_add_cells(new)
+        ref = o.df_d2()
+        got = c.download_distance_field().astype(np.int32)
+        assert np.array_equal(got == 0, ref == 0), "obstacle sets differ"
+        differ = got != ref
+        assert np.all(got <= ref) and np.all(ref[differ] - got[differ] <= 2)
+        assert differ.sum() <= 2e-5 * ref.size, "%d cells differ" % int(differ.sum())
+        # the same set built from scratch on the device: bit for bit
+        c2, _ = api.setup_context(scene)
+        try:
+            c2.build_distance_field(np.argwhere(ref == 0), scene.dims, scene.origin, scene.res, scene.max_dist, scene.padding)
+            assert np.array_equal(c2.download_distance_field(), got)
+        finally:
+            c2.close()
+        v_ref = o.is_states_valid(q)
+        v = c.is_states_valid(q)
+        assert (v != v_ref).sum() <= differ.sum()
+        assert 0.0 < v.mean() < 0.95 and (v != v_before).sum() > 20      # the update is what the verdicts see
+        # on a field that came from outside (the reference's own), removing and re-adding the same cells
+        c.set_distance_field(ref.astype(np.uint16), origin, res, dmax_sq)
+        some = np.argwhere(ref == 0)[::7]
+        c.distance_field_remove_cells(some)
+        assert (c.download_distance_field()[tuple(some.T)] > 0).all()
+        c.distance_field_add_cells(some)
+        again = c.download_distance_field().astype(np.int32)
+        assert np.array_equal(again == 0, ref == 0) and np.all(again <= ref) and (again != ref).sum() <= 2e-5 * ref.size
+        print("incremental update: %d cells removed, %d added, %d / %d cells where the reference's propagation is inexact" % (
+            len(gone), len(new), int(differ.sum()), ref.size))
+    finally:
+        c.close()
