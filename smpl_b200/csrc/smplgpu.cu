@@ -2612,11 +2612,12 @@ int smplgpu_bfs_bank_max_slots(smplgpu_ctx* ctx)
     const long long nx = ctx->grid.nx, ny = ctx->grid.ny, nz = ctx->grid.nz;
     // (nx+2)(ny+2)(n (nz+2)) <= 2^31 - 1
     long long by_index = 0x7FFFFFFFLL / ((nx + 2) * (ny + 2)) / (nz + 2);
-    // distances (4 B per padded cell) + four bitmaps + candidate words: ~4.7 B per cell; keep half the free memory
+    // distances (4 B per padded cell) + four bitmaps + candidate words: ~4.7 B per cell, + the tile kernel's four
+    // tile-major bitmaps (0.5 B per cell, padded to whole tiles: ~0.7 B); keep half the free memory
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
         size_t have = free_b + (ctx->has_bank ? (size_t)ctx->bank_cells * 5 : 0);
-        long long by_mem = (long long)((double)have * 0.5 / (4.7 * (double)((nx + 2) * (ny + 2) * (nz + 2))));
+        long long by_mem = (long long)((double)have * 0.5 / (5.4 * (double)((nx + 2) * (ny + 2) * (nz + 2))));
         by_index = std::min(by_index, by_mem);
     }
     return (int)std::max(1LL, std::min(by_index, 1LL << 20));
