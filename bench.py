@@ -449,6 +449,18 @@ def dropin_leg(api, scenes, local_rank):
             cache_launches += dropin_plan.last_batched[0]
         secs = time.perf_counter() - t0
         launches = ctx.launch_count() - l0
+        # the same queries through the reference's LAZY successors (GetLazySuccs / GetTrueCost under its LazyARAStar)
+        lazy = None
+        if hasattr(lib, "refdrop_plan_lazy"):
+            dropin_plan(lib, ctx, scene, starts[1], goals[1], params, batched=2, lazy=True)
+            l1 = ctx.launch_count()
+            t1 = time.perf_counter()
+            lgot, evals = [], 0
+            for s_, g_ in zip(starts, goals):
+                lgot.append(dropin_plan(lib, ctx, scene, s_, g_, params, batched=2, lazy=True))
+                evals += dropin_plan.last_evaluations
+            lazy = {"seconds": time.perf_counter() - t1, "launches": int(ctx.launch_count() - l1),
+                    "expansions": sum(g[1] for g in lgot), "evaluations": int(evals), "_got": lgot}
     finally:
         ctx.close()
     expansions = sum(g[1] for g in got)
@@ -456,6 +468,8 @@ def dropin_leg(api, scenes, local_rank):
            "queries_per_s": len(got) / secs, "launches": int(launches), "launches_per_expansion": launches / max(1, expansions),
            "caller": "the reference's ManipLattice::GetSuccs + ARAStar, unchanged (oracle/_ref/libref_dropin.so)",
            "_got": got, "_scene": scene, "_params": params, "_starts": starts, "_goals": goals}
+    if lazy is not None:
+        out["lazy"] = lazy
     return out
 
 
@@ -477,6 +491,17 @@ def dropin_cpu_compare(drop):
     drop["cpu_expansions_per_s"] = cexp / secs
     drop["identical_plans"] = same
     drop["cpu_sample"] = "the same %d queries through the reference's own CollisionSpace + BfsHeuristic + BFS_3D, 1 thread" % len(got)
+    lazy = drop.get("lazy")
+    if lazy is not None:
+        lgot = lazy.pop("_got")
+        t0 = time.perf_counter()
+        same = 0
+        for s_, g_, g in zip(starts, goals, lgot):
+            pr = pref.plan(scene, s_, g_, params, lazy=True)
+            same += int([int(pr["success"]), int(pr["expansions"]), int(pr["cost"]), int(pr["num_states"]),
+                         [int(i) for i in pr["path_ids"]]] == g)
+        lazy["cpu_seconds"] = time.perf_counter() - t0
+        lazy["identical_plans"] = same
 
 
 def dual_arm_leg(api, scenes, sharding, dist, torch, dev, args, rank, world, local_rank, barrier, stream):
@@ -1022,6 +1047,10 @@ def main():
         e2e.update({"dropin_expansions_per_s": drop["expansions_per_s"], "dropin_seconds": drop["seconds"],
                     "dropin_queries": drop["queries"], "dropin_launches_per_expansion": drop["launches_per_expansion"],
                     "dropin_identical_plans": drop.get("identical_plans")})
+        if drop.get("lazy"):
+            e2e.update({"dropin_lazy_seconds": drop["lazy"]["seconds"], "dropin_lazy_launches": drop["lazy"]["launches"],
+                        "dropin_lazy_expansions": drop["lazy"]["expansions"], "dropin_lazy_evaluations": drop["lazy"]["evaluations"],
+                        "dropin_lazy_identical_plans": drop["lazy"].get("identical_plans")})
     if dual is not None:
         e2e.update({"dual_arm_states_per_s": dual["states_per_s"], "dual_arm_broadcast_ms": dual["broadcast_ms"],
                     "dual_arm_broadcast_gbs": dual["broadcast_gbs"], "dual_arm_field_build_ms": dual["field_build_ms"],
@@ -1042,6 +1071,8 @@ def main():
             cpu.update({"ubr1_queries_per_s": ubr1["cpu_queries_per_s"], "ubr1_expansions_per_s": ubr1["cpu_expansions_per_s"]})
         if drop is not None and "cpu_expansions_per_s" in drop:
             cpu.update({"dropin_expansions_per_s": drop["cpu_expansions_per_s"], "dropin_seconds": drop["cpu_seconds"]})
+            if drop.get("lazy") and "cpu_seconds" in drop["lazy"]:
+                cpu["dropin_lazy_seconds"] = drop["lazy"]["cpu_seconds"]
         if dual is not None and "cpu_states_per_s" in dual:
             cpu["dual_arm_states_per_s"] = dual["cpu_states_per_s"]
         if bfs is not None and "cpu_mvoxel_s" in bfs:
@@ -1083,6 +1114,8 @@ def main():
     if drop is not None:
         for k in ("_got", "_scene", "_params", "_starts", "_goals"):
             drop.pop(k, None)
+        if drop.get("lazy"):
+            drop["lazy"].pop("_got", None)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
