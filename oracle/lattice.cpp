@@ -157,6 +157,140 @@ void ManipLatticePlanner::getSuccs(int state_id, std::vector<int>& succs, std::v
     }
 }
 
+/// mprimActive (manip_lattice_action_space.cpp:662-691)
+bool ManipLatticePlanner::primActive(size_t p, bool near_goal) const
+{
+    if (!m_prim_short[p]) {
+        return !(m_params.use_short_dist && near_goal);
+    }
+    return m_params.use_short_dist && near_goal;
+}
+
+/// ManipLattice::GetLazySuccs (manip_lattice.cpp:1012-1090): every action of the action space becomes a successor --
+/// no limit test, no collision test -- at the optimistic cost, flagged "not the true cost"
+void ManipLatticePlanner::getLazySuccs(int state_id, std::vector<int>& succs, std::vector<int>& costs,
+                                       std::vector<bool>& true_costs)
+{
+    if (state_id == m_goal_state_id) {
+        return; // goal state is absorbing
+    }
+    const std::vector<double> parent = m_states[state_id].state;
+    std::vector<double> pose;
+    m_robot->computePlanningLinkFK(parent, pose);
+    const bool near_goal = m_heur->getMetricGoalDistance(pose[0], pose[1], pose[2]) <= m_params.short_dist_thresh;
+    std::vector<double> succ(parent.size());
+    std::vector<int> coord;
+    for (size_t p = 0; p < m_prim_deltas.size(); ++p) {
+        if (!primActive(p, near_goal)) {
+            continue;
+        }
+        for (size_t j = 0; j < parent.size(); ++j) {
+            succ[j] = m_prim_deltas[p][j] + parent[j];
+        }
+        stateToCoord(succ, coord);
+        const bool is_goal = isGoal(succ);
+        const int succ_id = getOrCreateState(coord, succ);
+        succs.push_back(is_goal ? m_goal_state_id : succ_id);
+        costs.push_back(1000);        // cost(): DefaultCostMultiplier (manip_lattice.cpp:1388-1412)
+        true_costs.push_back(false);
+    }
+}
+
+/// ManipLattice::GetTrueCost (manip_lattice.cpp:1094-1167): the cheapest valid action of the parent that ends in the
+/// child's cell (or, for the goal id, in a goal state); -1 when there is none
+int ManipLatticePlanner::getTrueCost(int parent_id, int child_id)
+{
+    const std::vector<double> parent = m_states[parent_id].state;
+    std::vector<double> pose;
+    m_robot->computePlanningLinkFK(parent, pose);
+    const bool near_goal = m_heur->getMetricGoalDistance(pose[0], pose[1], pose[2]) <= m_params.short_dist_thresh;
+    const bool goal_edge = child_id == m_goal_state_id;
+    std::vector<double> succ(parent.size());
+    std::vector<int> coord;
+    int best_cost = std::numeric_limits<int>::max();
+    for (size_t p = 0; p < m_prim_deltas.size(); ++p) {
+        if (!primActive(p, near_goal)) {
+            continue;
+        }
+        for (size_t j = 0; j < parent.size(); ++j) {
+            succ[j] = m_prim_deltas[p][j] + parent[j];
+        }
+        stateToCoord(succ, coord);
+        if (goal_edge) {
+            if (!isGoal(succ)) {
+                continue;
+            }
+        } else if (coord != m_states[child_id].coord) {
+            continue;
+        }
+        if (!m_robot->checkJointLimits(succ) || !m_cc->isStateToStateValid(parent, succ)) {
+            continue;   // checkAction
+        }
+        const int edge_cost = (int)(1000 * 1.0);   // cost(parent, succ, 1, goal_edge), :1414-1437
+        if (edge_cost < best_cost) {
+            best_cost = edge_cost;
+        }
+    }
+    return best_cost != std::numeric_limits<int>::max() ? best_cost : -1;
+}
+
+/// setGoal + setStart of a query; false when the start is refused (res then holds the answer)
+bool ManipLatticePlanner::begin(const std::vector<double>& start, const double goal_xyz[3], PlanResult& res)
+{
+    m_states.clear();
+    m_coord_to_id.clear();
+    for (int i = 0; i < 3; ++i) m_goal[i] = goal_xyz[i];
+    m_goal_state_id = 0;                      // reserveHashEntry for the goal state (manip_lattice.cpp:122)
+    m_states.push_back(LatticeState());
+    m_heur->updateGoal(goal_xyz[0], goal_xyz[1], goal_xyz[2]);
+    if (!m_robot->checkJointLimits(start) || !m_cc->isStateValid(start)) {   // setStart (manip_lattice.cpp:1944-1980)
+        res.num_states = (int)m_states.size();
+        return false;
+    }
+    std::vector<int> coord;
+    stateToCoord(start, coord);
+    m_start_state_id = getOrCreateState(coord, start);
+    return true;
+}
+
+PlanResult ManipLatticePlanner::planLazy(const std::vector<double>& start, const double goal_xyz[3])
+{
+    PlanResult res;
+    if (!begin(start, goal_xyz, res)) {
+        return res;
+    }
+    const int bound = m_params.max_expansions;
+    int expansions = 0, evaluations = 0;
+    LazyAraStar search(
+        [&](int id, std::vector<int>& succs, std::vector<int>& costs, std::vector<bool>& trues) {
+            if (expansions >= bound) {
+                return;
+            }
+            ++expansions;
+            getLazySuccs(id, succs, costs, trues);
+        },
+        [&](int parent, int child) {
+            if (expansions >= bound) {
+                return -1;
+            }
+            ++evaluations;
+            return getTrueCost(parent, child);
+        },
+        [this](int id) { return goalHeuristic(id); });
+    const LazyAraStar::Result r = search.search(m_start_state_id, m_goal_state_id, m_params.epsilon);
+    res.expansions = expansions;
+    res.evaluations = evaluations;
+    res.num_states = (int)m_states.size();
+    if (!r.found) {
+        return res;
+    }
+    res.path_ids = r.path;
+    res.cost = r.cost;
+    res.success = true;
+    extractPath(res.path_ids, res.path_states);
+    return res;
+}
+
 PlanResult ManipLatticePlanner::plan(const std::vector<double>& start, const double goal_xyz[3])
 {
     PlanResult res;

@@ -9,6 +9,7 @@
 //   ManipLatticeActionSpace  smpl/src/graph/manip_lattice_action_space.cpp:201-228 (addMotionPrim),
 //                     376-449 (apply), 507-573 (getAction), 662-691 (mprimActive)
 //   ARAStar           oracle/arastar.h (pinned against the reference's own arastar.cpp)
+//   lazy successors   manip_lattice.cpp:1012-1090 (GetLazySuccs), 1094-1167 (GetTrueCost); search: oracle/lazy_arastar.h
 //
 // Decisions (fork defect 2): motion primitives use the documented plain format
 // (delta per joint, weight 1, no base rotation hack, converse added after each primitive); the IK "snap"
@@ -23,6 +24,7 @@
 #include <vector>
 
 #include "arastar.h"
+#include "lazy_arastar.h"
 #include "collision_space.h"
 #include "kdl_model.h"
 
@@ -53,7 +55,8 @@ struct PlanResult
     std::vector<int> path_ids;
     std::vector<std::vector<double>> path_states;
     int num_states;
-    PlanResult() : success(false), expansions(0), cost(0), num_states(0) { }
+    int evaluations;   // lazy search: GetTrueCost calls
+    PlanResult() : success(false), expansions(0), cost(0), num_states(0), evaluations(0) { }
 };
 
 class ManipLatticePlanner
@@ -64,6 +67,11 @@ public:
 
     /// PlannerInterface::planToPose reduced to: setGoal (BFS from the goal cell), setStart, ARA* replan
     PlanResult plan(const std::vector<double>& start, const double goal_xyz[3]);
+
+    /// the same query through the lazy successors (ManipLattice::GetLazySuccs / GetTrueCost, manip_lattice.cpp:1012-1167)
+    /// under the reference's in-tree LazyARAStar (oracle/lazy_arastar.h), bounded by max_expansions in the successor
+    /// function exactly as oracle/ref_planner_plugins.h:LatticeLazySuccFun bounds the reference's run
+    PlanResult planLazy(const std::vector<double>& start, const double goal_xyz[3]);
 
 private:
     struct LatticeState { std::vector<int> coord; std::vector<double> state; };
@@ -88,6 +96,10 @@ private:
     int getOrCreateState(const std::vector<int>& coord, const std::vector<double>& state);
     bool isGoal(const std::vector<double>& state) const;
     void getSuccs(int state_id, std::vector<int>& succs, std::vector<int>& costs);
+    bool primActive(size_t p, bool near_goal) const;
+    void getLazySuccs(int state_id, std::vector<int>& succs, std::vector<int>& costs, std::vector<bool>& true_costs);
+    int getTrueCost(int parent_id, int child_id);
+    bool begin(const std::vector<double>& start, const double goal_xyz[3], PlanResult& res);
     int goalHeuristic(int state_id) const;
     bool extractPath(const std::vector<int>& ids, std::vector<std::vector<double>>& path) const;
 

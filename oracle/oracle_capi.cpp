@@ -508,6 +508,10 @@ int oracle_goal_heuristics(oracle_scene* s, const double* q, int n, int32_t* h)
 // planning query: ManipLattice + ARA* over the oracle's checker / heuristic
 ///////////////////////////////////////////////////////////////////////////////
 
+// set by oracle_plan_lazy around a call of oracle_plan
+static thread_local bool tl_plan_lazy = false;
+static thread_local int tl_plan_lazy_evaluations = 0;
+
 /// mprims: n_prims rows of dof deltas (radians); short_flags[n_prims].
 /// out_summary: success, expansions, cost, path_len, num_states.  Returns seconds spent in plan().
 double oracle_plan(oracle_scene* s, const double* start, const double* goal_xyz,
@@ -532,7 +536,8 @@ double oracle_plan(oracle_scene* s, const double* start, const double* goal_xyz,
     ManipLatticePlanner planner(s->cc.get(), s->kdl.get(), s->heur.get(), s->xyz_offset, 0, pp);
     std::vector<double> st(start, start + s->dof);
     auto t0 = std::chrono::steady_clock::now();
-    PlanResult r = planner.plan(st, goal_xyz);
+    PlanResult r = tl_plan_lazy ? planner.planLazy(st, goal_xyz) : planner.plan(st, goal_xyz);
+    tl_plan_lazy_evaluations = r.evaluations;
     auto t1 = std::chrono::steady_clock::now();
     out_summary[0] = r.success ? 1 : 0;
     out_summary[1] = r.expansions;
@@ -549,6 +554,27 @@ double oracle_plan(oracle_scene* s, const double* start, const double* goal_xyz,
         out_summary[5] = (int)r.path_states.size();
     }
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+/// oracle_plan through the lazy successors and oracle/lazy_arastar.h (ManipLatticePlanner::planLazy);
+/// oracle_last_lazy_evaluations() = GetTrueCost calls of the last query on this thread
+double oracle_plan_lazy(oracle_scene* s, const double* start, const double* goal_xyz,
+                        const double* resolutions, const double* mprims, const uint8_t* short_flags, int n_prims,
+                        int use_short_dist, double short_dist_thresh, double epsilon, int max_expansions,
+                        const double* xyz_tolerance, int32_t* out_summary, int32_t* path_ids, int max_path,
+                        double* path_states)
+{
+    tl_plan_lazy = true;
+    const double secs = oracle_plan(s, start, goal_xyz, resolutions, mprims, short_flags, n_prims, use_short_dist,
+                                    short_dist_thresh, epsilon, max_expansions, xyz_tolerance, out_summary, path_ids,
+                                    max_path, path_states);
+    tl_plan_lazy = false;
+    return secs;
+}
+
+int oracle_last_lazy_evaluations(void)
+{
+    return tl_plan_lazy_evaluations;
 }
 
 /// oracle/arastar.h on an explicit graph (CSR successor lists), same signature as ref_arastar_search

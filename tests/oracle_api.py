@@ -51,7 +51,7 @@ def lib():
                                           C.c_double, C.c_double]
         L.oracle_bfs_create.restype = C.c_void_p
         L.oracle_bfs_create.argtypes = [C.c_int, C.c_int, C.c_int]
-        for name in ("oracle_time_states_valid", "oracle_time_edges_valid", "oracle_time_bfs_run", "oracle_plan"):
+        for name in ("oracle_time_states_valid", "oracle_time_edges_valid", "oracle_time_bfs_run", "oracle_plan", "oracle_plan_lazy"):
             getattr(L, name).restype = C.c_double
         L.oracle_time_bfs_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         _LIB = L
@@ -535,8 +535,9 @@ class OracleScene:
             raise RuntimeError("interpolate_path: more than %d points" % max_points)
         return out[:n].copy()
 
-    def plan(self, start, goal_xyz, params, max_path=4096):
-        """params: smpl_b200.scenes.PlanParams.  Returns dict(success, expansions, cost, path_ids, num_states, seconds)."""
+    def plan(self, start, goal_xyz, params, max_path=4096, lazy=False):
+        """params: smpl_b200.scenes.PlanParams.  Returns dict(success, expansions, cost, path_ids, num_states, seconds);
+        lazy: the lazy successors under oracle/lazy_arastar.h (+ `evaluations`)."""
         start = np.ascontiguousarray(start, dtype=np.float64)
         goal = np.ascontiguousarray(goal_xyz, dtype=np.float64)
         res = np.ascontiguousarray(params.resolutions, dtype=np.float64)
@@ -546,14 +547,18 @@ class OracleScene:
         summary = np.zeros(8, np.int32)
         path = np.zeros(max_path, np.int32)
         pstates = np.zeros((max_path, len(start)), np.float64)
-        secs = self.L.oracle_plan(self.h, _dp(start), _dp(goal), _dp(res), _dp(prims), _bp(flags), len(prims),
+        fn = self.L.oracle_plan_lazy if lazy else self.L.oracle_plan
+        secs = fn(self.h, _dp(start), _dp(goal), _dp(res), _dp(prims), _bp(flags), len(prims),
                                   int(params.use_short_dist), C.c_double(params.short_dist_thresh),
                                   C.c_double(params.epsilon), int(params.max_expansions), _dp(tol),
                                   _ip(summary), _ip(path), max_path, _dp(pstates))
         n = int(summary[3])
         assert int(summary[5]) == n, "extractPath failed"
-        return dict(path_states=pstates[:min(n, max_path)].copy(), success=bool(summary[0]), expansions=int(summary[1]), cost=int(summary[2]),
-                    path_ids=path[:min(n, max_path)].copy(), num_states=int(summary[4]), seconds=float(secs))
+        out = dict(path_states=pstates[:min(n, max_path)].copy(), success=bool(summary[0]), expansions=int(summary[1]), cost=int(summary[2]),
+                   path_ids=path[:min(n, max_path)].copy(), num_states=int(summary[4]), seconds=float(secs))
+        if lazy:
+            out["evaluations"] = int(self.L.oracle_last_lazy_evaluations())
+        return out
 
 
 _REF_CC = None

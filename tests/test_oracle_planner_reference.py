@@ -73,6 +73,36 @@ def test_committed_golden_plans_are_the_reference_builds():
 
 
 @needs_ref
+@pytest.mark.parametrize("name", ["pr2_tabletop", "ubr1_tabletop"])
+def test_lazy_restatement_plans_equal_reference_build(name):
+    """oracle/lazy_arastar.h + ManipLatticePlanner::getLazySuccs / getTrueCost against the reference's own
+    lazy_arastar.cpp + ManipLattice::GetLazySuccs / GetTrueCost (compiled from its sources), query by query: success,
+    expansions, evaluations, cost, lattice size, id path, joint path."""
+    scene, attach, params, starts, goals = plan_cases()[name]
+    o = make_restatement(scene, attach, with_kdl=True)
+    r = make_reference(scene, attach)
+    solved = 0
+    for s, g in zip(starts, goals):
+        o.heur_init(scene.inflation_radius, scene.cost_per_cell)
+        a = o.plan(s, g, params, lazy=True)
+        b = r.plan(scene, s, g, params, lazy=True)
+        assert summary(a) + [a["evaluations"]] == summary(b) + [b["evaluations"]]
+        assert np.array_equal(a["path_states"], b["path_states"])
+        solved += a["success"]
+    assert solved >= 2
+
+
+def test_lazy_restatement_plans_equal_golden_reference_outputs():
+    gold = json.load(open(os.path.join(GOLD, "plans_reference_lazy.json")))
+    for name, (scene, attach, params, starts, goals) in plan_cases().items():
+        o = make_restatement(scene, attach, with_kdl=True)
+        for s, g, want in list(zip(starts, goals, gold[name]))[:5]:
+            o.heur_init(scene.inflation_radius, scene.cost_per_cell)
+            p = o.plan(s, g, params, lazy=True)
+            assert summary(p) + [p["evaluations"]] == want
+
+
+@needs_ref
 def test_committed_lazy_golden_plans_are_the_reference_builds():
     """The reference's lazy successors -- ManipLattice::GetLazySuccs / GetTrueCost (manip_lattice.cpp:1012-1167) under its
     in-tree LazyARAStar (search/lazy_arastar.cpp), compiled from the reference's sources -- reproduce the committed
