@@ -2230,7 +2230,9 @@ static int launch_bank_level_chunk(smplgpu_ctx* ctx, cudaStream_t stream)
         const BfsTiles& t = ctx->bank_tiles;
         const bool large = ctx->bank_step_tiles == TILE_RPT_LARGE;
         const int threads = large ? TILE_THREADS / TILE_RPT_LARGE : TILE_THREADS;
-        for (int k = 0; k < BANK_TILE_CHUNK; ++k) {
+        // SMPLGPU_BANK_TILE_CHUNK: a smaller chunk, for the tests of the continuation path
+        static const int chunk = getenv("SMPLGPU_BANK_TILE_CHUNK") ? std::max(1, atoi(getenv("SMPLGPU_BANK_TILE_CHUNK"))) : BANK_TILE_CHUNK;
+        for (int k = 0; k < chunk; ++k) {
             const int step = ctx->bank_next_level - 1 + k;
             if (large) {
                 bfs_tiles_kernel<TILE_RPT_LARGE><<<ctx->bank_step_blocks, threads, 0, stream>>>(g, t, step + 1, step, 1, ctx->bank_done);
@@ -2238,8 +2240,8 @@ static int launch_bank_level_chunk(smplgpu_ctx* ctx, cudaStream_t stream)
                 bfs_tiles_kernel<1><<<ctx->bank_step_blocks, threads, 0, stream>>>(g, t, step + 1, step, 1, ctx->bank_done);
             }
         }
-        ctx->launches += BANK_TILE_CHUNK;
-        ctx->bank_next_level += BANK_TILE_CHUNK;
+        ctx->launches += chunk;
+        ctx->bank_next_level += chunk;
         CU(cudaGetLastError());
         return 0;
     }
