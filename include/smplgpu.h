@@ -393,6 +393,7 @@ typedef struct smplgpu_lattice_params {
     int32_t max_states;              /* room per query; a query creates at most 2 + expansions * stride states */
 } smplgpu_lattice_params;
 #define SMPLGPU_LATTICE_GOAL_FLAG (1 << 30)   /* in a successor word: the action reaches the goal region */
+#define SMPLGPU_LATTICE_SHORT_FLAG (1 << 29)  /* in a count word: the expansion applied the short-distance primitives */
 /* largest n_slots smplgpu_lattice_create can hold in the free device memory */
 int smplgpu_lattice_max_slots(smplgpu_ctx* ctx, int max_states);
 /* returns the stride: successor words per expansion = max(#long, #short primitives) */
@@ -408,7 +409,8 @@ int smplgpu_lattice_begin(smplgpu_ctx* ctx, const int32_t* slots, const double* 
  *   succ[i * stride + j]  id of the j-th active primitive's successor | SMPLGPU_LATTICE_GOAL_FLAG, or -1 when the
  *                         primitive is inactive, leaves the joint limits or its edge is in collision
  *   h[i * stride + j]     BfsHeuristic::GetGoalHeuristic of that successor
- *   count[i]              lattice size of the query after this expansion */
+ *   count[i]              lattice size of the query after this expansion | SMPLGPU_LATTICE_SHORT_FLAG when word j
+ *                         stands for the j-th SHORT-distance primitive (mprimActive), else the j-th long one; -1 = full */
 int smplgpu_lattice_expand_submit(smplgpu_ctx* ctx, const int32_t* slot, const int32_t* parent_id, int n, int buffer);
 int smplgpu_lattice_expand_wait(smplgpu_ctx* ctx, int buffer, const int32_t** succ, const int32_t** h,
                                 const int32_t** count);

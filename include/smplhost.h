@@ -79,6 +79,8 @@ typedef struct smplhost_plan_params
     double res;
     int dims[3];
     int n_threads;                  /* host threads for the per-query work (>= 1); results do not depend on it */
+    const double* prim_weights;     /* [n_prims] action weights (manip_lattice_action_space.cpp:182-190): an edge costs
+                                     * (int)(1000 * weight), manip_lattice.cpp:1414-1437; NULL = 1 for every primitive */
 } smplhost_plan_params;
 
 /* Plans nq queries (starts[nq][dof], goals[nq][3]) with at most max_concurrent searches in flight.

@@ -20,10 +20,12 @@ ManipLatticePlanner::ManipLatticePlanner(
     for (const MotionPrim& p : params.mprims) {
         m_prim_deltas.push_back(p.delta);
         m_prim_short.push_back(p.short_dist);
+        m_prim_cost.push_back((int)(1000 * p.weight));   // DefaultCostMultiplier * actionWeight, truncated
         std::vector<double> neg(p.delta);
         for (double& v : neg) v *= -1.0;
         m_prim_deltas.push_back(neg);
         m_prim_short.push_back(p.short_dist);
+        m_prim_cost.push_back((int)(1000 * p.weight));
     }
     // ManipLattice::init (manip_lattice.cpp:105-146)
     const size_t n = robot->min_limits.size();
@@ -153,7 +155,7 @@ void ManipLatticePlanner::getSuccs(int state_id, std::vector<int>& succs, std::v
         const int succ_id = getOrCreateState(coord, succ);
         const bool is_goal = isGoal(succ);
         succs.push_back(is_goal ? m_goal_state_id : succ_id);
-        costs.push_back((int)(1000 * 1.0)); // DefaultCostMultiplier * actionWeight
+        costs.push_back(m_prim_cost[p]);    // cost(parent, succ, weights[i], goal), manip_lattice.cpp:296
     }
 }
 

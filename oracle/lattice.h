@@ -12,7 +12,7 @@
 //   lazy successors   manip_lattice.cpp:1012-1090 (GetLazySuccs), 1094-1167 (GetTrueCost); search: oracle/lazy_arastar.h
 //
 // Decisions (fork defect 2): motion primitives use the documented plain format
-// (delta per joint, weight 1, no base rotation hack, converse added after each primitive); the IK "snap"
+// (delta per joint, a weight -- 1 unless given --, no base rotation hack, converse added after each primitive); the IK "snap"
 // primitives need third-party IK and are outside the parity set; the goal is an XYZ_GOAL (position within
 // xyz_tolerance of the target offset pose, manip_lattice.cpp:1673-1687); the search stops at the first
 // solution of the initial epsilon (improve = false) or after max_expansions, so results do not depend on
@@ -34,6 +34,8 @@ struct MotionPrim
 {
     std::vector<double> delta;
     bool short_dist;
+    double weight;   // the primitive file's weight column: an edge costs (int)(1000 * weight), manip_lattice.cpp:1414-1437
+    MotionPrim() : short_dist(false), weight(1.0) { }
 };
 
 struct PlanParams
@@ -82,6 +84,7 @@ private:
     PlanParams m_params;
     std::vector<std::vector<double>> m_prim_deltas;
     std::vector<bool> m_prim_short;
+    std::vector<int> m_prim_cost;      // GetSuccs' edge cost per primitive, converses included
 
     std::vector<double> m_min_limits, m_max_limits, m_coord_deltas;
     std::vector<bool> m_continuous, m_bounded;

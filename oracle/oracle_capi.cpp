@@ -508,6 +508,9 @@ int oracle_goal_heuristics(oracle_scene* s, const double* q, int n, int32_t* h)
 // planning query: ManipLattice + ARA* over the oracle's checker / heuristic
 ///////////////////////////////////////////////////////////////////////////////
 
+// per-primitive action weights for the next oracle_plan calls on this thread (empty = 1 each)
+static thread_local std::vector<double> tl_prim_weights;
+
 // set by oracle_plan_lazy around a call of oracle_plan
 static thread_local bool tl_plan_lazy = false;
 static thread_local int tl_plan_lazy_evaluations = 0;
@@ -526,6 +529,7 @@ double oracle_plan(oracle_scene* s, const double* start, const double* goal_xyz,
         MotionPrim mp;
         mp.delta.assign(mprims + (size_t)p * s->dof, mprims + (size_t)(p + 1) * s->dof);
         mp.short_dist = short_flags[p] != 0;
+        mp.weight = (int)tl_prim_weights.size() == n_prims ? tl_prim_weights[p] : 1.0;
         pp.mprims.push_back(mp);
     }
     pp.use_short_dist = use_short_dist != 0;
@@ -554,6 +558,12 @@ double oracle_plan(oracle_scene* s, const double* start, const double* goal_xyz,
         out_summary[5] = (int)r.path_states.size();
     }
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+/// action weights of the primitives (n = n_prims of the following oracle_plan calls; n = 0 clears them)
+void oracle_set_prim_weights(const double* weights, int n)
+{
+    tl_prim_weights.assign(weights, weights + (n > 0 ? n : 0));
 }
 
 /// oracle_plan through the lazy successors and oracle/lazy_arastar.h (ManipLatticePlanner::planLazy);

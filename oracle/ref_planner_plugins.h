@@ -1,7 +1,7 @@
 // ORACLE (test infrastructure only).  The action-space plug-in shared by ref_planner_shim.cpp and ref_dropin_shim.cpp:
 // this fork's ManipLatticeActionSpace reads a motion-primitive format its own files do not have and rotates joints 0/1
 // by joint 3 (SURVEY 8a defect 2); like oracle/lattice.cpp, ShimActionSpace follows the documented behaviour: every
-// primitive is one waypoint parent + delta, weight 1, long primitives unless use_short_dist and
+// primitive is one waypoint parent + delta, weight 1 unless set, long primitives unless use_short_dist and
 // RobotHeuristic::getMetricGoalDistance(planning link position) <= threshold (manip_lattice_action_space.cpp:376-449,
 // 662-691), IK snap primitives off.
 #ifndef ORACLE_REF_PLANNER_PLUGINS_H
@@ -25,6 +25,7 @@ public:
 
     std::vector<std::vector<double>> deltas;   // file order, converse after each primitive (add_converse)
     std::vector<bool> is_short;
+    std::vector<double> weight;                // per primitive (the fork's primitive files carry one, :182-190)
     bool use_short_dist = false;
     double short_dist_thresh = 0.0;
     ForwardKinematicsInterface* fk = nullptr;
@@ -55,7 +56,7 @@ public:
                 action[0][j] = deltas[p][j] + parent[j];
             }
             actions.push_back(std::move(action));
-            weights.push_back(1.0);
+            weights.push_back(p < weight.size() ? weight[p] : 1.0);
         }
         return true;
     }
@@ -65,15 +66,25 @@ public:
 };
 
 /// ManipLatticeActionSpace::addMotionPrim with add_converse (:201-228): the converse follows each primitive
+inline std::vector<double>& ShimPrimWeights()
+{
+    static thread_local std::vector<double> w;   // set through ref*_set_prim_weights; empty = 1 each
+    return w;
+}
+
 inline void FillPrimitives(ShimActionSpace& actions, const double* mprims, const uint8_t* short_flags, int n_prims, int dof)
 {
+    const std::vector<double>& w = ShimPrimWeights();
     for (int p = 0; p < n_prims; ++p) {
         std::vector<double> d(mprims + (size_t)p * dof, mprims + (size_t)(p + 1) * dof);
+        const double wp = (int)w.size() == n_prims ? w[p] : 1.0;
         actions.deltas.push_back(d);
         actions.is_short.push_back(short_flags[p] != 0);
+        actions.weight.push_back(wp);
         for (double& v : d) v = -v;
         actions.deltas.push_back(d);
         actions.is_short.push_back(short_flags[p] != 0);
+        actions.weight.push_back(wp);
     }
 }
 

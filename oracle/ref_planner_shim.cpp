@@ -211,6 +211,12 @@ int refcc_plan_lazy(refcc_scene* s, const char* chain_root, const char* chain_ti
     return r;
 }
 
+/// action weights of the primitives for the following refcc_plan calls on this thread (n = 0 clears them)
+void refcc_set_prim_weights(const double* weights, int n)
+{
+    ShimPrimWeights().assign(weights, weights + (n > 0 ? n : 0));
+}
+
 int refcc_last_lazy_evaluations(void)
 {
     return tl_lazy_evaluations;

@@ -50,7 +50,7 @@ class PlanParamsC(C.Structure):
                 ("epsilon", C.c_double), ("max_expansions", C.c_int), ("xyz_tolerance", C.c_double * 3),
                 ("cost_per_cell", C.c_int), ("inflation_radius", C.c_double), ("var_min", c_double_p),
                 ("var_max", c_double_p), ("var_continuous", c_uint8_p), ("origin", C.c_double * 3),
-                ("res", C.c_double), ("dims", C.c_int * 3), ("n_threads", C.c_int)]
+                ("res", C.c_double), ("dims", C.c_int * 3), ("n_threads", C.c_int), ("prim_weights", c_double_p)]
 
 
 def gpu_lib():
@@ -789,6 +789,11 @@ def plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=64, max
     P.var_min, P.var_max, P.var_continuous = _dp(lo), _dp(hi), _bp(cont)
     P.res = float(scene.res)
     P.n_threads = int(n_threads)
+    weights = getattr(params, "weights", None)
+    if weights is not None:
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        assert len(weights) == len(prims)
+        P.prim_weights = _dp(weights)
     for a in range(3):
         P.xyz_tolerance[a] = float(params.xyz_tolerance[a])
         P.origin[a] = float(scene.origin[a])

@@ -26,6 +26,7 @@ namespace smplgpu {
 
 constexpr int LATTICE_MAX_STRIDE = 32;        // successors per expansion: one lane each
 constexpr int LATTICE_GOAL_FLAG = 1 << 30;    // in a successor word: the action reaches the goal region
+constexpr int LATTICE_SHORT_FLAG = 1 << 29;   // in a count word: the expansion used the short-distance primitives
 
 struct LatticeBank
 {
@@ -164,7 +165,8 @@ __global__ void lattice_gen_kernel(const DevModel* __restrict__ M, LatticeBank B
 __device__ __forceinline__ void lattice_commit_warp(const DevModel* __restrict__ M, const GridParams& G, const LatticeBank& B,
                                                     const LatticeParams& L, const LatticeVals& V, const int* __restrict__ bfs,
                                                     int dimx, int dimy, int slot_dimz, int s, int lane, bool valid,
-                                                    const double* q, int* succ_out, int* h_out, int* count_out)
+                                                    const double* q, int* succ_out, int* h_out, int* count_out,
+                                                    bool near_goal)
 {
     const int dof = M->dof;
     int c[MAX_DOF];
@@ -237,7 +239,9 @@ __device__ __forceinline__ void lattice_commit_warp(const DevModel* __restrict__
     }
     full = __any_sync(0xffffffffu, full);
     if (lane == 0) {
-        *count_out = full ? -1 : B.count[s];
+        // which primitive set the successor words belong to travels with the count (the host needs it for the
+        // per-primitive action weights)
+        *count_out = full ? -1 : (B.count[s] | (near_goal ? LATTICE_SHORT_FLAG : 0));
     }
 }
 
@@ -245,7 +249,7 @@ __device__ __forceinline__ void lattice_commit_warp(const DevModel* __restrict__
 __global__ void __launch_bounds__(128)
 lattice_commit_kernel(const DevModel* __restrict__ M, GridParams G, LatticeBank B, LatticeParams L, LatticeVals V,
                       const int* __restrict__ bfs, int dimx, int dimy, int slot_dimz,
-                      const int* __restrict__ slot, int n, const double* __restrict__ q1,
+                      const int* __restrict__ slot, const int* __restrict__ parent, int n, const double* __restrict__ q1,
                       const uint8_t* __restrict__ active, const uint8_t* __restrict__ verdict,
                       int* __restrict__ out_succ, int* __restrict__ out_h, int* __restrict__ out_count,
                       const unsigned long long* __restrict__ stats, unsigned long long* resolved_total)
@@ -257,8 +261,11 @@ lattice_commit_kernel(const DevModel* __restrict__ M, GridParams G, LatticeBank 
     }
     const int t = i * B.stride + lane;
     const bool valid = lane < B.stride && active[t] != 0 && verdict[t] != 0;
+    // mprimActive, as lattice_gen_kernel decided it for this expansion
+    const double goal_dist = (double)B.gdist[(size_t)slot[i] * B.cap + parent[i]] * B.res;
+    const bool near_goal = B.use_short_dist && goal_dist <= B.short_dist_thresh;
     lattice_commit_warp(M, G, B, L, V, bfs, dimx, dimy, slot_dimz, slot[i], lane, valid, q1 + (size_t)t * M->dof,
-                        out_succ + (size_t)i * B.stride, out_h + (size_t)i * B.stride, out_count + i);
+                        out_succ + (size_t)i * B.stride, out_h + (size_t)i * B.stride, out_count + i, near_goal);
     if (i == 0 && lane == 0 && stats[3] != 0) {
         atomicAdd(resolved_total, stats[3]);   // edges of this round that the double-precision pass resolved
     }
@@ -407,8 +414,9 @@ lattice_round_kernel(const float* __restrict__ blob_g, int blob_words, const Dev
         }
         // ---- commit ----
         const bool valid = lane < B.stride && s_active[lane] != 0 && s_ok[lane] != 0;
+        const bool near_goal = B.use_short_dist && (double)B.gdist[(size_t)s * B.cap + p] * B.res <= B.short_dist_thresh;
         lattice_commit_warp(M, G, B, L, V, bfs, dimx, dimy, slot_dimz, s, lane, valid, s_q1[lane < B.stride ? lane : 0],
-                            out_succ + (size_t)i * B.stride, out_h + (size_t)i * B.stride, out_count + i);
+                            out_succ + (size_t)i * B.stride, out_h + (size_t)i * B.stride, out_count + i, near_goal);
     }
 }
 

@@ -3269,7 +3269,7 @@ int smplgpu_lattice_expand_submit(smplgpu_ctx* ctx, const int32_t* slot, const i
     if (r) return r;
     lattice_commit_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(
         ctx->d_model, ctx->grid, B, ctx->lat_params, ctx->lat_vals, ctx->bank.dist, ctx->bank.DX, ctx->bank.DY, ctx->bank_slot_dz,
-        in_slot, n, dq1, dactive, dverdict, out_succ, out_h, out_count, ctx->d_stats, ctx->lat_resolved);
+        in_slot, in_parent, n, dq1, dactive, dverdict, out_succ, out_h, out_count, ctx->d_stats, ctx->lat_resolved);
     ++ctx->launches;
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev_exp[b], ctx->stream));

@@ -56,6 +56,9 @@ BatchPlanner::BatchPlanner(smplgpu_ctx* ctx, const PlannerConfig& cfg, int max_c
             }
             m_prim_short.push_back(cfg.short_flags[p] != 0 ? 1 : 0);
             (cfg.short_flags[p] != 0 ? n_short : n_long) += 1;
+            // cost(parent, succ, actionWeight, goal) = DefaultCostMultiplier * actionWeight, truncated (manip_lattice.cpp:1436)
+            const double w = cfg.prim_weights.empty() ? 1.0 : cfg.prim_weights[p];
+            (cfg.short_flags[p] != 0 ? m_cost_short : m_cost_long).push_back((int)(1000 * w));
         }
     }
     m_stride = std::max(n_long, cfg.use_short_dist ? n_short : 0);
@@ -378,6 +381,11 @@ void BatchPlanner::expandOne(Query& Q)
 // expansion, in primitive order: succ[j] = lattice id | goal flag, or -1 (inactive primitive, joint limit, collision)
 void BatchPlanner::absorbOne(Query& Q, const int32_t* succ, const int32_t* h, int count)
 {
+    // word e stands for the e-th active primitive: of the short-distance set when the device flagged the expansion
+    const std::vector<int>& edge_costs = (count >= 0 && (count & SMPLGPU_LATTICE_SHORT_FLAG)) ? m_cost_short : m_cost_long;
+    if (count >= 0) {
+        count &= ~SMPLGPU_LATTICE_SHORT_FLAG;
+    }
     Q.num_states = count;
     // the search states of the successors are scattered over a megabyte-sized array: start the loads first
     for (int e = 0; e < m_stride; ++e) {
@@ -401,7 +409,7 @@ void BatchPlanner::absorbOne(Query& Q, const int32_t* succ, const int32_t* h, in
         sstate(Q, target);
         touch(Q, target, h[e]);
         SState& ss = Q.search[target];
-        const int new_cost = Q.search[Q.expanding].eg + (int)(1000 * 1.0);   // cost = DefaultCostMultiplier * weight (1)
+        const int new_cost = Q.search[Q.expanding].eg + ((size_t)e < edge_costs.size() ? edge_costs[e] : 1000);
         if ((unsigned int)new_cost < ss.g) {   // int vs unsigned, compared as unsigned (arastar.cpp:545-548)
             ss.g = new_cost;
             ss.bp = Q.expanding;

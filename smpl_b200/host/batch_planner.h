@@ -38,6 +38,9 @@ struct PlannerConfig
     std::vector<double> resolutions;
     std::vector<double> mprims;         // n_prims x dof deltas, file order (converses are added here)
     std::vector<uint8_t> short_flags;   // n_prims
+    // per-primitive action weight (the `weight` column of this fork's primitive files, manip_lattice_action_space.cpp:
+    // 182-190): an edge costs (int)(1000 * weight) (manip_lattice.cpp:1414-1437); empty = 1 for every primitive
+    std::vector<double> prim_weights;   // n_prims, or empty
     bool use_short_dist = true;
     double short_dist_thresh = 0.4;
     double epsilon = 100.0;
@@ -145,6 +148,7 @@ private:
     int m_max_concurrent;
     std::vector<double> m_prim_deltas;     // [n_prims][dof], converses included
     std::vector<uint8_t> m_prim_short;
+    std::vector<int> m_cost_long, m_cost_short;   // edge cost of the j-th active long / short primitive (converses included)
     int m_stride = 0;                      // successor words per expansion
     BatchStats m_stats;
 

@@ -250,6 +250,7 @@ int smplhost_plan_batch(smplgpu_ctx* ctx, const smplhost_plan_params* p, const d
     cfg.resolutions.assign(p->resolutions, p->resolutions + p->dof);
     cfg.mprims.assign(p->mprims, p->mprims + (size_t)p->n_prims * p->dof);
     cfg.short_flags.assign(p->short_flags, p->short_flags + p->n_prims);
+    if (p->prim_weights) cfg.prim_weights.assign(p->prim_weights, p->prim_weights + p->n_prims);
     cfg.use_short_dist = p->use_short_dist != 0;
     cfg.short_dist_thresh = p->short_dist_thresh;
     cfg.epsilon = p->epsilon;

@@ -256,6 +256,7 @@ class PlanParams:
             flags.append(1)
         self.mprims = np.array(prims)
         self.short_flags = np.array(flags, np.uint8)
+        self.weights = None                   # per-primitive action weights (None = 1): edge cost = int(1000 * weight)
         self.use_short_dist = True
         self.short_dist_thresh = 0.4
         self.epsilon = 100.0

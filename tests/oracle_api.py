@@ -547,6 +547,9 @@ class OracleScene:
         summary = np.zeros(8, np.int32)
         path = np.zeros(max_path, np.int32)
         pstates = np.zeros((max_path, len(start)), np.float64)
+        w = getattr(params, "weights", None)
+        w = np.zeros(0) if w is None else np.ascontiguousarray(w, dtype=np.float64)
+        self.L.oracle_set_prim_weights(_dp(w), len(w))
         fn = self.L.oracle_plan_lazy if lazy else self.L.oracle_plan
         secs = fn(self.h, _dp(start), _dp(goal), _dp(res), _dp(prims), _bp(flags), len(prims),
                                   int(params.use_short_dist), C.c_double(params.short_dist_thresh),
@@ -795,6 +798,9 @@ class RefCollisionScene:
         summary = np.zeros(8, np.int32)
         path = np.zeros(max_path, np.int32)
         pstates = np.zeros((max_path, len(start)), np.float64)
+        w = getattr(params, "weights", None)
+        w = np.zeros(0) if w is None else np.ascontiguousarray(w, dtype=np.float64)
+        self.R.refcc_set_prim_weights(_dp(w), len(w))
         fn = self.R.refcc_plan_lazy if lazy else self.R.refcc_plan
         rc = fn(self.h, scene.chain_root.encode(), scene.chain_tip.encode(), scene.planning_link.encode(),
                                _dp(T), _dp(off), C.c_double(scene.inflation_radius), int(scene.cost_per_cell),

@@ -168,6 +168,33 @@ def test_batch_planner_matches_sequential_oracle(tabletop):
         len(ref), n_ok, stats["rounds"], stats["edges_submitted"], stats["device_seconds"], stats["host_seconds"]))
 
 
+def test_batch_planner_with_action_weights_matches_oracle(tabletop):
+    """Edge cost = int(1000 * weight) with the primitive file's weight column (manip_lattice.cpp:296, 1414-1437;
+    manip_lattice_action_space.cpp:182-190): the device tells the host which primitive set an expansion's successor
+    words belong to (SMPLGPU_LATTICE_SHORT_FLAG in the count word), the host looks the weight up.  The oracle with the
+    same weights is pinned against the reference build in tests/test_oracle_planner_reference.py."""
+    scene, o, ctx, tables = tabletop
+    params = scenes.PlanParams(scene.dof)
+    params.max_expansions = 3000
+    params.weights = [(1.0, 2.5, 0.4, 1.7)[i % 4] for i in range(len(params.mprims))]
+    starts, goals = scenes.tabletop_queries(16, seed=13)
+    ref = _run_oracle(o, scene, params, starts, goals)
+    unit = scenes.PlanParams(scene.dof)
+    unit.max_expansions = 3000
+    ref_unit = _run_oracle(o, scene, unit, starts, goals)
+    got, _ = api.plan_batch(ctx, scene, tables, params, starts, goals, max_concurrent=6, n_threads=2)
+    n_ok = 0
+    for i, (a, b) in enumerate(zip(ref, got)):
+        assert (a["success"], a["expansions"], a["cost"], a["num_states"]) == \
+               (b["success"], b["expansions"], b["cost"], b["num_states"]), i
+        assert np.array_equal(a["path_ids"], b["path_ids"]), i
+        n_ok += a["success"]
+    assert n_ok >= 8
+    # the weights matter: costs are no longer multiples of 1000, and some plans change
+    assert any(a["success"] and a["cost"] % 1000 != 0 for a in ref)
+    assert sum(a["expansions"] != u["expansions"] for a, u in zip(ref, ref_unit)) >= 3
+
+
 def test_one_planner_thread_per_context_gives_the_same_plans(tabletop):
     scene, o, ctx, tables = tabletop
     params = scenes.PlanParams(scene.dof)

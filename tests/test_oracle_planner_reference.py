@@ -72,6 +72,34 @@ def test_committed_golden_plans_are_the_reference_builds():
         assert summary(r.plan(scene, np.array(s), np.array(g), params)) == res[:5]
 
 
+def weighted_params(params):
+    """the primitive file's weight column (manip_lattice_action_space.cpp:182-190): edge cost = int(1000 * weight)"""
+    import copy
+    p = copy.copy(params)
+    p.weights = [(1.0, 2.5, 0.4, 1.7)[i % 4] for i in range(len(params.mprims))]
+    return p
+
+
+@needs_ref
+def test_restatement_plans_with_action_weights_equal_reference_build():
+    """cost(parent, succ, actionWeight, goal) = DefaultCostMultiplier * actionWeight, truncated to int
+    (manip_lattice.cpp:296, 1414-1437): non-unit weights change which path ARA* returns; restatement and reference
+    build must agree, and differ from the unit-weight plans."""
+    scene, attach, params, starts, goals = plan_cases()["pr2_tabletop"]
+    wp = weighted_params(params)
+    o = make_restatement(scene, attach, with_kdl=True)
+    r = make_reference(scene, attach)
+    changed = 0
+    for s, g in list(zip(starts, goals))[:5]:
+        o.heur_init(scene.inflation_radius, scene.cost_per_cell)
+        a = o.plan(s, g, wp)
+        b = r.plan(scene, s, g, wp)
+        assert summary(a) == summary(b)
+        o.heur_init(scene.inflation_radius, scene.cost_per_cell)
+        changed += summary(o.plan(s, g, params)) != summary(a)
+    assert changed >= 2
+
+
 @needs_ref
 @pytest.mark.parametrize("name", ["pr2_tabletop", "ubr1_tabletop"])
 def test_lazy_restatement_plans_equal_reference_build(name):
